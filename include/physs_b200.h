@@ -1,0 +1,112 @@
+/* physs_b200.h -- C ABI of libphyss_b200.so: the B200 (sm_100a) state-space inference hot path.
+ *
+ * Drop-in boundary.  The reference (jonathanfrennert/physs_gp, pure Python/JAX) has no FFI; its
+ * operator API for this path is the string-keyed registry in src/lib/stgp/dispatch.py:133-189:
+ *     evoke('filter',   filter_type)  -> filter(data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag,
+ *                                               train_test_mask, train_index)
+ *                                        (computation/filters/kalman_filter.py:439-485, called at :541)
+ *     evoke('smoother', filter_type)  -> smoother(data, model, filter_res, dt, X_t, X_s, full_state)
+ *                                        (computation/filters/rts_smoother.py:162-192, called at :215)
+ * A backend registered as filter_type='b200' evaluates the (tiny, T-independent) prior quantities on
+ * the host and makes ONE call into this library per filter / smoother pass.  Each entry point below
+ * cites the reference function it replaces.  INTEGRATION.md shows the jax.ffi / ctypes stubs.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers to fp64 (C row-major, reference element order) unless noted;
+ *     `stream` is a cudaStream_t passed as void*.  Calls are stream-ordered and never synchronise.
+ *   - The caller owns every buffer; the library allocates nothing user-visible.
+ *   - A leading batch axis B (independent series / spatial blocks / latent functions) is added in
+ *     front of every reference array.  A `*_bstride` argument is the element stride between series
+ *     for that array; 0 means "shared by all series".
+ *   - NaN in Y marks a missing observation (utils/nan_utils.py:13-20).
+ *   - Numerical failure (non-PD Cholesky) writes NaN and still returns 0, as jnp.linalg.cholesky does;
+ *     the reference's NaN guard (trainers/natgrad_trainer.py:257-285) keeps working.
+ *   - Return value: 0 = ok; PHYSS_ERR_* otherwise (bad arguments / unsupported size / CUDA launch
+ *     failure).  No exceptions cross the ABI.
+ *   - jitter values are runtime arguments (settings.py:63-64 are read at trace time in the reference).
+ */
+#ifndef PHYSS_B200_H_
+#define PHYSS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHYSS_OK 0
+#define PHYSS_ERR_BAD_ARG 1
+#define PHYSS_ERR_UNSUPPORTED 2
+#define PHYSS_ERR_CUDA 3
+
+/* Discretisation modes (how A_k = expm(F dt_k) and Q_k reach the kernel). */
+#define PHYSS_DISC_GIVEN 0  /* caller supplies A[.,T,d,d] and Q[.,T,d,d]                                  */
+#define PHYSS_DISC_MATERN 1 /* block-diagonal stack of nblk Matern-(s-1/2) blocks of equal size s=d/nblk, */
+                            /* closed-form expm (kernels/ss_utils.py:6-10, kernels/matern.py:152-177,    */
+                            /* 306-329) from lam[., nblk] = sqrt(2 nu)/lengthscale, Q_k = Pinf - A Pinf A^T */
+                            /* (kernels/kernel.py:207-209) with block-diagonal Pinf[., d, d].             */
+
+/* ABI version (bumped on any signature change). */
+int physs_abi_version(void);
+
+/* Human-readable description of the last non-zero status on this thread. */
+const char* physs_last_error(void);
+
+/* 1 if a kernel specialisation exists for this (d, m, disc_mode, nblk), else 0. */
+int physs_kf_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk);
+
+/* Sequential Kalman filter over B independent series.
+ * Replaces filter('sequential') + kf_predict_step(LTI_SDE) + kf_update_step
+ * (computation/filters/kalman_filter.py:439-485, 214-241, 144-211).
+ *   dt   [., T]      dt[0] = 0, dt[k] = t_k - t_{k-1}  (filter_loop, kalman_filter.py:515)
+ *   m0   [., d]      initial mean   (prior.m_inf)
+ *   P0   [., d, d]   initial covariance (prior.P_inf)
+ *   Pinf [., d, d]   stationary covariance (DISC_MATERN only; may alias P0)
+ *   H    [., m, d]   measurement matrix (prior.H)
+ *   Y    [B, T, m]   observations, NaN = missing
+ *   R    [., ., m, m] observation covariance; R_bstride / R_tstride in elements (0 = broadcast)
+ * Outputs
+ *   mf   [B, T, d], Pf [B, T, d, d]   filtered moments (reference: {'m': [T,d,1], 'P': [T,d,d]})
+ *   lml  [B]                          sum_k lml_k
+ *   lml_k [B, T] or NULL              per-step terms
+ */
+int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int32_t d, int32_t m,
+                        int32_t disc_mode, int32_t nblk,
+                        const double* A, int64_t A_bstride,
+                        const double* Q, int64_t Q_bstride,
+                        const double* lam, int64_t lam_bstride,
+                        const double* dt, int64_t dt_bstride,
+                        const double* Pinf, int64_t Pinf_bstride,
+                        const double* m0, int64_t m0_bstride,
+                        const double* P0, int64_t P0_bstride,
+                        const double* H, int64_t H_bstride,
+                        const double* Y,
+                        const double* R, int64_t R_bstride, int64_t R_tstride,
+                        double jitter,
+                        double* mf, double* Pf, double* lml, double* lml_k);
+
+/* Sequential RTS smoother over B independent series.
+ * Replaces smoother('sequential') + rts_step_wrapper(LTI_SDE) + rts_smoother_step
+ * (computation/filters/rts_smoother.py:162-192, 69-106, 48-65).
+ *   dt   [., T]      dt[k] = t_{k+1} - t_k, dt[T-1] = 0  (smoother_loop, rts_smoother.py:209-211)
+ *   mf, Pf           filtered moments from physs_kf_filter_f64
+ *   Hout [mo, d] or NULL; mo = 0 / NULL means full_state=True (H = I, rts_smoother.py:28-31)
+ * Outputs
+ *   ms [B, T, mo'], Ps [B, T, mo', mo']   with mo' = (mo == 0 ? d : mo)
+ */
+int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int32_t d,
+                         int32_t disc_mode, int32_t nblk,
+                         const double* A, int64_t A_bstride,
+                         const double* Q, int64_t Q_bstride,
+                         const double* lam, int64_t lam_bstride,
+                         const double* dt, int64_t dt_bstride,
+                         const double* Pinf, int64_t Pinf_bstride,
+                         const double* mf, const double* Pf,
+                         const double* Hout, int32_t mo,
+                         double jitter,
+                         double* ms, double* Ps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYSS_B200_H_ */

@@ -1,0 +1,267 @@
+"""Oracle: LTI-SDE prior API and discretisation (numpy restatement, test infrastructure).
+
+Follows (paths relative to /root/reference/src/lib/stgp/):
+  kernels/ss_utils.py:6-53        Matern-3/2 expm + state-space rep, space-time kron rep
+  kernels/matern.py:109-177       Matern-5/2 rep + closed-form expm
+  kernels/matern.py:269-329       Matern-7/2 rep + closed-form expm
+  kernels/kernel.py:134-160       SumKernel block-diagonal stacking
+  kernels/kernel.py:207-209       Q_k = Pinf - A_k Pinf A_k^T   (stationary)
+  kernels/kernel.py:213-265       SpatioTemporalSeperableKernel (A = I kron A_t, Pinf = K_s kron Pinf_t)
+  transforms/transform.py:400-545 Independent: block-diagonal stacking of latents
+  transforms/sdes.py:55-172       LTI_SDE / LTI_SDE_Full_State_Obs prior API (m_inf, P_inf, H, expm, Q)
+"""
+import numpy as np
+import scipy.linalg as sla
+
+
+def block_diag(blocks):
+    return sla.block_diag(*blocks)
+
+
+class Matern32:
+    """kernels/ss_utils.py:6-38, kernels/matern.py:53-80 (unit variance) / :13-38 (scaled)."""
+    state_dim = 2
+
+    def __init__(self, lengthscale, variance=1.0):
+        self.ls = float(lengthscale)
+        self.var = float(variance)
+
+    def to_ss(self):
+        ls, var = self.ls, self.var
+        lam = 3.0 ** 0.5 / ls
+        F = np.array([[0.0, 1.0], [-(lam ** 2), -2 * lam]])
+        L = np.array([[0.0], [1.0]])
+        H = np.array([[1.0, 0.0]])
+        Qc = np.array([[12.0 * 3.0 ** 0.5 / ls ** 3.0 * var]])
+        minf = np.zeros([2, 1])
+        Pinf = np.array([[var, 0.0], [0.0, 3.0 * var / ls ** 2.0]])
+        return F, L, Qc, H, minf, Pinf
+
+    def expm(self, dt):
+        lam = np.sqrt(3.0) / self.ls
+        return np.exp(-dt * lam) * (dt * np.array([[lam, 1.0], [-lam ** 2.0, -lam]]) + np.eye(2))
+
+    def K(self, x1, x2):
+        """kernels/matern.py:82-90"""
+        r = np.abs(x1[:, None] - x2[None, :]) / self.ls
+        s3 = np.sqrt(3.0)
+        return self.var * (1.0 + s3 * r) * np.exp(-s3 * r)
+
+
+class Matern52:
+    """kernels/matern.py:109-188 (and the Scaled variant :191-266)."""
+    state_dim = 3
+
+    def __init__(self, lengthscale, variance=1.0):
+        self.ls = float(lengthscale)
+        self.var = float(variance)
+
+    def to_ss(self):
+        ls, var = self.ls, self.var
+        lam = 5.0 ** 0.5 / ls
+        F = np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0],
+                      [-(lam ** 3.0), -3.0 * lam ** 2.0, -3.0 * lam]])
+        L = np.array([[0.0], [0.0], [1.0]])
+        Qc = np.array([[var * 400.0 * 5.0 ** 0.5 / 3.0 / ls ** 5.0]])
+        H = np.array([[1.0, 0.0, 0.0]])
+        kappa = 5.0 / 3.0 * var / ls ** 2.0
+        minf = np.zeros([3, 1])
+        Pinf = np.array([[var, 0.0, -kappa], [0.0, kappa, 0.0],
+                         [-kappa, 0.0, 25.0 * var / ls ** 4.0]])
+        return F, L, Qc, H, minf, Pinf
+
+    def expm(self, dt):
+        lam = np.sqrt(5.0) / self.ls
+        dtlam = dt * lam
+        M = np.array([
+            [lam * (0.5 * dtlam + 1.0), dtlam + 1.0, 0.5 * dt],
+            [-0.5 * dtlam * lam ** 2, lam * (1.0 - dtlam), 1.0 - 0.5 * dtlam],
+            [lam ** 3 * (0.5 * dtlam - 1.0), lam ** 2 * (dtlam - 3), lam * (0.5 * dtlam - 2.0)],
+        ])
+        return np.exp(-dtlam) * (dt * M + np.eye(3))
+
+    def K(self, x1, x2):
+        r = np.abs(x1[:, None] - x2[None, :]) / self.ls
+        s5 = np.sqrt(5.0)
+        return self.var * (1.0 + s5 * r + (5.0 / 3.0) * r * r) * np.exp(-s5 * r)
+
+
+class Matern72:
+    """kernels/matern.py:269-341 (ScaledMatern72)."""
+    state_dim = 4
+
+    def __init__(self, lengthscale, variance=1.0):
+        self.ls = float(lengthscale)
+        self.var = float(variance)
+
+    def to_ss(self):
+        ls, var = self.ls, self.var
+        lam = 7.0 ** 0.5 / ls
+        F = np.array([[0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0],
+                      [-lam ** 4.0, -4.0 * lam ** 3.0, -6.0 * lam ** 2.0, -4.0 * lam]])
+        L = np.array([[0.0], [0.0], [0.0], [1.0]])
+        Qc = np.array([[var * 10976.0 * 7.0 ** 0.5 / 5.0 / ls ** 7.0]])
+        H = np.array([[1.0, 0.0, 0.0, 0.0]])
+        kappa = 7.0 / 5.0 * var / ls ** 2.0
+        kappa2 = 9.8 * var / ls ** 4.0
+        minf = np.zeros([4, 1])
+        Pinf = np.array([[var, 0.0, -kappa, 0.0], [0.0, kappa, 0.0, -kappa2],
+                         [-kappa, 0.0, kappa2, 0.0], [0.0, -kappa2, 0.0, 343.0 * var / ls ** 6.0]])
+        return F, L, Qc, H, minf, Pinf
+
+    def expm(self, dt):
+        lam = np.sqrt(7.0) / self.ls
+        lam2 = lam * lam
+        lam3 = lam2 * lam
+        dtlam = dt * lam
+        dtlam2 = dtlam ** 2
+        M = np.array([
+            [lam * (1.0 + 0.5 * dtlam + dtlam2 / 6.0), 1.0 + dtlam + 0.5 * dtlam2,
+             0.5 * dt * (1.0 + dtlam), dt ** 2 / 6],
+            [-dtlam2 * lam ** 2.0 / 6.0, lam * (1.0 + 0.5 * dtlam - 0.5 * dtlam2),
+             1.0 + dtlam - 0.5 * dtlam2, dt * (0.5 - dtlam / 6.0)],
+            [lam3 * dtlam * (dtlam / 6.0 - 0.5), dtlam * lam2 * (0.5 * dtlam - 2.0),
+             lam * (1.0 - 2.5 * dtlam + 0.5 * dtlam2), 1.0 - dtlam + dtlam2 / 6.0],
+            [lam2 ** 2 * (dtlam - 1.0 - dtlam2 / 6.0), lam3 * (3.5 * dtlam - 4.0 - 0.5 * dtlam2),
+             lam2 * (4.0 * dtlam - 6.0 - 0.5 * dtlam2), lam * (1.5 * dtlam - 3.0 - dtlam2 / 6.0)],
+        ])
+        return np.exp(-dtlam) * (dt * M + np.eye(4))
+
+    def K(self, x1, x2):
+        r = np.abs(x1[:, None] - x2[None, :]) / self.ls
+        s7 = np.sqrt(7.0)
+        return self.var * (1. + s7 * r + 14. / 5. * r ** 2 + 7. * s7 / 15. * r ** 3) * np.exp(-s7 * r)
+
+
+class GenericLTI:
+    """A stationary LTI SDE given by (F, H, Pinf) with A = scipy expm(F dt) -- the role played in
+    the reference by kernels that call jax.scipy.linalg.expm (kernels/periodic.py:250-253)."""
+
+    def __init__(self, F, H, Pinf, minf=None):
+        self.F = np.asarray(F, float)
+        self.H = np.asarray(H, float)
+        self.Pinf = np.asarray(Pinf, float)
+        self.state_dim = self.F.shape[0]
+        self.minf = np.zeros([self.state_dim, 1]) if minf is None else np.asarray(minf, float).reshape(-1, 1)
+
+    def to_ss(self):
+        d = self.state_dim
+        return self.F, np.zeros([d, 1]), np.zeros([1, 1]), self.H, self.minf, self.Pinf
+
+    def expm(self, dt):
+        return sla.expm(self.F * dt)
+
+
+class SumKernel:
+    """kernels/kernel.py:134-160: block-diagonal F/Pinf/expm, hstacked H."""
+
+    def __init__(self, parts):
+        self.parts = list(parts)
+        self.state_dim = sum(p.state_dim for p in self.parts)
+
+    def to_ss(self):
+        reps = [p.to_ss() for p in self.parts]
+        F = block_diag([r[0] for r in reps])
+        L = block_diag([r[1] for r in reps])
+        Qc = block_diag([r[2] for r in reps])
+        H = np.hstack([r[3] for r in reps])
+        minf = np.vstack([r[4] for r in reps])
+        Pinf = block_diag([r[5] for r in reps])
+        return F, L, Qc, H, minf, Pinf
+
+    def expm(self, dt):
+        return block_diag([p.expm(dt) for p in self.parts])
+
+    def K(self, x1, x2):
+        return sum(p.K(x1, x2) for p in self.parts)
+
+
+class SpaceTimeSeparable:
+    """kernels/kernel.py:213-265 + kernels/ss_utils.py:41-53.
+
+    K_spatial is passed in already evaluated (the spatial kernel itself is outside the hot path,
+    SURVEY.md section 2 row 14)."""
+
+    def __init__(self, temporal, K_spatial):
+        self.kt = temporal
+        self.Ks = np.asarray(K_spatial, float)
+        self.Ns = self.Ks.shape[0]
+        self.state_dim = self.kt.state_dim * self.Ns
+
+    def to_ss(self):
+        F, L, Qc, H, minf, Pinf = self.kt.to_ss()
+        eye = np.eye(self.Ns)
+        return (np.kron(eye, F), np.kron(eye, L), np.kron(self.Ks, Qc), np.kron(eye, H),
+                np.kron(np.ones([self.Ns, 1]), minf), np.kron(self.Ks, Pinf))
+
+    def expm(self, dt):
+        return np.kron(np.eye(self.Ns), self.kt.expm(dt))
+
+
+class LTI_SDE:
+    """transforms/sdes.py:18-97 over transforms/transform.py:400-545 (`Independent` of Q latents).
+
+    `latents` is a list of kernels; the joint state stacks them block-diagonally
+    (time-latent-space-state ordering, computation/filters/kalman_filter.py:4-14)."""
+
+    def __init__(self, latents, m_init=None):
+        self.latents = list(latents)
+        self.m_init = None if m_init is None else np.asarray(m_init, float).reshape(-1, 1)
+        self.state_dim = sum(k.state_dim for k in self.latents)
+
+    def state_space_representation(self):
+        reps = [k.to_ss() for k in self.latents]
+        F = block_diag([r[0] for r in reps])
+        L = block_diag([r[1] for r in reps])
+        Qc = block_diag([r[2] for r in reps])
+        H = block_diag([r[3] for r in reps])
+        minf = np.vstack([r[4] for r in reps])
+        Pinf = block_diag([r[5] for r in reps])
+        return F, L, Qc, H, minf, Pinf
+
+    def m_inf(self):
+        if self.m_init is not None:
+            return self.m_init
+        return self.state_space_representation()[4]
+
+    def P_inf(self):
+        return self.state_space_representation()[5]
+
+    def H(self):
+        return self.state_space_representation()[3]
+
+    def expm(self, dt):
+        return block_diag([k.expm(dt) for k in self.latents])
+
+    def Q(self, dt, A, Pinf):
+        # kernel.py:207-209 applied per latent block then re-stacked (transform.py:499-545);
+        # with block-diagonal A and Pinf that equals the dense expression below.
+        return Pinf - A @ Pinf @ A.T
+
+
+class LTI_SDE_Full_State_Obs(LTI_SDE):
+    """transforms/sdes.py:99-172 with overwrite_H=True, Ns=1, ds=1: H observes every state
+    component of every latent (identity up to the latent-df ordering, which for Ns=ds=1 is the
+    identity permutation), optionally only `keep_dims` of each latent (sdes.py:174-190)."""
+
+    def __init__(self, latents, keep_dims=None):
+        super().__init__(latents)
+        self.keep_dims = keep_dims
+
+    def H(self):
+        rows = []
+        off = 0
+        for k in self.latents:
+            d = k.state_dim
+            keep = range(d) if self.keep_dims is None else self.keep_dims
+            for j in keep:
+                e = np.zeros(self.state_dim)
+                e[off + j] = 1.0
+                rows.append(e)
+            off += d
+        return np.array(rows)
+
+
+def lyapunov_residual(F, L, Qc, Pinf):
+    """F Pinf + Pinf F^T + L Qc L^T  (zero for a correct stationary covariance; SURVEY 8c pin iii)."""
+    return F @ Pinf + Pinf @ F.T + L @ Qc @ L.T

@@ -1,0 +1,70 @@
+"""ctypes binding of libphyss_b200.so (the C ABI declared in include/physs_b200.h).
+
+There is deliberately NO fallback: if the CUDA library has not been built, importing the compute
+entry points raises.  Build it with `python -m physs_gp_b200.build` (or `__graft_entry__.build()`).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libphyss_b200.so")
+
+PHYSS_OK = 0
+DISC_GIVEN = 0
+DISC_MATERN = 1
+ABI_VERSION = 1
+
+_c_i32 = ctypes.c_int32
+_c_i64 = ctypes.c_int64
+_c_f64 = ctypes.c_double
+_ptr = ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/physs_b200.h declares.
+SIGNATURES = {
+    "physs_abi_version": (ctypes.c_int, []),
+    "physs_last_error": (ctypes.c_char_p, []),
+    "physs_kf_supported": (ctypes.c_int, [_c_i32, _c_i32, _c_i32, _c_i32]),
+    "physs_kf_filter_f64": (ctypes.c_int, [
+        _ptr, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32,
+        _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
+        _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
+        _ptr, _ptr, _c_i64, _c_i64, _c_f64,
+        _ptr, _ptr, _ptr, _ptr]),
+    "physs_rts_smooth_f64": (ctypes.c_int, [
+        _ptr, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32,
+        _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
+        _ptr, _ptr, _ptr, _c_i32, _c_f64, _ptr, _ptr]),
+}
+
+_lib = None
+
+
+class PhyssError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and attach signatures.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "physs_gp_b200: %s not found -- the CUDA library is not built. Run "
+            "`python -m physs_gp_b200.build`. There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.physs_abi_version()
+    if v != ABI_VERSION:
+        raise ImportError("physs_gp_b200: ABI version mismatch (lib %d, binding %d); rebuild" % (v, ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != PHYSS_OK:
+        msg = load().physs_last_error()
+        raise PhyssError("%s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))

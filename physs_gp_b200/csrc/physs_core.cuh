@@ -1,0 +1,486 @@
+// physs_core.cuh -- register-resident per-series state-space algebra (fp64).
+//
+// Everything here is PHYSS_HD (__host__ __device__) and templated on compile-time sizes so that
+//  (a) on the GPU every small matrix lives in registers, fully unrolled (one thread = one series);
+//  (b) the identical source compiles with g++ for the CPU-side logic check in tests/ (there is no
+//      GPU in the build container) -- that host build is a TEST of this file, not a product path.
+//
+// Reference semantics being reproduced (paths relative to /root/reference/src/lib/stgp/):
+//   computation/filters/kalman_filter.py:144-241   predict + masked update + lml
+//   computation/filters/rts_smoother.py:48-106     RTS step with jittered chol(P_pred)
+//   computation/linalg.py:12-33                    solve() = chol(S + jitter I) solve
+//   computation/gaussian.py:42-108                 log N with mask-to-identity, un-jittered chol
+//   kernels/ss_utils.py:6-10, kernels/matern.py:152-177,306-329   closed-form expm(F dt)
+//   kernels/kernel.py:207-209                      Q = Pinf - A Pinf A^T
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define PHYSS_HD __host__ __device__ __forceinline__
+#define PHYSS_UNROLL _Pragma("unroll")
+#else
+#define PHYSS_HD inline
+#define PHYSS_UNROLL
+#endif
+
+namespace physs {
+
+constexpr double kLog2Pi = 1.8378770664093454835606594728112;
+
+// ---------------------------------------------------------------------------------------------
+// Closed-form A = expm(F dt) for Matern-(S-1/2) state-space blocks, S = 1..4.
+// lam = sqrt(2 nu) / lengthscale.  S=2: ss_utils.py:6-10; S=3: matern.py:152-177; S=4: matern.py:306-329.
+// ---------------------------------------------------------------------------------------------
+template <int S>
+struct MaternExpm;
+
+template <>
+struct MaternExpm<1> {
+  static PHYSS_HD void eval(double lam, double dt, double (&A)[1][1]) { A[0][0] = exp(-lam * dt); }
+};
+
+template <>
+struct MaternExpm<2> {
+  static PHYSS_HD void eval(double lam, double dt, double (&A)[2][2]) {
+    const double e = exp(-dt * lam);
+    A[0][0] = e * (dt * lam + 1.0);
+    A[0][1] = e * dt;
+    A[1][0] = e * (dt * (-lam * lam));
+    A[1][1] = e * (dt * (-lam) + 1.0);
+  }
+};
+
+template <>
+struct MaternExpm<3> {
+  static PHYSS_HD void eval(double lam, double dt, double (&A)[3][3]) {
+    const double x = dt * lam;  // dtlam
+    const double e = exp(-x);
+    const double l2 = lam * lam;
+    A[0][0] = e * (dt * (lam * (0.5 * x + 1.0)) + 1.0);
+    A[0][1] = e * (dt * (x + 1.0));
+    A[0][2] = e * (dt * (0.5 * dt));
+    A[1][0] = e * (dt * (-0.5 * x * l2));
+    A[1][1] = e * (dt * (lam * (1.0 - x)) + 1.0);
+    A[1][2] = e * (dt * (1.0 - 0.5 * x));
+    A[2][0] = e * (dt * (l2 * lam * (0.5 * x - 1.0)));
+    A[2][1] = e * (dt * (l2 * (x - 3.0)));
+    A[2][2] = e * (dt * (lam * (0.5 * x - 2.0)) + 1.0);
+  }
+};
+
+template <>
+struct MaternExpm<4> {
+  static PHYSS_HD void eval(double lam, double dt, double (&A)[4][4]) {
+    const double x = dt * lam;
+    const double x2 = x * x;
+    const double e = exp(-x);
+    const double l2 = lam * lam;
+    const double l3 = l2 * lam;
+    A[0][0] = e * (dt * (lam * (1.0 + 0.5 * x + x2 / 6.0)) + 1.0);
+    A[0][1] = e * (dt * (1.0 + x + 0.5 * x2));
+    A[0][2] = e * (dt * (0.5 * dt * (1.0 + x)));
+    A[0][3] = e * (dt * (dt * dt / 6.0));
+    A[1][0] = e * (dt * (-x2 * l2 / 6.0));
+    A[1][1] = e * (dt * (lam * (1.0 + 0.5 * x - 0.5 * x2)) + 1.0);
+    A[1][2] = e * (dt * (1.0 + x - 0.5 * x2));
+    A[1][3] = e * (dt * (dt * (0.5 - x / 6.0)));
+    A[2][0] = e * (dt * (l3 * x * (x / 6.0 - 0.5)));
+    A[2][1] = e * (dt * (x * l2 * (0.5 * x - 2.0)));
+    A[2][2] = e * (dt * (lam * (1.0 - 2.5 * x + 0.5 * x2)) + 1.0);
+    A[2][3] = e * (dt * (1.0 - x + x2 / 6.0));
+    A[3][0] = e * (dt * (l2 * l2 * (x - 1.0 - x2 / 6.0)));
+    A[3][1] = e * (dt * (l3 * (3.5 * x - 4.0 - 0.5 * x2)));
+    A[3][2] = e * (dt * (l2 * (4.0 * x - 6.0 - 0.5 * x2)));
+    A[3][3] = e * (dt * (lam * (1.5 * x - 3.0 - x2 / 6.0)) + 1.0);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Block-diagonal transition: D = NB * S, block b is an S x S dense matrix.  S == D is a plain dense
+// transition (also used when A_k is supplied by the caller).
+// ---------------------------------------------------------------------------------------------
+template <int D, int S>
+struct Trans {
+  static constexpr int NB = D / S;
+  double a[NB][S][S];
+
+  // y = A x
+  PHYSS_HD void mulv(const double (&x)[D], double (&y)[D]) const {
+    PHYSS_UNROLL
+    for (int b = 0; b < NB; ++b) {
+      PHYSS_UNROLL
+      for (int i = 0; i < S; ++i) {
+        double acc = 0.0;
+        PHYSS_UNROLL
+        for (int k = 0; k < S; ++k) acc = fma(a[b][i][k], x[b * S + k], acc);
+        y[b * S + i] = acc;
+      }
+    }
+  }
+  // C = A X   (X, C dense D x D)
+  PHYSS_HD void mulL(const double (&X)[D][D], double (&C)[D][D]) const {
+    PHYSS_UNROLL
+    for (int b = 0; b < NB; ++b) {
+      PHYSS_UNROLL
+      for (int i = 0; i < S; ++i) {
+        PHYSS_UNROLL
+        for (int j = 0; j < D; ++j) {
+          double acc = 0.0;
+          PHYSS_UNROLL
+          for (int k = 0; k < S; ++k) acc = fma(a[b][i][k], X[b * S + k][j], acc);
+          C[b * S + i][j] = acc;
+        }
+      }
+    }
+  }
+  // Out = Add + C A^T, only the upper triangle is computed and mirrored (result is symmetric by
+  // construction: C = A X with X symmetric).
+  PHYSS_HD void mulRT_sym_add(const double (&C)[D][D], const double (&Add)[D][D],
+                              double (&Out)[D][D]) const {
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      PHYSS_UNROLL
+      for (int j = i; j < D; ++j) {
+        const int b = j / S, jj = j % S;
+        double acc = Add[i][j];
+        PHYSS_UNROLL
+        for (int k = 0; k < S; ++k) acc = fma(C[i][b * S + k], a[b][jj][k], acc);
+        Out[i][j] = acc;
+        Out[j][i] = acc;
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Small dense Cholesky / triangular solves (lower), in registers.  Non-PD input -> NaN (sqrt of a
+// negative number), which then propagates exactly as jnp.linalg.cholesky's NaNs do.
+// ---------------------------------------------------------------------------------------------
+template <int N>
+PHYSS_HD void chol_lower(const double (&A)[N][N], double (&L)[N][N], double (&rdiag)[N]) {
+  PHYSS_UNROLL
+  for (int j = 0; j < N; ++j) {
+    double s = A[j][j];
+    PHYSS_UNROLL
+    for (int k = 0; k < j; ++k) s = fma(-L[j][k], L[j][k], s);
+    const double ljj = sqrt(s);
+    const double r = 1.0 / ljj;
+    L[j][j] = ljj;
+    rdiag[j] = r;
+    PHYSS_UNROLL
+    for (int i = j + 1; i < N; ++i) {
+      double t = A[i][j];
+      PHYSS_UNROLL
+      for (int k = 0; k < j; ++k) t = fma(-L[i][k], L[j][k], t);
+      L[i][j] = t * r;
+    }
+  }
+}
+
+// Solve (L L^T) x = b in place for one right-hand side.
+template <int N>
+PHYSS_HD void chol_solve_vec(const double (&L)[N][N], const double (&rdiag)[N], double (&x)[N]) {
+  PHYSS_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double t = x[i];
+    PHYSS_UNROLL
+    for (int k = 0; k < i; ++k) t = fma(-L[i][k], x[k], t);
+    x[i] = t * rdiag[i];
+  }
+  PHYSS_UNROLL
+  for (int i = N - 1; i >= 0; --i) {
+    double t = x[i];
+    PHYSS_UNROLL
+    for (int k = i + 1; k < N; ++k) t = fma(-L[k][i], x[k], t);
+    x[i] = t * rdiag[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kalman update (kalman_filter.py:144-211) for a D-state, M-observation step.
+//   HID: H is the identity (full-state pseudo-observations, M == D) -- skips the H products.
+// y may contain NaN (= missing).  Returns this step's log marginal likelihood term.
+// ---------------------------------------------------------------------------------------------
+template <int D, int M, bool HID>
+PHYSS_HD double kf_update(double (&m)[D], double (&P)[D][D], const double (&H)[M][D],
+                          const double (&R)[M][M], const double (&y)[M], double jitter) {
+  // mask
+  bool obs[M];
+  int n_missing = 0;
+  PHYSS_UNROLL
+  for (int a = 0; a < M; ++a) {
+    obs[a] = !(y[a] != y[a]);
+    n_missing += obs[a] ? 0 : 1;
+  }
+  // HP = M H P_  (rows of missing observations zeroed), innovation
+  double HP[M][D];
+  double v[M];
+  PHYSS_UNROLL
+  for (int a = 0; a < M; ++a) {
+    double mu = 0.0;
+    PHYSS_UNROLL
+    for (int j = 0; j < D; ++j) {
+      double acc;
+      if (HID) {
+        acc = P[a][j];
+      } else {
+        acc = 0.0;
+        PHYSS_UNROLL
+        for (int k = 0; k < D; ++k) acc = fma(H[a][k], P[k][j], acc);
+      }
+      HP[a][j] = obs[a] ? acc : 0.0;
+    }
+    if (HID) {
+      mu = m[a];
+    } else {
+      PHYSS_UNROLL
+      for (int k = 0; k < D; ++k) mu = fma(H[a][k], m[k], mu);
+    }
+    v[a] = obs[a] ? (y[a] - mu) : 0.0;
+  }
+  // S = M H P_ H^T M + R     (R is not masked)
+  double S[M][M];
+  PHYSS_UNROLL
+  for (int a = 0; a < M; ++a) {
+    PHYSS_UNROLL
+    for (int b = a; b < M; ++b) {
+      double acc;
+      if (HID) {
+        acc = HP[a][b];
+      } else {
+        acc = 0.0;
+        PHYSS_UNROLL
+        for (int k = 0; k < D; ++k) acc = fma(HP[a][k], H[b][k], acc);
+      }
+      acc = obs[b] ? acc : 0.0;
+      S[a][b] = acc + R[a][b];
+      S[b][a] = acc + R[b][a];
+    }
+  }
+  double lml;
+  if (M == 1) {
+    // scalar fast path
+    const double Sj = S[0][0] + jitter;
+    const double rSj = 1.0 / Sj;
+    double K[D];
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) K[i] = HP[0][i] * rSj;
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) m[i] = fma(K[i], v[0], m[i]);
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      const double ks = K[i] * S[0][0];
+      PHYSS_UNROLL
+      for (int j = i; j < D; ++j) {
+        const double pij = fma(-ks, K[j], P[i][j]);
+        P[i][j] = pij;
+        P[j][i] = pij;
+      }
+    }
+    // masked step: mask_to_identity(S) = 1, v = 0  ->  lml_k = 0
+    const double Sl = obs[0] ? S[0][0] : 1.0;
+    lml = -0.5 * (log(Sl) + v[0] * v[0] / Sl) - (obs[0] ? 0.5 * kLog2Pi : 0.0);
+  } else {
+    // K^T = (S + jitter I)^{-1} (M H P_)
+    double Sj[M][M];
+    PHYSS_UNROLL
+    for (int a = 0; a < M; ++a) {
+      PHYSS_UNROLL
+      for (int b = 0; b < M; ++b) Sj[a][b] = S[a][b] + (a == b ? jitter : 0.0);
+    }
+    double L[M][M], rd[M];
+    chol_lower<M>(Sj, L, rd);
+    double Kt[M][D];  // Kt[a][i] = K[i][a]
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      double x[M];
+      PHYSS_UNROLL
+      for (int a = 0; a < M; ++a) x[a] = HP[a][i];
+      chol_solve_vec<M>(L, rd, x);
+      PHYSS_UNROLL
+      for (int a = 0; a < M; ++a) Kt[a][i] = x[a];
+    }
+    // m += K v
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      double acc = m[i];
+      PHYSS_UNROLL
+      for (int a = 0; a < M; ++a) acc = fma(Kt[a][i], v[a], acc);
+      m[i] = acc;
+    }
+    // P -= K S K^T   (un-jittered S)
+    double KS[D][M];
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      PHYSS_UNROLL
+      for (int b = 0; b < M; ++b) {
+        double acc = 0.0;
+        PHYSS_UNROLL
+        for (int a = 0; a < M; ++a) acc = fma(Kt[a][i], S[a][b], acc);
+        KS[i][b] = acc;
+      }
+    }
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      PHYSS_UNROLL
+      for (int j = i; j < D; ++j) {
+        double acc = P[i][j];
+        PHYSS_UNROLL
+        for (int b = 0; b < M; ++b) acc = fma(-KS[i][b], Kt[b][j], acc);
+        P[i][j] = acc;
+        P[j][i] = acc;
+      }
+    }
+    // lml: Cholesky of the UN-jittered S with missing rows/cols replaced by identity.
+    double Sm[M][M];
+    PHYSS_UNROLL
+    for (int a = 0; a < M; ++a) {
+      PHYSS_UNROLL
+      for (int b = 0; b < M; ++b) {
+        const bool keep = obs[a] && obs[b];
+        Sm[a][b] = keep ? S[a][b] : (a == b ? 1.0 : 0.0);
+      }
+    }
+    double L2[M][M], rd2[M];
+    chol_lower<M>(Sm, L2, rd2);
+    double logdet = 0.0;
+    PHYSS_UNROLL
+    for (int a = 0; a < M; ++a) logdet += log(L2[a][a] * L2[a][a]);
+    double w[M];
+    PHYSS_UNROLL
+    for (int a = 0; a < M; ++a) w[a] = v[a];
+    chol_solve_vec<M>(L2, rd2, w);
+    double mahal = 0.0;
+    PHYSS_UNROLL
+    for (int a = 0; a < M; ++a) mahal = fma(v[a], w[a], mahal);
+    lml = -0.5 * (M - n_missing) * kLog2Pi - 0.5 * logdet - 0.5 * mahal;
+  }
+  return lml;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Predict step.  Two equivalent forms:
+//   given-Q   : P_ = A P A^T + Q                       (kalman_filter.py:234-235 verbatim)
+//   stationary: P_ = Pinf + A (P - Pinf) A^T           (= A P A^T + (Pinf - A Pinf A^T), kernel.py:207-209,
+//               re-associated so that Q_k never has to be formed; differs by O(eps |Pinf|))
+// ---------------------------------------------------------------------------------------------
+template <int D, int S>
+PHYSS_HD void kf_predict_givenQ(const Trans<D, S>& A, const double (&Q)[D][D], double (&m)[D],
+                                double (&P)[D][D]) {
+  double m_[D];
+  A.mulv(m, m_);
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) m[i] = m_[i];
+  double C[D][D];
+  A.mulL(P, C);
+  A.mulRT_sym_add(C, Q, P);
+}
+
+template <int D, int S>
+PHYSS_HD void kf_predict_stationary(const Trans<D, S>& A, const double (&Pinf)[D][D],
+                                    double (&m)[D], double (&P)[D][D]) {
+  double m_[D];
+  A.mulv(m, m_);
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) m[i] = m_[i];
+  double dP[D][D];
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    PHYSS_UNROLL
+    for (int j = 0; j < D; ++j) dP[i][j] = P[i][j] - Pinf[i][j];
+  }
+  double C[D][D];
+  A.mulL(dP, C);
+  A.mulRT_sym_add(C, Pinf, P);
+}
+
+// ---------------------------------------------------------------------------------------------
+// RTS step (rts_smoother.py:48-106).  On entry (ms, Ps) is the smoothed state at k+1, (mf, Pf) the
+// filtered state at k; on exit (ms, Ps) is the smoothed state at k.
+//   Qadd: the matrix added to A Pf A^T, i.e. Q_k (given) -- for the stationary form pass
+//         stationary = true and Qadd = Pinf, which evaluates Pinf + (A Pf - A Pinf) A^T.
+// ---------------------------------------------------------------------------------------------
+template <int D, int S>
+PHYSS_HD void rts_step(const Trans<D, S>& A, const double (&Qadd)[D][D], bool stationary,
+                       const double (&mf)[D], const double (&Pf)[D][D], double jitter,
+                       double (&ms)[D], double (&Ps)[D][D]) {
+  double mp[D];
+  A.mulv(mf, mp);
+  double C[D][D];  // A Pf
+  A.mulL(Pf, C);
+  double Pp[D][D];
+  if (stationary) {
+    double E[D][D];
+    A.mulL(Qadd, E);  // A Pinf
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      PHYSS_UNROLL
+      for (int j = 0; j < D; ++j) E[i][j] = C[i][j] - E[i][j];
+    }
+    A.mulRT_sym_add(E, Qadd, Pp);
+  } else {
+    A.mulRT_sym_add(C, Qadd, Pp);
+  }
+  // chol(Pp + jitter I)
+  double Pj[D][D];
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    PHYSS_UNROLL
+    for (int j = 0; j < D; ++j) Pj[i][j] = Pp[i][j] + (i == j ? jitter : 0.0);
+  }
+  double L[D][D], rd[D];
+  chol_lower<D>(Pj, L, rd);
+  // G^T = (Pp + jit)^{-1} (A Pf)  -> column j of X solves for row j of G
+  double G[D][D];
+  PHYSS_UNROLL
+  for (int j = 0; j < D; ++j) {
+    double x[D];
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) x[i] = C[i][j];
+    chol_solve_vec<D>(L, rd, x);
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) G[j][i] = x[i];
+  }
+  // m = mf + G (ms - mp)
+  double dm[D];
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) dm[i] = ms[i] - mp[i];
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    double acc = mf[i];
+    PHYSS_UNROLL
+    for (int k = 0; k < D; ++k) acc = fma(G[i][k], dm[k], acc);
+    ms[i] = acc;
+  }
+  // P = Pf + G (Ps - Pp) G^T
+  double dP[D][D];
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    PHYSS_UNROLL
+    for (int j = 0; j < D; ++j) dP[i][j] = Ps[i][j] - Pp[i][j];
+  }
+  double W[D][D];
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    PHYSS_UNROLL
+    for (int j = 0; j < D; ++j) {
+      double acc = 0.0;
+      PHYSS_UNROLL
+      for (int k = 0; k < D; ++k) acc = fma(G[i][k], dP[k][j], acc);
+      W[i][j] = acc;
+    }
+  }
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    PHYSS_UNROLL
+    for (int j = i; j < D; ++j) {
+      double acc = Pf[i][j];
+      PHYSS_UNROLL
+      for (int k = 0; k < D; ++k) acc = fma(W[i][k], G[j][k], acc);
+      Ps[i][j] = acc;
+      Ps[j][i] = acc;
+    }
+  }
+}
+
+}  // namespace physs

@@ -1,0 +1,83 @@
+// physs_seq.cu -- size dispatch for the register-resident sequential filter / smoother
+// (one thread per series, state dim d <= 4).  The kernels live in physs_seq_impl.cuh and are
+// instantiated one (d, block size, discretisation) triple per translation unit (physs_seq_d*.cu) so
+// that the library builds in parallel.
+#include "physs_internal.h"
+
+namespace physs {
+
+int seq_filter_d1s1m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d1s1m(cudaStream_t st, const SeqSmoothArgs& a, int mo);
+int seq_filter_d1s1g(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d1s1g(cudaStream_t st, const SeqSmoothArgs& a, int mo);
+int seq_filter_d2s1m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d2s1m(cudaStream_t st, const SeqSmoothArgs& a, int mo);
+int seq_filter_d2s2m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d2s2m(cudaStream_t st, const SeqSmoothArgs& a, int mo);
+int seq_filter_d2s2g(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d2s2g(cudaStream_t st, const SeqSmoothArgs& a, int mo);
+int seq_filter_d3s1m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d3s1m(cudaStream_t st, const SeqSmoothArgs& a, int mo);
+int seq_filter_d3s3m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d3s3m(cudaStream_t st, const SeqSmoothArgs& a, int mo);
+int seq_filter_d3s3g(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d3s3g(cudaStream_t st, const SeqSmoothArgs& a, int mo);
+int seq_filter_d4s1m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d4s1m(cudaStream_t st, const SeqSmoothArgs& a, int mo);
+int seq_filter_d4s2m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d4s2m(cudaStream_t st, const SeqSmoothArgs& a, int mo);
+int seq_filter_d4s4m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d4s4m(cudaStream_t st, const SeqSmoothArgs& a, int mo);
+int seq_filter_d4s4g(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d4s4g(cudaStream_t st, const SeqSmoothArgs& a, int mo);
+
+bool seq_supported(int d, int m, int disc_mode, int nblk) {
+  if (d < 1 || d > 4 || m < 1 || m > d) return false;
+  if (disc_mode == PHYSS_DISC_GIVEN) return true;
+  if (disc_mode != PHYSS_DISC_MATERN || nblk <= 0 || d % nblk != 0) return false;
+  const int s = d / nblk;
+  return s == 1 || s == d || (d == 4 && s == 2);
+}
+
+int seq_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity,
+               const SeqFilterArgs& a) {
+  if (!seq_supported(d, m, disc_mode, nblk))
+    return set_error(PHYSS_ERR_UNSUPPORTED, "seq filter: no specialisation for this (d, m, blocks)");
+  const int s = (disc_mode == PHYSS_DISC_GIVEN) ? d : d / nblk;
+  const bool g = (disc_mode == PHYSS_DISC_GIVEN);
+  if (d == 1 && s == 1 && g == false) return seq_filter_d1s1m(st, a, m, h_identity);
+  if (d == 1 && s == 1 && g == true) return seq_filter_d1s1g(st, a, m, h_identity);
+  if (d == 2 && s == 1 && g == false) return seq_filter_d2s1m(st, a, m, h_identity);
+  if (d == 2 && s == 2 && g == false) return seq_filter_d2s2m(st, a, m, h_identity);
+  if (d == 2 && s == 2 && g == true) return seq_filter_d2s2g(st, a, m, h_identity);
+  if (d == 3 && s == 1 && g == false) return seq_filter_d3s1m(st, a, m, h_identity);
+  if (d == 3 && s == 3 && g == false) return seq_filter_d3s3m(st, a, m, h_identity);
+  if (d == 3 && s == 3 && g == true) return seq_filter_d3s3g(st, a, m, h_identity);
+  if (d == 4 && s == 1 && g == false) return seq_filter_d4s1m(st, a, m, h_identity);
+  if (d == 4 && s == 2 && g == false) return seq_filter_d4s2m(st, a, m, h_identity);
+  if (d == 4 && s == 4 && g == false) return seq_filter_d4s4m(st, a, m, h_identity);
+  if (d == 4 && s == 4 && g == true) return seq_filter_d4s4g(st, a, m, h_identity);
+  return set_error(PHYSS_ERR_UNSUPPORTED, "seq filter: unreachable");
+}
+
+int seq_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a) {
+  if (!seq_supported(d, mo == 0 ? d : mo, disc_mode, nblk))
+    return set_error(PHYSS_ERR_UNSUPPORTED, "seq smoother: no specialisation for this (d, mo, blocks)");
+  const int s = (disc_mode == PHYSS_DISC_GIVEN) ? d : d / nblk;
+  const bool g = (disc_mode == PHYSS_DISC_GIVEN);
+  if (d == 1 && s == 1 && g == false) return seq_smooth_d1s1m(st, a, mo);
+  if (d == 1 && s == 1 && g == true) return seq_smooth_d1s1g(st, a, mo);
+  if (d == 2 && s == 1 && g == false) return seq_smooth_d2s1m(st, a, mo);
+  if (d == 2 && s == 2 && g == false) return seq_smooth_d2s2m(st, a, mo);
+  if (d == 2 && s == 2 && g == true) return seq_smooth_d2s2g(st, a, mo);
+  if (d == 3 && s == 1 && g == false) return seq_smooth_d3s1m(st, a, mo);
+  if (d == 3 && s == 3 && g == false) return seq_smooth_d3s3m(st, a, mo);
+  if (d == 3 && s == 3 && g == true) return seq_smooth_d3s3g(st, a, mo);
+  if (d == 4 && s == 1 && g == false) return seq_smooth_d4s1m(st, a, mo);
+  if (d == 4 && s == 2 && g == false) return seq_smooth_d4s2m(st, a, mo);
+  if (d == 4 && s == 4 && g == false) return seq_smooth_d4s4m(st, a, mo);
+  if (d == 4 && s == 4 && g == true) return seq_smooth_d4s4g(st, a, mo);
+  return set_error(PHYSS_ERR_UNSUPPORTED, "seq smoother: unreachable");
+}
+
+}  // namespace physs

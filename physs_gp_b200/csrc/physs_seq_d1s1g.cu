@@ -1,0 +1,11 @@
+// physs_seq_d1s1g.cu -- instantiations of the register-resident sequential filter/smoother for
+// state dim 1, transition block size 1, caller-given A_k/Q_k.
+#include "physs_seq_impl.cuh"
+namespace physs {
+int seq_filter_d1s1g(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid) {
+  return filter_by_m<1, 1, true>(st, a, m, hid);
+}
+int seq_smooth_d1s1g(cudaStream_t st, const SeqSmoothArgs& a, int mo) {
+  return smooth_by_mo<1, 1, true>(st, a, mo);
+}
+}  // namespace physs

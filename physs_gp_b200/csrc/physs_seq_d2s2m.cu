@@ -1,0 +1,11 @@
+// physs_seq_d2s2m.cu -- instantiations of the register-resident sequential filter/smoother for
+// state dim 2, transition block size 2, closed-form Matern discretisation.
+#include "physs_seq_impl.cuh"
+namespace physs {
+int seq_filter_d2s2m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid) {
+  return filter_by_m<2, 2, false>(st, a, m, hid);
+}
+int seq_smooth_d2s2m(cudaStream_t st, const SeqSmoothArgs& a, int mo) {
+  return smooth_by_mo<2, 2, false>(st, a, mo);
+}
+}  // namespace physs

@@ -1,0 +1,11 @@
+// physs_seq_d3s3m.cu -- instantiations of the register-resident sequential filter/smoother for
+// state dim 3, transition block size 3, closed-form Matern discretisation.
+#include "physs_seq_impl.cuh"
+namespace physs {
+int seq_filter_d3s3m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid) {
+  return filter_by_m<3, 3, false>(st, a, m, hid);
+}
+int seq_smooth_d3s3m(cudaStream_t st, const SeqSmoothArgs& a, int mo) {
+  return smooth_by_mo<3, 3, false>(st, a, mo);
+}
+}  // namespace physs

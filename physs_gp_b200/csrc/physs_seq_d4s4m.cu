@@ -1,0 +1,11 @@
+// physs_seq_d4s4m.cu -- instantiations of the register-resident sequential filter/smoother for
+// state dim 4, transition block size 4, closed-form Matern discretisation.
+#include "physs_seq_impl.cuh"
+namespace physs {
+int seq_filter_d4s4m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid) {
+  return filter_by_m<4, 4, false>(st, a, m, hid);
+}
+int seq_smooth_d4s4m(cudaStream_t st, const SeqSmoothArgs& a, int mo) {
+  return smooth_by_mo<4, 4, false>(st, a, mo);
+}
+}  // namespace physs

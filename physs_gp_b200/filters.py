@@ -1,0 +1,155 @@
+"""The drop-in operators: `filter` / `smoother` registered under filter_type 'b200', and the host
+wrappers `filter_loop` / `smoother_loop` that feed them.
+
+Mirrors (paths relative to /root/reference/src/lib/stgp/computation/filters/):
+  kalman_filter.py:487-547  filter_loop(data, prior, R, R_inv, filter_type, train_test_mask, train_index)
+  kalman_filter.py:439-485  filter(data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask, train_index)
+  rts_smoother.py:194-219   smoother_loop(data, model, filter_res, full_state, filter_type)
+  rts_smoother.py:162-192   smoother(data, model, filter_res, dt, X_t, X_s, full_state)
+Same names, argument meaning and return structure; results are torch CUDA tensors (the analogue of
+the reference's device-resident jax arrays).  A leading batch axis B is accepted on Y / R and on the
+prior (`BatchedMaternSDE`), and is carried through to the outputs when present.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from . import settings
+from .dispatch import dispatch, evoke
+from .sdes import BatchedMaternSDE
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("physs_gp_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_dev(x, dev):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.float64, non_blocking=True)
+    return torch.as_tensor(np.asarray(x, dtype=np.float64)).to(dev, non_blocking=True)
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x, dtype=np.float64)
+
+
+def lower_prior(prior, X_s, dts, dev):
+    """Turn a prior object into what the kernels consume.
+
+    Returns (discs, m0, P0, H): one `ops.Disc` per dt array in `dts` (filter and smoother use
+    different dt conventions), m0 [*, d], P0 [*, d, d] device tensors and H as a numpy [m, d] array.
+    """
+    if isinstance(prior, BatchedMaternSDE):
+        lam = _to_dev(prior.lam(), dev)
+        Pinf = _to_dev(prior.P_inf(), dev)
+        disc = ops.Disc.matern(prior.nblk, lam, Pinf)
+        return [disc for _ in dts], _to_dev(prior.m_inf(), dev), Pinf, prior.H()
+    P_inf = np.asarray(prior.P_inf(None, X_s, None), np.float64)
+    m_inf = np.asarray(prior.m_inf(None, X_s, None), np.float64).reshape(1, -1)
+    H = np.asarray(prior.H(None, X_s, None), np.float64)
+    d = P_inf.shape[0]
+    blocks = prior.ss_blocks() if hasattr(prior, "ss_blocks") else None
+    P0 = _to_dev(P_inf[None], dev)
+    m0 = _to_dev(m_inf, dev)
+    if blocks is not None and len({s for s, _ in blocks}) == 1:
+        s = blocks[0][0]
+        mask = np.kron(np.eye(len(blocks)), np.ones([s, s]))
+        if np.all(P_inf * (1 - mask) == 0.0):
+            lam = _to_dev(np.array([[l for _, l in blocks]]), dev)
+            disc = ops.Disc.matern(len(blocks), lam, P0)
+            if ops.kf_supported(d, 1, disc):
+                return [disc for _ in dts], m0, P0, H
+    # generic route: evaluate the reference prior API once per distinct dt (host), ship A_k, Q_k
+    discs = []
+    for dt in dts:
+        dt_np = _np(dt).reshape(-1)
+        uniq, inv = np.unique(dt_np, return_inverse=True)
+        A_u = np.stack([np.asarray(prior.expm(X_s, float(u)), np.float64) for u in uniq])
+        Q_u = np.stack([np.asarray(prior.Q(float(u), A_u[i], P_inf, X_s), np.float64)
+                        for i, u in enumerate(uniq)])
+        discs.append(ops.Disc.given(_to_dev(A_u[inv], dev), _to_dev(Q_u[inv], dev)))
+    return discs, m0, P0, H
+
+
+def _is_identity(H):
+    return H.shape[0] == H.shape[1] and np.array_equal(H, np.eye(H.shape[0]))
+
+
+@dispatch('b200')
+def filter(data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask, train_index):
+    """B200 backend of evoke('filter', filter_type) -- kalman_filter.py:439-485.
+
+    Y [T, m, 1] (or [B, T, m, 1]), lik_mat R [T, m, m] (or [B, T, m, m] / broadcastable),
+    dt [T] with dt[0] = 0.  Returns (lml, {'m': [T, d, 1], 'P': [T, d, d]}) with a leading B when
+    the inputs were batched."""
+    if not lik_cov_flag:
+        # the reference's sequential path raises for precision sites too (kalman_filter.py:67)
+        raise NotImplementedError("sequential filter with a precision likelihood is not supported")
+    dev = _device()
+    Yd = _to_dev(Y, dev)
+    batched = Yd.dim() == 4 or isinstance(prior, BatchedMaternSDE)
+    if Yd.dim() == 3:
+        Yd = Yd[None]
+    Yd = Yd[..., 0]                                   # [B, T, m]
+    if isinstance(prior, BatchedMaternSDE) and Yd.shape[0] == 1 and prior.B > 1:
+        Yd = Yd.expand(prior.B, -1, -1)
+    dtd = _to_dev(dt, dev)
+    (disc,), m0, P0, H = lower_prior(prior, X_s, [dtd], dev)
+    R = _to_dev(lik_mat, dev)
+    Hd = None if _is_identity(H) else _to_dev(H, dev)
+    lml, mf, Pf = ops.kf_filter(dtd, Yd, R, Hd, m0, P0, disc, jitter=settings.jitter)
+    if batched:
+        return lml, {'m': mf[..., None], 'P': Pf}
+    return lml[0], {'m': mf[0][..., None], 'P': Pf[0]}
+
+
+@dispatch('b200')
+def smoother(data, model, filter_res, dt, X_t, X_s, full_state):
+    """B200 backend of evoke('smoother', filter_type) -- rts_smoother.py:162-192.
+    dt [T] with dt[k] = t_{k+1} - t_k, dt[T-1] = 0."""
+    dev = _device()
+    mf = _to_dev(filter_res['m'], dev)[..., 0]
+    Pf = _to_dev(filter_res['P'], dev)
+    batched = mf.dim() == 3
+    if not batched:
+        mf, Pf = mf[None], Pf[None]
+    dtd = _to_dev(dt, dev)
+    (disc,), _, _, H = lower_prior(model, X_s, [dtd], dev)
+    Hout = None if (full_state or _is_identity(H)) else _to_dev(H, dev)
+    ms, Ps = ops.rts_smooth(dtd, mf, Pf, disc, Hout=Hout, jitter=settings.jitter)
+    if batched:
+        return ms[..., None], Ps
+    return ms[0][..., None], Ps[0]
+
+
+def _time_axis(data, dev):
+    return _to_dev(data.X_time, dev).reshape(-1)
+
+
+def filter_loop(data, prior, R=None, R_inv=None, filter_type='b200', train_test_mask=None, train_index=None):
+    """kalman_filter.py:487-547: dt = [0, diff(t)], Y_st [Nt, P, Ns] -> [Nt, P*Ns, 1], pick R / R_inv,
+    resolve the backend by `filter_type`."""
+    dev = _device()
+    X_t = _time_axis(data, dev)
+    X_s = data.X_space
+    dt = torch.cat([torch.zeros(1, dtype=torch.float64, device=dev), X_t[1:] - X_t[:-1]])
+    Y = _to_dev(data.Y_st, dev)
+    Y = Y.reshape(*Y.shape[:-2], -1)[..., None]       # [..., Nt, P*Ns, 1]
+    if R_inv is not None:
+        lik_cov_flag, lik_mat = False, R_inv
+    else:
+        lik_cov_flag, lik_mat = True, R
+    filter_fn = evoke('filter', filter_type)
+    return filter_fn(data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask, train_index)
+
+
+def smoother_loop(data, model, filter_res, full_state=False, filter_type='b200'):
+    """rts_smoother.py:194-219: dt = [diff(t), 0]."""
+    dev = _device()
+    X_t = _time_axis(data, dev)
+    X_s = data.X_space
+    dt = torch.cat([X_t[1:] - X_t[:-1], torch.zeros(1, dtype=torch.float64, device=dev)])
+    smoother_fn = evoke('smoother', filter_type)
+    return smoother_fn(data, model, filter_res, dt, X_t, X_s, full_state)

@@ -1,0 +1,194 @@
+"""Host-side mirror of the prior API the filter consumes:
+  stgp/transforms/transform.py:400-545  Independent (block-diagonal stack of Q latent GPs)
+  stgp/transforms/sdes.py:18-97         LTI_SDE        (m_inf, P_inf, H, expm, Q, state_space_representation)
+  stgp/transforms/sdes.py:99-190        LTI_SDE_Full_State_Obs(_With_Mask)  (H observes the derivative state)
+Same method names and argument order, numpy on the host (these are d x d, T-independent objects).
+
+`BatchedMaternSDE` is new: B independent series with per-series hyper-parameters, evaluated
+vectorised -- the reference has no batch axis.
+"""
+import numpy as np
+
+from .kernels import _block_diag, Matern12, Matern32, Matern52, Matern72
+
+
+class GP:
+    """Minimal stand-in for a latent `GP(kernel)` node (stgp/models/gp.py:5-10)."""
+
+    def __init__(self, kernel):
+        self.kernel = kernel
+
+
+class Independent:
+    def __init__(self, latents):
+        self.parent = [l if hasattr(l, "kernel") else GP(l) for l in latents]
+
+    @property
+    def output_dim(self):
+        return len(self.parent)
+
+    def state_space_dim(self):
+        return [l.kernel.state_space_dim() for l in self.parent]
+
+    def state_space_representation(self, X_s=None):
+        reps = [l.kernel.to_ss(X_s) for l in self.parent]
+        F, L, Qc, H, minf, Pinf = [[r[i] for r in reps] for i in range(6)]
+        return (_block_diag(F), _block_diag(L), _block_diag(Qc), _block_diag(H),
+                np.vstack(minf), _block_diag(Pinf))
+
+    def expm(self, dt, X_s=None):
+        return _block_diag([l.kernel.expm(dt, X_s) for l in self.parent])
+
+    def Q(self, dt_k, A_k, P_inf, X_spatial=None):
+        # transform.py:499-545: per-latent kernel.Q on the diagonal blocks, re-stacked
+        out, off = [], 0
+        for l in self.parent:
+            n = l.kernel.to_ss(X_spatial)[0].shape[0]
+            sl = slice(off, off + n)
+            out.append(l.kernel.Q(dt_k, A_k[sl, sl], P_inf[sl, sl], X_spatial=X_spatial))
+            off += n
+        return _block_diag(out)
+
+    def ss_blocks(self):
+        blocks = []
+        for l in self.parent:
+            b = l.kernel.ss_blocks() if hasattr(l.kernel, "ss_blocks") else None
+            if b is None:
+                return None
+            blocks += b
+        return blocks
+
+
+class LTI_SDE:
+    """stgp/transforms/sdes.py:18-97."""
+
+    def __init__(self, gp, m_init=None):
+        self.gp = gp if isinstance(gp, Independent) else Independent([gp])
+        self.m_init = None if m_init is None else np.reshape(np.asarray(m_init, np.float64), [-1, 1])
+
+    def state_space_dim(self):
+        return self.gp.state_space_dim()
+
+    def state_space_representation(self, X_s=None, dt=None, t=None):
+        return self.gp.state_space_representation(X_s)
+
+    def H(self, x=None, X_s=None, t=None):
+        return self.gp.state_space_representation(X_s)[3]
+
+    def P_inf(self, x=None, X_s=None, t=None):
+        return self.gp.state_space_representation(X_s)[5]
+
+    def m_inf(self, x=None, X_s=None, t=None):
+        if self.m_init is not None:
+            return self.m_init
+        return self.gp.state_space_representation(X_s)[4]
+
+    def expm(self, X_s, t):
+        return self.gp.expm(t, X_s)
+
+    def Q(self, dt_k, A_k, P_inf, X_spatial=None):
+        return self.gp.Q(dt_k, A_k, P_inf, X_spatial=X_spatial)
+
+    def ss_blocks(self):
+        return self.gp.ss_blocks()
+
+
+class LTI_SDE_Full_State_Obs(LTI_SDE):
+    """stgp/transforms/sdes.py:99-172 for temporal models (Ns = ds = 1, overwrite_H=True): H selects
+    `keep_dims` of every latent's state (all of it by default), i.e. a row-subset of the identity."""
+
+    def __init__(self, gp, keep_dims=None):
+        super().__init__(gp)
+        self.keep_dims = None if keep_dims is None else list(keep_dims)
+
+    def H(self, x=None, X_s=None, t=None):
+        dims = self.gp.state_space_dim()
+        d = sum(dims)
+        rows, off = [], 0
+        for n in dims:
+            for j in (range(n) if self.keep_dims is None else self.keep_dims):
+                e = np.zeros(d)
+                e[off + j] = 1.0
+                rows.append(e)
+            off += n
+        return np.array(rows)
+
+
+LTI_SDE_Full_State_Obs_With_Mask = LTI_SDE_Full_State_Obs   # sdes.py:174-190 (keep_dims mandatory)
+
+_KINDS = {1: Matern12, 2: Matern32, 3: Matern52, 4: Matern72}
+
+
+class BatchedMaternSDE:
+    """B independent series, each a stack of `nblk` Matern-(s-1/2) blocks of equal size s with its own
+    lengthscales/variances [B, nblk]; `sum_blocks=True` observes the SUM of the blocks (SumKernel,
+    H = hstack) and False observes each block separately (Independent, H = block-diag).
+    `full_state_obs=True` gives H = I (LTI_SDE_Full_State_Obs)."""
+
+    def __init__(self, block_size, lengthscales, variances=None, sum_blocks=True, full_state_obs=False):
+        self.s = int(block_size)
+        self.ls = np.atleast_2d(np.asarray(lengthscales, np.float64))
+        self.var = np.ones_like(self.ls) if variances is None else np.broadcast_to(
+            np.atleast_2d(np.asarray(variances, np.float64)), self.ls.shape).copy()
+        self.B, self.nblk = self.ls.shape
+        self.d = self.s * self.nblk
+        self.sum_blocks = sum_blocks
+        self.full_state_obs = full_state_obs
+
+    def lam(self):
+        return np.sqrt(2.0 * self.s - 1.0) / self.ls          # [B, nblk]
+
+    def P_inf(self):
+        """[B, d, d] block-diagonal stationary covariances (closed forms of kernels.py, vectorised)."""
+        lam, v, s = self.lam(), self.var, self.s
+        blk = np.zeros([self.B, self.nblk, s, s])
+        if s == 1:
+            blk[..., 0, 0] = v
+        elif s == 2:
+            blk[..., 0, 0] = v
+            blk[..., 1, 1] = lam ** 2 * v
+        elif s == 3:
+            k = lam ** 2 * v / 3.0
+            blk[..., 0, 0] = v
+            blk[..., 1, 1] = k
+            blk[..., 0, 2] = blk[..., 2, 0] = -k
+            blk[..., 2, 2] = lam ** 4 * v
+        elif s == 4:
+            k1, k2 = lam ** 2 * v / 5.0, lam ** 4 * v / 5.0
+            blk[..., 0, 0] = v
+            blk[..., 1, 1] = k1
+            blk[..., 2, 2] = k2
+            blk[..., 3, 3] = lam ** 6 * v
+            blk[..., 0, 2] = blk[..., 2, 0] = -k1
+            blk[..., 1, 3] = blk[..., 3, 1] = -k2
+        else:
+            raise ValueError("block size must be 1..4")
+        P = np.zeros([self.B, self.d, self.d])
+        for b in range(self.nblk):
+            P[:, b * s:(b + 1) * s, b * s:(b + 1) * s] = blk[:, b]
+        return P
+
+    def m_inf(self):
+        return np.zeros([1, self.d])
+
+    def H(self):
+        if self.full_state_obs:
+            return np.eye(self.d)
+        if self.sum_blocks:
+            h = np.zeros([1, self.d])
+            h[0, ::self.s] = 1.0
+            return h
+        H = np.zeros([self.nblk, self.d])
+        for b in range(self.nblk):
+            H[b, b * self.s] = 1.0
+        return H
+
+    def series(self, b):
+        """The b-th series as an ordinary (reference-shaped) prior object."""
+        from .kernels import sum_kernels
+        ks = [_KINDS[self.s](self.ls[b, i], self.var[b, i]) for i in range(self.nblk)]
+        if self.full_state_obs:
+            return LTI_SDE_Full_State_Obs(Independent(ks))
+        if self.sum_blocks:
+            return LTI_SDE(Independent([sum_kernels(ks)]))
+        return LTI_SDE(Independent(ks))

@@ -1,0 +1,9 @@
+"""Numerically load-bearing global flags; mirror of the reference's stgp/settings.py:30-67.
+
+They are read when a b200 op is called and passed to the kernels as runtime scalars.
+"""
+jitter = 1e-5          # settings.py:63 -- gain solve, smoother chol(P_pred + jitter I)
+ng_jitter = 1e-7       # settings.py:64 -- theta <-> lambda transforms
+kalman_filter_force_symmetric = False   # settings.py:33 (only the default is supported)
+parallel_kf_force_linear_solve = False  # settings.py:55 (only the default is supported)
+verbose = False

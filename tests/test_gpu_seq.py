@@ -1,0 +1,215 @@
+"""-m gpu parity tests: the CUDA filter / smoother, called through the reference-shaped host API
+(filter_loop / smoother_loop -> evoke('filter'|'smoother', 'b200') -> C ABI), against the numpy
+oracle on identical seeded inputs.
+
+Tolerance (north_star): 1e-9 relative in fp64.  "Relative" is max|a - b| / max|b| per array: the
+reference itself mixes O(1) and O(lam^6) state components, so element-wise relative error is not
+meaningful for near-zero entries."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import filters as ofilters
+from oracle import sde as osde
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def _pair(kind, ls, var):
+    """(product kernel, oracle kernel) with identical hyper-parameters."""
+    from physs_gp_b200 import kernels as K
+    prod = {"m12": None, "m32": K.Matern32, "m52": K.Matern52, "m72": K.Matern72}[kind](ls, var)
+    orac = {"m32": osde.Matern32, "m52": osde.Matern52, "m72": osde.Matern72}[kind](ls, var)
+    return prod, orac
+
+
+def _priors(spec, full_state_obs=False, keep_dims=None):
+    """spec: list of latents, each a list of (kind, ls, var) summed."""
+    from physs_gp_b200 import kernels as K
+    from physs_gp_b200 import sdes
+    plat, olat = [], []
+    for latent in spec:
+        pk = [_pair(*p)[0] for p in latent]
+        ok = [_pair(*p)[1] for p in latent]
+        plat.append(K.sum_kernels(pk))
+        olat.append(ok[0] if len(ok) == 1 else osde.SumKernel(ok))
+    if full_state_obs:
+        return (sdes.LTI_SDE_Full_State_Obs(sdes.Independent(plat), keep_dims=keep_dims),
+                osde.LTI_SDE_Full_State_Obs(olat, keep_dims=keep_dims))
+    return sdes.LTI_SDE(sdes.Independent(plat)), osde.LTI_SDE(olat)
+
+
+SPECS = {
+    "c1_m32": ([[("m32", 1.0, 1.3)]], False),
+    "m52": ([[("m52", 0.7, 0.9)]], False),
+    "m72": ([[("m72", 1.2, 1.1)]], False),
+    "sum_m32x2": ([[("m32", 1.0, 1.3), ("m32", 0.4, 0.5)]], False),
+    "indep_m32x2": ([[("m32", 1.0, 1.3)], [("m32", 0.4, 0.5)]], False),
+    "m32_fullstate": ([[("m32", 1.0, 1.3)]], True),
+    "m52_fullstate": ([[("m52", 0.7, 0.9)]], True),
+    "m72_fullstate": ([[("m72", 1.2, 1.1)]], True),
+    "indep_m32x2_fullstate": ([[("m32", 1.0, 1.3)], [("m32", 0.4, 0.5)]], True),
+}
+
+
+def _run_case(spec, fso, T, seed, jitter, nan_frac, full_state, time_varying_R=True, keep_dims=None):
+    from physs_gp_b200 import data, filters, settings
+    rng = np.random.default_rng(seed)
+    pprior, oprior = _priors(spec, fso, keep_dims)
+    H = oprior.H()
+    m = H.shape[0]
+    t = synth.time_grid(T, 0.1, rng)
+    Y = synth.noisy_series(1, T, m, rng, nan_frac)[0]
+    R = synth.random_spd(rng, (T,), m) if time_varying_R else np.tile(0.1 * np.eye(m), [T, 1, 1])
+    lml_o, mf_o, Pf_o, _ = ofilters.filter_sequential(oprior, t, Y, R, jitter)
+    ms_o, Ps_o = ofilters.smoother_sequential(oprior, t, mf_o, Pf_o, full_state=full_state, jitter=jitter)
+    old = settings.jitter
+    settings.jitter = jitter
+    try:
+        d = data.TemporalData(t, Y[:, :, None])
+        lml, kf = filters.filter_loop(d, pprior, R=R if time_varying_R else R[:1])
+        mu, var = filters.smoother_loop(d, pprior, kf, full_state=full_state)
+    finally:
+        settings.jitter = old
+    torch.cuda.synchronize()
+    assert abs(float(lml) - lml_o) <= TOL * abs(lml_o), (float(lml), lml_o)
+    assert rel(kf['m'], mf_o) < TOL
+    assert rel(kf['P'], Pf_o) < TOL
+    assert rel(mu, ms_o) < TOL
+    assert rel(var, Ps_o) < TOL
+
+
+@pytest.mark.parametrize("name", sorted(SPECS))
+@pytest.mark.parametrize("jitter", [1e-5, 0.0])
+def test_filter_smoother_parity(cuda_device, name, jitter):
+    spec, fso = SPECS[name]
+    _run_case(spec, fso, T=300, seed=hash(name) % 1000, jitter=jitter, nan_frac=0.08, full_state=False)
+
+
+@pytest.mark.parametrize("name", ["m72", "sum_m32x2", "m52_fullstate"])
+def test_full_state_output(cuda_device, name):
+    spec, fso = SPECS[name]
+    _run_case(spec, fso, T=200, seed=7, jitter=1e-5, nan_frac=0.05, full_state=True)
+
+
+def test_keep_dims_partial_state_observation(cuda_device):
+    # LTI_SDE_Full_State_Obs_With_Mask (sdes.py:174-190): observe [f, df/dt] of a Matern-7/2 state
+    _run_case([[("m72", 1.2, 1.1)]], True, T=200, seed=11, jitter=1e-5, nan_frac=0.05,
+              full_state=False, keep_dims=[0, 1])
+
+
+def test_config1_matern32_T10k(cuda_device):
+    """BASELINE config 1: 1D Matern-3/2, Gaussian likelihood, N = 10k, exact lml."""
+    _run_case(SPECS["c1_m32"][0], False, T=10000, seed=0, jitter=1e-5, nan_frac=0.05,
+              full_state=False, time_varying_R=False)
+
+
+def test_edge_cases(cuda_device):
+    spec, fso = SPECS["m52"]
+    _run_case(spec, fso, T=1, seed=3, jitter=1e-5, nan_frac=0.0, full_state=False)      # single step
+    _run_case(spec, fso, T=2, seed=4, jitter=1e-5, nan_frac=0.0, full_state=True)
+    _run_case(spec, fso, T=50, seed=5, jitter=1e-5, nan_frac=1.0, full_state=False)     # all missing
+    _run_case(SPECS["indep_m32x2_fullstate"][0], True, T=60, seed=6, jitter=1e-5, nan_frac=0.5,
+              full_state=False)                                                        # ragged masks
+
+
+def test_generic_prior_goes_through_given_A_Q(cuda_device):
+    """A prior with no closed-form block description (dense F, scipy expm) takes the DISC_GIVEN route:
+    the shim evaluates prior.expm / prior.Q per distinct dt on the host, as the reference API allows."""
+    from physs_gp_b200 import data, filters
+    rng = np.random.default_rng(12)
+    F = np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [-2.0, -3.0, -1.5]])
+    import scipy.linalg as sla
+    Pinf = sla.solve_continuous_lyapunov(F, -np.diag([0.0, 0.0, 1.0]))
+    Hm = np.array([[1.0, 0.0, 0.0]])
+    ok = osde.GenericLTI(F, Hm, Pinf)
+    oprior = osde.LTI_SDE([ok])
+
+    class GenericPrior:                      # duck-typed reference prior API
+        def m_inf(self, x, X_s, t): return np.zeros([3, 1])
+        def P_inf(self, x, X_s, t): return Pinf
+        def H(self, x, X_s, t): return Hm
+        def expm(self, X_s, dt): return sla.expm(F * dt)
+        def Q(self, dt, A, P, X_spatial=None): return P - A @ P @ A.T
+
+    T = 150
+    t = synth.time_grid(T, 0.1, rng)
+    Y = synth.noisy_series(1, T, 1, rng, 0.05)[0]
+    R = np.tile(0.2 * np.eye(1), [T, 1, 1])
+    lml_o, mf_o, Pf_o, _ = ofilters.filter_sequential(oprior, t, Y, R)
+    ms_o, Ps_o = ofilters.smoother_sequential(oprior, t, mf_o, Pf_o)
+    d = data.TemporalData(t, Y[:, :, None])
+    lml, kf = filters.filter_loop(d, GenericPrior(), R=R)
+    mu, var = filters.smoother_loop(d, GenericPrior(), kf)
+    assert abs(float(lml) - lml_o) <= TOL * abs(lml_o)
+    assert rel(kf['P'], Pf_o) < TOL and rel(mu, ms_o) < TOL and rel(var, Ps_o) < TOL
+
+
+@pytest.mark.parametrize("s,nblk", [(2, 1), (3, 1), (4, 1), (2, 2)])
+def test_batched_per_series_hyperparameters(cuda_device, s, nblk):
+    """B series with their own lengthscales (BASELINE config 5 shape, small): every series must equal
+    the oracle run on that series alone."""
+    from physs_gp_b200 import data, filters, sdes
+    rng = np.random.default_rng(100 + 10 * s + nblk)
+    B, T = 37, 120
+    ls = synth.log_uniform(rng, 0.5, 2.0, (B, nblk))
+    var = synth.log_uniform(rng, 0.5, 2.0, (B, nblk))
+    prior = sdes.BatchedMaternSDE(s, ls, var, sum_blocks=True)
+    t = synth.time_grid(T, 0.1, rng)
+    Y = synth.noisy_series(B, T, 1, rng, 0.05)
+    R = np.full([1, 1, 1, 1], 0.1)
+    d = data.TemporalData(t, Y[..., None])
+    lml, kf = filters.filter_loop(d, prior, R=R)
+    mu, var_s = filters.smoother_loop(d, prior, kf, full_state=True)
+    kind = {2: osde.Matern32, 3: osde.Matern52, 4: osde.Matern72}[s]
+    for b in range(0, B, 6):
+        parts = [kind(ls[b, i], var[b, i]) for i in range(nblk)]
+        op = osde.LTI_SDE([parts[0] if nblk == 1 else osde.SumKernel(parts)])
+        lml_o, mf_o, Pf_o, _ = ofilters.filter_sequential(op, t, Y[b], np.tile(R[0, 0], [T, 1, 1]))
+        ms_o, Ps_o = ofilters.smoother_sequential(op, t, mf_o, Pf_o, full_state=True)
+        assert abs(float(lml[b]) - lml_o) <= TOL * abs(lml_o)
+        assert rel(kf['m'][b], mf_o) < TOL and rel(kf['P'][b], Pf_o) < TOL
+        assert rel(mu[b], ms_o) < TOL and rel(var_s[b], Ps_o) < TOL
+
+
+def test_full_size_properties(cuda_device):
+    """Size-independent properties at a BASELINE-sized shard (B = 2048 x T = 10k, Matern-7/2):
+    (i) permuting the series permutes the outputs bit-exactly (no cross-series coupling);
+    (ii) smoothed variance <= filtered variance; (iii) last smoothed step == last filtered step;
+    (iv) an all-missing series reproduces the prior (P = Pinf, lml = 0)."""
+    from physs_gp_b200 import data, filters, sdes
+    rng = np.random.default_rng(5)
+    B, T = 2048, 10000
+    ls = synth.log_uniform(rng, 5.0, 20.0, (B, 1)) * 0.1
+    prior = sdes.BatchedMaternSDE(4, ls)
+    t = synth.time_grid(T, 0.1, rng)
+    Y = synth.noisy_series(B, T, 1, rng, 0.05)
+    Y[3] = np.nan
+    R = np.full([1, 1, 1, 1], 0.1)
+    d = data.TemporalData(t, Y[..., None])
+    lml, kf = filters.filter_loop(d, prior, R=R)
+    mu, var = filters.smoother_loop(d, prior, kf, full_state=True)
+    assert torch.isfinite(lml).all() and torch.isfinite(var).all()
+    assert float(lml[3]) == 0.0
+    Pinf3 = torch.as_tensor(prior.P_inf()[3], device=var.device)
+    assert rel(kf['P'][3, -1], Pinf3.cpu().numpy()) < 1e-12
+    assert torch.equal(mu[:, -1], kf['m'][:, -1]) and torch.equal(var[:, -1], kf['P'][:, -1])
+    dP = torch.diagonal(kf['P'], dim1=-2, dim2=-1) - torch.diagonal(var, dim1=-2, dim2=-1)
+    scale = torch.diagonal(kf['P'], dim1=-2, dim2=-1).abs().amax(dim=(0, 1))
+    assert (dP / scale >= -1e-9).all()
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+    prior_p = sdes.BatchedMaternSDE(4, ls[perm.numpy()])
+    d_p = data.TemporalData(t, Y[perm.numpy()][..., None])
+    lml_p, kf_p = filters.filter_loop(d_p, prior_p, R=R)
+    mu_p, var_p = filters.smoother_loop(d_p, prior_p, kf_p, full_state=True)
+    permd = perm.to(lml.device)
+    assert torch.equal(lml_p.nan_to_num(), lml[permd].nan_to_num())
+    assert torch.equal(var_p, var[permd]) and torch.equal(mu_p, mu[permd])
