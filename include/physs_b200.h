@@ -14,6 +14,8 @@
  * Conventions
  *   - All pointers are DEVICE pointers to fp64 (C row-major, reference element order) unless noted;
  *     `stream` is a cudaStream_t passed as void*.  Calls are stream-ordered and never synchronise.
+ *   - Matrix / vector arrays (everything except dt, lam, lml) must be 16-byte aligned (any CUDA or
+ *     torch allocation is); the kernels use 128-bit accesses.
  *   - The caller owns every buffer; the library allocates nothing user-visible.
  *   - A leading batch axis B (independent series / spatial blocks / latent functions) is added in
  *     front of every reference array.  A `*_bstride` argument is the element stride between series

@@ -23,6 +23,10 @@ int cuda_status(cudaError_t e, const char* what) {
 
 using namespace physs;
 
+static inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
+template <typename... Ps>
+static inline bool any_misaligned(Ps... ps) { return (misaligned(ps) || ...); }
+
 extern "C" {
 
 int physs_abi_version(void) { return 1; }
@@ -30,7 +34,11 @@ int physs_abi_version(void) { return 1; }
 const char* physs_last_error(void) { return g_err; }
 
 int physs_kf_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {
-  return seq_supported(d, m, disc_mode, nblk) ? 1 : 0;
+  if (seq_supported(d, m, disc_mode, nblk)) return 1;
+  if (disc_mode == PHYSS_DISC_MATERN) {
+    if (nblk < 1 || d % nblk != 0 || d / nblk > 4) return 0;
+  }
+  return grp_supported(d, m) ? 1 : 0;
 }
 
 int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int32_t d, int32_t m,
@@ -52,6 +60,8 @@ int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int32_t d, int32_t m
   if (!dt || !m0 || !P0 || !Y || !R || !mf || !Pf || !lml)
     return set_error(PHYSS_ERR_BAD_ARG, "filter: null required pointer");
   if (!H && m != d) return set_error(PHYSS_ERR_BAD_ARG, "filter: H == NULL (identity) needs m == d");
+  if (any_misaligned(A, Q, Pinf, m0, P0, Y, R, mf, Pf))
+    return set_error(PHYSS_ERR_BAD_ARG, "filter: matrix/vector pointers must be 16-byte aligned");
   if (disc_mode == PHYSS_DISC_GIVEN) {
     if (!A || !Q) return set_error(PHYSS_ERR_BAD_ARG, "filter: DISC_GIVEN needs A and Q");
   } else if (disc_mode == PHYSS_DISC_MATERN) {
@@ -68,7 +78,10 @@ int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int32_t d, int32_t m
   a.P0 = P0; a.P0_bs = P0_bstride; a.H = H; a.H_bs = H_bstride;
   a.Y = Y; a.R = R; a.R_bs = R_bstride; a.R_ts = R_tstride;
   a.jitter = jitter; a.mf = mf; a.Pf = Pf; a.lml = lml; a.lml_k = lml_k;
-  return seq_filter((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a);
+  if (seq_supported(d, m, disc_mode, nblk))
+    return seq_filter((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a);
+  if (m > d) return set_error(PHYSS_ERR_UNSUPPORTED, "filter: m > d is not supported");
+  return grp_filter((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a);
 }
 
 int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int32_t d,
@@ -87,6 +100,8 @@ int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int32_t d,
   if (!dt || !mf || !Pf || !ms || !Ps)
     return set_error(PHYSS_ERR_BAD_ARG, "smoother: null required pointer");
   if (mo > 0 && !Hout) return set_error(PHYSS_ERR_BAD_ARG, "smoother: mo > 0 needs Hout");
+  if (any_misaligned(A, Q, Pinf, mf, Pf, ms, Ps))
+    return set_error(PHYSS_ERR_BAD_ARG, "smoother: matrix/vector pointers must be 16-byte aligned");
   if (disc_mode == PHYSS_DISC_GIVEN) {
     if (!A || !Q) return set_error(PHYSS_ERR_BAD_ARG, "smoother: DISC_GIVEN needs A and Q");
   } else if (disc_mode == PHYSS_DISC_MATERN) {
@@ -101,7 +116,10 @@ int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int32_t d,
   a.lam = lam; a.lam_bs = lam_bstride; a.dt = dt; a.dt_bs = dt_bstride;
   a.Pinf = Pinf; a.Pinf_bs = Pinf_bstride; a.mf = mf; a.Pf = Pf;
   a.Hout = (mo > 0) ? Hout : nullptr; a.jitter = jitter; a.ms = ms; a.Ps = Ps;
-  return seq_smooth((cudaStream_t)stream, d, (Hout ? mo : 0), disc_mode, nblk, a);
+  const int mo_eff = Hout ? mo : 0;
+  if (seq_supported(d, mo_eff == 0 ? d : mo_eff, disc_mode, nblk))
+    return seq_smooth((cudaStream_t)stream, d, mo_eff, disc_mode, nblk, a);
+  return grp_smooth((cudaStream_t)stream, d, mo_eff, disc_mode, nblk, a);
 }
 
 }  // extern "C"

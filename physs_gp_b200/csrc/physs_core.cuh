@@ -26,6 +26,58 @@
 namespace physs {
 
 constexpr double kLog2Pi = 1.8378770664093454835606594728112;
+constexpr double kLn2 = 0.69314718055994530941723212145818;
+
+// Branch-free reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~2^-20)
+// refined by three Newton steps to <= 2 ulp.  Unlike `1.0 / x` and `sqrt(x)` they compile to
+// straight-line code (no slow-path call), which keeps each time step one schedulable basic block.
+// x < 0 -> NaN, as the reference's Cholesky produces for a non-PD matrix.
+PHYSS_HD double fast_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+
+PHYSS_HD double fast_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = fma(y, fma(-hx * y, y, 0.5), y);
+  y = fma(y, fma(-hx * y, y, 0.5), y);
+  y = fma(y, fma(-hx * y, y, 0.5), y);
+  return y;
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
+// Running log-determinant / Mahalanobis accumulator for the marginal likelihood: sum_k log|S_k| is
+// carried as a (mantissa product, binary exponent) pair so that no log() sits in the time loop.
+struct LmlAcc {
+  double prod = 1.0;   // product of determinants, renormalised into [0.5, 1)
+  long long expo = 0;  // accumulated binary exponent
+  double quad = 0.0;   // sum of Mahalanobis terms
+  long long nobs = 0;  // number of observed scalars
+  PHYSS_HD void add(double det, double mahal, int n_obs) {
+    prod *= det;
+    int e;
+    prod = frexp(prod, &e);
+    expo += e;
+    quad += mahal;
+    nobs += n_obs;
+  }
+  PHYSS_HD double value() const {
+    return -0.5 * ((double)nobs * kLog2Pi + (log(prod) + (double)expo * kLn2) + quad);
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Closed-form A = expm(F dt) for Matern-(S-1/2) state-space blocks, S = 1..4.
@@ -163,8 +215,8 @@ PHYSS_HD void chol_lower(const double (&A)[N][N], double (&L)[N][N], double (&rd
     double s = A[j][j];
     PHYSS_UNROLL
     for (int k = 0; k < j; ++k) s = fma(-L[j][k], L[j][k], s);
-    const double ljj = sqrt(s);
-    const double r = 1.0 / ljj;
+    const double r = fast_rsqrt(s);
+    const double ljj = s * r;
     L[j][j] = ljj;
     rdiag[j] = r;
     PHYSS_UNROLL
@@ -202,8 +254,9 @@ PHYSS_HD void chol_solve_vec(const double (&L)[N][N], const double (&rdiag)[N], 
 // y may contain NaN (= missing).  Returns this step's log marginal likelihood term.
 // ---------------------------------------------------------------------------------------------
 template <int D, int M, bool HID>
-PHYSS_HD double kf_update(double (&m)[D], double (&P)[D][D], const double (&H)[M][D],
-                          const double (&R)[M][M], const double (&y)[M], double jitter) {
+PHYSS_HD void kf_update(double (&m)[D], double (&P)[D][D], const double (&H)[M][D],
+                        const double (&R)[M][M], const double (&y)[M], double jitter,
+                        double& det_out, double& mahal_out, int& nobs_out) {
   // mask
   bool obs[M];
   int n_missing = 0;
@@ -257,11 +310,9 @@ PHYSS_HD double kf_update(double (&m)[D], double (&P)[D][D], const double (&H)[M
       S[b][a] = acc + R[b][a];
     }
   }
-  double lml;
   if (M == 1) {
     // scalar fast path
-    const double Sj = S[0][0] + jitter;
-    const double rSj = 1.0 / Sj;
+    const double rSj = fast_rcp(S[0][0] + jitter);
     double K[D];
     PHYSS_UNROLL
     for (int i = 0; i < D; ++i) K[i] = HP[0][i] * rSj;
@@ -279,7 +330,9 @@ PHYSS_HD double kf_update(double (&m)[D], double (&P)[D][D], const double (&H)[M
     }
     // masked step: mask_to_identity(S) = 1, v = 0  ->  lml_k = 0
     const double Sl = obs[0] ? S[0][0] : 1.0;
-    lml = -0.5 * (log(Sl) + v[0] * v[0] / Sl) - (obs[0] ? 0.5 * kLog2Pi : 0.0);
+    det_out = Sl;
+    mahal_out = v[0] * v[0] * fast_rcp(Sl);
+    nobs_out = obs[0] ? 1 : 0;
   } else {
     // K^T = (S + jitter I)^{-1} (M H P_)
     double Sj[M][M];
@@ -343,9 +396,9 @@ PHYSS_HD double kf_update(double (&m)[D], double (&P)[D][D], const double (&H)[M
     }
     double L2[M][M], rd2[M];
     chol_lower<M>(Sm, L2, rd2);
-    double logdet = 0.0;
+    double det = 1.0;
     PHYSS_UNROLL
-    for (int a = 0; a < M; ++a) logdet += log(L2[a][a] * L2[a][a]);
+    for (int a = 0; a < M; ++a) det *= L2[a][a] * L2[a][a];
     double w[M];
     PHYSS_UNROLL
     for (int a = 0; a < M; ++a) w[a] = v[a];
@@ -353,9 +406,15 @@ PHYSS_HD double kf_update(double (&m)[D], double (&P)[D][D], const double (&H)[M
     double mahal = 0.0;
     PHYSS_UNROLL
     for (int a = 0; a < M; ++a) mahal = fma(v[a], w[a], mahal);
-    lml = -0.5 * (M - n_missing) * kLog2Pi - 0.5 * logdet - 0.5 * mahal;
+    det_out = det;
+    mahal_out = mahal;
+    nobs_out = M - n_missing;
   }
-  return lml;
+}
+
+// log N term of one step from its (det, mahal, nobs) triple (only used when per-step values are asked for)
+PHYSS_HD double lml_term(double det, double mahal, int nobs) {
+  return -0.5 * ((double)nobs * kLog2Pi + log(det) + mahal);
 }
 
 // ---------------------------------------------------------------------------------------------

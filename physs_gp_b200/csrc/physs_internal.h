@@ -46,4 +46,10 @@ int seq_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_id
                const SeqFilterArgs& a);
 int seq_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
 
+// physs_grp.cu: one lane group per series, shared-memory resident, runtime (d, m)
+bool grp_supported(int d, int m);
+int grp_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity,
+               const SeqFilterArgs& a);
+int grp_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
+
 }  // namespace physs

@@ -19,7 +19,9 @@ namespace physs {
 
 template <int N>
 __device__ __forceinline__ void load_vec(const double* __restrict__ src, double (&dst)[N]) {
-  if ((N % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+  // every base pointer of the ABI is 16-byte aligned (checked in physs_api.cu), so rows with an even
+  // number of doubles are always 16-byte aligned
+  if (N % 2 == 0) {
 #pragma unroll
     for (int i = 0; i < N / 2; ++i) {
       const double2 v = reinterpret_cast<const double2*>(src)[i];
@@ -34,7 +36,7 @@ __device__ __forceinline__ void load_vec(const double* __restrict__ src, double 
 
 template <int N>
 __device__ __forceinline__ void store_vec(double* __restrict__ dst, const double (&src)[N]) {
-  if ((N % 2 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+  if (N % 2 == 0) {
 #pragma unroll
     for (int i = 0; i < N / 2; ++i)
       reinterpret_cast<double2*>(dst)[i] = make_double2(src[2 * i], src[2 * i + 1]);
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) 
   double* __restrict__ mfp = p.mf + b * T * D;
   double* __restrict__ Pfp = p.Pf + b * T * D * D;
 
-  double lml_acc = 0.0;
+  LmlAcc acc;
   // software prefetch of the next step's streamed inputs
   double y_n[M], R_n[M][M], dt_n;
   load_vec<M>(Yp, y_n);
@@ -127,13 +129,15 @@ __global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) 
       matern_trans<D, S>(lam, dt, A);
       kf_predict_stationary<D, S>(A, Pinf, m, P);
     }
-    const double l = kf_update<D, M, HID>(m, P, H, R, y, p.jitter);
-    lml_acc += l;
+    double det, mahal;
+    int nobs;
+    kf_update<D, M, HID>(m, P, H, R, y, p.jitter, det, mahal, nobs);
+    acc.add(det, mahal, nobs);
     store_vec<D>(mfp + k * D, m);
     store_mat<D>(Pfp + k * D * D, P);
-    if (p.lml_k) p.lml_k[b * T + k] = l;
+    if (p.lml_k) p.lml_k[b * T + k] = lml_term(det, mahal, nobs);
   }
-  p.lml[b] = lml_acc;
+  p.lml[b] = acc.value();
 }
 
 // ---------------------------------------------------------------------------------------- smoother

@@ -11,12 +11,13 @@ template <int D, int S, int M, bool HID, bool GIVEN>
 static void run_filter(int64_t T, const double* A_, const double* Q_, const double* lam_, const double* dt,
                        const double* Pinf_, const double* m0, const double* P0, const double* H_,
                        const double* Y, const double* R_, int64_t R_ts, double jitter, double* mf,
-                       double* Pf, double* lml_k) {
+                       double* Pf, double* lml_k, double* lml_total) {
   double m[D], P[D][D], Pinf[D][D], H[M][D], lam[D / S];
   memcpy(m, m0, sizeof(m));
   memcpy(P, P0, sizeof(P));
   if (!GIVEN) { memcpy(Pinf, Pinf_, sizeof(Pinf)); memcpy(lam, lam_, sizeof(lam)); }
   if (!HID) memcpy(H, H_, sizeof(H));
+  LmlAcc acc;
   for (int64_t k = 0; k < T; ++k) {
     double y[M], R[M][M];
     memcpy(y, Y + k * M, sizeof(y));
@@ -31,10 +32,15 @@ static void run_filter(int64_t T, const double* A_, const double* Q_, const doub
       for (int b = 0; b < D / S; ++b) MaternExpm<S>::eval(lam[b], dt[k], A.a[b]);
       kf_predict_stationary<D, S>(A, Pinf, m, P);
     }
-    lml_k[k] = kf_update<D, M, HID>(m, P, H, R, y, jitter);
+    double det, mahal;
+    int nobs;
+    kf_update<D, M, HID>(m, P, H, R, y, jitter, det, mahal, nobs);
+    acc.add(det, mahal, nobs);
+    lml_k[k] = lml_term(det, mahal, nobs);
     memcpy(mf + k * D, m, sizeof(m));
     memcpy(Pf + k * D * D, P, sizeof(P));
   }
+  *lml_total = acc.value();
 }
 
 template <int D, int S, bool GIVEN>
@@ -70,7 +76,7 @@ static void run_smooth(int64_t T, const double* A_, const double* Q_, const doub
 #define CASE_F(D, S, M, HID, GIVEN)                                                            \
   if (d == D && s == S && m == M && hid == HID && given == GIVEN) {                             \
     run_filter<D, S, M, HID, GIVEN>(T, A, Q, lam, dt, Pinf, m0, P0, H, Y, R, R_ts, jitter, mf, Pf, \
-                                    lml_k);                                                     \
+                                    lml_k, lml_total);                                                   \
     return 0;                                                                                   \
   }
 #define CASE_S(D, S, GIVEN)                                                      \
@@ -83,7 +89,7 @@ extern "C" int host_filter(int d, int s, int m, int hid, int given, int64_t T, c
                            const double* Q, const double* lam, const double* dt, const double* Pinf,
                            const double* m0, const double* P0, const double* H, const double* Y,
                            const double* R, int64_t R_ts, double jitter, double* mf, double* Pf,
-                           double* lml_k) {
+                           double* lml_k, double* lml_total) {
   CASE_F(2, 2, 1, false, false) CASE_F(2, 2, 1, false, true) CASE_F(2, 2, 2, true, false)
   CASE_F(3, 3, 1, false, false) CASE_F(3, 3, 3, true, false) CASE_F(3, 3, 2, false, true)
   CASE_F(4, 4, 1, false, false) CASE_F(4, 2, 1, false, false) CASE_F(4, 2, 2, false, false)

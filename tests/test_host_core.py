@@ -86,9 +86,11 @@ def test_core_matches_oracle(lib, case, jitter):
         Qs = np.array([Pinf - a @ Pinf @ a.T for a in As])
         s = d
     mf2, Pf2, lk2 = np.zeros((T, d)), np.zeros((T, d, d)), np.zeros(T)
+    ltot = np.zeros(1)
     rc = lib.host_filter(d, s, m, int(hid), int(given), ctypes.c_int64(T), _ptr(A), _ptr(Q), _ptr(lam),
                          _ptr(dt), _ptr(Pinf), _ptr(m0), _ptr(Pinf), _ptr(H), _ptr(Y), _ptr(R),
-                         ctypes.c_int64(m * m), ctypes.c_double(jitter), _ptr(mf2), _ptr(Pf2), _ptr(lk2))
+                         ctypes.c_int64(m * m), ctypes.c_double(jitter), _ptr(mf2), _ptr(Pf2), _ptr(lk2),
+                         _ptr(ltot))
     assert rc == 0
     ms2, Ps2 = np.zeros((T, d)), np.zeros((T, d, d))
     rc = lib.host_smooth(d, s, int(given), ctypes.c_int64(T), _ptr(As), _ptr(Qs), _ptr(lam), _ptr(dts),
@@ -102,6 +104,7 @@ def test_core_matches_oracle(lib, case, jitter):
     assert rel(mf2, mf[:, :, 0]) < tol
     assert rel(Pf2, Pf) < tol
     assert abs(lk2.sum() - lml) < tol * abs(lml)
+    assert abs(ltot[0] - lml) < tol * abs(lml)      # product-of-determinants accumulator
     assert rel(lk2, lk) < 1e-10
     assert rel(ms2, ms[:, :, 0]) < tol
     assert rel(Ps2, Ps) < tol
