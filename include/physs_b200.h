@@ -108,6 +108,50 @@ int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int32_t d,
                          double jitter,
                          double* ms, double* Ps);
 
+/* CVI likelihood kinds */
+#define PHYSS_LIK_GAUSS 0            /* y = W u + e, e ~ N(0, noise): closed-form block ELL               */
+#define PHYSS_LIK_POISSON_EXP 1      /* independent Poisson(binsize * exp(f_p)), f = W u, Gauss-Hermite   */
+#define PHYSS_LIK_BERNOULLI_PROBIT 2 /* independent Bernoulli(Phi(f_p)) with the reference's +1e-5 jitter */
+#define PHYSS_LIK_GIVEN 3            /* dELL/dm, dELL/dS supplied by the caller (e.g. jax.grad of an MC ELL) */
+
+/* One CVI natural-gradient site update for N independent site blocks (N = B * T).
+ * Replaces natural_gradients(FullConjugateGaussian) (computation/natural_gradients/cvi_nat_grad.py:
+ * 346-410) + cvi_block_update (:47-87) + theta_to_lambda / lambda_to_theta
+ * (exponential_family_transforms.py:25-42,70-83) + the 'NG_Moment' re-entry
+ * (cvi_parameterisations.py:63-93), with the ELL gradients in closed form / Gauss-Hermite instead of
+ * jax.grad (cvi_nat_grad.py:381-383), or supplied (PHYSS_LIK_GIVEN).
+ *   Ytil [N, D], Vtil [N, D, D]    sites (the surrogate model's data and BlockDiagonalGaussian variance)
+ *   q_mu [N, D], q_var [N, D, D]   posterior marginals of the site blocks (surrogate.posterior_blocks())
+ *   y [N, P] data (NaN = missing); W [P, D] (NULL = identity, P == D) maps the block to likelihood inputs
+ *   noise [., P, P] Gaussian noise, noise_stride elements between blocks (0 = shared)
+ *   lik_param: Poisson binsize;  K, ghx[K], ghw[K]: Gauss-Hermite nodes and weights / sqrt(pi)
+ *   beta: step size;  ng_jitter: settings.ng_jitter
+ * Outputs: Ytil_out, Vtil_out (may alias the inputs); ell_out [N] or NULL: per-block data ELL.
+ */
+int physs_cvi_natgrad_step_f64(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik,
+                               const double* Ytil, const double* Vtil,
+                               const double* q_mu, const double* q_var,
+                               const double* y, const double* W,
+                               const double* noise, int64_t noise_stride,
+                               double lik_param, int32_t K, const double* ghx, const double* ghw,
+                               const double* dm_in, const double* dS_in,
+                               double beta, double ng_jitter,
+                               double* Ytil_out, double* Vtil_out, double* ell_out);
+
+/* Per-block expected log-likelihood (and optionally its gradients) under q = N(q_mu, q_var).
+ * Replaces full_gaussian_expected_log_likelihood (computation/elbos/expected_log_likelihoods.py:90-117)
+ * vmapped over blocks (dispatched_ell.py:47-132) and the non-Gaussian approximate_expectation route
+ * (dispatched_ell.py:406-434) with Gauss-Hermite quadrature.  The CVI ELBO (elbos.py:163-194) is
+ *   sum(ell_data) - sum(ell_surrogate) + lml_surrogate,
+ * where ell_surrogate is this call with lik = GAUSS, W = NULL, y = Ytil, noise = Vtil.
+ */
+int physs_cvi_ell_f64(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik,
+                      const double* q_mu, const double* q_var,
+                      const double* y, const double* W,
+                      const double* noise, int64_t noise_stride,
+                      double lik_param, int32_t K, const double* ghx, const double* ghw,
+                      double* ell_out, double* dm_out, double* dS_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,165 @@
+"""Oracle: CVI natural-gradient site update, expected log-likelihoods and ELBO (test infrastructure).
+
+Follows (paths relative to /root/reference/src/lib/stgp/):
+  computation/natural_gradients/exponential_family_transforms.py:25-42   theta_to_lambda   (ng_jitter)
+  computation/natural_gradients/exponential_family_transforms.py:70-83   lambda_to_theta   (ng_jitter)
+  computation/natural_gradients/cvi_nat_grad.py:47-87                    cvi_block_update
+  computation/natural_gradients/cvi_nat_grad.py:346-410                  natural_gradients(FullConjugateGaussian)
+  computation/natural_gradients/cvi_parameterisations.py:63-93           lambda -> theta re-entry ('NG_Moment')
+  computation/elbos/expected_log_likelihoods.py:90-117                   full_gaussian_expected_log_likelihood
+  computation/elbos/elbos.py:163-194                                     elbo(FullConjugateGaussian)
+  computation/general.py:9-26, likelihood/poisson.py:20-22, likelihood/bernoulli.py:17-19   scalar log-liks
+  computation/integrals/samples.py:67-90                                 Gauss-Hermite branch (DEAD code in
+       the reference: undefined names, use_quadrature=False) -- restated here as the formula it intends.
+
+PARITY STATUS.  theta<->lambda, cvi_block_update, the Gaussian/surrogate ELL and the ELBO assembly are
+deterministic in the reference and restated verbatim.  The reference obtains dELL/dm, dELL/dS by
+`jax.grad` (cvi_nat_grad.py:381-383); the closed forms used here (Gaussian: R^-1(y-m), -1/2 R^-1) are
+checked against finite differences of the restated ELL in tests/test_oracle_cvi.py.  The non-Gaussian
+ELL in the reference is Monte-Carlo on an objax PRNG stream (not reproducible without JAX); its
+Gauss-Hermite replacement below is **parity unpinned** against the reference and is validated against
+the Poisson closed form (expected_log_likelihoods.py:149-174) and high-order quadrature instead.
+"""
+import numpy as np
+from scipy.special import gammaln, ndtr
+
+from . import linalg as la
+
+
+# ------------------------------------------------------------------ exponential-family transforms
+
+def theta_to_lambda(theta_1, theta_2, ng_jitter=la.NG_JITTER):
+    """theta = (Y~ [D,1], V~ [D,D]) -> lambda = (V~^-1 Y~, -1/2 V~^-1)."""
+    D = theta_1.shape[0]
+    L = la.cholesky(theta_2 + ng_jitter * np.eye(D))
+    lambda_1 = la.cholesky_solve(L, theta_1)
+    lambda_2 = -0.5 * la.cholesky_solve(L, np.eye(D))
+    return lambda_1, lambda_2
+
+
+def lambda_to_theta(lambda_1, lambda_2, ng_jitter=la.NG_JITTER):
+    D = lambda_1.shape[0]
+    L = la.cholesky(la.add_jitter(-2 * lambda_2, ng_jitter))
+    theta_2 = la.cholesky_solve(L, np.eye(D))
+    theta_1 = theta_2 @ lambda_1
+    return theta_1, theta_2
+
+
+def cvi_block_update(lambda_1, lambda_2, m, s, m_grad, s_grad, beta):
+    """cvi_nat_grad.py:47-87 with enforce_psd_type=None."""
+    grad_1 = m_grad - 2 * s_grad @ m
+    grad_2 = s_grad
+    return (1 - beta) * lambda_1 + beta * grad_1, (1 - beta) * lambda_2 + beta * grad_2
+
+
+# ------------------------------------------------------------------ expected log-likelihoods
+
+def full_gaussian_ell(Y, noise, q_mu, q_covar):
+    """expected_log_likelihoods.py:90-117: log N(Y | q_mu, noise) - 1/2 tr(noise^-1 q_covar), NaN-masked.
+    Y, q_mu [P,1]; noise, q_covar [P,P]."""
+    mask = (~np.isnan(Y[:, 0])).astype(int)
+    ml = la.log_gaussian_with_mask(Y, q_mu, noise, mask)
+    N_mask = np.sum(1 - mask)
+    masked_noise = la.mask_to_identity(noise, mask)
+    L = la.cholesky(masked_noise)
+    masked_q = la.mask_to_identity(q_covar, mask)
+    traced = la.cholesky_solve(L, masked_q)
+    return ml - 0.5 * np.trace(traced) + 0.5 * N_mask
+
+
+def gaussian_ell_and_grads(Y, noise, W, q_mu, q_var):
+    """ELL of a Gaussian likelihood y = W u + e, e ~ N(0, noise), under q(u) = N(q_mu, q_var), with the
+    gradients w.r.t. (q_mu, q_var) that jax.grad produces in cvi_nat_grad.py:381-383.
+    W=None means W = I.  Y [P]; noise [P,P]; q_mu [D]; q_var [D,D]."""
+    D = q_mu.shape[0]
+    Wm = np.eye(D) if W is None else W
+    f_mu = Wm @ q_mu
+    f_var = Wm @ q_var @ Wm.T
+    ell = full_gaussian_ell(Y[:, None], noise, f_mu[:, None], f_var)
+    mask = ~np.isnan(Y)
+    Rinv = np.zeros_like(noise)
+    if mask.any():
+        idx = np.where(mask)[0]
+        Rinv[np.ix_(idx, idx)] = np.linalg.inv(noise[np.ix_(idx, idx)])
+    err = np.where(mask, np.nan_to_num(Y) - f_mu, 0.0)
+    dm = Wm.T @ (Rinv @ err)
+    dS = -0.5 * Wm.T @ Rinv @ Wm
+    return ell, dm, dS
+
+
+def log_poisson(y, f, binsize=1.0):
+    """general.py:9-11 with likelihood/poisson.py:20-22 (exp link)."""
+    lam = np.exp(f) * binsize
+    return y * np.log(lam) - lam - gammaln(y + 1.0)
+
+
+def log_bernoulli_probit(y, f):
+    """general.py:13-26 with likelihood/bernoulli.py:17-19: probit link, +1e-5 inside both logs."""
+    p = ndtr(f)
+    return y * np.log(p + 1e-5) + (1 - y) * np.log(1 - p + 1e-5)
+
+
+def _dlog_poisson(y, f, binsize):
+    lam = np.exp(f) * binsize
+    return y - lam, -lam
+
+
+def _dlog_bernoulli(y, f):
+    p = ndtr(f)
+    pdf = np.exp(-0.5 * f * f) / np.sqrt(2 * np.pi)
+    a, b = p + 1e-5, 1 - p + 1e-5
+    d1 = y * pdf / a - (1 - y) * pdf / b
+    dpdf = -f * pdf
+    d2 = y * (dpdf / a - pdf * pdf / (a * a)) - (1 - y) * (dpdf / b + pdf * pdf / (b * b))
+    return d1, d2
+
+
+def gh_ell_and_grads(y, m, v, kind, K=20, binsize=1.0):
+    """K-point Gauss-Hermite expected log-likelihood of a scalar site and its derivatives w.r.t. the
+    marginal mean m and variance v:  E[l(f)], E[l'(f)], 1/2 E[l''(f)]   (f ~ N(m, v)).
+    NaN y -> (0, 0, 0).  PARITY UNPINNED (see module docstring)."""
+    if np.isnan(y):
+        return 0.0, 0.0, 0.0
+    x, w = np.polynomial.hermite.hermgauss(K)
+    w = w / np.sqrt(np.pi)
+    f = m + np.sqrt(2.0 * v) * x
+    if kind == "poisson":
+        l = log_poisson(y, f, binsize)
+        d1, d2 = _dlog_poisson(y, f, binsize)
+    elif kind == "bernoulli":
+        l = log_bernoulli_probit(y, f)
+        d1, d2 = _dlog_bernoulli(y, f)
+    else:
+        raise ValueError(kind)
+    return float(np.sum(w * l)), float(np.sum(w * d1)), float(0.5 * np.sum(w * d2))
+
+
+def poisson_ell_closed_form(y, m, v, binsize=1.0):
+    """expected_log_likelihoods.py:149-174."""
+    return y * np.log(binsize) + y * m - binsize * np.exp(m + v / 2) - gammaln(y + 1.0)
+
+
+# ------------------------------------------------------------------ one CVI iteration / ELBO
+
+def cvi_step(Ytil, Vtil, q_mu, q_var, dm, dS, beta, ng_jitter=la.NG_JITTER):
+    """natural_gradients(FullConjugateGaussian) + 'NG_Moment' re-entry for all T blocks.
+    Ytil [T,D]; Vtil, q_var, dS [T,D,D]; q_mu, dm [T,D].  Returns new (Ytil, Vtil)."""
+    T, D = Ytil.shape
+    Yn, Vn = np.empty_like(Ytil), np.empty_like(Vtil)
+    for t in range(T):
+        l1, l2 = theta_to_lambda(Ytil[t][:, None], Vtil[t], ng_jitter)
+        l1n, l2n = cvi_block_update(l1, l2, q_mu[t][:, None], q_var[t], dm[t][:, None], dS[t], beta)
+        th1, th2 = lambda_to_theta(l1n, l2n, ng_jitter)
+        Yn[t], Vn[t] = th1[:, 0], th2
+    return Yn, Vn
+
+
+def surrogate_ell(Ytil, Vtil, q_mu, q_var):
+    """ELL of the surrogate likelihood N(Y~ | u, V~) under q (elbos.py:181-188)."""
+    return float(sum(full_gaussian_ell(Ytil[t][:, None], Vtil[t], q_mu[t][:, None], q_var[t])
+                     for t in range(Ytil.shape[0])))
+
+
+def elbo(ell_data, ell_surrogate, lml_surrogate):
+    """elbos.py:189: ELBO = ELL - ELL_surrogate + ML_surrogate."""
+    return ell_data - ell_surrogate + lml_surrogate

@@ -34,7 +34,15 @@ SIGNATURES = {
         _ptr, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32,
         _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
         _ptr, _ptr, _ptr, _c_i32, _c_f64, _ptr, _ptr]),
+    "physs_cvi_natgrad_step_f64": (ctypes.c_int, [
+        _ptr, _c_i64, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64,
+        _c_f64, _c_i32, _ptr, _ptr, _ptr, _ptr, _c_f64, _c_f64, _ptr, _ptr, _ptr]),
+    "physs_cvi_ell_f64": (ctypes.c_int, [
+        _ptr, _c_i64, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64,
+        _c_f64, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr]),
 }
+
+LIK_GAUSS, LIK_POISSON_EXP, LIK_BERNOULLI_PROBIT, LIK_GIVEN = 0, 1, 2, 3
 
 _lib = None
 

@@ -122,4 +122,54 @@ int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int32_t d,
   return grp_smooth((cudaStream_t)stream, d, mo_eff, disc_mode, nblk, a);
 }
 
+static int cvi_dispatch(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik, bool update,
+                        const CviArgs& a) {
+  if (N < 0 || D < 1) return set_error(PHYSS_ERR_BAD_ARG, "cvi: bad sizes");
+  if (N == 0) return PHYSS_OK;
+  if (lik != 3 && (P < 1 || P > D)) return set_error(PHYSS_ERR_BAD_ARG, "cvi: need 1 <= P <= D");
+  if (!a.W && lik != 3 && P != D) return set_error(PHYSS_ERR_BAD_ARG, "cvi: W == NULL (identity) needs P == D");
+  if ((lik == 1 || lik == 2) && (a.K < 1 || !a.ghx || !a.ghw))
+    return set_error(PHYSS_ERR_BAD_ARG, "cvi: Gauss-Hermite likelihoods need K, ghx, ghw");
+  if (cvi_reg_supported(D, lik == 3 ? 1 : P)) return cvi_reg_run((cudaStream_t)stream, D, P, lik, update, a);
+  return cvi_grp_run((cudaStream_t)stream, D, P, lik, update, a);
+}
+
+int physs_cvi_natgrad_step_f64(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik,
+                               const double* Ytil, const double* Vtil,
+                               const double* q_mu, const double* q_var,
+                               const double* y, const double* W,
+                               const double* noise, int64_t noise_stride,
+                               double lik_param, int32_t K, const double* ghx, const double* ghw,
+                               const double* dm_in, const double* dS_in,
+                               double beta, double ng_jitter,
+                               double* Ytil_out, double* Vtil_out, double* ell_out) {
+  if (N > 0 && (!Ytil || !Vtil || !q_mu || !q_var || !Ytil_out || !Vtil_out))
+    return set_error(PHYSS_ERR_BAD_ARG, "cvi step: null required pointer");
+  if (lik == 3 && N > 0 && (!dm_in || !dS_in)) return set_error(PHYSS_ERR_BAD_ARG, "cvi step: LIK_GIVEN needs dm, dS");
+  if (lik != 3 && N > 0 && !y) return set_error(PHYSS_ERR_BAD_ARG, "cvi step: needs data y");
+  if (lik == 0 && N > 0 && !noise) return set_error(PHYSS_ERR_BAD_ARG, "cvi step: Gaussian likelihood needs noise");
+  CviArgs a{};
+  a.N = N; a.Yt = Ytil; a.Vt = Vtil; a.qm = q_mu; a.qS = q_var; a.y = y; a.W = W;
+  a.noise = noise; a.noise_stride = noise_stride; a.lik_param = lik_param; a.K = K; a.ghx = ghx; a.ghw = ghw;
+  a.dm_in = dm_in; a.dS_in = dS_in; a.beta = beta; a.ngj = ng_jitter;
+  a.Yn = Ytil_out; a.Vn = Vtil_out; a.ell = ell_out; a.dm_out = nullptr; a.dS_out = nullptr;
+  return cvi_dispatch(stream, N, D, P, lik, true, a);
+}
+
+int physs_cvi_ell_f64(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik,
+                      const double* q_mu, const double* q_var,
+                      const double* y, const double* W,
+                      const double* noise, int64_t noise_stride,
+                      double lik_param, int32_t K, const double* ghx, const double* ghw,
+                      double* ell_out, double* dm_out, double* dS_out) {
+  if (N > 0 && (!q_mu || !q_var || !y)) return set_error(PHYSS_ERR_BAD_ARG, "cvi ell: null required pointer");
+  if (lik < 0 || lik > 2) return set_error(PHYSS_ERR_BAD_ARG, "cvi ell: likelihood must be 0, 1 or 2");
+  if (lik == 0 && N > 0 && !noise) return set_error(PHYSS_ERR_BAD_ARG, "cvi ell: Gaussian likelihood needs noise");
+  CviArgs a{};
+  a.N = N; a.qm = q_mu; a.qS = q_var; a.y = y; a.W = W;
+  a.noise = noise; a.noise_stride = noise_stride; a.lik_param = lik_param; a.K = K; a.ghx = ghx; a.ghw = ghw;
+  a.ell = ell_out; a.dm_out = dm_out; a.dS_out = dS_out;
+  return cvi_dispatch(stream, N, D, P, lik, false, a);
+}
+
 }  // extern "C"

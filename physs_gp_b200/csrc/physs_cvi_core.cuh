@@ -1,0 +1,252 @@
+// physs_cvi_core.cuh -- per-site CVI algebra in registers (D <= 4), PHYSS_HD so that tests can check
+// it on the host (see physs_core.cuh for the convention).
+//
+// Reference semantics (paths relative to /root/reference/src/lib/stgp/):
+//   computation/natural_gradients/exponential_family_transforms.py:25-42,70-83  theta <-> lambda (ng_jitter)
+//   computation/natural_gradients/cvi_nat_grad.py:47-87                         cvi_block_update
+//   computation/elbos/expected_log_likelihoods.py:90-117                        block-Gaussian ELL
+//   computation/general.py:9-26                                                 Poisson / Bernoulli log-liks
+//   computation/integrals/samples.py:67-90                                      Gauss-Hermite (intent)
+// The reference differentiates the ELL with jax.grad (cvi_nat_grad.py:381-383); the closed forms are
+//   Gaussian:  dm = W^T R^-1 (y - W m),  dS = -1/2 W^T R^-1 W   (missing rows/cols dropped)
+//   scalar non-Gaussian site f = w.u:  dm = w E[l'(f)],  dS = w w^T 1/2 E[l''(f)]
+#pragma once
+#include "physs_core.cuh"
+
+namespace physs {
+
+enum CviLik { CVI_LIK_GAUSS = 0, CVI_LIK_POISSON_EXP = 1, CVI_LIK_BERNOULLI_PROBIT = 2, CVI_LIK_GIVEN = 3 };
+
+constexpr double kInvSqrt2Pi = 0.39894228040143267793994605993438;
+constexpr double kInvSqrt2 = 0.70710678118654752440084436210485;
+
+// l(f), l'(f), l''(f) of the scalar likelihoods (general.py:9-26).
+PHYSS_HD void poisson_exp_terms(double y, double f, double binsize, double& l, double& d1, double& d2) {
+  const double lam = exp(f) * binsize;
+  l = y * (f + log(binsize)) - lam - lgamma(y + 1.0);
+  d1 = y - lam;
+  d2 = -lam;
+}
+
+PHYSS_HD void bernoulli_probit_terms(double y, double f, double& l, double& d1, double& d2) {
+  const double p = 0.5 * erfc(-f * kInvSqrt2);
+  const double pdf = exp(-0.5 * f * f) * kInvSqrt2Pi;
+  const double a = p + 1e-5, b = 1.0 - p + 1e-5;   // the reference's +1e-5 inside both logs
+  l = y * log(a) + (1.0 - y) * log(b);
+  const double ra = 1.0 / a, rb = 1.0 / b;
+  d1 = y * pdf * ra - (1.0 - y) * pdf * rb;
+  const double dpdf = -f * pdf;
+  d2 = y * (dpdf * ra - pdf * pdf * ra * ra) - (1.0 - y) * (dpdf * rb + pdf * pdf * rb * rb);
+}
+
+// Inverse of an SPD matrix through its (jittered) Cholesky factor: Ainv = (A + jit I)^-1.
+template <int N>
+PHYSS_HD void spd_inverse(const double (&A)[N][N], double jit, double (&Ainv)[N][N]) {
+  double Aj[N][N], L[N][N], rd[N];
+  PHYSS_UNROLL
+  for (int i = 0; i < N; ++i) {
+    PHYSS_UNROLL
+    for (int j = 0; j < N; ++j) Aj[i][j] = A[i][j] + (i == j ? jit : 0.0);
+  }
+  chol_lower<N>(Aj, L, rd);
+  PHYSS_UNROLL
+  for (int c = 0; c < N; ++c) {
+    double x[N];
+    PHYSS_UNROLL
+    for (int i = 0; i < N; ++i) x[i] = (i == c) ? 1.0 : 0.0;
+    chol_solve_vec<N>(L, rd, x);
+    PHYSS_UNROLL
+    for (int i = 0; i < N; ++i) Ainv[i][c] = x[i];
+  }
+}
+
+// Block-Gaussian expected log-likelihood  log N(y | f_mu, R) - 1/2 tr(R^-1 f_var)  with NaN masking
+// (expected_log_likelihoods.py:90-117), and optionally R^-1 restricted to the observed entries.
+template <int P>
+PHYSS_HD double gauss_ell(const double (&y)[P], const double (&R)[P][P], const double (&fmu)[P],
+                          const double (&fvar)[P][P], double (&Rinv)[P][P], double (&err)[P]) {
+  bool obs[P];
+  int nobs = 0;
+  PHYSS_UNROLL
+  for (int a = 0; a < P; ++a) { obs[a] = !(y[a] != y[a]); nobs += obs[a] ? 1 : 0; }
+  double Rm[P][P], L[P][P], rd[P];
+  PHYSS_UNROLL
+  for (int a = 0; a < P; ++a) {
+    PHYSS_UNROLL
+    for (int b = 0; b < P; ++b) Rm[a][b] = (obs[a] && obs[b]) ? R[a][b] : (a == b ? 1.0 : 0.0);
+    err[a] = obs[a] ? (y[a] - fmu[a]) : 0.0;
+  }
+  chol_lower<P>(Rm, L, rd);
+  double logdet = 0.0;
+  PHYSS_UNROLL
+  for (int a = 0; a < P; ++a) logdet += log(L[a][a] * L[a][a]);
+  // R^-1 (masked-to-identity), then zero the missing rows/cols for the gradient
+  double tr = 0.0, mahal = 0.0;
+  PHYSS_UNROLL
+  for (int c = 0; c < P; ++c) {
+    double x[P];
+    PHYSS_UNROLL
+    for (int i = 0; i < P; ++i) x[i] = (i == c) ? 1.0 : 0.0;
+    chol_solve_vec<P>(L, rd, x);
+    PHYSS_UNROLL
+    for (int i = 0; i < P; ++i) {
+      const bool keep = obs[i] && obs[c];
+      Rinv[i][c] = keep ? x[i] : 0.0;
+      tr = fma(keep ? x[i] : 0.0, fvar[c][i], tr);
+    }
+  }
+  PHYSS_UNROLL
+  for (int a = 0; a < P; ++a) {
+    double t = 0.0;
+    PHYSS_UNROLL
+    for (int b = 0; b < P; ++b) t = fma(Rinv[a][b], err[b], t);
+    mahal = fma(err[a], t, mahal);
+  }
+  return -0.5 * ((double)nobs * kLog2Pi + logdet + mahal + tr);
+}
+
+// ELL and its gradients w.r.t. the site-block marginal (qm, qS) for P outputs f = W u.
+//   LIK == GAUSS: noise [P][P];  POISSON/BERNOULLI: independent scalar sites, K-point Gauss-Hermite
+//   (nodes ghx, weights ghw already divided by sqrt(pi)); lik_param = Poisson binsize.
+template <int D, int P, int LIK>
+PHYSS_HD double cvi_ell_grads(const double (&qm)[D], const double (&qS)[D][D], const double (&y)[P],
+                              const double (&W)[P][D], const double (&noise)[P][P], double lik_param,
+                              int K, const double* ghx, const double* ghw, double (&dm)[D],
+                              double (&dS)[D][D]) {
+  double fmu[P], WS[P][D];
+  PHYSS_UNROLL
+  for (int a = 0; a < P; ++a) {
+    double t = 0.0;
+    PHYSS_UNROLL
+    for (int k = 0; k < D; ++k) t = fma(W[a][k], qm[k], t);
+    fmu[a] = t;
+    PHYSS_UNROLL
+    for (int j = 0; j < D; ++j) {
+      double u = 0.0;
+      PHYSS_UNROLL
+      for (int k = 0; k < D; ++k) u = fma(W[a][k], qS[k][j], u);
+      WS[a][j] = u;
+    }
+  }
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    dm[i] = 0.0;
+    PHYSS_UNROLL
+    for (int j = 0; j < D; ++j) dS[i][j] = 0.0;
+  }
+  double ell = 0.0;
+  if (LIK == CVI_LIK_GAUSS) {
+    double fvar[P][P], Rinv[P][P], err[P];
+    PHYSS_UNROLL
+    for (int a = 0; a < P; ++a) {
+      PHYSS_UNROLL
+      for (int b = 0; b < P; ++b) {
+        double t = 0.0;
+        PHYSS_UNROLL
+        for (int k = 0; k < D; ++k) t = fma(WS[a][k], W[b][k], t);
+        fvar[a][b] = t;
+      }
+    }
+    ell = gauss_ell<P>(y, noise, fmu, fvar, Rinv, err);
+    double Re[P], RW[P][D];
+    PHYSS_UNROLL
+    for (int a = 0; a < P; ++a) {
+      double t = 0.0;
+      PHYSS_UNROLL
+      for (int b = 0; b < P; ++b) t = fma(Rinv[a][b], err[b], t);
+      Re[a] = t;
+      PHYSS_UNROLL
+      for (int j = 0; j < D; ++j) {
+        double u = 0.0;
+        PHYSS_UNROLL
+        for (int b = 0; b < P; ++b) u = fma(Rinv[a][b], W[b][j], u);
+        RW[a][j] = u;
+      }
+    }
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      double t = 0.0;
+      PHYSS_UNROLL
+      for (int a = 0; a < P; ++a) t = fma(W[a][i], Re[a], t);
+      dm[i] = t;
+      PHYSS_UNROLL
+      for (int j = 0; j < D; ++j) {
+        double u = 0.0;
+        PHYSS_UNROLL
+        for (int a = 0; a < P; ++a) u = fma(W[a][i], RW[a][j], u);
+        dS[i][j] = -0.5 * u;
+      }
+    }
+  } else {
+    PHYSS_UNROLL
+    for (int a = 0; a < P; ++a) {
+      double fv = 0.0;
+      PHYSS_UNROLL
+      for (int k = 0; k < D; ++k) fv = fma(WS[a][k], W[a][k], fv);
+      const bool obs = !(y[a] != y[a]);
+      const double ya = obs ? y[a] : 0.0;
+      const double sd = sqrt(2.0 * fv);
+      double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+      for (int q = 0; q < K; ++q) {
+        const double f = fma(sd, ghx[q], fmu[a]);
+        double l, d1, d2;
+        if (LIK == CVI_LIK_POISSON_EXP) poisson_exp_terms(ya, f, lik_param, l, d1, d2);
+        else bernoulli_probit_terms(ya, f, l, d1, d2);
+        e0 = fma(ghw[q], l, e0);
+        e1 = fma(ghw[q], d1, e1);
+        e2 = fma(ghw[q], d2, e2);
+      }
+      if (obs) {
+        ell += e0;
+        PHYSS_UNROLL
+        for (int i = 0; i < D; ++i) {
+          dm[i] = fma(W[a][i], e1, dm[i]);
+          PHYSS_UNROLL
+          for (int j = 0; j < D; ++j) dS[i][j] = fma(0.5 * e2 * W[a][i], W[a][j], dS[i][j]);
+        }
+      }
+    }
+  }
+  return ell;
+}
+
+// One natural-gradient site update (theta -> lambda, cvi_block_update, lambda -> theta).
+template <int D>
+PHYSS_HD void cvi_site_update(const double (&Yt)[D], const double (&Vt)[D][D], const double (&qm)[D],
+                              const double (&qS)[D][D], const double (&dm)[D],
+                              const double (&dS)[D][D], double beta, double ngj, double (&Yn)[D],
+                              double (&Vn)[D][D]) {
+  double Vinv[D][D];
+  spd_inverse<D>(Vt, ngj, Vinv);                 // (V~ + ng_jitter I)^-1
+  double l1[D], l2[D][D];
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    double t = 0.0;
+    PHYSS_UNROLL
+    for (int k = 0; k < D; ++k) t = fma(Vinv[i][k], Yt[k], t);
+    // grad_1 = dm - 2 dS m
+    double g = dm[i];
+    PHYSS_UNROLL
+    for (int k = 0; k < D; ++k) g = fma(-2.0 * dS[i][k], qm[k], g);
+    l1[i] = (1.0 - beta) * t + beta * g;
+    PHYSS_UNROLL
+    for (int j = 0; j < D; ++j) l2[i][j] = (1.0 - beta) * (-0.5 * Vinv[i][j]) + beta * dS[i][j];
+  }
+  (void)qS;
+  double Pm[D][D];
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    PHYSS_UNROLL
+    for (int j = 0; j < D; ++j) Pm[i][j] = -2.0 * l2[i][j];
+  }
+  spd_inverse<D>(Pm, ngj, Vn);                   // V~' = (-2 lambda_2 + ng_jitter I)^-1
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    double t = 0.0;
+    PHYSS_UNROLL
+    for (int k = 0; k < D; ++k) t = fma(Vn[i][k], l1[k], t);
+    Yn[i] = t;
+  }
+}
+
+}  // namespace physs

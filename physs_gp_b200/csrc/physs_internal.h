@@ -46,6 +46,26 @@ int seq_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_id
                const SeqFilterArgs& a);
 int seq_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
 
+struct CviArgs {
+  int64_t N;
+  const double* Yt; const double* Vt;       // sites  [N,D], [N,D,D]
+  const double* qm; const double* qS;       // posterior marginals of the site blocks
+  const double* y;                          // data [N,P], NaN = missing
+  const double* W;                          // [P,D] shared, NULL = identity
+  const double* noise; int64_t noise_stride;  // Gaussian noise [.,P,P]
+  double lik_param; int K; const double* ghx; const double* ghw;
+  const double* dm_in; const double* dS_in;
+  double beta, ngj;
+  double* Yn; double* Vn;
+  double* ell; double* dm_out; double* dS_out;
+};
+
+// physs_cvi.cu: one thread per site block (D <= 4)
+bool cvi_reg_supported(int D, int P);
+int cvi_reg_run(cudaStream_t st, int D, int P, int lik, bool update, const CviArgs& a);
+// physs_cvi_grp.cu: one lane group per site block (D > 4)
+int cvi_grp_run(cudaStream_t st, int D, int P, int lik, bool update, const CviArgs& a);
+
 // physs_grp.cu: one lane group per series, shared-memory resident, runtime (d, m)
 bool grp_supported(int d, int m);
 int grp_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity,

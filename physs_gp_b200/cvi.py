@@ -1,0 +1,207 @@
+"""CVI natural-gradient step and ELBO on the B200 kernels -- host-side mirror of
+
+  stgp/approximate_posteriors/conjugate_gaussian_approximate_posterior.py:174-246  FullConjugateGaussian
+  stgp/models/vgp.py:148-157,274-282              VGP.get_objective / natural_gradient_update
+  stgp/computation/natural_gradients/cvi_nat_grad.py:346-410   natural_gradients(FullConjugateGaussian)
+  stgp/computation/elbos/elbos.py:163-194          elbo(FullConjugateGaussian)
+
+The sites (Y~ [T, D], V~ [T, D, D]) are literally the data and the BlockDiagonalGaussian noise of a
+surrogate `SDE_GP`, exactly as in the reference; one CVI iteration is
+    q_mu, q_var = surrogate.posterior_blocks()          (filter + smoother kernels)
+    sites <- physs_cvi_natgrad_step_f64(sites, q_mu, q_var, data, likelihood, beta)
+and the ELBO is  sum ELL(data) - sum ELL(surrogate) + lml(surrogate).
+A leading batch axis B (independent blocks / series) is carried throughout.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from . import settings
+from .data import TemporalData
+from .likelihood import BlockDiagonalGaussian
+from .models import SDE_GP
+
+
+# --------------------------------------------------------------------------- likelihood descriptions
+class GaussianLik:
+    """Gaussian likelihood on f = W u with noise covariance [P, P] (shared) -- likelihood/gaussian.py."""
+    kind = _lib.LIK_GAUSS
+
+    def __init__(self, noise):
+        self.noise = np.atleast_2d(np.asarray(noise, np.float64))
+        self.param = 0.0
+
+
+class PoissonLik:
+    """likelihood/poisson.py:9-28 (exp link)."""
+    kind = _lib.LIK_POISSON_EXP
+
+    def __init__(self, binsize=1.0):
+        self.param = float(binsize)
+        self.noise = None
+
+
+class BernoulliLik:
+    """likelihood/bernoulli.py:11-25 (probit link, +1e-5 inside the logs)."""
+    kind = _lib.LIK_BERNOULLI_PROBIT
+
+    def __init__(self):
+        self.param = 0.0
+        self.noise = None
+
+
+_GH_CACHE = {}
+
+
+def gauss_hermite(K, dev):
+    key = (K, str(dev))
+    if key not in _GH_CACHE:
+        x, w = np.polynomial.hermite.hermgauss(K)
+        _GH_CACHE[key] = (torch.as_tensor(x, device=dev), torch.as_tensor(w / np.sqrt(np.pi), device=dev))
+    return _GH_CACHE[key]
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _c(t):
+    assert t.is_cuda and t.dtype == torch.float64
+    return t.contiguous()
+
+
+def natgrad_step(Ytil, Vtil, q_mu, q_var, y, W, lik, beta, ng_jitter=None, K=20, dm=None, dS=None,
+                 want_ell=False, out=None, stream=None):
+    """Raw op: all tensors are CUDA float64 with the site blocks flattened to N = prod(leading dims).
+    Ytil [..., D], Vtil [..., D, D], q_mu, q_var alike; y [..., P]; W [P, D] or None.
+    Returns (Ytil_new, Vtil_new[, ell [...]])."""
+    lib = _lib.load()
+    Ytil, Vtil, q_mu, q_var = _c(Ytil), _c(Vtil), _c(q_mu), _c(q_var)
+    D = Ytil.shape[-1]
+    lead = Ytil.shape[:-1]
+    N = int(np.prod(lead))
+    dev = Ytil.device
+    given = dm is not None
+    kind = _lib.LIK_GIVEN if given else lik.kind
+    P = 1 if given else y.shape[-1]
+    yv = None if given else _c(y)
+    Wv = None if W is None else _c(W)
+    noise = None
+    nstride = 0
+    if not given and lik.kind == _lib.LIK_GAUSS:
+        noise = torch.as_tensor(lik.noise, device=dev) if not isinstance(lik.noise, torch.Tensor) else lik.noise
+        noise = _c(noise)
+        nstride = 0 if noise.dim() == 2 else P * P
+    ghx = ghw = None
+    if kind in (_lib.LIK_POISSON_EXP, _lib.LIK_BERNOULLI_PROBIT):
+        ghx, ghw = gauss_hermite(K, dev)
+    if out is None:
+        Yn, Vn = torch.empty_like(Ytil), torch.empty_like(Vtil)
+    else:
+        Yn, Vn = out
+    ell = torch.empty(lead, dtype=torch.float64, device=dev) if want_ell else None
+    ngj = settings.ng_jitter if ng_jitter is None else ng_jitter
+    s = stream if stream is not None else torch.cuda.current_stream()
+    with torch.cuda.device(dev):
+        st = lib.physs_cvi_natgrad_step_f64(
+            s.cuda_stream, N, D, P, kind, Ytil.data_ptr(), Vtil.data_ptr(), q_mu.data_ptr(), q_var.data_ptr(),
+            _ptr(yv), _ptr(Wv), _ptr(noise), nstride, float(0.0 if given else lik.param), int(K),
+            _ptr(ghx), _ptr(ghw), _ptr(_c(dm) if given else None), _ptr(_c(dS) if given else None),
+            float(beta), float(ngj), Yn.data_ptr(), Vn.data_ptr(), _ptr(ell))
+    _lib.check(st, "physs_cvi_natgrad_step_f64")
+    return (Yn, Vn, ell) if want_ell else (Yn, Vn)
+
+
+def expected_log_likelihood(q_mu, q_var, y, W, lik, K=20, noise=None, want_grads=False, stream=None):
+    """Raw op: per-block ELL [...], optionally with dELL/dm [..., D] and dELL/dS [..., D, D].
+    `noise` overrides lik.noise with a per-block tensor [..., P, P] (used for the surrogate ELL)."""
+    lib = _lib.load()
+    q_mu, q_var, y = _c(q_mu), _c(q_var), _c(y)
+    D, P = q_mu.shape[-1], y.shape[-1]
+    lead = q_mu.shape[:-1]
+    N = int(np.prod(lead))
+    dev = q_mu.device
+    Wv = None if W is None else _c(W)
+    nz, nstride = None, 0
+    if lik.kind == _lib.LIK_GAUSS:
+        nz = noise if noise is not None else torch.as_tensor(lik.noise, device=dev)
+        nz = _c(nz)
+        nstride = 0 if nz.dim() == 2 else P * P
+    ghx = ghw = None
+    if lik.kind != _lib.LIK_GAUSS:
+        ghx, ghw = gauss_hermite(K, dev)
+    ell = torch.empty(lead, dtype=torch.float64, device=dev)
+    dm = torch.empty(lead + (D,), dtype=torch.float64, device=dev) if want_grads else None
+    dS = torch.empty(lead + (D, D), dtype=torch.float64, device=dev) if want_grads else None
+    s = stream if stream is not None else torch.cuda.current_stream()
+    with torch.cuda.device(dev):
+        st = lib.physs_cvi_ell_f64(s.cuda_stream, N, D, P, lik.kind, q_mu.data_ptr(), q_var.data_ptr(),
+                                   y.data_ptr(), _ptr(Wv), _ptr(nz), nstride, float(lik.param), int(K),
+                                   _ptr(ghx), _ptr(ghw), ell.data_ptr(), _ptr(dm), _ptr(dS))
+    _lib.check(st, "physs_cvi_ell_f64")
+    return (ell, dm, dS) if want_grads else ell
+
+
+# --------------------------------------------------------------------------- reference-shaped objects
+class FullConjugateGaussian:
+    """q(u) prop. to N(Y~ | u, V~) p(u): sites stored as the surrogate SDE_GP's data and noise
+    (conjugate_gaussian_approximate_posterior.py:174-246).  Reference initialisation: Y~ = 1e-5,
+    V~ = I (:209-218)."""
+
+    def __init__(self, X_time, surrogate_prior, block_size, B=1, Y_tilde=None, V_tilde=None, device=None):
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        T = len(X_time)
+        D = block_size
+        self.block_size = D
+        self.X_time = X_time
+        self.Y_tilde = (torch.full((B, T, D), 1e-5, dtype=torch.float64, device=dev) if Y_tilde is None
+                        else torch.as_tensor(Y_tilde, dtype=torch.float64).to(dev).reshape(B, T, D).clone())
+        self.V_tilde = (torch.eye(D, dtype=torch.float64, device=dev).expand(B, T, D, D).contiguous()
+                        if V_tilde is None
+                        else torch.as_tensor(V_tilde, dtype=torch.float64).to(dev).reshape(B, T, D, D).clone())
+        self.prior = surrogate_prior
+
+    @property
+    def surrogate(self):
+        data = TemporalData(self.X_time, self.Y_tilde[..., None])          # [B, T, P=D, Ns=1]
+        return SDE_GP(data, self.prior, BlockDiagonalGaussian(self.V_tilde))
+
+
+class VGP:
+    """models/vgp.py: variational GP with a CVI approximate posterior.
+    data Y [B, T, P] (NaN = missing); W [P, D] maps a site block to the likelihood inputs
+    (None = identity)."""
+
+    def __init__(self, Y, likelihood, approximate_posterior, W=None, ell_quad_points=20):
+        q = approximate_posterior
+        dev = q.Y_tilde.device
+        self.q = q
+        self.Y = torch.as_tensor(Y, dtype=torch.float64).to(dev)
+        if self.Y.dim() == 2:
+            self.Y = self.Y[None]
+        self.lik = likelihood
+        self.W = None if W is None else torch.as_tensor(W, dtype=torch.float64).to(dev)
+        self.K = ell_quad_points
+
+    def natural_gradient_update(self, lr, enforce_psd_type=None, prediction_samples=None):
+        """vgp.py:274-282 -> cvi_nat_grad.py:508-515,346-410 -> cvi_parameterisations.py:63-93."""
+        if enforce_psd_type is not None:
+            raise NotImplementedError("only enforce_psd_type=None is implemented on the b200 path")
+        q = self.q
+        q_mu, q_var = q.surrogate.posterior_blocks()               # [B,T,D,1], [B,T,1,D,D]
+        q_mu, q_var = q_mu[..., 0], q_var[..., 0, :, :]
+        natgrad_step(q.Y_tilde, q.V_tilde, q_mu, q_var, self.Y, self.W, self.lik, lr, K=self.K,
+                     out=(q.Y_tilde, q.V_tilde))
+
+    def elbo(self):
+        """elbos.py:163-194; returns one ELBO per batch member [B]."""
+        q = self.q
+        lml, q_mu, q_var = q.surrogate.posterior_blocks(return_lml=True)
+        q_mu, q_var = q_mu[..., 0], q_var[..., 0, :, :]
+        ell = expected_log_likelihood(q_mu, q_var, self.Y, self.W, self.lik, K=self.K)
+        sur = GaussianLik(np.eye(q.block_size))
+        ell_s = expected_log_likelihood(q_mu, q_var, q.Y_tilde, None, sur, noise=q.V_tilde)
+        return ell.sum(dim=-1) - ell_s.sum(dim=-1) + lml
+
+    def get_objective(self):
+        return -self.elbo()

@@ -1,0 +1,165 @@
+"""-m gpu parity tests for the CVI kernels (site update, expected log-likelihoods, ELBO) against
+oracle/cvi.py, through physs_gp_b200.cvi -> C ABI.  Tolerance 1e-9 relative (array scale) for the
+deterministic pieces; the site update inverts V~ + ng_jitter I whose condition number enters the
+achievable agreement, so its tolerance is 1e-9 * cond (stated per test)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cvi as ocvi
+from oracle import filters as ofilters
+from oracle import sde as osde
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def _dev(x):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64).cuda()
+
+
+def _oracle_grads(lik_kind, y, W, noise, q_mu, q_var, binsize, K):
+    D = q_mu.shape[0]
+    Wm = np.eye(D) if W is None else W
+    if lik_kind == "gauss":
+        return ocvi.gaussian_ell_and_grads(y, noise, W, q_mu, q_var)
+    ell, dm, dS = 0.0, np.zeros(D), np.zeros((D, D))
+    for p in range(Wm.shape[0]):
+        w = Wm[p]
+        e0, e1, e2 = ocvi.gh_ell_and_grads(y[p], w @ q_mu, w @ q_var @ w, lik_kind, K=K, binsize=binsize)
+        ell += e0
+        dm += w * e1
+        dS += np.outer(w, w) * e2
+    return ell, dm, dS
+
+
+@pytest.mark.parametrize("D,P", [(1, 1), (2, 1), (2, 2), (3, 2), (4, 1), (4, 4), (6, 2), (8, 8), (12, 3)])
+@pytest.mark.parametrize("lik_kind", ["gauss", "poisson", "bernoulli"])
+def test_site_step_and_ell_match_oracle(cuda_device, D, P, lik_kind):
+    from physs_gp_b200 import cvi
+    rng = np.random.default_rng(100 * D + 10 * P + len(lik_kind))
+    N = 67
+    W = None if P == D else rng.normal(size=(P, D)) * 0.7
+    Ytil = rng.normal(size=(N, D))
+    Vtil = synth.random_spd(rng, (N,), D, base=0.5, spread=0.4)
+    q_mu = rng.normal(size=(N, D)) * 0.5
+    q_var = synth.random_spd(rng, (N,), D, base=0.05, spread=0.15)
+    if lik_kind == "gauss":
+        y = rng.normal(size=(N, P))
+        noise = synth.random_spd(rng, (), P, base=0.2, spread=0.3)
+        lik = cvi.GaussianLik(noise)
+    elif lik_kind == "poisson":
+        y = rng.integers(0, 6, size=(N, P)).astype(float)
+        noise = None
+        lik = cvi.PoissonLik(0.8)
+    else:
+        y = rng.integers(0, 2, size=(N, P)).astype(float)
+        noise = None
+        lik = cvi.BernoulliLik()
+    y[rng.uniform(size=y.shape) < 0.15] = np.nan
+    beta, ngj, K = 0.3, 1e-7, 20
+    Yn, Vn, ell = cvi.natgrad_step(_dev(Ytil), _dev(Vtil), _dev(q_mu), _dev(q_var), _dev(y),
+                                   None if W is None else _dev(W), lik, beta, ng_jitter=ngj, K=K, want_ell=True)
+    ell2, dm_g, dS_g = cvi.expected_log_likelihood(_dev(q_mu), _dev(q_var), _dev(y),
+                                                   None if W is None else _dev(W), lik, K=K, want_grads=True)
+    torch.cuda.synchronize()
+    ell_o, dm_o, dS_o = np.zeros(N), np.zeros((N, D)), np.zeros((N, D, D))
+    for n in range(N):
+        ell_o[n], dm_o[n], dS_o[n] = _oracle_grads(lik_kind, y[n], W, noise, q_mu[n], q_var[n], 0.8, K)
+    Yo, Vo = ocvi.cvi_step(Ytil, Vtil, q_mu, q_var, dm_o, dS_o, beta, ngj)
+    assert rel(ell, ell_o) < TOL and rel(ell2, ell_o) < TOL
+    assert rel(dm_g, dm_o) < TOL and rel(dS_g, dS_o) < TOL
+    cond = max(np.linalg.cond(Vtil[n]) for n in range(N))
+    assert rel(Vn, Vo) < TOL * max(1.0, cond) and rel(Yn, Yo) < TOL * max(1.0, cond)
+    # caller-supplied gradients (the route a jax.grad'ed Monte-Carlo ELL takes)
+    Yg, Vg = cvi.natgrad_step(_dev(Ytil), _dev(Vtil), _dev(q_mu), _dev(q_var), None, None, None, beta,
+                              ng_jitter=ngj, dm=_dev(dm_o), dS=_dev(dS_o))
+    assert rel(Vg, Vo) < TOL * max(1.0, cond) and rel(Yg, Yo) < TOL * max(1.0, cond)
+
+
+def test_surrogate_ell_matches_oracle(cuda_device):
+    from physs_gp_b200 import cvi
+    rng = np.random.default_rng(5)
+    N, D = 41, 3
+    Ytil = rng.normal(size=(N, D)); Vtil = synth.random_spd(rng, (N,), D, base=0.5)
+    q_mu = rng.normal(size=(N, D)); q_var = synth.random_spd(rng, (N,), D, base=0.05)
+    ell = cvi.expected_log_likelihood(_dev(q_mu), _dev(q_var), _dev(Ytil), None, cvi.GaussianLik(np.eye(D)),
+                                      noise=_dev(Vtil))
+    ref = np.array([ocvi.full_gaussian_ell(Ytil[n][:, None], Vtil[n], q_mu[n][:, None], q_var[n]) for n in range(N)])
+    assert rel(ell, ref) < TOL
+
+
+@pytest.mark.parametrize("kind", ["m32_f", "m52_fullstate"])
+def test_vgp_cvi_iterations_match_oracle(cuda_device, kind):
+    """Three full CVI iterations (filter + smoother + site update) and the ELBO, B = 3 blocks, against
+    the numpy oracle run block by block."""
+    from physs_gp_b200 import cvi, sdes
+    rng = np.random.default_rng(8)
+    B, T = 3, 80
+    t = synth.time_grid(T, 0.1, rng)
+    if kind == "m32_f":
+        s, D, fso = 2, 1, False
+        W = None
+    else:
+        s, D, fso = 3, 3, True
+        W = np.array([[1.0, 0.0, 0.0]])
+    ls = synth.log_uniform(rng, 0.5, 2.0, (B, 1)); var = synth.log_uniform(rng, 0.5, 2.0, (B, 1))
+    prior = sdes.BatchedMaternSDE(s, ls, var, full_state_obs=fso)
+    Y = rng.integers(0, 5, size=(B, T, 1)).astype(float)
+    Y[rng.uniform(size=Y.shape) < 0.1] = np.nan
+    q = cvi.FullConjugateGaussian(t, prior, D, B=B)
+    model = cvi.VGP(Y, cvi.PoissonLik(1.0), q, W=W, ell_quad_points=20)
+    beta = 0.3
+    for _ in range(3):
+        model.natural_gradient_update(beta)
+    elbo = model.elbo()
+    torch.cuda.synchronize()
+    okind = {2: osde.Matern32, 3: osde.Matern52}[s]
+    for b in range(B):
+        k = okind(ls[b, 0], var[b, 0])
+        op = osde.LTI_SDE_Full_State_Obs([k]) if fso else osde.LTI_SDE([k])
+        Yt = 1e-5 * np.ones((T, D)); Vt = np.tile(np.eye(D), [T, 1, 1])
+        Wm = np.eye(D) if W is None else W
+        for _ in range(3):
+            _, qm, qv = ofilters.filter_and_smooth(op, t, Yt, Vt)
+            dm = np.zeros((T, D)); dS = np.zeros((T, D, D))
+            for i in range(T):
+                _, dm[i], dS[i] = _oracle_grads("poisson", Y[b, i], Wm, None, qm[i][:, 0], qv[i], 1.0, 20)
+            Yt, Vt = ocvi.cvi_step(Yt, Vt, qm[:, :, 0], qv, dm, dS, beta)
+        lml, qm, qv = ofilters.filter_and_smooth(op, t, Yt, Vt)
+        ell = sum(_oracle_grads("poisson", Y[b, i], Wm, None, qm[i][:, 0], qv[i], 1.0, 20)[0] for i in range(T))
+        ell_s = ocvi.surrogate_ell(Yt, Vt, qm[:, :, 0], qv)
+        ref = ocvi.elbo(ell, ell_s, lml)
+        tol = 1e-7 if fso else TOL      # full-state sites: V~ has 1/ng_jitter entries (cond ~ 1e7)
+        assert rel(q.Y_tilde[b], Yt) < tol and rel(q.V_tilde[b], Vt) < tol
+        assert abs(float(elbo[b]) - ref) < tol * abs(ref)
+
+
+def test_cvi_gaussian_fixed_point_on_gpu(cuda_device):
+    """beta = 1 with a Gaussian likelihood: one step gives (Y~, V~) = (y, R) up to O(ng_jitter), and the
+    ELBO equals the exact log marginal likelihood."""
+    from physs_gp_b200 import cvi, data, filters, sdes, settings
+    rng = np.random.default_rng(9)
+    B, T = 4, 200
+    t = synth.time_grid(T, 0.1, rng)
+    prior = sdes.BatchedMaternSDE(2, synth.log_uniform(rng, 0.5, 2.0, (B, 1)))
+    Y = synth.noisy_series(B, T, 1, rng, 0.0)
+    q = cvi.FullConjugateGaussian(t, prior, 1, B=B)
+    model = cvi.VGP(Y, cvi.GaussianLik([[0.3]]), q)
+    old = settings.ng_jitter
+    settings.ng_jitter = 1e-10
+    try:
+        model.natural_gradient_update(1.0)
+        elbo = model.elbo()
+    finally:
+        settings.ng_jitter = old
+    assert float((q.Y_tilde[..., 0] - torch.as_tensor(Y[..., 0]).cuda()).abs().max()) < 1e-7
+    assert float((q.V_tilde - 0.3).abs().max()) < 1e-7
+    lml, _ = filters.filter_loop(data.TemporalData(t, Y[..., None]), prior, R=np.full([1, 1, 1, 1], 0.3))
+    assert float(((elbo - lml) / lml).abs().max()) < 1e-6

@@ -1,0 +1,87 @@
+"""Derived pins for the CVI oracle."""
+import numpy as np
+
+from oracle import cvi, filters, sde
+from tests import synth
+
+
+def test_theta_lambda_round_trip():
+    rng = np.random.default_rng(0)
+    D = 4
+    V = synth.random_spd(rng, (), D)
+    Y = rng.normal(size=(D, 1))
+    l1, l2 = cvi.theta_to_lambda(Y, V, ng_jitter=0.0)
+    t1, t2 = cvi.lambda_to_theta(l1, l2, ng_jitter=0.0)
+    np.testing.assert_allclose(t1, Y, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(t2, V, rtol=1e-10, atol=1e-12)
+
+
+def test_gaussian_ell_gradients_match_finite_differences():
+    rng = np.random.default_rng(1)
+    D, P = 4, 2
+    W = rng.normal(size=(P, D))
+    noise = synth.random_spd(rng, (), P)
+    q_mu = rng.normal(size=D)
+    q_var = synth.random_spd(rng, (), D)
+    for Y in (rng.normal(size=P), np.array([0.3, np.nan])):
+        ell, dm, dS = cvi.gaussian_ell_and_grads(Y, noise, W, q_mu, q_var)
+        eps = 1e-6
+        for i in range(D):
+            e = np.zeros(D); e[i] = eps
+            fd = (cvi.gaussian_ell_and_grads(Y, noise, W, q_mu + e, q_var)[0]
+                  - cvi.gaussian_ell_and_grads(Y, noise, W, q_mu - e, q_var)[0]) / (2 * eps)
+            assert abs(fd - dm[i]) < 1e-6 * max(1.0, abs(dm[i]))
+        for i in range(D):
+            for j in range(D):
+                E = np.zeros((D, D)); E[i, j] = eps
+                fd = (cvi.gaussian_ell_and_grads(Y, noise, W, q_mu, q_var + E)[0]
+                      - cvi.gaussian_ell_and_grads(Y, noise, W, q_mu, q_var - E)[0]) / (2 * eps)
+                assert abs(fd - dS[i, j]) < 1e-6 * max(1.0, abs(dS[i, j]))
+
+
+def test_gh_matches_poisson_closed_form_and_fd():
+    rng = np.random.default_rng(2)
+    for _ in range(5):
+        y = float(rng.integers(0, 8)); m = rng.normal() * 0.5; v = rng.uniform(0.05, 0.6)
+        ell, d1, d2 = cvi.gh_ell_and_grads(y, m, v, "poisson", K=20, binsize=0.7)
+        cf = cvi.poisson_ell_closed_form(y, m, v, 0.7)
+        assert abs(ell - cf) < 1e-10 * max(1.0, abs(cf))
+        eps = 1e-5
+        fd_m = (cvi.poisson_ell_closed_form(y, m + eps, v, 0.7) - cvi.poisson_ell_closed_form(y, m - eps, v, 0.7)) / (2 * eps)
+        fd_v = (cvi.poisson_ell_closed_form(y, m, v + eps, 0.7) - cvi.poisson_ell_closed_form(y, m, v - eps, 0.7)) / (2 * eps)
+        assert abs(d1 - fd_m) < 1e-7 and abs(d2 - fd_v) < 1e-7
+
+
+def test_gh_bernoulli_converges_with_order():
+    y, m, v = 1.0, 0.3, 0.5
+    a = cvi.gh_ell_and_grads(y, m, v, "bernoulli", K=20)
+    b = cvi.gh_ell_and_grads(y, m, v, "bernoulli", K=64)
+    assert max(abs(x - z) for x, z in zip(a, b)) < 1e-6
+
+
+def test_cvi_gaussian_fixed_point_and_elbo_equals_lml():
+    """With a Gaussian likelihood and beta = 1 one CVI step returns (Y~, V~) = (y, R) up to
+    O(ng_jitter), and the CVI ELBO then equals the exact marginal likelihood to the same order
+    (cvi_nat_grad.py:62-73, elbos.py:163-194)."""
+    rng = np.random.default_rng(3)
+    T = 60
+    k = sde.Matern32(1.0, 1.2)
+    prior = sde.LTI_SDE([k])                      # sites over f only: D = m = 1
+    t = synth.time_grid(T, 0.1, rng)
+    y = rng.normal(size=(T, 1))
+    Rn = 0.3
+    Ytil = 1e-5 * np.ones((T, 1))                 # reference init (conjugate_gaussian_approximate_posterior.py:209-218)
+    Vtil = np.tile(np.eye(1), [T, 1, 1])
+    _, q_mu, q_var = filters.filter_and_smooth(prior, t, Ytil, Vtil)
+    dm = np.empty((T, 1)); dS = np.empty((T, 1, 1))
+    for i in range(T):
+        _, dm[i], dS[i] = cvi.gaussian_ell_and_grads(y[i], np.array([[Rn]]), None, q_mu[i][:, 0], q_var[i])
+    Yn, Vn = cvi.cvi_step(Ytil, Vtil, q_mu[:, :, 0], q_var, dm, dS, beta=1.0, ng_jitter=1e-9)
+    np.testing.assert_allclose(Yn, y, rtol=0, atol=1e-7)
+    np.testing.assert_allclose(Vn[:, 0, 0], Rn, rtol=0, atol=1e-7)
+    # ELBO at the fixed point
+    lml_s, q_mu2, q_var2 = filters.filter_and_smooth(prior, t, Yn, Vn, jitter=0.0)
+    ell = sum(cvi.gaussian_ell_and_grads(y[i], np.array([[Rn]]), None, q_mu2[i][:, 0], q_var2[i])[0] for i in range(T))
+    ell_s = cvi.surrogate_ell(Yn, Vn, q_mu2[:, :, 0], q_var2)
+    exact, _, _, _ = filters.filter_sequential(prior, t, y, np.tile(np.array([[Rn]]), [T, 1, 1]), jitter=0.0)
+    assert abs(cvi.elbo(ell, ell_s, lml_s) - exact) < 1e-5 * abs(exact)
