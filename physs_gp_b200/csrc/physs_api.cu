@@ -70,7 +70,7 @@ int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int32_t d, int32_t m
   } else {
     return set_error(PHYSS_ERR_BAD_ARG, "filter: unknown disc_mode");
   }
-  SeqFilterArgs a;
+  SeqFilterArgs a{};
   a.B = B; a.T = T;
   a.A = A; a.A_bs = A_bstride; a.Q = Q; a.Q_bs = Q_bstride;
   a.lam = lam; a.lam_bs = lam_bstride; a.dt = dt; a.dt_bs = dt_bstride;
@@ -110,7 +110,7 @@ int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int32_t d,
   } else {
     return set_error(PHYSS_ERR_BAD_ARG, "smoother: unknown disc_mode");
   }
-  SeqSmoothArgs a;
+  SeqSmoothArgs a{};
   a.B = B; a.T = T;
   a.A = A; a.A_bs = A_bstride; a.Q = Q; a.Q_bs = Q_bstride;
   a.lam = lam; a.lam_bs = lam_bstride; a.dt = dt; a.dt_bs = dt_bstride;

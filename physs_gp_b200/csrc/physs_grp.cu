@@ -55,18 +55,57 @@ static GrpLayout make_layout(int d, int m, int mo, int nblk, bool given, bool sm
 }
 
 // ------------------------------------------------------------------------------------------ filter
+// relative agreement of the shared-memory (m, P) with the stored global one (chunk-mode fix-up);
+// evaluated redundantly by every lane of the group
+__device__ __forceinline__ bool grp_agrees(const double* mv, const double* P, int ld, int d,
+                                           const double* om, const double* oP, double delta) {
+  double dP = 0.0, sP = 0.0, dm = 0.0;
+  for (int i = 0; i < d; ++i) {
+    dm = fmax(dm, fabs(mv[i] - om[i]));
+    for (int j = 0; j < d; ++j) {
+      const double o = oP[i * d + j];
+      dP = fmax(dP, fabs(P[i * ld + j] - o));
+      sP = fmax(sP, fabs(o));
+    }
+  }
+  return (dP <= delta * sP) && (dm * dm <= delta * delta * sP);
+}
+
+// (series, chunk) owned by a group.  Plain mode: chunk 0 = the whole series.
+struct GrpWork {
+  int64_t b, c, v, t0, T, Tfull;
+  bool active, chunked;
+};
+
+template <typename Args>
+__device__ __forceinline__ GrpWork grp_work(const Args& p, int64_t gid) {
+  GrpWork w;
+  w.chunked = p.nchunk > 0;
+  const int64_t per = w.chunked ? p.chunk_count : 1;
+  const int64_t n = p.B * per;
+  w.active = gid < n;
+  const int64_t g = w.active ? gid : n - 1;     // inactive groups shadow the last one (no stores)
+  w.b = g / per;
+  w.c = w.chunked ? p.chunk_first + g % per : 0;
+  w.v = w.chunked ? w.b * p.nchunk + w.c : w.b;
+  w.t0 = w.chunked ? w.c * p.chunk_len : 0;
+  w.Tfull = p.T;
+  w.T = w.chunked ? ((p.chunk_len < w.Tfull - w.t0) ? p.chunk_len : (w.Tfull - w.t0)) : w.Tfull;
+  return w;
+}
+
 template <int G, bool GIVEN>
 __global__ void grp_filter_kernel(const SeqFilterArgs p, const GrpLayout L, const bool hid) {
   extern __shared__ __align__(16) double smem[];
   const int groups_per_block = blockDim.x / G;
   const int g_in_block = threadIdx.x / G;
-  const int64_t b = (int64_t)blockIdx.x * groups_per_block + g_in_block;
-  const bool active = b < p.B;
-  const int64_t bb = active ? b : p.B - 1;   // inactive groups shadow the last series (no stores)
+  const GrpWork wk = grp_work(p, (int64_t)blockIdx.x * groups_per_block + g_in_block);
+  const bool active = wk.active, chunked = wk.chunked;
+  const int64_t bb = wk.b, b = wk.b, vs = wk.v, t0 = wk.t0, Tfull = wk.Tfull;
   const int gl = Lanes<G>::gl();
   double* sm = smem + (size_t)g_in_block * L.total;
   const int d = L.d, m = L.m, ld = L.ld, ldm = L.ldm, s = L.s;
-  const int64_t T = p.T;
+  const int64_t T = wk.T;
 
   double* P = sm + L.P; double* A = sm + L.A; double* Qm = sm + L.Qm;
   double* W1 = sm + L.W1; double* W2 = sm + L.W2;
@@ -74,20 +113,28 @@ __global__ void grp_filter_kernel(const SeqFilterArgs p, const GrpLayout L, cons
   double* mv_ = sm + L.vm; double* mp = sm + L.vmp; double* v = sm + L.vv; double* w = sm + L.vw;
   double* rd = sm + L.vrd; double* lam = sm + L.vlam;
 
-  g2s<G>(P, ld, p.P0 + bb * p.P0_bs, d, d);
-  for (int i = gl; i < d; i += G) mv_[i] = p.m0[bb * p.m0_bs + i];
+  if (chunked && p.fixup) {
+    g2s<G>(P, ld, p.bnd_P + vs * d * d, d, d);
+    for (int i = gl; i < d; i += G) mv_[i] = p.bnd_m[vs * d + i];
+  } else {
+    g2s<G>(P, ld, p.P0 + bb * p.P0_bs, d, d);
+    for (int i = gl; i < d; i += G) mv_[i] = p.m0[bb * p.m0_bs + i];
+  }
   if (!GIVEN) {
     g2s<G>(Qm, ld, p.Pinf + bb * p.Pinf_bs, d, d);
     for (int i = gl; i < L.nblk; i += G) lam[i] = p.lam[bb * p.lam_bs + i];
   }
   if (!hid) g2s<G>(H, ld, p.H + bb * p.H_bs, m, d);
-  const double* dtp = p.dt + bb * p.dt_bs;
-  const double* Yp = p.Y + bb * T * m;
-  const double* Rp = p.R + bb * p.R_bs;
-  const double* Ap = GIVEN ? p.A + bb * p.A_bs : nullptr;
-  const double* Qp = GIVEN ? p.Q + bb * p.Q_bs : nullptr;
-  double* mfp = p.mf + bb * T * d;
-  double* Pfp = p.Pf + bb * T * d * d;
+  const double* dtp = p.dt + bb * p.dt_bs + t0;
+  const double* Yp = p.Y + (bb * Tfull + t0) * m;
+  const double* Rp = p.R + bb * p.R_bs + t0 * p.R_ts;
+  const double* Ap = GIVEN ? p.A + bb * p.A_bs + t0 * d * d : nullptr;
+  const double* Qp = GIVEN ? p.Q + bb * p.Q_bs + t0 * d * d : nullptr;
+  double* mfp = p.mf + (bb * Tfull + t0) * d;
+  double* Pfp = p.Pf + (bb * Tfull + t0) * d * d;
+  double* lkp = p.lml_k ? p.lml_k + bb * Tfull + t0 : nullptr;
+  int streak = 0;
+  bool done = false;
 
   auto stage = [&](int64_t k) {
     const int st = (int)(k & 1);
@@ -217,16 +264,27 @@ __global__ void grp_filter_kernel(const SeqFilterArgs p, const GrpLayout L, cons
     __syncwarp();
     double mahal = 0.0;
     for (int a = 0; a < m; ++a) mahal = fma(v[a], w[a], mahal);
-    acc.add(det, mahal, nobs);
-    // ---- outputs
-    if (active) {
+    if (!chunked) acc.add(det, mahal, nobs);
+    // ---- outputs (fix-up: compare with what is stored before overwriting it)
+    if (chunked && p.fixup && active && !done)
+      streak = grp_agrees(mv_, P, ld, d, mfp + k * d, Pfp + k * d * d, p.delta) ? streak + 1 : 0;
+    __syncwarp();
+    if (active && !done) {
       for (int i = gl; i < d; i += G) mfp[k * d + i] = mv_[i];
       s2g<G>(Pfp + k * d * d, P, ld, d, d);
-      if (p.lml_k && gl == 0) p.lml_k[b * T + k] = lml_term(det, mahal, nobs);
+      if (lkp && gl == 0) lkp[k] = lml_term(det, mahal, nobs);
+    }
+    if (chunked && p.fixup) {
+      if (streak >= p.patience) done = true;
+      if (__all_sync(0xffffffffu, done || !active)) break;   // every group of the warp converged
     }
     __syncwarp();
   }
-  if (active && gl == 0) p.lml[b] = acc.value();
+  if (chunked) {
+    if (p.fixup && active && !done && gl == 0) atomicOr(p.unconverged, 1);
+  } else if (active && gl == 0) {
+    p.lml[b] = acc.value();
+  }
 }
 
 // ---------------------------------------------------------------------------------------- smoother
@@ -235,14 +293,14 @@ __global__ void grp_smooth_kernel(const SeqSmoothArgs p, const GrpLayout L) {
   extern __shared__ __align__(16) double smem[];
   const int groups_per_block = blockDim.x / G;
   const int g_in_block = threadIdx.x / G;
-  const int64_t b = (int64_t)blockIdx.x * groups_per_block + g_in_block;
-  const bool active = b < p.B;
-  const int64_t bb = active ? b : p.B - 1;
+  const GrpWork wk = grp_work(p, (int64_t)blockIdx.x * groups_per_block + g_in_block);
+  const bool active = wk.active, chunked = wk.chunked;
+  const int64_t bb = wk.b, vs = wk.v, t0 = wk.t0, Tfull = wk.Tfull;
   const int gl = Lanes<G>::gl();
   double* sm = smem + (size_t)g_in_block * L.total;
   const int d = L.d, mo = L.mo, ld = L.ld, s = L.s;
   const int mp_ = (mo == 0) ? d : mo;
-  const int64_t T = p.T;
+  const int64_t T = wk.T;
 
   double* Ps = sm + L.P; double* A = sm + L.A; double* Qm = sm + L.Qm;
   double* W1 = sm + L.W1; double* W2 = sm + L.W2; double* W3 = sm + L.W3; double* Ho = sm + L.Ho;
@@ -254,17 +312,19 @@ __global__ void grp_smooth_kernel(const SeqSmoothArgs p, const GrpLayout L) {
     for (int i = gl; i < L.nblk; i += G) lam[i] = p.lam[bb * p.lam_bs + i];
   }
   if (mo > 0) g2s<G>(Ho, ld, p.Hout, mo, d);
-  const double* dtp = p.dt + bb * p.dt_bs;
-  const double* Ap = GIVEN ? p.A + bb * p.A_bs : nullptr;
-  const double* Qp = GIVEN ? p.Q + bb * p.Q_bs : nullptr;
-  const double* mfp = p.mf + bb * T * d;
-  const double* Pfp = p.Pf + bb * T * d * d;
-  double* msp = p.ms + bb * T * mp_;
-  double* Psp = p.Ps + bb * T * mp_ * mp_;
+  const double* dtp = p.dt + bb * p.dt_bs + t0;
+  const double* Ap = GIVEN ? p.A + bb * p.A_bs + t0 * d * d : nullptr;
+  const double* Qp = GIVEN ? p.Q + bb * p.Q_bs + t0 * d * d : nullptr;
+  const double* mfp = p.mf + (bb * Tfull + t0) * d;
+  const double* Pfp = p.Pf + (bb * Tfull + t0) * d * d;
+  double* msp = p.ms + (bb * Tfull + t0) * mp_;
+  double* Psp = p.Ps + (bb * Tfull + t0) * mp_ * mp_;
+  int streak = 0;
+  bool done = false;
 
   auto emit = [&](int64_t k) {
     if (mo == 0) {
-      if (active) {
+      if (active && !done) {
         for (int i = gl; i < d; i += G) msp[k * d + i] = ms[i];
         s2g<G>(Psp + k * d * d, Ps, ld, d, d);
       }
@@ -291,13 +351,26 @@ __global__ void grp_smooth_kernel(const SeqSmoothArgs p, const GrpLayout L) {
     cp_async_commit();
   };
 
-  g2s<G>(Ps, ld, Pfp + (T - 1) * d * d, d, d);
-  for (int i = gl; i < d; i += G) ms[i] = mfp[(T - 1) * d + i];
+  // plain mode: the last step is terminal.  Chunk mode: every step is an RTS step from the carried
+  // state of the next chunk's first step; the last chunk carries its own last filtered state over
+  // dt = 0, which reproduces the terminal condition (see physs_seq_impl.cuh).
+  const bool carried = chunked && wk.c < p.nchunk - 1;
+  if (carried) {
+    g2s<G>(Ps, ld, p.bnd_P + vs * d * d, d, d);
+    for (int i = gl; i < d; i += G) ms[i] = p.bnd_m[vs * d + i];
+  } else {
+    g2s<G>(Ps, ld, Pfp + (T - 1) * d * d, d, d);
+    for (int i = gl; i < d; i += G) ms[i] = mfp[(T - 1) * d + i];
+  }
   __syncwarp();
-  emit(T - 1);
+  int64_t kstart = T - 1;
+  if (!chunked) {
+    emit(T - 1);
+    kstart = T - 2;
+  }
   double dt_n = 0.0;
-  if (T >= 2) { stage(T - 2); dt_n = dtp[T - 2]; }
-  for (int64_t k = T - 2; k >= 0; --k) {
+  if (kstart >= 0) { stage(kstart); dt_n = dtp[kstart]; }
+  for (int64_t k = kstart; k >= 0; --k) {
     const int st = (int)(k & 1);
     const double dt = dt_n;
     cp_async_wait_all();
@@ -350,8 +423,16 @@ __global__ void grp_smooth_kernel(const SeqSmoothArgs p, const GrpLayout L) {
     // Ps = Pf + (G dP) G^T = Pf + W2 X
     mm<G, false, false>(Ps, ld, W2, ld, W1, ld, d, d, d, Pf, ld, 1.0);
     __syncwarp();
+    if (chunked && p.fixup && active && !done)
+      streak = grp_agrees(ms, Ps, ld, d, msp + k * d, Psp + k * d * d, p.delta) ? streak + 1 : 0;
+    __syncwarp();
     emit(k);
+    if (chunked && p.fixup) {
+      if (streak >= p.patience) done = true;
+      if (__all_sync(0xffffffffu, done || !active)) break;
+    }
   }
+  if (chunked && p.fixup && active && !done && gl == 0) atomicOr(p.unconverged, 1);
 }
 
 // ---------------------------------------------------------------------------------------- dispatch
@@ -372,7 +453,8 @@ static int run_filter(cudaStream_t st, const SeqFilterArgs& a, const GrpLayout& 
   if (smem > 200 * 1024)
     return set_error(PHYSS_ERR_UNSUPPORTED, "state dimension too large for the shared-memory path");
   const int gpb = threads / G;
-  const int64_t grid = (a.B + gpb - 1) / gpb;
+  const int64_t ngroups = a.B * (a.nchunk > 0 ? a.chunk_count : 1);
+  const int64_t grid = (ngroups + gpb - 1) / gpb;
   cudaError_t e = cudaFuncSetAttribute(grp_filter_kernel<G, GIVEN>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(grp_filter_kernel)");
@@ -389,7 +471,8 @@ static int run_smooth(cudaStream_t st, const SeqSmoothArgs& a, const GrpLayout& 
   if (smem > 200 * 1024)
     return set_error(PHYSS_ERR_UNSUPPORTED, "state dimension too large for the shared-memory path");
   const int gpb = threads / G;
-  const int64_t grid = (a.B + gpb - 1) / gpb;
+  const int64_t ngroups = a.B * (a.nchunk > 0 ? a.chunk_count : 1);
+  const int64_t grid = (ngroups + gpb - 1) / gpb;
   cudaError_t e = cudaFuncSetAttribute(grp_smooth_kernel<G, GIVEN>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(grp_smooth_kernel)");

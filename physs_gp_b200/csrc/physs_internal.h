@@ -25,6 +25,19 @@ struct SeqFilterArgs {
   const double* R; int64_t R_bs, R_ts;
   double jitter;
   double* mf; double* Pf; double* lml; double* lml_k;
+  // ---- chunk mode (parallel-in-time, physs_pscan.cu): virtual series v = (b, c), c-th chunk of
+  // `chunk_len` steps of series b.  fixup != 0: chunk c >= 1 restarts from the snapshot
+  // (bnd_m, bnd_P)[v] of the previous chunk's last filtered state, rewrites its outputs and stops once
+  // they agree with what is already stored to `delta` (relative) for `patience` consecutive steps;
+  // a chunk that reaches its end without converging raises *unconverged.
+  // One launch covers chunks [chunk_first, chunk_first + chunk_count) of every series; all chunks of
+  // a launch have the same length (the ragged tail chunk gets its own launch).  nchunk = chunks per
+  // series in total (boundary snapshots are indexed b * nchunk + c); nchunk == 0 means plain mode.
+  int64_t nchunk, chunk_len, chunk_first, chunk_count;
+  int fixup, patience;
+  double delta;
+  const double* bnd_m; const double* bnd_P;
+  int* unconverged;
 };
 
 struct SeqSmoothArgs {
@@ -38,6 +51,17 @@ struct SeqSmoothArgs {
   const double* Hout;
   double jitter;
   double* ms; double* Ps;
+  // ---- chunk mode: chunk c of series b starts (backwards) from the carried smoothed state
+  // (bnd_m, bnd_P)[v] that belongs to the first step of chunk c + 1 and treats ALL its steps as RTS
+  // steps (full_state output only).  fixup as for the filter (chunks c < nchunk - 1).
+  // One launch covers chunks [chunk_first, chunk_first + chunk_count) of every series; all chunks of
+  // a launch have the same length (the ragged tail chunk gets its own launch).  nchunk = chunks per
+  // series in total (boundary snapshots are indexed b * nchunk + c); nchunk == 0 means plain mode.
+  int64_t nchunk, chunk_len, chunk_first, chunk_count;
+  int fixup, patience;
+  double delta;
+  const double* bnd_m; const double* bnd_P;
+  int* unconverged;
 };
 
 // physs_seq.cu: one thread per series, registers (d in {1,2,3,4,6,8})
@@ -45,6 +69,10 @@ bool seq_supported(int d, int m, int disc_mode, int nblk);
 int seq_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity,
                const SeqFilterArgs& a);
 int seq_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
+// size dispatch shared by the plain and the chunked entry points (physs_api.cu)
+int run_filter_any(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity,
+                   const SeqFilterArgs& a);
+int run_smooth_any(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
 
 struct CviArgs {
   int64_t N;

@@ -68,16 +68,45 @@ __device__ __forceinline__ void matern_trans(const double (&lam)[D / S], double 
 }
 
 // ------------------------------------------------------------------------------------------ filter
-template <int D, int S, int M, bool HID, bool GIVEN>
+// relative agreement of a freshly computed (m, P) with the stored one (fix-up pass of chunk mode)
+template <int D>
+__device__ __forceinline__ bool agrees(const double (&m)[D], const double (&P)[D][D],
+                                       const double* __restrict__ om, const double* __restrict__ oP,
+                                       double delta) {
+  double dP = 0.0, sP = 0.0, dm = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    dm = fmax(dm, fabs(m[i] - om[i]));
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double o = oP[i * D + j];
+      dP = fmax(dP, fabs(P[i][j] - o));
+      sP = fmax(sP, fabs(o));
+    }
+  }
+  return (dP <= delta * sP) && (dm * dm <= delta * delta * sP);
+}
+
+template <int D, int S, int M, bool HID, bool GIVEN, bool CHUNK>
 __global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= p.B) return;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= p.B * (CHUNK ? p.chunk_count : 1)) return;
   constexpr int NB = D / S;
-  const int64_t T = p.T;
+  const int64_t b = CHUNK ? tid / p.chunk_count : tid;
+  const int64_t c = CHUNK ? p.chunk_first + tid % p.chunk_count : 0;
+  const int64_t v = CHUNK ? b * p.nchunk + c : b;          // boundary-snapshot index
+  const int64_t t0 = CHUNK ? c * p.chunk_len : 0;
+  const int64_t Tfull = p.T;
+  const int64_t T = CHUNK ? ((p.chunk_len < Tfull - t0) ? p.chunk_len : (Tfull - t0)) : Tfull;
 
   double m[D], P[D][D], Pinf[D][D], H[M][D], lam[NB];
-  load_vec<D>(p.m0 + b * p.m0_bs, m);
-  load_mat<D>(p.P0 + b * p.P0_bs, P);
+  if (CHUNK && p.fixup) {
+    load_vec<D>(p.bnd_m + v * D, m);
+    load_mat<D>(p.bnd_P + v * D * D, P);
+  } else {
+    load_vec<D>(p.m0 + b * p.m0_bs, m);
+    load_mat<D>(p.P0 + b * p.P0_bs, P);
+  }
   if (!GIVEN) {
     load_mat<D>(p.Pinf + b * p.Pinf_bs, Pinf);
 #pragma unroll
@@ -90,13 +119,15 @@ __global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) 
       for (int j = 0; j < D; ++j) H[a][j] = p.H[b * p.H_bs + a * D + j];
     }
   }
-  const double* __restrict__ dtp = p.dt + b * p.dt_bs;
-  const double* __restrict__ Yp = p.Y + b * T * M;
-  const double* __restrict__ Rp = p.R + b * p.R_bs;
-  const double* __restrict__ Ap = GIVEN ? p.A + b * p.A_bs : nullptr;
-  const double* __restrict__ Qp = GIVEN ? p.Q + b * p.Q_bs : nullptr;
-  double* __restrict__ mfp = p.mf + b * T * D;
-  double* __restrict__ Pfp = p.Pf + b * T * D * D;
+  const double* __restrict__ dtp = p.dt + b * p.dt_bs + t0;
+  const double* __restrict__ Yp = p.Y + (b * Tfull + t0) * M;
+  const double* __restrict__ Rp = p.R + b * p.R_bs + t0 * p.R_ts;
+  const double* __restrict__ Ap = GIVEN ? p.A + b * p.A_bs + t0 * D * D : nullptr;
+  const double* __restrict__ Qp = GIVEN ? p.Q + b * p.Q_bs + t0 * D * D : nullptr;
+  double* __restrict__ mfp = p.mf + (b * Tfull + t0) * D;
+  double* __restrict__ Pfp = p.Pf + (b * Tfull + t0) * D * D;
+  double* __restrict__ lkp = p.lml_k ? p.lml_k + b * Tfull + t0 : nullptr;
+  int streak = 0;
 
   LmlAcc acc;
   // software prefetch of the next step's streamed inputs
@@ -132,23 +163,37 @@ __global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) 
     double det, mahal;
     int nobs;
     kf_update<D, M, HID>(m, P, H, R, y, p.jitter, det, mahal, nobs);
-    acc.add(det, mahal, nobs);
+    if (!CHUNK) acc.add(det, mahal, nobs);
+    if (CHUNK && p.fixup) {
+      streak = agrees<D>(m, P, mfp + k * D, Pfp + k * D * D, p.delta) ? streak + 1 : 0;
+    }
     store_vec<D>(mfp + k * D, m);
     store_mat<D>(Pfp + k * D * D, P);
-    if (p.lml_k) p.lml_k[b * T + k] = lml_term(det, mahal, nobs);
+    if (lkp) lkp[k] = lml_term(det, mahal, nobs);
+    if (CHUNK && p.fixup && streak >= p.patience) return;
   }
-  p.lml[b] = acc.value();
+  if (CHUNK) {
+    if (p.fixup) atomicOr(p.unconverged, 1);
+  } else {
+    p.lml[b] = acc.value();
+  }
 }
 
 // ---------------------------------------------------------------------------------------- smoother
 // MO == 0: full_state (H = I).  MO > 0: project with Hout [MO, D].
-template <int D, int S, int MO, bool GIVEN>
+template <int D, int S, int MO, bool GIVEN, bool CHUNK>
 __global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= p.B) return;
+  static_assert(!CHUNK || MO == 0, "chunk mode carries and compares the full state");
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= p.B * (CHUNK ? p.chunk_count : 1)) return;
   constexpr int NB = D / S;
   constexpr int MP = (MO == 0) ? D : MO;
-  const int64_t T = p.T;
+  const int64_t b = CHUNK ? tid / p.chunk_count : tid;
+  const int64_t c = CHUNK ? p.chunk_first + tid % p.chunk_count : 0;
+  const int64_t v = CHUNK ? b * p.nchunk + c : b;
+  const int64_t t0 = CHUNK ? c * p.chunk_len : 0;
+  const int64_t Tfull = p.T;
+  const int64_t T = CHUNK ? ((p.chunk_len < Tfull - t0) ? p.chunk_len : (Tfull - t0)) : Tfull;
 
   double Pinf[D][D], lam[NB], Ho[MP][D];
   if (!GIVEN) {
@@ -163,13 +208,13 @@ __global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) 
       for (int j = 0; j < D; ++j) Ho[a][j] = p.Hout[a * D + j];
     }
   }
-  const double* __restrict__ dtp = p.dt + b * p.dt_bs;
-  const double* __restrict__ Ap = GIVEN ? p.A + b * p.A_bs : nullptr;
-  const double* __restrict__ Qp = GIVEN ? p.Q + b * p.Q_bs : nullptr;
-  const double* __restrict__ mfp = p.mf + b * T * D;
-  const double* __restrict__ Pfp = p.Pf + b * T * D * D;
-  double* __restrict__ msp = p.ms + b * T * MP;
-  double* __restrict__ Psp = p.Ps + b * T * MP * MP;
+  const double* __restrict__ dtp = p.dt + b * p.dt_bs + t0;
+  const double* __restrict__ Ap = GIVEN ? p.A + b * p.A_bs + t0 * D * D : nullptr;
+  const double* __restrict__ Qp = GIVEN ? p.Q + b * p.Q_bs + t0 * D * D : nullptr;
+  const double* __restrict__ mfp = p.mf + (b * Tfull + t0) * D;
+  const double* __restrict__ Pfp = p.Pf + (b * Tfull + t0) * D * D;
+  double* __restrict__ msp = p.ms + (b * Tfull + t0) * MP;
+  double* __restrict__ Psp = p.Ps + (b * Tfull + t0) * MP * MP;
 
   auto emit = [&](int64_t k, const double (&ms)[D], const double (&Ps)[D][D]) {
     if (MO == 0) {
@@ -207,18 +252,36 @@ __global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) 
   };
 
   double ms[D], Ps[D][D];
-  load_vec<D>(mfp + (T - 1) * D, ms);
-  load_mat<D>(Pfp + (T - 1) * D * D, Ps);
-  emit(T - 1, ms, Ps);
+  // plain mode: the last step is terminal (smoothed = filtered).  Chunk mode: every step of the chunk
+  // is an RTS step from the carried state of the next chunk's first step; the very last chunk carries
+  // its own last filtered state across dt = 0, which reproduces the terminal condition.
+  const bool carried = CHUNK && c < p.nchunk - 1;
+  int64_t kstart;
+  if (CHUNK) {
+    if (carried) {
+      load_vec<D>(p.bnd_m + v * D, ms);
+      load_mat<D>(p.bnd_P + v * D * D, Ps);
+    } else {
+      load_vec<D>(mfp + (T - 1) * D, ms);
+      load_mat<D>(Pfp + (T - 1) * D * D, Ps);
+    }
+    kstart = T - 1;
+  } else {
+    load_vec<D>(mfp + (T - 1) * D, ms);
+    load_mat<D>(Pfp + (T - 1) * D * D, Ps);
+    emit(T - 1, ms, Ps);
+    kstart = T - 2;
+  }
+  int streak = 0;
 
   // prefetch filtered moments one step ahead (addresses do not depend on the state)
   double mf_n[D], Pf_n[D][D], dt_n = 0.0;
-  if (T >= 2) {
-    load_vec<D>(mfp + (T - 2) * D, mf_n);
-    load_mat<D>(Pfp + (T - 2) * D * D, Pf_n);
-    dt_n = dtp[T - 2];
+  if (kstart >= 0) {
+    load_vec<D>(mfp + kstart * D, mf_n);
+    load_mat<D>(Pfp + kstart * D * D, Pf_n);
+    dt_n = dtp[kstart];
   }
-  for (int64_t k = T - 2; k >= 0; --k) {
+  for (int64_t k = kstart; k >= 0; --k) {
     double mf[D], Pf[D][D];
     const double dt = dt_n;
 #pragma unroll
@@ -242,8 +305,13 @@ __global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) 
       matern_trans<D, S>(lam, dt, A);
       rts_step<D, S>(A, Pinf, true, mf, Pf, p.jitter, ms, Ps);
     }
+    if (CHUNK && p.fixup) {
+      streak = agrees<D>(ms, Ps, msp + k * D, Psp + k * D * D, p.delta) ? streak + 1 : 0;
+    }
     emit(k, ms, Ps);
+    if (CHUNK && p.fixup && streak >= p.patience) return;
   }
+  if (CHUNK && p.fixup) atomicOr(p.unconverged, 1);
 }
 
 // ------------------------------------------------------------------------------------------ launch
@@ -257,17 +325,30 @@ static inline int pick_block(int64_t B) {
 
 template <int D, int S, int M, bool HID, bool GIVEN>
 static int launch_filter(cudaStream_t st, const SeqFilterArgs& a) {
-  const int block = pick_block(a.B);
-  const int64_t grid = (a.B + block - 1) / block;
-  seq_filter_kernel<D, S, M, HID, GIVEN><<<(unsigned)grid, block, 0, st>>>(a);
+  const int64_t n = a.B * (a.nchunk > 0 ? a.chunk_count : 1);
+  const int block = pick_block(n);
+  const int64_t grid = (n + block - 1) / block;
+  if (a.nchunk > 0)
+    seq_filter_kernel<D, S, M, HID, GIVEN, true><<<(unsigned)grid, block, 0, st>>>(a);
+  else
+    seq_filter_kernel<D, S, M, HID, GIVEN, false><<<(unsigned)grid, block, 0, st>>>(a);
   return cuda_status(cudaGetLastError(), "seq_filter_kernel launch");
 }
 
 template <int D, int S, int MO, bool GIVEN>
 static int launch_smooth(cudaStream_t st, const SeqSmoothArgs& a) {
-  const int block = pick_block(a.B);
-  const int64_t grid = (a.B + block - 1) / block;
-  seq_smooth_kernel<D, S, MO, GIVEN><<<(unsigned)grid, block, 0, st>>>(a);
+  const int64_t n = a.B * (a.nchunk > 0 ? a.chunk_count : 1);
+  const int block = pick_block(n);
+  const int64_t grid = (n + block - 1) / block;
+  if (a.nchunk > 0) {
+    if constexpr (MO == 0) {
+      seq_smooth_kernel<D, S, 0, GIVEN, true><<<(unsigned)grid, block, 0, st>>>(a);
+    } else {
+      return set_error(PHYSS_ERR_BAD_ARG, "chunked smoother needs full_state output");
+    }
+  } else {
+    seq_smooth_kernel<D, S, MO, GIVEN, false><<<(unsigned)grid, block, 0, st>>>(a);
+  }
   return cuda_status(cudaGetLastError(), "seq_smooth_kernel launch");
 }
 
