@@ -7,12 +7,13 @@
 Workload (config.workload = "c5"): BASELINE.json config 5 -- 65,536 independent series x 10,000
 steps, Matern-7/2 state blocks (state dim d = 4 * nblk, default d = 4), scalar Gaussian observations
 (m = 1, sigma^2 = 0.1), per-series lengthscales ~ LogU, shared irregular time grid, 5 % observations
-missing.  STRONG scaling: the 65,536 series are sharded contiguously over the N ranks (no data-path
-collective); each rank walks its shard in sub-batches of `--sub-batch` series whose full-state outputs
-(filtered m, P and smoothed m, P in reference layout [B, T, d, d]) are materialised in HBM.
+missing.  WEAK scaling: every rank owns 65,536 series of its own (series are independent, no data-path
+collective); each rank walks them in sub-batches of `--sub-batch` series whose full-state outputs
+(filtered m, P and smoothed m, P, each step's d x d block in reference element order, batch stored
+time-major) are materialised in HBM.
 
-A "step" = one pass of the hot path (filter kernel + smoother kernel) over the whole 65,536 x 10,000
-job.  `value` = series * T * K / (max over ranks of the CUDA-event time of the K timed steps), inputs
+A "step" = one pass of the hot path (filter kernel + smoother kernel) over the rank's 65,536 x 10,000
+job.  `value` = N * series * T * K / (max over ranks of the CUDA-event time of the K timed steps), inputs
 resident in HBM.  `e2e` = the same job through the reference-shaped host API with HOST buffers: per
 sub-batch a pinned-host -> device copy of Y, filter + smoother, and a device -> pinned-host read of the
 user-facing result (smoothed mean / variance of f and the per-series log marginal likelihood).
@@ -46,7 +47,7 @@ def parse():
     ap.add_argument("--state-dim", type=int, default=4, help="4 * nblk Matern-7/2 blocks (4, 8, ...)")
     ap.add_argument("--series", type=int, default=SERIES_TOTAL)
     ap.add_argument("--T", type=int, default=T_STEPS)
-    ap.add_argument("--sub-batch", type=int, default=8192)
+    ap.add_argument("--sub-batch", type=int, default=32768)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-series", type=int, default=0, help="series in the CPU sample (0 = auto)")
@@ -149,7 +150,8 @@ def device_observations(n, T, dev, seed):
     Y = torch.sin(freq * k + phase) + 0.3 * torch.randn((n, T), generator=g, device=dev, dtype=torch.float64)
     miss = torch.rand((n, T), generator=g, device=dev) < NAN_FRAC
     Y[miss] = float("nan")
-    return Y[..., None].contiguous()
+    # time-major in memory ([T, n, 1]), logical shape [n, T, 1]: the B200 layout
+    return Y.t().contiguous()[..., None].transpose(0, 1)
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -194,7 +196,7 @@ def run_reference(a):
         "impl": "reference", "metric": "filter+smoother state-steps/sec (fp64)", "value": value,
         "unit": "state-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * float(np.mean([el for _, el in rates])), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(a, sub_batch=None),
         "cpu_baseline": {"value": value, "unit": "state-steps/s", "cores": threads, "kind": "port",
                          "sample": sample},
@@ -204,14 +206,16 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(a, sub_batch):
-    return {"workload": "c5: %d independent series x %d steps, Matern-7/2 x %d (state dim %d), m=1, "
+def workload_config(a, sub_batch, world=1):
+    return {"workload": "c5: %d independent series x %d steps per GPU, Matern-7/2 x %d (state dim %d), m=1, "
                         "Gaussian noise, per-series lengthscales, 5%% missing" % (
                             a.series, a.T, a.state_dim // 4, a.state_dim),
-            "series": a.series, "T": a.T, "state_dim": a.state_dim, "obs_dim": 1,
-            "sub_batch": sub_batch, "outputs": "filtered+smoothed full state, reference layout",
+            "series_per_gpu": a.series, "series_total": a.series * world, "T": a.T,
+            "state_dim": a.state_dim, "obs_dim": 1, "sub_batch": sub_batch,
+            "outputs": "filtered (m, P) + smoothed (m, P) full state, fp64, every step materialised in HBM",
+            "layout": "time-major batch [T][B][d*d] (step strides (1, B) of the C ABI)",
             "l2": "inputs+outputs per launch >> 126 MB L2 (no flush needed)",
-            "parallelism": "series sharded over ranks, no collective"}
+            "parallelism": "independent series sharded over ranks (weak scaling), no data-path collective"}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -234,13 +238,13 @@ def run_b200(a):
     if d % 4:
         raise SystemExit("--state-dim must be a multiple of 4 (Matern-7/2 blocks)")
     nblk = d // 4
-    per_rank = a.series // world
-    lo = rank * per_rank
-    n_local = per_rank if rank < world - 1 else a.series - lo
+    # WEAK scaling: every rank owns `--series` series of its own (series are independent: no collective)
+    n_local = a.series
+    lo = rank * n_local
     sub = min(a.sub_batch, n_local)
     starts = list(range(0, n_local, sub))
 
-    ls_all, steps = make_hypers(a.series, nblk)
+    ls_all, steps = make_hypers(a.series * world, nblk)
     steps = steps[:T] if T <= T_STEPS else np.resize(steps, T)
     prior = sdes.BatchedMaternSDE(4, ls_all[lo:lo + n_local])
     lam = torch.as_tensor(prior.lam(), device=dev)
@@ -250,28 +254,29 @@ def run_b200(a):
     dt_f = torch.as_tensor(np.hstack([0.0, steps[1:]]), device=dev)     # dt[k] = t_k - t_{k-1}, dt[0] = 0
     dt_s = torch.as_tensor(np.hstack([steps[1:], 0.0]), device=dev)     # dt[k] = t_{k+1} - t_k, dt[T-1] = 0
     R = torch.full((1, 1, 1, 1), NOISE_VAR, dtype=torch.float64, device=dev)
-    Y = torch.cat([device_observations(min(sub, n_local - s), T, dev, seed=1000 + lo + s) for s in starts])
+    Ys = [device_observations(min(sub, n_local - s), T, dev, seed=1000 + lo + s) for s in starts]
 
-    mf = torch.empty((sub, T, d), dtype=torch.float64, device=dev)
-    Pf = torch.empty((sub, T, d, d), dtype=torch.float64, device=dev)
-    ms = torch.empty_like(mf)
-    Ps = torch.empty_like(Pf)
+    def bufs(n):
+        return (ops.empty_steps(n, T, (d,), dev, True), ops.empty_steps(n, T, (d, d), dev, True),
+                ops.empty_steps(n, T, (d,), dev, True), ops.empty_steps(n, T, (d, d), dev, True))
+    out_full = bufs(sub)
+    out_tail = bufs(n_local - starts[-1]) if n_local - starts[-1] != sub else out_full
     lml_all = torch.empty((n_local,), dtype=torch.float64, device=dev)
 
     ev = {"f": [], "s": []}
 
     def one_step(record):
-        for s in starts:
+        for i, s in enumerate(starts):
             n = min(sub, n_local - s)
+            mf, Pf, ms, Ps = out_full if n == sub else out_tail
             disc = ops.Disc.matern(nblk, lam[s:s + n], Pinf[s:s + n])
             if record:
                 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                 e0.record()
-            lml, _, _ = ops.kf_filter(dt_f, Y[s:s + n], R, H, m0, Pinf[s:s + n], disc, jitter=1e-5,
-                                      out=(mf[:n], Pf[:n]))
+            lml, _, _ = ops.kf_filter(dt_f, Ys[i], R, H, m0, Pinf[s:s + n], disc, jitter=1e-5, out=(mf, Pf))
             if record:
                 e1.record()
-            ops.rts_smooth(dt_s, mf[:n], Pf[:n], disc, Hout=None, jitter=1e-5, out=(ms[:n], Ps[:n]))
+            ops.rts_smooth(dt_s, mf, Pf, disc, Hout=None, jitter=1e-5, out=(ms, Ps))
             if record:
                 e2.record()
                 ev["f"].append((e0, e1, n)), ev["s"].append((e1, e2, n))
@@ -299,7 +304,7 @@ def run_b200(a):
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     elapsed_ms = float(elapsed_ms.item())
-    value = a.series * T * a.steps / (elapsed_ms * 1e-3)
+    value = a.series * world * T * a.steps / (elapsed_ms * 1e-3)
     assert torch.isfinite(lml_all).all(), "non-finite log marginal likelihood in the bench run"
 
     # per-kernel durations (this rank), roofline of the dominant kernel
@@ -321,12 +326,14 @@ def run_b200(a):
                 "traffic": recorded_traffic(d),
                 "bytes_per_state_step": {"filter": fb, "smoother": sb},
                 "kernels": kern,
-                "whole_step_frac": (fb + sb) * value / 1e9 / peak}
+                "whole_step_frac": (fb + sb) * (value / world) / 1e9 / peak}
 
     # ---------------------------------------------------------------- e2e through the host API
     e2e = None
     if not a.no_e2e:
-        e2e = run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Y)
+        del out_full, out_tail
+        torch.cuda.empty_cache()
+        e2e = run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys)
 
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
@@ -340,8 +347,8 @@ def run_b200(a):
         line = {
             "metric": "filter+smoother state-steps/sec (fp64)", "value": value, "unit": "state-steps/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(a, sub),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(a, sub, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": 2 * len(starts) * a.steps,
         }
@@ -350,7 +357,7 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
-def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Y_dev):
+def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys_dev):
     """Same job through the reference-shaped API (SDE_GP.filter_and_smooth) with HOST buffers."""
     import torch
     import torch.distributed as dist
@@ -359,7 +366,9 @@ def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Y_dev):
     T, d = a.T, a.state_dim
     t_host = np.cumsum(steps)
     Y_host = torch.empty((n_local, T, 1), dtype=torch.float64, pin_memory=True)
-    Y_host.copy_(Y_dev)
+    for s0, Yd in zip(starts, Ys_dev):
+        Y_host[s0:s0 + Yd.shape[0]].copy_(Yd)
+    del Ys_dev
     out_mu = torch.empty((n_local, T, 1), dtype=torch.float64, pin_memory=True)
     out_var = torch.empty((n_local, T, 1), dtype=torch.float64, pin_memory=True)
     out_lml = torch.empty((n_local,), dtype=torch.float64, pin_memory=True)
@@ -393,7 +402,7 @@ def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Y_dev):
     assert bool(torch.isfinite(out_lml).all())
     per_rank_in = n_local * T * 8 + 2 * T * 8
     per_rank_out = n_local * T * 16 + n_local * 8
-    return {"value": a.series * T * k / el, "unit": "state-steps/s", "steps": k,
+    return {"value": a.series * world * T * k / el, "unit": "state-steps/s", "steps": k,
             "h2d_bytes_per_step": per_rank_in * world, "d2h_bytes_per_step": per_rank_out * world,
             "api": "SDE_GP.filter_and_smooth(full_state=False, return_lml=True) per sub-batch, pinned host buffers",
             "result": "smoothed mean/variance of f [B,T] + lml [B]"}

@@ -20,6 +20,11 @@
  *   - A leading batch axis B (independent series / spatial blocks / latent functions) is added in
  *     front of every reference array.  A `*_bstride` argument is the element stride between series
  *     for that array; 0 means "shared by all series".
+ *   - Per-step arrays (Y, mf, Pf, ms, Ps, lml_k) share one pair of "step strides": the row of series b
+ *     at step k of an array with n doubles per step starts at base + (b*step_bstride + k*step_tstride)*n.
+ *     (0, 0) or (T, 1) = batch-major [B][T][n] (what jax.vmap over axis 0 of the reference returns);
+ *     (1, B) = time-major [T][B][n] (vmap with out_axes=1) -- the layout the kernels are fastest in: the
+ *     32 series of a warp then read / write one contiguous span per step with coalesced 16-byte accesses.
  *   - NaN in Y marks a missing observation (utils/nan_utils.py:13-20).
  *   - Numerical failure (non-PD Cholesky) writes NaN and still returns 0, as jnp.linalg.cholesky does;
  *     the reference's NaN guard (trainers/natgrad_trainer.py:257-285) keeps working.
@@ -72,7 +77,8 @@ int physs_kf_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk);
  *   lml  [B]                          sum_k lml_k
  *   lml_k [B, T] or NULL              per-step terms
  */
-int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int32_t d, int32_t m,
+int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                        int32_t d, int32_t m,
                         int32_t disc_mode, int32_t nblk,
                         const double* A, int64_t A_bstride,
                         const double* Q, int64_t Q_bstride,
@@ -96,7 +102,8 @@ int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int32_t d, int32_t m
  * Outputs
  *   ms [B, T, mo'], Ps [B, T, mo', mo']   with mo' = (mo == 0 ? d : mo)
  */
-int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int32_t d,
+int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                         int32_t d,
                          int32_t disc_mode, int32_t nblk,
                          const double* A, int64_t A_bstride,
                          const double* Q, int64_t Q_bstride,

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libphyss_b200.so")
 PHYSS_OK = 0
 DISC_GIVEN = 0
 DISC_MATERN = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _c_i32 = ctypes.c_int32
 _c_i64 = ctypes.c_int64
@@ -25,13 +25,13 @@ SIGNATURES = {
     "physs_last_error": (ctypes.c_char_p, []),
     "physs_kf_supported": (ctypes.c_int, [_c_i32, _c_i32, _c_i32, _c_i32]),
     "physs_kf_filter_f64": (ctypes.c_int, [
-        _ptr, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32,
+        _ptr, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32,
         _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
         _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
         _ptr, _ptr, _c_i64, _c_i64, _c_f64,
         _ptr, _ptr, _ptr, _ptr]),
     "physs_rts_smooth_f64": (ctypes.c_int, [
-        _ptr, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32,
+        _ptr, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32,
         _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
         _ptr, _ptr, _ptr, _c_i32, _c_f64, _ptr, _ptr]),
     "physs_cvi_natgrad_step_f64": (ctypes.c_int, [

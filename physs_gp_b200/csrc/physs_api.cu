@@ -27,9 +27,17 @@ static inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_
 template <typename... Ps>
 static inline bool any_misaligned(Ps... ps) { return (misaligned(ps) || ...); }
 
+// (0, 0) = default batch-major; otherwise rows must not overlap: (bs >= T, ts = 1) or (bs = 1, ts >= B)
+static inline bool step_strides_ok(int64_t B, int64_t T, int64_t bs, int64_t ts) {
+  if (bs == 0 && ts == 0) return true;
+  if (ts == 1 && bs >= T) return true;
+  if (bs == 1 && ts >= B) return true;
+  return false;
+}
+
 extern "C" {
 
-int physs_abi_version(void) { return 1; }
+int physs_abi_version(void) { return 2; }
 
 const char* physs_last_error(void) { return g_err; }
 
@@ -41,7 +49,8 @@ int physs_kf_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {
   return grp_supported(d, m) ? 1 : 0;
 }
 
-int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int32_t d, int32_t m,
+int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                        int32_t d, int32_t m,
                         int32_t disc_mode, int32_t nblk,
                         const double* A, int64_t A_bstride,
                         const double* Q, int64_t Q_bstride,
@@ -70,8 +79,11 @@ int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int32_t d, int32_t m
   } else {
     return set_error(PHYSS_ERR_BAD_ARG, "filter: unknown disc_mode");
   }
+  if (!step_strides_ok(B, T, step_bstride, step_tstride))
+    return set_error(PHYSS_ERR_BAD_ARG, "filter: step strides must be (0,0), batch-major (>=T,1) or time-major (1,>=B)");
   SeqFilterArgs a{};
   a.B = B; a.T = T;
+  a.sbs = step_bstride ? step_bstride : T; a.sts = step_bstride ? step_tstride : 1;
   a.A = A; a.A_bs = A_bstride; a.Q = Q; a.Q_bs = Q_bstride;
   a.lam = lam; a.lam_bs = lam_bstride; a.dt = dt; a.dt_bs = dt_bstride;
   a.Pinf = Pinf; a.Pinf_bs = Pinf_bstride; a.m0 = m0; a.m0_bs = m0_bstride;
@@ -84,7 +96,8 @@ int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int32_t d, int32_t m
   return grp_filter((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a);
 }
 
-int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int32_t d,
+int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                         int32_t d,
                          int32_t disc_mode, int32_t nblk,
                          const double* A, int64_t A_bstride,
                          const double* Q, int64_t Q_bstride,
@@ -110,8 +123,11 @@ int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int32_t d,
   } else {
     return set_error(PHYSS_ERR_BAD_ARG, "smoother: unknown disc_mode");
   }
+  if (!step_strides_ok(B, T, step_bstride, step_tstride))
+    return set_error(PHYSS_ERR_BAD_ARG, "smoother: step strides must be (0,0), batch-major (>=T,1) or time-major (1,>=B)");
   SeqSmoothArgs a{};
   a.B = B; a.T = T;
+  a.sbs = step_bstride ? step_bstride : T; a.sts = step_bstride ? step_tstride : 1;
   a.A = A; a.A_bs = A_bstride; a.Q = Q; a.Q_bs = Q_bstride;
   a.lam = lam; a.lam_bs = lam_bstride; a.dt = dt; a.dt_bs = dt_bstride;
   a.Pinf = Pinf; a.Pinf_bs = Pinf_bstride; a.mf = mf; a.Pf = Pf;

@@ -126,19 +126,21 @@ __global__ void grp_filter_kernel(const SeqFilterArgs p, const GrpLayout L, cons
   }
   if (!hid) g2s<G>(H, ld, p.H + bb * p.H_bs, m, d);
   const double* dtp = p.dt + bb * p.dt_bs + t0;
-  const double* Yp = p.Y + (bb * Tfull + t0) * m;
+  const int64_t sts = p.sts;
+  const int64_t row0 = bb * p.sbs + t0 * sts;
+  const double* Yp = p.Y + row0 * m;
   const double* Rp = p.R + bb * p.R_bs + t0 * p.R_ts;
   const double* Ap = GIVEN ? p.A + bb * p.A_bs + t0 * d * d : nullptr;
   const double* Qp = GIVEN ? p.Q + bb * p.Q_bs + t0 * d * d : nullptr;
-  double* mfp = p.mf + (bb * Tfull + t0) * d;
-  double* Pfp = p.Pf + (bb * Tfull + t0) * d * d;
-  double* lkp = p.lml_k ? p.lml_k + bb * Tfull + t0 : nullptr;
+  double* mfp = p.mf + row0 * d;
+  double* Pfp = p.Pf + row0 * d * d;
+  double* lkp = p.lml_k ? p.lml_k + row0 : nullptr;
   int streak = 0;
   bool done = false;
 
   auto stage = [&](int64_t k) {
     const int st = (int)(k & 1);
-    g2s_async<G>(sm + L.vy[st], m, Yp + k * m, 1, m);
+    g2s_async<G>(sm + L.vy[st], m, Yp + k * sts * m, 1, m);
     g2s_async<G>(sm + L.Rst[st], ldm, Rp + k * p.R_ts, m, m);
     if (GIVEN) {
       g2s_async<G>(sm + L.AQst[st][0], ld, Ap + k * d * d, d, d);
@@ -267,12 +269,12 @@ __global__ void grp_filter_kernel(const SeqFilterArgs p, const GrpLayout L, cons
     if (!chunked) acc.add(det, mahal, nobs);
     // ---- outputs (fix-up: compare with what is stored before overwriting it)
     if (chunked && p.fixup && active && !done)
-      streak = grp_agrees(mv_, P, ld, d, mfp + k * d, Pfp + k * d * d, p.delta) ? streak + 1 : 0;
+      streak = grp_agrees(mv_, P, ld, d, mfp + k * sts * d, Pfp + k * sts * d * d, p.delta) ? streak + 1 : 0;
     __syncwarp();
     if (active && !done) {
-      for (int i = gl; i < d; i += G) mfp[k * d + i] = mv_[i];
-      s2g<G>(Pfp + k * d * d, P, ld, d, d);
-      if (lkp && gl == 0) lkp[k] = lml_term(det, mahal, nobs);
+      for (int i = gl; i < d; i += G) mfp[k * sts * d + i] = mv_[i];
+      s2g<G>(Pfp + k * sts * d * d, P, ld, d, d);
+      if (lkp && gl == 0) lkp[k * sts] = lml_term(det, mahal, nobs);
     }
     if (chunked && p.fixup) {
       if (streak >= p.patience) done = true;
@@ -315,26 +317,28 @@ __global__ void grp_smooth_kernel(const SeqSmoothArgs p, const GrpLayout L) {
   const double* dtp = p.dt + bb * p.dt_bs + t0;
   const double* Ap = GIVEN ? p.A + bb * p.A_bs + t0 * d * d : nullptr;
   const double* Qp = GIVEN ? p.Q + bb * p.Q_bs + t0 * d * d : nullptr;
-  const double* mfp = p.mf + (bb * Tfull + t0) * d;
-  const double* Pfp = p.Pf + (bb * Tfull + t0) * d * d;
-  double* msp = p.ms + (bb * Tfull + t0) * mp_;
-  double* Psp = p.Ps + (bb * Tfull + t0) * mp_ * mp_;
+  const int64_t sts = p.sts;
+  const int64_t row0 = bb * p.sbs + t0 * sts;
+  const double* mfp = p.mf + row0 * d;
+  const double* Pfp = p.Pf + row0 * d * d;
+  double* msp = p.ms + row0 * mp_;
+  double* Psp = p.Ps + row0 * mp_ * mp_;
   int streak = 0;
   bool done = false;
 
   auto emit = [&](int64_t k) {
     if (mo == 0) {
       if (active && !done) {
-        for (int i = gl; i < d; i += G) msp[k * d + i] = ms[i];
-        s2g<G>(Psp + k * d * d, Ps, ld, d, d);
+        for (int i = gl; i < d; i += G) msp[k * sts * d + i] = ms[i];
+        s2g<G>(Psp + k * sts * d * d, Ps, ld, d, d);
       }
     } else {
       // W1 <- Hout Ps  [mo x d];  out = W1 Hout^T
       mm<G, false, false>(W1, ld, Ho, ld, Ps, ld, mo, d, d, nullptr, 0, 1.0);
       __syncwarp();
       if (active) {
-        mm<G, false, true>(Psp + k * mo * mo, mo, W1, ld, Ho, ld, mo, d, mo, nullptr, 0, 1.0);
-        mv<G, false>(msp + k * mo, Ho, ld, ms, mo, d, nullptr, 1.0);
+        mm<G, false, true>(Psp + k * sts * mo * mo, mo, W1, ld, Ho, ld, mo, d, mo, nullptr, 0, 1.0);
+        mv<G, false>(msp + k * sts * mo, Ho, ld, ms, mo, d, nullptr, 1.0);
       }
     }
     __syncwarp();
@@ -342,8 +346,8 @@ __global__ void grp_smooth_kernel(const SeqSmoothArgs p, const GrpLayout L) {
 
   auto stage = [&](int64_t k) {
     const int st = (int)(k & 1);
-    g2s_async<G>(sm + L.vmf[st], d, mfp + k * d, 1, d);
-    g2s_async<G>(sm + L.PfS[st], ld, Pfp + k * d * d, d, d);
+    g2s_async<G>(sm + L.vmf[st], d, mfp + k * sts * d, 1, d);
+    g2s_async<G>(sm + L.PfS[st], ld, Pfp + k * sts * d * d, d, d);
     if (GIVEN) {
       g2s_async<G>(sm + L.AQst[st][0], ld, Ap + k * d * d, d, d);
       g2s_async<G>(sm + L.AQst[st][1], ld, Qp + k * d * d, d, d);
@@ -359,8 +363,8 @@ __global__ void grp_smooth_kernel(const SeqSmoothArgs p, const GrpLayout L) {
     g2s<G>(Ps, ld, p.bnd_P + vs * d * d, d, d);
     for (int i = gl; i < d; i += G) ms[i] = p.bnd_m[vs * d + i];
   } else {
-    g2s<G>(Ps, ld, Pfp + (T - 1) * d * d, d, d);
-    for (int i = gl; i < d; i += G) ms[i] = mfp[(T - 1) * d + i];
+    g2s<G>(Ps, ld, Pfp + (T - 1) * sts * d * d, d, d);
+    for (int i = gl; i < d; i += G) ms[i] = mfp[(T - 1) * sts * d + i];
   }
   __syncwarp();
   int64_t kstart = T - 1;
@@ -424,7 +428,7 @@ __global__ void grp_smooth_kernel(const SeqSmoothArgs p, const GrpLayout L) {
     mm<G, false, false>(Ps, ld, W2, ld, W1, ld, d, d, d, Pf, ld, 1.0);
     __syncwarp();
     if (chunked && p.fixup && active && !done)
-      streak = grp_agrees(ms, Ps, ld, d, msp + k * d, Psp + k * d * d, p.delta) ? streak + 1 : 0;
+      streak = grp_agrees(ms, Ps, ld, d, msp + k * sts * d, Psp + k * sts * d * d, p.delta) ? streak + 1 : 0;
     __syncwarp();
     emit(k);
     if (chunked && p.fixup) {

@@ -13,6 +13,7 @@ int cuda_status(cudaError_t e, const char* what);
 
 struct SeqFilterArgs {
   int64_t B, T;
+  int64_t sbs, sts;   // step strides: row (b, k) of a per-step array with n doubles is at (b*sbs + k*sts)*n
   const double* A; int64_t A_bs;
   const double* Q; int64_t Q_bs;
   const double* lam; int64_t lam_bs;
@@ -42,6 +43,7 @@ struct SeqFilterArgs {
 
 struct SeqSmoothArgs {
   int64_t B, T;
+  int64_t sbs, sts;   // step strides (see SeqFilterArgs)
   const double* A; int64_t A_bs;
   const double* Q; int64_t Q_bs;
   const double* lam; int64_t lam_bs;

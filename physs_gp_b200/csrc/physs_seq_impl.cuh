@@ -4,10 +4,14 @@
 // Reference call sites replaced: kalman_filter.py:439-485 (filter('sequential')) and
 // rts_smoother.py:162-192 (smoother('sequential')); see include/physs_b200.h.
 //
-// Layout: reference order with a leading batch axis, [B][T][d][d] row-major.  One thread walks one
-// series in time; per step it streams y/R/dt in and (m, P) out with 16-byte vector accesses where the
-// row is 16-byte aligned.  HBM traffic per state-step is the algorithmic 8*(d*d + d + m*m + m + 1) B
-// for the filter and 8*2*(d*d + d) B for the smoother.
+// Layout: every per-step array (Y, mf, Pf, ms, Ps, lml_k) is addressed through two "step strides":
+// row (b, k) of an array with n doubles per step starts at base + (b * sbs + k * sts) * n.
+//   (sbs, sts) = (T, 1): batch-major [B][T][n], the order jax.vmap(axis 0) of the reference gives;
+//   (sbs, sts) = (1, B): time-major  [T][B][n], the layout the B200 path prefers -- the 32 series of a
+//   warp then touch one contiguous 32 * n * 8-byte span per step, which the kernels write / read with
+//   fully coalesced 16-byte accesses after a warp-local transpose through shared memory.
+// One thread walks one series in time.  HBM traffic per state-step is the algorithmic
+// 8*(d*d + d + m*m + m + 1) B for the filter and 8*2*(d*d + d) B for the smoother.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -67,6 +71,140 @@ __device__ __forceinline__ void matern_trans(const double (&lam)[D / S], double 
   for (int b = 0; b < D / S; ++b) MaternExpm<S>::eval(lam[b], dt, A.a[b]);
 }
 
+// ------------------------------------------------------------------- warp-cooperative row transfer
+// Rows of N doubles owned one per lane, 32 consecutive series contiguous in global memory (sbs == 1).
+// LD = padded row length of the shared-memory tile.
+template <int N>
+struct RowTile {
+  static constexpr int LD = (N % 2 == 0) ? N + 2 : N;
+  static constexpr int SIZE = 32 * LD;
+};
+
+// lane `lane` contributes v[N]; the warp writes rows [0, nvalid) to g (row r at g + r * N)
+template <int N>
+__device__ __forceinline__ void warp_store_rows(double* __restrict__ g, const double (&v)[N],
+                                                double* tile, int lane, int nvalid) {
+  constexpr int LD = RowTile<N>::LD;
+  if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j)
+      *reinterpret_cast<double2*>(tile + lane * LD + 2 * j) = make_double2(v[2 * j], v[2 * j + 1]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const int e = 2 * (i * 32 + lane);
+      const int r = e / N, c = e % N;
+      const double2 t = *reinterpret_cast<const double2*>(tile + r * LD + c);
+      if (r < nvalid) *reinterpret_cast<double2*>(g + e) = t;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) tile[lane * LD + j] = v[j];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int e = i * 32 + lane;
+      const int r = e / N, c = e % N;
+      if (r < nvalid) g[e] = tile[r * LD + c];
+    }
+  }
+  __syncwarp();
+}
+
+// phase 1 of a coalesced load: issue the global loads (rows >= nvalid shadow row nvalid - 1)
+template <int N>
+struct RowRaw {
+  double2 v2[(N % 2 == 0) ? N / 2 : 1];
+  double v1[(N % 2 == 0) ? 1 : N];
+};
+template <int N>
+__device__ __forceinline__ void warp_load_issue(const double* __restrict__ g, RowRaw<N>& raw, int lane,
+                                                int nvalid) {
+  if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const int e = 2 * (i * 32 + lane);
+      const int r = e / N, c = e % N;
+      const int rr = (r < nvalid) ? r : nvalid - 1;
+      raw.v2[i] = *reinterpret_cast<const double2*>(g + rr * N + c);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int e = i * 32 + lane;
+      const int r = e / N, c = e % N;
+      const int rr = (r < nvalid) ? r : nvalid - 1;
+      raw.v1[i] = g[rr * N + c];
+    }
+  }
+}
+// phase 2: transpose through the tile into the lane's own row
+template <int N>
+__device__ __forceinline__ void warp_load_finish(const RowRaw<N>& raw, double (&v)[N], double* tile,
+                                                 int lane) {
+  constexpr int LD = RowTile<N>::LD;
+  if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const int e = 2 * (i * 32 + lane);
+      *reinterpret_cast<double2*>(tile + (e / N) * LD + (e % N)) = raw.v2[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+      const double2 t = *reinterpret_cast<const double2*>(tile + lane * LD + 2 * j);
+      v[2 * j] = t.x;
+      v[2 * j + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int e = i * 32 + lane;
+      tile[(e / N) * LD + (e % N)] = raw.v1[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = tile[lane * LD + j];
+  }
+  __syncwarp();
+}
+
+template <int D>
+__device__ __forceinline__ double (&flat(double (&P)[D][D]))[D * D] {
+  return *reinterpret_cast<double (*)[D * D]>(&P[0][0]);
+}
+template <int D>
+__device__ __forceinline__ const double (&flat(const double (&P)[D][D]))[D * D] {
+  return *reinterpret_cast<const double (*)[D * D]>(&P[0][0]);
+}
+
+// (series, chunk) of a thread.  Series are padded to a multiple of 32 per chunk so that a warp never
+// straddles two chunks; lanes beyond B shadow series B - 1 and never store.
+struct SeqWork {
+  int64_t b, b0, c, v, t0, T;   // b0 = first series of this warp
+  bool active;
+  int nvalid;   // valid lanes of this warp
+};
+template <bool CHUNK, typename Args>
+__device__ __forceinline__ bool seq_work(const Args& p, SeqWork& w) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t Bp = (p.B + 31) & ~(int64_t)31;
+  const int64_t ci = tid / Bp;
+  if (ci >= (CHUNK ? p.chunk_count : 1)) return false;      // whole warps only
+  const int64_t bq = tid % Bp;
+  w.active = bq < p.B;
+  w.b = w.active ? bq : p.B - 1;
+  const int64_t warp0 = bq - (threadIdx.x & 31);
+  w.b0 = warp0;
+  const int64_t left = p.B - warp0;
+  w.nvalid = left >= 32 ? 32 : (int)left;
+  w.c = CHUNK ? p.chunk_first + ci : 0;
+  w.v = CHUNK ? w.b * p.nchunk + w.c : w.b;
+  w.t0 = CHUNK ? w.c * p.chunk_len : 0;
+  w.T = CHUNK ? ((p.chunk_len < p.T - w.t0) ? p.chunk_len : (p.T - w.t0)) : p.T;
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------ filter
 // relative agreement of a freshly computed (m, P) with the stored one (fix-up pass of chunk mode)
 template <int D>
@@ -89,15 +227,16 @@ __device__ __forceinline__ bool agrees(const double (&m)[D], const double (&P)[D
 
 template <int D, int S, int M, bool HID, bool GIVEN, bool CHUNK>
 __global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) {
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= p.B * (CHUNK ? p.chunk_count : 1)) return;
+  __shared__ __align__(16) double tiles[4][RowTile<D * D>::SIZE];
+  SeqWork wk;
+  if (!seq_work<CHUNK>(p, wk)) return;
   constexpr int NB = D / S;
-  const int64_t b = CHUNK ? tid / p.chunk_count : tid;
-  const int64_t c = CHUNK ? p.chunk_first + tid % p.chunk_count : 0;
-  const int64_t v = CHUNK ? b * p.nchunk + c : b;          // boundary-snapshot index
-  const int64_t t0 = CHUNK ? c * p.chunk_len : 0;
-  const int64_t Tfull = p.T;
-  const int64_t T = CHUNK ? ((p.chunk_len < Tfull - t0) ? p.chunk_len : (Tfull - t0)) : Tfull;
+  const int64_t b = wk.b, v = wk.v, t0 = wk.t0, T = wk.T;
+  const bool active = wk.active;
+  const int lane = threadIdx.x & 31;
+  double* tile = tiles[threadIdx.x >> 5];
+  const bool coal = (p.sbs == 1);
+  const int64_t sts = p.sts;
 
   double m[D], P[D][D], Pinf[D][D], H[M][D], lam[NB];
   if (CHUNK && p.fixup) {
@@ -119,15 +258,20 @@ __global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) 
       for (int j = 0; j < D; ++j) H[a][j] = p.H[b * p.H_bs + a * D + j];
     }
   }
+  const int64_t row0 = b * p.sbs + t0 * sts;                  // step-row index of (b, t0)
+  const int64_t wrow0 = wk.b0 * p.sbs + t0 * sts;             // ... of the warp's first lane
   const double* __restrict__ dtp = p.dt + b * p.dt_bs + t0;
-  const double* __restrict__ Yp = p.Y + (b * Tfull + t0) * M;
+  const double* __restrict__ Yp = p.Y + row0 * M;
   const double* __restrict__ Rp = p.R + b * p.R_bs + t0 * p.R_ts;
   const double* __restrict__ Ap = GIVEN ? p.A + b * p.A_bs + t0 * D * D : nullptr;
   const double* __restrict__ Qp = GIVEN ? p.Q + b * p.Q_bs + t0 * D * D : nullptr;
-  double* __restrict__ mfp = p.mf + (b * Tfull + t0) * D;
-  double* __restrict__ Pfp = p.Pf + (b * Tfull + t0) * D * D;
-  double* __restrict__ lkp = p.lml_k ? p.lml_k + b * Tfull + t0 : nullptr;
+  double* __restrict__ mfp = p.mf + row0 * D;
+  double* __restrict__ Pfp = p.Pf + row0 * D * D;
+  double* __restrict__ mfw = p.mf + wrow0 * D;
+  double* __restrict__ Pfw = p.Pf + wrow0 * D * D;
+  double* __restrict__ lkp = p.lml_k ? p.lml_k + row0 : nullptr;
   int streak = 0;
+  bool done = false;
 
   LmlAcc acc;
   // software prefetch of the next step's streamed inputs
@@ -146,7 +290,7 @@ __global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) 
       for (int c = 0; c < M; ++c) R[a][c] = R_n[a][c];
     }
     if (k + 1 < T) {
-      load_vec<M>(Yp + (k + 1) * M, y_n);
+      load_vec<M>(Yp + (k + 1) * sts * M, y_n);
       if (p.R_ts != 0) load_mat<M>(Rp + (k + 1) * p.R_ts, R_n);
       dt_n = dtp[k + 1];
     }
@@ -163,37 +307,47 @@ __global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) 
     double det, mahal;
     int nobs;
     kf_update<D, M, HID>(m, P, H, R, y, p.jitter, det, mahal, nobs);
-    if (!CHUNK) acc.add(det, mahal, nobs);
-    if (CHUNK && p.fixup) {
-      streak = agrees<D>(m, P, mfp + k * D, Pfp + k * D * D, p.delta) ? streak + 1 : 0;
+    acc.add(det, mahal, nobs);
+    if (CHUNK && p.fixup && !done) {
+      streak = agrees<D>(m, P, mfp + k * sts * D, Pfp + k * sts * D * D, p.delta) ? streak + 1 : 0;
     }
-    store_vec<D>(mfp + k * D, m);
-    store_mat<D>(Pfp + k * D * D, P);
-    if (lkp) lkp[k] = lml_term(det, mahal, nobs);
-    if (CHUNK && p.fixup && streak >= p.patience) return;
+    if (coal) {
+      // converged lanes keep rewriting what is already stored to `delta`; the warp leaves together
+      warp_store_rows<D>(mfw + k * sts * D, m, tile, lane, wk.nvalid);
+      warp_store_rows<D * D>(Pfw + k * sts * D * D, flat<D>(P), tile, lane, wk.nvalid);
+    } else if (active && !done) {
+      store_vec<D>(mfp + k * sts * D, m);
+      store_mat<D>(Pfp + k * sts * D * D, P);
+    }
+    if (lkp && active && !done) lkp[k * sts] = lml_term(det, mahal, nobs);
+    if (CHUNK && p.fixup) {
+      if (streak >= p.patience) done = true;
+      if (__all_sync(0xffffffffu, done || !active)) break;
+    }
   }
   if (CHUNK) {
-    if (p.fixup) atomicOr(p.unconverged, 1);
-  } else {
+    if (p.fixup && active && !done) atomicOr(p.unconverged, 1);
+  } else if (active) {
     p.lml[b] = acc.value();
   }
 }
 
 // ---------------------------------------------------------------------------------------- smoother
 // MO == 0: full_state (H = I).  MO > 0: project with Hout [MO, D].
-template <int D, int S, int MO, bool GIVEN, bool CHUNK>
+template <int D, int S, int MO, bool GIVEN, bool CHUNK, bool COAL>
 __global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) {
   static_assert(!CHUNK || MO == 0, "chunk mode carries and compares the full state");
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= p.B * (CHUNK ? p.chunk_count : 1)) return;
+  __shared__ __align__(16) double tiles[4][RowTile<D * D>::SIZE];
+  SeqWork wk;
+  if (!seq_work<CHUNK>(p, wk)) return;
   constexpr int NB = D / S;
   constexpr int MP = (MO == 0) ? D : MO;
-  const int64_t b = CHUNK ? tid / p.chunk_count : tid;
-  const int64_t c = CHUNK ? p.chunk_first + tid % p.chunk_count : 0;
-  const int64_t v = CHUNK ? b * p.nchunk + c : b;
-  const int64_t t0 = CHUNK ? c * p.chunk_len : 0;
-  const int64_t Tfull = p.T;
-  const int64_t T = CHUNK ? ((p.chunk_len < Tfull - t0) ? p.chunk_len : (Tfull - t0)) : Tfull;
+  const int64_t b = wk.b, v = wk.v, t0 = wk.t0, T = wk.T;
+  const bool active = wk.active;
+  const int lane = threadIdx.x & 31;
+  double* tile = tiles[threadIdx.x >> 5];
+  constexpr bool coal = COAL;
+  const int64_t sts = p.sts;
 
   double Pinf[D][D], lam[NB], Ho[MP][D];
   if (!GIVEN) {
@@ -208,18 +362,30 @@ __global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) 
       for (int j = 0; j < D; ++j) Ho[a][j] = p.Hout[a * D + j];
     }
   }
+  const int64_t row0 = b * p.sbs + t0 * sts;
+  const int64_t wrow0 = wk.b0 * p.sbs + t0 * sts;
   const double* __restrict__ dtp = p.dt + b * p.dt_bs + t0;
   const double* __restrict__ Ap = GIVEN ? p.A + b * p.A_bs + t0 * D * D : nullptr;
   const double* __restrict__ Qp = GIVEN ? p.Q + b * p.Q_bs + t0 * D * D : nullptr;
-  const double* __restrict__ mfp = p.mf + (b * Tfull + t0) * D;
-  const double* __restrict__ Pfp = p.Pf + (b * Tfull + t0) * D * D;
-  double* __restrict__ msp = p.ms + (b * Tfull + t0) * MP;
-  double* __restrict__ Psp = p.Ps + (b * Tfull + t0) * MP * MP;
+  const double* __restrict__ mfp = p.mf + row0 * D;
+  const double* __restrict__ Pfp = p.Pf + row0 * D * D;
+  const double* __restrict__ mfw = p.mf + wrow0 * D;
+  const double* __restrict__ Pfw = p.Pf + wrow0 * D * D;
+  double* __restrict__ msp = p.ms + row0 * MP;
+  double* __restrict__ Psp = p.Ps + row0 * MP * MP;
+  double* __restrict__ msw = p.ms + wrow0 * MP;
+  double* __restrict__ Psw = p.Ps + wrow0 * MP * MP;
+  bool done = false;
 
   auto emit = [&](int64_t k, const double (&ms)[D], const double (&Ps)[D][D]) {
-    if (MO == 0) {
-      store_vec<D>(msp + k * D, ms);
-      store_mat<D>(Psp + k * D * D, Ps);
+    if constexpr (MO == 0) {
+      if constexpr (coal) {
+        warp_store_rows<D>(msw + k * sts * D, ms, tile, lane, wk.nvalid);
+        warp_store_rows<D * D>(Psw + k * sts * D * D, flat<D>(Ps), tile, lane, wk.nvalid);
+      } else if (active && !done) {
+        store_vec<D>(msp + k * sts * D, ms);
+        store_mat<D>(Psp + k * sts * D * D, Ps);
+      }
     } else {
       double om[MP], oP[MP][MP], HPs[MP][D];
 #pragma unroll
@@ -246,8 +412,38 @@ __global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) 
           oP[a][c] = t;
         }
       }
-      store_vec<MP>(msp + k * MP, om);
-      store_mat<MP>(Psp + k * MP * MP, oP);
+      if (active) {
+        store_vec<MP>(msp + k * sts * MP, om);
+        store_mat<MP>(Psp + k * sts * MP * MP, oP);
+      }
+    }
+  };
+
+  // filtered moments of step k: direct per-thread loads, or (time-major) coalesced warp loads that are
+  // transposed through shared memory when they are consumed one iteration later
+  RowRaw<COAL ? D : 1> raw_m;
+  RowRaw<COAL ? D * D : 1> raw_P;
+  double mf_n[COAL ? 1 : D], Pf_n[COAL ? 1 : D][COAL ? 1 : D];
+  auto fetch = [&](int64_t k) {
+    if constexpr (coal) {
+      warp_load_issue<D>(mfw + k * sts * D, raw_m, lane, wk.nvalid);
+      warp_load_issue<D * D>(Pfw + k * sts * D * D, raw_P, lane, wk.nvalid);
+    } else {
+      load_vec<D>(mfp + k * sts * D, mf_n);
+      load_mat<D>(Pfp + k * sts * D * D, Pf_n);
+    }
+  };
+  auto land = [&](double (&mf)[D], double (&Pf)[D][D]) {
+    if constexpr (coal) {
+      warp_load_finish<D>(raw_m, mf, tile, lane);
+      warp_load_finish<D * D>(raw_P, flat<D>(Pf), tile, lane);
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        mf[i] = mf_n[i];
+#pragma unroll
+        for (int j = 0; j < D; ++j) Pf[i][j] = Pf_n[i][j];
+      }
     }
   };
 
@@ -255,44 +451,34 @@ __global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) 
   // plain mode: the last step is terminal (smoothed = filtered).  Chunk mode: every step of the chunk
   // is an RTS step from the carried state of the next chunk's first step; the very last chunk carries
   // its own last filtered state across dt = 0, which reproduces the terminal condition.
-  const bool carried = CHUNK && c < p.nchunk - 1;
+  const bool carried = CHUNK && wk.c < p.nchunk - 1;
   int64_t kstart;
+  if (CHUNK && carried) {
+    load_vec<D>(p.bnd_m + v * D, ms);
+    load_mat<D>(p.bnd_P + v * D * D, Ps);
+  } else {
+    load_vec<D>(mfp + (T - 1) * sts * D, ms);
+    load_mat<D>(Pfp + (T - 1) * sts * D * D, Ps);
+  }
   if (CHUNK) {
-    if (carried) {
-      load_vec<D>(p.bnd_m + v * D, ms);
-      load_mat<D>(p.bnd_P + v * D * D, Ps);
-    } else {
-      load_vec<D>(mfp + (T - 1) * D, ms);
-      load_mat<D>(Pfp + (T - 1) * D * D, Ps);
-    }
     kstart = T - 1;
   } else {
-    load_vec<D>(mfp + (T - 1) * D, ms);
-    load_mat<D>(Pfp + (T - 1) * D * D, Ps);
     emit(T - 1, ms, Ps);
     kstart = T - 2;
   }
   int streak = 0;
 
-  // prefetch filtered moments one step ahead (addresses do not depend on the state)
-  double mf_n[D], Pf_n[D][D], dt_n = 0.0;
+  double dt_n = 0.0;
   if (kstart >= 0) {
-    load_vec<D>(mfp + kstart * D, mf_n);
-    load_mat<D>(Pfp + kstart * D * D, Pf_n);
+    fetch(kstart);
     dt_n = dtp[kstart];
   }
   for (int64_t k = kstart; k >= 0; --k) {
     double mf[D], Pf[D][D];
     const double dt = dt_n;
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      mf[i] = mf_n[i];
-#pragma unroll
-      for (int j = 0; j < D; ++j) Pf[i][j] = Pf_n[i][j];
-    }
+    land(mf, Pf);
     if (k >= 1) {
-      load_vec<D>(mfp + (k - 1) * D, mf_n);
-      load_mat<D>(Pfp + (k - 1) * D * D, Pf_n);
+      fetch(k - 1);
       dt_n = dtp[k - 1];
     }
     Trans<D, S> A;
@@ -305,13 +491,16 @@ __global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) 
       matern_trans<D, S>(lam, dt, A);
       rts_step<D, S>(A, Pinf, true, mf, Pf, p.jitter, ms, Ps);
     }
-    if (CHUNK && p.fixup) {
-      streak = agrees<D>(ms, Ps, msp + k * D, Psp + k * D * D, p.delta) ? streak + 1 : 0;
+    if (CHUNK && p.fixup && !done) {
+      streak = agrees<D>(ms, Ps, msp + k * sts * D, Psp + k * sts * D * D, p.delta) ? streak + 1 : 0;
     }
     emit(k, ms, Ps);
-    if (CHUNK && p.fixup && streak >= p.patience) return;
+    if (CHUNK && p.fixup) {
+      if (streak >= p.patience) done = true;
+      if (__all_sync(0xffffffffu, done || !active)) break;
+    }
   }
-  if (CHUNK && p.fixup) atomicOr(p.unconverged, 1);
+  if (CHUNK && p.fixup && active && !done) atomicOr(p.unconverged, 1);
 }
 
 // ------------------------------------------------------------------------------------------ launch
@@ -325,7 +514,7 @@ static inline int pick_block(int64_t B) {
 
 template <int D, int S, int M, bool HID, bool GIVEN>
 static int launch_filter(cudaStream_t st, const SeqFilterArgs& a) {
-  const int64_t n = a.B * (a.nchunk > 0 ? a.chunk_count : 1);
+  const int64_t n = ((a.B + 31) / 32 * 32) * (a.nchunk > 0 ? a.chunk_count : 1);
   const int block = pick_block(n);
   const int64_t grid = (n + block - 1) / block;
   if (a.nchunk > 0)
@@ -337,17 +526,20 @@ static int launch_filter(cudaStream_t st, const SeqFilterArgs& a) {
 
 template <int D, int S, int MO, bool GIVEN>
 static int launch_smooth(cudaStream_t st, const SeqSmoothArgs& a) {
-  const int64_t n = a.B * (a.nchunk > 0 ? a.chunk_count : 1);
+  const int64_t n = ((a.B + 31) / 32 * 32) * (a.nchunk > 0 ? a.chunk_count : 1);
   const int block = pick_block(n);
   const int64_t grid = (n + block - 1) / block;
+  const bool coal = (a.sbs == 1);
   if (a.nchunk > 0) {
     if constexpr (MO == 0) {
-      seq_smooth_kernel<D, S, 0, GIVEN, true><<<(unsigned)grid, block, 0, st>>>(a);
+      if (coal) seq_smooth_kernel<D, S, 0, GIVEN, true, true><<<(unsigned)grid, block, 0, st>>>(a);
+      else seq_smooth_kernel<D, S, 0, GIVEN, true, false><<<(unsigned)grid, block, 0, st>>>(a);
     } else {
       return set_error(PHYSS_ERR_BAD_ARG, "chunked smoother needs full_state output");
     }
   } else {
-    seq_smooth_kernel<D, S, MO, GIVEN, false><<<(unsigned)grid, block, 0, st>>>(a);
+    if (coal) seq_smooth_kernel<D, S, MO, GIVEN, false, true><<<(unsigned)grid, block, 0, st>>>(a);
+    else seq_smooth_kernel<D, S, MO, GIVEN, false, false><<<(unsigned)grid, block, 0, st>>>(a);
   }
   return cuda_status(cudaGetLastError(), "seq_smooth_kernel launch");
 }

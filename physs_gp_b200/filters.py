@@ -95,6 +95,10 @@ def filter(data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask,
     Yd = Yd[..., 0]                                   # [B, T, m]
     if isinstance(prior, BatchedMaternSDE) and Yd.shape[0] == 1 and prior.B > 1:
         Yd = Yd.expand(prior.B, -1, -1)
+    if settings.time_major and Yd.shape[0] >= settings.time_major_min_batch and not ops.step_layout(Yd, "Y")[1]:
+        # B200 layout: store the batch time-major ([T, B, m] in memory, logical shape unchanged) so that
+        # the 32 series of a warp read / write contiguous spans; every output follows Y's memory order
+        Yd = Yd.transpose(0, 1).contiguous().transpose(0, 1)
     dtd = _to_dev(dt, dev)
     (disc,), m0, P0, H = lower_prior(prior, X_s, [dtd], dev)
     R = _to_dev(lik_mat, dev)

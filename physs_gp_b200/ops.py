@@ -59,6 +59,29 @@ def _bview(x, name, shape, inner):
     return v, v.stride()
 
 
+def step_layout(x, name):
+    """(tensor, time_major) for a per-step array x [B, T, ...]: the kernels take it batch-major (contiguous
+    [B, T, ...]) or time-major (a transposed view of a contiguous [T, B, ...] tensor) without a copy;
+    anything else is made batch-major contiguous."""
+    x = _dev(x, name)
+    if x.is_contiguous():
+        return x, False
+    if x.transpose(0, 1).is_contiguous():
+        return x, True
+    return x.contiguous(), False
+
+
+def empty_steps(B, T, inner, dev, time_major):
+    """Uninitialised per-step array of logical shape [B, T, *inner] in the requested memory order."""
+    if time_major:
+        return torch.empty((T, B) + tuple(inner), dtype=torch.float64, device=dev).transpose(0, 1)
+    return torch.empty((B, T) + tuple(inner), dtype=torch.float64, device=dev)
+
+
+def _strides(B, T, time_major):
+    return (1, B) if time_major else (T, 1)
+
+
 def _stream_ptr(stream):
     s = stream if stream is not None else torch.cuda.current_stream()
     return s.cuda_stream
@@ -89,18 +112,21 @@ def kf_filter(dt, Y, R, H, m0, P0, disc, jitter=None, want_lml_k=False, out=None
     R -> [B, T, m, m];  H -> [B, m, d] or None (identity, m == d);  m0 -> [B, d];  P0 -> [B, d, d].
     Returns (lml [B], mf [B, T, d], Pf [B, T, d, d][, lml_k [B, T]]).
     `out=(mf, Pf)` reuses caller-provided output buffers.
+
+    Memory order: if Y is a transposed view of a contiguous [T, B, m] tensor (time-major), the outputs
+    are produced time-major too (logical shape still [B, T, ...]) -- the fast, coalesced layout.
     """
     lib = _lib.load()
-    Y = _dev(Y, "Y")
     if Y.dim() != 3:
         raise ValueError("Y must be [B, T, m]")
-    Y = Y.contiguous()
+    Y, tmaj = step_layout(Y, "Y")
     B, T, m = Y.shape
+    sbs, sts = _strides(B, T, tmaj)
     P0v, sP0 = _bview(P0, "P0", (B, P0.shape[-1], P0.shape[-1]), 2)
     d = P0v.shape[-1]
     m0v, sm0 = _bview(m0, "m0", (B, d), 1)
     dtv, sdt = _bview(dt, "dt", (B, T), 1)
-    Rv, sR = _bview(R, "R", (B, T, m, m), 2)
+    Rv, sR = _bview(R, "R", (B, T, m, m), 2)   # any batch / time strides (0 = broadcast)
     if H is None:
         Hptr, sH = None, (0,)
     else:
@@ -109,18 +135,21 @@ def kf_filter(dt, Y, R, H, m0, P0, disc, jitter=None, want_lml_k=False, out=None
     keep, (pA, bA), (pQ, bQ), (pl, bl), (pPi, bPi) = _disc_args(disc, B, T, d)
     dev = Y.device
     if out is None:
-        mf = torch.empty((B, T, d), dtype=torch.float64, device=dev)
-        Pf = torch.empty((B, T, d, d), dtype=torch.float64, device=dev)
+        mf = empty_steps(B, T, (d,), dev, tmaj)
+        Pf = empty_steps(B, T, (d, d), dev, tmaj)
     else:
         mf, Pf = out
-        if tuple(mf.shape) != (B, T, d) or tuple(Pf.shape) != (B, T, d, d) or not (mf.is_contiguous() and Pf.is_contiguous()):
-            raise ValueError("out buffers must be contiguous [B,T,d] and [B,T,d,d]")
+        ok = tuple(mf.shape) == (B, T, d) and tuple(Pf.shape) == (B, T, d, d)
+        for o in (mf, Pf):
+            ok = ok and (o.transpose(0, 1).is_contiguous() if tmaj else o.is_contiguous())
+        if not ok:
+            raise ValueError("out buffers must be [B,T,d] and [B,T,d,d] in the memory order of Y")
     lml = torch.empty((B,), dtype=torch.float64, device=dev)
-    lml_k = torch.empty((B, T), dtype=torch.float64, device=dev) if want_lml_k else None
+    lml_k = empty_steps(B, T, (), dev, tmaj) if want_lml_k else None
     jit = settings.jitter if jitter is None else jitter
     with torch.cuda.device(dev):
         st = lib.physs_kf_filter_f64(
-            _stream_ptr(stream), B, T, d, m, disc.mode, disc.nblk,
+            _stream_ptr(stream), B, T, sbs, sts, d, m, disc.mode, disc.nblk,
             pA, bA, pQ, bQ, pl, bl, dtv.data_ptr(), sdt[0], pPi, bPi,
             m0v.data_ptr(), sm0[0], P0v.data_ptr(), sP0[0], Hptr, sH[0],
             Y.data_ptr(), Rv.data_ptr(), sR[0], sR[1], float(jit),
@@ -140,9 +169,12 @@ def rts_smooth(dt, mf, Pf, disc, Hout=None, jitter=None, out=None, stream=None):
     Returns (ms [B, T, mo'], Ps [B, T, mo', mo']).
     """
     lib = _lib.load()
-    mf = _dev(mf, "mf").contiguous()
-    Pf = _dev(Pf, "Pf").contiguous()
+    mf, tmaj = step_layout(mf, "mf")
+    Pf, tmaj_P = step_layout(Pf, "Pf")
+    if tmaj != tmaj_P:
+        mf, Pf, tmaj = mf.contiguous(), Pf.contiguous(), False
     B, T, d = mf.shape
+    sbs, sts = _strides(B, T, tmaj)
     dtv, sdt = _bview(dt, "dt", (B, T), 1)
     keep, (pA, bA), (pQ, bQ), (pl, bl), (pPi, bPi) = _disc_args(disc, B, T, d)
     if Hout is None:
@@ -153,14 +185,17 @@ def rts_smooth(dt, mf, Pf, disc, Hout=None, jitter=None, out=None, stream=None):
         Hptr, mp = Hout.data_ptr(), mo
     dev = mf.device
     if out is None:
-        ms = torch.empty((B, T, mp), dtype=torch.float64, device=dev)
-        Ps = torch.empty((B, T, mp, mp), dtype=torch.float64, device=dev)
+        ms = empty_steps(B, T, (mp,), dev, tmaj)
+        Ps = empty_steps(B, T, (mp, mp), dev, tmaj)
     else:
         ms, Ps = out
+        for o in (ms, Ps):
+            if not (o.transpose(0, 1).is_contiguous() if tmaj else o.is_contiguous()):
+                raise ValueError("out buffers must be in the memory order of mf / Pf")
     jit = settings.jitter if jitter is None else jitter
     with torch.cuda.device(dev):
         st = lib.physs_rts_smooth_f64(
-            _stream_ptr(stream), B, T, d, disc.mode, disc.nblk,
+            _stream_ptr(stream), B, T, sbs, sts, d, disc.mode, disc.nblk,
             pA, bA, pQ, bQ, pl, bl, dtv.data_ptr(), sdt[0], pPi, bPi,
             mf.data_ptr(), Pf.data_ptr(), Hptr, mo, float(jit), ms.data_ptr(), Ps.data_ptr())
     _lib.check(st, "physs_rts_smooth_f64")

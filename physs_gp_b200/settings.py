@@ -7,3 +7,9 @@ ng_jitter = 1e-7       # settings.py:64 -- theta <-> lambda transforms
 kalman_filter_force_symmetric = False   # settings.py:33 (only the default is supported)
 parallel_kf_force_linear_solve = False  # settings.py:55 (only the default is supported)
 verbose = False
+
+# B200 memory order of batched per-step arrays (no reference counterpart: the reference has no batch
+# axis).  True: batches of >= time_major_min_batch series are stored [T, B, ...] in memory (returned as
+# [B, T, ...] views), which lets a warp's 32 series move one contiguous span per step.
+time_major = True
+time_major_min_batch = 32

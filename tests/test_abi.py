@@ -41,7 +41,7 @@ def test_bad_arguments_return_status_not_crash():
     from physs_gp_b200 import _lib
     lib = _lib.load()
     # T < 1 is rejected before any CUDA call
-    st = lib.physs_kf_filter_f64(None, 1, 0, 2, 1, 0, 0, None, 0, None, 0, None, 0, None, 0, None, 0,
+    st = lib.physs_kf_filter_f64(None, 1, 0, 0, 0, 2, 1, 0, 0, None, 0, None, 0, None, 0, None, 0, None, 0,
                                  None, 0, None, 0, None, 0, None, None, 0, 0, 1e-5, None, None, None, None)
     assert st == 1
     assert b"bad sizes" in lib.physs_last_error()

@@ -153,11 +153,13 @@ def test_generic_prior_goes_through_given_A_Q(cuda_device):
     assert rel(kf['P'], Pf_o) < TOL and rel(mu, ms_o) < TOL and rel(var, Ps_o) < TOL
 
 
+@pytest.mark.parametrize("time_major", [True, False])
 @pytest.mark.parametrize("s,nblk", [(2, 1), (3, 1), (4, 1), (2, 2)])
-def test_batched_per_series_hyperparameters(cuda_device, s, nblk):
+def test_batched_per_series_hyperparameters(cuda_device, s, nblk, time_major, monkeypatch):
     """B series with their own lengthscales (BASELINE config 5 shape, small): every series must equal
-    the oracle run on that series alone."""
-    from physs_gp_b200 import data, filters, sdes
+    the oracle run on that series alone -- in both memory orders of the batch."""
+    from physs_gp_b200 import data, filters, sdes, settings
+    monkeypatch.setattr(settings, "time_major", time_major)
     rng = np.random.default_rng(100 + 10 * s + nblk)
     B, T = 37, 120
     ls = synth.log_uniform(rng, 0.5, 2.0, (B, nblk))
@@ -169,6 +171,8 @@ def test_batched_per_series_hyperparameters(cuda_device, s, nblk):
     d = data.TemporalData(t, Y[..., None])
     lml, kf = filters.filter_loop(d, prior, R=R)
     mu, var_s = filters.smoother_loop(d, prior, kf, full_state=True)
+    for o in (kf['P'], var_s):
+        assert o.transpose(0, 1).is_contiguous() == time_major and o.shape[:2] == (B, T)
     kind = {2: osde.Matern32, 3: osde.Matern52, 4: osde.Matern72}[s]
     for b in range(0, B, 6):
         parts = [kind(ls[b, i], var[b, i]) for i in range(nblk)]
@@ -213,3 +217,52 @@ def test_full_size_properties(cuda_device):
     permd = perm.to(lml.device)
     assert torch.equal(lml_p.nan_to_num(), lml[permd].nan_to_num())
     assert torch.equal(var_p, var[permd]) and torch.equal(mu_p, mu[permd])
+
+
+@pytest.mark.parametrize("d,m,given,mo", [(1, 1, False, 0), (2, 1, False, 0), (3, 1, False, 1), (3, 3, True, 0),
+                                          (4, 1, False, 0), (4, 2, False, 2), (4, 4, True, 0), (8, 1, False, 0),
+                                          (8, 3, True, 2)])
+def test_time_major_equals_batch_major_bitwise(cuda_device, d, m, given, mo):
+    """The memory order of the batch must not change a single bit of any series' result (ragged last
+    warp: B = 70), for the register kernels (d <= 4) and the shared-memory kernels (d = 8)."""
+    from physs_gp_b200 import ops
+    dev = cuda_device
+    rng = np.random.default_rng(1000 + 10 * d + m)
+    B, T = 70, 64
+    t = synth.time_grid(T, 0.1, rng)
+    dt_f = torch.as_tensor(np.hstack([0.0, np.diff(t)]), device=dev)
+    dt_s = torch.as_tensor(np.hstack([np.diff(t), 0.0]), device=dev)
+    Y = torch.as_tensor(synth.noisy_series(B, T, m, rng, 0.1), device=dev)
+    R = torch.as_tensor(synth.random_spd(rng, (B, T), m), device=dev)
+    H = torch.as_tensor(rng.normal(size=(1, m, d)), device=dev)
+    if given:
+        Fm = rng.normal(size=(d, d)) * 0.3 - np.eye(d)
+        import scipy.linalg as sla
+        Pinf = sla.solve_continuous_lyapunov(Fm, -np.eye(d))
+        A = np.stack([sla.expm(Fm * x) for x in np.hstack([0.0, np.diff(t)])])
+        Q = Pinf - A @ Pinf @ np.swapaxes(A, -1, -2)
+        A_s = np.stack([sla.expm(Fm * x) for x in np.hstack([np.diff(t), 0.0])])
+        Q_s = Pinf - A_s @ Pinf @ np.swapaxes(A_s, -1, -2)
+        disc_f = ops.Disc.given(torch.as_tensor(A[None], device=dev), torch.as_tensor(Q[None], device=dev))
+        disc_s = ops.Disc.given(torch.as_tensor(A_s[None], device=dev), torch.as_tensor(Q_s[None], device=dev))
+        P0 = torch.as_tensor(Pinf[None], device=dev)
+    else:
+        from physs_gp_b200 import sdes
+        s_blk = d if d <= 4 else 4
+        prior = sdes.BatchedMaternSDE(s_blk, synth.log_uniform(rng, 0.5, 2.0, (B, d // s_blk)))
+        lam = torch.as_tensor(prior.lam(), device=dev)
+        P0 = torch.as_tensor(prior.P_inf(), device=dev)
+        disc_f = disc_s = ops.Disc.matern(d // s_blk, lam, P0)
+    m0 = torch.zeros((1, d), dtype=torch.float64, device=dev)
+    Hout = torch.as_tensor(rng.normal(size=(mo, d)), device=dev) if mo else None
+    res = []
+    for tm in (False, True):
+        Yl = Y.transpose(0, 1).contiguous().transpose(0, 1) if tm else Y
+        lml, mf, Pf, lk = ops.kf_filter(dt_f, Yl, R, H, m0, P0, disc_f, jitter=1e-5, want_lml_k=True)
+        ms, Ps = ops.rts_smooth(dt_s, mf, Pf, disc_s, Hout=Hout, jitter=1e-5)
+        assert Pf.transpose(0, 1).is_contiguous() == tm and Ps.transpose(0, 1).is_contiguous() == tm
+        res.append((lml, mf, Pf, lk, ms, Ps))
+    torch.cuda.synchronize()
+    for a, b in zip(*res):
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b)
