@@ -1,0 +1,68 @@
+"""-m gpu: the CUDA path (host API -> C ABI) against tests/golden/ -- outputs of the reference's own
+source files (tests/golden/README.md) -- with NO oracle in between.  Tolerance 1e-9 relative (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden.cases import CASES
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-9
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def product_prior(name):
+    from physs_gp_b200 import kernels as K
+    from physs_gp_b200 import sdes
+    latents, fso = CASES[name][0], CASES[name][1]
+    kind = {"m32": K.Matern32, "m52": K.Matern52, "m72": K.Matern72}
+    lat = [K.sum_kernels([kind[k](ls, var) for k, ls, var in parts]) for parts in latents]
+    ind = sdes.Independent(lat)
+    return sdes.LTI_SDE_Full_State_Obs(ind) if fso else sdes.LTI_SDE(ind)
+
+
+@pytest.mark.parametrize("jit", [1e-5, 0.0])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_filter_smoother_matches_reference_vectors(cuda_device, name, jit, monkeypatch):
+    from physs_gp_b200 import data, filters, settings
+    monkeypatch.setattr(settings, "jitter", jit)
+    g = np.load(os.path.join(GOLD, "filter_%s_jit%s.npz" % (name, "1e-5" if jit else "0")))
+    prior = product_prior(name)
+    d = data.TemporalData(g["t"], g["Y"][:, :, None])
+    lml, kf = filters.filter_loop(d, prior, R=g["R"])
+    assert abs(float(lml) - float(g["seq_lml"])) <= TOL * abs(float(g["seq_lml"]))
+    assert rel(kf['m'], g["seq_mf"]) < TOL and rel(kf['P'], g["seq_Pf"]) < TOL
+    for fs in (False, True):
+        mu, var = filters.smoother_loop(d, prior, kf, full_state=fs)
+        assert rel(mu, g["seq_ms_full%d" % fs]) < TOL and rel(var, g["seq_Ps_full%d" % fs]) < TOL
+
+
+def test_cuda_cvi_blocks_match_reference_vectors(cuda_device):
+    """theta -> lambda -> cvi_block_update -> theta (one fused kernel) and the closed-form block ELL."""
+    from physs_gp_b200 import cvi
+    g = np.load(os.path.join(GOLD, "cvi_blocks.npz"))
+
+    def dev(x):
+        return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64).cuda()
+    for D in (1, 3, 6):
+        for tag, ngj in (("1e-7", 1e-7), ("1e-5", 1e-5)):
+            k = "D%d_ngj%s_" % (D, tag)
+            # reference: lambda' = cvi_block_update(theta_to_lambda(Y~, V~), ...); theta' = lambda_to_theta(lambda')
+            from oracle import cvi as ocvi   # only the (pinned) lambda -> theta of the reference's n1, n2
+            t1, t2 = ocvi.lambda_to_theta(g[k + "n1"], g[k + "n2"], ngj)
+            Yn, Vn = cvi.natgrad_step(dev(g[k + "Yt"][None, :, 0]), dev(g[k + "V"][None]), dev(g[k + "mq"][None, :, 0]),
+                                      dev(g[k + "S"][None]), None, None, None, float(g[k + "beta"]), ng_jitter=ngj,
+                                      dm=dev(g[k + "dm"][None, :, 0]), dS=dev(g[k + "dS"][None]))
+            cond = np.linalg.cond(g[k + "V"]) * np.linalg.cond(-2 * g[k + "n2"] + ngj * np.eye(D))
+            assert rel(Vn[0], t2) < TOL * max(1.0, cond) and rel(Yn[0], t1[:, 0]) < TOL * max(1.0, cond)
+            ell = cvi.expected_log_likelihood(dev(g[k + "mq"][None, :, 0]), dev(g[k + "S"][None]),
+                                              dev(g[k + "Yobs"][None, :, 0]), None, cvi.GaussianLik(np.eye(D)),
+                                              noise=dev(g[k + "V"][None]))
+            assert abs(float(ell[0]) - float(g[k + "ell"])) <= TOL * abs(float(g[k + "ell"]))
