@@ -115,6 +115,106 @@ int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_bstrid
                          double jitter,
                          double* ms, double* Ps);
 
+/* ------------------------------------------------------------------------------------------------
+ * Parallel-in-time forms.  Replace filter('parallel') / smoother('parallel')
+ * (computation/filters/parallel_kalman_filter.py:225-336 with the elements :73-175 and the operator
+ * :178-220; parallel_rts_smoother.py:57-103 with :21-55).  Same inputs / outputs as the sequential entry
+ * points; the time axis is cut into chunks of `chunk_len` steps, each chunk is folded into ONE scan
+ * element on chip, the reference's associative operators run between chunks only, and all chunks are then
+ * replayed concurrently by the sequential kernels (physs_gp_b200/csrc/physs_pscan.cu).
+ *
+ * Result contract: the SEQUENTIAL reference result (the default filter_type; SURVEY.md quirk Q1 -- the
+ * reference's own parallel path starts from 2 P_inf and is inconsistent with its sequential path).
+ * With jitter == 0 the scan is exact.  With jitter != 0 the reference's sequential recursion (jitter in
+ * the gain solve only, kalman_filter.py:144-211 + linalg.py:29-33) is not representable by scan elements;
+ * `polish` fix-up passes re-run every chunk from the previous chunk's replayed end state until it agrees
+ * with the stored result to `delta` (relative) for `patience` consecutive steps.  *status (device int,
+ * may be NULL) is 1 if some chunk reached its end without agreeing (raise chunk_len or polish).
+ *
+ *   ws: device workspace of physs_pscan_workspace_bytes(B, T, d, chunk_len) bytes, 16-byte aligned; it
+ *       carries state from *_local to *_finish.  lml_k may be NULL (the workspace is used).
+ *
+ * Time-sharded use (one long series over several GPUs): every rank calls *_local
+ * on its own time range and receives the scan element of the whole range (`total`: filter
+ * [B, 3 d^2 + 2 d] = [A | C | J | b | eta], smoother [B, 2 d^2 + d] = [E | L | g]); the totals are
+ * all-gathered (NCCL); *_fold pushes the prior through the totals of the preceding ranks (filter) or the
+ * terminal state through those of the following ranks (smoother); *_finish replays the local range from
+ * that carried state.
+ */
+int64_t physs_pscan_workspace_bytes(int64_t B, int64_t T, int32_t d, int64_t chunk_len);
+
+int physs_pscan_filter_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                           int32_t d, int32_t m, int32_t disc_mode, int32_t nblk,
+                           const double* A, int64_t A_bstride, const double* Q, int64_t Q_bstride,
+                           const double* lam, int64_t lam_bstride, const double* dt, int64_t dt_bstride,
+                           const double* Pinf, int64_t Pinf_bstride, const double* m0, int64_t m0_bstride,
+                           const double* P0, int64_t P0_bstride, const double* H, int64_t H_bstride,
+                           const double* Y, const double* R, int64_t R_bstride, int64_t R_tstride,
+                           double jitter,
+                           int64_t chunk_len, int32_t polish, double delta, int32_t patience, void* ws,
+                           double* mf, double* Pf, double* lml, double* lml_k, int32_t* status);
+
+int physs_pscan_filter_local_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                                 int32_t d, int32_t m, int32_t disc_mode, int32_t nblk,
+                                 const double* A, int64_t A_bstride, const double* Q, int64_t Q_bstride,
+                                 const double* lam, int64_t lam_bstride, const double* dt, int64_t dt_bstride,
+                                 const double* Pinf, int64_t Pinf_bstride, const double* m0, int64_t m0_bstride,
+                                 const double* P0, int64_t P0_bstride, const double* H, int64_t H_bstride,
+                                 const double* Y, const double* R, int64_t R_bstride, int64_t R_tstride,
+                                 double jitter,
+                                 int64_t chunk_len, void* ws, double* total);
+
+/* start_m [B, d], start_P [B, d, d]: filtered state just before this time range (NULL = (m0, P0)). */
+int physs_pscan_filter_finish_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                                  int32_t d, int32_t m, int32_t disc_mode, int32_t nblk,
+                                  const double* A, int64_t A_bstride, const double* Q, int64_t Q_bstride,
+                                  const double* lam, int64_t lam_bstride, const double* dt, int64_t dt_bstride,
+                                  const double* Pinf, int64_t Pinf_bstride, const double* m0, int64_t m0_bstride,
+                                  const double* P0, int64_t P0_bstride, const double* H, int64_t H_bstride,
+                                  const double* Y, const double* R, int64_t R_bstride, int64_t R_tstride,
+                                  double jitter,
+                                  int64_t chunk_len, int32_t polish, double delta, int32_t patience, void* ws,
+                                  const double* start_m, const double* start_P,
+                                  double* mf, double* Pf, double* lml, double* lml_k, int32_t* status);
+
+/* (m_out, P_out) = (m0, P0) pushed through totals[0 .. K-1] ([K, B, 3 d^2 + 2 d], time order). */
+int physs_pscan_filter_fold_f64(void* stream, int64_t B, int32_t d, int64_t K, const double* totals,
+                                const double* m0, int64_t m0_bstride, const double* P0, int64_t P0_bstride,
+                                double* m_out, double* P_out);
+
+int physs_pscan_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                           int32_t d, int32_t disc_mode, int32_t nblk,
+                           const double* A, int64_t A_bstride, const double* Q, int64_t Q_bstride,
+                           const double* lam, int64_t lam_bstride, const double* dt, int64_t dt_bstride,
+                           const double* Pinf, int64_t Pinf_bstride,
+                           const double* mf, const double* Pf, const double* Hout, int32_t mo, double jitter,
+                           int64_t chunk_len, void* ws, double* ms, double* Ps);
+
+int physs_pscan_smooth_local_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                                 int32_t d, int32_t disc_mode, int32_t nblk,
+                                 const double* A, int64_t A_bstride, const double* Q, int64_t Q_bstride,
+                                 const double* lam, int64_t lam_bstride, const double* dt, int64_t dt_bstride,
+                                 const double* Pinf, int64_t Pinf_bstride,
+                                 const double* mf, const double* Pf, const double* Hout, int32_t mo, double jitter,
+                                 int64_t chunk_len, void* ws, double* total);
+
+/* start_m [B, d], start_P [B, d, d]: smoothed state of the first step AFTER this time range (NULL = this
+ * range ends the series: terminal condition smoothed = filtered at T - 1).  On a range that does not end
+ * the series, dt[T - 1] must be the gap to that next step. */
+int physs_pscan_smooth_finish_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                                  int32_t d, int32_t disc_mode, int32_t nblk,
+                                  const double* A, int64_t A_bstride, const double* Q, int64_t Q_bstride,
+                                  const double* lam, int64_t lam_bstride, const double* dt, int64_t dt_bstride,
+                                  const double* Pinf, int64_t Pinf_bstride,
+                                  const double* mf, const double* Pf, const double* Hout, int32_t mo, double jitter,
+                                  int64_t chunk_len, void* ws, const double* start_m, const double* start_P,
+                                  double* ms, double* Ps);
+
+/* (m_out, P_out) = the state (m_end, P_end) [B, d], [B, d, d] pulled back through totals[K-1 .. 0]
+ * ([K, B, 2 d^2 + d], time order). */
+int physs_pscan_smooth_fold_f64(void* stream, int64_t B, int32_t d, int64_t K, const double* totals,
+                                const double* m_end, const double* P_end, double* m_out, double* P_out);
+
 /* CVI likelihood kinds */
 #define PHYSS_LIK_GAUSS 0            /* y = W u + e, e ~ N(0, noise): closed-form block ELL               */
 #define PHYSS_LIK_POISSON_EXP 1      /* independent Poisson(binsize * exp(f_p)), f = W u, Gauss-Hermite   */

@@ -12,12 +12,21 @@ LIB_PATH = os.path.join(_HERE, "libphyss_b200.so")
 PHYSS_OK = 0
 DISC_GIVEN = 0
 DISC_MATERN = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _c_i32 = ctypes.c_int32
 _c_i64 = ctypes.c_int64
 _c_f64 = ctypes.c_double
 _ptr = ctypes.c_void_p
+
+# shared argument prefixes of the filter / smoother families (include/physs_b200.h)
+_FILTER_HEAD = [_ptr, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32,
+                _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
+                _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
+                _ptr, _ptr, _c_i64, _c_i64, _c_f64]
+_SMOOTH_HEAD = [_ptr, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32,
+                _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
+                _ptr, _ptr, _ptr, _c_i32, _c_f64]
 
 # name -> (restype, argtypes); must list every symbol include/physs_b200.h declares.
 SIGNATURES = {
@@ -34,6 +43,18 @@ SIGNATURES = {
         _ptr, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32,
         _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
         _ptr, _ptr, _ptr, _c_i32, _c_f64, _ptr, _ptr]),
+    "physs_pscan_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i32, _c_i64]),
+    "physs_pscan_filter_f64": (ctypes.c_int, _FILTER_HEAD + [_c_i64, _c_i32, _c_f64, _c_i32, _ptr,
+                                                            _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "physs_pscan_filter_local_f64": (ctypes.c_int, _FILTER_HEAD + [_c_i64, _ptr, _ptr]),
+    "physs_pscan_filter_finish_f64": (ctypes.c_int, _FILTER_HEAD + [_c_i64, _c_i32, _c_f64, _c_i32, _ptr, _ptr, _ptr,
+                                                                   _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "physs_pscan_filter_fold_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _c_i64, _ptr, _ptr, _c_i64, _ptr, _c_i64,
+                                                   _ptr, _ptr]),
+    "physs_pscan_smooth_f64": (ctypes.c_int, _SMOOTH_HEAD + [_c_i64, _ptr, _ptr, _ptr]),
+    "physs_pscan_smooth_local_f64": (ctypes.c_int, _SMOOTH_HEAD + [_c_i64, _ptr, _ptr]),
+    "physs_pscan_smooth_finish_f64": (ctypes.c_int, _SMOOTH_HEAD + [_c_i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "physs_pscan_smooth_fold_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _c_i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "physs_cvi_natgrad_step_f64": (ctypes.c_int, [
         _ptr, _c_i64, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64,
         _c_f64, _c_i32, _ptr, _ptr, _ptr, _ptr, _c_f64, _c_f64, _ptr, _ptr, _ptr]),

@@ -21,6 +21,21 @@ int cuda_status(cudaError_t e, const char* what) {
 
 }  // namespace physs
 
+namespace physs {
+
+int run_filter_any(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity, const SeqFilterArgs& a) {
+  if (seq_supported(d, m, disc_mode, nblk)) return seq_filter(st, d, m, disc_mode, nblk, h_identity, a);
+  if (m > d) return set_error(PHYSS_ERR_UNSUPPORTED, "filter: m > d is not supported");
+  return grp_filter(st, d, m, disc_mode, nblk, h_identity, a);
+}
+
+int run_smooth_any(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a) {
+  if (seq_supported(d, mo == 0 ? d : mo, disc_mode, nblk)) return seq_smooth(st, d, mo, disc_mode, nblk, a);
+  return grp_smooth(st, d, mo, disc_mode, nblk, a);
+}
+
+}  // namespace physs
+
 using namespace physs;
 
 static inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
@@ -37,7 +52,7 @@ static inline bool step_strides_ok(int64_t B, int64_t T, int64_t bs, int64_t ts)
 
 extern "C" {
 
-int physs_abi_version(void) { return 2; }
+int physs_abi_version(void) { return 3; }
 
 const char* physs_last_error(void) { return g_err; }
 
@@ -49,21 +64,30 @@ int physs_kf_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {
   return grp_supported(d, m) ? 1 : 0;
 }
 
-int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
-                        int32_t d, int32_t m,
-                        int32_t disc_mode, int32_t nblk,
-                        const double* A, int64_t A_bstride,
-                        const double* Q, int64_t Q_bstride,
-                        const double* lam, int64_t lam_bstride,
-                        const double* dt, int64_t dt_bstride,
-                        const double* Pinf, int64_t Pinf_bstride,
-                        const double* m0, int64_t m0_bstride,
-                        const double* P0, int64_t P0_bstride,
-                        const double* H, int64_t H_bstride,
-                        const double* Y,
-                        const double* R, int64_t R_bstride, int64_t R_tstride,
-                        double jitter,
-                        double* mf, double* Pf, double* lml, double* lml_k) {
+// ---- shared argument checking / packing of the filter and smoother families
+#define FILTER_PARAMS                                                                             \
+  void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride, int32_t d, int32_t m, \
+      int32_t disc_mode, int32_t nblk, const double* A, int64_t A_bstride, const double* Q,      \
+      int64_t Q_bstride, const double* lam, int64_t lam_bstride, const double* dt, int64_t dt_bstride, \
+      const double* Pinf, int64_t Pinf_bstride, const double* m0, int64_t m0_bstride, const double* P0, \
+      int64_t P0_bstride, const double* H, int64_t H_bstride, const double* Y, const double* R,   \
+      int64_t R_bstride, int64_t R_tstride, double jitter
+#define FILTER_ARGS                                                                               \
+  stream, B, T, step_bstride, step_tstride, d, m, disc_mode, nblk, A, A_bstride, Q, Q_bstride, lam, \
+      lam_bstride, dt, dt_bstride, Pinf, Pinf_bstride, m0, m0_bstride, P0, P0_bstride, H, H_bstride, Y, R, \
+      R_bstride, R_tstride, jitter
+#define SMOOTH_PARAMS                                                                             \
+  void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride, int32_t d,     \
+      int32_t disc_mode, int32_t nblk, const double* A, int64_t A_bstride, const double* Q,      \
+      int64_t Q_bstride, const double* lam, int64_t lam_bstride, const double* dt, int64_t dt_bstride, \
+      const double* Pinf, int64_t Pinf_bstride, const double* mf, const double* Pf, const double* Hout, \
+      int32_t mo, double jitter
+#define SMOOTH_ARGS                                                                               \
+  stream, B, T, step_bstride, step_tstride, d, disc_mode, nblk, A, A_bstride, Q, Q_bstride, lam, lam_bstride, \
+      dt, dt_bstride, Pinf, Pinf_bstride, mf, Pf, Hout, mo, jitter
+
+static int pack_filter(FILTER_PARAMS, double* mf, double* Pf, double* lml, double* lml_k, SeqFilterArgs& a) {
+  (void)stream;
   if (B < 0 || T < 1 || d < 1 || m < 1) return set_error(PHYSS_ERR_BAD_ARG, "filter: bad sizes");
   if (B == 0) return PHYSS_OK;
   if (!dt || !m0 || !P0 || !Y || !R || !mf || !Pf || !lml)
@@ -81,7 +105,7 @@ int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride
   }
   if (!step_strides_ok(B, T, step_bstride, step_tstride))
     return set_error(PHYSS_ERR_BAD_ARG, "filter: step strides must be (0,0), batch-major (>=T,1) or time-major (1,>=B)");
-  SeqFilterArgs a{};
+  a = SeqFilterArgs{};
   a.B = B; a.T = T;
   a.sbs = step_bstride ? step_bstride : T; a.sts = step_bstride ? step_tstride : 1;
   a.A = A; a.A_bs = A_bstride; a.Q = Q; a.Q_bs = Q_bstride;
@@ -90,28 +114,14 @@ int physs_kf_filter_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride
   a.P0 = P0; a.P0_bs = P0_bstride; a.H = H; a.H_bs = H_bstride;
   a.Y = Y; a.R = R; a.R_bs = R_bstride; a.R_ts = R_tstride;
   a.jitter = jitter; a.mf = mf; a.Pf = Pf; a.lml = lml; a.lml_k = lml_k;
-  if (seq_supported(d, m, disc_mode, nblk))
-    return seq_filter((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a);
-  if (m > d) return set_error(PHYSS_ERR_UNSUPPORTED, "filter: m > d is not supported");
-  return grp_filter((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a);
+  return PHYSS_OK;
 }
 
-int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
-                         int32_t d,
-                         int32_t disc_mode, int32_t nblk,
-                         const double* A, int64_t A_bstride,
-                         const double* Q, int64_t Q_bstride,
-                         const double* lam, int64_t lam_bstride,
-                         const double* dt, int64_t dt_bstride,
-                         const double* Pinf, int64_t Pinf_bstride,
-                         const double* mf, const double* Pf,
-                         const double* Hout, int32_t mo,
-                         double jitter,
-                         double* ms, double* Ps) {
+static int pack_smooth(SMOOTH_PARAMS, double* ms, double* Ps, SeqSmoothArgs& a) {
+  (void)stream;
   if (B < 0 || T < 1 || d < 1 || mo < 0) return set_error(PHYSS_ERR_BAD_ARG, "smoother: bad sizes");
   if (B == 0) return PHYSS_OK;
-  if (!dt || !mf || !Pf || !ms || !Ps)
-    return set_error(PHYSS_ERR_BAD_ARG, "smoother: null required pointer");
+  if (!dt || !mf || !Pf) return set_error(PHYSS_ERR_BAD_ARG, "smoother: null required pointer");
   if (mo > 0 && !Hout) return set_error(PHYSS_ERR_BAD_ARG, "smoother: mo > 0 needs Hout");
   if (any_misaligned(A, Q, Pinf, mf, Pf, ms, Ps))
     return set_error(PHYSS_ERR_BAD_ARG, "smoother: matrix/vector pointers must be 16-byte aligned");
@@ -125,17 +135,124 @@ int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_bstrid
   }
   if (!step_strides_ok(B, T, step_bstride, step_tstride))
     return set_error(PHYSS_ERR_BAD_ARG, "smoother: step strides must be (0,0), batch-major (>=T,1) or time-major (1,>=B)");
-  SeqSmoothArgs a{};
+  a = SeqSmoothArgs{};
   a.B = B; a.T = T;
   a.sbs = step_bstride ? step_bstride : T; a.sts = step_bstride ? step_tstride : 1;
   a.A = A; a.A_bs = A_bstride; a.Q = Q; a.Q_bs = Q_bstride;
   a.lam = lam; a.lam_bs = lam_bstride; a.dt = dt; a.dt_bs = dt_bstride;
   a.Pinf = Pinf; a.Pinf_bs = Pinf_bstride; a.mf = mf; a.Pf = Pf;
   a.Hout = (mo > 0) ? Hout : nullptr; a.jitter = jitter; a.ms = ms; a.Ps = Ps;
-  const int mo_eff = Hout ? mo : 0;
-  if (seq_supported(d, mo_eff == 0 ? d : mo_eff, disc_mode, nblk))
-    return seq_smooth((cudaStream_t)stream, d, mo_eff, disc_mode, nblk, a);
-  return grp_smooth((cudaStream_t)stream, d, mo_eff, disc_mode, nblk, a);
+  return PHYSS_OK;
+}
+
+static int check_chunk(int64_t T, int64_t chunk_len, const void* ws) {
+  if (chunk_len < 1 || chunk_len > T) return set_error(PHYSS_ERR_BAD_ARG, "pscan: need 1 <= chunk_len <= T");
+  if (!ws || misaligned(ws)) return set_error(PHYSS_ERR_BAD_ARG, "pscan: workspace missing or misaligned");
+  return PHYSS_OK;
+}
+
+int physs_kf_filter_f64(FILTER_PARAMS, double* mf, double* Pf, double* lml, double* lml_k) {
+  SeqFilterArgs a;
+  int rc = pack_filter(FILTER_ARGS, mf, Pf, lml, lml_k, a);
+  if (rc || B == 0) return rc;
+  return run_filter_any((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a);
+}
+
+int physs_rts_smooth_f64(SMOOTH_PARAMS, double* ms, double* Ps) {
+  SeqSmoothArgs a;
+  int rc = pack_smooth(SMOOTH_ARGS, ms, Ps, a);
+  if (rc || B == 0) return rc;
+  if (!ms || !Ps) return set_error(PHYSS_ERR_BAD_ARG, "smoother: null output pointer");
+  return run_smooth_any((cudaStream_t)stream, d, Hout ? mo : 0, disc_mode, nblk, a);
+}
+
+int64_t physs_pscan_workspace_bytes(int64_t B, int64_t T, int32_t d, int64_t chunk_len) {
+  if (B < 1 || T < 1 || d < 1 || chunk_len < 1) return 0;
+  return 8 * pscan_workspace_doubles(B, T, d, chunk_len);
+}
+
+int physs_pscan_filter_f64(FILTER_PARAMS, int64_t chunk_len, int32_t polish, double delta, int32_t patience,
+                           void* ws, double* mf, double* Pf, double* lml, double* lml_k, int32_t* status) {
+  SeqFilterArgs a;
+  int rc = pack_filter(FILTER_ARGS, mf, Pf, lml, lml_k, a);
+  if (rc || B == 0) return rc;
+  if ((rc = check_chunk(T, chunk_len, ws))) return rc;
+  rc = pscan_filter_local((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a, chunk_len, (double*)ws, nullptr);
+  if (rc) return rc;
+  return pscan_filter_finish((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a, chunk_len, (double*)ws,
+                             false, nullptr, nullptr, polish, delta, patience, status);
+}
+
+int physs_pscan_filter_local_f64(FILTER_PARAMS, int64_t chunk_len, void* ws, double* total) {
+  SeqFilterArgs a;
+  double dummy;   // outputs are not touched by the local phase
+  int rc = pack_filter(FILTER_ARGS, (double*)ws, (double*)ws, &dummy, nullptr, a);
+  if (rc || B == 0) return rc;
+  if ((rc = check_chunk(T, chunk_len, ws))) return rc;
+  if (!total) return set_error(PHYSS_ERR_BAD_ARG, "pscan local: total is required");
+  return pscan_filter_local((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a, chunk_len, (double*)ws, total);
+}
+
+int physs_pscan_filter_finish_f64(FILTER_PARAMS, int64_t chunk_len, int32_t polish, double delta, int32_t patience,
+                                  void* ws, const double* start_m, const double* start_P, double* mf, double* Pf,
+                                  double* lml, double* lml_k, int32_t* status) {
+  SeqFilterArgs a;
+  int rc = pack_filter(FILTER_ARGS, mf, Pf, lml, lml_k, a);
+  if (rc || B == 0) return rc;
+  if ((rc = check_chunk(T, chunk_len, ws))) return rc;
+  return pscan_filter_finish((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a, chunk_len, (double*)ws,
+                             true, start_m, start_P, polish, delta, patience, status);
+}
+
+int physs_pscan_filter_fold_f64(void* stream, int64_t B, int32_t d, int64_t K, const double* totals,
+                                const double* m0, int64_t m0_bstride, const double* P0, int64_t P0_bstride,
+                                double* m_out, double* P_out) {
+  if (B < 0 || d < 1 || K < 0) return set_error(PHYSS_ERR_BAD_ARG, "pscan fold: bad sizes");
+  if (B == 0) return PHYSS_OK;
+  if (!m0 || !P0 || !m_out || !P_out || (K > 0 && !totals))
+    return set_error(PHYSS_ERR_BAD_ARG, "pscan fold: null required pointer");
+  return pscan_filter_fold((cudaStream_t)stream, d, B, K, totals, m0, m0_bstride, P0, P0_bstride, m_out, P_out);
+}
+
+int physs_pscan_smooth_f64(SMOOTH_PARAMS, int64_t chunk_len, void* ws, double* ms, double* Ps) {
+  SeqSmoothArgs a;
+  int rc = pack_smooth(SMOOTH_ARGS, ms, Ps, a);
+  if (rc || B == 0) return rc;
+  if (!ms || !Ps) return set_error(PHYSS_ERR_BAD_ARG, "smoother: null output pointer");
+  if ((rc = check_chunk(T, chunk_len, ws))) return rc;
+  rc = pscan_smooth_local((cudaStream_t)stream, d, disc_mode, nblk, a, chunk_len, (double*)ws, nullptr);
+  if (rc) return rc;
+  return pscan_smooth_finish((cudaStream_t)stream, d, Hout ? mo : 0, disc_mode, nblk, a, chunk_len, (double*)ws,
+                             nullptr, nullptr);
+}
+
+int physs_pscan_smooth_local_f64(SMOOTH_PARAMS, int64_t chunk_len, void* ws, double* total) {
+  SeqSmoothArgs a;
+  int rc = pack_smooth(SMOOTH_ARGS, nullptr, nullptr, a);
+  if (rc || B == 0) return rc;
+  if ((rc = check_chunk(T, chunk_len, ws))) return rc;
+  if (!total) return set_error(PHYSS_ERR_BAD_ARG, "pscan local: total is required");
+  return pscan_smooth_local((cudaStream_t)stream, d, disc_mode, nblk, a, chunk_len, (double*)ws, total);
+}
+
+int physs_pscan_smooth_finish_f64(SMOOTH_PARAMS, int64_t chunk_len, void* ws, const double* start_m,
+                                  const double* start_P, double* ms, double* Ps) {
+  SeqSmoothArgs a;
+  int rc = pack_smooth(SMOOTH_ARGS, ms, Ps, a);
+  if (rc || B == 0) return rc;
+  if (!ms || !Ps) return set_error(PHYSS_ERR_BAD_ARG, "smoother: null output pointer");
+  if ((rc = check_chunk(T, chunk_len, ws))) return rc;
+  return pscan_smooth_finish((cudaStream_t)stream, d, Hout ? mo : 0, disc_mode, nblk, a, chunk_len, (double*)ws,
+                             start_m, start_P);
+}
+
+int physs_pscan_smooth_fold_f64(void* stream, int64_t B, int32_t d, int64_t K, const double* totals,
+                                const double* m_end, const double* P_end, double* m_out, double* P_out) {
+  if (B < 0 || d < 1 || K < 0) return set_error(PHYSS_ERR_BAD_ARG, "pscan fold: bad sizes");
+  if (B == 0) return PHYSS_OK;
+  if (!m_end || !P_end || !m_out || !P_out || (K > 0 && !totals))
+    return set_error(PHYSS_ERR_BAD_ARG, "pscan fold: null required pointer");
+  return pscan_smooth_fold((cudaStream_t)stream, d, B, K, totals, m_end, P_end, m_out, P_out);
 }
 
 static int cvi_dispatch(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik, bool update,

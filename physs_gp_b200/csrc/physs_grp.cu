@@ -59,16 +59,18 @@ static GrpLayout make_layout(int d, int m, int mo, int nblk, bool given, bool sm
 // evaluated redundantly by every lane of the group
 __device__ __forceinline__ bool grp_agrees(const double* mv, const double* P, int ld, int d,
                                            const double* om, const double* oP, double delta) {
-  double dP = 0.0, sP = 0.0, dm = 0.0;
+  double dP = 0.0, sP = 0.0, dm = 0.0, sm = 0.0;
   for (int i = 0; i < d; ++i) {
-    dm = fmax(dm, fabs(mv[i] - om[i]));
+    const double omi = om[i];
+    dm = fmax(dm, fabs(mv[i] - omi));
+    sm = fmax(sm, fabs(omi));
     for (int j = 0; j < d; ++j) {
       const double o = oP[i * d + j];
       dP = fmax(dP, fabs(P[i * ld + j] - o));
       sP = fmax(sP, fabs(o));
     }
   }
-  return (dP <= delta * sP) && (dm * dm <= delta * delta * sP);
+  return (dP <= delta * sP) && (dm <= delta * sm || dm * dm <= delta * delta * sP);
 }
 
 // (series, chunk) owned by a group.  Plain mode: chunk 0 = the whole series.
@@ -113,7 +115,7 @@ __global__ void grp_filter_kernel(const SeqFilterArgs p, const GrpLayout L, cons
   double* mv_ = sm + L.vm; double* mp = sm + L.vmp; double* v = sm + L.vv; double* w = sm + L.vw;
   double* rd = sm + L.vrd; double* lam = sm + L.vlam;
 
-  if (chunked && p.fixup) {
+  if (chunked && p.from_bnd) {
     g2s<G>(P, ld, p.bnd_P + vs * d * d, d, d);
     for (int i = gl; i < d; i += G) mv_[i] = p.bnd_m[vs * d + i];
   } else {
@@ -358,7 +360,7 @@ __global__ void grp_smooth_kernel(const SeqSmoothArgs p, const GrpLayout L) {
   // plain mode: the last step is terminal.  Chunk mode: every step is an RTS step from the carried
   // state of the next chunk's first step; the last chunk carries its own last filtered state over
   // dt = 0, which reproduces the terminal condition (see physs_seq_impl.cuh).
-  const bool carried = chunked && wk.c < p.nchunk - 1;
+  const bool carried = chunked && (wk.c < p.nchunk - 1 || p.carry_last);
   if (carried) {
     g2s<G>(Ps, ld, p.bnd_P + vs * d * d, d, d);
     for (int i = gl; i < d; i += G) ms[i] = p.bnd_m[vs * d + i];
@@ -427,7 +429,7 @@ __global__ void grp_smooth_kernel(const SeqSmoothArgs p, const GrpLayout L) {
     // Ps = Pf + (G dP) G^T = Pf + W2 X
     mm<G, false, false>(Ps, ld, W2, ld, W1, ld, d, d, d, Pf, ld, 1.0);
     __syncwarp();
-    if (chunked && p.fixup && active && !done)
+    if (chunked && p.fixup && mo == 0 && active && !done)
       streak = grp_agrees(ms, Ps, ld, d, msp + k * sts * d, Psp + k * sts * d * d, p.delta) ? streak + 1 : 0;
     __syncwarp();
     emit(k);

@@ -35,6 +35,7 @@ struct SeqFilterArgs {
   // a launch have the same length (the ragged tail chunk gets its own launch).  nchunk = chunks per
   // series in total (boundary snapshots are indexed b * nchunk + c); nchunk == 0 means plain mode.
   int64_t nchunk, chunk_len, chunk_first, chunk_count;
+  int from_bnd;          // chunk starts from the boundary snapshot (bnd_m, bnd_P)[v] instead of (m0, P0)
   int fixup, patience;
   double delta;
   const double* bnd_m; const double* bnd_P;
@@ -60,6 +61,7 @@ struct SeqSmoothArgs {
   // a launch have the same length (the ragged tail chunk gets its own launch).  nchunk = chunks per
   // series in total (boundary snapshots are indexed b * nchunk + c); nchunk == 0 means plain mode.
   int64_t nchunk, chunk_len, chunk_first, chunk_count;
+  int carry_last;        // the last chunk also starts from its boundary snapshot (time-sharded ranges)
   int fixup, patience;
   double delta;
   const double* bnd_m; const double* bnd_P;
@@ -101,5 +103,21 @@ bool grp_supported(int d, int m);
 int grp_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity,
                const SeqFilterArgs& a);
 int grp_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
+
+// physs_pscan.cu: parallel-in-time chunked associative scan
+int64_t pscan_workspace_doubles(int64_t B, int64_t T, int d, int64_t chunk_len);
+int pscan_filter_local(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, SeqFilterArgs a,
+                       int64_t chunk_len, double* ws, double* total_out);
+int pscan_filter_finish(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, SeqFilterArgs a,
+                        int64_t chunk_len, double* ws, bool had_total, const double* start_m,
+                        const double* start_P, int polish, double delta, int patience, int* status_out);
+int pscan_filter_fold(cudaStream_t st, int d, int64_t B, int64_t K, const double* totals, const double* m0,
+                      int64_t m0_bs, const double* P0, int64_t P0_bs, double* m_out, double* P_out);
+int pscan_smooth_local(cudaStream_t st, int d, int disc_mode, int nblk, SeqSmoothArgs a, int64_t chunk_len,
+                       double* ws, double* total_out);
+int pscan_smooth_finish(cudaStream_t st, int d, int mo, int disc_mode, int nblk, SeqSmoothArgs a, int64_t chunk_len,
+                        double* ws, const double* start_m, const double* start_P);
+int pscan_smooth_fold(cudaStream_t st, int d, int64_t B, int64_t K, const double* totals, const double* m0,
+                      const double* P0, double* m_out, double* P_out);
 
 }  // namespace physs

@@ -211,10 +211,12 @@ template <int D>
 __device__ __forceinline__ bool agrees(const double (&m)[D], const double (&P)[D][D],
                                        const double* __restrict__ om, const double* __restrict__ oP,
                                        double delta) {
-  double dP = 0.0, sP = 0.0, dm = 0.0;
+  double dP = 0.0, sP = 0.0, dm = 0.0, sm = 0.0;
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    dm = fmax(dm, fabs(m[i] - om[i]));
+    const double omi = om[i];
+    dm = fmax(dm, fabs(m[i] - omi));
+    sm = fmax(sm, fabs(omi));
 #pragma unroll
     for (int j = 0; j < D; ++j) {
       const double o = oP[i * D + j];
@@ -222,7 +224,8 @@ __device__ __forceinline__ bool agrees(const double (&m)[D], const double (&P)[D
       sP = fmax(sP, fabs(o));
     }
   }
-  return (dP <= delta * sP) && (dm * dm <= delta * delta * sP);
+  // mean: relative to its own magnitude, or to the posterior standard deviation if that is larger
+  return (dP <= delta * sP) && (dm <= delta * sm || dm * dm <= delta * delta * sP);
 }
 
 template <int D, int S, int M, bool HID, bool GIVEN, bool CHUNK>
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) 
   const int64_t sts = p.sts;
 
   double m[D], P[D][D], Pinf[D][D], H[M][D], lam[NB];
-  if (CHUNK && p.fixup) {
+  if (CHUNK && p.from_bnd) {
     load_vec<D>(p.bnd_m + v * D, m);
     load_mat<D>(p.bnd_P + v * D * D, P);
   } else {
@@ -336,7 +339,6 @@ __global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) 
 // MO == 0: full_state (H = I).  MO > 0: project with Hout [MO, D].
 template <int D, int S, int MO, bool GIVEN, bool CHUNK, bool COAL>
 __global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) {
-  static_assert(!CHUNK || MO == 0, "chunk mode carries and compares the full state");
   __shared__ __align__(16) double tiles[4][RowTile<D * D>::SIZE];
   SeqWork wk;
   if (!seq_work<CHUNK>(p, wk)) return;
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) 
   // plain mode: the last step is terminal (smoothed = filtered).  Chunk mode: every step of the chunk
   // is an RTS step from the carried state of the next chunk's first step; the very last chunk carries
   // its own last filtered state across dt = 0, which reproduces the terminal condition.
-  const bool carried = CHUNK && wk.c < p.nchunk - 1;
+  const bool carried = CHUNK && (wk.c < p.nchunk - 1 || p.carry_last);
   int64_t kstart;
   if (CHUNK && carried) {
     load_vec<D>(p.bnd_m + v * D, ms);
@@ -491,8 +493,10 @@ __global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) 
       matern_trans<D, S>(lam, dt, A);
       rts_step<D, S>(A, Pinf, true, mf, Pf, p.jitter, ms, Ps);
     }
-    if (CHUNK && p.fixup && !done) {
-      streak = agrees<D>(ms, Ps, msp + k * sts * D, Psp + k * sts * D * D, p.delta) ? streak + 1 : 0;
+    if constexpr (MO == 0) {      // the fix-up comparison needs the stored full state
+      if (CHUNK && p.fixup && !done) {
+        streak = agrees<D>(ms, Ps, msp + k * sts * D, Psp + k * sts * D * D, p.delta) ? streak + 1 : 0;
+      }
     }
     emit(k, ms, Ps);
     if (CHUNK && p.fixup) {
@@ -531,12 +535,9 @@ static int launch_smooth(cudaStream_t st, const SeqSmoothArgs& a) {
   const int64_t grid = (n + block - 1) / block;
   const bool coal = (a.sbs == 1);
   if (a.nchunk > 0) {
-    if constexpr (MO == 0) {
-      if (coal) seq_smooth_kernel<D, S, 0, GIVEN, true, true><<<(unsigned)grid, block, 0, st>>>(a);
-      else seq_smooth_kernel<D, S, 0, GIVEN, true, false><<<(unsigned)grid, block, 0, st>>>(a);
-    } else {
-      return set_error(PHYSS_ERR_BAD_ARG, "chunked smoother needs full_state output");
-    }
+    if (MO != 0 && a.fixup) return set_error(PHYSS_ERR_BAD_ARG, "smoother fix-up needs full_state output");
+    if (coal) seq_smooth_kernel<D, S, MO, GIVEN, true, true><<<(unsigned)grid, block, 0, st>>>(a);
+    else seq_smooth_kernel<D, S, MO, GIVEN, true, false><<<(unsigned)grid, block, 0, st>>>(a);
   } else {
     if (coal) seq_smooth_kernel<D, S, MO, GIVEN, false, true><<<(unsigned)grid, block, 0, st>>>(a);
     else seq_smooth_kernel<D, S, MO, GIVEN, false, false><<<(unsigned)grid, block, 0, st>>>(a);

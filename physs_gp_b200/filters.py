@@ -77,8 +77,7 @@ def _is_identity(H):
     return H.shape[0] == H.shape[1] and np.array_equal(H, np.eye(H.shape[0]))
 
 
-@dispatch('b200')
-def filter(data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask, train_index):
+def _filter_impl(parallel, data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask, train_index):
     """B200 backend of evoke('filter', filter_type) -- kalman_filter.py:439-485.
 
     Y [T, m, 1] (or [B, T, m, 1]), lik_mat R [T, m, m] (or [B, T, m, m] / broadcastable),
@@ -103,14 +102,31 @@ def filter(data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask,
     (disc,), m0, P0, H = lower_prior(prior, X_s, [dtd], dev)
     R = _to_dev(lik_mat, dev)
     Hd = None if _is_identity(H) else _to_dev(H, dev)
-    lml, mf, Pf = ops.kf_filter(dtd, Yd, R, Hd, m0, P0, disc, jitter=settings.jitter)
+    if parallel:
+        lml, mf, Pf = ops.pscan_filter(dtd, Yd, R, Hd, m0, P0, disc, chunk_len=settings.pscan_chunk_len,
+                                       jitter=settings.jitter, polish=settings.pscan_polish)
+    else:
+        lml, mf, Pf = ops.kf_filter(dtd, Yd, R, Hd, m0, P0, disc, jitter=settings.jitter)
     if batched:
         return lml, {'m': mf[..., None], 'P': Pf}
     return lml[0], {'m': mf[0][..., None], 'P': Pf[0]}
 
 
 @dispatch('b200')
-def smoother(data, model, filter_res, dt, X_t, X_s, full_state):
+def filter(data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask, train_index):
+    """filter_type='b200': sequential-in-time kernels (one thread / lane group per series)."""
+    return _filter_impl(False, data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask, train_index)
+
+
+@dispatch('b200_parallel')
+def filter(data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask, train_index):  # noqa: F811
+    """filter_type='b200_parallel': parallel-in-time chunked associative scan (the counterpart of the
+    reference's filter('parallel'), parallel_kalman_filter.py:225-336).  Returns the SEQUENTIAL result
+    (SURVEY quirk Q1); use it for long series / small batches."""
+    return _filter_impl(True, data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask, train_index)
+
+
+def _smoother_impl(parallel, data, model, filter_res, dt, X_t, X_s, full_state):
     """B200 backend of evoke('smoother', filter_type) -- rts_smoother.py:162-192.
     dt [T] with dt[k] = t_{k+1} - t_k, dt[T-1] = 0."""
     dev = _device()
@@ -122,10 +138,26 @@ def smoother(data, model, filter_res, dt, X_t, X_s, full_state):
     dtd = _to_dev(dt, dev)
     (disc,), _, _, H = lower_prior(model, X_s, [dtd], dev)
     Hout = None if (full_state or _is_identity(H)) else _to_dev(H, dev)
-    ms, Ps = ops.rts_smooth(dtd, mf, Pf, disc, Hout=Hout, jitter=settings.jitter)
+    if parallel:
+        ms, Ps = ops.pscan_smooth(dtd, mf, Pf, disc, Hout=Hout, chunk_len=settings.pscan_chunk_len,
+                                  jitter=settings.jitter)
+    else:
+        ms, Ps = ops.rts_smooth(dtd, mf, Pf, disc, Hout=Hout, jitter=settings.jitter)
     if batched:
         return ms[..., None], Ps
     return ms[0][..., None], Ps[0]
+
+
+@dispatch('b200')
+def smoother(data, model, filter_res, dt, X_t, X_s, full_state):
+    return _smoother_impl(False, data, model, filter_res, dt, X_t, X_s, full_state)
+
+
+@dispatch('b200_parallel')
+def smoother(data, model, filter_res, dt, X_t, X_s, full_state):  # noqa: F811
+    """Counterpart of smoother('parallel') (parallel_rts_smoother.py:57-103); honours full_state
+    (the reference's parallel smoother ignores it)."""
+    return _smoother_impl(True, data, model, filter_res, dt, X_t, X_s, full_state)
 
 
 def _time_axis(data, dev):

@@ -105,6 +105,56 @@ def kf_supported(d, m, disc):
     return bool(_lib.load().physs_kf_supported(d, m, disc.mode, disc.nblk))
 
 
+class _Packed:
+    """Arguments of the filter / smoother families marshalled for the C ABI (+ tensors kept alive)."""
+    pass
+
+
+def _pack_filter(dt, Y, R, H, m0, P0, disc, jitter, stream):
+    if Y.dim() != 3:
+        raise ValueError("Y must be [B, T, m]")
+    Y, tmaj = step_layout(Y, "Y")
+    B, T, m = Y.shape
+    sbs, sts = _strides(B, T, tmaj)
+    P0v, sP0 = _bview(P0, "P0", (B, P0.shape[-1], P0.shape[-1]), 2)
+    d = P0v.shape[-1]
+    m0v, sm0 = _bview(m0, "m0", (B, d), 1)
+    dtv, sdt = _bview(dt, "dt", (B, T), 1)
+    Rv, sR = _bview(R, "R", (B, T, m, m), 2)   # any batch / time strides (0 = broadcast)
+    if H is None:
+        Hv, Hptr, sH = None, None, (0,)
+    else:
+        Hv, sH = _bview(H, "H", (B, m, d), 2)
+        Hptr = Hv.data_ptr()
+    keep, (pA, bA), (pQ, bQ), (pl, bl), (pPi, bPi) = _disc_args(disc, B, T, d)
+    jit = settings.jitter if jitter is None else jitter
+    p = _Packed()
+    p.B, p.T, p.d, p.m, p.tmaj, p.dev = B, T, d, m, tmaj, Y.device
+    p.keep = keep + [Y, P0v, m0v, dtv, Rv, Hv]
+    p.head = [_stream_ptr(stream), B, T, sbs, sts, d, m, disc.mode, disc.nblk,
+              pA, bA, pQ, bQ, pl, bl, dtv.data_ptr(), sdt[0], pPi, bPi,
+              m0v.data_ptr(), sm0[0], P0v.data_ptr(), sP0[0], Hptr, sH[0],
+              Y.data_ptr(), Rv.data_ptr(), sR[0], sR[1], float(jit)]
+    return p
+
+
+def _filter_outputs(p, out, want_lml_k):
+    B, T, d = p.B, p.T, p.d
+    if out is None:
+        mf = empty_steps(B, T, (d,), p.dev, p.tmaj)
+        Pf = empty_steps(B, T, (d, d), p.dev, p.tmaj)
+    else:
+        mf, Pf = out
+        ok = tuple(mf.shape) == (B, T, d) and tuple(Pf.shape) == (B, T, d, d)
+        for o in (mf, Pf):
+            ok = ok and (o.transpose(0, 1).is_contiguous() if p.tmaj else o.is_contiguous())
+        if not ok:
+            raise ValueError("out buffers must be [B,T,d] and [B,T,d,d] in the memory order of Y")
+    lml = torch.empty((B,), dtype=torch.float64, device=p.dev)
+    lml_k = empty_steps(B, T, (), p.dev, p.tmaj) if want_lml_k else None
+    return mf, Pf, lml, lml_k
+
+
 def kf_filter(dt, Y, R, H, m0, P0, disc, jitter=None, want_lml_k=False, out=None, stream=None):
     """Batched sequential Kalman filter (kalman_filter.py:439-485 semantics per series).
 
@@ -117,58 +167,18 @@ def kf_filter(dt, Y, R, H, m0, P0, disc, jitter=None, want_lml_k=False, out=None
     are produced time-major too (logical shape still [B, T, ...]) -- the fast, coalesced layout.
     """
     lib = _lib.load()
-    if Y.dim() != 3:
-        raise ValueError("Y must be [B, T, m]")
-    Y, tmaj = step_layout(Y, "Y")
-    B, T, m = Y.shape
-    sbs, sts = _strides(B, T, tmaj)
-    P0v, sP0 = _bview(P0, "P0", (B, P0.shape[-1], P0.shape[-1]), 2)
-    d = P0v.shape[-1]
-    m0v, sm0 = _bview(m0, "m0", (B, d), 1)
-    dtv, sdt = _bview(dt, "dt", (B, T), 1)
-    Rv, sR = _bview(R, "R", (B, T, m, m), 2)   # any batch / time strides (0 = broadcast)
-    if H is None:
-        Hptr, sH = None, (0,)
-    else:
-        Hv, sH = _bview(H, "H", (B, m, d), 2)
-        Hptr = Hv.data_ptr()
-    keep, (pA, bA), (pQ, bQ), (pl, bl), (pPi, bPi) = _disc_args(disc, B, T, d)
-    dev = Y.device
-    if out is None:
-        mf = empty_steps(B, T, (d,), dev, tmaj)
-        Pf = empty_steps(B, T, (d, d), dev, tmaj)
-    else:
-        mf, Pf = out
-        ok = tuple(mf.shape) == (B, T, d) and tuple(Pf.shape) == (B, T, d, d)
-        for o in (mf, Pf):
-            ok = ok and (o.transpose(0, 1).is_contiguous() if tmaj else o.is_contiguous())
-        if not ok:
-            raise ValueError("out buffers must be [B,T,d] and [B,T,d,d] in the memory order of Y")
-    lml = torch.empty((B,), dtype=torch.float64, device=dev)
-    lml_k = empty_steps(B, T, (), dev, tmaj) if want_lml_k else None
-    jit = settings.jitter if jitter is None else jitter
-    with torch.cuda.device(dev):
-        st = lib.physs_kf_filter_f64(
-            _stream_ptr(stream), B, T, sbs, sts, d, m, disc.mode, disc.nblk,
-            pA, bA, pQ, bQ, pl, bl, dtv.data_ptr(), sdt[0], pPi, bPi,
-            m0v.data_ptr(), sm0[0], P0v.data_ptr(), sP0[0], Hptr, sH[0],
-            Y.data_ptr(), Rv.data_ptr(), sR[0], sR[1], float(jit),
-            mf.data_ptr(), Pf.data_ptr(), lml.data_ptr(),
-            lml_k.data_ptr() if lml_k is not None else None)
+    p = _pack_filter(dt, Y, R, H, m0, P0, disc, jitter, stream)
+    mf, Pf, lml, lml_k = _filter_outputs(p, out, want_lml_k)
+    with torch.cuda.device(p.dev):
+        st = lib.physs_kf_filter_f64(*p.head, mf.data_ptr(), Pf.data_ptr(), lml.data_ptr(),
+                                     lml_k.data_ptr() if lml_k is not None else None)
     _lib.check(st, "physs_kf_filter_f64")
     if want_lml_k:
         return lml, mf, Pf, lml_k
     return lml, mf, Pf
 
 
-def rts_smooth(dt, mf, Pf, disc, Hout=None, jitter=None, out=None, stream=None):
-    """Batched sequential RTS smoother (rts_smoother.py:162-192 semantics per series).
-
-    dt -> [B, T] (dt[k] = t_{k+1} - t_k, dt[T-1] = 0);  mf [B, T, d], Pf [B, T, d, d];
-    Hout [mo, d] projects the output (None = full_state=True).
-    Returns (ms [B, T, mo'], Ps [B, T, mo', mo']).
-    """
-    lib = _lib.load()
+def _pack_smooth(dt, mf, Pf, disc, Hout, jitter, stream):
     mf, tmaj = step_layout(mf, "mf")
     Pf, tmaj_P = step_layout(Pf, "Pf")
     if tmaj != tmaj_P:
@@ -183,20 +193,184 @@ def rts_smooth(dt, mf, Pf, disc, Hout=None, jitter=None, out=None, stream=None):
         Hout = _dev(Hout, "Hout").contiguous()
         mo = Hout.shape[0]
         Hptr, mp = Hout.data_ptr(), mo
-    dev = mf.device
+    jit = settings.jitter if jitter is None else jitter
+    p = _Packed()
+    p.B, p.T, p.d, p.mp, p.tmaj, p.dev = B, T, d, mp, tmaj, mf.device
+    p.keep = keep + [mf, Pf, dtv, Hout]
+    p.head = [_stream_ptr(stream), B, T, sbs, sts, d, disc.mode, disc.nblk,
+              pA, bA, pQ, bQ, pl, bl, dtv.data_ptr(), sdt[0], pPi, bPi,
+              mf.data_ptr(), Pf.data_ptr(), Hptr, mo, float(jit)]
+    return p
+
+
+def _smooth_outputs(p, out):
     if out is None:
-        ms = empty_steps(B, T, (mp,), dev, tmaj)
-        Ps = empty_steps(B, T, (mp, mp), dev, tmaj)
+        ms = empty_steps(p.B, p.T, (p.mp,), p.dev, p.tmaj)
+        Ps = empty_steps(p.B, p.T, (p.mp, p.mp), p.dev, p.tmaj)
     else:
         ms, Ps = out
         for o in (ms, Ps):
-            if not (o.transpose(0, 1).is_contiguous() if tmaj else o.is_contiguous()):
+            if not (o.transpose(0, 1).is_contiguous() if p.tmaj else o.is_contiguous()):
                 raise ValueError("out buffers must be in the memory order of mf / Pf")
-    jit = settings.jitter if jitter is None else jitter
-    with torch.cuda.device(dev):
-        st = lib.physs_rts_smooth_f64(
-            _stream_ptr(stream), B, T, sbs, sts, d, disc.mode, disc.nblk,
-            pA, bA, pQ, bQ, pl, bl, dtv.data_ptr(), sdt[0], pPi, bPi,
-            mf.data_ptr(), Pf.data_ptr(), Hptr, mo, float(jit), ms.data_ptr(), Ps.data_ptr())
+    return ms, Ps
+
+
+def rts_smooth(dt, mf, Pf, disc, Hout=None, jitter=None, out=None, stream=None):
+    """Batched sequential RTS smoother (rts_smoother.py:162-192 semantics per series).
+
+    dt -> [B, T] (dt[k] = t_{k+1} - t_k, dt[T-1] = 0);  mf [B, T, d], Pf [B, T, d, d];
+    Hout [mo, d] projects the output (None = full_state=True).
+    Returns (ms [B, T, mo'], Ps [B, T, mo', mo']).
+    """
+    lib = _lib.load()
+    p = _pack_smooth(dt, mf, Pf, disc, Hout, jitter, stream)
+    ms, Ps = _smooth_outputs(p, out)
+    with torch.cuda.device(p.dev):
+        st = lib.physs_rts_smooth_f64(*p.head, ms.data_ptr(), Ps.data_ptr())
     _lib.check(st, "physs_rts_smooth_f64")
+    return ms, Ps
+
+
+# ------------------------------------------------------------------------------- parallel-in-time
+def default_chunk_len(B, T):
+    """Chunk length that gives the GPU ~ 148 SMs x 16 lane groups of independent work, clamped to
+    [32, T]: long single series get many short chunks, large batches few long ones."""
+    want_chunks = max(1, (148 * 16 + B - 1) // B)
+    return int(min(T, max(32, -(-T // want_chunks))))
+
+
+def pscan_workspace(B, T, d, chunk_len, dev):
+    n = _lib.load().physs_pscan_workspace_bytes(B, T, d, chunk_len)
+    return torch.empty((n // 8,), dtype=torch.float64, device=dev)
+
+
+def _polish_default(jit, polish):
+    """Fix-up passes after the scan.  Each pass contracts the O(jitter) boundary error by the filter's
+    forgetting over one chunk; a pass whose chunks already agree exits after `patience` steps, so spare
+    passes cost a few steps per chunk.  None: 4 passes when jitter != 0, none when the scan is exact."""
+    if polish is None:
+        return 4 if jit != 0.0 else 0
+    return int(polish)
+
+
+def pscan_filter(dt, Y, R, H, m0, P0, disc, chunk_len=None, jitter=None, polish=None, delta=1e-10, patience=4,
+                 want_lml_k=False, out=None, ws=None, stream=None, return_status=False):
+    """Parallel-in-time Kalman filter: same arguments / results as kf_filter (see include/physs_b200.h,
+    'Parallel-in-time forms').  `polish=None` picks 4 fix-up passes when jitter != 0 and none otherwise.
+    With return_status the device flag (1 = a chunk did not converge during polishing) is appended."""
+    lib = _lib.load()
+    p = _pack_filter(dt, Y, R, H, m0, P0, disc, jitter, stream)
+    L = default_chunk_len(p.B, p.T) if chunk_len is None else int(chunk_len)
+    mf, Pf, lml, lml_k = _filter_outputs(p, out, want_lml_k)
+    ws = pscan_workspace(p.B, p.T, p.d, L, p.dev) if ws is None else ws
+    status = torch.zeros((1,), dtype=torch.int32, device=p.dev)
+    with torch.cuda.device(p.dev):
+        st = lib.physs_pscan_filter_f64(*p.head, L, _polish_default(p.head[-1], polish), float(delta), int(patience),
+                                        ws.data_ptr(), mf.data_ptr(), Pf.data_ptr(), lml.data_ptr(),
+                                        lml_k.data_ptr() if lml_k is not None else None, status.data_ptr())
+    _lib.check(st, "physs_pscan_filter_f64")
+    res = (lml, mf, Pf) + ((lml_k,) if want_lml_k else ())
+    return res + ((status,) if return_status else ())
+
+
+def pscan_smooth(dt, mf, Pf, disc, Hout=None, chunk_len=None, jitter=None, out=None, ws=None, stream=None):
+    """Parallel-in-time RTS smoother: same arguments / results as rts_smooth."""
+    lib = _lib.load()
+    p = _pack_smooth(dt, mf, Pf, disc, Hout, jitter, stream)
+    L = default_chunk_len(p.B, p.T) if chunk_len is None else int(chunk_len)
+    ms, Ps = _smooth_outputs(p, out)
+    ws = pscan_workspace(p.B, p.T, p.d, L, p.dev) if ws is None else ws
+    with torch.cuda.device(p.dev):
+        st = lib.physs_pscan_smooth_f64(*p.head, L, ws.data_ptr(), ms.data_ptr(), Ps.data_ptr())
+    _lib.check(st, "physs_pscan_smooth_f64")
+    return ms, Ps
+
+
+# ---- time-sharded building blocks (used by physs_gp_b200/timeshard.py)
+def pscan_filter_local(dt, Y, R, H, m0, P0, disc, chunk_len, ws, jitter=None, stream=None):
+    """Scan element of this whole time range, [B, 3 d^2 + 2 d]; prefixes stay in `ws` for *_finish."""
+    lib = _lib.load()
+    p = _pack_filter(dt, Y, R, H, m0, P0, disc, jitter, stream)
+    total = torch.empty((p.B, 3 * p.d * p.d + 2 * p.d), dtype=torch.float64, device=p.dev)
+    with torch.cuda.device(p.dev):
+        st = lib.physs_pscan_filter_local_f64(*p.head, int(chunk_len), ws.data_ptr(), total.data_ptr())
+    _lib.check(st, "physs_pscan_filter_local_f64")
+    return total
+
+
+def pscan_filter_fold(totals, m0, P0, stream=None):
+    """(m0, P0) [B, d], [B, d, d] pushed through totals [K, B, ne] in time order."""
+    lib = _lib.load()
+    K, B = totals.shape[0], totals.shape[1]
+    d = P0.shape[-1]
+    m0v, sm0 = _bview(m0, "m0", (B, d), 1)
+    P0v, sP0 = _bview(P0, "P0", (B, d, d), 2)
+    totals = _dev(totals, "totals").contiguous()
+    mo = torch.empty((B, d), dtype=torch.float64, device=totals.device)
+    Po = torch.empty((B, d, d), dtype=torch.float64, device=totals.device)
+    with torch.cuda.device(totals.device):
+        st = lib.physs_pscan_filter_fold_f64(_stream_ptr(stream), B, d, K, totals.data_ptr(), m0v.data_ptr(), sm0[0],
+                                             P0v.data_ptr(), sP0[0], mo.data_ptr(), Po.data_ptr())
+    _lib.check(st, "physs_pscan_filter_fold_f64")
+    return mo, Po
+
+
+def pscan_filter_finish(dt, Y, R, H, m0, P0, disc, chunk_len, ws, start=None, jitter=None, polish=None, delta=1e-13,
+                        patience=4, want_lml_k=False, out=None, stream=None):
+    lib = _lib.load()
+    p = _pack_filter(dt, Y, R, H, m0, P0, disc, jitter, stream)
+    mf, Pf, lml, lml_k = _filter_outputs(p, out, want_lml_k)
+    status = torch.zeros((1,), dtype=torch.int32, device=p.dev)
+    sm = sP = None
+    if start is not None:
+        sm, sP = _dev(start[0], "start_m").contiguous(), _dev(start[1], "start_P").contiguous()
+    with torch.cuda.device(p.dev):
+        st = lib.physs_pscan_filter_finish_f64(*p.head, int(chunk_len), _polish_default(p.head[-1], polish),
+                                               float(delta), int(patience), ws.data_ptr(),
+                                               None if sm is None else sm.data_ptr(),
+                                               None if sP is None else sP.data_ptr(),
+                                               mf.data_ptr(), Pf.data_ptr(), lml.data_ptr(),
+                                               lml_k.data_ptr() if lml_k is not None else None, status.data_ptr())
+    _lib.check(st, "physs_pscan_filter_finish_f64")
+    return (lml, mf, Pf) + ((lml_k,) if want_lml_k else ()) + (status,)
+
+
+def pscan_smooth_local(dt, mf, Pf, disc, chunk_len, ws, jitter=None, stream=None):
+    lib = _lib.load()
+    p = _pack_smooth(dt, mf, Pf, disc, None, jitter, stream)
+    total = torch.empty((p.B, 2 * p.d * p.d + p.d), dtype=torch.float64, device=p.dev)
+    with torch.cuda.device(p.dev):
+        st = lib.physs_pscan_smooth_local_f64(*p.head, int(chunk_len), ws.data_ptr(), total.data_ptr())
+    _lib.check(st, "physs_pscan_smooth_local_f64")
+    return total
+
+
+def pscan_smooth_fold(totals, m_end, P_end, stream=None):
+    """(m_end, P_end) [B, d], [B, d, d] pulled back through totals [K, B, ns] (time order, last first)."""
+    lib = _lib.load()
+    K, B = totals.shape[0], totals.shape[1]
+    d = P_end.shape[-1]
+    totals = _dev(totals, "totals").contiguous()
+    m_end, P_end = _dev(m_end, "m_end").contiguous(), _dev(P_end, "P_end").contiguous()
+    mo = torch.empty((B, d), dtype=torch.float64, device=totals.device)
+    Po = torch.empty((B, d, d), dtype=torch.float64, device=totals.device)
+    with torch.cuda.device(totals.device):
+        st = lib.physs_pscan_smooth_fold_f64(_stream_ptr(stream), B, d, K, totals.data_ptr(), m_end.data_ptr(),
+                                             P_end.data_ptr(), mo.data_ptr(), Po.data_ptr())
+    _lib.check(st, "physs_pscan_smooth_fold_f64")
+    return mo, Po
+
+
+def pscan_smooth_finish(dt, mf, Pf, disc, chunk_len, ws, start=None, Hout=None, jitter=None, out=None, stream=None):
+    lib = _lib.load()
+    p = _pack_smooth(dt, mf, Pf, disc, Hout, jitter, stream)
+    ms, Ps = _smooth_outputs(p, out)
+    sm = sP = None
+    if start is not None:
+        sm, sP = _dev(start[0], "start_m").contiguous(), _dev(start[1], "start_P").contiguous()
+    with torch.cuda.device(p.dev):
+        st = lib.physs_pscan_smooth_finish_f64(*p.head, int(chunk_len), ws.data_ptr(),
+                                               None if sm is None else sm.data_ptr(),
+                                               None if sP is None else sP.data_ptr(), ms.data_ptr(), Ps.data_ptr())
+    _lib.check(st, "physs_pscan_smooth_finish_f64")
     return ms, Ps

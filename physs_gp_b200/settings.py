@@ -13,3 +13,9 @@ verbose = False
 # [B, T, ...] views), which lets a warp's 32 series move one contiguous span per step.
 time_major = True
 time_major_min_batch = 32
+
+# parallel-in-time path (filter_type='b200_parallel'): chunk length (None = chosen from B and T) and the
+# number of fix-up passes that reconcile the scan with the jittered sequential recursion (None = 4 if
+# jitter != 0 else 0); see include/physs_b200.h, "Parallel-in-time forms".
+pscan_chunk_len = None
+pscan_polish = None

@@ -1,0 +1,119 @@
+"""-m gpu parity tests of the parallel-in-time path (chunked associative scan, physs_pscan.cu) against the
+numpy oracle's SEQUENTIAL filter / smoother (the parity target) and against the CUDA
+sequential kernels at sizes the oracle cannot reach.  Tolerance 1e-9 relative (array scale)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import filters as ofilters
+from oracle import sde as osde
+from tests import synth
+from tests.test_gpu_seq import SPECS, _priors, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _oracle_and_inputs(name, T, seed, jitter, nan_frac=0.08):
+    spec, fso = SPECS[name]
+    rng = np.random.default_rng(seed)
+    pprior, oprior = _priors(spec, fso)
+    m = oprior.H().shape[0]
+    t = synth.time_grid(T, 0.1, rng)
+    Y = synth.noisy_series(1, T, m, rng, nan_frac)[0]
+    R = synth.random_spd(rng, (T,), m)
+    lml_o, mf_o, Pf_o, _ = ofilters.filter_sequential(oprior, t, Y, R, jitter)
+    return pprior, oprior, t, Y, R, lml_o, mf_o, Pf_o
+
+
+@pytest.mark.parametrize("jitter", [1e-5, 0.0])
+@pytest.mark.parametrize("name", ["c1_m32", "m52", "m72", "sum_m32x2", "indep_m32x2", "m52_fullstate",
+                                  "indep_m32x2_fullstate"])
+def test_parallel_filter_smoother_match_sequential_oracle(cuda_device, name, jitter, monkeypatch):
+    from physs_gp_b200 import data, filters, settings
+    monkeypatch.setattr(settings, "jitter", jitter)
+    monkeypatch.setattr(settings, "pscan_chunk_len", 37)          # ragged tail: 500 = 13 * 37 + 19
+    T = 500
+    pprior, oprior, t, Y, R, lml_o, mf_o, Pf_o = _oracle_and_inputs(name, T, 21, jitter)
+    d = data.TemporalData(t, Y[:, :, None])
+    lml, kf = filters.filter_loop(d, pprior, R=R, filter_type='b200_parallel')
+    assert abs(float(lml) - lml_o) <= TOL * abs(lml_o), (float(lml), lml_o)
+    assert rel(kf['m'], mf_o) < TOL and rel(kf['P'], Pf_o) < TOL
+    for fs in (True, False):
+        ms_o, Ps_o = ofilters.smoother_sequential(oprior, t, mf_o, Pf_o, full_state=fs, jitter=jitter)
+        mu, var = filters.smoother_loop(d, pprior, kf, full_state=fs, filter_type='b200_parallel')
+        assert rel(mu, ms_o) < TOL and rel(var, Ps_o) < TOL
+
+
+def _batch_problem(dev, B, T, d, m, given, seed, time_major):
+    from physs_gp_b200 import ops, sdes
+    rng = np.random.default_rng(seed)
+    t = synth.time_grid(T, 0.1, rng)
+    dt_f = torch.as_tensor(np.hstack([0.0, np.diff(t)]), device=dev)
+    dt_s = torch.as_tensor(np.hstack([np.diff(t), 0.0]), device=dev)
+    Y = torch.as_tensor(synth.noisy_series(B, T, m, rng, 0.1), device=dev)
+    if time_major:
+        Y = Y.transpose(0, 1).contiguous().transpose(0, 1)
+    R = torch.as_tensor(synth.random_spd(rng, (B, 1), m), device=dev)
+    H = torch.as_tensor(rng.normal(size=(1, m, d)), device=dev) if m != d else None
+    if given:
+        import scipy.linalg as sla
+        Fm = rng.normal(size=(d, d)) * 0.3 - 1.2 * np.eye(d)
+        Pinf = sla.solve_continuous_lyapunov(Fm, -np.eye(d))
+        uniq, inv = np.unique(np.hstack([0.0, np.diff(t)]), return_inverse=True)
+        Au = np.stack([sla.expm(Fm * x) for x in uniq])
+        A = Au[inv]
+        Q = Pinf - A @ Pinf @ np.swapaxes(A, -1, -2)
+        A_s = np.concatenate([A[1:], np.eye(d)[None]])
+        Q_s = np.concatenate([Q[1:], np.zeros((1, d, d))])
+        disc_f = ops.Disc.given(torch.as_tensor(A[None], device=dev), torch.as_tensor(Q[None], device=dev))
+        disc_s = ops.Disc.given(torch.as_tensor(A_s[None], device=dev), torch.as_tensor(Q_s[None], device=dev))
+        P0 = torch.as_tensor(Pinf[None], device=dev)
+    else:
+        s_blk = d if d <= 4 else (4 if d % 4 == 0 else 3)
+        prior = sdes.BatchedMaternSDE(s_blk, synth.log_uniform(rng, 0.5, 2.0, (B, d // s_blk)))
+        lam = torch.as_tensor(prior.lam(), device=dev)
+        P0 = torch.as_tensor(prior.P_inf(), device=dev)
+        disc_f = disc_s = ops.Disc.matern(d // s_blk, lam, P0)
+    m0 = torch.zeros((1, d), dtype=torch.float64, device=dev)
+    return dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s
+
+
+@pytest.mark.parametrize("B,T,d,m,given,time_major,chunk", [
+    (3, 20000, 4, 1, False, False, 256), (70, 3000, 4, 1, False, True, 200), (2, 8000, 6, 6, False, False, 128),
+    (2, 8000, 8, 3, True, False, 100), (1, 30000, 12, 12, False, False, 64), (1, 4000, 24, 2, False, False, 250),
+    (5, 1000, 3, 1, True, False, 1000), (4, 999, 2, 2, False, False, 1)])
+def test_parallel_equals_sequential_cuda(cuda_device, B, T, d, m, given, time_major, chunk):
+    """Long series / odd shapes: parallel-in-time == sequential CUDA path (itself oracle-checked)."""
+    from physs_gp_b200 import ops
+    dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s = _batch_problem(cuda_device, B, T, d, m, given, 7 + d, time_major)
+    # one-step chunks cannot host a fix-up pass (nothing to contract over): exact-scan case only
+    for jitter in ((1e-5, 0.0) if chunk >= 16 else (0.0,)):
+        lml, mf, Pf = ops.kf_filter(dt_f, Y, R, H, m0, P0, disc_f, jitter=jitter)
+        ms, Ps = ops.rts_smooth(dt_s, mf, Pf, disc_s, jitter=jitter)
+        lml2, mf2, Pf2, st = ops.pscan_filter(dt_f, Y, R, H, m0, P0, disc_f, chunk_len=chunk, jitter=jitter,
+                                              patience=min(4, chunk), return_status=True)
+        ms2, Ps2 = ops.pscan_smooth(dt_s, mf, Pf, disc_s, chunk_len=chunk, jitter=jitter)
+        torch.cuda.synchronize()
+        assert int(st.item()) == 0
+        assert rel(lml2, lml.cpu().numpy()) < TOL
+        assert rel(mf2, mf.cpu().numpy()) < TOL and rel(Pf2, Pf.cpu().numpy()) < TOL
+        assert rel(ms2, ms.cpu().numpy()) < TOL and rel(Ps2, Ps.cpu().numpy()) < TOL
+
+
+def test_scan_alone_is_exact_without_jitter(cuda_device):
+    """jitter = 0, no polish pass: the boundary states come from the associative scan only."""
+    from physs_gp_b200 import ops
+    dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s = _batch_problem(cuda_device, 2, 5000, 8, 2, False, 3, False)
+    lml, mf, Pf = ops.kf_filter(dt_f, Y, R, H, m0, P0, disc_f, jitter=0.0)
+    lml2, mf2, Pf2 = ops.pscan_filter(dt_f, Y, R, H, m0, P0, disc_f, chunk_len=50, jitter=0.0, polish=0)
+    assert rel(mf2, mf.cpu().numpy()) < TOL and rel(Pf2, Pf.cpu().numpy()) < TOL and rel(lml2, lml.cpu().numpy()) < TOL
+
+
+def test_unconverged_flag_is_raised(cuda_device):
+    """A chunk too short for the fix-up to settle (patience longer than the chunk) must raise the flag."""
+    from physs_gp_b200 import ops
+    dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s = _batch_problem(cuda_device, 1, 400, 4, 1, False, 5, False)
+    out = ops.pscan_filter(dt_f, Y, R, H, m0, P0, disc_f, chunk_len=8, jitter=1e-5, polish=1, patience=50,
+                           return_status=True)
+    assert int(out[-1].item()) == 1
