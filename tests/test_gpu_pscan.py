@@ -117,3 +117,52 @@ def test_unconverged_flag_is_raised(cuda_device):
     out = ops.pscan_filter(dt_f, Y, R, H, m0, P0, disc_f, chunk_len=8, jitter=1e-5, polish=1, patience=50,
                            return_status=True)
     assert int(out[-1].item()) == 1
+
+
+@pytest.mark.parametrize("d,m,given", [(4, 1, False), (8, 8, False), (6, 2, True)])
+def test_time_shards_on_one_gpu(cuda_device, d, m, given):
+    """The multi-GPU building blocks (local -> [all-gather] -> fold -> finish) run for 3 time ranges one
+    after the other on one GPU; the concatenation must equal the sequential result of the whole series."""
+    from physs_gp_b200 import ops, timeshard
+    B, T, chunk = 3, 2900, 64
+    dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s = _batch_problem(cuda_device, B, T, d, m, given, 31 + d, False)
+    jitter = 0.0
+    lml, mf, Pf = ops.kf_filter(dt_f, Y, R, H, m0, P0, disc_f, jitter=jitter)
+    ms, Ps = ops.rts_smooth(dt_s, mf, Pf, disc_s, jitter=jitter)
+    ranges = timeshard.time_ranges(T, 3)
+
+    def sl_disc(disc, t0, t1):
+        if disc.mode == 0:
+            return ops.Disc.given(disc.A[:, t0:t1].contiguous(), disc.Q[:, t0:t1].contiguous())
+        return disc
+    Rb = R.expand(B, T, m, m)
+    loc = []
+    for (t0, t1) in ranges:
+        ws = ops.pscan_workspace(B, t1 - t0, d, chunk, cuda_device)
+        args = (dt_f[t0:t1], Y[:, t0:t1].contiguous(), Rb[:, t0:t1].contiguous(), H, m0, P0, sl_disc(disc_f, t0, t1))
+        loc.append((ws, args, ops.pscan_filter_local(*args, chunk, ws, jitter=jitter)))
+    totals = torch.stack([x[2] for x in loc])
+    lml_sum, mfs, Pfs = 0.0, [], []
+    for r, (ws, args, _) in enumerate(loc):
+        start = ops.pscan_filter_fold(totals[:r], m0.expand(B, d), P0.expand(B, d, d)) if r > 0 else None
+        l, a, b_, st = ops.pscan_filter_finish(*args, chunk, ws, start=start, jitter=jitter)
+        lml_sum = lml_sum + l
+        mfs.append(a), Pfs.append(b_)
+    mf2, Pf2 = torch.cat(mfs, 1), torch.cat(Pfs, 1)
+    assert rel(lml_sum, lml.cpu().numpy()) < TOL
+    assert rel(mf2, mf.cpu().numpy()) < TOL and rel(Pf2, Pf.cpu().numpy()) < TOL
+    # smoother, backwards
+    sloc = []
+    for r, (t0, t1) in enumerate(ranges):
+        ws = loc[r][0]
+        sargs = (dt_s[t0:t1], mfs[r], Pfs[r], sl_disc(disc_s, t0, t1))
+        sloc.append((ws, sargs, ops.pscan_smooth_local(*sargs, chunk, ws, jitter=jitter)))
+    stotals = torch.stack([x[2] for x in sloc])
+    mss, Pss = [], []
+    for r, (ws, sargs, _) in enumerate(sloc):
+        start = None
+        if r < len(ranges) - 1:
+            start = ops.pscan_smooth_fold(stotals[r + 1:], mfs[-1][:, -1].contiguous(), Pfs[-1][:, -1].contiguous())
+        a, b_ = ops.pscan_smooth_finish(*sargs, chunk, ws, start=start, jitter=jitter)
+        mss.append(a), Pss.append(b_)
+    assert rel(torch.cat(mss, 1), ms.cpu().numpy()) < TOL and rel(torch.cat(Pss, 1), Ps.cpu().numpy()) < TOL
