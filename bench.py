@@ -44,6 +44,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "cvi"],
+                    help="c5 (default, the headline metric): batched sweep; c3: one long series, parallel-in-time "
+                         "scan, time-sharded over the ranks; cvi: CVI ELBO + natural-gradient step (config 4)")
+    ap.add_argument("--chunk-len", type=int, default=256, help="c3: steps per scan chunk")
+    ap.add_argument("--obs-dim", type=int, default=0, help="c3: observation dim (0 = full state, m = d)")
     ap.add_argument("--state-dim", type=int, default=4, help="4 * nblk Matern-7/2 blocks (4, 8, ...)")
     ap.add_argument("--series", type=int, default=SERIES_TOTAL)
     ap.add_argument("--T", type=int, default=T_STEPS)
@@ -315,7 +320,8 @@ def run_b200(a):
     s_units = [n * T for _, _, n in ev["s"]]
     peak, peak_src = measured_peak_gbs()
     kern = {}
-    for name, msl, units, bpu in (("seq_filter_kernel", f_ms, f_units, fb), ("seq_smooth_kernel", s_ms, s_units, sb)):
+    kn = ("seq_filter_kernel", "seq_smooth_kernel") if d <= 4 else ("grp_filter_kernel", "grp_smooth_kernel")
+    for name, msl, units, bpu in ((kn[0], f_ms, f_units, fb), (kn[1], s_ms, s_units, sb)):
         avg_ms = float(np.mean(msl))
         avg_bytes = float(np.mean(units)) * bpu
         kern[name] = {"avg_ms": avg_ms, "bytes_per_launch": avg_bytes,
@@ -326,7 +332,8 @@ def run_b200(a):
                 "traffic": recorded_traffic(d),
                 "bytes_per_state_step": {"filter": fb, "smoother": sb},
                 "kernels": kern,
-                "whole_step_frac": (fb + sb) * (value / world) / 1e9 / peak}
+                "whole_step_frac": (fb + sb) * (value / world) / 1e9 / peak,
+                "fp64_peak_tflops_measured": ops.fp64_peak_tflops(dev)}
 
     # ---------------------------------------------------------------- e2e through the host API
     e2e = None
@@ -408,10 +415,236 @@ def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys_dev):
             "result": "smoothed mean/variance of f [B,T] + lml [B]"}
 
 
+# ------------------------------------------------------------------ c3: one long series, parallel in time
+def run_c3(a):
+    """BASELINE config 3 shape: B long series (default 1) x T steps (default 1M), derivative-augmented state
+    d (default 8 = 2 x Matern-7/2), full-state Gaussian pseudo-observations (m = d, the CVI site
+    configuration) -- filter + smoother by the chunked associative scan; with N ranks the series is sharded
+    in TIME (one all-gather of range summaries per pass, physs_gp_b200/timeshard.py)."""
+    import torch
+    import torch.distributed as dist
+    from physs_gp_b200 import ops, sdes, timeshard
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        comm = timeshard.TorchDist()
+    else:
+        comm = timeshard.SingleProcess()
+    B = a.series if a.series != SERIES_TOTAL else 1
+    T = a.T if a.T != T_STEPS else 1000000
+    d = a.state_dim if a.state_dim != 4 else 8
+    m = a.obs_dim or d
+    nblk, L, jitter = d // 4, a.chunk_len, 1e-5
+    rng = np.random.default_rng(0)
+    steps = rng.uniform(0.5, 1.5, T) * DT0
+    dt_f, dt_s = np.hstack([0.0, steps[1:]]), np.hstack([steps[1:], 0.0])
+    prior = sdes.BatchedMaternSDE(4, np.exp(rng.uniform(np.log(0.5), np.log(2.0), (B, nblk))) * (10 * DT0),
+                                  full_state_obs=(m == d))
+    t0, t1 = timeshard.time_ranges(T, world)[rank]
+    tt = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=dev)   # noqa: E731
+    Yh = np.sin(0.01 * np.arange(t0, t1))[None, :, None] + 0.3 * rng.normal(size=(B, t1 - t0, m))
+    Y = tt(Yh)
+    lam, Pinf = tt(prior.lam()), tt(prior.P_inf())
+    H = None if m == d else tt(prior.H())
+    disc = ops.Disc.matern(nblk, lam, Pinf)
+    m0 = torch.zeros((1, d), dtype=torch.float64, device=dev)
+    R = NOISE_VAR * torch.eye(m, dtype=torch.float64, device=dev)[None, None]
+    ws = ops.pscan_workspace(B, t1 - t0, d, L, dev)
+    args = (tt(dt_f[t0:t1]), tt(dt_s[t0:t1]), Y, R, H, m0, Pinf, disc, disc)
+
+    def step():
+        return timeshard.filter_smooth(comm, ops, *args, chunk_len=L, jitter=jitter, ws=ws,
+                                       cross_rank_polish=world > 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(a.warmup):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        out = step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    el = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    ms = float(el.item()) / a.steps
+    assert torch.isfinite(out[0]).all() and int(out[-1].item()) == 0, "non-finite lml or unconverged fix-up"
+    value = B * T / (ms * 1e-3)
+    fb, sb = algorithmic_bytes(d, m)
+    flops = 14.3 * d ** 3 + 4 * m * d * d + 6 * m * m * d + 0.67 * m ** 3          # SURVEY 8d, sequential count
+    peak, peak_src = measured_peak_gbs()
+    fp64 = ops.fp64_peak_tflops(dev)
+    # e2e: host buffers in, smoothed mean / marginal variance of every state out
+    e2e = None
+    if not a.no_e2e:
+        Y_host = torch.empty(Y.shape, dtype=torch.float64, pin_memory=True); Y_host.copy_(Y)
+        o_m = torch.empty((B, t1 - t0, d), dtype=torch.float64, pin_memory=True)
+        o_v = torch.empty((B, t1 - t0, d), dtype=torch.float64, pin_memory=True)
+        o_l = torch.empty((B,), dtype=torch.float64, pin_memory=True)
+
+        def e2e_step():
+            Yd = Y_host.to(dev, non_blocking=True)
+            lml, mf, Pf, ms_, Ps_, st = timeshard.filter_smooth(comm, ops, args[0], args[1], Yd, *args[3:],
+                                                                chunk_len=L, jitter=jitter, ws=ws,
+                                                                cross_rank_polish=world > 1)
+            o_m.copy_(ms_, non_blocking=True)
+            o_v.copy_(torch.diagonal(Ps_, dim1=-2, dim2=-1), non_blocking=True)
+            o_l.copy_(lml, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_step()
+        barrier()
+        tw = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step()
+        elw = torch.tensor([time.perf_counter() - tw], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(elw, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * T * a.steps / float(elw.item()), "unit": "state-steps/s",
+               "h2d_bytes_per_step": B * T * m * 8, "d2h_bytes_per_step": B * T * 2 * d * 8 + B * 8,
+               "api": "timeshard.filter_smooth (pscan local/fold/finish over the C ABI), pinned host buffers",
+               "result": "smoothed mean + marginal variances of the full state [B,T,d] + lml"}
+    if rank == 0:
+        line = {"metric": "filter+smoother state-steps/sec (fp64)", "value": value, "unit": "state-steps/s",
+                "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "c3: %d series x %d steps, state dim %d (Matern-7/2 x %d), obs dim %d, "
+                                       "parallel-in-time chunked scan (chunk %d), jitter 1e-5" % (B, T, d, nblk, m, L),
+                           "series": B, "T": T, "state_dim": d, "obs_dim": m, "chunk_len": L,
+                           "l2": "per-pass working set %.1f GB >> 126 MB L2" % ((fb + sb) * B * T / 1e9),
+                           "parallelism": "time-sharded over ranks: all-gather of range summaries (NCCL)"},
+                "roofline": {"bound": "hbm", "achieved": (fb + sb) * (value / world) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": (fb + sb) * (value / world) / 1e9 / peak, "peak_source": peak_src,
+                             "traffic": None,
+                             "fp64": {"achieved_tflops": flops * (value / world) / 1e12, "peak_tflops": fp64,
+                                      "frac": flops * (value / world) / 1e12 / fp64,
+                                      "flops_per_state_step": flops, "peak_source": "physs_fp64_probe, this run"},
+                             "note": "against the SEQUENTIAL algorithmic bytes / flops per state-step "
+                                     "(SURVEY 8d): the scan's extra passes are overhead, not credit"},
+                "cpu_baseline": None, "e2e": e2e, "clocks": clocks, "gpu_launches": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------ cvi: ELBO + natgrad step
+def run_cvi(a):
+    """BASELINE config 4 shape: B spatial blocks (default 1000) x T steps (default 10k), Matern-3/2 state
+    (d = 2), scalar Poisson counts (exp link), Gauss-Hermite K = 20, beta = 0.1.  One step = ELBO evaluation
+    (filter + smoother on the sites, data ELL, surrogate ELL) + one natural-gradient site update (filter +
+    smoother, ELL gradients, theta <-> lambda, block update) -- vgp.py:148-157,274-282."""
+    import torch
+    import torch.distributed as dist
+    from physs_gp_b200 import cvi, ops, sdes
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = a.series if a.series != SERIES_TOTAL else 1000
+    T = a.T
+    rng = np.random.default_rng(rank)
+    t = np.cumsum(rng.uniform(0.5, 1.5, T) * DT0)
+    prior = sdes.BatchedMaternSDE(2, np.exp(rng.uniform(np.log(0.5), np.log(2.0), (B, 1))) * (10 * DT0))
+    rate = np.exp(0.5 * np.sin(0.02 * np.arange(T))[None, :] + 0.3 * rng.normal(size=(B, 1)))
+    Yh = rng.poisson(rate).astype(np.float64)[..., None]
+    Yh[rng.uniform(size=Yh.shape) < NAN_FRAC] = np.nan
+    q = cvi.FullConjugateGaussian(t, prior, 1, B=B, device=dev)
+    model = cvi.VGP(Yh, cvi.PoissonLik(1.0), q, ell_quad_points=20)
+
+    def step():
+        model.natural_gradient_update(0.1)
+        return model.elbo()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(a.warmup):
+        elbo = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        elbo = step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    el = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    ms = float(el.item()) / a.steps
+    assert torch.isfinite(elbo).all()
+    # e2e: data from pinned host memory every step, ELBO read back
+    Y_host = torch.empty(Yh.shape, dtype=torch.float64, pin_memory=True); Y_host.copy_(torch.as_tensor(Yh))
+    o_elbo = torch.empty((B,), dtype=torch.float64, pin_memory=True)
+
+    def e2e_step():
+        model.Y = Y_host.to(dev, non_blocking=True)
+        o_elbo.copy_(step(), non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_step(); barrier()
+    tw = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    elw = torch.tensor([time.perf_counter() - tw], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elw, op=dist.ReduceOp.MAX)
+    peak, peak_src = measured_peak_gbs()
+    d, D = 2, 1
+    fb, sb = algorithmic_bytes(d, 1)
+    # two posterior passes (natgrad + ELBO) each with time-varying site noise R_k (+8 B) ; site update: sites in/out
+    # + posterior read; ELLs: posterior read twice + data
+    byt = 2 * (fb + 8 + sb) + 8 * (2 * (D * D + D) + (D * D + D)) + 8 * (2 * (D * D + D) + 1 + (D * D + D))
+    if rank == 0:
+        line = {"metric": "CVI ELBO+natgrad step time", "value": ms, "unit": "ms", "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": False,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "cvi (config 4): %d blocks x %d steps per GPU, Matern-3/2 (d=2), Poisson "
+                                       "exp-link counts, Gauss-Hermite K=20, beta=0.1, 5%% missing" % (B, T),
+                           "blocks_per_gpu": B, "T": T, "state_dim": 2, "site_dim": 1, "quad_points": 20,
+                           "l2": "per-step working set %.1f GB >> 126 MB L2" % (byt * B * T / 1e9),
+                           "parallelism": "independent blocks per rank, no collective"},
+                "state_steps_per_s": world * B * T / (ms * 1e-3),
+                "roofline": {"bound": "hbm", "achieved": byt * B * T / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": byt * B * T / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                             "bytes_per_state_step": byt},
+                "cpu_baseline": None,
+                "e2e": {"value": 1e3 * float(elw.item()) / a.steps, "unit": "ms", "h2d_bytes_per_step": B * T * 8 * world,
+                        "d2h_bytes_per_step": B * 8 * world,
+                        "api": "VGP.natural_gradient_update(0.1) + VGP.elbo(), data from pinned host memory"},
+                "clocks": clocks, "gpu_launches": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "c3":
+        run_c3(a)
+    elif a.workload == "cvi":
+        run_cvi(a)
     else:
         run_b200(a)
 

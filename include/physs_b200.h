@@ -259,6 +259,10 @@ int physs_cvi_ell_f64(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik
                       double lik_param, int32_t K, const double* ghx, const double* ghw,
                       double* ell_out, double* dm_out, double* dS_out);
 
+/* FP64 FMA throughput probe (measurement aid for the FP64-pipe roofline; no reference counterpart).
+ * Launches blocks x 256 threads doing iters x 8 independent FMAs each: flops = blocks*256*iters*16. */
+int physs_fp64_probe(void* stream, int32_t blocks, int64_t iters, double* out);
+
 #ifdef __cplusplus
 }
 #endif

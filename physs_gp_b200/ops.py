@@ -374,3 +374,22 @@ def pscan_smooth_finish(dt, mf, Pf, disc, chunk_len, ws, start=None, Hout=None, 
                                                None if sP is None else sP.data_ptr(), ms.data_ptr(), Ps.data_ptr())
     _lib.check(st, "physs_pscan_smooth_finish_f64")
     return ms, Ps
+
+
+def fp64_peak_tflops(dev=None, iters=20000):
+    """Measured DFMA throughput of this GPU in TFLOP/s (CUDA events around physs_fp64_probe)."""
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dev is None else dev
+    out = torch.zeros((1,), dtype=torch.float64, device=dev)
+    blocks = 148 * 8
+    best = 0.0
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream()
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.physs_fp64_probe(st.cuda_stream, blocks, iters, out.data_ptr()), "physs_fp64_probe")
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, blocks * 256 * iters * 16 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
