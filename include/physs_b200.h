@@ -259,6 +259,24 @@ int physs_cvi_ell_f64(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik
                       double lik_param, int32_t K, const double* ghx, const double* ghw,
                       double* ell_out, double* dm_out, double* dS_out);
 
+/* Expected log-likelihood, its mean gradient and the (Gauss-Newton) site curvature of the PHYSS-GP
+ * damped-oscillator model: outputs T(u) = [x, x_tt + (g/l) sin x + b x_t] of the derivative-augmented block
+ * u (x, x_t, x_tt at block positions i0, i1, i2), Gaussian noise var_obs on the observation of x and
+ * var_col on the collocation residual.  Replaces, for this transform, MultiOutput([OutputMap,
+ * DampedPendulum1D]).forward (transforms/pdes.py:530-597) + the Monte-Carlo ELL (integrals/approximators.py:
+ * 16-58) + its jax.grad (natural_gradients/cvi_nat_grad.py:381-383) + the Laplace-Gauss-Newton delta-u
+ * curvature (cvi_hessian_approximations.py:333-431,542-577).  The expectation over sin(x) is closed-form.
+ *   y [N, 2]: (observation of x, collocation target, normally 0); NaN = absent at that step
+ *   gauss_newton != 0: dS = -1/2 sum_p J_p^T J_p / var_p with J at u = q_mu (enforce_psd_type=
+ *   'laplace_gauss_newton_delta_u'); == 0: the exact dELL/dS.
+ * Outputs (each may be NULL): ell [N], dm [N, D], dS [N, D, D]; feed dm, dS to physs_cvi_natgrad_step_f64
+ * with PHYSS_LIK_GIVEN.  The linear diffusion residual f_t - f_xx needs no special kernel: it is
+ * PHYSS_LIK_GAUSS with W = the residual's row vector. */
+int physs_cvi_ell_pendulum_f64(void* stream, int64_t N, int32_t D, int32_t i0, int32_t i1, int32_t i2,
+                               const double* q_mu, const double* q_var, const double* y,
+                               double g_over_l, double damping, double var_obs, double var_col,
+                               int32_t gauss_newton, double* ell_out, double* dm_out, double* dS_out);
+
 /* FP64 FMA throughput probe (measurement aid for the FP64-pipe roofline; no reference counterpart).
  * Launches blocks x 256 threads doing iters x 8 independent FMAs each: flops = blocks*256*iters*16. */
 int physs_fp64_probe(void* stream, int32_t blocks, int64_t iters, double* out);

@@ -163,3 +163,76 @@ def surrogate_ell(Ytil, Vtil, q_mu, q_var):
 def elbo(ell_data, ell_surrogate, lml_surrogate):
     """elbos.py:189: ELBO = ELL - ELL_surrogate + ML_surrogate."""
     return ell_data - ell_surrogate + lml_surrogate
+
+
+# ------------------------------------------------------------------ damped-oscillator collocation (config 3)
+
+def pendulum_forward(u, g_over_l, damping):
+    """transforms/pdes.py:584-597 (DampedPendulum1D.forward) stacked under the observation map of
+    zoo/sde_diff.py:757-763: T(u) = [x, x_tt + (g/l) sin x + b x_t] for u = (x, x_t, x_tt)."""
+    return np.array([u[0], u[2] + g_over_l * np.sin(u[0]) + damping * u[1]])
+
+
+def pendulum_ell_and_grads(y, q_mu, q_var, g_over_l, damping, var_obs, var_col, gauss_newton=False, idx=(0, 1, 2)):
+    """Expected log-likelihood of y = (observation of x, collocation target) under independent Gaussian
+    noise (var_obs, var_col) on T(u), u ~ N(q_mu, q_var), with its gradients w.r.t. (q_mu, q_var).
+
+    The reference evaluates this expectation by Monte-Carlo (approximators.py:16-58) and differentiates it
+    with jax.grad (cvi_nat_grad.py:381-383); here it is closed-form (Gaussian moments of sin / cos + Stein's
+    lemma), checked against dense Gauss-Hermite quadrature and finite differences in tests/test_oracle_cvi.py.
+    gauss_newton=True replaces dELL/dS by 1/2 sum_p mask_p J_p^T (-1/var_p) J_p, J_p = dT_p/du at u = q_mu
+    (cvi_hessian_approximations.py:333-431,483-486: Laplace Gauss-Newton, delta-u, delta-f)."""
+    i0, i1, i2 = idx
+    D = q_mu.shape[0]
+    a, b = g_over_l, damping
+    m0, m1, m2 = q_mu[i0], q_mu[i1], q_mu[i2]
+    S = 0.5 * (q_var + q_var.T)
+    ell, dm, dS = 0.0, np.zeros(D), np.zeros((D, D))
+    if not np.isnan(y[0]):
+        e = y[0] - m0
+        ell += -0.5 * (np.log(2 * np.pi) + np.log(var_obs) + (e * e + S[i0, i0]) / var_obs)
+        dm[i0] += e / var_obs
+        dS[i0, i0] += -0.5 / var_obs
+    if not np.isnan(y[1]):
+        E, E4 = np.exp(-0.5 * S[i0, i0]), np.exp(-2.0 * S[i0, i0])
+        sm, cm = np.sin(m0), np.cos(m0)
+        mul = m2 + b * m1 - y[1]
+        vl = S[i2, i2] + 2 * b * S[i1, i2] + b * b * S[i1, i1]
+        c = S[i0, i2] + b * S[i0, i1]
+        Rr = mul * mul + vl + 2 * a * (mul * sm + c * cm) * E + a * a * 0.5 * (1 - np.cos(2 * m0) * E4)
+        ell += -0.5 * (np.log(2 * np.pi) + np.log(var_col) + Rr / var_col)
+        k = -0.5 / var_col
+        t = 2 * mul + 2 * a * sm * E
+        dm[i0] += k * (2 * a * (mul * cm - c * sm) * E + a * a * np.sin(2 * m0) * E4)
+        dm[i1] += k * b * t
+        dm[i2] += k * t
+        if gauss_newton:
+            J = np.zeros(D)
+            J[i0], J[i1], J[i2] = a * cm, b, 1.0
+            dS += k * np.outer(J, J)
+        else:
+            G = np.zeros((D, D))
+            G[i0, i0] = -a * (mul * sm + c * cm) * E + a * a * np.cos(2 * m0) * E4
+            G[i1, i1], G[i2, i2] = b * b, 1.0
+            G[i0, i1] = G[i1, i0] = a * b * cm * E
+            G[i0, i2] = G[i2, i0] = a * cm * E
+            G[i1, i2] = G[i2, i1] = b
+            dS += k * G
+    return float(ell), dm, dS
+
+
+def pendulum_ell_quadrature(y, q_mu, q_var, g_over_l, damping, var_obs, var_col, K=40):
+    """The same expectation by K^3-point tensor Gauss-Hermite over (x, x_t, x_tt): independent check."""
+    x, w = np.polynomial.hermite.hermgauss(K)
+    w = w / np.sqrt(np.pi)
+    L = np.linalg.cholesky(q_var[:3, :3] + 1e-300 * np.eye(3))
+    Z = np.stack(np.meshgrid(x, x, x, indexing="ij"), -1).reshape(-1, 3) * np.sqrt(2.0)
+    Wt = np.einsum("i,j,k->ijk", w, w, w).reshape(-1)
+    U = q_mu[:3] + Z @ L.T
+    ell = 0.0
+    if not np.isnan(y[0]):
+        ell += np.sum(Wt * (-0.5 * (np.log(2 * np.pi * var_obs) + (y[0] - U[:, 0]) ** 2 / var_obs)))
+    if not np.isnan(y[1]):
+        r = U[:, 2] + g_over_l * np.sin(U[:, 0]) + damping * U[:, 1]
+        ell += np.sum(Wt * (-0.5 * (np.log(2 * np.pi * var_col) + (y[1] - r) ** 2 / var_col)))
+    return float(ell)

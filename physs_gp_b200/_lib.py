@@ -55,6 +55,8 @@ SIGNATURES = {
     "physs_pscan_smooth_local_f64": (ctypes.c_int, _SMOOTH_HEAD + [_c_i64, _ptr, _ptr]),
     "physs_pscan_smooth_finish_f64": (ctypes.c_int, _SMOOTH_HEAD + [_c_i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "physs_pscan_smooth_fold_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _c_i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "physs_cvi_ell_pendulum_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr,
+                                                  _c_f64, _c_f64, _c_f64, _c_f64, _c_i32, _ptr, _ptr, _ptr]),
     "physs_fp64_probe": (ctypes.c_int, [_ptr, _c_i32, _c_i64, _ptr]),
     "physs_cvi_natgrad_step_f64": (ctypes.c_int, [
         _ptr, _c_i64, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64,

@@ -412,6 +412,134 @@ PHYSS_HD void kf_update(double (&m)[D], double (&P)[D][D], const double (&H)[M][
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One step of a parallel-in-time chunk summary (physs_pscan.cu): the accumulated scan element
+// (A, b, C, J, eta) of parallel_kalman_filter.py:143-220 combined with the single-step element of this
+// observation.  Algebraically that is the masked Kalman update above applied to (b, C) -- same jittered
+// gain, same C - K S K^T -- plus   A <- (I - K H) A,  J += (HA)^T (S+jit)^-1 (HA),  eta += (HA)^T (S+jit)^-1 v
+// with HA = M H A (rows of missing observations zeroed).  On entry A, b, C are the PREDICTED quantities.
+// ---------------------------------------------------------------------------------------------
+template <int D, int M, bool HID>
+PHYSS_HD void kf_update_summary(double (&b)[D], double (&C)[D][D], double (&A)[D][D], double (&J)[D][D],
+                                double (&eta)[D], const double (&H)[M][D], const double (&R)[M][M],
+                                const double (&y)[M], double jitter) {
+  bool obs[M];
+  PHYSS_UNROLL
+  for (int a = 0; a < M; ++a) obs[a] = !(y[a] != y[a]);
+  double HP[M][D], HA[M][D], v[M];
+  PHYSS_UNROLL
+  for (int a = 0; a < M; ++a) {
+    double mu = 0.0;
+    PHYSS_UNROLL
+    for (int j = 0; j < D; ++j) {
+      double hc, ha;
+      if (HID) {
+        hc = C[a][j];
+        ha = A[a][j];
+      } else {
+        hc = 0.0;
+        ha = 0.0;
+        PHYSS_UNROLL
+        for (int k = 0; k < D; ++k) {
+          hc = fma(H[a][k], C[k][j], hc);
+          ha = fma(H[a][k], A[k][j], ha);
+        }
+      }
+      HP[a][j] = obs[a] ? hc : 0.0;
+      HA[a][j] = obs[a] ? ha : 0.0;
+    }
+    if (HID) {
+      mu = b[a];
+    } else {
+      PHYSS_UNROLL
+      for (int k = 0; k < D; ++k) mu = fma(H[a][k], b[k], mu);
+    }
+    v[a] = obs[a] ? (y[a] - mu) : 0.0;
+  }
+  double S[M][M], Sj[M][M];
+  PHYSS_UNROLL
+  for (int a = 0; a < M; ++a) {
+    PHYSS_UNROLL
+    for (int c = a; c < M; ++c) {
+      double acc;
+      if (HID) {
+        acc = HP[a][c];
+      } else {
+        acc = 0.0;
+        PHYSS_UNROLL
+        for (int k = 0; k < D; ++k) acc = fma(HP[a][k], H[c][k], acc);
+      }
+      acc = obs[c] ? acc : 0.0;
+      S[a][c] = acc + R[a][c];
+      S[c][a] = acc + R[c][a];
+    }
+  }
+  PHYSS_UNROLL
+  for (int a = 0; a < M; ++a) {
+    PHYSS_UNROLL
+    for (int c = 0; c < M; ++c) Sj[a][c] = S[a][c] + (a == c ? jitter : 0.0);
+  }
+  double L[M][M], rd[M];
+  chol_lower<M>(Sj, L, rd);
+  double Kt[M][D], Z[M][D], w[M];
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    double x[M], z[M];
+    PHYSS_UNROLL
+    for (int a = 0; a < M; ++a) { x[a] = HP[a][i]; z[a] = HA[a][i]; }
+    chol_solve_vec<M>(L, rd, x);
+    chol_solve_vec<M>(L, rd, z);
+    PHYSS_UNROLL
+    for (int a = 0; a < M; ++a) { Kt[a][i] = x[a]; Z[a][i] = z[a]; }
+  }
+  PHYSS_UNROLL
+  for (int a = 0; a < M; ++a) w[a] = v[a];
+  chol_solve_vec<M>(L, rd, w);
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    double accb = b[i], acce = eta[i];
+    PHYSS_UNROLL
+    for (int a = 0; a < M; ++a) {
+      accb = fma(Kt[a][i], v[a], accb);
+      acce = fma(HA[a][i], w[a], acce);
+    }
+    b[i] = accb;
+    eta[i] = acce;
+  }
+  double KS[D][M];
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    PHYSS_UNROLL
+    for (int c = 0; c < M; ++c) {
+      double acc = 0.0;
+      PHYSS_UNROLL
+      for (int a = 0; a < M; ++a) acc = fma(Kt[a][i], S[a][c], acc);
+      KS[i][c] = acc;
+    }
+  }
+  PHYSS_UNROLL
+  for (int i = 0; i < D; ++i) {
+    PHYSS_UNROLL
+    for (int j = 0; j < D; ++j) {
+      double av = A[i][j];
+      PHYSS_UNROLL
+      for (int a = 0; a < M; ++a) av = fma(-Kt[a][i], HA[a][j], av);
+      A[i][j] = av;
+    }
+    PHYSS_UNROLL
+    for (int j = i; j < D; ++j) {
+      double cv = C[i][j], jv = J[i][j];
+      PHYSS_UNROLL
+      for (int a = 0; a < M; ++a) {
+        cv = fma(-KS[i][a], Kt[a][j], cv);
+        jv = fma(HA[a][i], Z[a][j], jv);
+      }
+      C[i][j] = cv; C[j][i] = cv;
+      J[i][j] = jv; J[j][i] = jv;
+    }
+  }
+}
+
 // log N term of one step from its (det, mahal, nobs) triple (only used when per-step values are asked for)
 PHYSS_HD double lml_term(double det, double mahal, int nobs) {
   return -0.5 * ((double)nobs * kLog2Pi + log(det) + mahal);
@@ -459,10 +587,12 @@ PHYSS_HD void kf_predict_stationary(const Trans<D, S>& A, const double (&Pinf)[D
 //   Qadd: the matrix added to A Pf A^T, i.e. Q_k (given) -- for the stationary form pass
 //         stationary = true and Qadd = Pinf, which evaluates Pinf + (A Pf - A Pinf) A^T.
 // ---------------------------------------------------------------------------------------------
+//   Eacc != nullptr (parallel-in-time chunk summary, parallel_rts_smoother.py:25-55): additionally
+//   Eacc <- G Eacc, so that after folding a chunk  x_s[first] = Eacc x + ms,  P_s[first] = Eacc P Eacc^T + Ps.
 template <int D, int S>
 PHYSS_HD void rts_step(const Trans<D, S>& A, const double (&Qadd)[D][D], bool stationary,
                        const double (&mf)[D], const double (&Pf)[D][D], double jitter,
-                       double (&ms)[D], double (&Ps)[D][D]) {
+                       double (&ms)[D], double (&Ps)[D][D], double (*Eacc)[D] = nullptr) {
   double mp[D];
   A.mulv(mf, mp);
   double C[D][D];  // A Pf
@@ -499,6 +629,24 @@ PHYSS_HD void rts_step(const Trans<D, S>& A, const double (&Qadd)[D][D], bool st
     chol_solve_vec<D>(L, rd, x);
     PHYSS_UNROLL
     for (int i = 0; i < D; ++i) G[j][i] = x[i];
+  }
+  if (Eacc) {
+    double GE[D][D];
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      PHYSS_UNROLL
+      for (int j = 0; j < D; ++j) {
+        double acc = 0.0;
+        PHYSS_UNROLL
+        for (int k = 0; k < D; ++k) acc = fma(G[i][k], Eacc[k][j], acc);
+        GE[i][j] = acc;
+      }
+    }
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      PHYSS_UNROLL
+      for (int j = 0; j < D; ++j) Eacc[i][j] = GE[i][j];
+    }
   }
   // m = mf + G (ms - mp)
   double dm[D];

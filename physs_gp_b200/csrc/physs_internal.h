@@ -73,6 +73,9 @@ bool seq_supported(int d, int m, int disc_mode, int nblk);
 int seq_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity,
                const SeqFilterArgs& a);
 int seq_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
+int seq_filter_summary(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity,
+                       const SeqFilterArgs& a, double* elems);
+int seq_smooth_summary(cudaStream_t st, int d, int disc_mode, int nblk, const SeqSmoothArgs& a, double* elems);
 // size dispatch shared by the plain and the chunked entry points (physs_api.cu)
 int run_filter_any(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity,
                    const SeqFilterArgs& a);

@@ -781,22 +781,37 @@ __global__ void ps_gather_bnd_kernel(const double* __restrict__ mf, const double
   }
 }
 
-// lml[b] = sum_k lml_k[b, k]   (one warp per series, Kahan-compensated lane partials, tree over lanes)
-__global__ void ps_lml_reduce_kernel(const double* __restrict__ lml_k, int64_t B, int64_t T, int64_t sbs,
-                                     int64_t sts, double* __restrict__ lml) {
+// lml[b] = sum_k lml_k[b, k], two deterministic stages: one 256-thread block per (series, segment of
+// `seg` steps) -> partial[b, s]; then one warp per series over the partials.
+__global__ void __launch_bounds__(256) ps_lml_partial_kernel(const double* __restrict__ lml_k, int64_t T, int64_t sbs,
+                                                             int64_t sts, int64_t seg, int64_t nseg,
+                                                             double* __restrict__ partial) {
+  __shared__ double red[8];
+  const int64_t b = blockIdx.y, sg = blockIdx.x;
+  const int64_t k0 = sg * seg, k1 = (k0 + seg < T) ? k0 + seg : T;
+  double s = 0.0;
+  for (int64_t k = k0 + threadIdx.x; k < k1; k += 256) s += lml_k[b * sbs + k * sts];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[b * nseg + sg] = t;
+  }
+}
+__global__ void ps_lml_final_kernel(const double* __restrict__ partial, int64_t B, int64_t nseg,
+                                    double* __restrict__ lml) {
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= B) return;
-  double s = 0.0, comp = 0.0;
-  for (int64_t k = lane; k < T; k += 32) {
-    const double x = lml_k[w * sbs + k * sts] - comp;
-    const double t = s + x;
-    comp = (t - s) - x;
-    s = t;
-  }
+  double s = 0.0;
+  for (int64_t k = lane; k < nseg; k += 32) s += partial[w * nseg + k];
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) lml[w] = s;
 }
+static inline int64_t ps_lml_seg(int64_t T) { return T < 4096 ? T : 4096; }
+static inline int64_t ps_lml_nseg(int64_t T) { const int64_t sg = ps_lml_seg(T); return (T + sg - 1) / sg; }
 
 // dst[r * dst_stride + i] = src[r * src_stride + i], i < n, r < rows   (src_stride may be 0 = broadcast)
 __global__ void ps_copy_rows_kernel(double* __restrict__ dst, int64_t dst_stride, const double* __restrict__ src,
@@ -895,6 +910,7 @@ struct PsWorkspace {
   double* bnd_m; double* bnd_P;
   double* start_m; double* start_P;
   int* flag;
+  double* lml_partial;
   double* lml_k;
 };
 static int64_t ps_nchunk(int64_t T, int64_t chunk_len) { return (T + chunk_len - 1) / chunk_len; }
@@ -902,7 +918,7 @@ static int64_t ps_nchunk(int64_t T, int64_t chunk_len) { return (T + chunk_len -
 int64_t pscan_workspace_doubles(int64_t B, int64_t T, int d, int64_t chunk_len) {
   const int64_t nchunk = ps_nchunk(T, chunk_len);
   const int64_t sd = (int64_t)d + (int64_t)d * d;
-  return 2 * B * nchunk * ps_filter_elem(d) + B * nchunk * sd + B * sd + 2 + B * T;
+  return 2 * B * nchunk * ps_filter_elem(d) + B * nchunk * sd + B * sd + 2 + B * ((T + 4095) / 4096 + 1) + B * T;
 }
 static PsWorkspace ps_carve(double* ws, int64_t B, int64_t T, int d, int64_t chunk_len) {
   const int64_t nchunk = ps_nchunk(T, chunk_len);
@@ -915,6 +931,7 @@ static PsWorkspace ps_carve(double* ws, int64_t B, int64_t T, int d, int64_t chu
   w.start_m = p; p += B * d;
   w.start_P = p; p += B * (int64_t)d * d;
   w.flag = reinterpret_cast<int*>(p); p += 2;
+  w.lml_partial = p; p += B * ((T + 4095) / 4096 + 1);
   w.lml_k = p;
   return w;
 }
@@ -952,14 +969,20 @@ int pscan_filter_local(cudaStream_t st, int d, int m, int disc_mode, int nblk, b
   const PcLayout Lc = pc_layout(d);
   const int64_t nfull = a.T / chunk_len;
   const int64_t nfull_sum = nfull < nsum ? nfull : nsum;
-  if (nfull_sum > 0) {
-    rc = PS_BY_G_GIVEN(run_filter_summary, st, a, L, hid, (int64_t)0, nfull_sum, w.e0);
-    if (rc) return rc;
-  }
-  if (nsum > nfull_sum) {
-    rc = PS_BY_G_GIVEN(run_filter_summary, st, a, L, hid, nfull_sum, nsum - nfull_sum, w.e0);
-    if (rc) return rc;
-  }
+  const bool reg = seq_supported(d, m, disc_mode, nblk);     // register-resident summaries for d <= 4
+  auto summarise = [&](int64_t first, int64_t count) -> int {
+    if (count <= 0) return PHYSS_OK;
+    if (reg) {
+      SeqFilterArgs r = a;
+      r.chunk_first = first; r.chunk_count = count;
+      return seq_filter_summary(st, d, m, disc_mode, nblk, hid, r, w.e0);
+    }
+    return PS_BY_G_GIVEN(run_filter_summary, st, a, L, hid, first, count, w.e0);
+  };
+  rc = summarise(0, nfull_sum);
+  if (rc) return rc;
+  rc = summarise(nfull_sum, nsum - nfull_sum);
+  if (rc) return rc;
   double* in = w.e0; double* out = w.e1;
   for (int64_t stride = 1; stride < nsum; stride *= 2) {
     rc = PS_BY_G(run_filter_scan, st, in, out, a.B, nchunk, nsum, stride, Lc);
@@ -1034,9 +1057,14 @@ int pscan_filter_finish(cudaStream_t st, int d, int m, int disc_mode, int nblk, 
     a.fixup = 0;
   }
   {
+    const int64_t seg = ps_lml_seg(a.T), nseg = ps_lml_nseg(a.T);
+    double* partial = w.lml_partial;
+    ps_lml_partial_kernel<<<dim3((unsigned)nseg, (unsigned)a.B), 256, 0, st>>>(a.lml_k, a.T, a.sbs, a.sts, seg, nseg, partial);
+    rc = cuda_status(cudaGetLastError(), "ps_lml_partial_kernel launch");
+    if (rc) return rc;
     const int64_t threads = a.B * 32;
-    ps_lml_reduce_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(a.lml_k, a.B, a.T, a.sbs, a.sts, a.lml);
-    rc = cuda_status(cudaGetLastError(), "ps_lml_reduce_kernel launch");
+    ps_lml_final_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(partial, a.B, nseg, a.lml);
+    rc = cuda_status(cudaGetLastError(), "ps_lml_final_kernel launch");
     if (rc) return rc;
   }
   if (status_out) {
@@ -1067,14 +1095,15 @@ int pscan_smooth_local(cudaStream_t st, int d, int disc_mode, int nblk, SeqSmoot
   const PsLayout L = ps_layout(d, 1, given ? 0 : nblk, given, true);
   const SsLayout Ls = ss_layout(d);
   const int64_t nfull = a.T / chunk_len;
+  const bool reg = seq_supported(d, d, disc_mode, nblk);
   if (nfull > 0) {
     a.chunk_first = 0; a.chunk_count = nfull;
-    rc = PS_BY_G_GIVEN(run_smooth_summary, st, a, L, w.e0);
+    rc = reg ? seq_smooth_summary(st, d, disc_mode, nblk, a, w.e0) : PS_BY_G_GIVEN(run_smooth_summary, st, a, L, w.e0);
     if (rc) return rc;
   }
   if (nchunk > nfull) {
     a.chunk_first = nfull; a.chunk_count = nchunk - nfull;
-    rc = PS_BY_G_GIVEN(run_smooth_summary, st, a, L, w.e0);
+    rc = reg ? seq_smooth_summary(st, d, disc_mode, nblk, a, w.e0) : PS_BY_G_GIVEN(run_smooth_summary, st, a, L, w.e0);
     if (rc) return rc;
   }
   double* in = w.e0; double* out = w.e1;

@@ -31,6 +31,31 @@ int seq_smooth_d4s4m(cudaStream_t st, const SeqSmoothArgs& a, int mo);
 int seq_filter_d4s4g(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
 int seq_smooth_d4s4g(cudaStream_t st, const SeqSmoothArgs& a, int mo);
 
+int seq_filter_summary_d1s1m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
+int seq_smooth_summary_d1s1m(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
+int seq_filter_summary_d1s1g(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
+int seq_smooth_summary_d1s1g(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
+int seq_filter_summary_d2s1m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
+int seq_smooth_summary_d2s1m(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
+int seq_filter_summary_d2s2m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
+int seq_smooth_summary_d2s2m(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
+int seq_filter_summary_d2s2g(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
+int seq_smooth_summary_d2s2g(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
+int seq_filter_summary_d3s1m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
+int seq_smooth_summary_d3s1m(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
+int seq_filter_summary_d3s3m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
+int seq_smooth_summary_d3s3m(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
+int seq_filter_summary_d3s3g(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
+int seq_smooth_summary_d3s3g(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
+int seq_filter_summary_d4s1m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
+int seq_smooth_summary_d4s1m(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
+int seq_filter_summary_d4s2m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
+int seq_smooth_summary_d4s2m(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
+int seq_filter_summary_d4s4m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
+int seq_smooth_summary_d4s4m(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
+int seq_filter_summary_d4s4g(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
+int seq_smooth_summary_d4s4g(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
+
 bool seq_supported(int d, int m, int disc_mode, int nblk) {
   if (d < 1 || d > 4 || m < 1 || m > d) return false;
   if (disc_mode == PHYSS_DISC_GIVEN) return true;
@@ -78,6 +103,48 @@ int seq_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const Se
   if (d == 4 && s == 4 && g == false) return seq_smooth_d4s4m(st, a, mo);
   if (d == 4 && s == 4 && g == true) return seq_smooth_d4s4g(st, a, mo);
   return set_error(PHYSS_ERR_UNSUPPORTED, "seq smoother: unreachable");
+}
+
+
+int seq_filter_summary(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity,
+                       const SeqFilterArgs& a, double* elems) {
+  if (!seq_supported(d, m, disc_mode, nblk))
+    return set_error(PHYSS_ERR_UNSUPPORTED, "seq filter summary: no specialisation for this (d, m, blocks)");
+  const int s = (disc_mode == PHYSS_DISC_GIVEN) ? d : d / nblk;
+  const bool g = (disc_mode == PHYSS_DISC_GIVEN);
+  if (d == 1 && s == 1 && g == false) return seq_filter_summary_d1s1m(st, a, m, h_identity, elems);
+  if (d == 1 && s == 1 && g == true) return seq_filter_summary_d1s1g(st, a, m, h_identity, elems);
+  if (d == 2 && s == 1 && g == false) return seq_filter_summary_d2s1m(st, a, m, h_identity, elems);
+  if (d == 2 && s == 2 && g == false) return seq_filter_summary_d2s2m(st, a, m, h_identity, elems);
+  if (d == 2 && s == 2 && g == true) return seq_filter_summary_d2s2g(st, a, m, h_identity, elems);
+  if (d == 3 && s == 1 && g == false) return seq_filter_summary_d3s1m(st, a, m, h_identity, elems);
+  if (d == 3 && s == 3 && g == false) return seq_filter_summary_d3s3m(st, a, m, h_identity, elems);
+  if (d == 3 && s == 3 && g == true) return seq_filter_summary_d3s3g(st, a, m, h_identity, elems);
+  if (d == 4 && s == 1 && g == false) return seq_filter_summary_d4s1m(st, a, m, h_identity, elems);
+  if (d == 4 && s == 2 && g == false) return seq_filter_summary_d4s2m(st, a, m, h_identity, elems);
+  if (d == 4 && s == 4 && g == false) return seq_filter_summary_d4s4m(st, a, m, h_identity, elems);
+  if (d == 4 && s == 4 && g == true) return seq_filter_summary_d4s4g(st, a, m, h_identity, elems);
+  return set_error(PHYSS_ERR_UNSUPPORTED, "seq filter summary: unreachable");
+}
+
+int seq_smooth_summary(cudaStream_t st, int d, int disc_mode, int nblk, const SeqSmoothArgs& a, double* elems) {
+  if (!seq_supported(d, d, disc_mode, nblk))
+    return set_error(PHYSS_ERR_UNSUPPORTED, "seq smoother summary: no specialisation for this (d, blocks)");
+  const int s = (disc_mode == PHYSS_DISC_GIVEN) ? d : d / nblk;
+  const bool g = (disc_mode == PHYSS_DISC_GIVEN);
+  if (d == 1 && s == 1 && g == false) return seq_smooth_summary_d1s1m(st, a, elems);
+  if (d == 1 && s == 1 && g == true) return seq_smooth_summary_d1s1g(st, a, elems);
+  if (d == 2 && s == 1 && g == false) return seq_smooth_summary_d2s1m(st, a, elems);
+  if (d == 2 && s == 2 && g == false) return seq_smooth_summary_d2s2m(st, a, elems);
+  if (d == 2 && s == 2 && g == true) return seq_smooth_summary_d2s2g(st, a, elems);
+  if (d == 3 && s == 1 && g == false) return seq_smooth_summary_d3s1m(st, a, elems);
+  if (d == 3 && s == 3 && g == false) return seq_smooth_summary_d3s3m(st, a, elems);
+  if (d == 3 && s == 3 && g == true) return seq_smooth_summary_d3s3g(st, a, elems);
+  if (d == 4 && s == 1 && g == false) return seq_smooth_summary_d4s1m(st, a, elems);
+  if (d == 4 && s == 2 && g == false) return seq_smooth_summary_d4s2m(st, a, elems);
+  if (d == 4 && s == 4 && g == false) return seq_smooth_summary_d4s4m(st, a, elems);
+  if (d == 4 && s == 4 && g == true) return seq_smooth_summary_d4s4g(st, a, elems);
+  return set_error(PHYSS_ERR_UNSUPPORTED, "seq smoother summary: unreachable");
 }
 
 }  // namespace physs

@@ -8,4 +8,10 @@ int seq_filter_d2s1m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid) {
 int seq_smooth_d2s1m(cudaStream_t st, const SeqSmoothArgs& a, int mo) {
   return smooth_by_mo<2, 1, false>(st, a, mo);
 }
+int seq_filter_summary_d2s1m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems) {
+  return filter_summary_by_m<2, 1, false>(st, a, m, hid, elems);
+}
+int seq_smooth_summary_d2s1m(cudaStream_t st, const SeqSmoothArgs& a, double* elems) {
+  return launch_smooth_summary<2, 1, false>(st, a, elems);
+}
 }  // namespace physs

@@ -516,6 +516,200 @@ static inline int pick_block(int64_t B) {
   return 128;
 }
 
+// ------------------------------------------------------------------------- parallel-in-time summaries
+// One thread per (series, chunk): folds the chunk's steps into ONE scan element, in registers (the d <= 4
+// counterpart of ps_filter_summary_kernel / ps_smooth_summary_kernel in physs_pscan.cu; same element
+// layout in global memory: filter [A | C | J | b | eta], smoother [E | L | g], index b * nchunk + c).
+template <int D, int S, int M, bool HID, bool GIVEN>
+__global__ void __launch_bounds__(128) seq_filter_summary_kernel(const SeqFilterArgs p, double* __restrict__ elems) {
+  SeqWork wk;
+  if (!seq_work<true>(p, wk)) return;
+  constexpr int NB = D / S;
+  const int64_t b = wk.b, t0 = wk.t0, T = wk.T;
+  const int64_t sts = p.sts;
+  double Pinf[D][D], H[M][D], lam[NB];
+  if (!GIVEN) {
+    load_mat<D>(p.Pinf + b * p.Pinf_bs, Pinf);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) lam[i] = p.lam[b * p.lam_bs + i];
+  }
+  if (!HID) {
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) H[a][j] = p.H[b * p.H_bs + a * D + j];
+    }
+  }
+  double A[D][D], bv[D], C[D][D], J[D][D], eta[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    bv[i] = 0.0;
+    eta[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      A[i][j] = (i == j) ? 1.0 : 0.0;
+      C[i][j] = 0.0;
+      J[i][j] = 0.0;
+    }
+  }
+  const int64_t row0 = b * p.sbs + t0 * sts;
+  const double* __restrict__ dtp = p.dt + b * p.dt_bs + t0;
+  const double* __restrict__ Yp = p.Y + row0 * M;
+  const double* __restrict__ Rp = p.R + b * p.R_bs + t0 * p.R_ts;
+  const double* __restrict__ Ap = GIVEN ? p.A + b * p.A_bs + t0 * D * D : nullptr;
+  const double* __restrict__ Qp = GIVEN ? p.Q + b * p.Q_bs + t0 * D * D : nullptr;
+  double y_n[M], R_n[M][M], dt_n;
+  load_vec<M>(Yp, y_n);
+  load_mat<M>(Rp, R_n);
+  dt_n = dtp[0];
+  for (int64_t k = 0; k < T; ++k) {
+    double y[M], R[M][M];
+    const double dt = dt_n;
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      y[a] = y_n[a];
+#pragma unroll
+      for (int c = 0; c < M; ++c) R[a][c] = R_n[a][c];
+    }
+    if (k + 1 < T) {
+      load_vec<M>(Yp + (k + 1) * sts * M, y_n);
+      if (p.R_ts != 0) load_mat<M>(Rp + (k + 1) * p.R_ts, R_n);
+      dt_n = dtp[k + 1];
+    }
+    Trans<D, S> Phi;
+    if constexpr (GIVEN) {
+      double Q[D][D];
+      load_trans_dense<D, S>(Ap + k * D * D, Phi);
+      load_mat<D>(Qp + k * D * D, Q);
+      kf_predict_givenQ<D, S>(Phi, Q, bv, C);
+    } else {
+      matern_trans<D, S>(lam, dt, Phi);
+      kf_predict_stationary<D, S>(Phi, Pinf, bv, C);
+    }
+    double Abar[D][D];
+    Phi.mulL(A, Abar);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) A[i][j] = Abar[i][j];
+    }
+    kf_update_summary<D, M, HID>(bv, C, A, J, eta, H, R, y, p.jitter);
+  }
+  if (wk.active) {
+    double* __restrict__ e = elems + (b * p.nchunk + wk.c) * (3 * D * D + 2 * D);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        e[i * D + j] = A[i][j];
+        e[D * D + i * D + j] = C[i][j];
+        e[2 * D * D + i * D + j] = J[i][j];
+      }
+      e[3 * D * D + i] = bv[i];
+      e[3 * D * D + D + i] = eta[i];
+    }
+  }
+}
+
+template <int D, int S, bool GIVEN>
+__global__ void __launch_bounds__(128) seq_smooth_summary_kernel(const SeqSmoothArgs p, double* __restrict__ elems) {
+  SeqWork wk;
+  if (!seq_work<true>(p, wk)) return;
+  constexpr int NB = D / S;
+  const int64_t b = wk.b, t0 = wk.t0, T = wk.T;
+  const int64_t sts = p.sts;
+  double Pinf[D][D], lam[NB];
+  if (!GIVEN) {
+    load_mat<D>(p.Pinf + b * p.Pinf_bs, Pinf);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) lam[i] = p.lam[b * p.lam_bs + i];
+  }
+  double E[D][D], g[D], L[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    g[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      E[i][j] = (i == j) ? 1.0 : 0.0;
+      L[i][j] = 0.0;
+    }
+  }
+  const int64_t row0 = b * p.sbs + t0 * sts;
+  const double* __restrict__ dtp = p.dt + b * p.dt_bs + t0;
+  const double* __restrict__ Ap = GIVEN ? p.A + b * p.A_bs + t0 * D * D : nullptr;
+  const double* __restrict__ Qp = GIVEN ? p.Q + b * p.Q_bs + t0 * D * D : nullptr;
+  const double* __restrict__ mfp = p.mf + row0 * D;
+  const double* __restrict__ Pfp = p.Pf + row0 * D * D;
+  double mf_n[D], Pf_n[D][D], dt_n;
+  load_vec<D>(mfp + (T - 1) * sts * D, mf_n);
+  load_mat<D>(Pfp + (T - 1) * sts * D * D, Pf_n);
+  dt_n = dtp[T - 1];
+  for (int64_t k = T - 1; k >= 0; --k) {
+    double mf[D], Pf[D][D];
+    const double dt = dt_n;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      mf[i] = mf_n[i];
+#pragma unroll
+      for (int j = 0; j < D; ++j) Pf[i][j] = Pf_n[i][j];
+    }
+    if (k >= 1) {
+      load_vec<D>(mfp + (k - 1) * sts * D, mf_n);
+      load_mat<D>(Pfp + (k - 1) * sts * D * D, Pf_n);
+      dt_n = dtp[k - 1];
+    }
+    Trans<D, S> Phi;
+    if constexpr (GIVEN) {
+      double Q[D][D];
+      load_trans_dense<D, S>(Ap + k * D * D, Phi);
+      load_mat<D>(Qp + k * D * D, Q);
+      rts_step<D, S>(Phi, Q, false, mf, Pf, p.jitter, g, L, E);
+    } else {
+      matern_trans<D, S>(lam, dt, Phi);
+      rts_step<D, S>(Phi, Pinf, true, mf, Pf, p.jitter, g, L, E);
+    }
+  }
+  if (wk.active) {
+    double* __restrict__ e = elems + (b * p.nchunk + wk.c) * (2 * D * D + D);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        e[i * D + j] = E[i][j];
+        e[D * D + i * D + j] = L[i][j];
+      }
+      e[2 * D * D + i] = g[i];
+    }
+  }
+}
+
+template <int D, int S, int M, bool HID, bool GIVEN>
+static int launch_filter_summary(cudaStream_t st, const SeqFilterArgs& a, double* elems) {
+  const int64_t n = ((a.B + 31) / 32 * 32) * a.chunk_count;
+  const int block = pick_block(n);
+  seq_filter_summary_kernel<D, S, M, HID, GIVEN><<<(unsigned)((n + block - 1) / block), block, 0, st>>>(a, elems);
+  return cuda_status(cudaGetLastError(), "seq_filter_summary_kernel launch");
+}
+
+template <int D, int S, bool GIVEN>
+static int filter_summary_by_m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems) {
+  if (hid && m == D) return launch_filter_summary<D, S, D, true, GIVEN>(st, a, elems);
+  if (m == 1) return launch_filter_summary<D, S, 1, false, GIVEN>(st, a, elems);
+  if (D >= 2 && m == 2) return launch_filter_summary<D, S, (D >= 2 ? 2 : 1), false, GIVEN>(st, a, elems);
+  if (D >= 3 && m == 3) return launch_filter_summary<D, S, (D >= 3 ? 3 : 1), false, GIVEN>(st, a, elems);
+  if (D >= 4 && m == 4) return launch_filter_summary<D, S, (D >= 4 ? 4 : 1), false, GIVEN>(st, a, elems);
+  return set_error(PHYSS_ERR_UNSUPPORTED, "seq filter summary: unsupported observation dim");
+}
+
+template <int D, int S, bool GIVEN>
+static int launch_smooth_summary(cudaStream_t st, const SeqSmoothArgs& a, double* elems) {
+  const int64_t n = ((a.B + 31) / 32 * 32) * a.chunk_count;
+  const int block = pick_block(n);
+  seq_smooth_summary_kernel<D, S, GIVEN><<<(unsigned)((n + block - 1) / block), block, 0, st>>>(a, elems);
+  return cuda_status(cudaGetLastError(), "seq_smooth_summary_kernel launch");
+}
+
+
 template <int D, int S, int M, bool HID, bool GIVEN>
 static int launch_filter(cudaStream_t st, const SeqFilterArgs& a) {
   const int64_t n = ((a.B + 31) / 32 * 32) * (a.nchunk > 0 ? a.chunk_count : 1);

@@ -70,21 +70,51 @@ def _c(t):
     return t.contiguous()
 
 
+def _is_tm(t):
+    """[B, T, ...] view of a contiguous [T, B, ...] tensor (the time-major batch layout of ops.py)."""
+    return t.dim() >= 3 and not t.is_contiguous() and t.transpose(0, 1).is_contiguous()
+
+
+def _block_order(tensors):
+    """The site kernels treat the leading dims as one flat axis of independent blocks, so any memory order
+    works as long as every per-block array uses the same one.  If all of them are time-major views, run on
+    the underlying [T, B, ...] memory (no copies); otherwise make everything batch-major contiguous.
+    Returns (tensors, time_major)."""
+    live = [t for t in tensors if t is not None]
+    if live and all(_is_tm(t) for t in live):
+        return [None if t is None else t.transpose(0, 1) for t in tensors], True
+    return [None if t is None else _c(t) for t in tensors], False
+
+
+def _like(x, tm):
+    """Uninitialised tensor with the logical shape and memory order of x (x already in kernel order)."""
+    return torch.empty_like(x)
+
+
+def _back(x, tm):
+    return x.transpose(0, 1) if (tm and x is not None) else x
+
+
+def time_major_blocks(x):
+    """Re-store a [B, T, ...] tensor time-major (logical shape unchanged)."""
+    return x.transpose(0, 1).contiguous().transpose(0, 1)
+
+
 def natgrad_step(Ytil, Vtil, q_mu, q_var, y, W, lik, beta, ng_jitter=None, K=20, dm=None, dS=None,
                  want_ell=False, out=None, stream=None):
     """Raw op: all tensors are CUDA float64 with the site blocks flattened to N = prod(leading dims).
     Ytil [..., D], Vtil [..., D, D], q_mu, q_var alike; y [..., P]; W [P, D] or None.
     Returns (Ytil_new, Vtil_new[, ell [...]])."""
     lib = _lib.load()
-    Ytil, Vtil, q_mu, q_var = _c(Ytil), _c(Vtil), _c(q_mu), _c(q_var)
+    given = dm is not None
+    (Ytil, Vtil, q_mu, q_var, yv, dm, dS), tm = _block_order(
+        [Ytil, Vtil, q_mu, q_var, None if given else y, dm, dS])
     D = Ytil.shape[-1]
     lead = Ytil.shape[:-1]
     N = int(np.prod(lead))
     dev = Ytil.device
-    given = dm is not None
     kind = _lib.LIK_GIVEN if given else lik.kind
-    P = 1 if given else y.shape[-1]
-    yv = None if given else _c(y)
+    P = 1 if given else yv.shape[-1]
     Wv = None if W is None else _c(W)
     noise = None
     nstride = 0
@@ -98,7 +128,9 @@ def natgrad_step(Ytil, Vtil, q_mu, q_var, y, W, lik, beta, ng_jitter=None, K=20,
     if out is None:
         Yn, Vn = torch.empty_like(Ytil), torch.empty_like(Vtil)
     else:
-        Yn, Vn = out
+        (Yn, Vn), tm_out = _block_order(list(out))
+        if tm_out != tm or Yn.data_ptr() != out[0].data_ptr() or Vn.data_ptr() != out[1].data_ptr():
+            raise ValueError("out buffers must use the memory order of the sites")
     ell = torch.empty(lead, dtype=torch.float64, device=dev) if want_ell else None
     ngj = settings.ng_jitter if ng_jitter is None else ng_jitter
     s = stream if stream is not None else torch.cuda.current_stream()
@@ -106,9 +138,10 @@ def natgrad_step(Ytil, Vtil, q_mu, q_var, y, W, lik, beta, ng_jitter=None, K=20,
         st = lib.physs_cvi_natgrad_step_f64(
             s.cuda_stream, N, D, P, kind, Ytil.data_ptr(), Vtil.data_ptr(), q_mu.data_ptr(), q_var.data_ptr(),
             _ptr(yv), _ptr(Wv), _ptr(noise), nstride, float(0.0 if given else lik.param), int(K),
-            _ptr(ghx), _ptr(ghw), _ptr(_c(dm) if given else None), _ptr(_c(dS) if given else None),
+            _ptr(ghx), _ptr(ghw), _ptr(dm if given else None), _ptr(dS if given else None),
             float(beta), float(ngj), Yn.data_ptr(), Vn.data_ptr(), _ptr(ell))
     _lib.check(st, "physs_cvi_natgrad_step_f64")
+    Yn, Vn, ell = _back(Yn, tm), _back(Vn, tm), _back(ell, tm)
     return (Yn, Vn, ell) if want_ell else (Yn, Vn)
 
 
@@ -116,7 +149,8 @@ def expected_log_likelihood(q_mu, q_var, y, W, lik, K=20, noise=None, want_grads
     """Raw op: per-block ELL [...], optionally with dELL/dm [..., D] and dELL/dS [..., D, D].
     `noise` overrides lik.noise with a per-block tensor [..., P, P] (used for the surrogate ELL)."""
     lib = _lib.load()
-    q_mu, q_var, y = _c(q_mu), _c(q_var), _c(y)
+    per_block_noise = noise if (noise is not None and noise.dim() > 2) else None
+    (q_mu, q_var, y, per_block_noise), tm = _block_order([q_mu, q_var, y, per_block_noise])
     D, P = q_mu.shape[-1], y.shape[-1]
     lead = q_mu.shape[:-1]
     N = int(np.prod(lead))
@@ -124,8 +158,10 @@ def expected_log_likelihood(q_mu, q_var, y, W, lik, K=20, noise=None, want_grads
     Wv = None if W is None else _c(W)
     nz, nstride = None, 0
     if lik.kind == _lib.LIK_GAUSS:
-        nz = noise if noise is not None else torch.as_tensor(lik.noise, device=dev)
-        nz = _c(nz)
+        if per_block_noise is not None:
+            nz = per_block_noise
+        else:
+            nz = _c(noise if noise is not None else torch.as_tensor(lik.noise, device=dev))
         nstride = 0 if nz.dim() == 2 else P * P
     ghx = ghw = None
     if lik.kind != _lib.LIK_GAUSS:
@@ -139,6 +175,43 @@ def expected_log_likelihood(q_mu, q_var, y, W, lik, K=20, noise=None, want_grads
                                    y.data_ptr(), _ptr(Wv), _ptr(nz), nstride, float(lik.param), int(K),
                                    _ptr(ghx), _ptr(ghw), ell.data_ptr(), _ptr(dm), _ptr(dS))
     _lib.check(st, "physs_cvi_ell_f64")
+    ell, dm, dS = _back(ell, tm), _back(dm, tm), _back(dS, tm)
+    return (ell, dm, dS) if want_grads else ell
+
+
+class DampedPendulumLik:
+    """Likelihood of the PHYSS-GP damped-oscillator model: MultiOutput([observe x, DampedPendulum1D residual])
+    (zoo/sde_diff.py:757-763, transforms/pdes.py:530-597) with Gaussian noise `var_obs` on x and `var_col` on
+    the collocation residual.  Data rows are (observation of x, collocation target = 0), NaN = absent.
+    state_index: positions of (x, x_t, x_tt) inside the site block."""
+    kind = "pendulum"
+
+    def __init__(self, g, l, b, var_obs, var_col, state_index=(0, 1, 2)):
+        self.g_over_l, self.b = float(g) / float(l), float(b)
+        self.var_obs, self.var_col = float(var_obs), float(var_col)
+        self.state_index = tuple(int(i) for i in state_index)
+
+
+def pendulum_expected_log_likelihood(q_mu, q_var, y, lik, gauss_newton=False, want_grads=False, stream=None):
+    """Raw op: closed-form collocation ELL [...], optionally dELL/dm [..., D] and the site curvature
+    [..., D, D] (exact dELL/dS, or its Gauss-Newton delta-u replacement).  y [..., 2]."""
+    lib = _lib.load()
+    (q_mu, q_var, y), tm = _block_order([q_mu, q_var, y])
+    D = q_mu.shape[-1]
+    lead = q_mu.shape[:-1]
+    N = int(np.prod(lead))
+    dev = q_mu.device
+    ell = torch.empty(lead, dtype=torch.float64, device=dev)
+    dm = torch.empty(lead + (D,), dtype=torch.float64, device=dev) if want_grads else None
+    dS = torch.empty(lead + (D, D), dtype=torch.float64, device=dev) if want_grads else None
+    s = stream if stream is not None else torch.cuda.current_stream()
+    i0, i1, i2 = lik.state_index
+    with torch.cuda.device(dev):
+        st = lib.physs_cvi_ell_pendulum_f64(s.cuda_stream, N, D, i0, i1, i2, q_mu.data_ptr(), q_var.data_ptr(),
+                                            y.data_ptr(), lik.g_over_l, lik.b, lik.var_obs, lik.var_col,
+                                            1 if gauss_newton else 0, ell.data_ptr(), _ptr(dm), _ptr(dS))
+    _lib.check(st, "physs_cvi_ell_pendulum_f64")
+    ell, dm, dS = _back(ell, tm), _back(dm, tm), _back(dS, tm)
     return (ell, dm, dS) if want_grads else ell
 
 
@@ -148,7 +221,8 @@ class FullConjugateGaussian:
     (conjugate_gaussian_approximate_posterior.py:174-246).  Reference initialisation: Y~ = 1e-5,
     V~ = I (:209-218)."""
 
-    def __init__(self, X_time, surrogate_prior, block_size, B=1, Y_tilde=None, V_tilde=None, device=None):
+    def __init__(self, X_time, surrogate_prior, block_size, B=1, Y_tilde=None, V_tilde=None, device=None,
+                 filter_type='b200'):
         dev = device or torch.device("cuda", torch.cuda.current_device())
         T = len(X_time)
         D = block_size
@@ -159,12 +233,16 @@ class FullConjugateGaussian:
         self.V_tilde = (torch.eye(D, dtype=torch.float64, device=dev).expand(B, T, D, D).contiguous()
                         if V_tilde is None
                         else torch.as_tensor(V_tilde, dtype=torch.float64).to(dev).reshape(B, T, D, D).clone())
+        if settings.time_major and B >= settings.time_major_min_batch:
+            # sites live in the batch layout the filter / smoother kernels produce (no re-ordering copies)
+            self.Y_tilde, self.V_tilde = time_major_blocks(self.Y_tilde), time_major_blocks(self.V_tilde)
         self.prior = surrogate_prior
+        self.filter_type = filter_type        # threaded to the surrogate SDE_GP (zoo/sde_diff.py:690,712,736,752)
 
     @property
     def surrogate(self):
         data = TemporalData(self.X_time, self.Y_tilde[..., None])          # [B, T, P=D, Ns=1]
-        return SDE_GP(data, self.prior, BlockDiagonalGaussian(self.V_tilde))
+        return SDE_GP(data, self.prior, BlockDiagonalGaussian(self.V_tilde), filter_type=self.filter_type)
 
 
 class VGP:
@@ -176,20 +254,35 @@ class VGP:
         q = approximate_posterior
         dev = q.Y_tilde.device
         self.q = q
-        self.Y = torch.as_tensor(Y, dtype=torch.float64).to(dev)
-        if self.Y.dim() == 2:
-            self.Y = self.Y[None]
+        self.set_data(Y)
         self.lik = likelihood
         self.W = None if W is None else torch.as_tensor(W, dtype=torch.float64).to(dev)
         self.K = ell_quad_points
 
+    def set_data(self, Y):
+        """Data [B, T, P] (host or device); stored in the memory order of the sites."""
+        dev = self.q.Y_tilde.device
+        Y = torch.as_tensor(Y, dtype=torch.float64).to(dev, non_blocking=True)
+        if Y.dim() == 2:
+            Y = Y[None]
+        self.Y = time_major_blocks(Y) if _is_tm(self.q.Y_tilde) else Y
+
     def natural_gradient_update(self, lr, enforce_psd_type=None, prediction_samples=None):
         """vgp.py:274-282 -> cvi_nat_grad.py:508-515,346-410 -> cvi_parameterisations.py:63-93."""
-        if enforce_psd_type is not None:
-            raise NotImplementedError("only enforce_psd_type=None is implemented on the b200 path")
+        pde = getattr(self.lik, "kind", None) == "pendulum"
+        if enforce_psd_type not in (None, 'laplace_gauss_newton_delta_u') or (enforce_psd_type and not pde):
+            raise NotImplementedError("enforce_psd_type: None, or 'laplace_gauss_newton_delta_u' with a PDE "
+                                      "collocation likelihood, are implemented on the b200 path")
         q = self.q
         q_mu, q_var = q.surrogate.posterior_blocks()               # [B,T,D,1], [B,T,1,D,D]
         q_mu, q_var = q_mu[..., 0], q_var[..., 0, :, :]
+        if pde:
+            # cvi_nat_grad.py:381-387: dELL/dm from the ELL, dELL/dS replaced by the Gauss-Newton curvature
+            _, dm, dS = pendulum_expected_log_likelihood(q_mu, q_var, self.Y, self.lik,
+                                                         gauss_newton=enforce_psd_type is not None, want_grads=True)
+            natgrad_step(q.Y_tilde, q.V_tilde, q_mu, q_var, None, None, None, lr, dm=dm, dS=dS,
+                         out=(q.Y_tilde, q.V_tilde))
+            return
         natgrad_step(q.Y_tilde, q.V_tilde, q_mu, q_var, self.Y, self.W, self.lik, lr, K=self.K,
                      out=(q.Y_tilde, q.V_tilde))
 
@@ -198,7 +291,10 @@ class VGP:
         q = self.q
         lml, q_mu, q_var = q.surrogate.posterior_blocks(return_lml=True)
         q_mu, q_var = q_mu[..., 0], q_var[..., 0, :, :]
-        ell = expected_log_likelihood(q_mu, q_var, self.Y, self.W, self.lik, K=self.K)
+        if getattr(self.lik, "kind", None) == "pendulum":
+            ell = pendulum_expected_log_likelihood(q_mu, q_var, self.Y, self.lik)
+        else:
+            ell = expected_log_likelihood(q_mu, q_var, self.Y, self.W, self.lik, K=self.K)
         sur = GaussianLik(np.eye(q.block_size))
         ell_s = expected_log_likelihood(q_mu, q_var, q.Y_tilde, None, sur, noise=q.V_tilde)
         return ell.sum(dim=-1) - ell_s.sum(dim=-1) + lml

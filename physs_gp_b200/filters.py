@@ -126,6 +126,20 @@ def filter(data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask,
     return _filter_impl(True, data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask, train_index)
 
 
+def _auto_parallel(B, T):
+    """filter_type='b200_auto' (the counterpart of the reference's parallel='auto', zoo/sde_diff.py:370-378):
+    go parallel in time when the batch alone cannot fill the GPU (one thread / lane group per series needs
+    ~10^4 series) and the series is long enough to cut into chunks."""
+    return B < settings.auto_parallel_max_batch and T >= settings.auto_parallel_min_steps
+
+
+@dispatch('b200_auto')
+def filter(data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, train_test_mask, train_index):  # noqa: F811
+    B = Y.shape[0] if Y.dim() == 4 else (prior.B if isinstance(prior, BatchedMaternSDE) else 1)
+    return _filter_impl(_auto_parallel(B, Y.shape[-3]), data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag,
+                        train_test_mask, train_index)
+
+
 def _smoother_impl(parallel, data, model, filter_res, dt, X_t, X_s, full_state):
     """B200 backend of evoke('smoother', filter_type) -- rts_smoother.py:162-192.
     dt [T] with dt[k] = t_{k+1} - t_k, dt[T-1] = 0."""
@@ -189,3 +203,10 @@ def smoother_loop(data, model, filter_res, full_state=False, filter_type='b200')
     dt = torch.cat([X_t[1:] - X_t[:-1], torch.zeros(1, dtype=torch.float64, device=dev)])
     smoother_fn = evoke('smoother', filter_type)
     return smoother_fn(data, model, filter_res, dt, X_t, X_s, full_state)
+
+
+@dispatch('b200_auto')
+def smoother(data, model, filter_res, dt, X_t, X_s, full_state):  # noqa: F811
+    mf = filter_res['m']
+    B, T = (mf.shape[0], mf.shape[1]) if mf.dim() == 4 else (1, mf.shape[0])
+    return _smoother_impl(_auto_parallel(B, T), data, model, filter_res, dt, X_t, X_s, full_state)

@@ -232,10 +232,12 @@ def rts_smooth(dt, mf, Pf, disc, Hout=None, jitter=None, out=None, stream=None):
 
 
 # ------------------------------------------------------------------------------- parallel-in-time
-def default_chunk_len(B, T):
-    """Chunk length that gives the GPU ~ 148 SMs x 16 lane groups of independent work, clamped to
-    [32, T]: long single series get many short chunks, large batches few long ones."""
-    want_chunks = max(1, (148 * 16 + B - 1) // B)
+def default_chunk_len(B, T, d=8):
+    """Chunk length that gives the GPU enough independent (series, chunk) pairs, clamped to [32, T]:
+    ~64k for the register kernels (d <= 4: one THREAD per pair), ~148 SMs x 64 lane groups above.
+    Long single series get many short chunks, large batches few long ones."""
+    target = 65536 if d <= 4 else 148 * 64
+    want_chunks = max(1, (target + B - 1) // B)
     return int(min(T, max(32, -(-T // want_chunks))))
 
 
@@ -260,7 +262,7 @@ def pscan_filter(dt, Y, R, H, m0, P0, disc, chunk_len=None, jitter=None, polish=
     With return_status the device flag (1 = a chunk did not converge during polishing) is appended."""
     lib = _lib.load()
     p = _pack_filter(dt, Y, R, H, m0, P0, disc, jitter, stream)
-    L = default_chunk_len(p.B, p.T) if chunk_len is None else int(chunk_len)
+    L = default_chunk_len(p.B, p.T, p.d) if chunk_len is None else int(chunk_len)
     mf, Pf, lml, lml_k = _filter_outputs(p, out, want_lml_k)
     ws = pscan_workspace(p.B, p.T, p.d, L, p.dev) if ws is None else ws
     status = torch.zeros((1,), dtype=torch.int32, device=p.dev)
@@ -277,7 +279,7 @@ def pscan_smooth(dt, mf, Pf, disc, Hout=None, chunk_len=None, jitter=None, out=N
     """Parallel-in-time RTS smoother: same arguments / results as rts_smooth."""
     lib = _lib.load()
     p = _pack_smooth(dt, mf, Pf, disc, Hout, jitter, stream)
-    L = default_chunk_len(p.B, p.T) if chunk_len is None else int(chunk_len)
+    L = default_chunk_len(p.B, p.T, p.d) if chunk_len is None else int(chunk_len)
     ms, Ps = _smooth_outputs(p, out)
     ws = pscan_workspace(p.B, p.T, p.d, L, p.dev) if ws is None else ws
     with torch.cuda.device(p.dev):

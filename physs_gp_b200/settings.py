@@ -19,3 +19,7 @@ time_major_min_batch = 32
 # jitter != 0 else 0); see include/physs_b200.h, "Parallel-in-time forms".
 pscan_chunk_len = None
 pscan_polish = None
+
+# filter_type='b200_auto': parallel in time below this batch size and above this series length
+auto_parallel_max_batch = 8192
+auto_parallel_min_steps = 1024

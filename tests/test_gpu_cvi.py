@@ -163,3 +163,73 @@ def test_cvi_gaussian_fixed_point_on_gpu(cuda_device):
     assert float((q.V_tilde - 0.3).abs().max()) < 1e-7
     lml, _ = filters.filter_loop(data.TemporalData(t, Y[..., None]), prior, R=np.full([1, 1, 1, 1], 0.3))
     assert float(((elbo - lml) / lml).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("D,idx", [(3, (0, 1, 2)), (4, (0, 1, 2)), (6, (3, 4, 5)), (8, (4, 1, 6))])
+@pytest.mark.parametrize("gn", [False, True])
+def test_pendulum_collocation_kernel_matches_oracle(cuda_device, D, idx, gn):
+    """physs_cvi_ell_pendulum_f64 (closed-form collocation ELL, mean gradient, exact / Gauss-Newton curvature)
+    against oracle.cvi.pendulum_ell_and_grads."""
+    from physs_gp_b200 import cvi
+    rng = np.random.default_rng(7 * D + gn)
+    N = 53
+    q_mu = rng.normal(size=(N, D))
+    q_var = synth.random_spd(rng, (N,), D, base=0.02, spread=0.2)
+    y = np.stack([q_mu[:, idx[0]] + 0.1 * rng.normal(size=N), np.zeros(N)], -1)
+    y[rng.uniform(size=N) < 0.3, 0] = np.nan
+    y[rng.uniform(size=N) < 0.2, 1] = np.nan
+    lik = cvi.DampedPendulumLik(g=9.81, l=7.0, b=0.2, var_obs=0.05, var_col=0.01, state_index=idx)
+    ell, dm, dS = cvi.pendulum_expected_log_likelihood(_dev(q_mu), _dev(q_var), _dev(y), lik, gauss_newton=gn,
+                                                       want_grads=True)
+    ref = [ocvi.pendulum_ell_and_grads(y[n], q_mu[n], q_var[n], 9.81 / 7.0, 0.2, 0.05, 0.01, gn, idx) for n in range(N)]
+    assert rel(ell, np.array([r[0] for r in ref])) < TOL
+    assert rel(dm, np.stack([r[1] for r in ref])) < TOL
+    assert rel(dS, np.stack([r[2] for r in ref])) < TOL
+
+
+def test_pendulum_cvi_iterations_match_oracle_and_fit(cuda_device):
+    """Physics-informed CVI on a simulated damped pendulum (BASELINE config 3 shape, small): Matern-7/2 state
+    (x, x_t, x_tt, x_ttt), full-state sites, sparse noisy observations of x + collocation at every step,
+    Gauss-Newton curvature.  Four iterations must equal the numpy oracle and the posterior must track x."""
+    from physs_gp_b200 import cvi, sdes
+    rng = np.random.default_rng(4)
+    T, dt = 300, 0.02
+    a, b = 9.81 / 1.0, 0.3
+    x, v = 1.2, 0.0
+    xs = []
+    for _ in range(T):                       # RK-free fine Euler integration of the true dynamics
+        for _ in range(20):
+            acc = -a * np.sin(x) - b * v
+            x, v = x + v * dt / 20, v + acc * dt / 20
+        xs.append(x)
+    xs = np.array(xs)
+    t = dt * np.arange(1, T + 1)
+    Y = np.full((1, T, 2), np.nan)
+    obs = np.arange(0, T, 10)
+    Y[0, obs, 0] = xs[obs] + 0.05 * rng.normal(size=len(obs))
+    Y[0, :, 1] = 0.0
+    prior = sdes.BatchedMaternSDE(4, np.array([[0.6]]), np.array([[2.0]]), full_state_obs=True)
+    q = cvi.FullConjugateGaussian(t, prior, 4, B=1)
+    lik = cvi.DampedPendulumLik(g=9.81, l=1.0, b=b, var_obs=0.05 ** 2, var_col=0.5 ** 2)
+    model = cvi.VGP(Y, lik, q)
+    elbos = []
+    NIT = 8
+    for _ in range(NIT):
+        model.natural_gradient_update(0.5, enforce_psd_type='laplace_gauss_newton_delta_u')
+        elbos.append(float(model.elbo()[0]))
+    torch.cuda.synchronize()
+    # oracle
+    op = osde.LTI_SDE_Full_State_Obs([osde.Matern72(0.6, 2.0)])
+    Yt = 1e-5 * np.ones((T, 4)); Vt = np.tile(np.eye(4), [T, 1, 1])
+    for _ in range(NIT):
+        _, qm, qv = ofilters.filter_and_smooth(op, t, Yt, Vt)
+        g = [ocvi.pendulum_ell_and_grads(Y[0, i], qm[i][:, 0], qv[i], a, b, 0.05 ** 2, 0.5 ** 2, True) for i in range(T)]
+        Yt, Vt = ocvi.cvi_step(Yt, Vt, qm[:, :, 0], qv, np.stack([x_[1] for x_ in g]), np.stack([x_[2] for x_ in g]), 0.5)
+    lml, qm, qv = ofilters.filter_and_smooth(op, t, Yt, Vt)
+    ell = sum(ocvi.pendulum_ell_and_grads(Y[0, i], qm[i][:, 0], qv[i], a, b, 0.05 ** 2, 0.5 ** 2)[0] for i in range(T))
+    ref = ocvi.elbo(ell, ocvi.surrogate_ell(Yt, Vt, qm[:, :, 0], qv), lml)
+    assert rel(q.Y_tilde[0], Yt) < 1e-6 and rel(q.V_tilde[0], Vt) < 1e-6     # V~ has 1/ng_jitter entries (cond ~ 1e7)
+    assert abs(elbos[-1] - ref) < 1e-6 * abs(ref)
+    assert elbos[-1] > elbos[0]
+    mu, _ = q.surrogate.posterior_blocks()
+    assert float(np.abs(mu[0, :, 0, 0].cpu().numpy() - xs).max()) < 0.3

@@ -85,3 +85,34 @@ def test_cvi_gaussian_fixed_point_and_elbo_equals_lml():
     ell_s = cvi.surrogate_ell(Yn, Vn, q_mu2[:, :, 0], q_var2)
     exact, _, _, _ = filters.filter_sequential(prior, t, y, np.tile(np.array([[Rn]]), [T, 1, 1]), jitter=0.0)
     assert abs(cvi.elbo(ell, ell_s, lml_s) - exact) < 1e-5 * abs(exact)
+
+
+def test_pendulum_collocation_ell_closed_form_vs_quadrature_and_finite_differences():
+    """The closed-form damped-oscillator collocation ELL (oracle.cvi.pendulum_ell_and_grads): value against a
+    40^3-point tensor Gauss-Hermite rule, gradients against central finite differences of the closed form."""
+    from oracle import cvi as ocvi
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        G = rng.normal(size=(3, 3)) * 0.3
+        S = G @ G.T + 0.02 * np.eye(3)
+        m = rng.normal(size=3) * np.array([1.0, 0.5, 0.5])
+        y = np.array([m[0] + 0.1, 0.0]) if trial < 3 else np.array([np.nan, 0.0])
+        args = (1.3, 0.2, 0.05, 0.01)
+        ell, dm, dS = ocvi.pendulum_ell_and_grads(y, m, S, *args)
+        assert abs(ell - ocvi.pendulum_ell_quadrature(y, m, S, *args)) < 1e-9 * max(1.0, abs(ell))
+        h = 1e-6
+        for i in range(3):
+            e = np.zeros(3); e[i] = h
+            fd = (ocvi.pendulum_ell_and_grads(y, m + e, S, *args)[0] - ocvi.pendulum_ell_and_grads(y, m - e, S, *args)[0]) / (2 * h)
+            assert abs(fd - dm[i]) < 1e-6 * max(1.0, abs(dm[i]))
+            for j in range(3):
+                E = np.zeros((3, 3)); E[i, j] += h / 2; E[j, i] += h / 2      # symmetric perturbation
+                fd = (ocvi.pendulum_ell_and_grads(y, m, S + E, *args)[0] - ocvi.pendulum_ell_and_grads(y, m, S - E, *args)[0]) / (2 * h)
+                sym = 0.5 * (dS[i, j] + dS[j, i]) if i != j else dS[i, j]
+                assert abs(fd - (sym if i == j else 2 * sym * 0.5)) < 1e-6 * max(1.0, abs(sym)), (i, j, fd, sym)
+        # Gauss-Newton curvature is negative semi-definite and equals -1/2 J^T J / var
+        _, _, dS_gn = ocvi.pendulum_ell_and_grads(y, m, S, *args, gauss_newton=True)
+        assert np.linalg.eigvalsh(dS_gn).max() <= 1e-12
+        J = np.array([1.3 * np.cos(m[0]), 0.2, 1.0])
+        ref = -0.5 * np.outer(J, J) / 0.01 + (0 if np.isnan(y[0]) else -0.5 * np.outer([1, 0, 0], [1, 0, 0]) / 0.05)
+        assert np.allclose(dS_gn, ref, rtol=1e-13, atol=1e-13)
