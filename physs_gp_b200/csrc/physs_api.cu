@@ -1,5 +1,6 @@
 // physs_api.cu -- the extern "C" surface of libphyss_b200.so (see include/physs_b200.h).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "physs_internal.h"
@@ -23,14 +24,31 @@ int cuda_status(cudaError_t e, const char* what) {
 
 namespace physs {
 
+// PHYSS_FORCE_GRP=1 (debug / A-B timing only): route sizes both families cover to the lane-group kernels
+static bool force_grp(int d) {
+  static const bool on = [] { const char* e = getenv("PHYSS_FORCE_GRP"); return e && e[0] == '1'; }();
+  return on && d > 4;
+}
+
+// d = 8 is covered by both families.  Measured on B200: one thread per series with
+// local-memory tiles wins 3x over the lane-group kernels when thousands of series are in flight and the
+// update is light (m <= 4); with few (series, chunk) pairs or full-state updates its per-step dependency
+// chain (thousands of instructions through local memory) makes it 3-30x slower.
+static bool prefer_seq(int d, int m, int64_t B, int64_t nchunk) {
+  if (d <= 4) return true;
+  return nchunk == 0 && B >= 4096 && m <= 4;
+}
+
 int run_filter_any(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity, const SeqFilterArgs& a) {
-  if (seq_supported(d, m, disc_mode, nblk)) return seq_filter(st, d, m, disc_mode, nblk, h_identity, a);
+  if (!force_grp(d) && prefer_seq(d, m, a.B, a.nchunk) && seq_supported(d, m, disc_mode, nblk))
+    return seq_filter(st, d, m, disc_mode, nblk, h_identity, a);
   if (m > d) return set_error(PHYSS_ERR_UNSUPPORTED, "filter: m > d is not supported");
   return grp_filter(st, d, m, disc_mode, nblk, h_identity, a);
 }
 
 int run_smooth_any(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a) {
-  if (seq_supported(d, mo == 0 ? d : mo, disc_mode, nblk)) return seq_smooth(st, d, mo, disc_mode, nblk, a);
+  if (!force_grp(d) && prefer_seq(d, 1, a.B, a.nchunk) && seq_supported(d, mo == 0 ? d : mo, disc_mode, nblk))
+    return seq_smooth(st, d, mo, disc_mode, nblk, a);
   return grp_smooth(st, d, mo, disc_mode, nblk, a);
 }
 

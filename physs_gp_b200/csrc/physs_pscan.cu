@@ -969,7 +969,7 @@ int pscan_filter_local(cudaStream_t st, int d, int m, int disc_mode, int nblk, b
   const PcLayout Lc = pc_layout(d);
   const int64_t nfull = a.T / chunk_len;
   const int64_t nfull_sum = nfull < nsum ? nfull : nsum;
-  const bool reg = seq_supported(d, m, disc_mode, nblk);     // register-resident summaries for d <= 4
+  const bool reg = d <= 4 && seq_supported(d, m, disc_mode, nblk);     // register-resident summaries for d <= 4
   auto summarise = [&](int64_t first, int64_t count) -> int {
     if (count <= 0) return PHYSS_OK;
     if (reg) {
@@ -1095,7 +1095,7 @@ int pscan_smooth_local(cudaStream_t st, int d, int disc_mode, int nblk, SeqSmoot
   const PsLayout L = ps_layout(d, 1, given ? 0 : nblk, given, true);
   const SsLayout Ls = ss_layout(d);
   const int64_t nfull = a.T / chunk_len;
-  const bool reg = seq_supported(d, d, disc_mode, nblk);
+  const bool reg = d <= 4 && seq_supported(d, d, disc_mode, nblk);
   if (nfull > 0) {
     a.chunk_first = 0; a.chunk_count = nfull;
     rc = reg ? seq_smooth_summary(st, d, disc_mode, nblk, a, w.e0) : PS_BY_G_GIVEN(run_smooth_summary, st, a, L, w.e0);

@@ -29,6 +29,8 @@ int seq_smooth_d4s2m(cudaStream_t st, const SeqSmoothArgs& a, int mo);
 int seq_filter_d4s4m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
 int seq_smooth_d4s4m(cudaStream_t st, const SeqSmoothArgs& a, int mo);
 int seq_filter_d4s4g(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_filter_d8s4m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid);
+int seq_smooth_d8s4m(cudaStream_t st, const SeqSmoothArgs& a, int mo);
 int seq_smooth_d4s4g(cudaStream_t st, const SeqSmoothArgs& a, int mo);
 
 int seq_filter_summary_d1s1m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems);
@@ -57,6 +59,8 @@ int seq_filter_summary_d4s4g(cudaStream_t st, const SeqFilterArgs& a, int m, boo
 int seq_smooth_summary_d4s4g(cudaStream_t st, const SeqSmoothArgs& a, double* elems);
 
 bool seq_supported(int d, int m, int disc_mode, int nblk) {
+  // d = 8 as two Matern-7/2 blocks (m <= 4 or full-state m = 8): thread-per-series with local-memory tiles
+  if (d == 8 && disc_mode == PHYSS_DISC_MATERN && nblk == 2 && (m == 8 || (m >= 1 && m <= 4))) return true;
   if (d < 1 || d > 4 || m < 1 || m > d) return false;
   if (disc_mode == PHYSS_DISC_GIVEN) return true;
   if (disc_mode != PHYSS_DISC_MATERN || nblk <= 0 || d % nblk != 0) return false;
@@ -82,6 +86,7 @@ int seq_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_id
   if (d == 4 && s == 2 && g == false) return seq_filter_d4s2m(st, a, m, h_identity);
   if (d == 4 && s == 4 && g == false) return seq_filter_d4s4m(st, a, m, h_identity);
   if (d == 4 && s == 4 && g == true) return seq_filter_d4s4g(st, a, m, h_identity);
+  if (d == 8 && s == 4 && g == false) return seq_filter_d8s4m(st, a, m, h_identity);
   return set_error(PHYSS_ERR_UNSUPPORTED, "seq filter: unreachable");
 }
 
@@ -102,6 +107,7 @@ int seq_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const Se
   if (d == 4 && s == 2 && g == false) return seq_smooth_d4s2m(st, a, mo);
   if (d == 4 && s == 4 && g == false) return seq_smooth_d4s4m(st, a, mo);
   if (d == 4 && s == 4 && g == true) return seq_smooth_d4s4g(st, a, mo);
+  if (d == 8 && s == 4 && g == false) return seq_smooth_d8s4m(st, a, mo);
   return set_error(PHYSS_ERR_UNSUPPORTED, "seq smoother: unreachable");
 }
 

@@ -178,6 +178,13 @@ __device__ __forceinline__ const double (&flat(const double (&P)[D][D]))[D * D] 
   return *reinterpret_cast<const double (*)[D * D]>(&P[0][0]);
 }
 
+// warps per block: the row tile of the largest per-step block must fit the 48 KB static shared memory
+template <int D>
+struct SeqBlock {
+  static constexpr int WARPS = (RowTile<D * D>::SIZE * 8 * 4 <= 48 * 1024) ? 4 : 2;
+  static constexpr int THREADS = 32 * WARPS;
+};
+
 // (series, chunk) of a thread.  Series are padded to a multiple of 32 per chunk so that a warp never
 // straddles two chunks; lanes beyond B shadow series B - 1 and never store.
 struct SeqWork {
@@ -229,8 +236,8 @@ __device__ __forceinline__ bool agrees(const double (&m)[D], const double (&P)[D
 }
 
 template <int D, int S, int M, bool HID, bool GIVEN, bool CHUNK>
-__global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) {
-  __shared__ __align__(16) double tiles[4][RowTile<D * D>::SIZE];
+__global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const SeqFilterArgs p) {
+  __shared__ __align__(16) double tiles[SeqBlock<D>::WARPS][RowTile<D * D>::SIZE];
   SeqWork wk;
   if (!seq_work<CHUNK>(p, wk)) return;
   constexpr int NB = D / S;
@@ -338,8 +345,8 @@ __global__ void __launch_bounds__(128) seq_filter_kernel(const SeqFilterArgs p) 
 // ---------------------------------------------------------------------------------------- smoother
 // MO == 0: full_state (H = I).  MO > 0: project with Hout [MO, D].
 template <int D, int S, int MO, bool GIVEN, bool CHUNK, bool COAL>
-__global__ void __launch_bounds__(128) seq_smooth_kernel(const SeqSmoothArgs p) {
-  __shared__ __align__(16) double tiles[4][RowTile<D * D>::SIZE];
+__global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_smooth_kernel(const SeqSmoothArgs p) {
+  __shared__ __align__(16) double tiles[SeqBlock<D>::WARPS][RowTile<D * D>::SIZE];
   SeqWork wk;
   if (!seq_work<CHUNK>(p, wk)) return;
   constexpr int NB = D / S;
@@ -713,7 +720,7 @@ static int launch_smooth_summary(cudaStream_t st, const SeqSmoothArgs& a, double
 template <int D, int S, int M, bool HID, bool GIVEN>
 static int launch_filter(cudaStream_t st, const SeqFilterArgs& a) {
   const int64_t n = ((a.B + 31) / 32 * 32) * (a.nchunk > 0 ? a.chunk_count : 1);
-  const int block = pick_block(n);
+  const int block = pick_block(n) < SeqBlock<D>::THREADS ? pick_block(n) : SeqBlock<D>::THREADS;
   const int64_t grid = (n + block - 1) / block;
   if (a.nchunk > 0)
     seq_filter_kernel<D, S, M, HID, GIVEN, true><<<(unsigned)grid, block, 0, st>>>(a);
@@ -725,7 +732,7 @@ static int launch_filter(cudaStream_t st, const SeqFilterArgs& a) {
 template <int D, int S, int MO, bool GIVEN>
 static int launch_smooth(cudaStream_t st, const SeqSmoothArgs& a) {
   const int64_t n = ((a.B + 31) / 32 * 32) * (a.nchunk > 0 ? a.chunk_count : 1);
-  const int block = pick_block(n);
+  const int block = pick_block(n) < SeqBlock<D>::THREADS ? pick_block(n) : SeqBlock<D>::THREADS;
   const int64_t grid = (n + block - 1) / block;
   const bool coal = (a.sbs == 1);
   if (a.nchunk > 0) {
