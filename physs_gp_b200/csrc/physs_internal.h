@@ -107,6 +107,11 @@ int grp_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_id
                const SeqFilterArgs& a);
 int grp_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
 
+// physs_rt.cu: one lane group per series, register-tiled products, compile-time padded dims (d <= 32)
+bool rt_supported(int d, int m);
+int rt_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity, const SeqFilterArgs& a);
+int rt_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
+
 // physs_pscan.cu: parallel-in-time chunked associative scan
 int64_t pscan_workspace_doubles(int64_t B, int64_t T, int d, int64_t chunk_len);
 int pscan_filter_local(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, SeqFilterArgs a,
