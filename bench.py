@@ -167,11 +167,14 @@ def device_observations(n, T, dev, seed):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_rate(d, T, sample_series, seed=0, nthreads=0):
+def cpu_port_rate(d, T, sample_series, seed=0, nthreads=None):
     """state-steps/s of the C oracle port (oracle/ssm_oracle.c, OpenMP over series) on host cores."""
     from oracle import c_oracle
     from physs_gp_b200 import sdes
     c_oracle.build()
+    if nthreads is None:
+        # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+        nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     nblk = d // 4
     rng = np.random.default_rng(seed)
     ls, steps = make_hypers(sample_series, nblk, seed)

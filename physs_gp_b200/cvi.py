@@ -301,3 +301,82 @@ class VGP:
 
     def get_objective(self):
         return -self.elbo()
+
+
+class MeanFieldConjugateGaussian:
+    """q(u) = prod_q q_q(u_q): one conjugate-Gaussian factor -- i.e. one surrogate SDE_GP -- per latent
+    (approximate_posteriors/conjugate_gaussian_approximate_posterior.py:127-172).  The reference runs the
+    Q surrogates under batch_or_loop (cvi_nat_grad_utils.py:111-119); here they are Q FullConjugateGaussian
+    objects whose filter / smoother calls are independent batched launches."""
+
+    def __init__(self, approx_posteriors):
+        self.approx_posteriors = list(approx_posteriors)
+        self.block_sizes = [q.block_size for q in self.approx_posteriors]
+        self.block_size = sum(self.block_sizes)
+
+
+class MeanFieldVGP:
+    """VGP with a mean-field CVI posterior (models/vgp.py with MeanFieldConjugateGaussian):
+    natural_gradients mean-field variant cvi_nat_grad.py:89-145 and elbo elbos.py:136-160.
+
+    The likelihood sees the stacked latent block u = (u_1, ..., u_Q) through W [P, sum D_q]; under the
+    mean-field posterior its covariance is block diagonal, the ELL gradients are evaluated on the stacked
+    marginal by the same kernel as the full posterior, and each factor is updated with its own diagonal
+    block of dELL/dS (cvi_nat_grad.py:103-139)."""
+
+    def __init__(self, Y, likelihood, approximate_posterior, W=None, ell_quad_points=20):
+        self.q = approximate_posterior
+        q0 = self.q.approx_posteriors[0]
+        dev = q0.Y_tilde.device
+        Y = torch.as_tensor(Y, dtype=torch.float64).to(dev)
+        self.Y = Y[None] if Y.dim() == 2 else Y
+        self.lik = likelihood
+        self.W = None if W is None else torch.as_tensor(W, dtype=torch.float64).to(dev)
+        self.K = ell_quad_points
+
+    def _stacked_marginal(self, want_lml=False):
+        mus, covs, lmls = [], [], []
+        for q in self.q.approx_posteriors:
+            lml, mu, var = q.surrogate.posterior_blocks(return_lml=True)
+            mus.append(mu[..., 0].contiguous())
+            covs.append(var[..., 0, :, :].contiguous())
+            lmls.append(lml)
+        m = torch.cat(mus, dim=-1)
+        D = m.shape[-1]
+        S = torch.zeros(m.shape + (D,), dtype=torch.float64, device=m.device)
+        o = 0
+        for c in covs:
+            k = c.shape[-1]
+            S[..., o:o + k, o:o + k] = c
+            o += k
+        return (m, S, mus, covs, lmls) if want_lml else (m, S, mus, covs)
+
+    def natural_gradient_update(self, lr, enforce_psd_type=None, prediction_samples=None):
+        if enforce_psd_type is not None:
+            raise NotImplementedError("enforce_psd_type is not implemented for the mean-field posterior")
+        m, S, mus, covs = self._stacked_marginal()
+        _, dm, dS = expected_log_likelihood(m, S, self.Y, self.W, self.lik, K=self.K, want_grads=True)
+        o = 0
+        for q, mu_q, cov_q in zip(self.q.approx_posteriors, mus, covs):
+            k = q.block_size
+            dm_q = dm[..., o:o + k].contiguous()
+            dS_q = dS[..., o:o + k, o:o + k].contiguous()
+            Yt, Vt = q.Y_tilde.contiguous(), q.V_tilde.contiguous()
+            Yn, Vn = natgrad_step(Yt, Vt, mu_q, cov_q, None, None, None, lr, dm=dm_q, dS=dS_q)
+            q.Y_tilde.copy_(Yn)
+            q.V_tilde.copy_(Vn)
+            o += k
+
+    def elbo(self):
+        m, S, mus, covs, lmls = self._stacked_marginal(want_lml=True)
+        ell = expected_log_likelihood(m, S, self.Y, self.W, self.lik, K=self.K).sum(dim=-1)
+        out = ell
+        for q, mu_q, cov_q, lml in zip(self.q.approx_posteriors, mus, covs, lmls):
+            sur = GaussianLik(np.eye(q.block_size))
+            ell_s = expected_log_likelihood(mu_q, cov_q, q.Y_tilde.contiguous(), None, sur,
+                                            noise=q.V_tilde.contiguous())
+            out = out - ell_s.sum(dim=-1) + lml           # - KL_q = -(ELL_sur,q - lml_q)   (elbos.py:74-90)
+        return out
+
+    def get_objective(self):
+        return -self.elbo()

@@ -233,3 +233,48 @@ def test_pendulum_cvi_iterations_match_oracle_and_fit(cuda_device):
     assert elbos[-1] > elbos[0]
     mu, _ = q.surrogate.posterior_blocks()
     assert float(np.abs(mu[0, :, 0, 0].cpu().numpy() - xs).max()) < 0.3
+
+
+def test_mean_field_cvi_matches_oracle(cuda_device):
+    """MeanFieldConjugateGaussian (cvi_nat_grad.py:89-145, elbos.py:136-160): two latents (Matern-3/2 and
+    Matern-5/2), Poisson counts driven by f_1 + f_2; three iterations and the ELBO against the numpy oracle."""
+    from physs_gp_b200 import cvi, sdes
+    rng = np.random.default_rng(12)
+    B, T = 2, 70
+    t = synth.time_grid(T, 0.1, rng)
+    pri = [sdes.BatchedMaternSDE(2, np.full((B, 1), 0.8), np.full((B, 1), 1.1)),
+           sdes.BatchedMaternSDE(3, np.full((B, 1), 0.5), np.full((B, 1), 0.7))]
+    qs = [cvi.FullConjugateGaussian(t, p, 1, B=B) for p in pri]
+    Y = rng.integers(0, 6, size=(B, T, 1)).astype(float)
+    Y[rng.uniform(size=Y.shape) < 0.1] = np.nan
+    W = np.array([[1.0, 1.0]])
+    model = cvi.MeanFieldVGP(Y, cvi.PoissonLik(1.0), cvi.MeanFieldConjugateGaussian(qs), W=W, ell_quad_points=20)
+    beta = 0.4
+    for _ in range(3):
+        model.natural_gradient_update(beta)
+    elbo = model.elbo()
+    torch.cuda.synchronize()
+    ops_ = [osde.LTI_SDE([osde.Matern32(0.8, 1.1)]), osde.LTI_SDE([osde.Matern52(0.5, 0.7)])]
+    for b in range(B):
+        Yt = [1e-5 * np.ones((T, 1)) for _ in range(2)]
+        Vt = [np.tile(np.eye(1), [T, 1, 1]) for _ in range(2)]
+
+        def marg():
+            out = [ofilters.filter_and_smooth(ops_[q], t, Yt[q], Vt[q]) for q in range(2)]
+            m = np.concatenate([o[1][:, :, 0] for o in out], -1)           # [T, 2]
+            S = np.zeros((T, 2, 2))
+            S[:, 0, 0], S[:, 1, 1] = out[0][2][:, 0, 0], out[1][2][:, 0, 0]
+            return out, m, S
+        for _ in range(3):
+            out, m, S = marg()
+            g = [_oracle_grads("poisson", Y[b, i], W, None, m[i], S[i], 1.0, 20) for i in range(T)]
+            for q in range(2):
+                dm = np.array([x[1][q] for x in g])[:, None]
+                dS = np.array([x[2][q, q] for x in g])[:, None, None]
+                Yt[q], Vt[q] = ocvi.cvi_step(Yt[q], Vt[q], m[:, q:q + 1], S[:, q:q + 1, q:q + 1], dm, dS, beta)
+        out, m, S = marg()
+        ref = sum(_oracle_grads("poisson", Y[b, i], W, None, m[i], S[i], 1.0, 20)[0] for i in range(T))
+        for q in range(2):
+            ref += -ocvi.surrogate_ell(Yt[q], Vt[q], m[:, q:q + 1], S[:, q:q + 1, q:q + 1]) + out[q][0]
+            assert rel(qs[q].Y_tilde[b], Yt[q]) < TOL and rel(qs[q].V_tilde[b], Vt[q]) < TOL
+        assert abs(float(elbo[b]) - ref) < TOL * abs(ref)
