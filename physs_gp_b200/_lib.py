@@ -68,7 +68,20 @@ SIGNATURES = {
 
 LIK_GAUSS, LIK_POISSON_EXP, LIK_BERNOULLI_PROBIT, LIK_GIVEN = 0, 1, 2, 3
 
+BIG_LIB_PATH = os.path.join(_HERE, "libphyss_b200_big.so")
+_c_i32p = ctypes.POINTER(ctypes.c_int32)
+# include/physs_b200_big.h
+BIG_SIGNATURES = {
+    "physs_big_last_error": (ctypes.c_char_p, []),
+    "physs_big_workspace_bytes": (_c_i64, [_c_i32, _c_i32]),
+    "physs_kf_filter_big_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _c_i32, _ptr, _ptr, _c_i32p, _ptr, _ptr, _ptr,
+                                               _ptr, _ptr, _c_i64, _c_f64, _ptr, _c_i64, _ptr, _ptr, _ptr]),
+    "physs_rts_smooth_big_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _ptr, _ptr, _c_i32p, _ptr, _ptr, _ptr, _c_i32,
+                                                _c_f64, _ptr, _c_i64, _ptr, _ptr]),
+}
+
 _lib = None
+_big = None
 
 
 class PhyssError(RuntimeError):
@@ -99,4 +112,28 @@ def load():
 def check(status, what):
     if status != PHYSS_OK:
         msg = load().physs_last_error()
+        raise PhyssError("%s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))
+
+
+def load_big():
+    """Load libphyss_b200_big.so (large-block path; depends on cuBLAS / cuSOLVER).  Raises if missing."""
+    global _big
+    if _big is not None:
+        return _big
+    if not os.path.exists(BIG_LIB_PATH):
+        raise ImportError(
+            "physs_gp_b200: %s not found -- run `python -m physs_gp_b200.build`. There is no CPU fallback."
+            % BIG_LIB_PATH)
+    lib = ctypes.CDLL(BIG_LIB_PATH)
+    for name, (res, args) in BIG_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _big = lib
+    return lib
+
+
+def check_big(status, what):
+    if status != 0:
+        msg = load_big().physs_big_last_error()
         raise PhyssError("%s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))

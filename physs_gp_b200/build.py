@@ -17,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libphyss_b200.so")
+LIB_BIG = os.path.join(HERE, "libphyss_b200_big.so")     # large-block path: links cuBLAS + cuSOLVER
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -87,7 +88,26 @@ def build_library(force=False, jobs=None, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    build_big(force=force)
     return LIB, logs
+
+
+def build_big(force=False):
+    """libphyss_b200_big.so from csrc/big/physs_big.cu (one translation unit, -lcublas -lcusolver)."""
+    src = os.path.join(CSRC, "big", "physs_big.cu")
+    hdr = os.path.join(INCLUDE, "physs_b200_big.h")
+    stamp = LIB_BIG + ".stamp"
+    with open(src, "rb") as f, open(hdr, "rb") as g:
+        digest = hashlib.sha256(f.read() + g.read() + " ".join(NVCC_FLAGS).encode()).hexdigest()
+    if (not force and os.path.exists(LIB_BIG) and os.path.exists(stamp) and open(stamp).read() == digest):
+        return LIB_BIG
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", src, "-o", LIB_BIG, "-lcublas", "-lcusolver"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return LIB_BIG
 
 
 def main():

@@ -73,6 +73,26 @@ def lower_prior(prior, X_s, dts, dev):
     return discs, m0, P0, H
 
 
+def lower_prior_big(prior, X_s, dt, dev):
+    """Large-block route (d > settings.big_block_min_dim, one series): prior.expm / prior.Q are evaluated once
+    per DISTINCT step size on the host (the reference API) and shipped as [nA, d, d] with a host index."""
+    P_inf = np.asarray(prior.P_inf(None, X_s, None), np.float64)
+    m_inf = np.asarray(prior.m_inf(None, X_s, None), np.float64).reshape(-1)
+    H = np.asarray(prior.H(None, X_s, None), np.float64)
+    dt_np = _np(dt).reshape(-1)
+    uniq, inv = np.unique(dt_np, return_inverse=True)
+    A_u = np.stack([np.asarray(prior.expm(X_s, float(u)), np.float64) for u in uniq])
+    Q_u = np.stack([np.asarray(prior.Q(float(u), A_u[i], P_inf, X_s), np.float64) for i, u in enumerate(uniq)])
+    return ops.BigDisc(_to_dev(A_u, dev), _to_dev(Q_u, dev), inv), _to_dev(m_inf, dev), _to_dev(P_inf, dev), H
+
+
+def _use_big(prior, X_s, batched_B):
+    if isinstance(prior, BatchedMaternSDE) or batched_B != 1:
+        return False
+    d = np.asarray(prior.P_inf(None, X_s, None)).shape[0]
+    return d > settings.big_block_min_dim
+
+
 def _is_identity(H):
     return H.shape[0] == H.shape[1] and np.array_equal(H, np.eye(H.shape[0]))
 
@@ -88,6 +108,19 @@ def _filter_impl(parallel, data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, 
         raise NotImplementedError("sequential filter with a precision likelihood is not supported")
     dev = _device()
     Yd = _to_dev(Y, dev)
+    one = Yd.dim() == 3 or (Yd.dim() == 4 and Yd.shape[0] == 1)
+    if one and _use_big(prior, X_s, 1):
+        # one series with a large state (BASELINE config 2): cuBLAS / cuSOLVER-backed path
+        disc, m0, P0, H = lower_prior_big(prior, X_s, _to_dev(dt, dev), dev)
+        R = _to_dev(lik_mat, dev)
+        lead = Yd.dim() == 4
+        if lead:
+            Yd = Yd[0]
+            R = R[0] if R.dim() == 4 else R
+        lml, mf, Pf = ops.kf_filter_big(Yd[..., 0], R, _to_dev(H, dev), m0, P0, disc, jitter=settings.jitter)
+        if lead:
+            return lml[None], {'m': mf[None, ..., None], 'P': Pf[None]}
+        return lml, {'m': mf[..., None], 'P': Pf}
     batched = Yd.dim() == 4 or isinstance(prior, BatchedMaternSDE)
     if Yd.dim() == 3:
         Yd = Yd[None]
@@ -146,6 +179,16 @@ def _smoother_impl(parallel, data, model, filter_res, dt, X_t, X_s, full_state):
     dev = _device()
     mf = _to_dev(filter_res['m'], dev)[..., 0]
     Pf = _to_dev(filter_res['P'], dev)
+    one = mf.dim() == 2 or (mf.dim() == 3 and mf.shape[0] == 1)
+    if one and _use_big(model, X_s, 1):
+        disc, _, _, H = lower_prior_big(model, X_s, _to_dev(dt, dev), dev)
+        Hout = None if (full_state or _is_identity(H)) else _to_dev(H, dev)
+        lead = mf.dim() == 3
+        ms, Ps = ops.rts_smooth_big(mf[0] if lead else mf, Pf[0] if lead else Pf, disc, Hout=Hout,
+                                    jitter=settings.jitter)
+        if lead:
+            return ms[None, ..., None], Ps[None]
+        return ms[..., None], Ps
     batched = mf.dim() == 3
     if not batched:
         mf, Pf = mf[None], Pf[None]

@@ -395,3 +395,70 @@ def fp64_peak_tflops(dev=None, iters=20000):
             torch.cuda.synchronize()
             best = max(best, blocks * 256 * iters * 16 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     return best
+
+
+# ------------------------------------------------------------------------------------- large blocks
+class BigDisc:
+    """Discretisation of the large-block path: A, Q [nA, d, d] device tensors, one pair per DISTINCT step
+    size, and a host int32 index [T] selecting the pair of every step."""
+
+    def __init__(self, A, Q, index):
+        import numpy as np
+        self.A, self.Q = _dev(A, "A").contiguous(), _dev(Q, "Q").contiguous()
+        self.index = np.ascontiguousarray(index, dtype=np.int32)
+
+
+def _big_ws(d, m, dev):
+    n = _lib.load_big().physs_big_workspace_bytes(d, m)
+    if n <= 0:
+        raise _lib.PhyssError("physs_big_workspace_bytes failed (cuSOLVER handle?)")
+    return torch.empty((n // 8 + 2,), dtype=torch.float64, device=dev)
+
+
+def kf_filter_big(Y, R, H, m0, P0, disc, jitter=None, stream=None):
+    """One series, large state: Y [T, m], R [T|1, m, m], H [m, d], m0 [d], P0 [d, d] -> (lml [], mf, Pf)."""
+    import ctypes
+    lib = _lib.load_big()
+    Y, H, m0, P0 = (_dev(x, n).contiguous() for x, n in ((Y, "Y"), (H, "H"), (m0, "m0"), (P0, "P0")))
+    R = _dev(R, "R").contiguous()
+    T, m = Y.shape
+    d = P0.shape[-1]
+    R_ts = m * m if (R.dim() == 3 and R.shape[0] > 1) else 0
+    dev = Y.device
+    mf = torch.empty((T, d), dtype=torch.float64, device=dev)
+    Pf = torch.empty((T, d, d), dtype=torch.float64, device=dev)
+    lml = torch.empty((1,), dtype=torch.float64, device=dev)
+    ws = _big_ws(d, m, dev)
+    jit = settings.jitter if jitter is None else jitter
+    idx = disc.index.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    with torch.cuda.device(dev):
+        st = lib.physs_kf_filter_big_f64(_stream_ptr(stream), T, d, m, disc.A.data_ptr(), disc.Q.data_ptr(), idx,
+                                         m0.data_ptr(), P0.data_ptr(), H.data_ptr(), Y.data_ptr(), R.data_ptr(),
+                                         R_ts, float(jit), ws.data_ptr(), ws.numel() * 8, mf.data_ptr(),
+                                         Pf.data_ptr(), lml.data_ptr())
+    _lib.check_big(st, "physs_kf_filter_big_f64")
+    return lml[0], mf, Pf
+
+
+def rts_smooth_big(mf, Pf, disc, Hout=None, jitter=None, stream=None):
+    import ctypes
+    lib = _lib.load_big()
+    mf, Pf = _dev(mf, "mf").contiguous(), _dev(Pf, "Pf").contiguous()
+    T, d = mf.shape
+    dev = mf.device
+    if Hout is None:
+        mo, Hp, mp = 0, None, d
+    else:
+        Hout = _dev(Hout, "Hout").contiguous()
+        mo, Hp, mp = Hout.shape[0], Hout.data_ptr(), Hout.shape[0]
+    ms = torch.empty((T, mp), dtype=torch.float64, device=dev)
+    Ps = torch.empty((T, mp, mp), dtype=torch.float64, device=dev)
+    ws = _big_ws(d, d, dev)
+    jit = settings.jitter if jitter is None else jitter
+    idx = disc.index.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    with torch.cuda.device(dev):
+        st = lib.physs_rts_smooth_big_f64(_stream_ptr(stream), T, d, disc.A.data_ptr(), disc.Q.data_ptr(), idx,
+                                          mf.data_ptr(), Pf.data_ptr(), Hp, mo, float(jit), ws.data_ptr(),
+                                          ws.numel() * 8, ms.data_ptr(), Ps.data_ptr())
+    _lib.check_big(st, "physs_rts_smooth_big_f64")
+    return ms, Ps

@@ -23,3 +23,7 @@ pscan_polish = None
 # filter_type='b200_auto': parallel in time below this batch size and above this series length
 auto_parallel_max_batch = 8192
 auto_parallel_min_steps = 1024
+
+# single series with state dim above this go to the large-block path (libphyss_b200_big.so: cuBLAS / cuSOLVER
+# per step); at or below it the shared-memory lane-group kernels are used
+big_block_min_dim = 32
