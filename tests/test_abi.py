@@ -10,8 +10,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "physs_b200.h")
 
 
-def _declared_symbols():
-    src = open(HEADER).read()
+HEADER_BIG = os.path.join(ROOT, "include", "physs_b200_big.h")
+
+
+def _declared_symbols(header=HEADER):
+    src = open(header).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(physs_[a-z0-9_]+)\s*\(", src)))
 
@@ -28,6 +31,24 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for s in _declared_symbols():
         assert hasattr(lib, s), "libphyss_b200.so does not export %s" % s
+
+
+def test_big_block_library_exports_every_declared_symbol():
+    """libphyss_b200_big.so (cuBLAS / cuSOLVER-backed large-block path) against include/physs_b200_big.h."""
+    from physs_gp_b200 import _lib
+    from physs_gp_b200.build import build_big
+    build_big()
+    lib = ctypes.CDLL(_lib.BIG_LIB_PATH)
+    syms = _declared_symbols(HEADER_BIG)
+    assert "physs_kf_filter_big_f64" in syms and "physs_rts_smooth_big_f64" in syms
+    for s in syms:
+        assert hasattr(lib, s), "libphyss_b200_big.so does not export %s" % s
+    assert sorted(_lib.BIG_SIGNATURES) == syms
+    # bad sizes are rejected before any CUDA / library call
+    big = _lib.load_big()
+    st = big.physs_kf_filter_big_f64(None, 0, 4, 2, None, None, None, None, None, None, None, None, 0, 1e-5, None, 0,
+                                     None, None, None)
+    assert st == 1 and b"bad sizes" in big.physs_big_last_error()
 
 
 def test_binding_table_covers_header():
