@@ -154,6 +154,33 @@ int physs_pscan_filter_f64(void* stream, int64_t B, int64_t T, int64_t step_bstr
                            int64_t chunk_len, int32_t polish, double delta, int32_t patience, void* ws,
                            double* mf, double* Pf, double* lml, double* lml_k, int32_t* status);
 
+/* Speculative parallel-in-time variants (no reference counterpart; an optimisation of the above for priors
+ * whose filter forgets its initial state within `warm` <= chunk_len steps, e.g. every stationary Matern
+ * model): no summaries and no scan -- chunk c > 0 of the filter starts `warm` steps early from (m0, P0),
+ * chunk c of the smoother `warm` steps late from the filtered state there, and the same fix-up passes
+ * (polish >= 1) both VERIFY each chunk against a restart from its neighbour's replayed state and repair it.
+ * *status = 1 means some chunk still disagreed in the last pass: rerun with the exact scan entry points.
+ * The smoother variant needs full-state output (Hout = NULL). */
+int physs_pscan_filter_spec_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                                int32_t d, int32_t m, int32_t disc_mode, int32_t nblk,
+                                const double* A, int64_t A_bstride, const double* Q, int64_t Q_bstride,
+                                const double* lam, int64_t lam_bstride, const double* dt, int64_t dt_bstride,
+                                const double* Pinf, int64_t Pinf_bstride, const double* m0, int64_t m0_bstride,
+                                const double* P0, int64_t P0_bstride, const double* H, int64_t H_bstride,
+                                const double* Y, const double* R, int64_t R_bstride, int64_t R_tstride,
+                                double jitter,
+                                int64_t chunk_len, int64_t warm, int32_t polish, double delta, int32_t patience,
+                                void* ws, double* mf, double* Pf, double* lml, double* lml_k, int32_t* status);
+
+int physs_pscan_smooth_spec_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                                int32_t d, int32_t disc_mode, int32_t nblk,
+                                const double* A, int64_t A_bstride, const double* Q, int64_t Q_bstride,
+                                const double* lam, int64_t lam_bstride, const double* dt, int64_t dt_bstride,
+                                const double* Pinf, int64_t Pinf_bstride,
+                                const double* mf, const double* Pf, const double* Hout, int32_t mo, double jitter,
+                                int64_t chunk_len, int64_t warm, int32_t polish, double delta, int32_t patience,
+                                void* ws, double* ms, double* Ps, int32_t* status);
+
 int physs_pscan_filter_local_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
                                  int32_t d, int32_t m, int32_t disc_mode, int32_t nblk,
                                  const double* A, int64_t A_bstride, const double* Q, int64_t Q_bstride,

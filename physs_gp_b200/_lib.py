@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libphyss_b200.so")
 PHYSS_OK = 0
 DISC_GIVEN = 0
 DISC_MATERN = 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _c_i32 = ctypes.c_int32
 _c_i64 = ctypes.c_int64
@@ -46,6 +46,10 @@ SIGNATURES = {
     "physs_pscan_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i32, _c_i64]),
     "physs_pscan_filter_f64": (ctypes.c_int, _FILTER_HEAD + [_c_i64, _c_i32, _c_f64, _c_i32, _ptr,
                                                             _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "physs_pscan_filter_spec_f64": (ctypes.c_int, _FILTER_HEAD + [_c_i64, _c_i64, _c_i32, _c_f64, _c_i32, _ptr,
+                                                                 _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "physs_pscan_smooth_spec_f64": (ctypes.c_int, _SMOOTH_HEAD + [_c_i64, _c_i64, _c_i32, _c_f64, _c_i32, _ptr,
+                                                                 _ptr, _ptr, _ptr]),
     "physs_pscan_filter_local_f64": (ctypes.c_int, _FILTER_HEAD + [_c_i64, _ptr, _ptr]),
     "physs_pscan_filter_finish_f64": (ctypes.c_int, _FILTER_HEAD + [_c_i64, _c_i32, _c_f64, _c_i32, _ptr, _ptr, _ptr,
                                                                    _ptr, _ptr, _ptr, _ptr, _ptr]),

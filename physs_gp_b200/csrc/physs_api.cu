@@ -74,7 +74,7 @@ static inline bool step_strides_ok(int64_t B, int64_t T, int64_t bs, int64_t ts)
 
 extern "C" {
 
-int physs_abi_version(void) { return 3; }
+int physs_abi_version(void) { return 4; }
 
 const char* physs_last_error(void) { return g_err; }
 
@@ -203,6 +203,28 @@ int physs_pscan_filter_f64(FILTER_PARAMS, int64_t chunk_len, int32_t polish, dou
   if (rc) return rc;
   return pscan_filter_finish((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a, chunk_len, (double*)ws,
                              false, nullptr, nullptr, polish, delta, patience, status);
+}
+
+int physs_pscan_filter_spec_f64(FILTER_PARAMS, int64_t chunk_len, int64_t warm, int32_t polish, double delta,
+                                int32_t patience, void* ws, double* mf, double* Pf, double* lml, double* lml_k,
+                                int32_t* status) {
+  SeqFilterArgs a;
+  int rc = pack_filter(FILTER_ARGS, mf, Pf, lml, lml_k, a);
+  if (rc || B == 0) return rc;
+  if ((rc = check_chunk(T, chunk_len, ws))) return rc;
+  return pscan_filter_spec((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a, chunk_len, warm, polish,
+                           delta, patience, (double*)ws, status);
+}
+
+int physs_pscan_smooth_spec_f64(SMOOTH_PARAMS, int64_t chunk_len, int64_t warm, int32_t polish, double delta,
+                                int32_t patience, void* ws, double* ms, double* Ps, int32_t* status) {
+  SeqSmoothArgs a;
+  int rc = pack_smooth(SMOOTH_ARGS, ms, Ps, a);
+  if (rc || B == 0) return rc;
+  if (!ms || !Ps) return set_error(PHYSS_ERR_BAD_ARG, "smoother: null output pointer");
+  if ((rc = check_chunk(T, chunk_len, ws))) return rc;
+  return pscan_smooth_spec((cudaStream_t)stream, d, Hout ? mo : 0, disc_mode, nblk, a, chunk_len, warm, polish,
+                           delta, patience, (double*)ws, status);
 }
 
 int physs_pscan_filter_local_f64(FILTER_PARAMS, int64_t chunk_len, void* ws, double* total) {

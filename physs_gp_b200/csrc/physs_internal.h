@@ -36,6 +36,7 @@ struct SeqFilterArgs {
   // series in total (boundary snapshots are indexed b * nchunk + c); nchunk == 0 means plain mode.
   int64_t nchunk, chunk_len, chunk_first, chunk_count;
   int from_bnd;          // chunk starts from the boundary snapshot (bnd_m, bnd_P)[v] instead of (m0, P0)
+  int64_t warm;          // speculative mode (from_bnd == 0): chunk c > 0 starts `warm` steps early from (m0, P0)
   int fixup, patience;
   double delta;
   const double* bnd_m; const double* bnd_P;
@@ -62,6 +63,7 @@ struct SeqSmoothArgs {
   // series in total (boundary snapshots are indexed b * nchunk + c); nchunk == 0 means plain mode.
   int64_t nchunk, chunk_len, chunk_first, chunk_count;
   int carry_last;        // the last chunk also starts from its boundary snapshot (time-sharded ranges)
+  int64_t warm;          // speculative mode (> 0): chunk starts `warm` steps late from the FILTERED state there
   int fixup, patience;
   double delta;
   const double* bnd_m; const double* bnd_P;
@@ -125,6 +127,11 @@ int pscan_smooth_local(cudaStream_t st, int d, int disc_mode, int nblk, SeqSmoot
                        double* ws, double* total_out);
 int pscan_smooth_finish(cudaStream_t st, int d, int mo, int disc_mode, int nblk, SeqSmoothArgs a, int64_t chunk_len,
                         double* ws, const double* start_m, const double* start_P);
+int pscan_filter_spec(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, SeqFilterArgs a,
+                      int64_t chunk_len, int64_t warm, int polish, double delta, int patience, double* ws,
+                      int* status_out);
+int pscan_smooth_spec(cudaStream_t st, int d, int mo, int disc_mode, int nblk, SeqSmoothArgs a, int64_t chunk_len,
+                      int64_t warm, int polish, double delta, int patience, double* ws, int* status_out);
 int pscan_smooth_fold(cudaStream_t st, int d, int64_t B, int64_t K, const double* totals, const double* m0,
                       const double* P0, double* m_out, double* P_out);
 

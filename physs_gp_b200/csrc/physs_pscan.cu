@@ -781,6 +781,23 @@ __global__ void ps_gather_bnd_kernel(const double* __restrict__ mf, const double
   }
 }
 
+// smoother polish: boundary of chunk c (c < nchunk - 1) <- replayed smoothed state at the first step of chunk c + 1
+__global__ void ps_gather_bnd_next_kernel(const double* __restrict__ ms, const double* __restrict__ Ps, int64_t B,
+                                          int64_t nchunk, int64_t chunk_len, int64_t sbs, int64_t sts, int d,
+                                          double* __restrict__ bnd_m, double* __restrict__ bnd_P) {
+  const int64_t n = B * nchunk * (int64_t)(d * d + d);
+  const int per = d * d + d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = i / per;
+    const int e = (int)(i - v * per);
+    const int64_t b = v / nchunk, c = v % nchunk;
+    if (c == nchunk - 1) continue;
+    const int64_t row = b * sbs + ((c + 1) * chunk_len) * sts;
+    if (e < d) bnd_m[v * d + e] = ms[row * d + e];
+    else bnd_P[v * d * d + (e - d)] = Ps[row * d * d + (e - d)];
+  }
+}
+
 // lml[b] = sum_k lml_k[b, k], two deterministic stages: one 256-thread block per (series, segment of
 // `seg` steps) -> partial[b, s]; then one warp per series over the partials.
 __global__ void __launch_bounds__(256) ps_lml_partial_kernel(const double* __restrict__ lml_k, int64_t T, int64_t sbs,
@@ -1070,6 +1087,131 @@ int pscan_filter_finish(cudaStream_t st, int d, int m, int disc_mode, int nblk, 
   if (status_out) {
     e = cudaMemcpyAsync(status_out, w.flag, sizeof(int), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return cuda_status(e, "pscan filter: status copy");
+  }
+  return PHYSS_OK;
+}
+
+// ---------------------------------------------------------------------------------- speculative mode
+// No scan: every chunk c > 0 starts `warm` steps early from the initial state (m0, P0) -- for the reference's
+// filters the stationary prior -- and discards those steps: the filter forgets its start at the rate the
+// polish passes rely on anyway.  The same fix-up passes then (i) verify every chunk against a restart from
+// the previous chunk's end state and (ii) repair it where the warm-up was too short; *status reports chunks
+// that still disagreed in the last pass.  Costs (1 + warm / chunk_len) replays instead of summary + scan +
+// replay; the caller falls back to the exact scan when the flag is raised.
+int pscan_filter_spec(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, SeqFilterArgs a,
+                      int64_t chunk_len, int64_t warm, int polish, double delta, int patience, double* ws,
+                      int* status_out) {
+  int rc = check_matern(d, disc_mode, nblk);
+  if (rc) return rc;
+  if (d > 32) return set_error(PHYSS_ERR_UNSUPPORTED, "pscan speculative mode: d <= 32 only");
+  if (warm < 1 || warm > chunk_len) return set_error(PHYSS_ERR_BAD_ARG, "pscan speculative mode: need 1 <= warm <= chunk_len");
+  if (polish < 1) polish = 1;                               // at least the verification pass
+  const int64_t nchunk = ps_nchunk(a.T, chunk_len);
+  PsWorkspace w = ps_carve(ws, a.B, a.T, d, chunk_len);
+  cudaError_t e = cudaMemsetAsync(w.flag, 0, 2 * sizeof(double), st);
+  if (e != cudaSuccess) return cuda_status(e, "pscan filter: flag reset");
+  if (!a.lml_k) a.lml_k = w.lml_k;
+  a.nchunk = nchunk; a.chunk_len = chunk_len;
+  a.bnd_m = w.bnd_m; a.bnd_P = w.bnd_P; a.unconverged = w.flag;
+  a.from_bnd = 0; a.fixup = 0; a.warm = warm; a.delta = delta; a.patience = patience;
+  const int64_t nfull = a.T / chunk_len;
+  auto replay = [&](int64_t first, int64_t count) -> int {
+    if (count <= 0) return PHYSS_OK;
+    SeqFilterArgs r = a;
+    r.chunk_first = first; r.chunk_count = count;
+    return run_filter_any(st, d, m, disc_mode, nblk, hid, r);
+  };
+  // chunk 0 has no warm-up, chunks >= 1 all have exactly `warm` (<= chunk_len) steps of it: separate launches
+  // keep the trip count uniform inside every warp
+  rc = replay(0, nfull > 0 ? 1 : 0);
+  if (rc) return rc;
+  rc = replay(1, nfull - 1);
+  if (rc) return rc;
+  rc = replay(nfull, nchunk - nfull);
+  if (rc) return rc;
+  a.warm = 0; a.from_bnd = 1;
+  for (int it = 0; it < polish && nchunk > 1; ++it) {
+    const int64_t total = a.B * nchunk * (int64_t)(d * d + d);
+    const int64_t want = (total + 255) / 256;
+    ps_gather_bnd_kernel<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, st>>>(a.mf, a.Pf, a.B, nchunk, chunk_len,
+                                                                                     a.sbs, a.sts, d, w.bnd_m, w.bnd_P);
+    rc = cuda_status(cudaGetLastError(), "ps_gather_bnd_kernel launch");
+    if (rc) return rc;
+    e = cudaMemsetAsync(w.flag, 0, sizeof(int), st);
+    if (e != cudaSuccess) return cuda_status(e, "pscan filter: flag reset");
+    a.fixup = 1;
+    rc = replay(1, nfull - 1);
+    if (rc) return rc;
+    if (nfull >= 1) { rc = replay(nfull, nchunk - nfull); if (rc) return rc; }
+    a.fixup = 0;
+  }
+  {
+    const int64_t seg = ps_lml_seg(a.T), nseg = ps_lml_nseg(a.T);
+    ps_lml_partial_kernel<<<dim3((unsigned)nseg, (unsigned)a.B), 256, 0, st>>>(a.lml_k, a.T, a.sbs, a.sts, seg, nseg,
+                                                                              w.lml_partial);
+    rc = cuda_status(cudaGetLastError(), "ps_lml_partial_kernel launch");
+    if (rc) return rc;
+    const int64_t threads = a.B * 32;
+    ps_lml_final_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(w.lml_partial, a.B, nseg, a.lml);
+    rc = cuda_status(cudaGetLastError(), "ps_lml_final_kernel launch");
+    if (rc) return rc;
+  }
+  if (status_out) {
+    e = cudaMemcpyAsync(status_out, w.flag, sizeof(int), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_status(e, "pscan filter: status copy");
+  }
+  return PHYSS_OK;
+}
+
+// Smoother counterpart: chunk c starts `warm` steps past its end from the filtered state there; full-state
+// output only (the fix-up passes compare and carry the full smoothed state).
+int pscan_smooth_spec(cudaStream_t st, int d, int mo, int disc_mode, int nblk, SeqSmoothArgs a, int64_t chunk_len,
+                      int64_t warm, int polish, double delta, int patience, double* ws, int* status_out) {
+  int rc = check_matern(d, disc_mode, nblk);
+  if (rc) return rc;
+  if (d > 32) return set_error(PHYSS_ERR_UNSUPPORTED, "pscan speculative mode: d <= 32 only");
+  if (mo != 0) return set_error(PHYSS_ERR_UNSUPPORTED, "pscan speculative smoother: full_state output only");
+  if (warm < 1 || warm > chunk_len) return set_error(PHYSS_ERR_BAD_ARG, "pscan speculative mode: need 1 <= warm <= chunk_len");
+  if (polish < 1) polish = 1;
+  const int64_t nchunk = ps_nchunk(a.T, chunk_len);
+  PsWorkspace w = ps_carve(ws, a.B, a.T, d, chunk_len);
+  cudaError_t e = cudaMemsetAsync(w.flag, 0, 2 * sizeof(double), st);
+  if (e != cudaSuccess) return cuda_status(e, "pscan smoother: flag reset");
+  a.nchunk = nchunk; a.chunk_len = chunk_len;
+  a.bnd_m = w.bnd_m; a.bnd_P = w.bnd_P; a.unconverged = w.flag;
+  a.carry_last = 0; a.fixup = 0; a.warm = warm; a.delta = delta; a.patience = patience;
+  auto replay = [&](int64_t first, int64_t count) -> int {
+    if (count <= 0) return PHYSS_OK;
+    SeqSmoothArgs r = a;
+    r.chunk_first = first; r.chunk_count = count;
+    return run_smooth_any(st, d, 0, disc_mode, nblk, r);
+  };
+  // uniform warm-up inside a launch: chunks [0, nchunk - 2) have >= chunk_len >= warm steps after them, the last
+  // two chunks (shorter run-out / terminal condition) get their own launches
+  const int64_t nmain = nchunk >= 2 ? nchunk - 2 : 0;
+  rc = replay(0, nmain);
+  if (rc) return rc;
+  if (nchunk >= 2) { rc = replay(nchunk - 2, 1); if (rc) return rc; }
+  rc = replay(nchunk - 1, 1);
+  if (rc) return rc;
+  a.warm = 0;
+  for (int it = 0; it < polish && nchunk > 1; ++it) {
+    const int64_t total = a.B * nchunk * (int64_t)(d * d + d);
+    const int64_t want = (total + 255) / 256;
+    ps_gather_bnd_next_kernel<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, st>>>(
+        a.ms, a.Ps, a.B, nchunk, chunk_len, a.sbs, a.sts, d, w.bnd_m, w.bnd_P);
+    rc = cuda_status(cudaGetLastError(), "ps_gather_bnd_next_kernel launch");
+    if (rc) return rc;
+    e = cudaMemsetAsync(w.flag, 0, sizeof(int), st);
+    if (e != cudaSuccess) return cuda_status(e, "pscan smoother: flag reset");
+    a.fixup = 1;
+    rc = replay(0, nchunk - 1);                              // all full-length chunks before the last one
+    if (rc) return rc;
+    a.fixup = 0;
+  }
+  if (status_out) {
+    e = cudaMemcpyAsync(status_out, w.flag, sizeof(int), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_status(e, "pscan smoother: status copy");
   }
   return PHYSS_OK;
 }

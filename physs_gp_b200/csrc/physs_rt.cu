@@ -195,9 +195,13 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
   };
 
   LmlAcc acc;
-  stage(0);
-  double dt_n = dtp[0];
-  for (int64_t k = 0; k < T; ++k) {
+  // speculative chunk mode: start `warm` steps early from (m0, P0), discard those steps.  Groups of one warp
+  // may own different chunks, so every group runs the same number of warm-up steps (chunk 0 is never
+  // launched together with later chunks in this mode, see pscan_filter_spec)
+  const int64_t w0 = (chunked && !p.from_bnd && p.warm > 0) ? ((p.warm < t0) ? p.warm : t0) : 0;
+  stage(-w0);
+  double dt_n = dtp[-w0];
+  for (int64_t k = -w0; k < T; ++k) {
     const int st = (int)(k & 1);
     const double dt = dt_n;
     grp::cp_async_wait_all();
@@ -328,6 +332,7 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
     }
     if (!chunked) acc.add(det, mahal, nobs);
     __syncwarp();
+    if (k < 0) continue;                                     // warm-up step: nothing is stored
     // ---- outputs (fix-up: compare with what is stored before overwriting it)
     if (chunked && p.fixup) {          // warp-uniform: the comparison shuffles across the whole warp
       const bool ag = rt_agrees<G, DM>(mv_, P, d, mfp + k * sts * d, Pfp + k * sts * d * d, p.delta);
@@ -434,16 +439,20 @@ __global__ void rt_smooth_kernel(const SeqSmoothArgs p, const RtLayout L) {
     grp::cp_async_commit();
   };
 
-  const bool carried = chunked && (wk.c < p.nchunk - 1 || p.carry_last);
+  // speculative chunk mode: start w0 steps past the chunk's end from the filtered state there
+  const bool spec = chunked && p.warm > 0;
+  const int64_t after = p.T - (t0 + T);
+  const int64_t w0 = spec ? ((p.warm < after) ? p.warm : after) : 0;
+  const bool carried = chunked && !spec && (wk.c < p.nchunk - 1 || p.carry_last);
   if (carried) {
     g2s<G, DM>(Ps, p.bnd_P + vs * d * d, d, d);
     for (int i = gl; i < d; i += G) ms[i] = p.bnd_m[vs * d + i];
   } else {
-    g2s<G, DM>(Ps, Pfp + (T - 1) * sts * d * d, d, d);
-    for (int i = gl; i < d; i += G) ms[i] = mfp[(T - 1) * sts * d + i];
+    g2s<G, DM>(Ps, Pfp + (T - 1 + w0) * sts * d * d, d, d);
+    for (int i = gl; i < d; i += G) ms[i] = mfp[(T - 1 + w0) * sts * d + i];
   }
   __syncwarp();
-  int64_t kstart = T - 1;
+  int64_t kstart = (w0 > 0) ? T - 2 + w0 : T - 1;
   if (!chunked) {
     emit(T - 1);
     kstart = T - 2;
@@ -505,7 +514,7 @@ __global__ void rt_smooth_kernel(const SeqSmoothArgs p, const RtLayout L) {
       if (!done) streak = ag ? streak + 1 : 0;
     }
     __syncwarp();
-    emit(k);
+    if (k < T) emit(k);                                      // steps past the chunk's end are warm-up
     if (chunked && p.fixup) {
       if (streak >= p.patience) done = true;
       if (__all_sync(0xffffffffu, done || !active)) break;

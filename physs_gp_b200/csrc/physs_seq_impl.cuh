@@ -284,13 +284,16 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
   bool done = false;
 
   LmlAcc acc;
+  // speculative chunk mode: start `warm` steps before the chunk from (m0, P0) and discard those steps
+  // (uniform over the warp: its lanes share the chunk)
+  const int64_t w0 = (CHUNK && !p.from_bnd && p.warm > 0) ? ((p.warm < t0) ? p.warm : t0) : 0;
   // software prefetch of the next step's streamed inputs
   double y_n[M], R_n[M][M], dt_n;
-  load_vec<M>(Yp, y_n);
-  load_mat<M>(Rp, R_n);
-  dt_n = dtp[0];
+  load_vec<M>(Yp - w0 * sts * M, y_n);
+  load_mat<M>(Rp - w0 * p.R_ts, R_n);
+  dt_n = dtp[-w0];
 
-  for (int64_t k = 0; k < T; ++k) {
+  for (int64_t k = -w0; k < T; ++k) {
     double y[M], R[M][M];
     const double dt = dt_n;
 #pragma unroll
@@ -321,6 +324,7 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
     if (CHUNK && p.fixup && !done) {
       streak = agrees<D>(m, P, mfp + k * sts * D, Pfp + k * sts * D * D, p.delta) ? streak + 1 : 0;
     }
+    if (k < 0) continue;                                   // warm-up step: nothing is stored
     if (coal) {
       // converged lanes keep rewriting what is already stored to `delta`; the warp leaves together
       warp_store_rows<D>(mfw + k * sts * D, m, tile, lane, wk.nvalid);
@@ -460,17 +464,22 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_smooth_kernel(const 
   // plain mode: the last step is terminal (smoothed = filtered).  Chunk mode: every step of the chunk
   // is an RTS step from the carried state of the next chunk's first step; the very last chunk carries
   // its own last filtered state across dt = 0, which reproduces the terminal condition.
-  const bool carried = CHUNK && (wk.c < p.nchunk - 1 || p.carry_last);
+  // speculative chunk mode (warm > 0): no boundary is known; start `w0` steps past the chunk's end from the
+  // FILTERED state there (a terminal-like condition) and discard the steps outside the chunk
+  const bool spec = CHUNK && p.warm > 0;
+  const int64_t after = p.T - (t0 + T);
+  const int64_t w0 = spec ? ((p.warm < after) ? p.warm : after) : 0;
+  const bool carried = CHUNK && !spec && (wk.c < p.nchunk - 1 || p.carry_last);
   int64_t kstart;
-  if (CHUNK && carried) {
+  if (carried) {
     load_vec<D>(p.bnd_m + v * D, ms);
     load_mat<D>(p.bnd_P + v * D * D, Ps);
   } else {
-    load_vec<D>(mfp + (T - 1) * sts * D, ms);
-    load_mat<D>(Pfp + (T - 1) * sts * D * D, Ps);
+    load_vec<D>(mfp + (T - 1 + w0) * sts * D, ms);
+    load_mat<D>(Pfp + (T - 1 + w0) * sts * D * D, Ps);
   }
   if (CHUNK) {
-    kstart = T - 1;
+    kstart = (w0 > 0) ? T - 2 + w0 : T - 1;
   } else {
     emit(T - 1, ms, Ps);
     kstart = T - 2;
@@ -505,7 +514,7 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_smooth_kernel(const 
         streak = agrees<D>(ms, Ps, msp + k * sts * D, Psp + k * sts * D * D, p.delta) ? streak + 1 : 0;
       }
     }
-    emit(k, ms, Ps);
+    if (k < T) emit(k, ms, Ps);                             // steps past the chunk's end are warm-up
     if (CHUNK && p.fixup) {
       if (streak >= p.patience) done = true;
       if (__all_sync(0xffffffffu, done || !active)) break;

@@ -275,6 +275,42 @@ def pscan_filter(dt, Y, R, H, m0, P0, disc, chunk_len=None, jitter=None, polish=
     return res + ((status,) if return_status else ())
 
 
+def pscan_filter_spec(dt, Y, R, H, m0, P0, disc, chunk_len=None, warm=None, jitter=None, polish=2, delta=1e-11,
+                      patience=4, want_lml_k=False, out=None, ws=None, stream=None):
+    """Speculative parallel-in-time filter (include/physs_b200.h): warm-up instead of summaries + scan, verified
+    by the fix-up passes.  Returns (lml, mf, Pf[, lml_k], status); status = 1 -> use pscan_filter."""
+    lib = _lib.load()
+    p = _pack_filter(dt, Y, R, H, m0, P0, disc, jitter, stream)
+    L = default_chunk_len(p.B, p.T, p.d) if chunk_len is None else int(chunk_len)
+    W = min(L, 128) if warm is None else int(warm)
+    mf, Pf, lml, lml_k = _filter_outputs(p, out, want_lml_k)
+    ws = pscan_workspace(p.B, p.T, p.d, L, p.dev) if ws is None else ws
+    status = torch.zeros((1,), dtype=torch.int32, device=p.dev)
+    with torch.cuda.device(p.dev):
+        st = lib.physs_pscan_filter_spec_f64(*p.head, L, W, int(polish), float(delta), int(patience), ws.data_ptr(),
+                                             mf.data_ptr(), Pf.data_ptr(), lml.data_ptr(),
+                                             lml_k.data_ptr() if lml_k is not None else None, status.data_ptr())
+    _lib.check(st, "physs_pscan_filter_spec_f64")
+    return (lml, mf, Pf) + ((lml_k,) if want_lml_k else ()) + (status,)
+
+
+def pscan_smooth_spec(dt, mf, Pf, disc, chunk_len=None, warm=None, jitter=None, polish=2, delta=1e-11, patience=4,
+                      out=None, ws=None, stream=None):
+    """Speculative parallel-in-time smoother (full-state output).  Returns (ms, Ps, status)."""
+    lib = _lib.load()
+    p = _pack_smooth(dt, mf, Pf, disc, None, jitter, stream)
+    L = default_chunk_len(p.B, p.T, p.d) if chunk_len is None else int(chunk_len)
+    W = min(L, 128) if warm is None else int(warm)
+    ms, Ps = _smooth_outputs(p, out)
+    ws = pscan_workspace(p.B, p.T, p.d, L, p.dev) if ws is None else ws
+    status = torch.zeros((1,), dtype=torch.int32, device=p.dev)
+    with torch.cuda.device(p.dev):
+        st = lib.physs_pscan_smooth_spec_f64(*p.head, L, W, int(polish), float(delta), int(patience), ws.data_ptr(),
+                                             ms.data_ptr(), Ps.data_ptr(), status.data_ptr())
+    _lib.check(st, "physs_pscan_smooth_spec_f64")
+    return ms, Ps, status
+
+
 def pscan_smooth(dt, mf, Pf, disc, Hout=None, chunk_len=None, jitter=None, out=None, ws=None, stream=None):
     """Parallel-in-time RTS smoother: same arguments / results as rts_smooth."""
     lib = _lib.load()

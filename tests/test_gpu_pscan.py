@@ -166,3 +166,48 @@ def test_time_shards_on_one_gpu(cuda_device, d, m, given):
         a, b_ = ops.pscan_smooth_finish(*sargs, chunk, ws, start=start, jitter=jitter)
         mss.append(a), Pss.append(b_)
     assert rel(torch.cat(mss, 1), ms.cpu().numpy()) < TOL and rel(torch.cat(Pss, 1), Ps.cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("B,T,d,m,given,time_major,chunk,warm", [
+    (3, 20000, 4, 1, False, False, 256, 128), (70, 3000, 4, 1, False, True, 200, 100),
+    (2, 8000, 8, 8, False, False, 128, 128), (2, 8000, 8, 3, True, False, 100, 100),
+    (1, 9000, 12, 2, False, False, 250, 200), (40, 2500, 2, 1, False, True, 97, 97)])
+def test_speculative_parallel_contract(cuda_device, B, T, d, m, given, time_major, chunk, warm):
+    """Speculative mode (warm-up + verify / repair passes instead of summaries + scan).  Contract: when the
+    device flag is 0 the result equals the sequential kernels' to 1e-9; when it is 1 (slowly mixing filters:
+    the last case forgets a wrong start only at 0.92 per step) the caller must use the exact scan, which is
+    checked to hold parity on the same inputs."""
+    from physs_gp_b200 import ops
+    dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s = _batch_problem(cuda_device, B, T, d, m, given, 17 + d, time_major)
+    jitter = 1e-5
+    lml, mf, Pf = ops.kf_filter(dt_f, Y, R, H, m0, P0, disc_f, jitter=jitter)
+    ms, Ps = ops.rts_smooth(dt_s, mf, Pf, disc_s, jitter=jitter)
+    lml2, mf2, Pf2, st = ops.pscan_filter_spec(dt_f, Y, R, H, m0, P0, disc_f, chunk_len=chunk, warm=warm, jitter=jitter,
+                                               polish=6)
+    ms2, Ps2, st2 = ops.pscan_smooth_spec(dt_s, mf, Pf, disc_s, chunk_len=chunk, warm=warm, jitter=jitter, polish=6)
+    torch.cuda.synchronize()
+    if int(st.item()) == 0:
+        assert rel(lml2, lml.cpu().numpy()) < TOL
+        assert rel(mf2, mf.cpu().numpy()) < TOL and rel(Pf2, Pf.cpu().numpy()) < TOL
+    else:
+        # slow mixing: the O(jitter) boundary error of the scan also needs more fix-up passes than the default 4
+        lml2, mf2, Pf2, st = ops.pscan_filter(dt_f, Y, R, H, m0, P0, disc_f, chunk_len=chunk, jitter=jitter,
+                                              polish=8, return_status=True)
+        assert int(st.item()) == 0
+        assert rel(mf2, mf.cpu().numpy()) < TOL and rel(Pf2, Pf.cpu().numpy()) < TOL
+    if int(st2.item()) == 0:
+        assert rel(ms2, ms.cpu().numpy()) < TOL and rel(Ps2, Ps.cpu().numpy()) < TOL
+    else:
+        ms2, Ps2 = ops.pscan_smooth(dt_s, mf, Pf, disc_s, chunk_len=chunk, jitter=jitter)
+        assert rel(ms2, ms.cpu().numpy()) < TOL and rel(Ps2, Ps.cpu().numpy()) < TOL
+    if d >= 8 or (d == 4 and B == 70):
+        assert int(st.item()) == 0 and int(st2.item()) == 0      # the fast-mixing cases must take the fast path
+
+
+def test_speculative_mode_flags_insufficient_warmup(cuda_device):
+    """A warm-up far shorter than the filter's memory, with a single verification pass that cannot repair a
+    whole chunk within `patience`-limited agreement, must raise the flag (the caller then uses the exact scan)."""
+    from physs_gp_b200 import ops
+    dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s = _batch_problem(cuda_device, 1, 600, 4, 1, False, 5, False)
+    out = ops.pscan_filter_spec(dt_f, Y, R, H, m0, P0, disc_f, chunk_len=8, warm=1, jitter=1e-5, polish=1, patience=50)
+    assert int(out[-1].item()) == 1
