@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "cvi", "c2"],
+    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "cvi", "c2", "c3cvi"],
                     help="c5 (default, the headline metric): batched sweep; c3: one long series, parallel-in-time "
                          "scan, time-sharded over the ranks; cvi: CVI ELBO + natural-gradient step (config 4)")
     ap.add_argument("--chunk-len", type=int, default=256, help="c3: steps per scan chunk")
@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--cpu-sample-series", type=int, default=0, help="series in the CPU sample (0 = auto)")
     a = ap.parse_args()
     dflt = {"c5": (SERIES_TOTAL, T_STEPS, 4), "c3": (1, 1000000, 8), "cvi": (1000, T_STEPS, 2),
-            "c2": (200, 5000, 400)}[a.workload]
+            "c2": (200, 5000, 400), "c3cvi": (1, 1000000, 4)}[a.workload]
     a.series = dflt[0] if a.series is None else a.series
     a.T = dflt[1] if a.T is None else a.T
     a.state_dim = dflt[2] if a.state_dim is None else a.state_dim
@@ -764,10 +764,94 @@ def run_c2(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------ c3cvi: physics-informed CVI step on one long series
+def run_c3cvi(a):
+    """BASELINE config 3, the CVI side: damped-oscillator collocation model on ONE series of T steps (default
+    1M) -- Matern-7/2 state (x, x_t, x_tt, x_ttt), full-state sites (m = d = 4), sparse noisy observations of x,
+    collocation residual x_tt + (g/l) sin x + b x_t = 0 at every step, Laplace-Gauss-Newton curvature.
+    One step = natural_gradient_update (posterior by the parallel-in-time scan + closed-form collocation ELL
+    gradients + site update) + ELBO (second posterior pass + data / surrogate ELLs)."""
+    import torch
+    from physs_gp_b200 import cvi, sdes, settings
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    T = a.T
+    # full-state sites carry 1 / ng_jitter variances on the unobserved derivatives, so the surrogate filter mixes
+    # slowly in those directions: longer chunks and more fix-up passes than the defaults
+    settings.pscan_chunk_len = a.chunk_len if a.chunk_len != 256 else 512
+    settings.pscan_polish = 8
+    rng = np.random.default_rng(0)
+    t = 0.02 * np.arange(1, T + 1)
+    x_true = 1.0 * np.exp(-0.01 * t) * np.cos(3.0 * t)                  # decaying oscillation (stand-in signal)
+    Y = np.full((1, T, 2), np.nan)
+    obs = np.arange(0, T, 10)
+    Y[0, obs, 0] = x_true[obs] + 0.05 * rng.normal(size=len(obs))
+    Y[0, :, 1] = 0.0
+    prior = sdes.BatchedMaternSDE(4, np.array([[0.6]]), np.array([[2.0]]), full_state_obs=True)
+    q = cvi.FullConjugateGaussian(t, prior, 4, B=1, device=dev, filter_type="b200_parallel")
+    lik = cvi.DampedPendulumLik(g=9.81, l=1.0, b=0.3, var_obs=0.05 ** 2, var_col=0.5 ** 2)
+    model = cvi.VGP(Y, lik, q)
+
+    def step():
+        model.natural_gradient_update(0.5, enforce_psd_type='laplace_gauss_newton_delta_u')
+        return model.elbo()
+    for _ in range(a.warmup):
+        elbo = step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        elbo = step()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / a.steps
+    assert torch.isfinite(elbo).all()
+    Y_host = torch.empty((1, T, 2), dtype=torch.float64, pin_memory=True); Y_host.copy_(torch.as_tensor(Y))
+    o = torch.empty((1,), dtype=torch.float64, pin_memory=True)
+
+    def e2e_step():
+        model.set_data(Y_host)
+        o.copy_(step(), non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_step()
+    tw = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    elw = (time.perf_counter() - tw) / a.steps
+    peak, peak_src = measured_peak_gbs()
+    d = D = 4
+    fb, sb = algorithmic_bytes(d, d)
+    byt = 2 * (fb + sb) + 8 * (2 * (D * D + D) + (D * D + D) + 2 + (D * D + D)) + 8 * (2 * (D * D + D) + 2 + (D * D + D))
+    line = {"metric": "CVI ELBO+natgrad step time", "value": ms, "unit": "ms", "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "c3cvi (config 3): damped-oscillator collocation CVI, 1 series x %d steps, "
+                                   "Matern-7/2 derivative state d=4, full-state sites, Gauss-Newton curvature, "
+                                   "parallel-in-time scan" % T, "T": T, "state_dim": 4, "site_dim": 4,
+                       "l2": "per-step working set %.1f GB >> 126 MB L2" % (byt * T / 1e9),
+                       "parallelism": "single GPU (time sharding: --workload c3)"},
+            "state_steps_per_s": T / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": byt * T / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": byt * T / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                         "bytes_per_state_step": byt},
+            "cpu_baseline": None,
+            "e2e": {"value": 1e3 * elw, "unit": "ms", "h2d_bytes_per_step": T * 16, "d2h_bytes_per_step": 8,
+                    "api": "VGP.natural_gradient_update(0.5, 'laplace_gauss_newton_delta_u') + VGP.elbo()"},
+            "clocks": clocks, "gpu_launches": None}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "c3cvi":
+        run_c3cvi(a)
     elif a.workload == "c2":
         run_c2(a)
     elif a.workload == "c3":

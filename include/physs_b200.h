@@ -304,6 +304,14 @@ int physs_cvi_ell_pendulum_f64(void* stream, int64_t N, int32_t D, int32_t i0, i
                                double g_over_l, double damping, double var_obs, double var_col,
                                int32_t gauss_newton, double* ell_out, double* dm_out, double* dS_out);
 
+/* Gauss-Newton site curvature from caller-supplied Jacobians, for ANY prior transform: dS = -1/2 sum_p mask_p
+ * J_p^T J_p / var_p per site block (cvi_hessian_approximations.py:380-431,483-486,574; the Jacobians
+ * J [N, P, D] = d T(u)/du are what the reference computes with jax.jacfwd, :358-368, and stay on the JAX side).
+ *   var [., P] conditional likelihood variances (var_stride elements between blocks, 0 = shared)
+ *   y [N, P] or NULL: NaN entries drop the corresponding output from the sum. */
+int physs_cvi_gauss_newton_f64(void* stream, int64_t N, int32_t D, int32_t P, const double* J, const double* var,
+                               int64_t var_stride, const double* y, double* dS_out);
+
 /* FP64 FMA throughput probe (measurement aid for the FP64-pipe roofline; no reference counterpart).
  * Launches blocks x 256 threads doing iters x 8 independent FMAs each: flops = blocks*256*iters*16. */
 int physs_fp64_probe(void* stream, int32_t blocks, int64_t iters, double* out);

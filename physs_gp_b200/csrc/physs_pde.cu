@@ -122,3 +122,57 @@ int physs_cvi_ell_pendulum_f64(void* stream, int64_t N, int32_t D, int32_t i0, i
 }
 
 }
+
+// ------------------------------------------------------------------------------------------------
+// Generic Gauss-Newton site curvature from caller-supplied Jacobians (any prior transform): the reference
+// obtains J_p = d T_p(u) / du per time step by jax.jacfwd (cvi_hessian_approximations.py:358-368) and forms
+//   G = sum_p mask_p J_p^T (-Lambda_p^-1) J_p,     dS = 1/2 G      (:380-431, 483-486, 574)
+// with Lambda_p the conditional likelihood variance (Laplace-Gauss-Newton) and the mask from missing data.
+// One thread per site block.
+namespace physs {
+
+struct GnArgs {
+  int64_t N; int D, P;
+  const double* J;        // [N, P, D]
+  const double* var;      // [., P] likelihood variances, var_stride elements between blocks (0 = shared)
+  int64_t var_stride;
+  const double* y;        // [N, P] data, NaN = missing (NULL = all observed)
+  double* dS;             // [N, D, D]
+};
+
+__global__ void __launch_bounds__(128) gauss_newton_kernel(const GnArgs p) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const int D = p.D, P = p.P;
+  const double* __restrict__ J = p.J + n * (int64_t)P * D;
+  const double* __restrict__ var = p.var + n * p.var_stride;
+  double* __restrict__ dS = p.dS + n * (int64_t)D * D;
+  for (int i = 0; i < D; ++i) {
+    for (int j = i; j < D; ++j) {
+      double acc = 0.0;
+      for (int a = 0; a < P; ++a) {
+        const bool obs = p.y ? !(p.y[n * P + a] != p.y[n * P + a]) : true;
+        if (obs) acc = fma(J[a * D + i] / var[a], J[a * D + j], acc);
+      }
+      dS[i * D + j] = -0.5 * acc;
+      dS[j * D + i] = -0.5 * acc;
+    }
+  }
+}
+
+}  // namespace physs
+
+extern "C" {
+
+int physs_cvi_gauss_newton_f64(void* stream, int64_t N, int32_t D, int32_t P, const double* J, const double* var,
+                               int64_t var_stride, const double* y, double* dS_out) {
+  using namespace physs;
+  if (N < 0 || D < 1 || P < 1) return set_error(PHYSS_ERR_BAD_ARG, "gauss-newton: bad sizes");
+  if (N == 0) return PHYSS_OK;
+  if (!J || !var || !dS_out) return set_error(PHYSS_ERR_BAD_ARG, "gauss-newton: null required pointer");
+  GnArgs a{N, D, P, J, var, var_stride, y, dS_out};
+  gauss_newton_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+  return cuda_status(cudaGetLastError(), "gauss_newton_kernel launch");
+}
+
+}

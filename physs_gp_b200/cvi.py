@@ -215,6 +215,27 @@ def pendulum_expected_log_likelihood(q_mu, q_var, y, lik, gauss_newton=False, wa
     return (ell, dm, dS) if want_grads else ell
 
 
+def gauss_newton_curvature(J, var, y=None, stream=None):
+    """Raw op: dS [..., D, D] = -1/2 sum_p mask_p J_p^T J_p / var_p from Jacobians J [..., P, D] of the prior
+    transform (computed by the caller, e.g. jax.jacfwd), likelihood variances var [P] or [..., P], and optional
+    data y [..., P] whose NaNs mask outputs (cvi_hessian_approximations.py:380-431)."""
+    lib = _lib.load()
+    J = _c(J)
+    P, D = J.shape[-2], J.shape[-1]
+    lead = J.shape[:-2]
+    N = int(np.prod(lead))
+    var = _c(torch.as_tensor(var, dtype=torch.float64, device=J.device))
+    vstride = 0 if var.dim() == 1 else P
+    yv = None if y is None else _c(y)
+    dS = torch.empty(lead + (D, D), dtype=torch.float64, device=J.device)
+    s = stream if stream is not None else torch.cuda.current_stream()
+    with torch.cuda.device(J.device):
+        st = lib.physs_cvi_gauss_newton_f64(s.cuda_stream, N, D, P, J.data_ptr(), var.data_ptr(), vstride, _ptr(yv),
+                                            dS.data_ptr())
+    _lib.check(st, "physs_cvi_gauss_newton_f64")
+    return dS
+
+
 # --------------------------------------------------------------------------- reference-shaped objects
 class FullConjugateGaussian:
     """q(u) prop. to N(Y~ | u, V~) p(u): sites stored as the surrogate SDE_GP's data and noise

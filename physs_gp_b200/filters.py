@@ -10,6 +10,8 @@ Same names, argument meaning and return structure; results are torch CUDA tensor
 the reference's device-resident jax arrays).  A leading batch axis B is accepted on Y / R and on the
 prior (`BatchedMaternSDE`), and is carried through to the outputs when present.
 """
+import warnings
+
 import numpy as np
 import torch
 
@@ -136,8 +138,15 @@ def _filter_impl(parallel, data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, 
     R = _to_dev(lik_mat, dev)
     Hd = None if _is_identity(H) else _to_dev(H, dev)
     if parallel:
-        lml, mf, Pf = ops.pscan_filter(dtd, Yd, R, Hd, m0, P0, disc, chunk_len=settings.pscan_chunk_len,
-                                       jitter=settings.jitter, polish=settings.pscan_polish)
+        lml, mf, Pf, status = ops.pscan_filter(dtd, Yd, R, Hd, m0, P0, disc, chunk_len=settings.pscan_chunk_len,
+                                               jitter=settings.jitter, polish=settings.pscan_polish,
+                                               return_status=True)
+        if settings.pscan_check_status and int(status.item()) != 0:
+            # some chunk did not reconcile with the jittered sequential recursion within the fix-up passes
+            # (slowly mixing filter / chunks too short): return the sequential kernels' result instead
+            warnings.warn("physs_gp_b200: parallel-in-time filter did not converge to the sequential recursion "
+                          "(raise settings.pscan_polish or settings.pscan_chunk_len); using the sequential kernels")
+            lml, mf, Pf = ops.kf_filter(dtd, Yd, R, Hd, m0, P0, disc, jitter=settings.jitter)
     else:
         lml, mf, Pf = ops.kf_filter(dtd, Yd, R, Hd, m0, P0, disc, jitter=settings.jitter)
     if batched:

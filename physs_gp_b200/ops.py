@@ -233,12 +233,14 @@ def rts_smooth(dt, mf, Pf, disc, Hout=None, jitter=None, out=None, stream=None):
 
 # ------------------------------------------------------------------------------- parallel-in-time
 def default_chunk_len(B, T, d=8):
-    """Chunk length that gives the GPU enough independent (series, chunk) pairs, clamped to [32, T]:
+    """Chunk length that gives the GPU enough independent (series, chunk) pairs, clamped to [128, T]:
     ~64k for the register kernels (d <= 4: one THREAD per pair), ~148 SMs x 64 lane groups above.
     Long single series get many short chunks, large batches few long ones."""
     target = 65536 if d <= 4 else 148 * 64
     want_chunks = max(1, (target + B - 1) // B)
-    return int(min(T, max(32, -(-T // want_chunks))))
+    # not below 128 steps: the fix-up passes contract the O(jitter) boundary error by the filter's forgetting
+    # over ONE chunk, so chunks shorter than the mixing time cost more passes than they gain in parallelism
+    return int(min(T, max(128, -(-T // want_chunks))))
 
 
 def pscan_workspace(B, T, d, chunk_len, dev):

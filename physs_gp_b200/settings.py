@@ -27,3 +27,6 @@ auto_parallel_min_steps = 1024
 # single series with state dim above this go to the large-block path (libphyss_b200_big.so: cuBLAS / cuSOLVER
 # per step); at or below it the shared-memory lane-group kernels are used
 big_block_min_dim = 32
+# read the device flag of the parallel-in-time filter (one host sync) and fall back to the sequential kernels
+# when a chunk did not converge; set False to keep the call fully asynchronous
+pscan_check_status = True

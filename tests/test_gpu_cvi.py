@@ -278,3 +278,30 @@ def test_mean_field_cvi_matches_oracle(cuda_device):
             ref += -ocvi.surrogate_ell(Yt[q], Vt[q], m[:, q:q + 1], S[:, q:q + 1, q:q + 1]) + out[q][0]
             assert rel(qs[q].Y_tilde[b], Yt[q]) < TOL and rel(qs[q].V_tilde[b], Vt[q]) < TOL
         assert abs(float(elbo[b]) - ref) < TOL * abs(ref)
+
+
+def test_generic_gauss_newton_curvature(cuda_device):
+    """physs_cvi_gauss_newton_f64 against numpy, and against the pendulum kernel's own Gauss-Newton block."""
+    from physs_gp_b200 import cvi
+    rng = np.random.default_rng(21)
+    N, P, D = 37, 3, 5
+    J = rng.normal(size=(N, P, D))
+    var = np.array([0.1, 0.5, 2.0])
+    y = rng.normal(size=(N, P))
+    y[rng.uniform(size=y.shape) < 0.3] = np.nan
+    dS = cvi.gauss_newton_curvature(_dev(J), var, _dev(y))
+    ref = np.zeros((N, D, D))
+    for n in range(N):
+        for p_ in range(P):
+            if not np.isnan(y[n, p_]):
+                ref[n] += -0.5 * np.outer(J[n, p_], J[n, p_]) / var[p_]
+    assert rel(dS, ref) < 1e-13
+    # damped oscillator: J = [[1, 0, 0], [a cos x, b, 1]]
+    a, b = 1.4, 0.2
+    qm = rng.normal(size=(N, 3)); qS = synth.random_spd(rng, (N,), 3, base=0.05)
+    yy = np.zeros((N, 2))
+    Jp = np.zeros((N, 2, 3)); Jp[:, 0, 0] = 1.0; Jp[:, 1, 0] = a * np.cos(qm[:, 0]); Jp[:, 1, 1] = b; Jp[:, 1, 2] = 1.0
+    lik = cvi.DampedPendulumLik(g=a, l=1.0, b=b, var_obs=0.05, var_col=0.01)
+    _, _, dS_p = cvi.pendulum_expected_log_likelihood(_dev(qm), _dev(qS), _dev(yy), lik, gauss_newton=True, want_grads=True)
+    dS_g = cvi.gauss_newton_curvature(_dev(Jp), np.array([0.05, 0.01]), _dev(yy))
+    assert rel(dS_g, dS_p.cpu().numpy()) < 1e-12
