@@ -113,6 +113,9 @@ int grp_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const Se
 bool rt_supported(int d, int m);
 int rt_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity, const SeqFilterArgs& a);
 int rt_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
+int rt_filter_summary(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, const SeqFilterArgs& a,
+                      int64_t cfirst, int64_t ccount, double* elems);
+int rt_smooth_summary(cudaStream_t st, int d, int disc_mode, int nblk, const SeqSmoothArgs& a, double* elems);
 
 // physs_pscan.cu: parallel-in-time chunked associative scan
 int64_t pscan_workspace_doubles(int64_t B, int64_t T, int d, int64_t chunk_len);

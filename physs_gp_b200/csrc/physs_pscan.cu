@@ -28,6 +28,8 @@
 //
 // Elements in global memory (per (series b, chunk c), index v = b * nchunk + c):
 //   filter   [A d*d | C d*d | J d*d | b d | eta d]      smoother   [E d*d | L d*d | g d]
+#include <stdlib.h>
+
 #include "physs_internal.h"
 #include "physs_warp.cuh"
 
@@ -36,6 +38,11 @@ namespace physs {
 using namespace grp;
 
 static inline int ps_group_size(int d) { return d <= 8 ? 8 : (d <= 16 ? 16 : 32); }
+// PHYSS_FORCE_GRP=1 (A-B timing only): runtime-sized summary kernels instead of the register-tiled ones
+static bool ps_force_grp() {
+  static const bool on = [] { const char* e = getenv("PHYSS_FORCE_GRP"); return e && e[0] == '1'; }();
+  return on;
+}
 
 // ------------------------------------------------------------------------------------------ layouts
 struct PsLayout {
@@ -994,6 +1001,7 @@ int pscan_filter_local(cudaStream_t st, int d, int m, int disc_mode, int nblk, b
       r.chunk_first = first; r.chunk_count = count;
       return seq_filter_summary(st, d, m, disc_mode, nblk, hid, r, w.e0);
     }
+    if (rt_supported(d, m) && !ps_force_grp()) return rt_filter_summary(st, d, m, disc_mode, nblk, hid, a, first, count, w.e0);
     return PS_BY_G_GIVEN(run_filter_summary, st, a, L, hid, first, count, w.e0);
   };
   rc = summarise(0, nfull_sum);
@@ -1238,14 +1246,17 @@ int pscan_smooth_local(cudaStream_t st, int d, int disc_mode, int nblk, SeqSmoot
   const SsLayout Ls = ss_layout(d);
   const int64_t nfull = a.T / chunk_len;
   const bool reg = d <= 4 && seq_supported(d, d, disc_mode, nblk);
+  const bool rt = rt_supported(d, d) && !ps_force_grp();
   if (nfull > 0) {
     a.chunk_first = 0; a.chunk_count = nfull;
-    rc = reg ? seq_smooth_summary(st, d, disc_mode, nblk, a, w.e0) : PS_BY_G_GIVEN(run_smooth_summary, st, a, L, w.e0);
+    rc = reg ? seq_smooth_summary(st, d, disc_mode, nblk, a, w.e0)
+             : (rt ? rt_smooth_summary(st, d, disc_mode, nblk, a, w.e0) : PS_BY_G_GIVEN(run_smooth_summary, st, a, L, w.e0));
     if (rc) return rc;
   }
   if (nchunk > nfull) {
     a.chunk_first = nfull; a.chunk_count = nchunk - nfull;
-    rc = reg ? seq_smooth_summary(st, d, disc_mode, nblk, a, w.e0) : PS_BY_G_GIVEN(run_smooth_summary, st, a, L, w.e0);
+    rc = reg ? seq_smooth_summary(st, d, disc_mode, nblk, a, w.e0)
+             : (rt ? rt_smooth_summary(st, d, disc_mode, nblk, a, w.e0) : PS_BY_G_GIVEN(run_smooth_summary, st, a, L, w.e0));
     if (rc) return rc;
   }
   double* in = w.e0; double* out = w.e1;

@@ -110,7 +110,7 @@ __device__ __forceinline__ void mm_nn(double* __restrict__ C, const double* __re
 
 // C[i][j] = (Add ? Add[i][j] : 0) + sign * sum_l A[i][l] * B[j][l]   for i < n, j < m   (dense A B^T)
 // The lane keeps its row of A in registers; rows of B are broadcast.  Columns >= m of C are left untouched.
-template <int G, int DM>
+template <int G, int DM, bool TA = false>
 __device__ __forceinline__ void mm_nt(double* __restrict__ C, const double* __restrict__ A,
                                       const double* __restrict__ B, int n, int m, const double* Add,
                                       double sign) {
@@ -118,12 +118,17 @@ __device__ __forceinline__ void mm_nt(double* __restrict__ C, const double* __re
   const int gl = lane<G>();
   for (int i = gl; i < n; i += G) {
     double a[DM];
-    const double2* __restrict__ arow = reinterpret_cast<const double2*>(A + i * LD);
+    if (TA) {                                             // row i of A^T = column i of A
 #pragma unroll
-    for (int l2 = 0; l2 < DM / 2; ++l2) {
-      const double2 t = arow[l2];
-      a[2 * l2] = t.x;
-      a[2 * l2 + 1] = t.y;
+      for (int l = 0; l < DM; ++l) a[l] = A[l * LD + i];
+    } else {
+      const double2* __restrict__ arow = reinterpret_cast<const double2*>(A + i * LD);
+#pragma unroll
+      for (int l2 = 0; l2 < DM / 2; ++l2) {
+        const double2 t = arow[l2];
+        a[2 * l2] = t.x;
+        a[2 * l2 + 1] = t.y;
+      }
     }
     for (int j = 0; j < m; ++j) {
       const double2* __restrict__ brow = reinterpret_cast<const double2*>(B + j * LD);
