@@ -30,6 +30,8 @@
 //   filter   [A d*d | C d*d | J d*d | b d | eta d]      smoother   [E d*d | L d*d | g d]
 #include <stdlib.h>
 
+#include <cuda/ptx>
+
 #include "physs_internal.h"
 #include "physs_warp.cuh"
 
@@ -42,6 +44,34 @@ static inline int ps_group_size(int d) { return d <= 8 ? 8 : (d <= 16 ? 16 : 32)
 static bool ps_force_grp() {
   static const bool on = [] { const char* e = getenv("PHYSS_FORCE_GRP"); return e && e[0] == '1'; }();
   return on;
+}
+
+// ------------------------------------------------------------------- TMA (bulk-copy) staging of scan elements
+// A scan element is a handful of dense row-major blocks in global memory ([A | C | J | b | eta] or
+// [E | L | g]).  For even d every row is a multiple of 16 bytes and 16-byte aligned, so ONE elected lane of
+// the group stages the whole element with 1-D bulk copies (cp.async.bulk.shared.global, the TMA engine) into
+// the padded shared-memory rows and arms the group's mbarrier with the byte count; the other lanes only wait
+// on the barrier.  Odd d falls back to per-lane loads.
+namespace ptx = cuda::ptx;
+
+__device__ __forceinline__ void tma_rows(double* sdst, int ld, const double* __restrict__ gsrc, int n, int m,
+                                         uint64_t* bar) {
+  for (int i = 0; i < n; ++i)
+    ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sdst + i * ld, gsrc + (size_t)i * m,
+                       (uint32_t)(m * sizeof(double)), bar);
+}
+// bounded spin on the mbarrier phase (a lost completion must surface as a wrong result, not as a hung GPU)
+__device__ __forceinline__ void tma_wait(uint64_t* bar, uint32_t parity) {
+  for (int it = 0; it < (1 << 20); ++it)
+    if (ptx::mbarrier_try_wait_parity(bar, parity)) return;
+}
+template <int G>
+__device__ __forceinline__ void tma_bar_init(uint64_t* bar) {
+  if (Lanes<G>::gl() == 0) {
+    ptx::mbarrier_init(bar, 1);
+    ptx::fence_proxy_async(ptx::space_shared);      // make the initialised barrier visible to the async proxy
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------ layouts
@@ -281,18 +311,19 @@ __global__ void ps_filter_summary_kernel(const SeqFilterArgs p, const PsLayout L
 // ------------------------------------------------------------------------------ 2. filter combine
 struct PcLayout {
   int d, ld;
-  int Ai, Ci, Ji, Aj, Cj, Jj, M1, M1T, X1, X2, W, bi, ei, bj, ej, t1, t2;
+  int Ai, Ci, Ji, Aj, Cj, Jj, M1, M1T, X1, X2, W, bi, ei, bj, ej, t1, t2, bar;
   int total;
 };
 static PcLayout pc_layout(int d) {
   PcLayout L{};
-  L.d = d; L.ld = d | 1;
+  L.d = d; L.ld = (d % 2 == 0) ? d + 2 : (d | 1);      // even d: 16-byte aligned rows (TMA staging)
   int off = 0;
   auto take = [&](int n) { int o = off; off += (n + 1) & ~1; return o; };
   const int dd = d * L.ld;
   L.Ai = take(dd); L.Ci = take(dd); L.Ji = take(dd); L.Aj = take(dd); L.Cj = take(dd); L.Jj = take(dd);
   L.M1 = take(dd); L.M1T = take(dd); L.X1 = take(dd); L.X2 = take(dd); L.W = take(dd);
   L.bi = take(d); L.ei = take(d); L.bj = take(d); L.ej = take(d); L.t1 = take(d); L.t2 = take(d);
+  L.bar = take(2);
   L.total = off;
   return L;
 }
@@ -365,17 +396,42 @@ __device__ __forceinline__ void filter_combine(double* sm, const PcLayout& L) {
   __syncwarp();
 }
 
+// issue (no wait): element e -> slot `right ? j : i`.  Returns the bytes in flight on the barrier (0 = the
+// copy was done synchronously with per-lane loads).
 template <int G>
-__device__ __forceinline__ void load_filter_elem(double* sm, const PcLayout& L, bool right,
-                                                 const double* __restrict__ e) {
+__device__ __forceinline__ uint32_t load_filter_elem(double* sm, const PcLayout& L, bool right,
+                                                     const double* __restrict__ e) {
   const int d = L.d, ld = L.ld, gl = Lanes<G>::gl();
-  g2s<G>(sm + (right ? L.Aj : L.Ai), ld, e, d, d);
-  g2s<G>(sm + (right ? L.Cj : L.Ci), ld, e + d * d, d, d);
-  g2s<G>(sm + (right ? L.Jj : L.Ji), ld, e + 2 * d * d, d, d);
-  for (int i = gl; i < d; i += G) {
-    sm[(right ? L.bj : L.bi) + i] = e[3 * d * d + i];
-    sm[(right ? L.ej : L.ei) + i] = e[3 * d * d + d + i];
+  double* A = sm + (right ? L.Aj : L.Ai); double* C = sm + (right ? L.Cj : L.Ci); double* J = sm + (right ? L.Jj : L.Ji);
+  double* b = sm + (right ? L.bj : L.bi); double* eta = sm + (right ? L.ej : L.ei);
+  if ((d & 1) == 0) {
+    if (gl == 0) {
+      uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
+      ptx::fence_proxy_async(ptx::space_shared);   // order earlier generic-proxy accesses to these rows
+      tma_rows(A, ld, e, d, d, bar);
+      tma_rows(C, ld, e + d * d, d, d, bar);
+      tma_rows(J, ld, e + 2 * d * d, d, d, bar);
+      tma_rows(b, d, e + 3 * d * d, 1, d, bar);
+      tma_rows(eta, d, e + 3 * d * d + d, 1, d, bar);
+    }
+    return (uint32_t)((3 * d * d + 2 * d) * sizeof(double));
   }
+  g2s<G>(A, ld, e, d, d);
+  g2s<G>(C, ld, e + d * d, d, d);
+  g2s<G>(J, ld, e + 2 * d * d, d, d);
+  for (int i = gl; i < d; i += G) { b[i] = e[3 * d * d + i]; eta[i] = e[3 * d * d + d + i]; }
+  return 0;
+}
+// arm the barrier with the bytes issued by load_*_elem and wait for this phase
+template <int G>
+__device__ __forceinline__ void tma_finish(double* sm, int bar_off, uint32_t bytes, uint32_t& parity) {
+  if (bytes == 0) { __syncwarp(); return; }
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + bar_off);
+  if (Lanes<G>::gl() == 0) ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, bar, bytes);
+  __syncwarp();                                     // the arrival is posted before anybody starts to poll
+  tma_wait(bar, parity);
+  parity ^= 1u;
+  __syncwarp();
 }
 // left operand = identity element (A = I, rest 0) or a bare state (A = 0, b = m, C = P, J = 0, eta = 0)
 template <int G>
@@ -416,10 +472,12 @@ __global__ void ps_filter_scan_kernel(const double* __restrict__ in, double* __r
   const int64_t b = g / nsum, c = g % nsum;
   double* sm = smem + (size_t)g_in_block * L.total;
   const int64_t ne = ps_filter_elem(L.d);
-  load_filter_elem<G>(sm, L, true, in + (b * nchunk + c) * ne);
-  if (c >= stride) load_filter_elem<G>(sm, L, false, in + (b * nchunk + c - stride) * ne);
+  tma_bar_init<G>(reinterpret_cast<uint64_t*>(sm + L.bar));
+  uint32_t parity = 0;
+  uint32_t bytes = load_filter_elem<G>(sm, L, true, in + (b * nchunk + c) * ne);
+  if (c >= stride) bytes += load_filter_elem<G>(sm, L, false, in + (b * nchunk + c - stride) * ne);
   else left_special<G>(sm, L, nullptr, nullptr);
-  __syncwarp();
+  tma_finish<G>(sm, L.bar, bytes, parity);
   filter_combine<G>(sm, L);
   if (active) store_filter_elem<G>(sm, L, out + (b * nchunk + c) * ne);
 }
@@ -445,9 +503,11 @@ __global__ void ps_filter_apply_kernel(const double* __restrict__ prefix, int64_
   const int d = L.d, ld = L.ld, gl = Lanes<G>::gl();
   double* sm = smem + (size_t)g_in_block * L.total;
   const int64_t ne = ps_filter_elem(d);
-  load_filter_elem<G>(sm, L, true, prefix + (b * nchunk + c) * ne);
+  tma_bar_init<G>(reinterpret_cast<uint64_t*>(sm + L.bar));
+  uint32_t parity = 0;
+  const uint32_t bytes = load_filter_elem<G>(sm, L, true, prefix + (b * nchunk + c) * ne);
   left_special<G>(sm, L, m0 + b * m0_bs, P0 + b * P0_bs);
-  __syncwarp();
+  tma_finish<G>(sm, L.bar, bytes, parity);
   filter_combine<G>(sm, L);
   if (active) {
     // bnd index c + 1 (< nchunk by construction of the callers); boundary 0 is the start state itself
@@ -582,15 +642,16 @@ __global__ void ps_smooth_summary_kernel(const SeqSmoothArgs p, const PsLayout L
 
 // smoother scan (suffix): out[c] = in[c] o in[c + stride]   (identity on the right past the end)
 //   E = E_i E_j ; g = E_i g_j + g_i ; L = E_i L_j E_i^T + L_i   (parallel_rts_smoother.py:39-55)
-struct SsLayout { int d, ld, Ei, Li, Ej, Lj, W, Eo, gi, gj, total; };
+struct SsLayout { int d, ld, Ei, Li, Ej, Lj, W, Eo, gi, gj, bar, total; };
 static SsLayout ss_layout(int d) {
   SsLayout L{};
-  L.d = d; L.ld = d | 1;
+  L.d = d; L.ld = (d % 2 == 0) ? d + 2 : (d | 1);
   int off = 0;
   auto take = [&](int n) { int o = off; off += (n + 1) & ~1; return o; };
   const int dd = d * L.ld;
   L.Ei = take(dd); L.Li = take(dd); L.Ej = take(dd); L.Lj = take(dd); L.W = take(dd); L.Eo = take(dd);
   L.gi = take(d); L.gj = take(d);
+  L.bar = take(2);
   L.total = off;
   return L;
 }
@@ -610,12 +671,24 @@ __device__ __forceinline__ void smooth_combine(double* sm, const SsLayout& L) {
 }
 
 template <int G>
-__device__ __forceinline__ void load_smooth_elem(double* sm, const SsLayout& L, bool right,
-                                                 const double* __restrict__ e) {
+__device__ __forceinline__ uint32_t load_smooth_elem(double* sm, const SsLayout& L, bool right,
+                                                     const double* __restrict__ e) {
   const int d = L.d, ld = L.ld, gl = Lanes<G>::gl();
-  g2s<G>(sm + (right ? L.Ej : L.Ei), ld, e, d, d);
-  g2s<G>(sm + (right ? L.Lj : L.Li), ld, e + d * d, d, d);
-  for (int i = gl; i < d; i += G) sm[(right ? L.gj : L.gi) + i] = e[2 * d * d + i];
+  double* E = sm + (right ? L.Ej : L.Ei); double* Lm = sm + (right ? L.Lj : L.Li); double* g = sm + (right ? L.gj : L.gi);
+  if ((d & 1) == 0) {
+    if (gl == 0) {
+      uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
+      ptx::fence_proxy_async(ptx::space_shared);
+      tma_rows(E, ld, e, d, d, bar);
+      tma_rows(Lm, ld, e + d * d, d, d, bar);
+      tma_rows(g, d, e + 2 * d * d, 1, d, bar);
+    }
+    return (uint32_t)((2 * d * d + d) * sizeof(double));
+  }
+  g2s<G>(E, ld, e, d, d);
+  g2s<G>(Lm, ld, e + d * d, d, d);
+  for (int i = gl; i < d; i += G) g[i] = e[2 * d * d + i];
+  return 0;
 }
 // right operand = identity map (E = I, g = 0, L = 0) or a bare state (E = 0, g = m, L = P)
 template <int G>
@@ -645,10 +718,12 @@ __global__ void ps_smooth_scan_kernel(const double* __restrict__ in, double* __r
   const int d = L.d, ld = L.ld, gl = Lanes<G>::gl();
   double* sm = smem + (size_t)g_in_block * L.total;
   const int64_t ns = ps_smooth_elem(d);
-  load_smooth_elem<G>(sm, L, false, in + (b * nchunk + c) * ns);
-  if (c + stride < nchunk) load_smooth_elem<G>(sm, L, true, in + (b * nchunk + c + stride) * ns);
+  tma_bar_init<G>(reinterpret_cast<uint64_t*>(sm + L.bar));
+  uint32_t parity = 0;
+  uint32_t bytes = load_smooth_elem<G>(sm, L, false, in + (b * nchunk + c) * ns);
+  if (c + stride < nchunk) bytes += load_smooth_elem<G>(sm, L, true, in + (b * nchunk + c + stride) * ns);
   else right_special<G>(sm, L, nullptr, nullptr);
-  __syncwarp();
+  tma_finish<G>(sm, L.bar, bytes, parity);
   smooth_combine<G>(sm, L);
   if (!active) return;
   double* eo = out + (b * nchunk + c) * ns;
@@ -680,9 +755,11 @@ __global__ void ps_smooth_apply_kernel(const double* __restrict__ suffix, int64_
   double* sm = smem + (size_t)g_in_block * L.total;
   const int64_t ns = ps_smooth_elem(d);
   const int64_t cs = (c + 1 < nchunk) ? c + 1 : c;          // the last chunk's slot is written directly below
-  load_smooth_elem<G>(sm, L, false, suffix + (b * nchunk + cs) * ns);
+  tma_bar_init<G>(reinterpret_cast<uint64_t*>(sm + L.bar));
+  uint32_t parity = 0;
+  const uint32_t bytes = load_smooth_elem<G>(sm, L, false, suffix + (b * nchunk + cs) * ns);
   right_special<G>(sm, L, start_m + b * d, start_P + b * d * d);
-  __syncwarp();
+  tma_finish<G>(sm, L.bar, bytes, parity);
   smooth_combine<G>(sm, L);
   if (!active) return;
   double* om = bnd_m + (b * nchunk + c) * d;
@@ -716,10 +793,11 @@ __global__ void ps_filter_fold_kernel(const double* __restrict__ totals, int64_t
   double* sm = smem + (size_t)g_in_block * L.total;
   const int64_t ne = ps_filter_elem(d);
   left_special<G>(sm, L, m0 + b * m0_bs, P0 + b * P0_bs);
-  __syncwarp();
+  tma_bar_init<G>(reinterpret_cast<uint64_t*>(sm + L.bar));
+  uint32_t parity = 0;
   for (int64_t k = 0; k < K; ++k) {
-    load_filter_elem<G>(sm, L, true, totals + (k * B + b) * ne);
-    __syncwarp();
+    const uint32_t bytes = load_filter_elem<G>(sm, L, true, totals + (k * B + b) * ne);
+    tma_finish<G>(sm, L.bar, bytes, parity);
     filter_combine<G>(sm, L);
     // result (A = 0, b, C, J = 0, eta = 0) becomes the next left operand
     for (int idx = gl; idx < d * d; idx += G) {
@@ -749,10 +827,11 @@ __global__ void ps_smooth_fold_kernel(const double* __restrict__ totals, int64_t
   double* sm = smem + (size_t)g_in_block * L.total;
   const int64_t ns = ps_smooth_elem(d);
   right_special<G>(sm, L, m0 + b * d, P0 + b * d * d);
-  __syncwarp();
+  tma_bar_init<G>(reinterpret_cast<uint64_t*>(sm + L.bar));
+  uint32_t parity = 0;
   for (int64_t k = K - 1; k >= 0; --k) {
-    load_smooth_elem<G>(sm, L, false, totals + (k * B + b) * ns);
-    __syncwarp();
+    const uint32_t bytes = load_smooth_elem<G>(sm, L, false, totals + (k * B + b) * ns);
+    tma_finish<G>(sm, L.bar, bytes, parity);
     smooth_combine<G>(sm, L);            // (Eo, gi, Lj); with Ej = 0 the map part stays 0
     for (int i = gl; i < d; i += G) sm[L.gj + i] = sm[L.gi + i];
     for (int idx = gl; idx < d * d; idx += G) {
