@@ -338,7 +338,13 @@ def run_b200(a):
     s_units = [n * T for _, _, n in ev["s"]]
     peak, peak_src = measured_peak_gbs()
     kern = {}
-    kn = ("seq_filter_kernel", "seq_smooth_kernel") if d <= 4 else ("grp_filter_kernel", "grp_smooth_kernel")
+    # which kernel family the C ABI dispatches this shape to (physs_api.cu: prefer_seq / rt_supported)
+    if d <= 4 or (d == 8 and sub >= 4096):
+        kn = ("seq_filter_kernel<%d>" % d, "seq_smooth_kernel<%d>" % d)
+    elif d <= 32:
+        kn = ("rt_filter_kernel<%d>" % d, "rt_smooth_kernel<%d>" % d)
+    else:
+        kn = ("grp_filter_kernel", "grp_smooth_kernel")
     for name, msl, units, bpu in ((kn[0], f_ms, f_units, fb), (kn[1], s_ms, s_units, sb)):
         avg_ms = float(np.mean(msl))
         avg_bytes = float(np.mean(units)) * bpu
@@ -352,6 +358,11 @@ def run_b200(a):
                 "kernels": kern,
                 "whole_step_frac": (fb + sb) * (value / world) / 1e9 / peak,
                 "fp64_peak_tflops_measured": ops.fp64_peak_tflops(dev)}
+    # the other regime of SURVEY 8d: F(d, m) flop per state-step against the FP64 pipe measured on this box
+    flops = 14.3 * d ** 3 + 4 * d * d + 6 * d + 0.67
+    tf = flops * (value / world) / 1e12
+    roofline["fp64"] = {"flops_per_state_step": flops, "achieved_tflops": tf,
+                        "frac": tf / roofline["fp64_peak_tflops_measured"]}
 
     # ---------------------------------------------------------------- e2e through the host API
     e2e = None

@@ -45,7 +45,7 @@ static RtLayout rt_layout(int d, int m, int mo, int nblk, bool given, bool smoot
   if (given) {
     for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) L.AQst[a][b] = take(MAT);
   }
-  L.vm = take(LD); L.vmp = take(LD); L.vdm = take(LD); L.vrd = take(LD);
+  L.vm = take(LD); L.vmp = take(LD); L.vdm = take(LD); L.vrd = take(3 * LD);   // rd + two column buffers (chol)
   L.vlam = take(nblk > 0 ? nblk : 1);
   L.total = rt_slab(off);
   return L;
@@ -219,10 +219,7 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
       mm_nt<G, DM>(P, W2, Ak, d, d, Qk, 1.0);                              // A P A^T + Q
     } else {
       rt_matern_A<G, DM>(A, s, L.nblk, lam, dt);
-      for (int i = gl; i < d; i += G) {                                     // dP = P - Pinf
-#pragma unroll
-        for (int j = 0; j < DM; ++j) W1[i * LD + j] = P[i * LD + j] - Qm[i * LD + j];
-      }
+      sub_rows<G, DM>(W1, P, Qm, d);                                        // dP = P - Pinf
       __syncwarp();
       mv<G, DM, false>(mp, A, mv_, d, d, nullptr, 1.0, s);
       mm_nn<G, DM, false>(W2, A, W1, d, d, nullptr, 1.0, s);                // A dP
@@ -251,7 +248,7 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
           for (int l = 0; l < d; ++l) hp = fma(P[i * LD + l], H[l], hp);
         }
         hp = obs ? hp : 0.0;
-        K[i * LD] = hp;
+        w[i] = hp;                                                           // gain column, contiguous
         sv = fma(hid ? (i == 0 ? 1.0 : 0.0) : H[i], hp, sv);
       }
 #pragma unroll
@@ -259,14 +256,22 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
       const double Sv = sv + R[0];
       const double rSj = fast_rcp(Sv + p.jitter);
       const double vv = obs ? (y[0] - mu) : 0.0;
-      __syncwarp();
-      for (int i = gl; i < d; i += G) K[i * LD] *= rSj;                      // K = P H^T / (S + jitter)
+      for (int i = gl; i < d; i += G) w[i] *= rSj;                           // K = P H^T / (S + jitter)
       __syncwarp();
       for (int i = gl; i < d; i += G) {
-        const double ki = K[i * LD];
+        const double ki = w[i];
         mv_[i] = fma(ki, vv, mp[i]);
-        const double ks = ki * Sv;
-        for (int j = 0; j < d; ++j) P[i * LD + j] = fma(-ks, K[j * LD], P[i * LD + j]);
+        const double ks = -ki * Sv;
+        double2* __restrict__ prow = reinterpret_cast<double2*>(P + i * LD);
+        const double2* __restrict__ k2 = reinterpret_cast<const double2*>(w);
+#pragma unroll
+        for (int j2 = 0; j2 < DM / 2; ++j2) {                                // P -= K S K^T (K zero-padded)
+          double2 pr = prow[j2];
+          const double2 kk = k2[j2];
+          pr.x = fma(ks, kk.x, pr.x);
+          pr.y = fma(ks, kk.y, pr.y);
+          prow[j2] = pr;
+        }
       }
       const double Sl = obs ? Sv : 1.0;
       det = Sl;
@@ -340,11 +345,8 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
     }
     __syncwarp();
     if (active && !done) {
-      for (int i = gl; i < d; i += G) {
-        mfp[k * sts * d + i] = mv_[i];
-        double* __restrict__ o = Pfp + k * sts * d * d + i * d;
-        for (int j = 0; j < d; ++j) o[j] = P[i * LD + j];
-      }
+      for (int i = gl; i < d; i += G) mfp[k * sts * d + i] = mv_[i];
+      s2g<G, DM>(Pfp + k * sts * d * d, P, d, d);
       if (lkp && gl == 0) lkp[k * sts] = lml_term(det, mahal, nobs);
     }
     if (chunked && p.fixup) {
@@ -403,11 +405,8 @@ __global__ void rt_smooth_kernel(const SeqSmoothArgs p, const RtLayout L) {
   auto emit = [&](int64_t k) {
     if (mo == 0) {
       if (active && !done) {
-        for (int i = gl; i < d; i += G) {
-          msp[k * sts * d + i] = ms[i];
-          double* __restrict__ o = Psp + k * sts * d * d + i * d;
-          for (int j = 0; j < d; ++j) o[j] = Ps[i * LD + j];
-        }
+        for (int i = gl; i < d; i += G) msp[k * sts * d + i] = ms[i];
+        s2g<G, DM>(Psp + k * sts * d * d, Ps, d, d);
       }
     } else {
       mm_nn<G, DM, false>(W1, Ho, Ps, mo, d, nullptr, 1.0);                   // Hout Ps  [mo x d]
@@ -478,10 +477,7 @@ __global__ void rt_smooth_kernel(const SeqSmoothArgs p, const RtLayout L) {
       mm_nn<G, DM, false>(W2, Ak, W1, d, d, Qk, 1.0);                          // A (Pf A^T) + Q
     } else {
       rt_matern_A<G, DM>(A, s, L.nblk, lam, dt);
-      for (int i = gl; i < d; i += G) {                                         // dPf = Pf - Pinf
-#pragma unroll
-        for (int j = 0; j < DM; ++j) W3[i * LD + j] = Pf[i * LD + j] - Qm[i * LD + j];
-      }
+      sub_rows<G, DM>(W3, Pf, Qm, d);                                           // dPf = Pf - Pinf
       __syncwarp();
       mv<G, DM, false>(mpred, A, mf, d, d, nullptr, 1.0, s);
       mm_nt_blk<G, DM>(W1, Pf, A, d, d, s, nullptr, 1.0);                       // Pf A^T
@@ -491,13 +487,9 @@ __global__ void rt_smooth_kernel(const SeqSmoothArgs p, const RtLayout L) {
     }
     __syncwarp();
     // dP = Ps - Pp -> W3 ; dm = ms - mpred ; Pp += jitter I
+    sub_rows<G, DM>(W3, Ps, W2, d);
     for (int i = gl; i < d; i += G) {
-#pragma unroll
-      for (int j = 0; j < DM; ++j) {
-        const double pp = W2[i * LD + j];
-        W3[i * LD + j] = Ps[i * LD + j] - pp;
-        if (i == j) W2[i * LD + j] = pp + p.jitter;
-      }
+      W2[i * LD + i] += p.jitter;
       dm[i] = ms[i] - mpred[i];
     }
     __syncwarp();
@@ -555,7 +547,7 @@ static RtSumLayout rt_sum_layout(int d, int m, int nblk, bool given, bool smooth
   if (given) {
     for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) L.AQst[a][b] = take(MAT);
   }
-  L.vb = take(LD); L.vbb = take(LD); L.vdm = take(LD); L.vrd = take(LD);
+  L.vb = take(LD); L.vbb = take(LD); L.vdm = take(LD); L.vrd = take(3 * LD);
   L.vlam = take(nblk > 0 ? nblk : 1);
   L.total = rt_slab(off);
   return L;
@@ -778,10 +770,7 @@ __global__ void rt_smooth_summary_kernel(const SeqSmoothArgs p, const RtSumLayou
       mm_nn<G, DM, false>(W2, Ak, W1, d, d, Qk, 1.0);
     } else {
       rt_matern_A<G, DM>(A, s, L.nblk, lam, dt);
-      for (int i = gl; i < d; i += G) {
-#pragma unroll
-        for (int j = 0; j < DM; ++j) W3[i * LD + j] = Pf[i * LD + j] - Qm[i * LD + j];
-      }
+      sub_rows<G, DM>(W3, Pf, Qm, d);
       __syncwarp();
       mv<G, DM, false>(mpred, A, mf, d, d, nullptr, 1.0, s);
       mm_nt_blk<G, DM>(W1, Pf, A, d, d, s, nullptr, 1.0);
@@ -790,13 +779,9 @@ __global__ void rt_smooth_summary_kernel(const SeqSmoothArgs p, const RtSumLayou
       mm_nn<G, DM, false>(W2, A, W4, d, d, Qm, 1.0, s);
     }
     __syncwarp();
+    sub_rows<G, DM>(W3, Ls, W2, d);
     for (int i = gl; i < d; i += G) {
-#pragma unroll
-      for (int j = 0; j < DM; ++j) {
-        const double pp = W2[i * LD + j];
-        W3[i * LD + j] = Ls[i * LD + j] - pp;
-        if (i == j) W2[i * LD + j] = pp + p.jitter;
-      }
+      W2[i * LD + i] += p.jitter;
       dm[i] = gv[i] - mpred[i];
     }
     __syncwarp();

@@ -13,6 +13,7 @@
 // operands stay zero-padded), so the unrolled loops may always run over all DM columns.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 #include "physs_core.cuh"
 #include "physs_warp.cuh"
@@ -146,10 +147,70 @@ __device__ __forceinline__ void mm_nt(double* __restrict__ C, const double* __re
 }
 
 // C[i][j] = Add[i][j] + sign * sum_{l in block(j)} A[i][l] * B[j][l]   (A opB with block-diagonal opB = B^T)
+// Compile-time block size: the lane keeps its row of A in registers, the BS entries of row j of B inside
+// its diagonal block are broadcast loads (16-byte when BS is even), the row of C is written in pairs.
+// All DM columns are produced (rows >= m of B are zero padding).
+template <int G, int DM, int BS>
+__device__ __forceinline__ void mm_nt_blk_bs(double* __restrict__ C, const double* __restrict__ A,
+                                             const double* __restrict__ B, int n, const double* Add,
+                                             double sign) {
+  constexpr int LD = Dim<DM>::LD;
+  const int gl = lane<G>();
+  for (int i = gl; i < n; i += G) {
+    double a[DM];
+    const double2* __restrict__ arow = reinterpret_cast<const double2*>(A + i * LD);
+#pragma unroll
+    for (int l2 = 0; l2 < DM / 2; ++l2) {
+      const double2 t = arow[l2];
+      a[2 * l2] = t.x;
+      a[2 * l2 + 1] = t.y;
+    }
+    double2* __restrict__ crow = reinterpret_cast<double2*>(C + i * LD);
+    const double2* __restrict__ addrow = Add ? reinterpret_cast<const double2*>(Add + i * LD) : nullptr;
+#pragma unroll
+    for (int j2 = 0; j2 < DM / 2; ++j2) {
+      double o[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = 2 * j2 + h;
+        const int l0 = (j / BS) * BS;
+        double acc = 0.0;
+        if (BS % 2 == 0) {
+          const double2* __restrict__ bb = reinterpret_cast<const double2*>(B + j * LD + l0);
+#pragma unroll
+          for (int q = 0; q < BS / 2; ++q) {
+            if (l0 + 2 * q + 1 < DM) {
+              const double2 b = bb[q];
+              acc = fma(a[l0 + 2 * q], b.x, acc);
+              acc = fma(a[l0 + 2 * q + 1], b.y, acc);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < BS; ++q)
+            if (l0 + q < DM) acc = fma(a[l0 + q], B[j * LD + l0 + q], acc);
+        }
+        o[h] = acc;
+      }
+      double2 base = addrow ? addrow[j2] : make_double2(0.0, 0.0);
+      base.x = fma(sign, o[0], base.x);
+      base.y = fma(sign, o[1], base.y);
+      crow[j2] = base;
+    }
+  }
+}
+
 template <int G, int DM>
 __device__ __forceinline__ void mm_nt_blk(double* __restrict__ C, const double* __restrict__ A,
                                           const double* __restrict__ B, int n, int m, int bs,
                                           const double* Add, double sign) {
+  switch (bs) {
+    case 1: mm_nt_blk_bs<G, DM, 1>(C, A, B, n, Add, sign); return;
+    case 2: mm_nt_blk_bs<G, DM, 2>(C, A, B, n, Add, sign); return;
+    case 3: mm_nt_blk_bs<G, DM, 3>(C, A, B, n, Add, sign); return;
+    case 4: mm_nt_blk_bs<G, DM, 4>(C, A, B, n, Add, sign); return;
+    default: break;
+  }
   constexpr int LD = Dim<DM>::LD;
   const int gl = lane<G>();
   for (int i = gl; i < n; i += G) {
@@ -178,14 +239,68 @@ __device__ __forceinline__ void mv(double* __restrict__ y, const double* __restr
   }
 }
 
-// In-place lower Cholesky of the n x n matrix A (lower triangle), rd[j] = 1 / L[j][j]; returns det(A).
-// Right-looking by columns: after column j is scaled, lane i updates its trailing row i with the
-// broadcast column.  Non-PD -> NaN.
+// In-place lower Cholesky of the n x n matrix A, rd[j] = 1 / L[j][j]; returns det(A).  Non-PD -> NaN.
+// `rd` must have room for 3 * LD doubles: rd[0 .. LD) the reciprocal diagonal, then two column buffers.
+//
+// G == DM (one row per lane): the lane keeps its row in REGISTERS.  Step j: every lane publishes its entry of
+// column j to a column buffer (one store), all lanes read the pivot and the column back as 16-byte
+// broadcasts and update their whole register row -- entries right of the diagonal are computed too (no
+// predicates) and never used.  The strict UPPER triangle of A is filled with L^T, so that the backward
+// substitution of chol_solve_t reads rows, not columns.  DM^2/2 fused multiply-adds, DM^2/4 loads and
+// DM stores per factorisation, against two loads and a store per multiply-add of the in-place form.
+//
+// G < DM: right-looking in shared memory (several rows per lane); the upper triangle is left untouched.
 template <int G, int DM>
 __device__ __forceinline__ double chol(double* __restrict__ A, int n, double* __restrict__ rd) {
   constexpr int LD = Dim<DM>::LD;
   const int gl = lane<G>();
   double det = 1.0;
+  if (G == DM) {
+    const int i = gl;
+    double a[DM];
+    {
+      const double2* __restrict__ row = reinterpret_cast<const double2*>(A + i * LD);
+#pragma unroll
+      for (int l2 = 0; l2 < DM / 2; ++l2) {
+        const double2 t = (i < n) ? row[l2] : make_double2(0.0, 0.0);   // rows >= n may lie outside the slot
+        a[2 * l2] = t.x;
+        a[2 * l2 + 1] = t.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DM; ++j) {
+      if (j < n) {                                            // uniform
+        double* __restrict__ cb = rd + LD + (j & 1) * LD;
+        cb[i] = a[j];                                         // column j before scaling; entry j = pivot
+        __syncwarp();
+        const double s = cb[j];
+        const double r = fast_rsqrt(s);
+        det *= s;
+        const double lij = a[j] * r;
+        const double f = -lij * r;                            // L[i][j] L[c][j] = (a_ij r) (a_cj r)
+        const double2* __restrict__ cb2 = reinterpret_cast<const double2*>(cb);
+#pragma unroll
+        for (int c2 = (j + 1) / 2; c2 < DM / 2; ++c2) {
+          const double2 b = cb2[c2];
+          if (2 * c2 > j) a[2 * c2] = fma(f, b.x, a[2 * c2]);
+          a[2 * c2 + 1] = fma(f, b.y, a[2 * c2 + 1]);
+        }
+        a[j] = (i == j) ? s * r : lij;
+        if (i == j) rd[j] = r;
+        if (i > j) A[j * LD + i] = lij;                       // L^T into the upper triangle
+      }
+    }
+    if (i < n) {                                              // lower triangle + diagonal of the own row
+      double2* __restrict__ row = reinterpret_cast<double2*>(A + i * LD);
+#pragma unroll
+      for (int l2 = 0; l2 < DM / 2; ++l2) {
+        if (2 * l2 + 1 <= i) row[l2] = make_double2(a[2 * l2], a[2 * l2 + 1]);
+        else if (2 * l2 == i) A[i * LD + i] = a[2 * l2];
+      }
+    }
+    __syncwarp();
+    return det;
+  }
   for (int j = 0; j < n; ++j) {
     const double s = A[j * LD + j];
     const double r = fast_rsqrt(s);
@@ -209,7 +324,8 @@ __device__ __forceinline__ double chol(double* __restrict__ A, int n, double* __
 
 // X <- (L L^T)^{-1} X for nrhs columns, X stored TRANSPOSED: column c of the system is ROW c of Xt
 // (Xt[c][0..n)), one system per lane: the lane keeps its own row in registers and the L entries are
-// broadcasts.  Entries of the row beyond n are passed through unchanged.
+// broadcasts.  Entries of the row beyond n must be finite (zero padding) and come back unchanged.
+// G == DM: the factor carries L^T in its upper triangle (chol above), both sweeps read rows.
 template <int G, int DM>
 __device__ __forceinline__ void chol_solve_t(const double* __restrict__ L, int n, const double* __restrict__ rd,
                                              double* __restrict__ Xt, int nrhs) {
@@ -229,26 +345,38 @@ __device__ __forceinline__ void chol_solve_t(const double* __restrict__ L, int n
 #pragma unroll
     for (int i = 0; i < DM; ++i) {
       if (i < n) {
-        double t = x[i];
+        double t0 = x[i], t1 = 0.0;
         const double2* __restrict__ lrow = reinterpret_cast<const double2*>(L + i * LD);
 #pragma unroll
         for (int l2 = 0; l2 < (i + 1) / 2; ++l2) {
           const double2 b = lrow[l2];
-          t = fma(-b.x, x[2 * l2], t);
-          if (2 * l2 + 1 < i) t = fma(-b.y, x[2 * l2 + 1], t);
+          t0 = fma(-b.x, x[2 * l2], t0);
+          if (2 * l2 + 1 < i) t1 = fma(-b.y, x[2 * l2 + 1], t1);
         }
-        x[i] = t * rd[i];
+        x[i] = (t0 + t1) * rd[i];
       }
     }
 #pragma unroll
     for (int i = DM - 1; i >= 0; --i) {
       if (i < n) {
-        double t = x[i];
+        if (G == DM) {
+          double t0 = x[i], t1 = 0.0;
+          const double2* __restrict__ urow = reinterpret_cast<const double2*>(L + i * LD);
 #pragma unroll
-        for (int l = i + 1; l < DM; ++l) {
-          if (l < n) t = fma(-L[l * LD + i], x[l], t);
+          for (int l2 = (i + 1) / 2; l2 < DM / 2; ++l2) {
+            const double2 b = urow[l2];                       // zero beyond n
+            if (2 * l2 > i) t0 = fma(-b.x, x[2 * l2], t0);
+            t1 = fma(-b.y, x[2 * l2 + 1], t1);
+          }
+          x[i] = (t0 + t1) * rd[i];
+        } else {
+          double t = x[i];
+#pragma unroll
+          for (int l = i + 1; l < DM; ++l) {
+            if (l < n) t = fma(-L[l * LD + i], x[l], t);
+          }
+          x[i] = t * rd[i];
         }
-        x[i] = t * rd[i];
       }
     }
 #pragma unroll
@@ -256,11 +384,26 @@ __device__ __forceinline__ void chol_solve_t(const double* __restrict__ L, int n
   }
 }
 
-// dense n x m global (row stride m) <-> padded shared slot
+// dense n x m global (row stride m) <-> padded shared slot.  Full-size square matrices (n == m == DM) at a
+// 16-byte aligned global address move as double2: consecutive lanes take consecutive pieces of a row, so a
+// warp instruction covers whole 128-byte lines of the dense matrix.
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
 template <int G, int DM>
 __device__ __forceinline__ void g2s(double* __restrict__ dst, const double* __restrict__ src, int n, int m) {
   constexpr int LD = Dim<DM>::LD;
+  constexpr int PR = DM / 2;
   const int gl = lane<G>();
+  if (n == DM && m == DM && aligned16(src)) {
+    const double2* __restrict__ s2 = reinterpret_cast<const double2*>(src);
+#pragma unroll
+    for (int idx = gl; idx < DM * PR; idx += G)
+      *reinterpret_cast<double2*>(dst + (idx / PR) * LD + 2 * (idx % PR)) = s2[idx];
+    return;
+  }
   for (int idx = gl; idx < n * m; idx += G) {
     const int i = idx / m, j = idx - i * m;
     dst[i * LD + j] = src[idx];
@@ -269,7 +412,13 @@ __device__ __forceinline__ void g2s(double* __restrict__ dst, const double* __re
 template <int G, int DM>
 __device__ __forceinline__ void g2s_async(double* __restrict__ dst, const double* __restrict__ src, int n, int m) {
   constexpr int LD = Dim<DM>::LD;
+  constexpr int PR = DM / 2;
   const int gl = lane<G>();
+  if (n == DM && m == DM && aligned16(src)) {
+#pragma unroll
+    for (int idx = gl; idx < DM * PR; idx += G) cp_async16(dst + (idx / PR) * LD + 2 * (idx % PR), src + 2 * idx);
+    return;
+  }
   for (int idx = gl; idx < n * m; idx += G) {
     const int i = idx / m, j = idx - i * m;
     grp::cp_async8(dst + i * LD + j, src + idx);
@@ -278,10 +427,35 @@ __device__ __forceinline__ void g2s_async(double* __restrict__ dst, const double
 template <int G, int DM>
 __device__ __forceinline__ void s2g(double* __restrict__ dst, const double* __restrict__ src, int n, int m) {
   constexpr int LD = Dim<DM>::LD;
+  constexpr int PR = DM / 2;
   const int gl = lane<G>();
+  if (n == DM && m == DM && aligned16(dst)) {
+    double2* __restrict__ d2 = reinterpret_cast<double2*>(dst);
+#pragma unroll
+    for (int idx = gl; idx < DM * PR; idx += G)
+      d2[idx] = *reinterpret_cast<const double2*>(src + (idx / PR) * LD + 2 * (idx % PR));
+    return;
+  }
   for (int idx = gl; idx < n * m; idx += G) {
     const int i = idx / m, j = idx - i * m;
     dst[idx] = src[i * LD + j];
+  }
+}
+
+// D[i][:] = X[i][:] - Y[i][:] over all DM columns of the own rows i < n (16-byte pieces)
+template <int G, int DM>
+__device__ __forceinline__ void sub_rows(double* __restrict__ D, const double* __restrict__ X,
+                                         const double* __restrict__ Y, int n) {
+  constexpr int LD = Dim<DM>::LD;
+  for (int i = lane<G>(); i < n; i += G) {
+    const double2* __restrict__ x = reinterpret_cast<const double2*>(X + i * LD);
+    const double2* __restrict__ y = reinterpret_cast<const double2*>(Y + i * LD);
+    double2* __restrict__ o = reinterpret_cast<double2*>(D + i * LD);
+#pragma unroll
+    for (int j2 = 0; j2 < DM / 2; ++j2) {
+      const double2 a = x[j2], b = y[j2];
+      o[j2] = make_double2(a.x - b.x, a.y - b.y);
+    }
   }
 }
 
