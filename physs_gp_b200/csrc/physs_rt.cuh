@@ -242,20 +242,19 @@ __device__ __forceinline__ void mv(double* __restrict__ y, const double* __restr
 // In-place lower Cholesky of the n x n matrix A, rd[j] = 1 / L[j][j]; returns det(A).  Non-PD -> NaN.
 // `rd` must have room for 3 * LD doubles: rd[0 .. LD) the reciprocal diagonal, then two column buffers.
 //
-// G == DM (one row per lane): the lane keeps its row in REGISTERS.  Step j: every lane publishes its entry of
+// One row per lane (G == DM): the lane keeps its row in REGISTERS.  Step j: every lane publishes its entry of
 // column j to a column buffer (one store), all lanes read the pivot and the column back as 16-byte
 // broadcasts and update their whole register row -- entries right of the diagonal are computed too (no
 // predicates) and never used.  The strict UPPER triangle of A is filled with L^T, so that the backward
 // substitution of chol_solve_t reads rows, not columns.  DM^2/2 fused multiply-adds, DM^2/4 loads and
 // DM stores per factorisation, against two loads and a store per multiply-add of the in-place form.
-//
-// G < DM: right-looking in shared memory (several rows per lane); the upper triangle is left untouched.
 template <int G, int DM>
 __device__ __forceinline__ double chol(double* __restrict__ A, int n, double* __restrict__ rd) {
   constexpr int LD = Dim<DM>::LD;
   const int gl = lane<G>();
+  static_assert(G == DM, "one row per lane");
   double det = 1.0;
-  if (G == DM) {
+  {
     const int i = gl;
     double a[DM];
     {
@@ -301,31 +300,12 @@ __device__ __forceinline__ double chol(double* __restrict__ A, int n, double* __
     __syncwarp();
     return det;
   }
-  for (int j = 0; j < n; ++j) {
-    const double s = A[j * LD + j];
-    const double r = fast_rsqrt(s);
-    det *= s;
-    __syncwarp();
-    // column j: L[i][j] = A[i][j] * r  (i > j), diagonal = s * r
-    for (int i = j + gl; i < n; i += G) {
-      if (i == j) { A[j * LD + j] = s * r; rd[j] = r; }
-      else A[i * LD + j] *= r;
-    }
-    __syncwarp();
-    // trailing update: A[i][c] -= L[i][j] L[c][j]  for j < c <= i
-    for (int i = j + 1 + gl; i < n; i += G) {
-      const double lij = A[i * LD + j];
-      for (int c = j + 1; c <= i; ++c) A[i * LD + c] = fma(-lij, A[c * LD + j], A[i * LD + c]);
-    }
-    __syncwarp();
-  }
-  return det;
 }
 
 // X <- (L L^T)^{-1} X for nrhs columns, X stored TRANSPOSED: column c of the system is ROW c of Xt
 // (Xt[c][0..n)), one system per lane: the lane keeps its own row in registers and the L entries are
 // broadcasts.  Entries of the row beyond n must be finite (zero padding) and come back unchanged.
-// G == DM: the factor carries L^T in its upper triangle (chol above), both sweeps read rows.
+// The factor carries L^T in its upper triangle (chol above): both sweeps read rows.
 template <int G, int DM>
 __device__ __forceinline__ void chol_solve_t(const double* __restrict__ L, int n, const double* __restrict__ rd,
                                              double* __restrict__ Xt, int nrhs) {
@@ -359,28 +339,159 @@ __device__ __forceinline__ void chol_solve_t(const double* __restrict__ L, int n
 #pragma unroll
     for (int i = DM - 1; i >= 0; --i) {
       if (i < n) {
-        if (G == DM) {
-          double t0 = x[i], t1 = 0.0;
-          const double2* __restrict__ urow = reinterpret_cast<const double2*>(L + i * LD);
+        double t0 = x[i], t1 = 0.0;
+        const double2* __restrict__ urow = reinterpret_cast<const double2*>(L + i * LD);
 #pragma unroll
-          for (int l2 = (i + 1) / 2; l2 < DM / 2; ++l2) {
-            const double2 b = urow[l2];                       // zero beyond n
-            if (2 * l2 > i) t0 = fma(-b.x, x[2 * l2], t0);
-            t1 = fma(-b.y, x[2 * l2 + 1], t1);
-          }
-          x[i] = (t0 + t1) * rd[i];
-        } else {
-          double t = x[i];
-#pragma unroll
-          for (int l = i + 1; l < DM; ++l) {
-            if (l < n) t = fma(-L[l * LD + i], x[l], t);
-          }
-          x[i] = t * rd[i];
+        for (int l2 = (i + 1) / 2; l2 < DM / 2; ++l2) {
+          const double2 b = urow[l2];                         // zero beyond n
+          if (2 * l2 > i) t0 = fma(-b.x, x[2 * l2], t0);
+          t1 = fma(-b.y, x[2 * l2 + 1], t1);
         }
+        x[i] = (t0 + t1) * rd[i];
       }
     }
 #pragma unroll
     for (int l2 = 0; l2 < DM / 2; ++l2) row[l2] = make_double2(x[2 * l2], x[2 * l2 + 1]);
+  }
+}
+
+// ---- compact block-diagonal operands (DISC_MATERN).  A block-diagonal matrix with square blocks of bs <= 4
+// keeps the in-block entries of row i at Mc[i * CB + q], q < bs (CB = 4: 32-byte rows, unused entries zero);
+// l0(i) = (i / bs) * bs is the first column of the block of row i.
+constexpr int CB = 4;
+
+// y[i] = sum_q Mc[i][q] x[l0(i) + q]
+template <int G, int DM>
+__device__ __forceinline__ void mv_c(double* __restrict__ y, const double* __restrict__ Mc,
+                                     const double* __restrict__ x, int n, int bs) {
+  for (int i = lane<G>(); i < n; i += G) {
+    const int l0 = (i / bs) * bs;
+    double acc = 0.0;
+    for (int q = 0; q < bs; ++q) acc = fma(Mc[i * CB + q], x[l0 + q], acc);
+    y[i] = acc;
+  }
+}
+
+// M[i][l0(i) + q] += sign * Mc[i][q]   (own rows, in place)
+template <int G, int DM>
+__device__ __forceinline__ void add_c(double* __restrict__ M, const double* __restrict__ Mc, int n, int bs,
+                                      double sign) {
+  constexpr int LD = Dim<DM>::LD;
+  for (int i = lane<G>(); i < n; i += G) {
+    const int l0 = (i / bs) * bs;
+    for (int q = 0; q < bs; ++q) M[i * LD + l0 + q] = fma(sign, Mc[i * CB + q], M[i * LD + l0 + q]);
+  }
+}
+
+// D[i][:] = X[i][:] over all DM columns of the own rows
+template <int G, int DM>
+__device__ __forceinline__ void copy_rows(double* __restrict__ D, const double* __restrict__ X, int n) {
+  constexpr int LD = Dim<DM>::LD;
+  for (int i = lane<G>(); i < n; i += G) {
+    const double2* __restrict__ x = reinterpret_cast<const double2*>(X + i * LD);
+    double2* __restrict__ o = reinterpret_cast<double2*>(D + i * LD);
+#pragma unroll
+    for (int j2 = 0; j2 < DM / 2; ++j2) o[j2] = x[j2];
+  }
+}
+
+// C[i][:] = sum_q Mc[i][q] B[l0(i) + q][:]  (+ Addc on the diagonal blocks)   block-diagonal times dense.
+// One row per lane in registers; lanes of one block read the same rows of B.  C must not alias B.
+template <int G, int DM>
+__device__ __forceinline__ void mm_cn(double* __restrict__ C, const double* __restrict__ Mc,
+                                      const double* __restrict__ B, int n, int bs,
+                                      const double* __restrict__ Addc) {
+  constexpr int LD = Dim<DM>::LD;
+  for (int i = lane<G>(); i < n; i += G) {
+    const int l0 = (i / bs) * bs;
+    double c[DM];
+#pragma unroll
+    for (int j = 0; j < DM; ++j) c[j] = 0.0;
+    for (int q = 0; q < bs; ++q) {
+      const double a = Mc[i * CB + q];
+      const double2* __restrict__ brow = reinterpret_cast<const double2*>(B + (l0 + q) * LD);
+#pragma unroll
+      for (int j2 = 0; j2 < DM / 2; ++j2) {
+        const double2 b = brow[j2];
+        c[2 * j2] = fma(a, b.x, c[2 * j2]);
+        c[2 * j2 + 1] = fma(a, b.y, c[2 * j2 + 1]);
+      }
+    }
+    double2* __restrict__ crow = reinterpret_cast<double2*>(C + i * LD);
+#pragma unroll
+    for (int j2 = 0; j2 < DM / 2; ++j2) crow[j2] = make_double2(c[2 * j2], c[2 * j2 + 1]);
+    if (Addc)
+      for (int q = 0; q < bs; ++q) C[i * LD + l0 + q] += Addc[i * CB + q];
+  }
+}
+
+// C[i][j] = sum_q A[i][l0(j) + q] Bc[j][q]  (+ Addc on the diagonal blocks)   dense times block-diagonal^T.
+// Block by block along the row: the BS entries of the own row inside block b and the BS x BS entries of
+// block b of Bc (broadcast) give the BS outputs of the same columns, so C may be A itself (in place) and
+// nothing larger than a block is live in registers.  n must be a multiple of BS.
+template <int G, int DM, int BS>
+__device__ __forceinline__ void mm_nc_bs(double* C, const double* A, const double* __restrict__ Bc, int n,
+                                         const double* __restrict__ Addc) {
+  constexpr int LD = Dim<DM>::LD;
+  for (int i = lane<G>(); i < n; i += G) {
+    const int bi = i / BS;
+    const double* arow = A + i * LD;
+    double* crow = C + i * LD;
+#pragma unroll 2
+    for (int b = 0; b * BS < n; ++b) {
+      const int l0 = b * BS;
+      double a[BS], o[BS];
+      if (BS % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < BS / 2; ++q) {
+          const double2 t = *reinterpret_cast<const double2*>(arow + l0 + 2 * q);
+          a[2 * q] = t.x;
+          a[2 * q + 1] = t.y;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < BS; ++q) a[q] = arow[l0 + q];
+      }
+#pragma unroll
+      for (int jj = 0; jj < BS; ++jj) {
+        const double* __restrict__ brow = Bc + (l0 + jj) * CB;
+        double acc = 0.0;
+        if (BS % 2 == 0) {
+#pragma unroll
+          for (int q = 0; q < BS / 2; ++q) {
+            const double2 t = *reinterpret_cast<const double2*>(brow + 2 * q);
+            acc = fma(a[2 * q], t.x, acc);
+            acc = fma(a[2 * q + 1], t.y, acc);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < BS; ++q) acc = fma(a[q], brow[q], acc);
+        }
+        o[jj] = acc;
+      }
+      if (Addc && b == bi) {
+#pragma unroll
+        for (int jj = 0; jj < BS; ++jj) o[jj] += Addc[i * CB + jj];
+      }
+      if (BS % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < BS / 2; ++q)
+          *reinterpret_cast<double2*>(crow + l0 + 2 * q) = make_double2(o[2 * q], o[2 * q + 1]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < BS; ++q) crow[l0 + q] = o[q];
+      }
+    }
+  }
+}
+template <int G, int DM>
+__device__ __forceinline__ void mm_nc(double* C, const double* A, const double* __restrict__ Bc, int n, int bs,
+                                      const double* __restrict__ Addc) {
+  switch (bs) {
+    case 1: mm_nc_bs<G, DM, 1>(C, A, Bc, n, Addc); return;
+    case 2: mm_nc_bs<G, DM, 2>(C, A, Bc, n, Addc); return;
+    case 3: mm_nc_bs<G, DM, 3>(C, A, Bc, n, Addc); return;
+    default: mm_nc_bs<G, DM, 4>(C, A, Bc, n, Addc); return;
   }
 }
 
