@@ -339,8 +339,10 @@ def run_b200(a):
     peak, peak_src = measured_peak_gbs()
     kern = {}
     # which kernel family the C ABI dispatches this shape to (physs_api.cu: prefer_seq / rt_supported)
-    if d <= 4 or (d == 8 and sub >= 4096):
+    if d <= 4:
         kn = ("seq_filter_kernel<%d>" % d, "seq_smooth_kernel<%d>" % d)
+    elif d == 8 and sub >= 4096 and os.environ.get("PHYSS_NO_SEQ8") != "1":
+        kn = ("seq_filter_kernel<8>", "rt_smooth_kernel<8>")
     elif d <= 32:
         kn = ("rt_filter_kernel<%d>" % d, "rt_smooth_kernel<%d>" % d)
     else:
@@ -485,6 +487,7 @@ def run_c3(a):
     prior = sdes.BatchedMaternSDE(4, np.exp(rng.uniform(np.log(0.5), np.log(2.0), (B, nblk))) * (10 * DT0),
                                   full_state_obs=(m == d))
     t0, t1 = timeshard.time_ranges(T, world)[rank]
+    L = ops.even_chunk_len(t1 - t0, L)            # a chunk length that divides the range: no ragged launch
     tt = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=dev)   # noqa: E731
     Yh = np.sin(0.01 * np.arange(t0, t1))[None, :, None] + 0.3 * rng.normal(size=(B, t1 - t0, m))
     Y = tt(Yh)

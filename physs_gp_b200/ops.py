@@ -240,7 +240,21 @@ def default_chunk_len(B, T, d=8):
     want_chunks = max(1, (target + B - 1) // B)
     # not below 128 steps: the fix-up passes contract the O(jitter) boundary error by the filter's forgetting
     # over ONE chunk, so chunks shorter than the mixing time cost more passes than they gain in parallelism
-    return int(min(T, max(128, -(-T // want_chunks))))
+    return even_chunk_len(T, int(min(T, max(128, -(-T // want_chunks)))))
+
+
+def even_chunk_len(T, L, slack=0.25):
+    """The chunk length closest to L (within +-slack) that divides T, else L.  Without a ragged last chunk
+    every pass of the scan is ONE launch per kernel: the ragged chunk runs as a launch of its own (its
+    lane groups take fewer steps than the others of a warp would), serialised behind the main one."""
+    T, L = int(T), int(L)
+    if L <= 0 or T <= L or T % L == 0:
+        return L
+    best = None
+    for c in range(max(1, int(L * (1 - slack))), int(L * (1 + slack)) + 1):
+        if T % c == 0 and (best is None or abs(c - L) < abs(best - L)):
+            best = c
+    return best if best is not None else L
 
 
 def pscan_workspace(B, T, d, chunk_len, dev):
