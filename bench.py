@@ -341,8 +341,6 @@ def run_b200(a):
     # which kernel family the C ABI dispatches this shape to (physs_api.cu: prefer_seq / rt_supported)
     if d <= 4:
         kn = ("seq_filter_kernel<%d>" % d, "seq_smooth_kernel<%d>" % d)
-    elif d == 8 and sub >= 4096 and os.environ.get("PHYSS_NO_SEQ8") != "1":
-        kn = ("seq_filter_kernel<8>", "rt_smooth_kernel<8>")
     elif d <= 32:
         kn = ("rt_filter_kernel<%d>" % d, "rt_smooth_kernel<%d>" % d)
     else:

@@ -30,17 +30,15 @@ static bool force_grp(int d) {
   return on && d > 4;
 }
 
-// d = 8 is covered by both families.  Measured on B200: one thread per series with
-// local-memory tiles wins 3x over the lane-group kernels when thousands of series are in flight and the
-// update is light (m <= 4); with few (series, chunk) pairs or full-state updates its per-step dependency
-// chain (thousands of instructions through local memory) makes it 3-30x slower.
+// d <= 4: one thread per series, everything in registers.  d = 8 is covered by both families:
 static bool prefer_seq(int d, int m, int64_t B, int64_t nchunk, bool smoother) {
   if (d <= 4) return true;
-  static const bool no_seq8 = [] { const char* e = getenv("PHYSS_NO_SEQ8"); return e && e[0] == '1'; }();
-  if (no_seq8) return false;
-  // d = 8, measured at 8192 series x 10000 steps: filter 53 ms (thread per series) vs 94 ms (lane group),
-  // smoother 176 ms vs 156 ms -> the smoother goes to the lane-group kernel
-  return !smoother && nchunk == 0 && B >= 4096 && m <= 4;
+  // d = 8 thread-per-series variant: superseded by the lane-group kernels with compile-time shapes (measured at
+  // 7104 series x 10000 steps: filter 53 ms vs 32 ms, smoother 176 ms vs 72 ms); PHYSS_SEQ8=1 keeps it reachable
+  // for A-B timing
+  static const bool seq8 = [] { const char* e = getenv("PHYSS_SEQ8"); return e && e[0] == '1'; }();
+  (void)smoother;
+  return seq8 && nchunk == 0 && B >= 4096 && m <= 4;
 }
 
 int run_filter_any(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity, const SeqFilterArgs& a) {

@@ -203,7 +203,10 @@ __device__ __forceinline__ void rt_load_Pc(double* __restrict__ Pc, const double
 }
 
 // ------------------------------------------------------------------------------------------ filter
-template <int G, int DM, bool GIVEN>
+// DC / SC / MC: compile-time state dim / Matern block size / observation dim (0 = read from the layout).
+// The full-size Matern-7/2 shapes (d == DM, s == 4) get their own instantiation: loop bounds, block
+// indices and the block-size switch fold to constants.
+template <int G, int DM, bool GIVEN, int DC = 0, int SC = 0, int MC = 0>
 __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const bool hid) {
   extern __shared__ __align__(16) double smem[];
   constexpr int LD = Dim<DM>::LD;
@@ -214,7 +217,8 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
   const int64_t bb = wk.b, vs = wk.v, t0 = wk.t0, T = wk.T;
   const int gl = lane<G>();
   double* sm = smem + (size_t)g_in_block * L.total;
-  const int d = L.d, m = L.m, s = L.s;
+  const int d = DC ? DC : L.d, m = MC ? MC : L.m, s = SC ? SC : L.s;
+  const int nblk = (DC && SC) ? DC / SC : L.nblk;
 
   for (int idx = gl; idx < L.total; idx += G) sm[idx] = 0.0;       // zero padding is an invariant
   __syncwarp();
@@ -233,7 +237,7 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
   }
   if (!GIVEN) {
     rt_load_Pc<G, DM>(Pc, p.Pinf + bb * p.Pinf_bs, d, s);
-    for (int i = gl; i < L.nblk; i += G) lam[i] = p.lam[bb * p.lam_bs + i];
+    for (int i = gl; i < nblk; i += G) lam[i] = p.lam[bb * p.lam_bs + i];
   }
   if (!hid) g2s<G, DM>(H, p.H + bb * p.H_bs, m, d);
   const double* dtp = p.dt + bb * p.dt_bs + t0;
@@ -284,7 +288,7 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
       __syncwarp();
       mm_nt<G, DM>(P, W2, Ak, d, d, Qk, 1.0);                              // A P A^T + Q
     } else {
-      rt_matern_Ac<G, DM>(Ac, s, L.nblk, lam, dt);
+      rt_matern_Ac<G, DM>(Ac, s, nblk, lam, dt);
       add_c<G, DM>(P, Pc, d, s, -1.0);                                      // dP = P - Pinf (in place)
       __syncwarp();
       mv_c<G, DM>(mp, Ac, mv_, d, s);
@@ -429,7 +433,7 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
 }
 
 // ---------------------------------------------------------------------------------------- smoother
-template <int G, int DM, bool GIVEN>
+template <int G, int DM, bool GIVEN, int DC = 0, int SC = 0>
 __global__ void rt_smooth_kernel(const SeqSmoothArgs p, const RtLayout L) {
   extern __shared__ __align__(16) double smem[];
   constexpr int LD = Dim<DM>::LD;
@@ -440,7 +444,8 @@ __global__ void rt_smooth_kernel(const SeqSmoothArgs p, const RtLayout L) {
   const int64_t bb = wk.b, vs = wk.v, t0 = wk.t0, T = wk.T;
   const int gl = lane<G>();
   double* sm = smem + (size_t)g_in_block * L.total;
-  const int d = L.d, mo = L.mo, s = L.s;
+  const int d = DC ? DC : L.d, mo = L.mo, s = SC ? SC : L.s;
+  const int nblk = (DC && SC) ? DC / SC : L.nblk;
   const int mp_ = (mo == 0) ? d : mo;
 
   for (int idx = gl; idx < L.total; idx += G) sm[idx] = 0.0;
@@ -454,7 +459,7 @@ __global__ void rt_smooth_kernel(const SeqSmoothArgs p, const RtLayout L) {
 
   if (!GIVEN) {
     rt_load_Pc<G, DM>(Pc, p.Pinf + bb * p.Pinf_bs, d, s);
-    for (int i = gl; i < L.nblk; i += G) lam[i] = p.lam[bb * p.lam_bs + i];
+    for (int i = gl; i < nblk; i += G) lam[i] = p.lam[bb * p.lam_bs + i];
   }
   if (mo > 0) g2s<G, DM>(Ho, p.Hout, mo, d);
   const double* dtp = p.dt + bb * p.dt_bs + t0;
@@ -547,7 +552,7 @@ __global__ void rt_smooth_kernel(const SeqSmoothArgs p, const RtLayout L) {
       __syncwarp();
       mm_nn<G, DM, false>(W2, Ak, W1, d, d, Qk, 1.0);                          // A (Pf A^T) + Q
     } else {
-      rt_matern_Ac<G, DM>(Ac, s, L.nblk, lam, dt);
+      rt_matern_Ac<G, DM>(Ac, s, nblk, lam, dt);
       copy_rows<G, DM>(W3, Pf, d);
       add_c<G, DM>(W3, Pc, d, s, -1.0);                                         // dPf = Pf - Pinf
       __syncwarp();
@@ -598,11 +603,18 @@ int rt_run_filter(cudaStream_t st, const SeqFilterArgs& a, int d, int m, int nbl
   const int gpb = threads / G;
   const int64_t ngroups = a.B * (a.nchunk > 0 ? a.chunk_count : 1);
   const int64_t grid = (ngroups + gpb - 1) / gpb;
-  cudaError_t e = cudaFuncSetAttribute(rt_filter_kernel<G, DM, GIVEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
-  if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(rt_filter_kernel)");
-  rt_filter_kernel<G, DM, GIVEN><<<(unsigned)grid, threads, smem, st>>>(a, L, hid);
-  return cuda_status(cudaGetLastError(), "rt_filter_kernel launch");
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(rt_filter_kernel)");
+    kern<<<(unsigned)grid, threads, smem, st>>>(a, L, hid);
+    return cuda_status(cudaGetLastError(), "rt_filter_kernel launch");
+  };
+  if (!GIVEN && d == DM && L.s == 4) {
+    if (m == 1) return launch(rt_filter_kernel<G, DM, GIVEN, GIVEN ? 0 : DM, GIVEN ? 0 : 4, GIVEN ? 0 : 1>);
+    if (m == d) return launch(rt_filter_kernel<G, DM, GIVEN, GIVEN ? 0 : DM, GIVEN ? 0 : 4, GIVEN ? 0 : DM>);
+    return launch(rt_filter_kernel<G, DM, GIVEN, GIVEN ? 0 : DM, GIVEN ? 0 : 4, 0>);
+  }
+  return launch(rt_filter_kernel<G, DM, GIVEN>);
 }
 
 template <int G, int DM, bool GIVEN>
@@ -615,11 +627,14 @@ int rt_run_smooth(cudaStream_t st, const SeqSmoothArgs& a, int d, int mo, int nb
   const int gpb = threads / G;
   const int64_t ngroups = a.B * (a.nchunk > 0 ? a.chunk_count : 1);
   const int64_t grid = (ngroups + gpb - 1) / gpb;
-  cudaError_t e = cudaFuncSetAttribute(rt_smooth_kernel<G, DM, GIVEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
-  if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(rt_smooth_kernel)");
-  rt_smooth_kernel<G, DM, GIVEN><<<(unsigned)grid, threads, smem, st>>>(a, L);
-  return cuda_status(cudaGetLastError(), "rt_smooth_kernel launch");
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(rt_smooth_kernel)");
+    kern<<<(unsigned)grid, threads, smem, st>>>(a, L);
+    return cuda_status(cudaGetLastError(), "rt_smooth_kernel launch");
+  };
+  if (!GIVEN && d == DM && L.s == 4) return launch(rt_smooth_kernel<G, DM, GIVEN, GIVEN ? 0 : DM, GIVEN ? 0 : 4>);
+  return launch(rt_smooth_kernel<G, DM, GIVEN>);
 }
 
 

@@ -43,7 +43,7 @@ static RtSumLayout rt_sum_layout(int d, int m, int nblk, bool given, bool smooth
   return L;
 }
 
-template <int G, int DM, bool GIVEN>
+template <int G, int DM, bool GIVEN, int DC = 0, int SC = 0, int MC = 0>
 __global__ void rt_filter_summary_kernel(const SeqFilterArgs p, const RtSumLayout L, const bool hid,
                                          const int64_t cfirst, const int64_t ccount, double* __restrict__ elems) {
   extern __shared__ __align__(16) double smem[];
@@ -59,7 +59,8 @@ __global__ void rt_filter_summary_kernel(const SeqFilterArgs p, const RtSumLayou
   const int64_t T = (p.chunk_len < p.T - t0) ? p.chunk_len : (p.T - t0);
   const int gl = lane<G>();
   double* sm = smem + (size_t)g_in_block * L.total;
-  const int d = L.d, m = L.m, s = L.s;
+  const int d = DC ? DC : L.d, m = MC ? MC : L.m, s = SC ? SC : L.s;   // compile-time shapes as in rt_filter_kernel
+  const int nblk = (DC && SC) ? DC / SC : L.nblk;
   for (int idx = gl; idx < L.total; idx += G) sm[idx] = 0.0;
   __syncwarp();
   double* C = sm + L.C; double* A = sm + L.A; double* Qm = sm + L.Qm; double* W1 = sm + L.W1; double* W2 = sm + L.W2;
@@ -71,7 +72,7 @@ __global__ void rt_filter_summary_kernel(const SeqFilterArgs p, const RtSumLayou
   for (int i = gl; i < d; i += G) Acc[i * LD + i] = 1.0;     // conditional element of an empty interval
   if (!GIVEN) {
     g2s<G, DM>(Qm, p.Pinf + bb * p.Pinf_bs, d, d);
-    for (int i = gl; i < L.nblk; i += G) lam[i] = p.lam[bb * p.lam_bs + i];
+    for (int i = gl; i < nblk; i += G) lam[i] = p.lam[bb * p.lam_bs + i];
   }
   if (!hid) g2s<G, DM>(H, p.H + bb * p.H_bs, m, d);
   const double* dtp = p.dt + bb * p.dt_bs + t0;
@@ -111,7 +112,7 @@ __global__ void rt_filter_summary_kernel(const SeqFilterArgs p, const RtSumLayou
       __syncwarp();
       mm_nt<G, DM>(C, W2, Ak, d, d, Qk, 1.0);
     } else {
-      rt_matern_A<G, DM>(A, s, L.nblk, lam, dt);
+      rt_matern_A<G, DM>(A, s, nblk, lam, dt);
       for (int i = gl; i < d; i += G) {
 #pragma unroll
         for (int j = 0; j < DM; ++j) W1[i * LD + j] = C[i * LD + j] - Qm[i * LD + j];
@@ -197,7 +198,7 @@ __global__ void rt_filter_summary_kernel(const SeqFilterArgs p, const RtSumLayou
   }
 }
 
-template <int G, int DM, bool GIVEN>
+template <int G, int DM, bool GIVEN, int DC = 0, int SC = 0>
 __global__ void rt_smooth_summary_kernel(const SeqSmoothArgs p, const RtSumLayout L, double* __restrict__ elems) {
   extern __shared__ __align__(16) double smem[];
   constexpr int LD = Dim<DM>::LD;
@@ -212,7 +213,8 @@ __global__ void rt_smooth_summary_kernel(const SeqSmoothArgs p, const RtSumLayou
   const int64_t T = (p.chunk_len < p.T - t0) ? p.chunk_len : (p.T - t0);
   const int gl = lane<G>();
   double* sm = smem + (size_t)g_in_block * L.total;
-  const int d = L.d, s = L.s;
+  const int d = DC ? DC : L.d, s = SC ? SC : L.s;
+  const int nblk = (DC && SC) ? DC / SC : L.nblk;
   for (int idx = gl; idx < L.total; idx += G) sm[idx] = 0.0;
   __syncwarp();
   double* Ls = sm + L.C; double* A = sm + L.A; double* Qm = sm + L.Qm; double* W1 = sm + L.W1; double* W2 = sm + L.W2;
@@ -222,7 +224,7 @@ __global__ void rt_smooth_summary_kernel(const SeqSmoothArgs p, const RtSumLayou
   for (int i = gl; i < d; i += G) E[i * LD + i] = 1.0;
   if (!GIVEN) {
     g2s<G, DM>(Qm, p.Pinf + bb * p.Pinf_bs, d, d);
-    for (int i = gl; i < L.nblk; i += G) lam[i] = p.lam[bb * p.lam_bs + i];
+    for (int i = gl; i < nblk; i += G) lam[i] = p.lam[bb * p.lam_bs + i];
   }
   const double* dtp = p.dt + bb * p.dt_bs + t0;
   const double* Ap = GIVEN ? p.A + bb * p.A_bs + t0 * d * d : nullptr;
@@ -259,7 +261,7 @@ __global__ void rt_smooth_summary_kernel(const SeqSmoothArgs p, const RtSumLayou
       __syncwarp();
       mm_nn<G, DM, false>(W2, Ak, W1, d, d, Qk, 1.0);
     } else {
-      rt_matern_A<G, DM>(A, s, L.nblk, lam, dt);
+      rt_matern_A<G, DM>(A, s, nblk, lam, dt);
       sub_rows<G, DM>(W3, Pf, Qm, d);
       __syncwarp();
       mv<G, DM, false>(mpred, A, mf, d, d, nullptr, 1.0, s);
@@ -307,11 +309,18 @@ int rt_run_filter_summary(cudaStream_t st, const SeqFilterArgs& a, int d, int m,
   if (smem > 200 * 1024) return set_error(PHYSS_ERR_UNSUPPORTED, "rt filter summary: shared memory");
   const int gpb = threads / G;
   const int64_t grid = (a.B * ccount + gpb - 1) / gpb;
-  cudaError_t e = cudaFuncSetAttribute(rt_filter_summary_kernel<G, DM, GIVEN>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(rt_filter_summary_kernel)");
-  rt_filter_summary_kernel<G, DM, GIVEN><<<(unsigned)grid, threads, smem, st>>>(a, L, hid, cfirst, ccount, elems);
-  return cuda_status(cudaGetLastError(), "rt_filter_summary_kernel launch");
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(rt_filter_summary_kernel)");
+    kern<<<(unsigned)grid, threads, smem, st>>>(a, L, hid, cfirst, ccount, elems);
+    return cuda_status(cudaGetLastError(), "rt_filter_summary_kernel launch");
+  };
+  if (!GIVEN && d == DM && L.s == 4) {
+    if (m == 1) return launch(rt_filter_summary_kernel<G, DM, GIVEN, GIVEN ? 0 : DM, GIVEN ? 0 : 4, GIVEN ? 0 : 1>);
+    if (m == d) return launch(rt_filter_summary_kernel<G, DM, GIVEN, GIVEN ? 0 : DM, GIVEN ? 0 : 4, GIVEN ? 0 : DM>);
+    return launch(rt_filter_summary_kernel<G, DM, GIVEN, GIVEN ? 0 : DM, GIVEN ? 0 : 4, 0>);
+  }
+  return launch(rt_filter_summary_kernel<G, DM, GIVEN>);
 }
 
 template <int G, int DM, bool GIVEN>
@@ -323,11 +332,14 @@ int rt_run_smooth_summary(cudaStream_t st, const SeqSmoothArgs& a, int d, int nb
   if (smem > 200 * 1024) return set_error(PHYSS_ERR_UNSUPPORTED, "rt smoother summary: shared memory");
   const int gpb = threads / G;
   const int64_t grid = (a.B * a.chunk_count + gpb - 1) / gpb;
-  cudaError_t e = cudaFuncSetAttribute(rt_smooth_summary_kernel<G, DM, GIVEN>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(rt_smooth_summary_kernel)");
-  rt_smooth_summary_kernel<G, DM, GIVEN><<<(unsigned)grid, threads, smem, st>>>(a, L, elems);
-  return cuda_status(cudaGetLastError(), "rt_smooth_summary_kernel launch");
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(rt_smooth_summary_kernel)");
+    kern<<<(unsigned)grid, threads, smem, st>>>(a, L, elems);
+    return cuda_status(cudaGetLastError(), "rt_smooth_summary_kernel launch");
+  };
+  if (!GIVEN && d == DM && L.s == 4) return launch(rt_smooth_summary_kernel<G, DM, GIVEN, GIVEN ? 0 : DM, GIVEN ? 0 : 4>);
+  return launch(rt_smooth_summary_kernel<G, DM, GIVEN>);
 }
 
 

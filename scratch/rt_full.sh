@@ -9,9 +9,10 @@ try:
 except Exception as e: print('$name failed', e)
 PY
 }
+timeout 900 python -m pytest tests/test_gpu_grp.py tests/test_gpu_pscan.py tests/test_gpu_golden.py -x -q 2>&1 | tail -2
 C="--steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
-run g_c5_d32 python bench.py --state-dim 32 --series 1024 --sub-batch 512 $C
-run g_c5_d16 python bench.py --state-dim 16 --series 4096 --sub-batch 2048 $C
-run g_c5_d8 python bench.py --state-dim 8 --series 16384 --sub-batch 8192 $C
-PHYSS_NO_SEQ8=1 run g_c5_d8_rt python bench.py --state-dim 8 --series 16384 --sub-batch 8192 $C
+run g_c5_d32 python bench.py --state-dim 32 --series 1184 --sub-batch 592 $C
+run g_c5_d16 python bench.py --state-dim 16 --series 4736 --sub-batch 2368 $C
+run g_c5_d8 python bench.py --state-dim 8 --series 14208 --sub-batch 7104 $C
+PHYSS_NO_SEQ8=1 run g_c5_d8_rt python bench.py --state-dim 8 --series 14208 --sub-batch 7104 $C
 run g_c3 python bench.py --workload c3 --steps 3 --warmup 3 --no-cpu-baseline
