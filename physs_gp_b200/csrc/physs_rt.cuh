@@ -383,6 +383,45 @@ __device__ __forceinline__ void add_c(double* __restrict__ M, const double* __re
   }
 }
 
+// Qc = Pc - Ac Pc Ac^T block by block (kernels/kernel.py:207-209, the reference's Q_k = Pinf - A Pinf A^T), all
+// three compact.  The lane of row i reads the Ac / Pc rows of its own block (written by other lanes: sync first).
+template <int G, int DM>
+__device__ __forceinline__ void q_c(double* __restrict__ Qc, const double* __restrict__ Ac,
+                                    const double* __restrict__ Pc, int n, int bs) {
+  for (int i = lane<G>(); i < n; i += G) {
+    const int l0 = (i / bs) * bs;
+    double t[CB];
+#pragma unroll
+    for (int b = 0; b < CB; ++b) t[b] = 0.0;
+    for (int a = 0; a < bs; ++a) {
+      const double aia = Ac[i * CB + a];
+#pragma unroll
+      for (int b = 0; b < CB; ++b) t[b] = fma(aia, Pc[(l0 + a) * CB + b], t[b]);   // unused entries are zero
+    }
+    for (int q = 0; q < bs; ++q) {
+      double acc = Pc[i * CB + q];
+#pragma unroll
+      for (int b = 0; b < CB; ++b) acc = fma(-t[b], Ac[(l0 + q) * CB + b], acc);
+      Qc[i * CB + q] = acc;
+    }
+  }
+}
+
+// D[i][:] -= Y[i][:] over all DM columns of the own rows (in place)
+template <int G, int DM>
+__device__ __forceinline__ void sub_rows_inplace(double* __restrict__ D, const double* __restrict__ Y, int n) {
+  constexpr int LD = Dim<DM>::LD;
+  for (int i = lane<G>(); i < n; i += G) {
+    const double2* __restrict__ y = reinterpret_cast<const double2*>(Y + i * LD);
+    double2* __restrict__ o = reinterpret_cast<double2*>(D + i * LD);
+#pragma unroll
+    for (int j2 = 0; j2 < DM / 2; ++j2) {
+      const double2 a = o[j2], b = y[j2];
+      o[j2] = make_double2(a.x - b.x, a.y - b.y);
+    }
+  }
+}
+
 // D[i][:] = X[i][:] over all DM columns of the own rows
 template <int G, int DM>
 __device__ __forceinline__ void copy_rows(double* __restrict__ D, const double* __restrict__ X, int n) {

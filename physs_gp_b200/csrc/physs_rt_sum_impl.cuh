@@ -304,14 +304,14 @@ int rt_run_filter_summary(cudaStream_t st, const SeqFilterArgs& a, int d, int m,
                                  int64_t cfirst, int64_t ccount, double* elems) {
   const RtSumLayout L = rt_sum_layout<DM>(d, m, GIVEN ? 0 : nblk, GIVEN, false);
   const size_t per_group = (size_t)L.total * sizeof(double);
-  const int threads = rt_pick_threads(G, per_group);
-  const size_t smem = per_group * (threads / G);
-  if (smem > 200 * 1024) return set_error(PHYSS_ERR_UNSUPPORTED, "rt filter summary: shared memory");
-  const int gpb = threads / G;
-  const int64_t grid = (a.B * ccount + gpb - 1) / gpb;
+  const int64_t ngroups = a.B * ccount;
   auto launch = [&](auto kern) -> int {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(rt_filter_summary_kernel)");
+    int threads = 0;
+    size_t smem = 0;
+    const int rc = rt_configure(kern, G, per_group, &threads, &smem, "rt_filter_summary_kernel: configuration");
+    if (rc) return rc;
+    const int gpb = threads / G;
+    const int64_t grid = (ngroups + gpb - 1) / gpb;
     kern<<<(unsigned)grid, threads, smem, st>>>(a, L, hid, cfirst, ccount, elems);
     return cuda_status(cudaGetLastError(), "rt_filter_summary_kernel launch");
   };
@@ -327,14 +327,14 @@ template <int G, int DM, bool GIVEN>
 int rt_run_smooth_summary(cudaStream_t st, const SeqSmoothArgs& a, int d, int nblk, double* elems) {
   const RtSumLayout L = rt_sum_layout<DM>(d, 1, GIVEN ? 0 : nblk, GIVEN, true);
   const size_t per_group = (size_t)L.total * sizeof(double);
-  const int threads = rt_pick_threads(G, per_group);
-  const size_t smem = per_group * (threads / G);
-  if (smem > 200 * 1024) return set_error(PHYSS_ERR_UNSUPPORTED, "rt smoother summary: shared memory");
-  const int gpb = threads / G;
-  const int64_t grid = (a.B * a.chunk_count + gpb - 1) / gpb;
+  const int64_t ngroups = a.B * a.chunk_count;
   auto launch = [&](auto kern) -> int {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(rt_smooth_summary_kernel)");
+    int threads = 0;
+    size_t smem = 0;
+    const int rc = rt_configure(kern, G, per_group, &threads, &smem, "rt_smooth_summary_kernel: configuration");
+    if (rc) return rc;
+    const int gpb = threads / G;
+    const int64_t grid = (ngroups + gpb - 1) / gpb;
     kern<<<(unsigned)grid, threads, smem, st>>>(a, L, elems);
     return cuda_status(cudaGetLastError(), "rt_smooth_summary_kernel launch");
   };

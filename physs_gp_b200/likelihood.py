@@ -12,6 +12,10 @@ class Gaussian:
     def R(self, Nt, m):
         return self.variance_scalar * np.eye(m)[None]          # [1, m, m], broadcast over time
 
+    def R_predict(self, Nt, NS, unique_idx, m):
+        """Noise for the merged train + test grid of `predict_f` (sde_gp.py get_likelihood_for_prediction)."""
+        return self.R(len(unique_idx), m)
+
 
 class BlockDiagonalGaussian:
     """Per-step full m x m noise blocks [Nt, m, m] (the CVI site covariance V-tilde lives here,
@@ -26,6 +30,18 @@ class BlockDiagonalGaussian:
 
     def R(self, Nt, m):
         return self._variance
+
+    def R_predict(self, Nt, NS, unique_idx, m):
+        """Per-step blocks on the merged grid: the training blocks where a training row survives, identity at
+        the test rows (their observations are NaN: the block only enters the masked innovation covariance)."""
+        import torch
+        V = self._variance
+        if isinstance(V, torch.Tensor):
+            eye = torch.eye(m, dtype=V.dtype, device=V.device).expand(*V.shape[:-3], NS, m, m)
+            return torch.cat([V, eye], dim=-3)[..., torch.as_tensor(unique_idx, device=V.device), :, :]
+        V = np.asarray(V)
+        eye = np.broadcast_to(np.eye(m), (*V.shape[:-3], NS, m, m))
+        return np.concatenate([V, eye], axis=-3)[..., unique_idx, :, :]
 
 
 def get_R_R_inv(likelihood, Nt, m):

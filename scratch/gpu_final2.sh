@@ -6,8 +6,8 @@ python bench.py --workload c3cvi --steps 3 --warmup 3 > gpurun_out/f_c3cvi.json 
 python bench.py --workload cvi --steps 3 --warmup 3 > gpurun_out/f_cvi.json 2> gpurun_out/f_cvi.err; tail -c 300 gpurun_out/f_cvi.err
 C="--steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
 python bench.py --state-dim 8 --series 14208 --sub-batch 7104 $C > gpurun_out/f_c5_d8.json 2>gpurun_out/f_c5_d8.err
-python bench.py --state-dim 16 --series 4736 --sub-batch 2368 $C > gpurun_out/f_c5_d16.json 2>gpurun_out/f_c5_d16.err
-python bench.py --state-dim 32 --series 1184 --sub-batch 592 $C > gpurun_out/f_c5_d32.json 2>gpurun_out/f_c5_d32.err
+python bench.py --state-dim 16 --series 5328 --sub-batch 2664 $C > gpurun_out/f_c5_d16.json 2>gpurun_out/f_c5_d16.err
+python bench.py --state-dim 32 --series 1480 --sub-batch 740 $C > gpurun_out/f_c5_d32.json 2>gpurun_out/f_c5_d32.err
 for f in f_c5 f_c3 f_c3cvi f_cvi f_c5_d8 f_c5_d16 f_c5_d32; do python - <<PY
 import json
 try:
