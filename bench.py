@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "cvi", "c2", "c3cvi"],
+    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "cvi", "c2", "c3cvi", "grad"],
                     help="c5 (default, the headline metric): batched sweep; c3: one long series, parallel-in-time "
                          "scan, time-sharded over the ranks; cvi: CVI ELBO + natural-gradient step (config 4)")
     ap.add_argument("--chunk-len", type=int, default=256, help="c3: steps per scan chunk")
@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--cpu-sample-series", type=int, default=0, help="series in the CPU sample (0 = auto)")
     a = ap.parse_args()
     dflt = {"c5": (SERIES_TOTAL, T_STEPS, 4), "c3": (1, 1000000, 8), "cvi": (1000, T_STEPS, 2),
-            "c2": (200, 5000, 400), "c3cvi": (1, 1000000, 4)}[a.workload]
+            "c2": (200, 5000, 400), "c3cvi": (1, 1000000, 4), "grad": (32768, T_STEPS, 4)}[a.workload]
     a.series = dflt[0] if a.series is None else a.series
     a.T = dflt[1] if a.T is None else a.T
     a.state_dim = dflt[2] if a.state_dim is None else a.state_dim
@@ -868,6 +868,85 @@ def run_c3cvi(a):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ grad: lml value + hyper-parameter gradient
+def run_grad(a):
+    """value and gradient of the log marginal likelihood for a batch of series (the C5
+    shape: Matern-7/2, d = 4, m = 1, per-series lengthscales, 5 % missing) -- one forward filter launch and one
+    reverse launch (physs_kf_filter_vjp_f64).  Metric: state-steps/s of the (value, gradient) pair."""
+    import torch
+    from physs_gp_b200 import ops, sdes
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        raise SystemExit("--workload grad is a single-GPU workload")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    d, T, B = a.state_dim, a.T, a.series
+    nblk = d // 4
+    ls_all, steps = make_hypers(B, nblk)
+    steps = steps[:T] if T <= T_STEPS else np.resize(steps, T)
+    prior = sdes.BatchedMaternSDE(4, ls_all)
+    lam = torch.as_tensor(prior.lam(), device=dev)
+    Pinf = torch.as_tensor(prior.P_inf(), device=dev)
+    H = torch.as_tensor(prior.H(), device=dev)
+    m0 = torch.zeros((1, d), dtype=torch.float64, device=dev)
+    dt_f = torch.as_tensor(np.hstack([0.0, steps[1:]]), device=dev)
+    R = torch.full((1, 1, 1, 1), NOISE_VAR, dtype=torch.float64, device=dev)
+    Y = device_observations(B, T, dev, seed=1000)
+    disc = ops.Disc.matern(nblk, lam, Pinf)
+    mf = ops.empty_steps(B, T, (d,), dev, True)
+    Pf = ops.empty_steps(B, T, (d, d), dev, True)
+    ev = []
+
+    def step(record):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if record else None
+        if record:
+            e[0].record()
+        lml, _, _ = ops.kf_filter(dt_f, Y, R, H, m0, Pinf, disc, jitter=1e-5, out=(mf, Pf))
+        if record:
+            e[1].record()
+        g = ops.kf_filter_vjp(dt_f, Y, R, H, m0, Pinf, disc, mf, Pf, jitter=1e-5)
+        if record:
+            e[2].record()
+            ev.append(e)
+        return lml, g
+
+    for _ in range(a.warmup):
+        step(False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(a.steps):
+        lml, g = step(True)
+    t1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = t0.elapsed_time(t1)
+    assert torch.isfinite(lml).all() and torch.isfinite(g["glam"]).all()
+    value = B * T * a.steps / (ms * 1e-3)
+    f_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    v_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    peak, peak_src = measured_peak_gbs()
+    fb = 8 * (d * d + d + 3)                       # filter: y, R, dt in; (m, P) out
+    vb = 8 * (d * d + d + 3)                       # reverse: (m, P)[k-1], y, R, dt in; reductions stay on chip
+    kern = {"seq_filter_kernel<%d>" % d: {"avg_ms": f_ms, "achieved_gbs": B * T * fb / (f_ms * 1e-3) / 1e9},
+            "kf_vjp_kernel<%d>" % d: {"avg_ms": v_ms, "achieved_gbs": B * T * vb / (v_ms * 1e-3) / 1e9}}
+    dom = max(kern, key=lambda k: kern[k]["avg_ms"])
+    line = {"metric": "lml value+gradient state-steps/sec (fp64)", "value": value, "unit": "state-steps/s",
+            "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "grad: %d series x %d steps, Matern-7/2 (state dim %d), m=1, 5%% missing: lml and its "
+                                   "gradient w.r.t. (lam, Pinf, H, R, m0, P0) per series" % (B, T, d),
+                       "series": B, "T": T, "state_dim": d, "layout": "time-major",
+                       "l2": "per-launch working set >> 126 MB L2"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak,
+                         "unit": "GB/s", "frac": kern[dom]["achieved_gbs"] / peak, "peak_source": peak_src,
+                         "traffic": None, "bytes_per_state_step": {"filter": fb, "reverse": vb}, "kernels": kern},
+            "cpu_baseline": None, "e2e": None, "clocks": clocks, "gpu_launches": 2 * a.steps}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -880,6 +959,8 @@ def main():
         run_c3(a)
     elif a.workload == "cvi":
         run_cvi(a)
+    elif a.workload == "grad":
+        run_grad(a)
     else:
         run_b200(a)
 

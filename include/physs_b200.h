@@ -115,6 +115,37 @@ int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_bstrid
                          double jitter,
                          double* ms, double* Ps);
 
+/* Reverse pass (vector-Jacobian product) of physs_kf_filter_f64's lml: d lml[b] / d (inputs), scaled by g_lml[b].
+ * Replaces `jax.jacrev` / `jax.grad` THROUGH filter('sequential') in the reference's hyper-parameter steps
+ * (trainers/trainer.py:43,128-136; trainers/standard.py:58-91): the backward half of a `jax.custom_vjp` around
+ * the filter call.  Same inputs as physs_kf_filter_f64 plus its outputs (mf, Pf); every matrix
+ * entry counts as an independent variable (what autodiff of the reference's formulation gives, K from
+ * solve(S, M H P_)).  Supported: d <= 4, m == 1 (physs_kf_vjp_supported).
+ *   g_lml  [B] or NULL (= 1)
+ *   DISC_GIVEN : gA, gQ [B, T, d, d] in the step layout (required)
+ *   DISC_MATERN: glam [B, nblk], gPinf [B, d, d] (required): the chain through A_k = expm(F(lam) dt_k) (closed
+ *                forms) and Q_k = Pinf - A_k Pinf A_k^T (kernels/kernel.py:207-209) is folded on chip
+ *   gH [B, m, d], gR_step [B, T, m, m] (step layout), gR_sum [B, m, m], gm0 [B, d], gP0 [B, d, d]: NULL = skip
+ */
+int physs_kf_vjp_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk);
+int physs_kf_filter_vjp_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                            int32_t d, int32_t m,
+                            int32_t disc_mode, int32_t nblk,
+                            const double* A, int64_t A_bstride,
+                            const double* Q, int64_t Q_bstride,
+                            const double* lam, int64_t lam_bstride,
+                            const double* dt, int64_t dt_bstride,
+                            const double* Pinf, int64_t Pinf_bstride,
+                            const double* m0, int64_t m0_bstride,
+                            const double* P0, int64_t P0_bstride,
+                            const double* H, int64_t H_bstride,
+                            const double* Y,
+                            const double* R, int64_t R_bstride, int64_t R_tstride,
+                            double jitter,
+                            const double* mf, const double* Pf, const double* g_lml,
+                            double* gA, double* gQ, double* glam, double* gPinf, double* gH,
+                            double* gR_step, double* gR_sum, double* gm0, double* gP0);
+
 /* ------------------------------------------------------------------------------------------------
  * Parallel-in-time forms.  Replace filter('parallel') / smoother('parallel')
  * (computation/filters/parallel_kalman_filter.py:225-336 with the elements :73-175 and the operator

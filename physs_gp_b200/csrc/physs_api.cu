@@ -74,7 +74,7 @@ static inline bool step_strides_ok(int64_t B, int64_t T, int64_t bs, int64_t ts)
 
 extern "C" {
 
-int physs_abi_version(void) { return 4; }
+int physs_abi_version(void) { return 5; }
 
 const char* physs_last_error(void) { return g_err; }
 
@@ -178,6 +178,26 @@ int physs_kf_filter_f64(FILTER_PARAMS, double* mf, double* Pf, double* lml, doub
   int rc = pack_filter(FILTER_ARGS, mf, Pf, lml, lml_k, a);
   if (rc || B == 0) return rc;
   return run_filter_any((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a);
+}
+
+int physs_kf_vjp_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {
+  return vjp_supported(d, m, disc_mode, nblk) ? 1 : 0;
+}
+
+int physs_kf_filter_vjp_f64(FILTER_PARAMS, const double* mf, const double* Pf, const double* g_lml, double* gA,
+                            double* gQ, double* glam, double* gPinf, double* gH, double* gR_step, double* gR_sum,
+                            double* gm0, double* gP0) {
+  SeqFilterArgs a;
+  double dummy = 0.0;                       // pack_filter insists on an lml pointer; the reverse pass writes none
+  int rc = pack_filter(FILTER_ARGS, const_cast<double*>(mf), const_cast<double*>(Pf), &dummy, nullptr, a);
+  if (rc || B == 0) return rc;
+  a.lml = nullptr;
+  if (disc_mode == PHYSS_DISC_GIVEN ? (!gA || !gQ) : (!glam || !gPinf))
+    return set_error(PHYSS_ERR_BAD_ARG, "filter vjp: missing gradient output for this disc_mode");
+  VjpOut o{};
+  o.g_lml = g_lml; o.gA = gA; o.gQ = gQ; o.glam = glam; o.gPinf = gPinf; o.gH = gH;
+  o.gR_step = gR_step; o.gR_sum = gR_sum; o.gm0 = gm0; o.gP0 = gP0;
+  return kf_vjp((cudaStream_t)stream, d, m, disc_mode, nblk, a, o);
 }
 
 int physs_rts_smooth_f64(SMOOTH_PARAMS, double* ms, double* Ps) {

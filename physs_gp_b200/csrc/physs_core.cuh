@@ -83,18 +83,40 @@ struct LmlAcc {
 // Closed-form A = expm(F dt) for Matern-(S-1/2) state-space blocks, S = 1..4.
 // lam = sqrt(2 nu) / lengthscale.  S=2: ss_utils.py:6-10; S=3: matern.py:152-177; S=4: matern.py:306-329.
 // ---------------------------------------------------------------------------------------------
+// Forward-mode pair (value, derivative) for d/dlam of the closed forms (used by the adjoint kernel, physs_vjp.cu)
+struct Dual {
+  double v, d;
+};
+PHYSS_HD Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.d + b.d}; }
+PHYSS_HD Dual operator+(Dual a, double b) { return {a.v + b, a.d}; }
+PHYSS_HD Dual operator+(double a, Dual b) { return {a + b.v, b.d}; }
+PHYSS_HD Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.d - b.d}; }
+PHYSS_HD Dual operator-(Dual a, double b) { return {a.v - b, a.d}; }
+PHYSS_HD Dual operator-(double a, Dual b) { return {a - b.v, -b.d}; }
+PHYSS_HD Dual operator-(Dual a) { return {-a.v, -a.d}; }
+PHYSS_HD Dual operator*(Dual a, Dual b) { return {a.v * b.v, fma(a.v, b.d, a.d * b.v)}; }
+PHYSS_HD Dual operator*(Dual a, double b) { return {a.v * b, a.d * b}; }
+PHYSS_HD Dual operator*(double a, Dual b) { return {a * b.v, a * b.d}; }
+PHYSS_HD Dual operator/(Dual a, double b) { return {a.v / b, a.d / b}; }
+PHYSS_HD double texp(double x) { return exp(x); }
+PHYSS_HD Dual texp(Dual x) { const double e = exp(x.v); return {e, e * x.d}; }
+
 template <int S>
 struct MaternExpm;
 
 template <>
 struct MaternExpm<1> {
-  static PHYSS_HD void eval(double lam, double dt, double (&A)[1][1]) { A[0][0] = exp(-lam * dt); }
+  static PHYSS_HD void eval(double lam, double dt, double (&A)[1][1]) { evalT<double>(lam, dt, A); }
+  template <class T>
+  static PHYSS_HD void evalT(T lam, double dt, T (&A)[1][1]) { A[0][0] = texp(-(lam * dt)); }
 };
 
 template <>
 struct MaternExpm<2> {
-  static PHYSS_HD void eval(double lam, double dt, double (&A)[2][2]) {
-    const double e = exp(-dt * lam);
+  static PHYSS_HD void eval(double lam, double dt, double (&A)[2][2]) { evalT<double>(lam, dt, A); }
+  template <class T>
+  static PHYSS_HD void evalT(T lam, double dt, T (&A)[2][2]) {
+    const T e = texp(-(dt * lam));
     A[0][0] = e * (dt * lam + 1.0);
     A[0][1] = e * dt;
     A[1][0] = e * (dt * (-lam * lam));
@@ -104,10 +126,12 @@ struct MaternExpm<2> {
 
 template <>
 struct MaternExpm<3> {
-  static PHYSS_HD void eval(double lam, double dt, double (&A)[3][3]) {
-    const double x = dt * lam;  // dtlam
-    const double e = exp(-x);
-    const double l2 = lam * lam;
+  static PHYSS_HD void eval(double lam, double dt, double (&A)[3][3]) { evalT<double>(lam, dt, A); }
+  template <class T>
+  static PHYSS_HD void evalT(T lam, double dt, T (&A)[3][3]) {
+    const T x = dt * lam;  // dtlam
+    const T e = texp(-x);
+    const T l2 = lam * lam;
     A[0][0] = e * (dt * (lam * (0.5 * x + 1.0)) + 1.0);
     A[0][1] = e * (dt * (x + 1.0));
     A[0][2] = e * (dt * (0.5 * dt));
@@ -122,12 +146,14 @@ struct MaternExpm<3> {
 
 template <>
 struct MaternExpm<4> {
-  static PHYSS_HD void eval(double lam, double dt, double (&A)[4][4]) {
-    const double x = dt * lam;
-    const double x2 = x * x;
-    const double e = exp(-x);
-    const double l2 = lam * lam;
-    const double l3 = l2 * lam;
+  static PHYSS_HD void eval(double lam, double dt, double (&A)[4][4]) { evalT<double>(lam, dt, A); }
+  template <class T>
+  static PHYSS_HD void evalT(T lam, double dt, T (&A)[4][4]) {
+    const T x = dt * lam;
+    const T x2 = x * x;
+    const T e = texp(-x);
+    const T l2 = lam * lam;
+    const T l3 = l2 * lam;
     A[0][0] = e * (dt * (lam * (1.0 + 0.5 * x + x2 / 6.0)) + 1.0);
     A[0][1] = e * (dt * (1.0 + x + 0.5 * x2));
     A[0][2] = e * (dt * (0.5 * dt * (1.0 + x)));

@@ -43,6 +43,17 @@ struct SeqFilterArgs {
   int* unconverged;
 };
 
+// Outputs of the filter's reverse pass (physs_vjp.cu); any pointer may be NULL except the ones the mode needs.
+struct VjpOut {
+  const double* g_lml;            // [B] cotangent of lml (NULL = 1)
+  double* gA; double* gQ;         // DISC_GIVEN: per-step [.., d, d] in the step layout
+  double* glam; double* gPinf;    // DISC_MATERN: [B, nblk], [B, d, d]
+  double* gH;                     // [B, m, d]
+  double* gR_step;                // per-step [.., m, m] in the step layout, or NULL
+  double* gR_sum;                 // [B, m, m] sum over the steps, or NULL
+  double* gm0; double* gP0;       // [B, d], [B, d, d]
+};
+
 struct SeqSmoothArgs {
   int64_t B, T;
   int64_t sbs, sts;   // step strides (see SeqFilterArgs)
@@ -111,6 +122,8 @@ int grp_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const Se
 
 // physs_rt.cu: one lane group per series, register-tiled products, compile-time padded dims (d <= 32)
 bool rt_supported(int d, int m);
+bool vjp_supported(int d, int m, int disc_mode, int nblk);
+int kf_vjp(cudaStream_t st, int d, int m, int disc_mode, int nblk, const SeqFilterArgs& a, const VjpOut& o);
 int rt_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity, const SeqFilterArgs& a);
 int rt_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
 int rt_filter_summary(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, const SeqFilterArgs& a,

@@ -1,0 +1,356 @@
+// physs_vjp.cu -- reverse pass of the sequential Kalman filter's log marginal likelihood (SURVEY.md section 8,
+// row f1): what `jax.jacrev` through filter('sequential') computes for the hyper-parameter steps of the
+// reference (stgp/trainers/trainer.py:43,128-136; stgp/trainers/standard.py:58-91), as ONE kernel.
+//
+// The forward recursion is kalman_filter.py:144-241 (predict, masked update with the jittered gain solve,
+// P - K S K^T, masked lml).  The reverse pass walks the steps backwards, rebuilds step k's prediction from the
+// STORED filtered state of step k-1 (the forward kernel's outputs: nothing else is saved) and pushes the
+// adjoints (m_bar, P_bar) of the filtered state through the step.  Derivation and pins: oracle/adjoint.py,
+// tests/test_oracle_adjoint.py (torch autograd through a transcription of the forward recursion).
+//
+// Mapping: one thread = one series, d <= 4, scalar observations (m = 1): everything in registers, as the
+// forward register kernels.  Per step the thread reads (m, P)[k-1], y_k, R_k, dt_k and, in DISC_GIVEN mode,
+// A_k / Q_k, and writes gA_k / gQ_k; in DISC_MATERN mode the chain to (lam, Pinf) is folded on chip
+// (dA/dlam from the closed forms evaluated on dual numbers) and nothing per-step is written but gR.
+#include <stdint.h>
+
+#include "physs_core.cuh"
+#include "physs_internal.h"
+
+namespace physs {
+
+template <int D, int S, bool GIVEN>
+__global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, const VjpOut o) {
+  constexpr int NB = D / S;
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  const int64_t sbs = p.sbs, sts = p.sts;
+  const double gbar = o.g_lml ? o.g_lml[b] : 1.0;
+  const double jit = p.jitter;
+
+  double h[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) h[i] = p.H ? p.H[b * p.H_bs + i] : (i == 0 ? 1.0 : 0.0);
+  double Pinf[D][D], lam[NB];
+  if (!GIVEN) {
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) Pinf[i][j] = p.Pinf[b * p.Pinf_bs + i * D + j];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) lam[q] = p.lam[b * p.lam_bs + q];
+  }
+
+  double mbar[D], Pbar[D][D], gH[D], gPinf[D][D], glam[NB];
+  double gRsum = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    mbar[i] = 0.0;
+    gH[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) { Pbar[i][j] = 0.0; gPinf[i][j] = 0.0; }
+  }
+#pragma unroll
+  for (int q = 0; q < NB; ++q) glam[q] = 0.0;
+
+  for (int64_t k = p.T - 1; k >= 0; --k) {
+    const int64_t row = b * sbs + k * sts;
+    // ---- state before the step
+    double m[D], P[D][D];
+    if (k > 0) {
+      const int64_t prow = b * sbs + (k - 1) * sts;
+#pragma unroll
+      for (int i = 0; i < D; ++i) m[i] = p.mf[prow * D + i];
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) P[i][j] = p.Pf[prow * D * D + i * D + j];
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; ++i) m[i] = p.m0[b * p.m0_bs + i];
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) P[i][j] = p.P0[b * p.P0_bs + i * D + j];
+    }
+    const double y = p.Y[row];
+    const double R = p.R[b * p.R_bs + k * p.R_ts];
+    const double dt = p.dt[b * p.dt_bs + k];
+    // ---- transition (dense D x D; off-block entries are zero in DISC_MATERN mode)
+    double A[D][D], Q[D][D];
+    if (GIVEN) {
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          A[i][j] = p.A[b * p.A_bs + k * D * D + i * D + j];
+          Q[i][j] = p.Q[b * p.Q_bs + k * D * D + i * D + j];
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) A[i][j] = 0.0;
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        double a[S][S];
+        MaternExpm<S>::eval(lam[q], dt, a);
+#pragma unroll
+        for (int i = 0; i < S; ++i)
+#pragma unroll
+          for (int j = 0; j < S; ++j) A[q * S + i][q * S + j] = a[i][j];
+      }
+      // Q_k = Pinf - A Pinf A^T (kernels/kernel.py:207-209)
+      double AP[D][D];
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          double acc = 0.0;
+#pragma unroll
+          for (int l = 0; l < D; ++l) acc = fma(A[i][l], Pinf[l][j], acc);
+          AP[i][j] = acc;
+        }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          double acc = 0.0;
+#pragma unroll
+          for (int l = 0; l < D; ++l) acc = fma(AP[i][l], A[j][l], acc);
+          Q[i][j] = Pinf[i][j] - acc;
+        }
+    }
+    // ---- forward: predict
+    double mp[D], AP[D][D], Pp[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = 0; l < D; ++l) acc = fma(A[i][l], m[l], acc);
+      mp[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < D; ++l) acc = fma(A[i][l], P[l][j], acc);
+        AP[i][j] = acc;                                        // A P
+      }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double acc = Q[i][j];
+#pragma unroll
+        for (int l = 0; l < D; ++l) acc = fma(AP[i][l], A[j][l], acc);
+        Pp[i][j] = acc;
+      }
+    // ---- reverse: update (scalar observation)
+    double mpbar[D], Ppbar[D][D];
+    double Rbar = 0.0;
+    const bool obs = !(y != y);
+    if (obs) {
+      double c[D], hmp = 0.0, hc = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc = fma(h[j], Pp[j][i], acc);
+        c[i] = acc;                                            // W = H P_ (kalman_filter.py: solve(S, M H P_))
+        hmp = fma(h[i], mp[i], hmp);
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) hc = fma(h[i], c[i], hc);
+      const double Sv = hc + R, Sj = Sv + jit;
+      const double rSj = 1.0 / Sj, rS = 1.0 / Sv;
+      const double v = y - hmp;
+      const double alpha = Sv * rSj * rSj;                     // P+ = P_ - K S K^T = P_ - alpha W^T W
+      // adjoints
+      double Kdotm = 0.0, Kbar_c = 0.0, cPc = 0.0;
+      double Pc[D], Ptc[D];                                    // Pbar c, Pbar^T c
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        Kdotm = fma(c[i] * rSj, mbar[i], Kdotm);
+        double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          a1 = fma(Pbar[i][j], c[j], a1);
+          a2 = fma(Pbar[j][i], c[j], a2);
+        }
+        Pc[i] = a1;
+        Ptc[i] = a2;
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        cPc = fma(c[i], Pc[i], cPc);
+        Kbar_c = fma(mbar[i] * v, c[i], Kbar_c);               // (K_bar from the mean) . c
+      }
+      const double vbar = Kdotm - gbar * v * rS;
+      const double abar = -cPc;                                 // alpha_bar
+      double Sbar = abar * (rSj * rSj - 2.0 * Sv * rSj * rSj * rSj) - Kbar_c * rSj * rSj
+                    + gbar * (-0.5) * (rS - v * v * rS * rS);
+      Rbar = Sbar;
+      double cbar[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) cbar[i] = -alpha * (Pc[i] + Ptc[i]) + mbar[i] * v * rSj + Sbar * h[i];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc = fma(Pp[i][j], cbar[j], acc);      // P_ W_bar^T
+        gH[i] += Sbar * c[i] + acc - vbar * mp[i];
+        mpbar[i] = mbar[i] - vbar * h[i];
+#pragma unroll
+        for (int j = 0; j < D; ++j) Ppbar[i][j] = fma(h[i], cbar[j], Pbar[i][j]);   // W = H P_
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        mpbar[i] = mbar[i];
+#pragma unroll
+        for (int j = 0; j < D; ++j) Ppbar[i][j] = Pbar[i][j];
+      }
+    }
+    if (o.gR_step) o.gR_step[row] = Rbar;
+    gRsum += Rbar;
+    // ---- reverse: predict.  Abar = mp_bar m^T + (Pp_bar + Pp_bar^T) A P ; m_bar = A^T mp_bar ; P_bar = A^T Pp_bar A
+    double Abar[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double acc = mpbar[i] * m[j];
+#pragma unroll
+        for (int l = 0; l < D; ++l) acc = fma(Ppbar[i][l] + Ppbar[l][i], AP[l][j], acc);
+        Abar[i][j] = acc;
+      }
+    double T1[D][D];                                           // Pp_bar A
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < D; ++l) acc = fma(Ppbar[i][l], A[l][j], acc);
+        T1[i][j] = acc;
+      }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = 0; l < D; ++l) acc = fma(A[l][i], mpbar[l], acc);
+      mbar[i] = acc;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double a2 = 0.0;
+#pragma unroll
+        for (int l = 0; l < D; ++l) a2 = fma(A[l][i], T1[l][j], a2);
+        Pbar[i][j] = a2;                                       // A^T Pp_bar A
+      }
+    }
+    if (GIVEN) {
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          o.gA[row * D * D + i * D + j] = Abar[i][j];
+          o.gQ[row * D * D + i * D + j] = Ppbar[i][j];
+        }
+    } else {
+      // Q_k = Pinf - A Pinf A^T :  Pinf_bar += Q_bar - A^T Q_bar A ;  Abar -= (Q_bar + Q_bar^T) A Pinf   (Q_bar = Pp_bar)
+      double APi[D][D];
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          double acc = 0.0;
+#pragma unroll
+          for (int l = 0; l < D; ++l) acc = fma(A[i][l], Pinf[l][j], acc);
+          APi[i][j] = acc;
+        }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          gPinf[i][j] += Ppbar[i][j] - Pbar[i][j];             // Pbar already holds A^T Pp_bar A
+          double acc = 0.0;
+#pragma unroll
+          for (int l = 0; l < D; ++l) acc = fma(Ppbar[i][l] + Ppbar[l][i], APi[l][j], acc);
+          Abar[i][j] -= acc;
+        }
+      // chain to lam through the closed forms on dual numbers
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        Dual a[S][S];
+        MaternExpm<S>::template evalT<Dual>(Dual{lam[q], 1.0}, dt, a);
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < S; ++i)
+#pragma unroll
+          for (int j = 0; j < S; ++j) acc = fma(Abar[q * S + i][q * S + j], a[i][j].d, acc);
+        glam[q] += acc;
+      }
+    }
+  }
+  // ---- results
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    if (o.gH) o.gH[b * D + i] = gH[i];
+    if (o.gm0) o.gm0[b * D + i] = mbar[i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      if (o.gP0) o.gP0[b * D * D + i * D + j] = Pbar[i][j];
+      if (!GIVEN && o.gPinf) o.gPinf[b * D * D + i * D + j] = gPinf[i][j];
+    }
+  }
+  if (!GIVEN && o.glam) {
+#pragma unroll
+    for (int q = 0; q < NB; ++q) o.glam[b * NB + q] = glam[q];
+  }
+  if (o.gR_sum) o.gR_sum[b] = gRsum;
+}
+
+template <int D, int S, bool GIVEN>
+static int vjp_launch(cudaStream_t st, const SeqFilterArgs& a, const VjpOut& o) {
+  const int threads = 128;
+  const int64_t grid = (a.B + threads - 1) / threads;
+  kf_vjp_kernel<D, S, GIVEN><<<(unsigned)grid, threads, 0, st>>>(a, o);
+  return cuda_status(cudaGetLastError(), "kf_vjp_kernel launch");
+}
+
+bool vjp_supported(int d, int m, int disc_mode, int nblk) {
+  if (m != 1 || d < 1 || d > 4) return false;
+  if (disc_mode == PHYSS_DISC_GIVEN) return true;
+  if (disc_mode != PHYSS_DISC_MATERN || nblk < 1 || d % nblk) return false;
+  return true;                                                  // block size d / nblk in 1..4
+}
+
+int kf_vjp(cudaStream_t st, int d, int m, int disc_mode, int nblk, const SeqFilterArgs& a, const VjpOut& o) {
+  if (!vjp_supported(d, m, disc_mode, nblk))
+    return set_error(PHYSS_ERR_UNSUPPORTED, "filter vjp: supported for d <= 4, m == 1");
+  if (disc_mode == PHYSS_DISC_GIVEN) {
+    switch (d) {
+      case 1: return vjp_launch<1, 1, true>(st, a, o);
+      case 2: return vjp_launch<2, 2, true>(st, a, o);
+      case 3: return vjp_launch<3, 3, true>(st, a, o);
+      default: return vjp_launch<4, 4, true>(st, a, o);
+    }
+  }
+  const int s = d / nblk;
+  switch (d * 10 + s) {
+    case 11: return vjp_launch<1, 1, false>(st, a, o);
+    case 21: return vjp_launch<2, 1, false>(st, a, o);
+    case 22: return vjp_launch<2, 2, false>(st, a, o);
+    case 31: return vjp_launch<3, 1, false>(st, a, o);
+    case 33: return vjp_launch<3, 3, false>(st, a, o);
+    case 41: return vjp_launch<4, 1, false>(st, a, o);
+    case 42: return vjp_launch<4, 2, false>(st, a, o);
+    case 44: return vjp_launch<4, 4, false>(st, a, o);
+    default: return set_error(PHYSS_ERR_UNSUPPORTED, "filter vjp: block size");
+  }
+}
+
+}  // namespace physs

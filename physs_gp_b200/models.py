@@ -51,6 +51,43 @@ class SDE_GP:
             return mu, var.diagonal(dim1=-2, dim2=-1)[..., None]
         return mu, var
 
+    # ---------------------------------------------------------------- lml and its hyper-parameter gradient
+    def log_marginal_likelihood_and_grad(self):
+        """Value and gradient of the lml with respect to the kernel and noise hyper-parameters -- the pair
+        the reference's trainers take with `jax.value_and_grad` / `jacrev` THROUGH the filter
+        (stgp/trainers/standard.py:58-91, stgp/trainers/trainer.py:43,128-136).  One forward filter launch, one
+        reverse launch (`physs_kf_filter_vjp_f64`), then the T-independent chain of the prior's closed forms on
+        the host.  For `BatchedMaternSDE` priors with scalar Gaussian observations (d <= 4).
+
+        Returns (lml [B], {'lengthscale': [B, nblk], 'variance': [B, nblk], 'noise': [B]})."""
+        from . import ops, settings
+        from .likelihood import Gaussian
+        from .sdes import BatchedMaternSDE
+        prior, data = self.prior, self.data
+        if not isinstance(prior, BatchedMaternSDE) or not isinstance(self.likelihood, Gaussian):
+            raise NotImplementedError("lml gradient: BatchedMaternSDE prior with a Gaussian likelihood")
+        if data.P * data.Ns != 1 or prior.full_state_obs:
+            raise NotImplementedError("lml gradient: scalar observations (m == 1)")
+        dev = filters._device()
+        X_t = filters._time_axis(data, dev)
+        dt = torch.cat([torch.zeros(1, dtype=torch.float64, device=dev), X_t[1:] - X_t[:-1]])
+        Y = filters._to_dev(data.Y_st, dev)
+        Y = Y.reshape(*Y.shape[:-2], 1)                           # [.., Nt, 1]
+        if Y.dim() == 2:
+            Y = Y[None]
+        if Y.shape[0] == 1 and prior.B > 1:
+            Y = Y.expand(prior.B, -1, -1)
+        if settings.time_major and Y.shape[0] >= settings.time_major_min_batch and not ops.step_layout(Y, "Y")[1]:
+            Y = Y.transpose(0, 1).contiguous().transpose(0, 1)
+        (disc,), m0, P0, H = filters.lower_prior(prior, data.X_space, [dt], dev)
+        R = torch.full((1, 1, 1, 1), self.likelihood.variance_scalar, dtype=torch.float64, device=dev)
+        Hd = filters._to_dev(H, dev)
+        lml, mf, Pf = ops.kf_filter(dt, Y, R, Hd, m0, P0, disc, jitter=settings.jitter)
+        g = ops.kf_filter_vjp(dt, Y, R, Hd, m0, P0, disc, mf, Pf, jitter=settings.jitter)
+        g_ls, g_var = prior.hyper_grads(g['glam'].cpu().numpy(), (g['gPinf'] + g['gP0']).cpu().numpy())
+        return lml, {'lengthscale': torch.as_tensor(g_ls, device=dev), 'variance': torch.as_tensor(g_var, device=dev),
+                     'noise': g['gR'][:, 0, 0]}
+
     # ---------------------------------------------------------------- prediction at new times
     def predict_f(self, XS, diagonal=True, squeeze=False, filter_only=False, force_full_state=False):
         """Posterior at new time points -- mirror of `predict_f` (stgp/models/sde_gp.py:392-488): the test

@@ -178,6 +178,49 @@ def kf_filter(dt, Y, R, H, m0, P0, disc, jitter=None, want_lml_k=False, out=None
     return lml, mf, Pf
 
 
+def kf_filter_vjp(dt, Y, R, H, m0, P0, disc, mf, Pf, g_lml=None, jitter=None, want_R_step=False, stream=None):
+    """Reverse pass of `kf_filter`'s lml (include/physs_b200.h: physs_kf_filter_vjp_f64): gradients of
+    sum_b g_lml[b] * lml[b] with respect to the filter's inputs, given its outputs (mf, Pf).
+
+    Returns a dict: DISC_GIVEN -> 'gA', 'gQ' [B, T, d, d]; DISC_MATERN -> 'glam' [B, nblk], 'gPinf' [B, d, d];
+    always 'gH' [B, m, d], 'gR' [B, m, m] (summed over the steps), 'gm0' [B, d], 'gP0' [B, d, d];
+    'gR_step' [B, T, m, m] with want_R_step.  Supported for d <= 4, m == 1."""
+    lib = _lib.load()
+    p = _pack_filter(dt, Y, R, H, m0, P0, disc, jitter, stream)
+    B, T, d, m, dev = p.B, p.T, p.d, p.m, p.dev
+    if not lib.physs_kf_vjp_supported(d, m, disc.mode, disc.nblk):
+        raise NotImplementedError("kf_filter_vjp: d <= 4 and m == 1 only (d=%d, m=%d)" % (d, m))
+    mfv, tm1 = step_layout(_dev(mf, "mf"), "mf")
+    Pfv, tm2 = step_layout(_dev(Pf, "Pf"), "Pf")
+    if tm1 != p.tmaj or tm2 != p.tmaj:
+        raise ValueError("kf_filter_vjp: mf / Pf must be in the memory order of Y (the filter's own outputs are)")
+    z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)      # noqa: E731
+    out = {"gH": z(B, m, d), "gR": z(B, m, m), "gm0": z(B, d), "gP0": z(B, d, d)}
+    gA = gQ = glam = gPinf = gRs = None
+    if disc.mode == _lib.DISC_GIVEN:
+        gA = empty_steps(B, T, (d, d), dev, p.tmaj)
+        gQ = empty_steps(B, T, (d, d), dev, p.tmaj)
+        out["gA"], out["gQ"] = gA, gQ
+    else:
+        glam, gPinf = z(B, disc.nblk), z(B, d, d)
+        out["glam"], out["gPinf"] = glam, gPinf
+    if want_R_step:
+        gRs = empty_steps(B, T, (m, m), dev, p.tmaj)
+        out["gR_step"] = gRs
+    g = None
+    if g_lml is not None:
+        g = _dev(g_lml, "g_lml").reshape(-1).contiguous()
+        if g.numel() != B:
+            raise ValueError("g_lml must have one entry per series")
+    ptr = lambda t: t.data_ptr() if t is not None else None                      # noqa: E731
+    with torch.cuda.device(dev):
+        st = lib.physs_kf_filter_vjp_f64(*p.head, mfv.data_ptr(), Pfv.data_ptr(), ptr(g), ptr(gA), ptr(gQ),
+                                         ptr(glam), ptr(gPinf), out["gH"].data_ptr(), ptr(gRs),
+                                         out["gR"].data_ptr(), out["gm0"].data_ptr(), out["gP0"].data_ptr())
+    _lib.check(st, "physs_kf_filter_vjp_f64")
+    return out
+
+
 def _pack_smooth(dt, mf, Pf, disc, Hout, jitter, stream):
     mf, tmaj = step_layout(mf, "mf")
     Pf, tmaj_P = step_layout(Pf, "Pf")

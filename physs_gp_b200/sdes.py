@@ -171,6 +171,23 @@ class BatchedMaternSDE:
     def m_inf(self):
         return np.zeros([1, self.d])
 
+    def hyper_grads(self, glam, gPinf):
+        """Chain gradients with respect to (lam [B, nblk], Pinf [B, d, d]) -- what the filter's reverse pass
+        returns, with the P0 = Pinf contribution already added to gPinf -- to the kernels' own parameters:
+        lam = sqrt(2 s - 1) / lengthscale and, in every closed form above, Pinf[i][j] = c_ij * variance *
+        lam^(i + j) inside a block.  Returns (d/d lengthscale, d/d variance), each [B, nblk]."""
+        glam, gPinf = np.asarray(glam, np.float64), np.asarray(gPinf, np.float64)
+        lam, P, s = self.lam(), self.P_inf(), self.s
+        powers = np.add.outer(np.arange(s), np.arange(s)).astype(np.float64)        # i + j
+        g_ls, g_var = np.zeros_like(lam), np.zeros_like(lam)
+        for b in range(self.nblk):
+            sl = slice(b * s, (b + 1) * s)
+            gp, pb = gPinf[:, sl, sl], P[:, sl, sl]
+            dlam = glam[:, b] + np.sum(gp * pb * powers, axis=(1, 2)) / lam[:, b]
+            g_ls[:, b] = -dlam * lam[:, b] / self.ls[:, b]
+            g_var[:, b] = np.sum(gp * pb, axis=(1, 2)) / self.var[:, b]
+        return g_ls, g_var
+
     def H(self):
         if self.full_state_obs:
             return np.eye(self.d)
