@@ -26,17 +26,46 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
   if (b >= p.B) return;
   const int64_t sbs = p.sbs, sts = p.sts;
   const double gbar = o.g_lml ? o.g_lml[b] : 1.0;
+  // The state before step k, (m, P)[k-1], is fetched ONE STEP AHEAD with cp.async into a two-stage shared-memory
+  // ring laid out [stage][piece][thread] (conflict-free): with 255 registers per thread only 8 warps fit on an SM,
+  // so the DRAM latency of a dependent load per step would bound the kernel (measured 4.5x slower without).
+  constexpr int PW = (D % 2 == 0) ? 2 : 1;                       // doubles per copy piece (16 B when rows allow)
+  constexpr int NPC = (D * D + D) / PW;                          // pieces per step
+  __shared__ __align__(16) double ring[2][NPC][128][PW];
+  const int tid = threadIdx.x;
+  auto issue = [&](int64_t k) {
+    const int st = (int)(k & 1);
+    const double* pm;
+    const double* pP;
+    if (k > 0) {
+      const int64_t prow = b * sbs + (k - 1) * sts;
+      pm = p.mf + prow * D;
+      pP = p.Pf + prow * D * D;
+    } else {
+      pm = p.m0 + b * p.m0_bs;
+      pP = p.P0 + b * p.P0_bs;
+    }
+#pragma unroll
+    for (int e = 0; e < D * D / PW; ++e) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(&ring[st][e][tid][0]);
+      if (PW == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(pP + 2 * e) : "memory");
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(pP + e) : "memory");
+    }
+#pragma unroll
+    for (int e = 0; e < D / PW; ++e) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(&ring[st][D * D / PW + e][tid][0]);
+      if (PW == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(pm + 2 * e) : "memory");
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(pm + e) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   const double jit = p.jitter;
 
   double h[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) h[i] = p.H ? p.H[b * p.H_bs + i] : (i == 0 ? 1.0 : 0.0);
-  double Pinf[D][D], lam[NB];
+  double lam[NB];
   if (!GIVEN) {
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-      for (int j = 0; j < D; ++j) Pinf[i][j] = p.Pinf[b * p.Pinf_bs + i * D + j];
 #pragma unroll
     for (int q = 0; q < NB; ++q) lam[q] = p.lam[b * p.lam_bs + q];
   }
@@ -53,31 +82,33 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
 #pragma unroll
   for (int q = 0; q < NB; ++q) glam[q] = 0.0;
 
+  issue(p.T - 1);
+  double y_n = p.Y[b * sbs + (p.T - 1) * sts];
+  double R_n = p.R[b * p.R_bs + (p.T - 1) * p.R_ts];
+  double dt_n = p.dt[b * p.dt_bs + p.T - 1];
   for (int64_t k = p.T - 1; k >= 0; --k) {
     const int64_t row = b * sbs + k * sts;
-    // ---- state before the step
-    double m[D], P[D][D];
+    const double y = y_n, R = R_n, dt = dt_n;
     if (k > 0) {
-      const int64_t prow = b * sbs + (k - 1) * sts;
-#pragma unroll
-      for (int i = 0; i < D; ++i) m[i] = p.mf[prow * D + i];
-#pragma unroll
-      for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int j = 0; j < D; ++j) P[i][j] = p.Pf[prow * D * D + i * D + j];
+      issue(k - 1);
+      y_n = p.Y[b * sbs + (k - 1) * sts];
+      R_n = p.R[b * p.R_bs + (k - 1) * p.R_ts];
+      dt_n = p.dt[b * p.dt_bs + k - 1];
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
-#pragma unroll
-      for (int i = 0; i < D; ++i) m[i] = p.m0[b * p.m0_bs + i];
-#pragma unroll
-      for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int j = 0; j < D; ++j) P[i][j] = p.P0[b * p.P0_bs + i * D + j];
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    const double y = p.Y[row];
-    const double R = p.R[b * p.R_bs + k * p.R_ts];
-    const double dt = p.dt[b * p.dt_bs + k];
+    // ---- state before the step (own pieces of the ring: no block-level synchronisation needed)
+    double m[D], P[D][D];
+    {
+      const int st = (int)(k & 1);
+#pragma unroll
+      for (int e = 0; e < D * D; ++e) P[e / D][e % D] = ring[st][e / PW][tid][e % PW];
+#pragma unroll
+      for (int e = 0; e < D; ++e) m[e] = ring[st][D * D / PW + e / PW][tid][e % PW];
+    }
     // ---- transition (dense D x D; off-block entries are zero in DISC_MATERN mode)
-    double A[D][D], Q[D][D];
+    double A[D][D], Q[D][D], dA[NB][S][S];
     if (GIVEN) {
 #pragma unroll
       for (int i = 0; i < D; ++i)
@@ -93,35 +124,19 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
         for (int j = 0; j < D; ++j) A[i][j] = 0.0;
 #pragma unroll
       for (int q = 0; q < NB; ++q) {
-        double a[S][S];
-        MaternExpm<S>::eval(lam[q], dt, a);
+        Dual a[S][S];                                          // closed form and its d/dlam in one evaluation
+        MaternExpm<S>::template evalT<Dual>(Dual{lam[q], 1.0}, dt, a);
 #pragma unroll
         for (int i = 0; i < S; ++i)
 #pragma unroll
-          for (int j = 0; j < S; ++j) A[q * S + i][q * S + j] = a[i][j];
+          for (int j = 0; j < S; ++j) {
+            A[q * S + i][q * S + j] = a[i][j].v;
+            dA[q][i][j] = a[i][j].d;
+          }
       }
-      // Q_k = Pinf - A Pinf A^T (kernels/kernel.py:207-209)
-      double AP[D][D];
-#pragma unroll
-      for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          double acc = 0.0;
-#pragma unroll
-          for (int l = 0; l < D; ++l) acc = fma(A[i][l], Pinf[l][j], acc);
-          AP[i][j] = acc;
-        }
-#pragma unroll
-      for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          double acc = 0.0;
-#pragma unroll
-          for (int l = 0; l < D; ++l) acc = fma(AP[i][l], A[j][l], acc);
-          Q[i][j] = Pinf[i][j] - acc;
-        }
     }
-    // ---- forward: predict
+    // ---- forward: predict.  DISC_MATERN: P_ = A P A^T + (Pinf - A Pinf A^T) = Pinf + A (P - Pinf) A^T, so that ONE
+    // product W = A (P - Pinf) serves the prediction and, below, the adjoint of A through both P_ and Q_k
     double mp[D], AP[D][D], Pp[D][D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
@@ -130,6 +145,12 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
       for (int l = 0; l < D; ++l) acc = fma(A[i][l], m[l], acc);
       mp[i] = acc;
     }
+    if (!GIVEN) {
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) P[i][j] -= p.Pinf[b * p.Pinf_bs + i * D + j];     // same address every step: L1
+    }
 #pragma unroll
     for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -137,13 +158,13 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
         double acc = 0.0;
 #pragma unroll
         for (int l = 0; l < D; ++l) acc = fma(A[i][l], P[l][j], acc);
-        AP[i][j] = acc;                                        // A P
+        AP[i][j] = acc;                                        // A P   (DISC_MATERN: A (P - Pinf))
       }
 #pragma unroll
     for (int i = 0; i < D; ++i)
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        double acc = Q[i][j];
+        double acc = GIVEN ? Q[i][j] : p.Pinf[b * p.Pinf_bs + i * D + j];
 #pragma unroll
         for (int l = 0; l < D; ++l) acc = fma(AP[i][l], A[j][l], acc);
         Pp[i][j] = acc;
@@ -260,37 +281,20 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
           o.gQ[row * D * D + i * D + j] = Ppbar[i][j];
         }
     } else {
-      // Q_k = Pinf - A Pinf A^T :  Pinf_bar += Q_bar - A^T Q_bar A ;  Abar -= (Q_bar + Q_bar^T) A Pinf   (Q_bar = Pp_bar)
-      double APi[D][D];
+      // Q_k = Pinf - A Pinf A^T :  Pinf_bar += Q_bar - A^T Q_bar A  (Q_bar = Pp_bar; Pbar already holds A^T Pp_bar A);
+      // the -(Q_bar + Q_bar^T) A Pinf part of Abar is already inside Abar through W = A (P - Pinf)
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-          double acc = 0.0;
-#pragma unroll
-          for (int l = 0; l < D; ++l) acc = fma(A[i][l], Pinf[l][j], acc);
-          APi[i][j] = acc;
-        }
-#pragma unroll
-      for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          gPinf[i][j] += Ppbar[i][j] - Pbar[i][j];             // Pbar already holds A^T Pp_bar A
-          double acc = 0.0;
-#pragma unroll
-          for (int l = 0; l < D; ++l) acc = fma(Ppbar[i][l] + Ppbar[l][i], APi[l][j], acc);
-          Abar[i][j] -= acc;
-        }
+        for (int j = 0; j < D; ++j) gPinf[i][j] += Ppbar[i][j] - Pbar[i][j];
       // chain to lam through the closed forms on dual numbers
 #pragma unroll
       for (int q = 0; q < NB; ++q) {
-        Dual a[S][S];
-        MaternExpm<S>::template evalT<Dual>(Dual{lam[q], 1.0}, dt, a);
         double acc = 0.0;
 #pragma unroll
         for (int i = 0; i < S; ++i)
 #pragma unroll
-          for (int j = 0; j < S; ++j) acc = fma(Abar[q * S + i][q * S + j], a[i][j].d, acc);
+          for (int j = 0; j < S; ++j) acc = fma(Abar[q * S + i][q * S + j], dA[q][i][j], acc);
         glam[q] += acc;
       }
     }
