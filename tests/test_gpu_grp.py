@@ -29,6 +29,8 @@ CASES = [
     (4, 3, "indep", 4, 100),      # d=12, m=3
     (4, 4, "sum", 5, 120),        # d=16, m=1  (config 5)
     (2, 5, "sum", 4, 100),        # d=10, m=1
+    (4, 4, "full", 3, 60),        # d=16, m=16 (compile-time shape variant m == d at DM = 16)
+    (4, 2, "indep", 4, 90),       # d=8, m=2   (compile-time d and block size, runtime m)
     (4, 8, "sum", 3, 80),         # d=32, m=1  (config 5)
     (4, 8, "full", 2, 40),        # d=32, m=32
     (1, 5, "indep", 3, 50),       # d=5 Ornstein-Uhlenbeck blocks
