@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--series", type=int, default=None, help="series per GPU (default 65536; c3: 1; cvi: 1000)")
     ap.add_argument("--T", type=int, default=None, help="steps (default 10000; c3: 1000000)")
     ap.add_argument("--sub-batch", type=int, default=32768)
-    ap.add_argument("--e2e-sub-batch", type=int, default=8192)
+    ap.add_argument("--e2e-sub-batch", type=int, default=4096)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-series", type=int, default=0, help="series in the CPU sample (0 = auto)")
@@ -102,16 +102,22 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.skip = [], None, index, 0
 
     def start(self):
+        """Starts `nvidia-smi -lms 20` and returns once it is delivering rows (it takes a few hundred ms to come
+        up -- longer than a short timed region), so that every row kept is from the timed region itself."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < 3.0:
+                time.sleep(0.005)
+            self.skip = len(self.rows)
         except Exception:
             self.proc = None
 
@@ -129,7 +135,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[self.skip:] or self.rows
+        for r in rows:
             if len(r) < 8:
                 continue
             try:
@@ -397,11 +404,13 @@ def run_b200(a):
 def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys_dev):
     """Same job through the reference-shaped API (SDE_GP.filter_and_smooth) with HOST buffers.
 
-    Every sub-batch is one user-level call sequence on its own CUDA stream (three streams round-robin):
+    Every sub-batch is one user-level call sequence on its own CUDA stream (eight streams round-robin):
     pinned-host -> device copy of its observations, filter + smoother through the host API -> C ABI, and a
-    device -> pinned-host read of the result.  The API is stream-ordered and never synchronises, so the
-    H2D of sub-batch i+1, the kernels of sub-batch i and the D2H of sub-batch i-1 overlap on the two copy
-    engines and the SMs; every byte still crosses PCIe inside the timed region."""
+    device -> pinned-host read of the result.  The API is stream-ordered and never synchronises the host, so
+    the H2D of later sub-batches, the kernels of the current ones and the D2H of earlier ones overlap on the two
+    copy engines and the SMs; every byte still crosses PCIe inside the timed region.  Measured on this box: PCIe
+    55 GB/s H2D, 57 GB/s D2H, 50 + 50 GB/s concurrently (scratch/pcie.py): the 16 B per state-step of the
+    read-back bound this number at 3.1e9 state-steps/s; sub-batch / stream count swept in scratch/e2e_probe2.py."""
     import torch
     import torch.distributed as dist
     from physs_gp_b200 import data, likelihood, models, sdes
@@ -418,7 +427,7 @@ def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys_dev):
     lik = likelihood.Gaussian(NOISE_VAR)
     esub = min(a.e2e_sub_batch, n_local)
     estarts = list(range(0, n_local, esub))
-    streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(8)]
     torch.cuda.synchronize()
 
     def step(readback=True):

@@ -28,9 +28,15 @@ def _device():
 
 
 def _to_dev(x, dev):
+    """Host -> device without stalling the host: a copy from PAGEABLE memory synchronises the stream before it
+    starts (the host then waits for every kernel already queued on it -- measured 10 ms per call in a
+    pipelined batch), so host arrays go through a pinned staging tensor (torch's caching host allocator keeps
+    it alive until the copy has run) and the copy is stream-ordered like everything else."""
     if isinstance(x, torch.Tensor):
+        if x.device.type == 'cpu' and not x.is_pinned():
+            x = x.to(torch.float64).pin_memory()
         return x.to(device=dev, dtype=torch.float64, non_blocking=True)
-    return torch.as_tensor(np.asarray(x, dtype=np.float64)).to(dev, non_blocking=True)
+    return torch.as_tensor(np.asarray(x, dtype=np.float64)).pin_memory().to(dev, non_blocking=True)
 
 
 def _np(x):
