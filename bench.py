@@ -323,6 +323,7 @@ def run_b200(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    barrier()                                 # rank 0 waits for nvidia-smi to come up: keep the ranks together
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for _ in range(a.steps):
@@ -530,6 +531,7 @@ def run_c3(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    barrier()                                 # rank 0 waits for nvidia-smi to come up: keep the ranks together
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
@@ -640,6 +642,7 @@ def run_cvi(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    barrier()                                 # rank 0 waits for nvidia-smi to come up: keep the ranks together
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
@@ -741,6 +744,7 @@ def run_c2(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    barrier()                                 # rank 0 waits for nvidia-smi to come up: keep the ranks together
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
@@ -958,6 +962,9 @@ def run_grad(a):
 
 def main():
     a = parse()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # NCCL's version / debug banner goes to stdout by default: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if a.impl == "reference":
         run_reference(a)
     elif a.workload == "c3cvi":

@@ -27,16 +27,19 @@ def _device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_PIN_LIMIT = 256 << 20      # larger pageable arrays are copied as they are (their copy time dwarfs the stall)
+
+
 def _to_dev(x, dev):
     """Host -> device without stalling the host: a copy from PAGEABLE memory synchronises the stream before it
     starts (the host then waits for every kernel already queued on it -- measured 10 ms per call in a
     pipelined batch), so host arrays go through a pinned staging tensor (torch's caching host allocator keeps
     it alive until the copy has run) and the copy is stream-ordered like everything else."""
-    if isinstance(x, torch.Tensor):
-        if x.device.type == 'cpu' and not x.is_pinned():
-            x = x.to(torch.float64).pin_memory()
-        return x.to(device=dev, dtype=torch.float64, non_blocking=True)
-    return torch.as_tensor(np.asarray(x, dtype=np.float64)).pin_memory().to(dev, non_blocking=True)
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(np.asarray(x, dtype=np.float64))
+    if x.device.type == 'cpu' and not x.is_pinned() and x.numel() * 8 <= _PIN_LIMIT:
+        x = x.to(torch.float64).pin_memory()
+    return x.to(device=dev, dtype=torch.float64, non_blocking=True)
 
 
 def _np(x):
