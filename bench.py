@@ -962,9 +962,12 @@ def run_grad(a):
 
 def main():
     a = parse()
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        # NCCL's version / debug banner goes to stdout by default: keep stdout for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries the ONE JSON line and nothing else: native libraries that write to file descriptor 1 (NCCL's
+    # version banner at N > 1) are sent to stderr, Python's own stdout keeps the original descriptor
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(keep, "w")
     if a.impl == "reference":
         run_reference(a)
     elif a.workload == "c3cvi":
