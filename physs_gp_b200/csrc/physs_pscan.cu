@@ -969,6 +969,234 @@ static int run_filter_scan(cudaStream_t st, const double* in, double* out, int64
                            int64_t stride, const PcLayout& L) {
   PS_LAUNCH((ps_filter_scan_kernel<G>), L, B * nsum, in, out, B, nchunk, nsum, stride, L);
 }
+// ---------------------------------------------------------------------------------------------------------
+// Register forms of the two scan steps for d <= 3: one THREAD per element pair.  A d = 2 filter element is 16
+// doubles; the lane-group kernels above spend their time on staging and group synchronisation there (measured
+// 82 us per pass for 79k elements, 20 % of the CVI step of config 4), while the combine itself is a few dozen
+// multiply-adds.  Same operators (parallel_kalman_filter.py:178-220 with the general solves of :201-211 and
+// force_symmetric :216-219; parallel_rts_smoother.py:39-55).
+template <int D>
+__device__ __forceinline__ void small_solve(double (&M)[D][D], double (&X)[D][D]) {   // X <- M^-1 X (partial pivoting)
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    int pv = k;
+    double best = fabs(M[k][k]);
+#pragma unroll
+    for (int r = k + 1; r < D; ++r) {
+      const double v = fabs(M[r][k]);
+      if (v > best) { best = v; pv = r; }
+    }
+#pragma unroll
+    for (int r = k + 1; r < D; ++r) {
+      const bool sw = (r == pv);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double a = M[k][c], b = M[r][c];
+        M[k][c] = sw ? b : a;
+        M[r][c] = sw ? a : b;
+        const double xa = X[k][c], xb = X[r][c];
+        X[k][c] = sw ? xb : xa;
+        X[r][c] = sw ? xa : xb;
+      }
+    }
+    const double inv = 1.0 / M[k][k];
+#pragma unroll
+    for (int r = k + 1; r < D; ++r) {
+      const double f = M[r][k] * inv;
+#pragma unroll
+      for (int c = k + 1; c < D; ++c) M[r][c] = fma(-f, M[k][c], M[r][c]);
+#pragma unroll
+      for (int c = 0; c < D; ++c) X[r][c] = fma(-f, X[k][c], X[r][c]);
+    }
+  }
+#pragma unroll
+  for (int k = D - 1; k >= 0; --k) {
+    const double inv = 1.0 / M[k][k];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      double t = X[k][c];
+#pragma unroll
+      for (int r = k + 1; r < D; ++r) t = fma(-M[k][r], X[r][c], t);
+      X[k][c] = t * inv;
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) ps_filter_scan_reg_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                                 int64_t B, int64_t nchunk, int64_t nsum, int64_t stride) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * nsum) return;
+  const int64_t b = gid / nsum, c = gid % nsum;
+  constexpr int NE = 3 * D * D + 2 * D;
+  const double* r = in + (b * nchunk + c) * NE;
+  double* o = out + (b * nchunk + c) * NE;
+  if (c < stride) {                                       // identity on the left
+#pragma unroll
+    for (int i = 0; i < NE; ++i) o[i] = r[i];
+    return;
+  }
+  const double* l = in + (b * nchunk + c - stride) * NE;
+  double Ai[D][D], Ci[D][D], Ji[D][D], Aj[D][D], Cj[D][D], Jj[D][D], bi[D], ei[D], bj[D], ej[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      Ai[i][j] = l[i * D + j]; Ci[i][j] = l[D * D + i * D + j]; Ji[i][j] = l[2 * D * D + i * D + j];
+      Aj[i][j] = r[i * D + j]; Cj[i][j] = r[D * D + i * D + j]; Jj[i][j] = r[2 * D * D + i * D + j];
+    }
+    bi[i] = l[3 * D * D + i]; ei[i] = l[3 * D * D + D + i];
+    bj[i] = r[3 * D * D + i]; ej[i] = r[3 * D * D + D + i];
+  }
+  // M1 = I + Ci Jj ;  X1 = M1^-T Aj^T (= (Aj M1^-1)^T) ;  X2 = M1^-1 Ai
+  double M1[D][D], M1T[D][D], X1[D][D], X2[D][D], t1[D], t2[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double a1 = bi[i], a2 = ej[i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int q = 0; q < D; ++q) acc = fma(Ci[i][q], Jj[q][j], acc);
+      M1[i][j] = acc;
+      M1T[j][i] = acc;
+      X1[i][j] = Aj[j][i];
+      X2[i][j] = Ai[i][j];
+      a1 = fma(Ci[i][j], ej[j], a1);                        // t1 = bi + Ci ej
+      a2 = fma(-Jj[i][j], bi[j], a2);                       // t2 = ej - Jj bi
+    }
+    t1[i] = a1;
+    t2[i] = a2;
+  }
+  small_solve<D>(M1T, X1);
+  small_solve<D>(M1, X2);
+  // A_out = X1^T Ai ; W = X1^T Ci ; C_out = W Aj^T + Cj ; b_out = X1^T t1 + bj
+  // V = X2^T Jj ; J_out = V Ai + Ji ; eta_out = X2^T t2 + ei
+  double W[D][D], V[D][D], Co[D][D], Jo[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double a1 = bj[i], a2 = ei[i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double ao = 0.0, w = 0.0, v = 0.0;
+#pragma unroll
+      for (int q = 0; q < D; ++q) {
+        ao = fma(X1[q][i], Ai[q][j], ao);
+        w = fma(X1[q][i], Ci[q][j], w);
+        v = fma(X2[q][i], Jj[q][j], v);
+      }
+      o[i * D + j] = ao;
+      W[i][j] = w;
+      V[i][j] = v;
+      a1 = fma(X1[j][i], t1[j], a1);
+      a2 = fma(X2[j][i], t2[j], a2);
+    }
+    o[3 * D * D + i] = a1;
+    o[3 * D * D + D + i] = a2;
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double co = Cj[i][j], jo = Ji[i][j];
+#pragma unroll
+      for (int q = 0; q < D; ++q) {
+        co = fma(W[i][q], Aj[j][q], co);
+        jo = fma(V[i][q], Ai[q][j], jo);
+      }
+      Co[i][j] = co;
+      Jo[i][j] = jo;
+    }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      o[D * D + i * D + j] = 0.5 * (Co[i][j] + Co[j][i]);
+      o[2 * D * D + i * D + j] = 0.5 * (Jo[i][j] + Jo[j][i]);
+    }
+}
+
+// suffix scan step of the smoother: out[c] = in[c] o in[c + stride]  (identity on the right past the end)
+template <int D>
+__global__ void __launch_bounds__(128) ps_smooth_scan_reg_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                                 int64_t B, int64_t nchunk, int64_t stride) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * nchunk) return;
+  const int64_t b = gid / nchunk, c = gid % nchunk;
+  constexpr int NS = 2 * D * D + D;
+  const double* l = in + (b * nchunk + c) * NS;
+  double* o = out + (b * nchunk + c) * NS;
+  if (c + stride >= nchunk) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) o[i] = l[i];
+    return;
+  }
+  const double* r = in + (b * nchunk + c + stride) * NS;
+  double Ei[D][D], Li[D][D], Ej[D][D], Lj[D][D], gi[D], gj[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      Ei[i][j] = l[i * D + j]; Li[i][j] = l[D * D + i * D + j];
+      Ej[i][j] = r[i * D + j]; Lj[i][j] = r[D * D + i * D + j];
+    }
+    gi[i] = l[2 * D * D + i];
+    gj[i] = r[2 * D * D + i];
+  }
+  double W[D][D], Lo[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double g = gi[i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double w = 0.0, eo = 0.0;
+#pragma unroll
+      for (int q = 0; q < D; ++q) {
+        w = fma(Ei[i][q], Lj[q][j], w);                    // Ei Lj
+        eo = fma(Ei[i][q], Ej[q][j], eo);                  // Ei Ej
+      }
+      W[i][j] = w;
+      o[i * D + j] = eo;
+      g = fma(Ei[i][j], gj[j], g);                          // Ei gj + gi
+    }
+    o[2 * D * D + i] = g;
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double acc = Li[i][j];
+#pragma unroll
+      for (int q = 0; q < D; ++q) acc = fma(W[i][q], Ei[j][q], acc);   // Ei Lj Ei^T + Li
+      Lo[i][j] = acc;
+    }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) o[D * D + i * D + j] = 0.5 * (Lo[i][j] + Lo[j][i]);
+}
+
+static bool ps_reg_scan(int d) { return d >= 1 && d <= 3 && !ps_force_grp(); }
+
+static int run_filter_scan_reg(cudaStream_t st, int d, const double* in, double* out, int64_t B, int64_t nchunk,
+                               int64_t nsum, int64_t stride) {
+  const int64_t n = B * nsum;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (d == 1) ps_filter_scan_reg_kernel<1><<<grid, 128, 0, st>>>(in, out, B, nchunk, nsum, stride);
+  else if (d == 2) ps_filter_scan_reg_kernel<2><<<grid, 128, 0, st>>>(in, out, B, nchunk, nsum, stride);
+  else ps_filter_scan_reg_kernel<3><<<grid, 128, 0, st>>>(in, out, B, nchunk, nsum, stride);
+  return cuda_status(cudaGetLastError(), "ps_filter_scan_reg_kernel launch");
+}
+static int run_smooth_scan_reg(cudaStream_t st, int d, const double* in, double* out, int64_t B, int64_t nchunk,
+                               int64_t stride) {
+  const int64_t n = B * nchunk;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (d == 1) ps_smooth_scan_reg_kernel<1><<<grid, 128, 0, st>>>(in, out, B, nchunk, stride);
+  else if (d == 2) ps_smooth_scan_reg_kernel<2><<<grid, 128, 0, st>>>(in, out, B, nchunk, stride);
+  else ps_smooth_scan_reg_kernel<3><<<grid, 128, 0, st>>>(in, out, B, nchunk, stride);
+  return cuda_status(cudaGetLastError(), "ps_smooth_scan_reg_kernel launch");
+}
+
 template <int G>
 static int run_filter_apply(cudaStream_t st, const double* prefix, int64_t B, int64_t nchunk, int64_t nsum,
                             const double* m0, int64_t m0_bs, const double* P0, int64_t P0_bs, double* bnd_m,
@@ -1089,7 +1317,8 @@ int pscan_filter_local(cudaStream_t st, int d, int m, int disc_mode, int nblk, b
   if (rc) return rc;
   double* in = w.e0; double* out = w.e1;
   for (int64_t stride = 1; stride < nsum; stride *= 2) {
-    rc = PS_BY_G(run_filter_scan, st, in, out, a.B, nchunk, nsum, stride, Lc);
+    rc = ps_reg_scan(d) ? run_filter_scan_reg(st, d, in, out, a.B, nchunk, nsum, stride)
+                        : PS_BY_G(run_filter_scan, st, in, out, a.B, nchunk, nsum, stride, Lc);
     if (rc) return rc;
     double* t = in; in = out; out = t;
   }
@@ -1340,7 +1569,8 @@ int pscan_smooth_local(cudaStream_t st, int d, int disc_mode, int nblk, SeqSmoot
   }
   double* in = w.e0; double* out = w.e1;
   for (int64_t stride = 1; stride < nchunk; stride *= 2) {
-    rc = PS_BY_G(run_smooth_scan, st, in, out, a.B, nchunk, stride, Ls);
+    rc = ps_reg_scan(d) ? run_smooth_scan_reg(st, d, in, out, a.B, nchunk, stride)
+                        : PS_BY_G(run_smooth_scan, st, in, out, a.B, nchunk, stride, Ls);
     if (rc) return rc;
     double* t = in; in = out; out = t;
   }
