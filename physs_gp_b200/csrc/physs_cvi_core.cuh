@@ -21,9 +21,12 @@ constexpr double kInvSqrt2Pi = 0.39894228040143267793994605993438;
 constexpr double kInvSqrt2 = 0.70710678118654752440084436210485;
 
 // l(f), l'(f), l''(f) of the scalar likelihoods (general.py:9-26).
-PHYSS_HD void poisson_exp_terms(double y, double f, double binsize, double& l, double& d1, double& d2) {
+// `c0` = y log(binsize) - lgamma(y + 1): the part of l(f) that does not depend on f, evaluated ONCE per site by
+// the caller (lgamma inside the quadrature loop cost more than the exp it sits next to).
+PHYSS_HD double poisson_exp_const(double y, double binsize) { return y * log(binsize) - lgamma(y + 1.0); }
+PHYSS_HD void poisson_exp_terms(double y, double f, double binsize, double c0, double& l, double& d1, double& d2) {
   const double lam = exp(f) * binsize;
-  l = y * (f + log(binsize)) - lam - lgamma(y + 1.0);
+  l = fma(y, f, c0) - lam;
   d1 = y - lam;
   d2 = -lam;
 }
@@ -187,10 +190,11 @@ PHYSS_HD double cvi_ell_grads(const double (&qm)[D], const double (&qS)[D][D], c
       const double ya = obs ? y[a] : 0.0;
       const double sd = sqrt(2.0 * fv);
       double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+      const double c0 = (LIK == CVI_LIK_POISSON_EXP) ? poisson_exp_const(ya, lik_param) : 0.0;
       for (int q = 0; q < K; ++q) {
         const double f = fma(sd, ghx[q], fmu[a]);
         double l, d1, d2;
-        if (LIK == CVI_LIK_POISSON_EXP) poisson_exp_terms(ya, f, lik_param, l, d1, d2);
+        if (LIK == CVI_LIK_POISSON_EXP) poisson_exp_terms(ya, f, lik_param, c0, l, d1, d2);
         else bernoulli_probit_terms(ya, f, l, d1, d2);
         e0 = fma(ghw[q], l, e0);
         e1 = fma(ghw[q], d1, e1);

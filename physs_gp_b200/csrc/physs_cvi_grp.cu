@@ -126,10 +126,11 @@ __global__ void cvi_grp_kernel(const CviArgs p, const CviGrpLayout L) {
         const double ya = obs ? y[a] : 0.0;
         const double sd = sqrt(2.0 * fv);
         double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+        const double c0 = (LIK == CVI_LIK_POISSON_EXP) ? poisson_exp_const(ya, p.lik_param) : 0.0;
         for (int q = 0; q < p.K; ++q) {
           const double f = fma(sd, p.ghx[q], fmu[a]);
           double l, d1, d2;
-          if (LIK == CVI_LIK_POISSON_EXP) poisson_exp_terms(ya, f, p.lik_param, l, d1, d2);
+          if (LIK == CVI_LIK_POISSON_EXP) poisson_exp_terms(ya, f, p.lik_param, c0, l, d1, d2);
           else bernoulli_probit_terms(ya, f, l, d1, d2);
           e0 = fma(p.ghw[q], l, e0);
           e1 = fma(p.ghw[q], d1, e1);
