@@ -20,7 +20,7 @@
 namespace physs {
 
 template <int D, int S, bool GIVEN>
-__global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, const VjpOut o) {
+__global__ void __launch_bounds__(64) kf_vjp_kernel(const SeqFilterArgs p, const VjpOut o) {
   constexpr int NB = D / S;
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= p.B) return;
@@ -31,7 +31,13 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
   // so the DRAM latency of a dependent load per step would bound the kernel (measured 4.5x slower without).
   constexpr int PW = (D % 2 == 0) ? 2 : 1;                       // doubles per copy piece (16 B when rows allow)
   constexpr int NPC = (D * D + D) / PW;                          // pieces per step
-  __shared__ __align__(16) double ring[2][NPC][128][PW];
+  constexpr int TPB = 64;                                        // threads per block (launch)
+  __shared__ __align__(16) double ring[2][NPC][TPB][PW];
+  // per-thread copies of Pinf and of dA/dlam live in shared memory ([entry][thread], conflict-free): in registers
+  // they spilled, re-read from global memory every step they stalled the dependency chain (long scoreboard)
+  __shared__ double sPinf[GIVEN ? 1 : D * D][TPB];
+  __shared__ double sdA[GIVEN ? 1 : D * S][TPB];
+  __shared__ double sgP[GIVEN ? 1 : D * D][TPB];                 // running gradient w.r.t. Pinf
   const int tid = threadIdx.x;
   auto issue = [&](int64_t k) {
     const int st = (int)(k & 1);
@@ -68,16 +74,21 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
   if (!GIVEN) {
 #pragma unroll
     for (int q = 0; q < NB; ++q) lam[q] = p.lam[b * p.lam_bs + q];
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) sPinf[e][threadIdx.x] = p.Pinf[b * p.Pinf_bs + e];
   }
 
-  double mbar[D], Pbar[D][D], gH[D], gPinf[D][D], glam[NB];
+  double mbar[D], Pbar[D][D], gH[D], glam[NB];
   double gRsum = 0.0;
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     mbar[i] = 0.0;
     gH[i] = 0.0;
 #pragma unroll
-    for (int j = 0; j < D; ++j) { Pbar[i][j] = 0.0; gPinf[i][j] = 0.0; }
+    for (int j = 0; j < D; ++j) {
+      Pbar[i][j] = 0.0;
+      if (!GIVEN) sgP[i * D + j][threadIdx.x] = 0.0;
+    }
   }
 #pragma unroll
   for (int q = 0; q < NB; ++q) glam[q] = 0.0;
@@ -108,7 +119,7 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
       for (int e = 0; e < D; ++e) m[e] = ring[st][D * D / PW + e / PW][tid][e % PW];
     }
     // ---- transition (dense D x D; off-block entries are zero in DISC_MATERN mode)
-    double A[D][D], Q[D][D], dA[NB][S][S];
+    double A[D][D], Q[D][D];
     if (GIVEN) {
 #pragma unroll
       for (int i = 0; i < D; ++i)
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
 #pragma unroll
           for (int j = 0; j < S; ++j) {
             A[q * S + i][q * S + j] = a[i][j].v;
-            dA[q][i][j] = a[i][j].d;
+            sdA[GIVEN ? 0 : (q * S + i) * S + j][tid] = a[i][j].d;
           }
       }
     }
@@ -149,7 +160,7 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
-        for (int j = 0; j < D; ++j) P[i][j] -= p.Pinf[b * p.Pinf_bs + i * D + j];     // same address every step: L1
+        for (int j = 0; j < D; ++j) P[i][j] -= sPinf[GIVEN ? 0 : i * D + j][tid];
     }
 #pragma unroll
     for (int i = 0; i < D; ++i)
@@ -164,7 +175,7 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
     for (int i = 0; i < D; ++i)
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        double acc = GIVEN ? Q[i][j] : p.Pinf[b * p.Pinf_bs + i * D + j];
+        double acc = GIVEN ? Q[i][j] : sPinf[GIVEN ? 0 : i * D + j][tid];
 #pragma unroll
         for (int l = 0; l < D; ++l) acc = fma(AP[i][l], A[j][l], acc);
         Pp[i][j] = acc;
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
-        for (int j = 0; j < D; ++j) gPinf[i][j] += Ppbar[i][j] - Pbar[i][j];
+        for (int j = 0; j < D; ++j) sgP[GIVEN ? 0 : i * D + j][tid] += Ppbar[i][j] - Pbar[i][j];
       // chain to lam through the closed forms on dual numbers
 #pragma unroll
       for (int q = 0; q < NB; ++q) {
@@ -294,7 +305,7 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
 #pragma unroll
         for (int i = 0; i < S; ++i)
 #pragma unroll
-          for (int j = 0; j < S; ++j) acc = fma(Abar[q * S + i][q * S + j], dA[q][i][j], acc);
+          for (int j = 0; j < S; ++j) acc = fma(Abar[q * S + i][q * S + j], sdA[GIVEN ? 0 : (q * S + i) * S + j][tid], acc);
         glam[q] += acc;
       }
     }
@@ -307,7 +318,7 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
 #pragma unroll
     for (int j = 0; j < D; ++j) {
       if (o.gP0) o.gP0[b * D * D + i * D + j] = Pbar[i][j];
-      if (!GIVEN && o.gPinf) o.gPinf[b * D * D + i * D + j] = gPinf[i][j];
+      if (!GIVEN && o.gPinf) o.gPinf[b * D * D + i * D + j] = sgP[GIVEN ? 0 : i * D + j][tid];
     }
   }
   if (!GIVEN && o.glam) {
@@ -319,7 +330,7 @@ __global__ void __launch_bounds__(128) kf_vjp_kernel(const SeqFilterArgs p, cons
 
 template <int D, int S, bool GIVEN>
 static int vjp_launch(cudaStream_t st, const SeqFilterArgs& a, const VjpOut& o) {
-  const int threads = 128;
+  const int threads = 64;                                        // = TPB of the kernel
   const int64_t grid = (a.B + threads - 1) / threads;
   kf_vjp_kernel<D, S, GIVEN><<<(unsigned)grid, threads, 0, st>>>(a, o);
   return cuda_status(cudaGetLastError(), "kf_vjp_kernel launch");
