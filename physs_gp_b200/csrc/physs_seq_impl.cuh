@@ -525,11 +525,18 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_smooth_kernel(const 
 
 // ------------------------------------------------------------------------------------------ launch
 static inline int pick_block(int64_t B) {
-  // With few series the limiter is FP64 issue per SM sub-partition: spread warps as thinly as
-  // possible (one warp per CTA) until every sub-partition of the 148 SMs has one.
-  if (B <= 148LL * 4 * 32) return 32;
-  if (B <= 148LL * 8 * 32) return 64;
-  return 128;
+  // Every thread lives for the whole launch (one series each), so what matters is how evenly the warps fall on
+  // the 148 SMs: the SM with the most warps finishes last.  Pick the block size (32 / 64 / 128 threads) with the
+  // fewest warps on the fullest SM -- e.g. 32,768 series: 1024 one-warp blocks put 7 warps on the fullest SM,
+  // 256 four-warp blocks put 8 there (and leave 40 SMs with 4).  Ties go to the larger block.
+  int best = 128;
+  int64_t best_warps = -1;
+  for (int bs = 128; bs >= 32; bs /= 2) {
+    const int64_t blocks = (B + bs - 1) / bs;
+    const int64_t warps = ((blocks + 147) / 148) * (bs / 32);
+    if (best_warps < 0 || warps < best_warps) { best_warps = warps; best = bs; }
+  }
+  return best;
 }
 
 // ------------------------------------------------------------------------- parallel-in-time summaries
