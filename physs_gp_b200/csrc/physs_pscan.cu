@@ -1176,7 +1176,7 @@ __global__ void __launch_bounds__(128) ps_smooth_scan_reg_kernel(const double* _
     for (int j = 0; j < D; ++j) o[D * D + i * D + j] = 0.5 * (Lo[i][j] + Lo[j][i]);
 }
 
-static bool ps_reg_scan(int d) { return d >= 1 && d <= 3 && !ps_force_grp(); }
+static bool ps_reg_scan(int d) { return d >= 1 && d <= 4 && !ps_force_grp(); }
 
 static int run_filter_scan_reg(cudaStream_t st, int d, const double* in, double* out, int64_t B, int64_t nchunk,
                                int64_t nsum, int64_t stride) {
@@ -1184,7 +1184,8 @@ static int run_filter_scan_reg(cudaStream_t st, int d, const double* in, double*
   const unsigned grid = (unsigned)((n + 127) / 128);
   if (d == 1) ps_filter_scan_reg_kernel<1><<<grid, 128, 0, st>>>(in, out, B, nchunk, nsum, stride);
   else if (d == 2) ps_filter_scan_reg_kernel<2><<<grid, 128, 0, st>>>(in, out, B, nchunk, nsum, stride);
-  else ps_filter_scan_reg_kernel<3><<<grid, 128, 0, st>>>(in, out, B, nchunk, nsum, stride);
+  else if (d == 3) ps_filter_scan_reg_kernel<3><<<grid, 128, 0, st>>>(in, out, B, nchunk, nsum, stride);
+  else ps_filter_scan_reg_kernel<4><<<grid, 128, 0, st>>>(in, out, B, nchunk, nsum, stride);
   return cuda_status(cudaGetLastError(), "ps_filter_scan_reg_kernel launch");
 }
 static int run_smooth_scan_reg(cudaStream_t st, int d, const double* in, double* out, int64_t B, int64_t nchunk,
@@ -1193,7 +1194,8 @@ static int run_smooth_scan_reg(cudaStream_t st, int d, const double* in, double*
   const unsigned grid = (unsigned)((n + 127) / 128);
   if (d == 1) ps_smooth_scan_reg_kernel<1><<<grid, 128, 0, st>>>(in, out, B, nchunk, stride);
   else if (d == 2) ps_smooth_scan_reg_kernel<2><<<grid, 128, 0, st>>>(in, out, B, nchunk, stride);
-  else ps_smooth_scan_reg_kernel<3><<<grid, 128, 0, st>>>(in, out, B, nchunk, stride);
+  else if (d == 3) ps_smooth_scan_reg_kernel<3><<<grid, 128, 0, st>>>(in, out, B, nchunk, stride);
+  else ps_smooth_scan_reg_kernel<4><<<grid, 128, 0, st>>>(in, out, B, nchunk, stride);
   return cuda_status(cudaGetLastError(), "ps_smooth_scan_reg_kernel launch");
 }
 
