@@ -97,6 +97,38 @@ ffi::Error RtsSmoothImpl(cudaStream_t stream, F64 A, F64 Q, F64 lam, F64 dt, F64
   return Status(rc);
 }
 
+// filter_vjp('b200'): the backward rule of the jax.custom_vjp around the filter call.
+// operands: the filter's operands, its results (mf, Pf) and the cotangent g_lml [B]
+// results  : DISC_GIVEN  -> gA, gQ [B, T, d, d] (glam, gPinf empty);  DISC_MATERN -> glam [B, nblk], gPinf [B, d, d]
+//            (gA, gQ empty);  always gH [B, m, d], gR [B, T, m, m] (per step), gm0 [B, d], gP0 [B, d, d]
+ffi::Error KfFilterVjpImpl(cudaStream_t stream, F64 A, F64 Q, F64 lam, F64 dt, F64 Pinf, F64 m0, F64 P0, F64 H,
+                           F64 Y, F64 R, F64 mf, F64 Pf, F64 g_lml, F64Out gA, F64Out gQ, F64Out glam,
+                           F64Out gPinf, F64Out gH, F64Out gR, F64Out gm0, F64Out gP0, int32_t disc_mode,
+                           int32_t nblk, int32_t time_major, int32_t h_identity, double jitter) {
+  const auto ydim = Y.dimensions();
+  if (ydim.size() != 3) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "Y must be rank 3");
+  const int64_t B = time_major ? ydim[1] : ydim[0];
+  const int64_t T = time_major ? ydim[0] : ydim[1];
+  const int32_t m = static_cast<int32_t>(ydim[2]);
+  const int32_t d = static_cast<int32_t>(P0.dimensions().back());
+  const int64_t dd = static_cast<int64_t>(d) * d;
+  const auto rdim = R.dimensions();
+  const int64_t R_t = (rdim.size() >= 3 && rdim[rdim.size() - 3] > 1) ? static_cast<int64_t>(m) * m : 0;
+  const int64_t R_b = (rdim.size() == 4 && rdim[0] > 1) ? (R_t ? T * m * m : static_cast<int64_t>(m) * m) : 0;
+  const bool given = disc_mode == PHYSS_DISC_GIVEN;
+  const int rc = physs_kf_filter_vjp_f64(
+      stream, B, T, time_major ? 1 : T, time_major ? B : 1, d, m, disc_mode, nblk,
+      given ? A.typed_data() : nullptr, BatchStride(A, 3, T * dd), given ? Q.typed_data() : nullptr,
+      BatchStride(Q, 3, T * dd), given ? nullptr : lam.typed_data(), BatchStride(lam, 1, nblk), dt.typed_data(),
+      BatchStride(dt, 1, T), given ? nullptr : Pinf.typed_data(), BatchStride(Pinf, 2, dd), m0.typed_data(),
+      BatchStride(m0, 1, d), P0.typed_data(), BatchStride(P0, 2, dd), h_identity ? nullptr : H.typed_data(),
+      BatchStride(H, 2, static_cast<int64_t>(m) * d), Y.typed_data(), R.typed_data(), R_b, R_t, jitter,
+      mf.typed_data(), Pf.typed_data(), g_lml.typed_data(), given ? gA->typed_data() : nullptr,
+      given ? gQ->typed_data() : nullptr, given ? nullptr : glam->typed_data(), given ? nullptr : gPinf->typed_data(),
+      gH->typed_data(), gR->typed_data(), /*gR_sum=*/nullptr, gm0->typed_data(), gP0->typed_data());
+  return Status(rc);
+}
+
 }  // namespace
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(
@@ -118,3 +150,15 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Ret<F64>().Ret<F64>()                                       // ms, Ps
         .Attr<int32_t>("disc_mode").Attr<int32_t>("nblk").Attr<int32_t>("time_major")
         .Attr<int32_t>("full_state").Attr<double>("jitter"));
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(
+    PhyssKfFilterVjpFfi, KfFilterVjpImpl,
+    ffi::Ffi::Bind()
+        .Ctx<ffi::PlatformStream<cudaStream_t>>()
+        .Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>()      // A, Q, lam, dt, P_inf
+        .Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>()      // m0, P0, H, Y, R
+        .Arg<F64>().Arg<F64>().Arg<F64>()                            // mf, Pf, g_lml
+        .Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>()                 // gA, gQ, glam, gPinf
+        .Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>()                 // gH, gR, gm0, gP0
+        .Attr<int32_t>("disc_mode").Attr<int32_t>("nblk").Attr<int32_t>("time_major")
+        .Attr<int32_t>("h_identity").Attr<double>("jitter"));
