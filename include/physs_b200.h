@@ -115,6 +115,29 @@ int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_bstrid
                          double jitter,
                          double* ms, double* Ps);
 
+/* Filter + smoother in one call (`physs_kf_filter_smooth_f64`): physs_kf_filter_f64
+ * followed by physs_rts_smooth_f64 on the same stream with the filter's outputs -- what
+ * `BASE_SDE_GP.filter_and_smooth` (models/sde_gp.py:212-302) does with two dispatched calls; one FFI custom call
+ * instead of two.  dt_smooth [., T] is the smoother's convention (dt[k] = t_{k+1} - t_k, dt[T-1] = 0). */
+int physs_kf_filter_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                               int32_t d, int32_t m,
+                               int32_t disc_mode, int32_t nblk,
+                               const double* A, int64_t A_bstride,
+                               const double* Q, int64_t Q_bstride,
+                               const double* lam, int64_t lam_bstride,
+                               const double* dt, int64_t dt_bstride,
+                               const double* Pinf, int64_t Pinf_bstride,
+                               const double* m0, int64_t m0_bstride,
+                               const double* P0, int64_t P0_bstride,
+                               const double* H, int64_t H_bstride,
+                               const double* Y,
+                               const double* R, int64_t R_bstride, int64_t R_tstride,
+                               double jitter,
+                               const double* A_smooth, const double* Q_smooth,
+                               const double* dt_smooth, int64_t dt_smooth_bstride,
+                               const double* Hout, int32_t mo,
+                               double* mf, double* Pf, double* lml, double* lml_k, double* ms, double* Ps);
+
 /* Reverse pass (vector-Jacobian product) of physs_kf_filter_f64's lml: d lml[b] / d (inputs), scaled by g_lml[b].
  * Replaces `jax.jacrev` / `jax.grad` THROUGH filter('sequential') in the reference's hyper-parameter steps
  * (trainers/trainer.py:43,128-136; trainers/standard.py:58-91): the backward half of a `jax.custom_vjp` around

@@ -43,6 +43,8 @@ SIGNATURES = {
         _ptr, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32,
         _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
         _ptr, _ptr, _ptr, _c_i32, _c_f64, _ptr, _ptr]),
+    "physs_kf_filter_smooth_f64": (ctypes.c_int, _FILTER_HEAD + [_ptr, _ptr, _ptr, _c_i64, _ptr, _c_i32,
+                                                                _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "physs_kf_vjp_supported": (ctypes.c_int, [_c_i32, _c_i32, _c_i32, _c_i32]),
     "physs_kf_filter_vjp_f64": (ctypes.c_int, _FILTER_HEAD + [_ptr] * 12),
     "physs_pscan_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i32, _c_i64]),

@@ -180,6 +180,18 @@ int physs_kf_filter_f64(FILTER_PARAMS, double* mf, double* Pf, double* lml, doub
   return run_filter_any((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a);
 }
 
+int physs_kf_filter_smooth_f64(FILTER_PARAMS, const double* A_smooth, const double* Q_smooth, const double* dt_smooth,
+                               int64_t dt_smooth_bstride, const double* Hout, int32_t mo, double* mf, double* Pf,
+                               double* lml, double* lml_k, double* ms, double* Ps) {
+  int rc = physs_kf_filter_f64(FILTER_ARGS, mf, Pf, lml, lml_k);
+  if (rc) return rc;
+  // DISC_GIVEN: the smoother's transitions follow ITS dt convention (A_smooth[k] = expm(F dt_smooth[k]))
+  return physs_rts_smooth_f64(stream, B, T, step_bstride, step_tstride, d, disc_mode, nblk,
+                              disc_mode == PHYSS_DISC_GIVEN ? A_smooth : A, A_bstride,
+                              disc_mode == PHYSS_DISC_GIVEN ? Q_smooth : Q, Q_bstride, lam, lam_bstride, dt_smooth,
+                              dt_smooth_bstride, Pinf, Pinf_bstride, mf, Pf, Hout, mo, jitter, ms, Ps);
+}
+
 int physs_kf_vjp_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {
   return vjp_supported(d, m, disc_mode, nblk) ? 1 : 0;
 }

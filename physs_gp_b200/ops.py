@@ -178,6 +178,38 @@ def kf_filter(dt, Y, R, H, m0, P0, disc, jitter=None, want_lml_k=False, out=None
     return lml, mf, Pf
 
 
+def kf_filter_smooth(dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s=None, Hout=None, jitter=None, stream=None):
+    """Filter + smoother in ONE C-ABI call (physs_kf_filter_smooth_f64): same results as `kf_filter` followed by
+    `rts_smooth`.  dt_f / dt_s are the two dt conventions; disc_s (DISC_GIVEN only) carries the smoother's A_k, Q_k.
+    Returns (lml, mf, Pf, ms, Ps)."""
+    lib = _lib.load()
+    p = _pack_filter(dt_f, Y, R, H, m0, P0, disc_f, jitter, stream)
+    mf, Pf, lml, _ = _filter_outputs(p, None, False)
+    B, T, d = p.B, p.T, p.d
+    dtv, sdt = _bview(dt_s, "dt_s", (B, T), 1)
+    pA = pQ = None
+    keep = []
+    if disc_f.mode == _lib.DISC_GIVEN:
+        if disc_s is None:
+            raise ValueError("DISC_GIVEN needs disc_s (the smoother's transitions)")
+        keep, (pA, bA), (pQ, bQ), _, _ = _disc_args(disc_s, B, T, d)
+        if (bA, bQ) != (p.head[10], p.head[12]):
+            raise ValueError("disc_f and disc_s must share their batch layout")
+    if Hout is None:
+        mo, Hptr, mp = 0, None, d
+    else:
+        Hout = _dev(Hout, "Hout").contiguous()
+        mo, Hptr, mp = Hout.shape[0], Hout.data_ptr(), Hout.shape[0]
+    ms = empty_steps(B, T, (mp,), p.dev, p.tmaj)
+    Ps = empty_steps(B, T, (mp, mp), p.dev, p.tmaj)
+    with torch.cuda.device(p.dev):
+        st = lib.physs_kf_filter_smooth_f64(*p.head, pA, pQ, dtv.data_ptr(), sdt[0], Hptr, mo, mf.data_ptr(),
+                                            Pf.data_ptr(), lml.data_ptr(), None, ms.data_ptr(), Ps.data_ptr())
+    _lib.check(st, "physs_kf_filter_smooth_f64")
+    del keep
+    return lml, mf, Pf, ms, Ps
+
+
 def kf_filter_vjp(dt, Y, R, H, m0, P0, disc, mf, Pf, g_lml=None, jitter=None, want_R_step=False, stream=None):
     """Reverse pass of `kf_filter`'s lml (include/physs_b200.h: physs_kf_filter_vjp_f64): gradients of
     sum_b g_lml[b] * lml[b] with respect to the filter's inputs, given its outputs (mf, Pf).
