@@ -1176,6 +1176,166 @@ __global__ void __launch_bounds__(128) ps_smooth_scan_reg_kernel(const double* _
     for (int j = 0; j < D; ++j) o[D * D + i * D + j] = 0.5 * (Lo[i][j] + Lo[j][i]);
 }
 
+// apply steps in registers (same role as ps_filter_apply_kernel / ps_smooth_apply_kernel above)
+template <int D>
+__global__ void __launch_bounds__(128) ps_filter_apply_reg_kernel(const double* __restrict__ prefix, int64_t B,
+                                                                  int64_t nchunk, int64_t nsum,
+                                                                  const double* __restrict__ m0, int64_t m0_bs,
+                                                                  const double* __restrict__ P0, int64_t P0_bs,
+                                                                  double* __restrict__ bnd_m, double* __restrict__ bnd_P) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * nsum) return;
+  const int64_t b = gid / nsum, c = gid % nsum;
+  constexpr int NE = 3 * D * D + 2 * D;
+  const double* r = prefix + (b * nchunk + c) * NE;
+  double Ci[D][D], bi[D], Aj[D][D], Cj[D][D], Jj[D][D], bj[D], ej[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      Ci[i][j] = P0[b * P0_bs + i * D + j];
+      Aj[i][j] = r[i * D + j]; Cj[i][j] = r[D * D + i * D + j]; Jj[i][j] = r[2 * D * D + i * D + j];
+    }
+    bi[i] = m0[b * m0_bs + i];
+    bj[i] = r[3 * D * D + i]; ej[i] = r[3 * D * D + D + i];
+  }
+  // left = bare state (A = 0, b = m0, C = P0, J = 0, eta = 0):  M1 = I + P0 Jj ; X1 = M1^-T Aj^T ; t1 = m0 + P0 ej
+  double M1T[D][D], X1[D][D], t1[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double a1 = bi[i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int q = 0; q < D; ++q) acc = fma(Ci[i][q], Jj[q][j], acc);
+      M1T[j][i] = acc;
+      X1[i][j] = Aj[j][i];
+      a1 = fma(Ci[i][j], ej[j], a1);
+    }
+    t1[i] = a1;
+  }
+  small_solve<D>(M1T, X1);
+  double W[D][D], Co[D][D];
+  double* om = bnd_m + (b * nchunk + c + 1) * D;
+  double* oP = bnd_P + (b * nchunk + c + 1) * D * D;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double a1 = bj[i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double w = 0.0;
+#pragma unroll
+      for (int q = 0; q < D; ++q) w = fma(X1[q][i], Ci[q][j], w);
+      W[i][j] = w;
+      a1 = fma(X1[j][i], t1[j], a1);
+    }
+    om[i] = a1;                                            // b_out = X1^T t1 + bj
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double co = Cj[i][j];
+#pragma unroll
+      for (int q = 0; q < D; ++q) co = fma(W[i][q], Aj[j][q], co);
+      Co[i][j] = co;                                       // C_out = W Aj^T + Cj
+    }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) oP[i * D + j] = 0.5 * (Co[i][j] + Co[j][i]);
+  if (c == 0) {                                            // boundary 0 is the start state itself
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      bnd_m[(b * nchunk) * D + i] = bi[i];
+#pragma unroll
+      for (int j = 0; j < D; ++j) bnd_P[(b * nchunk) * D * D + i * D + j] = Ci[i][j];
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) ps_smooth_apply_reg_kernel(const double* __restrict__ suffix, int64_t B,
+                                                                  int64_t nchunk, const double* __restrict__ start_m,
+                                                                  const double* __restrict__ start_P,
+                                                                  double* __restrict__ bnd_m, double* __restrict__ bnd_P) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * nchunk) return;
+  const int64_t b = gid / nchunk, c = gid % nchunk;
+  constexpr int NS = 2 * D * D + D;
+  double* om = bnd_m + (b * nchunk + c) * D;
+  double* oP = bnd_P + (b * nchunk + c) * D * D;
+  double m[D], P[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    m[i] = start_m[b * D + i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) P[i][j] = start_P[b * D * D + i * D + j];
+  }
+  if (c + 1 >= nchunk) {                                   // the last chunk starts from the start state itself
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      om[i] = m[i];
+#pragma unroll
+      for (int j = 0; j < D; ++j) oP[i * D + j] = P[i][j];
+    }
+    return;
+  }
+  const double* l = suffix + (b * nchunk + c + 1) * NS;    // (E, L, g) of chunks c + 1 .. end
+  double E[D][D], W[D][D], Lo[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) E[i][j] = l[i * D + j];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double g = l[2 * D * D + i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double w = 0.0;
+#pragma unroll
+      for (int q = 0; q < D; ++q) w = fma(E[i][q], P[q][j], w);
+      W[i][j] = w;
+      g = fma(E[i][j], m[j], g);
+    }
+    om[i] = g;                                             // E m + g
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double acc = l[D * D + i * D + j];
+#pragma unroll
+      for (int q = 0; q < D; ++q) acc = fma(W[i][q], E[j][q], acc);
+      Lo[i][j] = acc;                                      // E P E^T + L
+    }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) oP[i * D + j] = 0.5 * (Lo[i][j] + Lo[j][i]);
+}
+
+static int run_filter_apply_reg(cudaStream_t st, int d, const double* prefix, int64_t B, int64_t nchunk, int64_t nsum,
+                                const double* m0, int64_t m0_bs, const double* P0, int64_t P0_bs, double* bnd_m,
+                                double* bnd_P) {
+  const int64_t n = B * nsum;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+#define PHYSS_AP(D_) ps_filter_apply_reg_kernel<D_><<<grid, 128, 0, st>>>(prefix, B, nchunk, nsum, m0, m0_bs, P0, P0_bs, bnd_m, bnd_P)
+  if (d == 1) PHYSS_AP(1); else if (d == 2) PHYSS_AP(2); else if (d == 3) PHYSS_AP(3); else PHYSS_AP(4);
+#undef PHYSS_AP
+  return cuda_status(cudaGetLastError(), "ps_filter_apply_reg_kernel launch");
+}
+static int run_smooth_apply_reg(cudaStream_t st, int d, const double* suffix, int64_t B, int64_t nchunk,
+                                const double* start_m, const double* start_P, double* bnd_m, double* bnd_P) {
+  const int64_t n = B * nchunk;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+#define PHYSS_AP(D_) ps_smooth_apply_reg_kernel<D_><<<grid, 128, 0, st>>>(suffix, B, nchunk, start_m, start_P, bnd_m, bnd_P)
+  if (d == 1) PHYSS_AP(1); else if (d == 2) PHYSS_AP(2); else if (d == 3) PHYSS_AP(3); else PHYSS_AP(4);
+#undef PHYSS_AP
+  return cuda_status(cudaGetLastError(), "ps_smooth_apply_reg_kernel launch");
+}
+
 static bool ps_reg_scan(int d) { return d >= 1 && d <= 4 && !ps_force_grp(); }
 
 static int run_filter_scan_reg(cudaStream_t st, int d, const double* in, double* out, int64_t B, int64_t nchunk,
@@ -1351,7 +1511,8 @@ int pscan_filter_finish(cudaStream_t st, int d, int m, int disc_mode, int nblk, 
   cudaError_t e;
   if (nchunk > 1) {
     const double* prefix = ps_scan_result(w, had_total ? nchunk : nchunk - 1);
-    rc = PS_BY_G(run_filter_apply, st, prefix, a.B, nchunk, nchunk - 1, sm0, sm0_bs, sP0, sP0_bs, w.bnd_m, w.bnd_P, Lc);
+    rc = ps_reg_scan(d) ? run_filter_apply_reg(st, d, prefix, a.B, nchunk, nchunk - 1, sm0, sm0_bs, sP0, sP0_bs, w.bnd_m, w.bnd_P)
+                        : PS_BY_G(run_filter_apply, st, prefix, a.B, nchunk, nchunk - 1, sm0, sm0_bs, sP0, sP0_bs, w.bnd_m, w.bnd_P, Lc);
     if (rc) return rc;
   } else {
     rc = ps_copy_rows(st, w.bnd_m, d, sm0, sm0_bs, d, a.B, "pscan filter: copy of the start mean");
@@ -1607,7 +1768,8 @@ int pscan_smooth_finish(cudaStream_t st, int d, int mo, int disc_mode, int nblk,
   }
   if (nchunk > 1) {
     const double* suffix = ps_scan_result(w, nchunk);
-    rc = PS_BY_G(run_smooth_apply, st, suffix, a.B, nchunk, start_m, start_P, w.bnd_m, w.bnd_P, Ls);
+    rc = ps_reg_scan(d) ? run_smooth_apply_reg(st, d, suffix, a.B, nchunk, start_m, start_P, w.bnd_m, w.bnd_P)
+                        : PS_BY_G(run_smooth_apply, st, suffix, a.B, nchunk, start_m, start_P, w.bnd_m, w.bnd_P, Ls);
     if (rc) return rc;
   } else {
     e = cudaMemcpyAsync(w.bnd_m, start_m, a.B * d * 8, cudaMemcpyDeviceToDevice, st);
