@@ -131,7 +131,27 @@ __device__ __forceinline__ void mm_nt(double* __restrict__ C, const double* __re
         a[2 * l2 + 1] = t.y;
       }
     }
-    for (int j = 0; j < m; ++j) {
+    // two output columns per pass: four independent accumulation chains instead of two (the DM-long dot
+    // products are latency-bound with one warp per scheduler)
+    int j = 0;
+    for (; j + 1 < m; j += 2) {
+      const double2* __restrict__ br0 = reinterpret_cast<const double2*>(B + j * LD);
+      const double2* __restrict__ br1 = reinterpret_cast<const double2*>(B + (j + 1) * LD);
+      double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+#pragma unroll
+      for (int l2 = 0; l2 < DM / 2; ++l2) {
+        const double2 b0 = br0[l2], b1 = br1[l2];
+        a00 = fma(a[2 * l2], b0.x, a00);
+        a01 = fma(a[2 * l2 + 1], b0.y, a01);
+        a10 = fma(a[2 * l2], b1.x, a10);
+        a11 = fma(a[2 * l2 + 1], b1.y, a11);
+      }
+      const double base0 = Add ? Add[i * LD + j] : 0.0;
+      const double base1 = Add ? Add[i * LD + j + 1] : 0.0;
+      C[i * LD + j] = fma(sign, a00 + a01, base0);
+      C[i * LD + j + 1] = fma(sign, a10 + a11, base1);
+    }
+    for (; j < m; ++j) {
       const double2* __restrict__ brow = reinterpret_cast<const double2*>(B + j * LD);
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
