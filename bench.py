@@ -410,8 +410,8 @@ def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys_dev):
     device -> pinned-host read of the result.  The API is stream-ordered and never synchronises the host, so
     the H2D of later sub-batches, the kernels of the current ones and the D2H of earlier ones overlap on the two
     copy engines and the SMs; every byte still crosses PCIe inside the timed region.  Measured on this box: PCIe
-    55 GB/s H2D, 57 GB/s D2H, 50 + 50 GB/s concurrently (scratch/pcie.py): the 16 B per state-step of the
-    read-back bound this number at 3.1e9 state-steps/s; sub-batch / stream count swept in scratch/e2e_probe2.py."""
+    55 GB/s H2D, 57 GB/s D2H, 50 + 50 GB/s concurrently (tools/pcie.py): the 16 B per state-step of the
+    read-back bound this number at 3.1e9 state-steps/s; sub-batch / stream count swept in tools/e2e_probe2.py."""
     import torch
     import torch.distributed as dist
     from physs_gp_b200 import data, likelihood, models, sdes

@@ -17,8 +17,8 @@ here, so the reference cannot run on its real numerical stack.  The oracle is
 pinned in two ways instead:
   1. `tests/golden/make_golden.py` executes the reference's OWN unmodified
      source files from `/root/reference` on a small numpy-backed stand-in for
-     the `jax` API (`tests/golden/jaxshim/`), and commits the input/output
-     vectors as fixtures; `tests/test_oracle_golden.py` checks the oracle
+     the `jax` API (built inside `make_golden.py` itself), and commits the input/output
+     vectors as fixtures; `tests/test_golden.py` checks the oracle
      against them.  This pins the algorithm (step order, jitter placement,
      masks, dt conventions) to the reference source, but on numpy/LAPACK
      arithmetic rather than XLA's.

@@ -126,6 +126,17 @@ __global__ void add_diag(double* __restrict__ A, int n, double x) {
   if (i < n) A[(size_t)i * n + i] += x;
 }
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + 255) / 256); }
+// cusolverDnDpotrf reports a non-PD input only through *info and leaves a finite, partially factored matrix
+// behind.  The reference's jnp.linalg.cholesky gives NaN there and the header promises NaN on numerical
+// failure, so (stream-ordered, no host sync) a failed factorisation poisons the factor -- every later potrs
+// then yields NaN -- and, when given, the running lml.
+__global__ void poison_on_potrf_failure(const int* __restrict__ info, double* __restrict__ factor,
+                                        double* __restrict__ lml) {
+  if (*info != 0) {
+    factor[0] = nan("");
+    if (lml) lml[0] = nan("");
+  }
+}
 
 struct Ws {
   double *W, *PHt, *HPHt, *S, *Sj, *Sm, *KS, *mp, *mu, *v, *w, *lwork, *dP, *Pp, *T1, *ms, *Ps0, *Ps1, *HPs;
@@ -217,6 +228,7 @@ int physs_kf_filter_big_f64(void* stream, int64_t T, int32_t d, int32_t m, const
     CB(gemm_rm(h->blas, false, false, m, m, d, 1.0, H, d, w.PHt, m, 0.0, w.HPHt, m));       // H P_ H^T (cols masked)
     build_S<<<blocks_for((int64_t)m * m), 256, 0, st>>>(w.HPHt, Rk, y, m, jitter, w.S, w.Sj, w.Sm);
     CS(cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, m, w.Sj, m, w.lwork, w.lwork_n, w.info));
+    poison_on_potrf_failure<<<1, 1, 0, st>>>(w.info, w.Sj, nullptr);
     CS(cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, m, d, w.Sj, m, w.PHt, m, w.info));  // -> K [d x m]
     CU(cudaMemcpyAsync(m_k, w.mp, (size_t)d * 8, cudaMemcpyDeviceToDevice, st));
     CB(gemv_rm(h->blas, false, d, m, 1.0, w.PHt, m, w.v, 1.0, m_k));                        // m = m_ + K v
@@ -224,6 +236,7 @@ int physs_kf_filter_big_f64(void* stream, int64_t T, int32_t d, int32_t m, const
     CB(gemm_rm(h->blas, false, true, d, d, m, -1.0, w.KS, m, w.PHt, m, 1.0, P_k, d));       // P = P_ - K S K^T
     // lml: un-jittered S, missing rows / cols -> identity
     CS(cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, m, w.Sm, m, w.lwork, w.lwork_n, w.info));
+    poison_on_potrf_failure<<<1, 1, 0, st>>>(w.info, w.Sm, lml);
     CS(cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, m, 1, w.Sm, m, w.w, m, w.info));
     lml_accumulate<<<1, 256, 0, st>>>(w.Sm, m, w.v, w.w, y, lml);
     m_prev = m_k;
@@ -282,6 +295,7 @@ int physs_rts_smooth_big_f64(void* stream, int64_t T, int32_t d, const double* A
     axpby_kernel<<<blocks_for(d), 256, 0, st>>>(w.v, m_cur, w.mp, -1.0, d, 0, 0.0);
     add_diag<<<blocks_for(d), 256, 0, st>>>(w.Pp, d, jitter);
     CS(cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, d, w.Pp, d, w.lwork, w.lwork_n, w.info));
+    poison_on_potrf_failure<<<1, 1, 0, st>>>(w.info, w.Pp, nullptr);
     // potrs leaves (column-major) X = (Pp + jit)^-1 A Pf, i.e. row-major X^T = G  (rts_smoother.py:58-60)
     CS(cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, d, d, w.Pp, d, w.W, d, w.info));
     // m = mf + G dm

@@ -356,7 +356,9 @@ PHYSS_HD void kf_update(double (&m)[D], double (&P)[D][D], const double (&H)[M][
     }
     // masked step: mask_to_identity(S) = 1, v = 0  ->  lml_k = 0
     const double Sl = obs[0] ? S[0][0] : 1.0;
-    det_out = Sl;
+    // a non-positive S is a failed Cholesky in the reference (gaussian.py:56-57): NaN, not a sign that a later
+    // step's negative S could cancel in the running determinant product
+    det_out = (Sl > 0.0) ? Sl : nan("");
     mahal_out = v[0] * v[0] * fast_rcp(Sl);
     nobs_out = obs[0] ? 1 : 0;
   } else {

@@ -890,7 +890,8 @@ __global__ void __launch_bounds__(256) ps_lml_partial_kernel(const double* __res
                                                              int64_t sts, int64_t seg, int64_t nseg,
                                                              double* __restrict__ partial) {
   __shared__ double red[8];
-  const int64_t b = blockIdx.y, sg = blockIdx.x;
+  // flat grid of B * nseg blocks (gridDim.y is capped at 65,535: B >= 65,536 series must not fail)
+  const int64_t b = (int64_t)blockIdx.x / nseg, sg = (int64_t)blockIdx.x % nseg;
   const int64_t k0 = sg * seg, k1 = (k0 + seg < T) ? k0 + seg : T;
   double s = 0.0;
   for (int64_t k = k0 + threadIdx.x; k < k1; k += 256) s += lml_k[b * sbs + k * sts];
@@ -1555,7 +1556,7 @@ int pscan_filter_finish(cudaStream_t st, int d, int m, int disc_mode, int nblk, 
   {
     const int64_t seg = ps_lml_seg(a.T), nseg = ps_lml_nseg(a.T);
     double* partial = w.lml_partial;
-    ps_lml_partial_kernel<<<dim3((unsigned)nseg, (unsigned)a.B), 256, 0, st>>>(a.lml_k, a.T, a.sbs, a.sts, seg, nseg, partial);
+    ps_lml_partial_kernel<<<(unsigned)(nseg * a.B), 256, 0, st>>>(a.lml_k, a.T, a.sbs, a.sts, seg, nseg, partial);
     rc = cuda_status(cudaGetLastError(), "ps_lml_partial_kernel launch");
     if (rc) return rc;
     const int64_t threads = a.B * 32;
@@ -1626,8 +1627,7 @@ int pscan_filter_spec(cudaStream_t st, int d, int m, int disc_mode, int nblk, bo
   }
   {
     const int64_t seg = ps_lml_seg(a.T), nseg = ps_lml_nseg(a.T);
-    ps_lml_partial_kernel<<<dim3((unsigned)nseg, (unsigned)a.B), 256, 0, st>>>(a.lml_k, a.T, a.sbs, a.sts, seg, nseg,
-                                                                              w.lml_partial);
+    ps_lml_partial_kernel<<<(unsigned)(nseg * a.B), 256, 0, st>>>(a.lml_k, a.T, a.sbs, a.sts, seg, nseg, w.lml_partial);
     rc = cuda_status(cudaGetLastError(), "ps_lml_partial_kernel launch");
     if (rc) return rc;
     const int64_t threads = a.B * 32;

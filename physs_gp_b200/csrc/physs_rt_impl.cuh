@@ -377,7 +377,7 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
         }
       }
       const double Sl = obs ? Sv : 1.0;
-      det = Sl;
+      det = (Sl > 0.0) ? Sl : nan("");                                        // non-PD S: NaN as in the reference
       mahal = vv * vv * fast_rcp(Sl);
     } else {
       // ---- K rows: PHt = P_ H^T with columns of missing observations zeroed  -> K [d x m]

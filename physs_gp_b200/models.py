@@ -46,9 +46,15 @@ class SDE_GP:
         return (lml, mu, var) if return_lml else (mu, var)
 
     def posterior(self, diagonal=True, full_state=False):
+        """sde_gp.py:279-305: with `full_state=False` the mean is stacked time-space to [Nt * m', 1] and, with
+        `diagonal`, the variances to [Nt * m', 1] (a leading B when batched); otherwise the block outputs."""
         mu, var = self.filter_and_smooth(full_state=full_state)
-        if not full_state and diagonal:
-            return mu, var.diagonal(dim1=-2, dim2=-1)[..., None]
+        if full_state:
+            return mu, var
+        lead = tuple(mu.shape[:-3])
+        mu = mu.reshape(lead + (-1, 1))
+        if diagonal:
+            return mu, var.diagonal(dim1=-2, dim2=-1).reshape(lead + (-1, 1))
         return mu, var
 
     # ---------------------------------------------------------------- lml and its hyper-parameter gradient

@@ -55,7 +55,12 @@ def _bview(x, name, shape, inner):
             ok = False
         exp *= shape[dim]
     if not ok:
-        v = x.contiguous().expand(*shape)
+        # materialise the trailing `inner` dims (the kernels index them densely: a broadcast A_k [d, d] or
+        # dt [1] must become real [T, d, d] / [T] storage); the leading dims may stay broadcast (stride 0)
+        lead = len(shape) - inner
+        xs = x.reshape((1,) * (len(shape) - x.dim()) + tuple(x.shape))
+        xs = xs.expand(*(tuple(xs.shape[:lead]) + tuple(shape[lead:]))).contiguous()
+        v = xs.expand(*shape)
     return v, v.stride()
 
 

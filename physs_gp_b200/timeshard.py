@@ -22,10 +22,16 @@ dt conventions per rank (global arrays dt_f = [0, diff(t)], dt_s = [diff(t), 0] 
 Fix-up passes of the filter (jitter != 0) stay inside a rank: the first chunk of rank r > 0 starts from the
 folded scan state, which is O(jitter) away from the jittered sequential recursion; its error decays over
 that chunk exactly as for every other chunk boundary, but is not re-polished across the rank boundary.
-`cross_rank_polish=True` sends each rank's replayed last state to its successor (one extra point-to-point
-message of (d + d^2) * 8 bytes per series) and re-runs the finish step from it.
+`cross_rank_polish=True` (the default whenever jitter != 0) sends each rank's replayed last state to its
+successor (one extra message of (d + d^2) * 8 bytes per series) and re-runs the finish step from it.
+
+Collectives per call: one all-gather of the filter range summaries, one (optional) all-gather for the
+cross-rank polish, one all-gather that carries the smoother range summaries together with every rank's last
+filtered state, lml share and fix-up status (the status returned is the MAX over ranks).
 """
 import torch
+
+from . import settings
 
 
 class SingleProcess:
@@ -34,9 +40,6 @@ class SingleProcess:
 
     def all_gather(self, x):
         return x[None]
-
-    def all_reduce_sum(self, x):
-        return x
 
     def shift_from_prev(self, x):
         return None
@@ -56,11 +59,6 @@ class TorchDist:
         self.dist.all_gather_into_tensor(out, x, group=self.group)     # concatenated along dim 0
         return out.view((self.world,) + tuple(x.shape))
 
-    def all_reduce_sum(self, x):
-        x = x.clone()
-        self.dist.all_reduce(x, op=self.dist.ReduceOp.SUM, group=self.group)
-        return x
-
     def shift_from_prev(self, x):
         """Every rank sends x to rank + 1; returns what rank - 1 sent (None on rank 0)."""
         gathered = self.all_gather(x)          # tiny messages: one collective beats G point-to-point pairs
@@ -79,7 +77,7 @@ def time_ranges(T, world):
 
 
 def filter_smooth(comm, ops, dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s, chunk_len, jitter=None, polish=None,
-                  Hout=None, cross_rank_polish=False, ws=None):
+                  Hout=None, cross_rank_polish=None, ws=None):
     """Filter + smoother of the local time range of a series sharded over comm.world ranks.
 
     All arguments are the LOCAL slices (see module docstring); disc_f / disc_s are ops.Disc for the local
@@ -100,6 +98,10 @@ def filter_smooth(comm, ops, dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s, chunk_
     out = ops.pscan_filter_finish(dt_f, Y, R, H, m0, P0, disc_f, chunk_len, ws, start=start, jitter=jitter,
                                   polish=polish)
     lml_loc, mf, Pf, status = out
+    if cross_rank_polish is None:
+        # with jitter != 0 the first chunk of every rank > 0 starts O(jitter) away from the jittered sequential
+        # recursion and no rank-local fix-up pass re-visits it: polish across ranks by default
+        cross_rank_polish = G > 1 and (settings.jitter if jitter is None else jitter) != 0.0
     if cross_rank_polish and G > 1:
         last = torch.cat([mf[:, -1, :], Pf[:, -1].reshape(B, d * d)], dim=1).contiguous()
         prev = comm.shift_from_prev(last)
@@ -108,19 +110,23 @@ def filter_smooth(comm, ops, dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s, chunk_
             lml_loc, mf, Pf, status = ops.pscan_filter_finish(dt_f, Y, R, H, m0, P0, disc_f, chunk_len, ws,
                                                               start=start, jitter=jitter, polish=polish,
                                                               out=(mf, Pf))
-    lml = comm.all_reduce_sum(lml_loc)
     # -------------------------------------------------------------- smoother
+    # ONE all-gather for the backward direction: every rank contributes
+    #   [ range summary (E, L, g) | its last filtered state (m, P) | its share of the lml | its fix-up status ]
+    # so the lml reduction, the terminal state of the last rank and the global status ride along with the
+    # summaries instead of three more collectives (the ranks sum the lml shares in rank order: deterministic).
     stotal = ops.pscan_smooth_local(dt_s, mf, Pf, disc_s, chunk_len, ws, jitter=jitter)
-    stotals = comm.all_gather(stotal)                                 # [G, B, ns]
+    ns = stotal.shape[1]
+    pack = torch.cat([stotal, mf[:, -1, :], Pf[:, -1].reshape(B, d * d), lml_loc.reshape(B, 1),
+                      status.to(torch.float64).reshape(1, 1).expand(B, 1)], dim=1).contiguous()
+    packs = comm.all_gather(pack)                                     # [G, B, ns + d + d*d + 2]
+    lml = packs[:, :, ns + d + d * d].sum(dim=0)
+    status = packs[:, 0, ns + d + d * d + 1].max().to(status.dtype).reshape(status.shape)
     sstart = None
-    if G > 1:
-        # terminal state = filtered state at the last step of the LAST rank (every rank contributes its own
-        # last state so that the collective is uniform; only the last entry is used)
-        term = torch.cat([mf[:, -1, :], Pf[:, -1].reshape(B, d * d)], dim=1).contiguous()
-        terms = comm.all_gather(term)
-        if r < G - 1:
-            m_end = terms[G - 1][:, :d].contiguous()
-            P_end = terms[G - 1][:, d:].reshape(B, d, d).contiguous()
-            sstart = ops.pscan_smooth_fold(stotals[r + 1:], m_end, P_end)
+    if G > 1 and r < G - 1:
+        # terminal state = filtered state at the last step of the LAST rank
+        m_end = packs[G - 1][:, ns:ns + d].contiguous()
+        P_end = packs[G - 1][:, ns + d:ns + d + d * d].reshape(B, d, d).contiguous()
+        sstart = ops.pscan_smooth_fold(packs[r + 1:, :, :ns].contiguous(), m_end, P_end)
     ms, Ps = ops.pscan_smooth_finish(dt_s, mf, Pf, disc_s, chunk_len, ws, start=sstart, Hout=Hout, jitter=jitter)
     return lml, mf, Pf, ms, Ps, status

@@ -29,7 +29,7 @@ for obj in sorted(glob.glob(os.path.join(OBJ, "*.o"))):
                     if op == k or op.startswith(k + ".") or (k in ("LDGSTS", "UBLKCP", "SYNCS", "LDL", "STL", "BAR", "SHFL") and op.startswith(k)):
                         out[cur][k] += 1
                         break
-res = {"how": "cuobjdump -sass of the in-tree objects (static instruction counts per kernel, sm_100a); scratch/sass_summary.py",
+res = {"how": "cuobjdump -sass of the in-tree objects (static instruction counts per kernel, sm_100a); tools/sass_summary.py",
        "kernels": {k.replace("physs::", ""): dict(v) for k, v in sorted(out.items())}}
 json.dump(res, open("profiles/sass_r01_summary.json", "w"), indent=1)
 print(len(out), "kernels")
