@@ -57,6 +57,10 @@ def parse():
     ap.add_argument("--e2e-sub-batch", type=int, default=4096)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="c5: weak = --series per GPU (default); strong = --series in TOTAL, split over the ranks")
+    ap.add_argument("--no-sweep", action="store_true",
+                    help="c5 default line: skip the d = 8 / 16 / 32 sweep and the CVI-step section")
     ap.add_argument("--cpu-sample-series", type=int, default=0, help="series in the CPU sample (0 = auto)")
     a = ap.parse_args()
     dflt = {"c5": (SERIES_TOTAL, T_STEPS, 4), "c3": (1, 1000000, 8), "cvi": (1000, T_STEPS, 2),
@@ -181,8 +185,7 @@ def cpu_port_rate(d, T, sample_series, seed=0, nthreads=None, budget_s=10.0):
     from physs_gp_b200 import sdes
     c_oracle.build()
     if nthreads is None:
-        # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
-        nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        nthreads = _host_threads()
     nblk = d // 4
     rng = np.random.default_rng(seed)
     ls, steps = make_hypers(sample_series, nblk, seed)
@@ -205,12 +208,154 @@ def cpu_port_rate(d, T, sample_series, seed=0, nthreads=None, budget_s=10.0):
     return sample_series * T * reps / el, out["threads"], el, reps
 
 
+def _host_threads():
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+CPU_KIND_NOTE = ("restatement, not the JAX reference (jax/jaxlib are not installable here): oracle/ssm_oracle.c, the "
+                 "numpy oracle's C port, OpenMP over series")
+
+
+def cpu_c3_rate(d, m, T_sample, budget_s=10.0):
+    """state-steps/s of the C oracle port on ONE long series (config 3 shape, m = d full-state sites): the
+    sequential recursion cannot use more than one core per series."""
+    from oracle import c_oracle
+    from physs_gp_b200 import sdes
+    c_oracle.build()
+    rng = np.random.default_rng(0)
+    nblk = d // 4
+    steps = rng.uniform(0.5, 1.5, T_sample) * DT0
+    prior = sdes.BatchedMaternSDE(4, np.exp(rng.uniform(np.log(0.5), np.log(2.0), (1, nblk))) * (10 * DT0),
+                                  full_state_obs=(m == d))
+    Y = np.sin(0.01 * np.arange(T_sample))[None, :, None] + 0.3 * rng.normal(size=(1, T_sample, m))
+    H = np.eye(d) if m == d else prior.H()
+    args = (4, prior.lam(), prior.P_inf(), H, np.cumsum(steps), Y, NOISE_VAR * np.eye(m))
+    c_oracle.filter_smooth(*args, jitter=1e-5, full_state=True, keep_filtered=True, nthreads=1)
+    el, reps = 0.0, 0
+    while el < budget_s and reps < 50:
+        t0 = time.perf_counter()
+        c_oracle.filter_smooth(*args, jitter=1e-5, full_state=True, keep_filtered=True, nthreads=1)
+        el += time.perf_counter() - t0
+        reps += 1
+    return T_sample * reps / el, el, reps
+
+
+def cpu_cvi_step_ms(B_full, T, sample_blocks, budget_s=10.0, beta=0.1, K=20):
+    """ms per CVI iteration (natural-gradient update + ELBO) of the CPU restatement oracle/cvi_vec.py (C port of
+    the filter / smoother + vectorised numpy site algebra) on `sample_blocks` blocks, scaled linearly to B_full."""
+    from oracle import c_oracle, cvi_vec
+    from physs_gp_b200 import sdes
+    c_oracle.build()
+    nthreads = _host_threads()
+    rng = np.random.default_rng(0)
+    n = sample_blocks
+    t = np.cumsum(rng.uniform(0.5, 1.5, T) * DT0)
+    prior = sdes.BatchedMaternSDE(2, np.exp(rng.uniform(np.log(0.5), np.log(2.0), (n, 1))) * (10 * DT0))
+    rate = np.exp(0.5 * np.sin(0.02 * np.arange(T))[None, :] + 0.3 * rng.normal(size=(n, 1)))
+    Y = rng.poisson(rate).astype(np.float64)
+    Y[rng.uniform(size=Y.shape) < NAN_FRAC] = np.nan
+    pa = (2, prior.lam(), prior.P_inf(), prior.H())
+    Yt, Vt = np.full((n, T), 1e-5), np.ones((n, T))
+    Yt, Vt, _ = cvi_vec.cvi_iteration(pa, t, Y, Yt, Vt, "poisson", beta, K=K, nthreads=nthreads)       # warm-up
+    el, reps = 0.0, 0
+    while el < budget_s and reps < 100:
+        t0 = time.perf_counter()
+        Yt, Vt, elbo = cvi_vec.cvi_iteration(pa, t, Y, Yt, Vt, "poisson", beta, K=K, nthreads=nthreads)
+        el += time.perf_counter() - t0
+        reps += 1
+    assert np.isfinite(elbo).all()
+    ms_sample = 1e3 * el / reps
+    return ms_sample * B_full / n, nthreads, el, reps, ms_sample
+
+
+def cpu_c2_rate(Ns, T_sample):
+    """state-steps/s of the numpy oracle (LAPACK through numpy, its own threading) on the config-2 shape."""
+    from oracle import filters as of
+    from oracle import sde as osde
+    rng = np.random.default_rng(0)
+    Xs = rng.uniform(size=(Ns, 2))
+    D2 = ((Xs[:, None, :] - Xs[None, :, :]) ** 2).sum(-1)
+    Ks = np.exp(-0.5 * D2 / 0.2 ** 2) + 1e-6 * np.eye(Ns)
+    prior = osde.LTI_SDE([osde.SpaceTimeSeparable(osde.Matern32(10 * DT0, 1.0), Ks)])
+    t = DT0 * np.arange(1, T_sample + 1)
+    Y = rng.normal(size=(T_sample, Ns))
+    R = np.tile(NOISE_VAR * np.eye(Ns), [T_sample, 1, 1])
+    t0 = time.perf_counter()
+    lml, mf, Pf, _ = of.filter_sequential(prior, t, Y, R, 1e-5)
+    of.smoother_sequential(prior, t, mf, Pf, full_state=False, jitter=1e-5)
+    el = time.perf_counter() - t0
+    return T_sample / el, el
+
+
 def run_reference(a):
+    """CPU arm: the reference's algorithm on the host cores for the SAME workload / metric / unit as the B200 arm.
+    The JAX reference is not installable here, so this times the oracle restatement (kind "port") on a bounded
+    sample of the workload and says so in config.workload and cpu_baseline.sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     d, T = a.state_dim, a.T
     cores = os.cpu_count() or 1
+    base = {"impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "gpu_launches": 0}
+    if a.workload == "cvi":
+        n = a.cpu_sample_series or max(cores, 8)
+        vals = []
+        for i in range(a.warmup + a.steps):
+            ms_full, threads, el, reps, ms_s = cpu_cvi_step_ms(a.series, T, n, budget_s=2.0)
+            if i >= a.warmup:
+                vals.append(ms_full)
+        value = float(np.mean(vals))
+        sample = ("%d of %d blocks x %d steps, ~2 s per bench step, scaled linearly to %d blocks (oracle/cvi_vec.py: "
+                  "C port of filter + smoother, vectorised numpy site algebra / Gauss-Hermite K=20) -- %s"
+                  % (n, a.series, T, a.series, CPU_KIND_NOTE))
+        cfg = cvi_config(a.series, T)
+        cfg["workload"] += " [CPU arm: %s]" % sample
+        line = dict(base, metric="CVI ELBO+natgrad step time", value=value, unit="ms", ms_per_step=value,
+                    higher_is_better=False, scaling="weak", config=cfg,
+                    cpu_baseline={"value": value, "unit": "ms", "cores": threads, "kind": "port", "sample": sample},
+                    e2e={"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return
+    if a.workload in ("c3", "c3cvi"):
+        m = a.obs_dim or d
+        Ts = min(T, 100000)
+        vals = []
+        for i in range(a.warmup + a.steps):
+            r, el, reps = cpu_c3_rate(d, m, Ts, budget_s=2.0)
+            if i >= a.warmup:
+                vals.append((r, el))
+        value = float(np.mean([r for r, _ in vals]))
+        sample = ("first %d of %d steps of the series, ~2 s per bench step, ONE core (the sequential recursion of a "
+                  "single series does not thread) -- %s" % (Ts, T, CPU_KIND_NOTE))
+        line = dict(base, metric="filter+smoother state-steps/sec (fp64)", value=value, unit="state-steps/s",
+                    ms_per_step=1e3 * a.series * T / value, higher_is_better=True, scaling="strong",
+                    config={"workload": "c3: %d series x %d steps, state dim %d, obs dim %d [CPU arm: %s]"
+                                        % (a.series, T, d, m, sample), "series": a.series, "T": T, "state_dim": d,
+                            "obs_dim": m},
+                    cpu_baseline={"value": value, "unit": "state-steps/s", "cores": 1, "kind": "port", "sample": sample},
+                    e2e={"value": value, "unit": "state-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return
+    if a.workload == "c2":
+        Ns = a.series
+        vals = []
+        for i in range(a.warmup + a.steps):
+            r, el = cpu_c2_rate(Ns, 8)
+            if i >= a.warmup:
+                vals.append(r)
+        value = float(np.mean(vals))
+        sample = ("8 of %d time steps (numpy oracle oracle/filters.py, LAPACK threading as numpy configures it) -- "
+                  "restatement, not the JAX reference" % T)
+        line = dict(base, metric="filter+smoother state-steps/sec (fp64)", value=value, unit="state-steps/s",
+                    ms_per_step=1e3 * T / value, higher_is_better=True, scaling="weak",
+                    config={"workload": "c2: separable Matern-3/2 x RBF, %d spatial x %d time points, state dim %d "
+                                        "[CPU arm: %s]" % (Ns, T, 2 * Ns, sample), "spatial_points": Ns, "T": T},
+                    cpu_baseline={"value": value, "unit": "state-steps/s", "cores": cores, "kind": "port", "sample": sample},
+                    e2e={"value": value, "unit": "state-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return
     n = a.cpu_sample_series or max(cores * 8, 64)
     if d > 4:
         n = max(cores * 2, 16)
@@ -220,32 +365,47 @@ def run_reference(a):
         if i >= a.warmup:
             rates.append((r, el))
     value = float(np.mean([r for r, _ in rates]))
-    sample = ("%d series x %d steps, repeated for ~3 s per step (oracle/ssm_oracle.c, OpenMP over series), "
-              "d=%d, m=1" % (n, T, d))
-    line = {
-        "impl": "reference", "metric": "filter+smoother state-steps/sec (fp64)", "value": value,
-        "unit": "state-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3 * float(np.mean([el for _, el in rates])), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(a, sub_batch=None),
-        "cpu_baseline": {"value": value, "unit": "state-steps/s", "cores": threads, "kind": "port",
-                         "sample": sample},
-        "e2e": {"value": value, "unit": "state-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
+    sample = ("%d of %d series x %d steps, repeated for ~3 s per bench step, rate scaled linearly, d=%d, m=1 -- %s"
+              % (n, a.series, T, d, CPU_KIND_NOTE))
+    cfg = workload_config(a, sub_batch=None)
+    cfg["workload"] += " [CPU arm: %s]" % sample
+    line = dict(base, metric="filter+smoother state-steps/sec (fp64)", value=value, unit="state-steps/s",
+                ms_per_step=1e3 * float(np.mean([el for _, el in rates])), higher_is_better=True,
+                scaling=a.scaling, config=cfg,
+                cpu_baseline={"value": value, "unit": "state-steps/s", "cores": threads, "kind": "port",
+                              "sample": sample},
+                e2e={"value": value, "unit": "state-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     print(json.dumps(line), flush=True)
 
 
+def series_split(a, world):
+    """(series per GPU, series in total) under --scaling weak (default: --series per GPU) / strong (--series total)."""
+    if a.scaling == "strong":
+        if a.series % world:
+            raise SystemExit("--scaling strong: --series must be divisible by the number of GPUs")
+        return a.series // world, a.series
+    return a.series, a.series * world
+
+
 def workload_config(a, sub_batch, world=1):
-    return {"workload": "c5: %d independent series x %d steps per GPU, Matern-7/2 x %d (state dim %d), m=1, "
+    per, total = series_split(a, world)
+    return {"workload": "c5: %d independent series x %d steps %s, Matern-7/2 x %d (state dim %d), m=1, "
                         "Gaussian noise, per-series lengthscales, 5%% missing" % (
-                            a.series, a.T, a.state_dim // 4, a.state_dim),
-            "series_per_gpu": a.series, "series_total": a.series * world, "T": a.T,
+                            a.series, a.T, "per GPU" if a.scaling == "weak" else "in total, split over the GPUs",
+                            a.state_dim // 4, a.state_dim),
+            "series_per_gpu": per, "series_total": total, "T": a.T,
             "state_dim": a.state_dim, "obs_dim": 1, "sub_batch": sub_batch,
             "outputs": "filtered (m, P) + smoothed (m, P) full state, fp64, every step materialised in HBM",
             "layout": "time-major batch [T][B][d*d] (step strides (1, B) of the C ABI)",
             "l2": "inputs+outputs per launch >> 126 MB L2 (no flush needed)",
-            "parallelism": "independent series sharded over ranks (weak scaling), no data-path collective"}
+            "parallelism": "independent series sharded over ranks (%s scaling), no data-path collective" % a.scaling}
+
+
+def cvi_config(B, T):
+    return {"workload": "cvi (config 4): %d blocks x %d steps per GPU, Matern-3/2 (d=2), Poisson exp-link counts, "
+                        "Gauss-Hermite K=20, beta=0.1, 5%% missing" % (B, T),
+            "blocks_per_gpu": B, "T": T, "state_dim": 2, "site_dim": 1, "quad_points": 20,
+            "parallelism": "independent blocks per rank, no collective"}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -268,13 +428,14 @@ def run_b200(a):
     if d % 4:
         raise SystemExit("--state-dim must be a multiple of 4 (Matern-7/2 blocks)")
     nblk = d // 4
-    # WEAK scaling: every rank owns `--series` series of its own (series are independent: no collective)
-    n_local = a.series
+    # weak scaling (default): every rank owns `--series` series of its own; strong: `--series` in total, split
+    # over the ranks.  Series are independent: no data-path collective either way.
+    n_local, n_total = series_split(a, world)
     lo = rank * n_local
     sub = min(a.sub_batch, n_local)
     starts = list(range(0, n_local, sub))
 
-    ls_all, steps = make_hypers(a.series * world, nblk)
+    ls_all, steps = make_hypers(n_total, nblk)
     steps = steps[:T] if T <= T_STEPS else np.resize(steps, T)
     prior = sdes.BatchedMaternSDE(4, ls_all[lo:lo + n_local])
     lam = torch.as_tensor(prior.lam(), device=dev)
@@ -335,7 +496,7 @@ def run_b200(a):
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     elapsed_ms = float(elapsed_ms.item())
-    value = a.series * world * T * a.steps / (elapsed_ms * 1e-3)
+    value = n_total * T * a.steps / (elapsed_ms * 1e-3)
     assert torch.isfinite(lml_all).all(), "non-finite log marginal likelihood in the bench run"
 
     # per-kernel durations (this rank), roofline of the dominant kernel
@@ -374,9 +535,9 @@ def run_b200(a):
 
     # ---------------------------------------------------------------- e2e through the host API
     e2e = None
+    del out_full, out_tail
+    torch.cuda.empty_cache()
     if not a.no_e2e:
-        del out_full, out_tail
-        torch.cuda.empty_cache()
         e2e = run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys)
 
     cpu = None
@@ -385,21 +546,148 @@ def run_b200(a):
         n = a.cpu_sample_series or (max(cores * 8, 64) if d <= 4 else max(cores * 2, 16))
         r, threads, el, reps = cpu_port_rate(d, T, n, budget_s=12.0)
         cpu = {"value": r, "unit": "state-steps/s", "cores": threads, "kind": "port",
-               "sample": "%d series x %d steps x %d repeats = %.1f s of CPU work (oracle/ssm_oracle.c, OpenMP over "
-                         "series, the numpy oracle's C port)" % (n, T, reps, el)}
+               "sample": "%d of %d series x %d steps x %d repeats = %.1f s of CPU work, rate scaled linearly -- %s"
+                         % (n, n_local, T, reps, el, CPU_KIND_NOTE)}
+
+    # ------------------------------------------- the rest of BASELINE config 5 (d = 8, 16, 32) and metric (2)
+    sweep, cvi_sec = None, None
+    if not a.no_sweep and d == 4:
+        Ys = None
+        torch.cuda.empty_cache()
+        sweep = {}
+        for dd in (8, 16, 32):
+            sweep["d%d" % dd] = sweep_point(a, dev, world, rank, dd, n_local, n_total, lo,
+                                            cpu=(rank == 0 and not a.no_cpu_baseline))
+            torch.cuda.empty_cache()
+        cvi_sec = cvi_measure(a, dev, world, rank, local, 1000, T_STEPS, steps=max(3, min(a.steps, 10)),
+                              warmup=max(3, a.warmup), with_clocks=False,
+                              cpu=(rank == 0 and not a.no_cpu_baseline))
 
     if rank == 0:
+        launches = 2 * len(starts) * a.steps
         line = {
             "metric": "filter+smoother state-steps/sec (fp64)", "value": value, "unit": "state-steps/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(a, sub, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": 2 * len(starts) * a.steps,
+            "gpu_launches": launches,
         }
+        if sweep is not None:
+            line["sweep"] = sweep
+            line["cvi"] = cvi_sec
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def wave_series(d):
+    """Series the library keeps resident on the whole GPU for this state dim (one full wave of the smoother
+    kernel); sub-batches are sized in whole waves so that no launch ends on a half-empty GPU."""
+    from physs_gp_b200 import ops
+    return ops.kf_wave_series(d, 1, d // 4)
+
+
+def sweep_point(a, dev, world, rank, d, n_local, n_total, lo, cpu):
+    """One timed pass of filter + smoother over this rank's n_local series at state dim d (BASELINE config 5,
+    d = 8 / 16 / 32), in sub-batches of whole waves that fit HBM; per-launch CUDA events; max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from physs_gp_b200 import ops, sdes
+    T, nblk = a.T, d // 4
+    per_series = T * (d * d + d) * 8 * 2                       # filtered + smoothed full-state outputs
+    wave = wave_series(d)
+    cap = int(135e9 // per_series)
+    sub = wave * max(1, cap // wave) if cap >= wave else max(32, wave // -(-wave // cap))
+    sub = min(sub, n_local)
+    starts = list(range(0, n_local, sub))
+    ls_all, steps = make_hypers(n_total, nblk)
+    steps = steps[:T] if T <= T_STEPS else np.resize(steps, T)
+    prior = sdes.BatchedMaternSDE(4, ls_all[lo:lo + n_local])
+    lam = torch.as_tensor(prior.lam(), device=dev)
+    Pinf = torch.as_tensor(prior.P_inf(), device=dev)
+    H = torch.as_tensor(prior.H(), device=dev)
+    m0 = torch.zeros((1, d), dtype=torch.float64, device=dev)
+    dt_f = torch.as_tensor(np.hstack([0.0, steps[1:]]), device=dev)
+    dt_s = torch.as_tensor(np.hstack([steps[1:], 0.0]), device=dev)
+    R = torch.full((1, 1, 1, 1), NOISE_VAR, dtype=torch.float64, device=dev)
+    Y = device_observations(sub, T, dev, seed=2000 + lo)        # the same observations for every sub-batch
+    mf, Pf = ops.empty_steps(sub, T, (d,), dev, True), ops.empty_steps(sub, T, (d, d), dev, True)
+    ms, Ps = ops.empty_steps(sub, T, (d,), dev, True), ops.empty_steps(sub, T, (d, d), dev, True)
+    tail = n_local - starts[-1]
+
+    def views(n):
+        if n == sub:
+            return Y, mf, Pf, ms, Ps
+        # ragged last sub-batch: fresh time-major buffers of the right batch size (views would not be time-major)
+        return (device_observations(n, T, dev, seed=2001 + lo), ops.empty_steps(n, T, (d,), dev, True),
+                ops.empty_steps(n, T, (d, d), dev, True), ops.empty_steps(n, T, (d,), dev, True),
+                ops.empty_steps(n, T, (d, d), dev, True))
+    tail_bufs = views(tail) if tail != sub else None
+
+    def one_pass(record):
+        ev, lmls = [], []
+        for s0 in starts:
+            n = min(sub, n_local - s0)
+            Yv, mfv, Pfv, msv, Psv = (Y, mf, Pf, ms, Ps) if n == sub else tail_bufs
+            disc = ops.Disc.matern(nblk, lam[s0:s0 + n], Pinf[s0:s0 + n])
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if record else None
+            if record:
+                e[0].record()
+            lml, _, _ = ops.kf_filter(dt_f, Yv, R, H, m0, Pinf[s0:s0 + n], disc, jitter=1e-5, out=(mfv, Pfv))
+            if record:
+                e[1].record()
+            ops.rts_smooth(dt_s, mfv, Pfv, disc, Hout=None, jitter=1e-5, out=(msv, Psv))
+            if record:
+                e[2].record()
+                ev.append((e, n))
+            lmls.append(lml)
+        return ev, lmls
+
+    # warm-up: the first sub-batch once (kernel load, clocks), then ONE timed pass over all n_local series
+    disc0 = ops.Disc.matern(nblk, lam[:min(sub, 256)], Pinf[:min(sub, 256)])
+    w = min(sub, 256)
+    for _ in range(2):
+        ops.kf_filter(dt_f[:200], Y[:w, :200], R, H, m0, Pinf[:w], disc0, jitter=1e-5)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    ev, lmls = one_pass(True)
+    t1.record()
+    torch.cuda.synchronize()
+    assert all(bool(torch.isfinite(x).all()) for x in lmls), "non-finite lml in the sweep (d=%d)" % d
+    el = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    ms_pass = float(el.item())
+    value = n_total * T / (ms_pass * 1e-3)
+    f_ms = float(np.sum([e[0].elapsed_time(e[1]) for e, _ in ev]))
+    s_ms = float(np.sum([e[1].elapsed_time(e[2]) for e, _ in ev]))
+    fb, sb = algorithmic_bytes(d, 1)
+    peak, _ = measured_peak_gbs()
+    fp64_peak = ops.fp64_peak_tflops(dev)
+    flops = 14.3 * d ** 3 + 4 * d * d + 6 * d + 0.67
+    per_gpu = value / world
+    out = {"value": value, "unit": "state-steps/s", "state_dim": d, "series_per_gpu": n_local, "T": T,
+           "sub_batch": sub, "wave_series": wave, "passes_timed": 1, "ms_per_pass": ms_pass,
+           "filter_ms": f_ms, "smoother_ms": s_ms, "gpu_launches": 2 * len(starts),
+           "hbm": {"bytes_per_state_step": fb + sb, "achieved_gbs": (fb + sb) * per_gpu / 1e9,
+                   "frac": (fb + sb) * per_gpu / 1e9 / peak},
+           "fp64": {"flops_per_state_step": flops, "achieved_tflops": flops * per_gpu / 1e12,
+                    "peak_tflops_measured": fp64_peak, "frac": flops * per_gpu / 1e12 / fp64_peak}}
+    out["roofline"] = {"bound": "hbm" if out["hbm"]["frac"] >= out["fp64"]["frac"] else "fp64",
+                       "frac": max(out["hbm"]["frac"], out["fp64"]["frac"])}
+    del Y, mf, Pf, ms, Ps, tail_bufs
+    if cpu:
+        cores = os.cpu_count() or 1
+        n = max(cores * 2, 16)
+        r, threads, elc, reps = cpu_port_rate(d, T, n, budget_s=3.0)
+        out["cpu_baseline"] = {"value": r, "unit": "state-steps/s", "cores": threads, "kind": "port",
+                               "sample": "%d of %d series x %d steps x %d repeats = %.1f s -- %s"
+                                         % (n, n_local, T, reps, elc, CPU_KIND_NOTE)}
+    return out
 
 
 def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys_dev):
@@ -464,7 +752,7 @@ def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys_dev):
     k2, el2 = timed(False)
     per_rank_in = n_local * T * 8 + 2 * T * 8
     per_rank_out = n_local * T * 16 + n_local * 8
-    return {"value": a.series * world * T * k / el, "unit": "state-steps/s", "steps": k,
+    return {"value": n_local * world * T * k / el, "unit": "state-steps/s", "steps": k,
             "h2d_bytes_per_step": per_rank_in * world, "d2h_bytes_per_step": per_rank_out * world,
             "sub_batch": esub, "streams": len(streams),
             "api": "SDE_GP.filter_and_smooth(full_state=False, return_lml=True) per sub-batch, pinned host "
@@ -472,7 +760,7 @@ def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys_dev):
             "result": "smoothed mean/variance of f [B,T] + lml [B] read back to pinned host memory",
             # the same calls when only the loss (lml per series) is read back and the posterior stays in HBM
             # for the next consumer (a CVI step, predict_f), as the reference's device arrays would
-            "loss_only": {"value": a.series * world * T * k2 / el2, "unit": "state-steps/s", "steps": k2,
+            "loss_only": {"value": n_local * world * T * k2 / el2, "unit": "state-steps/s", "steps": k2,
                           "h2d_bytes_per_step": per_rank_in * world, "d2h_bytes_per_step": n_local * 8 * world,
                           "result": "lml [B] read back; smoothed mean/variance left on the device"}}
 
@@ -603,22 +891,16 @@ def run_c3(a):
 
 
 # ------------------------------------------------------------------------------ cvi: ELBO + natgrad step
-def run_cvi(a):
+def cvi_measure(a, dev, world, rank, local, B, T, steps, warmup, with_clocks, cpu):
     """BASELINE config 4 shape: B spatial blocks (default 1000) x T steps (default 10k), Matern-3/2 state
-    (d = 2), scalar Poisson counts (exp link), Gauss-Hermite K = 20, beta = 0.1.  One step = ELBO evaluation
-    (filter + smoother on the sites, data ELL, surrogate ELL) + one natural-gradient site update (filter +
-    smoother, ELL gradients, theta <-> lambda, block update) -- vgp.py:148-157,274-282."""
+    (d = 2), scalar Poisson counts (exp link), Gauss-Hermite K = 20, beta = 0.1.  One step = one natural-gradient
+    site update (filter + smoother, ELL gradients, theta <-> lambda, block update) + one ELBO evaluation (filter +
+    smoother on the new sites, data ELL, surrogate ELL) -- vgp.py:274-282,148-157.  Returns the metric-(2) record
+    (ms per step, roofline, e2e, CPU restatement beside it)."""
     import torch
     import torch.distributed as dist
-    from physs_gp_b200 import cvi, ops, sdes
+    from physs_gp_b200 import cvi, sdes
 
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B, T = a.series, a.T
     rng = np.random.default_rng(rank)
     t = np.cumsum(rng.uniform(0.5, 1.5, T) * DT0)
     prior = sdes.BatchedMaternSDE(2, np.exp(rng.uniform(np.log(0.5), np.log(2.0), (B, 1))) * (10 * DT0))
@@ -636,24 +918,24 @@ def run_cvi(a):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         elbo = step()
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and with_clocks:
         sampler.start()
     barrier()                                 # rank 0 waits for nvidia-smi to come up: keep the ranks together
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.steps):
+    for _ in range(steps):
         elbo = step()
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and with_clocks) else None
     el = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    ms = float(el.item()) / a.steps
+    ms = float(el.item()) / steps
     assert torch.isfinite(elbo).all()
     # e2e: data from pinned host memory every step, ELBO read back
     Y_host = torch.empty(Yh.shape, dtype=torch.float64, pin_memory=True); Y_host.copy_(torch.as_tensor(Yh))
@@ -665,7 +947,7 @@ def run_cvi(a):
         torch.cuda.synchronize()
     e2e_step(); barrier()
     tw = time.perf_counter()
-    for _ in range(a.steps):
+    for _ in range(steps):
         e2e_step()
     elw = torch.tensor([time.perf_counter() - tw], dtype=torch.float64, device=dev)
     if world > 1:
@@ -676,24 +958,44 @@ def run_cvi(a):
     # two posterior passes (natgrad + ELBO) each with time-varying site noise R_k (+8 B) ; site update: sites in/out
     # + posterior read; ELLs: posterior read twice + data
     byt = 2 * (fb + 8 + sb) + 8 * (2 * (D * D + D) + (D * D + D)) + 8 * (2 * (D * D + D) + 1 + (D * D + D))
+    cfg = cvi_config(B, T)
+    cfg["l2"] = "per-step working set %.1f GB >> 126 MB L2" % (byt * B * T / 1e9)
+    rec = {"metric": "CVI ELBO+natgrad step time", "value": ms, "unit": "ms", "ms_per_step": ms, "steps": steps,
+           "warmup": warmup, "higher_is_better": False, "config": cfg,
+           "state_steps_per_s": world * B * T / (ms * 1e-3),
+           "roofline": {"bound": "hbm", "achieved": byt * B * T / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": byt * B * T / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                        "bytes_per_state_step": byt},
+           "cpu_baseline": None,
+           "e2e": {"value": 1e3 * float(elw.item()) / steps, "unit": "ms", "h2d_bytes_per_step": B * T * 8 * world,
+                   "d2h_bytes_per_step": B * 8 * world,
+                   "api": "VGP.natural_gradient_update(0.1) + VGP.elbo(), data from pinned host memory"},
+           "clocks": clocks}
+    if cpu:
+        n = a.cpu_sample_series or max(os.cpu_count() or 1, 8)
+        ms_full, threads, elc, reps, ms_s = cpu_cvi_step_ms(B, T, n, budget_s=6.0)
+        rec["cpu_baseline"] = {"value": ms_full, "unit": "ms", "cores": threads, "kind": "port",
+                               "sample": "%d of %d blocks x %d steps x %d iterations = %.1f s (%.1f ms per iteration of "
+                                         "the sample, scaled linearly to %d blocks; oracle/cvi_vec.py: C port of filter + "
+                                         "smoother, vectorised numpy site algebra) -- restatement, not the JAX reference"
+                                         % (n, B, T, reps, elc, ms_s, B)}
+    return rec
+
+
+def run_cvi(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rec = cvi_measure(a, dev, world, rank, local, a.series, a.T, a.steps, a.warmup, with_clocks=True,
+                      cpu=(rank == 0 and not a.no_cpu_baseline))
     if rank == 0:
-        line = {"metric": "CVI ELBO+natgrad step time", "value": ms, "unit": "ms", "n_gpus": world,
-                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": False,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "cvi (config 4): %d blocks x %d steps per GPU, Matern-3/2 (d=2), Poisson "
-                                       "exp-link counts, Gauss-Hermite K=20, beta=0.1, 5%% missing" % (B, T),
-                           "blocks_per_gpu": B, "T": T, "state_dim": 2, "site_dim": 1, "quad_points": 20,
-                           "l2": "per-step working set %.1f GB >> 126 MB L2" % (byt * B * T / 1e9),
-                           "parallelism": "independent blocks per rank, no collective"},
-                "state_steps_per_s": world * B * T / (ms * 1e-3),
-                "roofline": {"bound": "hbm", "achieved": byt * B * T / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": byt * B * T / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
-                             "bytes_per_state_step": byt},
-                "cpu_baseline": None,
-                "e2e": {"value": 1e3 * float(elw.item()) / a.steps, "unit": "ms", "h2d_bytes_per_step": B * T * 8 * world,
-                        "d2h_bytes_per_step": B * 8 * world,
-                        "api": "VGP.natural_gradient_update(0.1) + VGP.elbo(), data from pinned host memory"},
-                "clocks": clocks, "gpu_launches": None}
+        line = dict(rec, n_gpus=world, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                    gpu_launches=None)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

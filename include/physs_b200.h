@@ -62,6 +62,13 @@ const char* physs_last_error(void);
 /* 1 if a kernel specialisation exists for this (d, m, disc_mode, nblk), else 0. */
 int physs_kf_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk);
 
+/* Number of independent series ONE full wave of the smoother kernel for this shape keeps resident on the current
+ * device (occupancy x series per block x SM count), or 0 when the shape has no fixed-wave kernel.  Every series is
+ * walked by one thread / lane group for the whole launch, so a batch that is a whole number of waves never ends
+ * on a half-empty GPU: callers that split a large batch (the reference has no batch axis; jax.vmap callers pick
+ * the chunking) should use multiples of this.  Host-only query, no launch, no stream. */
+int64_t physs_kf_wave_series(int32_t d, int32_t disc_mode, int32_t nblk);
+
 /* Sequential Kalman filter over B independent series.
  * Replaces filter('sequential') + kf_predict_step(LTI_SDE) + kf_update_step
  * (computation/filters/kalman_filter.py:439-485, 214-241, 144-211).

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libphyss_b200.so")
 PHYSS_OK = 0
 DISC_GIVEN = 0
 DISC_MATERN = 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _c_i32 = ctypes.c_int32
 _c_i64 = ctypes.c_int64
@@ -33,6 +33,7 @@ SIGNATURES = {
     "physs_abi_version": (ctypes.c_int, []),
     "physs_last_error": (ctypes.c_char_p, []),
     "physs_kf_supported": (ctypes.c_int, [_c_i32, _c_i32, _c_i32, _c_i32]),
+    "physs_kf_wave_series": (_c_i64, [_c_i32, _c_i32, _c_i32]),
     "physs_kf_filter_f64": (ctypes.c_int, [
         _ptr, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32,
         _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,

@@ -74,7 +74,7 @@ static inline bool step_strides_ok(int64_t B, int64_t T, int64_t bs, int64_t ts)
 
 extern "C" {
 
-int physs_abi_version(void) { return 6; }
+int physs_abi_version(void) { return 7; }
 
 const char* physs_last_error(void) { return g_err; }
 
@@ -84,6 +84,17 @@ int physs_kf_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {
     if (nblk < 1 || d % nblk != 0 || d / nblk > 4) return 0;
   }
   return grp_supported(d, m) ? 1 : 0;
+}
+
+int64_t physs_kf_wave_series(int32_t d, int32_t disc_mode, int32_t nblk) {
+  if (d < 1) return 0;
+  if (disc_mode == PHYSS_DISC_MATERN && (nblk < 1 || d % nblk != 0)) return 0;
+  int64_t wave = 0;
+  SeqSmoothArgs a{};
+  a.B = 1; a.T = 1; a.sbs = 1; a.sts = 1;
+  a.wave_out = &wave;
+  if (run_smooth_any(nullptr, d, 0, disc_mode, nblk, a) != PHYSS_OK) return 0;
+  return wave;
 }
 
 // ---- shared argument checking / packing of the filter and smoother families

@@ -154,22 +154,26 @@ struct MaternExpm<4> {
     const T e = texp(-x);
     const T l2 = lam * lam;
     const T l3 = l2 * lam;
-    A[0][0] = e * (dt * (lam * (1.0 + 0.5 * x + x2 / 6.0)) + 1.0);
+    // 1/6 as a multiplication: a double division is a ~25-instruction sequence with a slow-path BRANCH that
+    // splits the time step into several basic blocks (no scheduling across them); the products differ from the
+    // reference's quotients by <= 1 ulp
+    constexpr double kSixth = 1.0 / 6.0;
+    A[0][0] = e * (dt * (lam * (1.0 + 0.5 * x + x2 * kSixth)) + 1.0);
     A[0][1] = e * (dt * (1.0 + x + 0.5 * x2));
     A[0][2] = e * (dt * (0.5 * dt * (1.0 + x)));
-    A[0][3] = e * (dt * (dt * dt / 6.0));
-    A[1][0] = e * (dt * (-x2 * l2 / 6.0));
+    A[0][3] = e * (dt * (dt * dt * kSixth));
+    A[1][0] = e * (dt * (-x2 * l2 * kSixth));
     A[1][1] = e * (dt * (lam * (1.0 + 0.5 * x - 0.5 * x2)) + 1.0);
     A[1][2] = e * (dt * (1.0 + x - 0.5 * x2));
-    A[1][3] = e * (dt * (dt * (0.5 - x / 6.0)));
-    A[2][0] = e * (dt * (l3 * x * (x / 6.0 - 0.5)));
+    A[1][3] = e * (dt * (dt * (0.5 - x * kSixth)));
+    A[2][0] = e * (dt * (l3 * x * (x * kSixth - 0.5)));
     A[2][1] = e * (dt * (x * l2 * (0.5 * x - 2.0)));
     A[2][2] = e * (dt * (lam * (1.0 - 2.5 * x + 0.5 * x2)) + 1.0);
-    A[2][3] = e * (dt * (1.0 - x + x2 / 6.0));
-    A[3][0] = e * (dt * (l2 * l2 * (x - 1.0 - x2 / 6.0)));
+    A[2][3] = e * (dt * (1.0 - x + x2 * kSixth));
+    A[3][0] = e * (dt * (l2 * l2 * (x - 1.0 - x2 * kSixth)));
     A[3][1] = e * (dt * (l3 * (3.5 * x - 4.0 - 0.5 * x2)));
     A[3][2] = e * (dt * (l2 * (4.0 * x - 6.0 - 0.5 * x2)));
-    A[3][3] = e * (dt * (lam * (1.5 * x - 3.0 - x2 / 6.0)) + 1.0);
+    A[3][3] = e * (dt * (lam * (1.5 * x - 3.0 - x2 * kSixth)) + 1.0);
   }
 };
 
@@ -615,17 +619,17 @@ PHYSS_HD void kf_predict_stationary(const Trans<D, S>& A, const double (&Pinf)[D
 //   Qadd: the matrix added to A Pf A^T, i.e. Q_k (given) -- for the stationary form pass
 //         stationary = true and Qadd = Pinf, which evaluates Pinf + (A Pf - A Pinf) A^T.
 // ---------------------------------------------------------------------------------------------
-//   Eacc != nullptr (parallel-in-time chunk summary, parallel_rts_smoother.py:25-55): additionally
-//   Eacc <- G Eacc, so that after folding a chunk  x_s[first] = Eacc x + ms,  P_s[first] = Eacc P Eacc^T + Ps.
+// The step is split in two halves so that callers can software-pipeline it (physs_seq_impl.cuh):
+//   rts_front: everything that depends on the FILTERED moments only -- m_pred, P_pred, the gain G;
+//   rts_back : the two-line recursion that consumes the smoothed state of step k+1.
+// Successive fronts are independent of each other; only the backs form the sequential chain.
 template <int D, int S>
-PHYSS_HD void rts_step(const Trans<D, S>& A, const double (&Qadd)[D][D], bool stationary,
-                       const double (&mf)[D], const double (&Pf)[D][D], double jitter,
-                       double (&ms)[D], double (&Ps)[D][D], double (*Eacc)[D] = nullptr) {
-  double mp[D];
+PHYSS_HD void rts_front(const Trans<D, S>& A, const double (&Qadd)[D][D], bool stationary,
+                        const double (&mf)[D], const double (&Pf)[D][D], double jitter,
+                        double (&mp)[D], double (&Pp)[D][D], double (&G)[D][D]) {
   A.mulv(mf, mp);
   double C[D][D];  // A Pf
   A.mulL(Pf, C);
-  double Pp[D][D];
   if (stationary) {
     double E[D][D];
     A.mulL(Qadd, E);  // A Pinf
@@ -648,7 +652,6 @@ PHYSS_HD void rts_step(const Trans<D, S>& A, const double (&Qadd)[D][D], bool st
   double L[D][D], rd[D];
   chol_lower<D>(Pj, L, rd);
   // G^T = (Pp + jit)^{-1} (A Pf)  -> column j of X solves for row j of G
-  double G[D][D];
   PHYSS_UNROLL
   for (int j = 0; j < D; ++j) {
     double x[D];
@@ -658,24 +661,11 @@ PHYSS_HD void rts_step(const Trans<D, S>& A, const double (&Qadd)[D][D], bool st
     PHYSS_UNROLL
     for (int i = 0; i < D; ++i) G[j][i] = x[i];
   }
-  if (Eacc) {
-    double GE[D][D];
-    PHYSS_UNROLL
-    for (int i = 0; i < D; ++i) {
-      PHYSS_UNROLL
-      for (int j = 0; j < D; ++j) {
-        double acc = 0.0;
-        PHYSS_UNROLL
-        for (int k = 0; k < D; ++k) acc = fma(G[i][k], Eacc[k][j], acc);
-        GE[i][j] = acc;
-      }
-    }
-    PHYSS_UNROLL
-    for (int i = 0; i < D; ++i) {
-      PHYSS_UNROLL
-      for (int j = 0; j < D; ++j) Eacc[i][j] = GE[i][j];
-    }
-  }
+}
+
+template <int D>
+PHYSS_HD void rts_back(const double (&mf)[D], const double (&Pf)[D][D], const double (&mp)[D],
+                       const double (&Pp)[D][D], const double (&G)[D][D], double (&ms)[D], double (&Ps)[D][D]) {
   // m = mf + G (ms - mp)
   double dm[D];
   PHYSS_UNROLL
@@ -716,6 +706,35 @@ PHYSS_HD void rts_step(const Trans<D, S>& A, const double (&Qadd)[D][D], bool st
       Ps[j][i] = acc;
     }
   }
+}
+
+//   Eacc != nullptr (parallel-in-time chunk summary, parallel_rts_smoother.py:25-55): additionally
+//   Eacc <- G Eacc, so that after folding a chunk  x_s[first] = Eacc x + ms,  P_s[first] = Eacc P Eacc^T + Ps.
+template <int D, int S>
+PHYSS_HD void rts_step(const Trans<D, S>& A, const double (&Qadd)[D][D], bool stationary,
+                       const double (&mf)[D], const double (&Pf)[D][D], double jitter,
+                       double (&ms)[D], double (&Ps)[D][D], double (*Eacc)[D] = nullptr) {
+  double mp[D], Pp[D][D], G[D][D];
+  rts_front<D, S>(A, Qadd, stationary, mf, Pf, jitter, mp, Pp, G);
+  if (Eacc) {
+    double GE[D][D];
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      PHYSS_UNROLL
+      for (int j = 0; j < D; ++j) {
+        double acc = 0.0;
+        PHYSS_UNROLL
+        for (int k = 0; k < D; ++k) acc = fma(G[i][k], Eacc[k][j], acc);
+        GE[i][j] = acc;
+      }
+    }
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      PHYSS_UNROLL
+      for (int j = 0; j < D; ++j) Eacc[i][j] = GE[i][j];
+    }
+  }
+  rts_back<D>(mf, Pf, mp, Pp, G, ms, Ps);
 }
 
 }  // namespace physs

@@ -79,6 +79,9 @@ struct SeqSmoothArgs {
   double delta;
   const double* bnd_m; const double* bnd_P;
   int* unconverged;
+  // host-side query (physs_kf_wave_series): when set, the launcher writes the number of series one full wave
+  // of its kernel keeps resident on the device and returns WITHOUT launching
+  int64_t* wave_out;
 };
 
 // physs_seq.cu: one thread per series, registers (d in {1,2,3,4,6,8})

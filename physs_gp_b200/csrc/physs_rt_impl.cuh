@@ -659,6 +659,14 @@ int rt_run_smooth(cudaStream_t st, const SeqSmoothArgs& a, int d, int mo, int nb
     const int rc = rt_configure(kern, G, per_group, &threads, &smem, "rt_smooth_kernel: configuration");
     if (rc) return rc;
     const int gpb = threads / G;
+    if (a.wave_out) {
+      int blocks = 0, dev = 0, sms = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, threads, smem);
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      *a.wave_out = (int64_t)blocks * gpb * sms;
+      return PHYSS_OK;
+    }
     const int64_t grid = (ngroups + gpb - 1) / gpb;
     rt_report("smoother", kern, threads, smem, gpb, ngroups);
     kern<<<(unsigned)grid, threads, smem, st>>>(a, L);

@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "physs_core.cuh"
 #include "physs_internal.h"
@@ -523,6 +524,210 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_smooth_kernel(const 
   if (CHUNK && p.fixup && active && !done) atomicOr(p.unconverged, 1);
 }
 
+// ------------------------------------------------------------- software-pipelined smoother (time-major)
+// The RTS step of series b at step k splits into a FRONT half that needs only the filtered moments of step k
+// (A_k, m_pred, P_pred, Cholesky, gain G_k: ~3/4 of the arithmetic and all of its long dependency chains) and a
+// BACK half (ms_k = mf_k + G_k (ms_{k+1} - m_pred), Ps_k = Pf_k + G_k (Ps_{k+1} - P_pred) G_k^T) that is the only
+// part chained through time.  One thread still walks one series, but every loop iteration now holds the front of
+// step k and the back of step k + 1 in ONE basic block with no dependence between them, so the instruction
+// scheduler overlaps the Cholesky / substitution chains of one with the matrix products of the other (the batch
+// leaves < 2 warps per scheduler: instruction-level parallelism is the only latency hiding there is).
+// The filtered rows arrive through a 3-stage cp.async ring per warp (16-byte LDGSTS straight into the padded
+// transpose tile, no staging registers), issued one iteration ahead; the back half re-reads (mf, Pf) of its step
+// from the ring instead of carrying them in registers.  Same arithmetic, operation for operation, as rts_step.
+__device__ __forceinline__ void seq_cp_async16(double* smem_dst, const double* gsrc) {
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void seq_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void seq_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// rows [0, 32) of N doubles, contiguous in global memory at g, into the padded tile (row r at tile + r * LD)
+template <int N>
+__device__ __forceinline__ void warp_rows_async(const double* __restrict__ g, double* tile, int lane, int nvalid) {
+  static_assert(N % 2 == 0, "16-byte pieces");
+  constexpr int LD = RowTile<N>::LD;
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    const int e = 2 * (i * 32 + lane);
+    const int r = e / N, c = e % N;
+    const int rr = (r < nvalid) ? r : nvalid - 1;
+    seq_cp_async16(tile + r * LD + c, g + rr * N + c);
+  }
+}
+template <int N>
+__device__ __forceinline__ void tile_own_row(const double* tile, int lane, double (&v)[N]) {
+  constexpr int LD = RowTile<N>::LD;
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) {
+    const double2 t = *reinterpret_cast<const double2*>(tile + lane * LD + 2 * j);
+    v[2 * j] = t.x;
+    v[2 * j + 1] = t.y;
+  }
+}
+
+template <int D>
+struct SeqPipe {
+  static constexpr int NST = 3;                                            // ring stages
+  static constexpr int STAGE = RowTile<D>::SIZE + RowTile<D * D>::SIZE;    // doubles per stage (mf | Pf)
+  static constexpr int PER_WARP = NST * STAGE + RowTile<D * D>::SIZE;      // + the output transpose tile
+  static constexpr size_t smem_bytes(int warps) { return (size_t)warps * PER_WARP * sizeof(double); }
+};
+
+template <int D, int S, int MO, bool GIVEN>
+__global__ void __launch_bounds__(128) seq_smooth_pipe_kernel(const SeqSmoothArgs p) {
+  extern __shared__ __align__(16) double pipe_smem[];
+  SeqWork wk;
+  if (!seq_work<false>(p, wk)) return;
+  constexpr int NB = D / S;
+  constexpr int MP = (MO == 0) ? D : MO;
+  constexpr int NST = SeqPipe<D>::NST;
+  const int64_t b = wk.b, T = wk.T;
+  const bool active = wk.active;
+  const int lane = threadIdx.x & 31;
+  double* ring = pipe_smem + (size_t)(threadIdx.x >> 5) * SeqPipe<D>::PER_WARP;
+  double* tile = ring + NST * SeqPipe<D>::STAGE;
+  const int64_t sts = p.sts;
+
+  double Pinf[D][D], lam[NB], Ho[MP][D];
+  if (!GIVEN) {
+    load_mat<D>(p.Pinf + b * p.Pinf_bs, Pinf);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) lam[i] = p.lam[b * p.lam_bs + i];
+  }
+  if (MO != 0) {
+#pragma unroll
+    for (int a = 0; a < MP; ++a) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) Ho[a][j] = p.Hout[a * D + j];
+    }
+  }
+  const int64_t row0 = b * p.sbs;
+  const int64_t wrow0 = wk.b0 * p.sbs;
+  const double* __restrict__ dtp = p.dt + b * p.dt_bs;
+  const double* __restrict__ Ap = GIVEN ? p.A + b * p.A_bs : nullptr;
+  const double* __restrict__ Qp = GIVEN ? p.Q + b * p.Q_bs : nullptr;
+  const double* __restrict__ mfp = p.mf + row0 * D;
+  const double* __restrict__ Pfp = p.Pf + row0 * D * D;
+  const double* __restrict__ mfw = p.mf + wrow0 * D;
+  const double* __restrict__ Pfw = p.Pf + wrow0 * D * D;
+  double* __restrict__ msp = p.ms + row0 * MP;
+  double* __restrict__ Psp = p.Ps + row0 * MP * MP;
+  double* __restrict__ msw = p.ms + wrow0 * MP;
+  double* __restrict__ Psw = p.Ps + wrow0 * MP * MP;
+
+  auto emit = [&](int64_t k, const double (&ms)[D], const double (&Ps)[D][D]) {
+    if constexpr (MO == 0) {
+      warp_store_rows<D>(msw + k * sts * D, ms, tile, lane, wk.nvalid);
+      warp_store_rows<D * D>(Psw + k * sts * D * D, flat<D>(Ps), tile, lane, wk.nvalid);
+    } else {
+      double om[MP], oP[MP][MP], HPs[MP][D];
+#pragma unroll
+      for (int a = 0; a < MP; ++a) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc = fma(Ho[a][j], ms[j], acc);
+        om[a] = acc;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          double t = 0.0;
+#pragma unroll
+          for (int c = 0; c < D; ++c) t = fma(Ho[a][c], Ps[c][j], t);
+          HPs[a][j] = t;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < MP; ++a) {
+#pragma unroll
+        for (int c = 0; c < MP; ++c) {
+          double t = 0.0;
+#pragma unroll
+          for (int j = 0; j < D; ++j) t = fma(HPs[a][j], Ho[c][j], t);
+          oP[a][c] = t;
+        }
+      }
+      if (active) {
+        store_vec<MP>(msp + k * sts * MP, om);
+        store_mat<MP>(Psp + k * sts * MP * MP, oP);
+      }
+    }
+  };
+  auto stage_of = [&](int64_t k) { return ring + (int)(k % NST) * SeqPipe<D>::STAGE; };
+  auto issue = [&](int64_t k) {
+    double* st = stage_of(k);
+    warp_rows_async<D>(mfw + k * sts * D, st, lane, wk.nvalid);
+    warp_rows_async<D * D>(Pfw + k * sts * D * D, st + RowTile<D>::SIZE, lane, wk.nvalid);
+    seq_cp_async_commit();
+  };
+  auto front = [&](int64_t k, double dt, double (&mp)[D], double (&Pp)[D][D], double (&G)[D][D]) {
+    const double* st = stage_of(k);
+    double mf[D], Pf[D][D];
+    tile_own_row<D>(st, lane, mf);
+    tile_own_row<D * D>(st + RowTile<D>::SIZE, lane, flat<D>(Pf));
+    Trans<D, S> A;
+    if constexpr (GIVEN) {
+      double Q[D][D];
+      load_trans_dense<D, S>(Ap + k * D * D, A);
+      load_mat<D>(Qp + k * D * D, Q);
+      rts_front<D, S>(A, Q, false, mf, Pf, p.jitter, mp, Pp, G);
+    } else {
+      matern_trans<D, S>(lam, dt, A);
+      rts_front<D, S>(A, Pinf, true, mf, Pf, p.jitter, mp, Pp, G);
+    }
+  };
+  auto back = [&](int64_t k, const double (&mp)[D], const double (&Pp)[D][D], const double (&G)[D][D],
+                  double (&ms)[D], double (&Ps)[D][D]) {
+    const double* st = stage_of(k);
+    double mf[D], Pf[D][D];
+    tile_own_row<D>(st, lane, mf);
+    tile_own_row<D * D>(st + RowTile<D>::SIZE, lane, flat<D>(Pf));
+    rts_back<D>(mf, Pf, mp, Pp, G, ms, Ps);
+  };
+
+  // terminal step: smoothed = filtered
+  double ms[D], Ps[D][D];
+  load_vec<D>(mfp + (T - 1) * sts * D, ms);
+  load_mat<D>(Pfp + (T - 1) * sts * D * D, Ps);
+  emit(T - 1, ms, Ps);
+  if (T < 2) return;
+  // prologue: front(T - 2)
+  double mp[D], Pp[D][D], G[D][D];
+  issue(T - 2);
+  if (T >= 3) issue(T - 3);
+  double dt_n = (T >= 3) ? dtp[T - 3] : 0.0;
+  {
+    if (T >= 3) asm volatile("cp.async.wait_group 1;" ::: "memory"); else seq_cp_async_wait_all();
+    __syncwarp();
+    front(T - 2, dtp[T - 2], mp, Pp, G);
+  }
+  // steady state: front(k) and back(k + 1) share the iteration; rows of step k - 1 are in flight
+  for (int64_t k = T - 3; k >= 0; --k) {
+    const double dt = dt_n;
+    seq_cp_async_wait_all();
+    __syncwarp();                                      // stage k landed for every lane; stage k + 2 is free again
+    if (k >= 1) {
+      issue(k - 1);
+      dt_n = dtp[k - 1];
+    }
+    double mp2[D], Pp2[D][D], G2[D][D];
+    front(k, dt, mp2, Pp2, G2);
+    back(k + 1, mp, Pp, G, ms, Ps);
+    emit(k + 1, ms, Ps);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      mp[i] = mp2[i];
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        Pp[i][j] = Pp2[i][j];
+        G[i][j] = G2[i][j];
+      }
+    }
+  }
+  // epilogue: back(0)
+  back(0, mp, Pp, G, ms, Ps);
+  emit(0, ms, Ps);
+}
+
 // ------------------------------------------------------------------------------------------ launch
 static inline int pick_block(int64_t B) {
   // Every thread lives for the whole launch (one series each), so what matters is how evenly the warps fall on
@@ -745,12 +950,58 @@ static int launch_filter(cudaStream_t st, const SeqFilterArgs& a) {
   return cuda_status(cudaGetLastError(), "seq_filter_kernel launch");
 }
 
+// series one full wave of a thread-per-series kernel keeps resident (occupancy x threads x SMs)
+template <typename K>
+static int seq_wave(K kern, int threads, int64_t* out) {
+  int blocks = 0, dev = 0, sms = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, threads, 0);
+  if (e == cudaSuccess) e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return cuda_status(e, "seq kernel occupancy query");
+  *out = (int64_t)blocks * threads * sms;
+  return PHYSS_OK;
+}
+
 template <int D, int S, int MO, bool GIVEN>
 static int launch_smooth(cudaStream_t st, const SeqSmoothArgs& a) {
+  if (a.wave_out) {
+    if constexpr (D % 2 == 0) {
+      auto kern = seq_smooth_pipe_kernel<D, S, MO, GIVEN>;
+      const size_t smem = SeqPipe<D>::smem_bytes(1);
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      int blocks = 0, dev = 0, sms = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, 32, smem);
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      *a.wave_out = (int64_t)blocks * 32 * sms;
+      return PHYSS_OK;
+    } else {
+      return seq_wave(seq_smooth_kernel<D, S, MO, GIVEN, false, true>, 32, a.wave_out);
+    }
+  }
   const int64_t n = ((a.B + 31) / 32 * 32) * (a.nchunk > 0 ? a.chunk_count : 1);
   const int block = pick_block(n) < SeqBlock<D>::THREADS ? pick_block(n) : SeqBlock<D>::THREADS;
   const int64_t grid = (n + block - 1) / block;
   const bool coal = (a.sbs == 1);
+  if constexpr (D % 2 == 0) {
+    static const bool no_pipe = [] { const char* e = getenv("PHYSS_SEQ_NOPIPE"); return e && e[0] == '1'; }();
+    if (coal && a.nchunk == 0 && !no_pipe) {
+      // one warp per block: the block scheduler spreads the (few) warps of a batch evenly over the SMs
+      auto kern = seq_smooth_pipe_kernel<D, S, MO, GIVEN>;
+      const size_t smem = SeqPipe<D>::smem_bytes(1);
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return cuda_status(e, "seq_smooth_pipe_kernel: configuration");
+        configured = true;
+      }
+      kern<<<(unsigned)(n / 32), 32, smem, st>>>(a);
+      return cuda_status(cudaGetLastError(), "seq_smooth_pipe_kernel launch");
+    }
+  }
   if (a.nchunk > 0) {
     if (MO != 0 && a.fixup) return set_error(PHYSS_ERR_BAD_ARG, "smoother fix-up needs full_state output");
     if (coal) seq_smooth_kernel<D, S, MO, GIVEN, true, true><<<(unsigned)grid, block, 0, st>>>(a);

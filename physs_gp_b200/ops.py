@@ -106,6 +106,17 @@ def _disc_args(disc, B, T, d):
     return keep, null, null, (lam.data_ptr(), sl[0]), (Pinf.data_ptr(), sP[0])
 
 
+def kf_wave_series(d, m=1, nblk=0):
+    """Series one full wave of the smoother kernel keeps resident on the current GPU for state dim d
+    (`physs_kf_wave_series`; nblk > 0: DISC_MATERN with nblk blocks, else DISC_GIVEN).  Batches that are whole
+    multiples of it never end on a half-empty GPU."""
+    with torch.cuda.device(torch.cuda.current_device()):
+        w = int(_lib.load().physs_kf_wave_series(int(d), _lib.DISC_MATERN if nblk else _lib.DISC_GIVEN, int(nblk)))
+    if w <= 0:
+        raise _lib.PhyssError("physs_kf_wave_series: no fixed-wave kernel for d = %d" % d)
+    return w
+
+
 def kf_supported(d, m, disc):
     return bool(_lib.load().physs_kf_supported(d, m, disc.mode, disc.nblk))
 

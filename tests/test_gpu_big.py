@@ -61,3 +61,17 @@ def test_big_block_equals_lane_group_kernels(cuda_device, monkeypatch):
     assert rel(lml_b, lml_a.cpu().numpy()) < TOL
     assert rel(kf_b['P'], kf_a['P'].cpu().numpy()) < TOL and rel(kf_b['m'], kf_a['m'].cpu().numpy()) < TOL
     assert rel(var_b, var_a.cpu().numpy()) < TOL and rel(mu_b, mu_a.cpu().numpy()) < TOL
+
+
+def test_big_block_non_pd_gives_nan(cuda_device, monkeypatch):
+    """a non-PD innovation covariance must come back as NaN (the reference's jnp.linalg.cholesky
+    yields NaN, the trainer's NaN guard relies on it), not as a finite partially-factored result."""
+    from physs_gp_b200 import data, filters, settings
+    pprior, oprior, t, Y, R = _st_problem(20, 12, 5, nan_frac=0.0)
+    R = R.copy()
+    R[4] = -50.0 * np.eye(20)                                    # S_4 = H P H^T + R_4 is negative definite
+    d = data.TemporalData(t, Y[:, :, None])
+    lml, kf = filters.filter_loop(d, pprior, R=R)
+    assert not np.isfinite(float(lml))
+    assert not torch.isfinite(kf['P'][4:]).any() and not torch.isfinite(kf['m'][4:]).any()
+    assert torch.isfinite(kf['P'][:4]).all()

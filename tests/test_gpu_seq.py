@@ -266,3 +266,46 @@ def test_time_major_equals_batch_major_bitwise(cuda_device, d, m, given, mo):
     for a, b in zip(*res):
         assert torch.isfinite(a).all()
         assert torch.equal(a, b)
+
+
+def test_broadcast_transitions_are_materialised(cuda_device):
+    """Disc.given(A, Q) with time-invariant A, Q ([d, d], broadcast over T) and a dt of shape [1]
+    must give the same result as the explicit [T, d, d] arrays (the kernels index the time axis densely)."""
+    from physs_gp_b200 import ops
+    dev = cuda_device
+    rng = np.random.default_rng(5)
+    B, T, d = 3, 50, 2
+    oprior = osde.LTI_SDE([osde.Matern32(0.8, 1.1)])
+    A1 = oprior.expm(0.1)
+    Q1 = oprior.Q(0.1, A1, oprior.P_inf())
+    tt = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=dev)   # noqa: E731
+    Y = tt(rng.normal(size=(B, T, 1)))
+    R = tt(np.full((1, 1, 1, 1), 0.1))
+    H, m0, P0 = tt(oprior.H()[None]), tt(np.zeros((1, d))), tt(oprior.P_inf()[None])
+    full = ops.Disc.given(tt(np.tile(A1, [T, 1, 1])), tt(np.tile(Q1, [T, 1, 1])))
+    bcast = ops.Disc.given(tt(A1), tt(Q1))
+    dt_full, dt_b = tt(np.full(T, 0.1)), tt(np.full(1, 0.1))
+    lml_a, mf_a, Pf_a = ops.kf_filter(dt_full, Y, R, H, m0, P0, full, jitter=1e-5)
+    lml_b, mf_b, Pf_b = ops.kf_filter(dt_b, Y, R, H, m0, P0, bcast, jitter=1e-5)
+    assert torch.equal(lml_a, lml_b) and torch.equal(mf_a, mf_b) and torch.equal(Pf_a, Pf_b)
+    ms_a, Ps_a = ops.rts_smooth(dt_full, mf_a, Pf_a, full, Hout=None, jitter=1e-5)
+    ms_b, Ps_b = ops.rts_smooth(dt_b, mf_b, Pf_b, bcast, Hout=None, jitter=1e-5)
+    assert torch.equal(ms_a, ms_b) and torch.equal(Ps_a, Ps_b)
+
+
+def test_scalar_update_non_pd_innovation_gives_nan_lml(cuda_device):
+    """with m = 1 two steps with S < 0 must not cancel in the running determinant product --
+    the reference's cholesky(S) gives NaN at each such step."""
+    from physs_gp_b200 import ops
+    dev = cuda_device
+    rng = np.random.default_rng(6)
+    B, T, d = 2, 20, 2
+    oprior = osde.LTI_SDE([osde.Matern32(0.8, 1.1)])
+    tt = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=dev)   # noqa: E731
+    Y = tt(rng.normal(size=(B, T, 1)))
+    Rn = np.full((1, T, 1, 1), 0.1)
+    Rn[0, 3] = Rn[0, 7] = -25.0                                   # two negative innovation variances
+    disc = ops.Disc.matern(1, tt(np.full((1, 1), np.sqrt(3.0) / 0.8)), tt(oprior.P_inf()[None]))
+    lml, _, _ = ops.kf_filter(tt(np.full(T, 0.1)), Y, tt(Rn), tt(oprior.H()[None]), tt(np.zeros((1, d))),
+                              tt(oprior.P_inf()[None]), disc, jitter=1e-5)
+    assert torch.isnan(lml).all()

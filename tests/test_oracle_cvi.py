@@ -116,3 +116,41 @@ def test_pendulum_collocation_ell_closed_form_vs_quadrature_and_finite_differenc
         J = np.array([1.3 * np.cos(m[0]), 0.2, 1.0])
         ref = -0.5 * np.outer(J, J) / 0.01 + (0 if np.isnan(y[0]) else -0.5 * np.outer([1, 0, 0], [1, 0, 0]) / 0.05)
         assert np.allclose(dS_gn, ref, rtol=1e-13, atol=1e-13)
+
+
+def test_vectorised_scalar_cvi_iteration_matches_block_loops():
+    """oracle/cvi_vec.py (the CPU restatement timed by bench.py for config 4) == the per-block loops of
+    oracle/cvi.py composed as natural_gradients + elbo, on a small Poisson and Bernoulli problem."""
+    from oracle import cvi_vec
+    rng = np.random.default_rng(11)
+    B, T = 3, 40
+    t = np.cumsum(rng.uniform(0.5, 1.5, T) * 0.1)
+    ls = rng.uniform(0.5, 2.0, B)
+    for kind in ("poisson", "bernoulli"):
+        Y = (rng.poisson(1.5, size=(B, T)) if kind == "poisson" else rng.integers(0, 2, size=(B, T))).astype(float)
+        Y[rng.uniform(size=Y.shape) < 0.1] = np.nan
+        Ytil = rng.normal(size=(B, T)) * 0.3
+        Vtil = rng.uniform(0.5, 2.0, size=(B, T))
+        kerns = [sde.Matern32(l, 1.0) for l in ls]
+        lam = np.array([[np.sqrt(3.0) / l] for l in ls])
+        Pinf = np.stack([sde.LTI_SDE([k]).P_inf() for k in kerns])
+        H = sde.LTI_SDE([kerns[0]]).H()
+        Yn, Vn, el = cvi_vec.cvi_iteration((2, lam, Pinf, H), t, Y, Ytil, Vtil, kind, 0.3, K=20, binsize=0.8)
+        for b in range(B):
+            prior = sde.LTI_SDE([kerns[b]])
+
+            def posterior(Yt, Vt):
+                lml, mf, Pf, _ = filters.filter_sequential(prior, t, Yt[:, None], Vt[:, None, None], 1e-5)
+                ms, Ps = filters.smoother_sequential(prior, t, mf, Pf, full_state=False, jitter=1e-5)
+                return lml, ms[:, :, 0], Ps
+            _, qm, qv = posterior(Ytil[b], Vtil[b])
+            g = [cvi.gh_ell_and_grads(Y[b, k], qm[k, 0], qv[k, 0, 0], kind, 20, 0.8) for k in range(T)]
+            dm = np.array([x[1] for x in g])[:, None]
+            dS = np.array([x[2] for x in g])[:, None, None]
+            Y1, V1 = cvi.cvi_step(Ytil[b][:, None], Vtil[b][:, None, None], qm, qv, dm, dS, 0.3)
+            np.testing.assert_allclose(Yn[b], Y1[:, 0], rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(Vn[b], V1[:, 0, 0], rtol=1e-10, atol=1e-12)
+            lml, qm2, qv2 = posterior(Y1[:, 0], V1[:, 0, 0])
+            ell = sum(cvi.gh_ell_and_grads(Y[b, k], qm2[k, 0], qv2[k, 0, 0], kind, 20, 0.8)[0] for k in range(T))
+            ref = cvi.elbo(ell, cvi.surrogate_ell(Y1, V1, qm2, qv2), lml)
+            assert abs(el[b] - ref) < 1e-9 * abs(ref)
