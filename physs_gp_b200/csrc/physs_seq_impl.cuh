@@ -288,15 +288,19 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
   // speculative chunk mode: start `warm` steps before the chunk from (m0, P0) and discard those steps
   // (uniform over the warp: its lanes share the chunk)
   const int64_t w0 = (CHUNK && !p.from_bnd && p.warm > 0) ? ((p.warm < t0) ? p.warm : t0) : 0;
-  // software prefetch of the next step's streamed inputs
+  // software prefetch of the next step's streamed inputs; the closed-form transition of step k + 1 is evaluated
+  // during step k (it depends on dt only, so its exp / polynomial chain overlaps the predict / update chain of
+  // the current step inside one basic block instead of heading the critical path of the next one)
   double y_n[M], R_n[M][M], dt_n;
   load_vec<M>(Yp - w0 * sts * M, y_n);
   load_mat<M>(Rp - w0 * p.R_ts, R_n);
-  dt_n = dtp[-w0];
+  dt_n = (1 - w0 < T) ? dtp[1 - w0] : 0.0;                   // dt of the step AFTER the first one
+  Trans<D, S> A_n;
+  if constexpr (!GIVEN) matern_trans<D, S>(lam, dtp[-w0], A_n);
 
   for (int64_t k = -w0; k < T; ++k) {
     double y[M], R[M][M];
-    const double dt = dt_n;
+    const double dt_next = dt_n;
 #pragma unroll
     for (int a = 0; a < M; ++a) {
       y[a] = y_n[a];
@@ -306,8 +310,8 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
     if (k + 1 < T) {
       load_vec<M>(Yp + (k + 1) * sts * M, y_n);
       if (p.R_ts != 0) load_mat<M>(Rp + (k + 1) * p.R_ts, R_n);
-      dt_n = dtp[k + 1];
     }
+    if (k + 2 < T) dt_n = dtp[k + 2];
     Trans<D, S> A;
     if constexpr (GIVEN) {
       double Q[D][D];
@@ -315,7 +319,8 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
       load_mat<D>(Qp + k * D * D, Q);
       kf_predict_givenQ<D, S>(A, Q, m, P);
     } else {
-      matern_trans<D, S>(lam, dt, A);
+      A = A_n;
+      matern_trans<D, S>(lam, dt_next, A_n);                  // unconditional (dt_next is stale past the end: unused)
       kf_predict_stationary<D, S>(A, Pinf, m, P);
     }
     double det, mahal;

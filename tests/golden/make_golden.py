@@ -238,6 +238,10 @@ def install_standin():
             assert onp.ndim(a) == b, "chex.assert_rank: %s != %s" % (onp.ndim(a), b)
 
     def assert_shape(x, s):
+        if isinstance(x, (list, tuple)):
+            for a, b in zip(x, s):
+                assert_shape(a, b)
+            return
         assert tuple(onp.shape(x)) == tuple(s), "chex.assert_shape: %s != %s" % (onp.shape(x), s)
 
     def assert_equal(a, b):

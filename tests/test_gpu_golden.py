@@ -66,3 +66,50 @@ def test_cuda_cvi_blocks_match_reference_vectors(cuda_device):
                                               dev(g[k + "Yobs"][None, :, 0]), None, cvi.GaussianLik(np.eye(D)),
                                               noise=dev(g[k + "V"][None]))
             assert abs(float(ell[0]) - float(g[k + "ell"])) <= TOL * abs(float(g[k + "ell"]))
+
+
+def test_cuda_cvi_iteration_and_elbo_match_reference_assembly(cuda_device, monkeypatch):
+    """One whole CVI iteration and the ELBO through the reference-shaped objects (cvi.VGP.natural_gradient_update
+    / .elbo: posterior kernels -> fused site kernel -> ELL kernels) against the reference's OWN
+    `natural_gradients` + `elbo` (tests/golden/make_golden_cvi.py; Gaussian likelihood, full-state sites)."""
+    from physs_gp_b200 import cvi, kernels as K, sdes, settings
+    g = np.load(os.path.join(GOLD, "cvi_assembly.npz"))
+    keys = sorted({k.rsplit("_", 1)[0] for k in g.files if k.endswith("_elbo")})
+    kind = {"m32": K.Matern32, "m52": K.Matern52, "m72": K.Matern72}
+    for key in keys:
+        monkeypatch.setattr(settings, "jitter", float(g[key + "_jitter"]))
+        monkeypatch.setattr(settings, "ng_jitter", float(g[key + "_ng_jitter"]))
+        ls, var = g[key + "_hyper"]
+        prior = sdes.LTI_SDE_Full_State_Obs(sdes.Independent([kind[str(g[key + "_kernel"][0])](float(ls), float(var))]))
+        Ytil, Vtil = g[key + "_Ytil"], g[key + "_Vtil"]
+        T, D = Ytil.shape
+        q = cvi.FullConjugateGaussian(g[key + "_t"], prior, D, B=1, Y_tilde=Ytil[None], V_tilde=Vtil[None],
+                                      device=cuda_device)
+        model = cvi.VGP(g[key + "_Yobs"][None], cvi.GaussianLik(g[key + "_noise"]), q)
+        # the ELBO the generator recorded is evaluated at the ORIGINAL sites; evaluate it before the update
+        elbo = float(model.elbo()[0])
+        assert abs(elbo - float(g[key + "_elbo"])) <= TOL * abs(float(g[key + "_elbo"])), key
+        model.natural_gradient_update(float(g[key + "_beta"]))
+        cond = max(np.linalg.cond(Vtil[k]) for k in range(T))
+        assert rel(q.Y_tilde[0], g[key + "_Ytil_new"]) < TOL * max(1.0, cond), key
+        assert rel(q.V_tilde[0], g[key + "_Vtil_new"]) < TOL * max(1.0, cond), key
+
+
+def test_cuda_gauss_newton_curvature_matches_reference_assembly(cuda_device):
+    """The collocation kernel's Gauss-Newton curvature (physs_cvi_ell_pendulum_f64, gauss_newton=1) and the
+    generic physs_cvi_gauss_newton_f64 on the recorded Jacobians, against 0.5 * the reference's own assembly lines
+    (cvi_hessian_approximations.py slice, see tests/golden/make_golden_cvi.py)."""
+    from physs_gp_b200 import cvi
+    g = np.load(os.path.join(GOLD, "gn_pendulum.npz"))
+
+    def dev(x):
+        return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64).cuda()
+    u, Y, H = g["u"], g["Y"], g["approx_hessian"]
+    T, D = u.shape
+    lik = cvi.DampedPendulumLik(g=float(g["g"]), l=float(g["l"]), b=float(g["b"]), var_obs=float(g["var_obs"]),
+                                var_col=float(g["var_col"]))
+    q_var = np.tile(0.1 * np.eye(D), [T, 1, 1])
+    _, _, dS = cvi.pendulum_expected_log_likelihood(dev(u), dev(q_var), dev(Y), lik, gauss_newton=True, want_grads=True)
+    assert rel(dS, H) < 1e-12
+    dS2 = cvi.gauss_newton_curvature(dev(g["J"]), np.array([float(g["var_obs"]), float(g["var_col"])]), y=dev(Y))
+    assert rel(dS2, H) < 1e-12
