@@ -357,6 +357,47 @@ def main():
     fn = os.path.join(HERE, "independent_stack.npz")
     onp.savez_compressed(fn, **st)
     written.append(fn)
+    # ===================================== Monte-Carlo ELL of the reference (the path config 4 really takes)
+    # mv_indepentdent_monte_carlo (integrals/approximators.py:16-58) with the reference's own scalar
+    # log-likelihoods (general.py:9-26, likelihood/poisson.py:20-22, likelihood/bernoulli.py:17-19), driven by a
+    # numpy PRNG in place of objax.random (the objax threefry stream is not reproducible here): the fixture records
+    # the MC mean and its standard error, which tests/test_oracle_cvi.py uses as a STATISTICAL pin (4 sigma) for
+    # the Gauss-Hermite quadrature that replaces MC on the B200 path.
+    import scipy.special as ssp
+    ns_m = dict(base_ns)
+    mc_rng = onp.random.default_rng(2024)
+    ns_m["objax"] = types.SimpleNamespace(random=types.SimpleNamespace(
+        normal=lambda shape, mean=0.0, stddev=1.0, generator=None: A(mc_rng.normal(size=shape))))
+    ns_m["jax"] = types.SimpleNamespace(vmap=lambda f, in_axes, out_axes=0: (
+        # the generic stand-in vmap loops in Python; here only argument 1 (the samples) is batched and the
+        # reparameterisation is elementwise, so the batch is evaluated sample-by-sample in chunks
+        lambda fn, samples, mu, var, *args: onp.stack([onp.asarray(f(fn, A(s), mu, var, *args)) for s in samples])))
+    mc = mg.extract("computation/integrals/approximators.py", ["mv_indepentdent_monte_carlo"], ns_m)[
+        "mv_indepentdent_monte_carlo"]
+    gen_ns = {"np": jnp, "jit": mg._jit, "chex": types.SimpleNamespace(assert_rank=lambda *a: None),
+              "gammaln": lambda x: A(ssp.gammaln(x))}
+    logs = mg.extract("computation/general.py", ["log_poisson", "log_bernoulli"], gen_ns)
+    S = 200000
+    sites = [(3.0, 0.4, 0.3), (0.0, -0.5, 0.8), (7.0, 1.2, 0.15), (1.0, 0.1, 1.5)]
+    mcout = {"num_samples": S}
+    for kind in ("poisson", "bernoulli"):
+        ys = onp.array([s[0] if kind == "poisson" else float(s[0] > 1) for s in sites])
+        mu = A(onp.array([s[1] for s in sites])[:, None, None])
+        var = A(onp.array([s[2] for s in sites])[:, None, None])
+        binsize = 0.8
+        if kind == "poisson":
+            fn_ = lambda f: A(logs["log_poisson"](ys[:, None, None], jnp.exp(f) * binsize))   # noqa: E731
+        else:
+            fn_ = lambda f: A(ys[:, None, None] * jnp.log(A(ssp.ndtr(f)) + 1e-5)              # noqa: E731
+                              + (1 - ys[:, None, None]) * jnp.log(1 - A(ssp.ndtr(f)) + 1e-5))
+        samp = onp.asarray(mc(fn_, mu, var, generator=object(), num_samples=S, average=False))   # [S, N, 1, 1]
+        mcout[kind + "_y"], mcout[kind + "_m"], mcout[kind + "_v"] = ys, onp.asarray(mu)[:, 0, 0], onp.asarray(var)[:, 0, 0]
+        mcout[kind + "_mc_mean"] = samp.mean(0)[:, 0, 0]
+        mcout[kind + "_mc_stderr"] = samp.std(0, ddof=1)[:, 0, 0] / onp.sqrt(S)
+        mcout[kind + "_binsize"] = binsize
+    fn = os.path.join(HERE, "mc_ell.npz")
+    onp.savez_compressed(fn, **mcout)
+    written.append(fn)
     for f in written:
         print("wrote", os.path.relpath(f, HERE), os.path.getsize(f), "bytes")
 

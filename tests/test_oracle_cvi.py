@@ -154,3 +154,18 @@ def test_vectorised_scalar_cvi_iteration_matches_block_loops():
             ell = sum(cvi.gh_ell_and_grads(Y[b, k], qm2[k, 0], qv2[k, 0, 0], kind, 20, 0.8)[0] for k in range(T))
             ref = cvi.elbo(ell, cvi.surrogate_ell(Y1, V1, qm2, qv2), lml)
             assert abs(el[b] - ref) < 1e-9 * abs(ref)
+
+
+def test_gauss_hermite_ell_within_4_sigma_of_reference_monte_carlo():
+    """Statistical pin of the quadrature that replaces the reference's Monte-Carlo ELL: K = 20
+    Gauss-Hermite vs 2e5 reparameterised samples drawn by the reference's own mv_indepentdent_monte_carlo
+    (integrals/approximators.py:16-58) with its own Poisson / Bernoulli log-likelihoods
+    (tests/golden/make_golden_cvi.py -> tests/golden/mc_ell.npz), within 4 standard errors."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mc_ell.npz"))
+    for kind in ("poisson", "bernoulli"):
+        for y, m, v, mean, se in zip(g[kind + "_y"], g[kind + "_m"], g[kind + "_v"], g[kind + "_mc_mean"],
+                                     g[kind + "_mc_stderr"]):
+            ell = cvi.gh_ell_and_grads(float(y), float(m), float(v), kind, K=20, binsize=float(g[kind + "_binsize"]))[0]
+            assert abs(ell - mean) < 4.0 * se, (kind, y, m, v, ell, mean, se)
+            assert se < 0.02 * max(1.0, abs(mean))             # the pin is tight enough to mean something
