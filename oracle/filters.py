@@ -3,6 +3,7 @@
 Follows (paths relative to /root/reference/src/lib/stgp/computation/filters/):
   kalman_filter.py:144-211    kf_update_step (masking, jittered gain solve, P - K S K^T, lml)
   kalman_filter.py:214-241    kf_predict_step(LTI_SDE)
+  kalman_filter.py:340-427    kf_predict_step(PDE): collocation (EKF) step -- filter_pde_sequential
   kalman_filter.py:439-485    filter('sequential'): scan from (m_inf, P_inf), lml = sum
   kalman_filter.py:487-547    filter_loop: dt = [0, diff(t)], Y -> [T, m, 1]
   rts_smoother.py:48-65       rts_smoother_step (jittered chol of P_pred)
@@ -21,12 +22,15 @@ from . import linalg as la
 
 # ------------------------------------------------------------------ sequential filter
 
-def kf_update_step(m_, P_, H, R, y, jitter=la.JITTER):
-    """kalman_filter.py:144-211.  y: [m,1] with NaN = missing.  Returns m, P, lml_k."""
+def kf_update_step(m_, P_, H, R, y, jitter=la.JITTER, innovation=None):
+    """kalman_filter.py:144-211.  y: [m,1] with NaN = missing.  Returns m, P, lml_k.
+    `innovation` (the reference's last argument): the predicted observation; H m_ for linear observations, the
+    non-linear residual g(m_) for the collocation update of the PDE filter (:413)."""
     mask = (~np.isnan(y)).astype(int)              # nan_utils.py:13-20
     y0 = np.nan_to_num(y)
     M = np.tile(mask, [1, y.shape[0]]) * np.eye(y.shape[0])
-    innovation = H @ m_
+    if innovation is None:
+        innovation = H @ m_
     mu = M @ innovation
     var = M @ H @ P_ @ H.T @ M.T
     v = y0 - mu
@@ -57,6 +61,78 @@ def filter_sequential(prior, X_time, Y, R, jitter=la.JITTER):
         m_ = A @ m
         P_ = A @ P @ A.T + Q
         m, P, l = kf_update_step(m_, P_, H, R[k], Ycol[k], jitter)
+        ms.append(m), Ps.append(P), lmls.append(l)
+    lmls = np.array(lmls)
+    return float(np.sum(lmls)), np.array(ms), np.array(Ps), lmls
+
+
+# ------------------------------------------------------------------ collocation (EKF) filter
+
+class PointResidual:
+    """Point-wise collocation residual of an ODE / PDE on the derivative-augmented state x [d]:
+
+        g(x, k) = w . x + sum_q coef_q * phi_q(x[idx_q]) + forcing[k],     phi in {sin, cos, square, cube}
+
+    with its Jacobian dg/dx = w + sum_q coef_q phi_q'(x[idx_q]) e_idx_q -- what `PDE.forward_g` / `PDE.H_jac`
+    (transforms/pdes.py:236-245) evaluate with jax.jacfwd for the point-wise residuals the reference ships
+    (Pendulum1D :482-528, DampedPendulum1D :530-597, SimpleODE :424-480, Allen-Cahn's u^3 - u :700-811)."""
+    KINDS = {"sin": 0, "cos": 1, "square": 2, "cube": 3}
+
+    def __init__(self, w, terms=(), forcing=None):
+        self.w = np.asarray(w, float)
+        self.terms = [(k, int(i), float(c)) for k, i, c in terms]
+        self.forcing = None if forcing is None else np.asarray(forcing, float)
+
+    def g(self, x, k):
+        x = np.ravel(x)
+        v = float(self.w @ x)
+        for kind, i, c in self.terms:
+            v += c * {"sin": np.sin, "cos": np.cos, "square": lambda z: z * z, "cube": lambda z: z ** 3}[kind](x[i])
+        return v + (0.0 if self.forcing is None else self.forcing[k])
+
+    def jac(self, x):
+        x = np.ravel(x)
+        J = self.w.copy()
+        for kind, i, c in self.terms:
+            J[i] += c * {"sin": np.cos, "cos": lambda z: -np.sin(z), "square": lambda z: 2 * z,
+                         "cube": lambda z: 3 * z * z}[kind](x[i])
+        return J[None, :]
+
+
+def filter_pde_sequential(prior, residuals, X_time, Y, R, boundary=None, y_pseudo=None, observe_data=True,
+                          jitter=la.JITTER):
+    """kf_predict_step(PDE, 'sequential') (kalman_filter.py:340-427) inside filter('sequential') (:439-485):
+    LTI predict, optional boundary update with R * 0 (:382-391), pseudo-observation update with H = dg/dx at the
+    PREDICTED mean, zero noise and innovation g(m_) (:395-414; both evaluated before the boundary update, :378-379),
+    then the data update (:417-421).  The step's lml is that of the LAST update executed (the `ys` returned).
+
+    residuals: list of Pc PointResidual (the reference needs Pc >= 2: `np.squeeze(f)[..., None]`, :413, is rank 1
+    for a single output).  Y [T, m] data (NaN = missing); boundary [T, m] or None (NaN = no boundary observation
+    at that step); y_pseudo [Pc]: the pseudo observations (0, or NaN for "no collocation on this output").
+    Returns lml, m [T,d,1], P [T,d,d], lml_k."""
+    Pc = len(residuals)
+    y_ps = np.zeros(Pc) if y_pseudo is None else np.asarray(y_pseudo, float)
+    T = X_time.shape[0]
+    dt = np.hstack([np.zeros(1), np.diff(X_time)])
+    Ycol = np.reshape(Y, [T, -1])[..., None]
+    m, P = prior.m_inf(), prior.P_inf()
+    P_inf, H = prior.P_inf(), prior.H()
+    ms, Ps, lmls = [], [], []
+    for k in range(T):
+        A = prior.expm(dt[k])
+        Q = prior.Q(dt[k], A, P_inf)
+        m_ = A @ m
+        P_ = A @ P @ A.T + Q
+        f = np.array([[r.g(m_, k)] for r in residuals])
+        Hj = np.vstack([r.jac(m_) for r in residuals])
+        l = 0.0
+        if boundary is not None:
+            m_, P_, l = kf_update_step(m_, P_, H, R[k] * 0.0, np.reshape(boundary[k], [-1, 1]), jitter,
+                                       innovation=H @ m_)
+        m_, P_, l = kf_update_step(m_, P_, Hj, np.zeros((Pc, Pc)), y_ps[:, None], jitter, innovation=f)
+        if observe_data:
+            m_, P_, l = kf_update_step(m_, P_, H, R[k], Ycol[k], jitter, innovation=H @ m_)
+        m, P = m_, P_
         ms.append(m), Ps.append(P), lmls.append(l)
     lmls = np.array(lmls)
     return float(np.sum(lmls)), np.array(ms), np.array(Ps), lmls

@@ -211,3 +211,41 @@ def test_product_prior_stacking_matches_reference():
             Pinf = prior.P_inf()
             assert rel(Ak, g[key + "_A"]) < 1e-14 and rel(Pinf, g[key + "_Pinf"]) < 1e-14
             assert rel(prior.Q(dt, Ak, Pinf), g[key + "_Q"]) < 1e-12
+
+
+# ------------------------------------------------------------------------------- collocation (EKF) filter step
+def _ekf_files():
+    return sorted(glob.glob(os.path.join(GOLD, "ekf_*.npz")))
+
+
+def ekf_residuals(g):
+    out = []
+    for p in range(int(g["n_res"])):
+        terms = [(str(k), int(i), float(c)) for k, i, c in
+                 zip(g["term_kind%d" % p], g["term_idx%d" % p], g["term_coef%d" % p])]
+        f = g["forcing%d" % p]
+        out.append(ofilters.PointResidual(g["w%d" % p], terms, f if f.size else None))
+    return out
+
+
+def test_ekf_golden_files_present():
+    assert len(_ekf_files()) == 5
+
+
+@pytest.mark.parametrize("path", _ekf_files(), ids=[os.path.basename(p)[4:-4] for p in _ekf_files()])
+def test_oracle_collocation_filter_matches_reference(path):
+    """oracle.filters.filter_pde_sequential == the reference's kf_predict_step(PDE, 'sequential')
+    (kalman_filter.py:340-427) run by tests/golden/make_golden_ekf.py, and the smoother on its output ==
+    rts_step_wrapper(PDE) (rts_smoother.py:108-150)."""
+    g = np.load(path)
+    ls, var = g["hyper"]
+    prior = osde.LTI_SDE([KIND[str(g["kernel"][0])](float(ls), float(var))])
+    jit = float(g["jitter"])
+    bnd = g["boundary"] if "boundary" in g.files else None
+    lml, mf, Pf, _ = ofilters.filter_pde_sequential(prior, ekf_residuals(g), g["t"], g["Y"], g["R"], boundary=bnd,
+                                                    y_pseudo=g["y_pseudo"], observe_data=bool(g["observe_data"]),
+                                                    jitter=jit)
+    assert abs(lml - float(g["lml"])) < 1e-11 * abs(float(g["lml"]))
+    assert rel(mf, g["mf"]) < 1e-11 and rel(Pf, g["Pf"]) < 1e-11
+    ms, Ps = ofilters.smoother_sequential(prior, g["t"], mf, Pf, full_state=True, jitter=jit)
+    assert rel(ms, g["ms"]) < 1e-10 and rel(Ps, g["Ps"]) < 1e-10
