@@ -145,6 +145,47 @@ int physs_kf_filter_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_
                                const double* Hout, int32_t mo,
                                double* mf, double* Pf, double* lml, double* lml_k, double* ms, double* Ps);
 
+/* Collocation (EKF) Kalman filter over B independent series: the state-space prior constrained by a point-wise
+ * ODE / PDE residual at every step.  Replaces kf_predict_step(PDE, 'sequential') inside filter('sequential')
+ * (computation/filters/kalman_filter.py:340-427, 439-485).  Per step: LTI predict; residual f = g(m_) and Jacobian
+ * H_jac = dg/dx(m_) at the PREDICTED mean (:378-379; the reference: jax.jacfwd of PDE.forward_g,
+ * transforms/pdes.py:236-245); optional boundary update with H, R * 0 and y = boundary[k] (:382-391); pseudo-
+ * observation update with H_jac, ZERO noise, y = y_pseudo and innovation f (:395-414); data update with H, R, Y
+ * when observe_data != 0 (:417-421).  lml_k is the term of the LAST update of the step, as in the reference.
+ * The smoother of this model is physs_rts_smooth_f64 on (mf, Pf) (rts_smoother.py:108-150).
+ *
+ * Residual table (HOST pointers, read during the call; pc = 1 or 2 outputs, n_terms <= 8):
+ *     g_p(x, k) = sum_j res_w[p, j] x[j] + sum_{q : term_out[q] = p} term_coef[q] * phi_{term_kind[q]}(x[term_idx[q]])
+ *                 + forcing[p, k]
+ *   phi: PHYSS_RES_SIN / _COS / _SQUARE / _CUBE.  forcing [pc, T] (DEVICE, shared by the batch) or NULL.
+ *   y_pseudo [pc] (HOST): the pseudo observation, NaN = output not collocated (PDE.psuedo_observations).
+ *   boundary [B, T, m] in the step layout (DEVICE, NaN = no boundary observation at that step) or NULL.
+ * Shapes supported: 2 <= d <= 4 with one Matern block (DISC_MATERN, nblk = 1) or DISC_GIVEN; m = 1, or identity H
+ * with m = d.  Everything else as physs_kf_filter_f64. */
+#define PHYSS_RES_SIN 0
+#define PHYSS_RES_COS 1
+#define PHYSS_RES_SQUARE 2
+#define PHYSS_RES_CUBE 3
+int physs_kf_filter_colloc_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                               int32_t d, int32_t m,
+                               int32_t disc_mode, int32_t nblk,
+                               const double* A, int64_t A_bstride,
+                               const double* Q, int64_t Q_bstride,
+                               const double* lam, int64_t lam_bstride,
+                               const double* dt, int64_t dt_bstride,
+                               const double* Pinf, int64_t Pinf_bstride,
+                               const double* m0, int64_t m0_bstride,
+                               const double* P0, int64_t P0_bstride,
+                               const double* H, int64_t H_bstride,
+                               const double* Y,
+                               const double* R, int64_t R_bstride, int64_t R_tstride,
+                               double jitter,
+                               int32_t pc, const double* res_w, int32_t n_terms, const int32_t* term_out,
+                               const int32_t* term_kind, const int32_t* term_idx, const double* term_coef,
+                               const double* forcing, const double* y_pseudo, const double* boundary,
+                               int32_t observe_data,
+                               double* mf, double* Pf, double* lml, double* lml_k);
+
 /* Reverse pass (vector-Jacobian product) of physs_kf_filter_f64's lml: d lml[b] / d (inputs), scaled by g_lml[b].
  * Replaces `jax.jacrev` / `jax.grad` THROUGH filter('sequential') in the reference's hyper-parameter steps
  * (trainers/trainer.py:43,128-136; trainers/standard.py:58-91): the backward half of a `jax.custom_vjp` around

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libphyss_b200.so")
 PHYSS_OK = 0
 DISC_GIVEN = 0
 DISC_MATERN = 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _c_i32 = ctypes.c_int32
 _c_i64 = ctypes.c_int64
@@ -46,6 +46,8 @@ SIGNATURES = {
         _ptr, _ptr, _ptr, _c_i32, _c_f64, _ptr, _ptr]),
     "physs_kf_filter_smooth_f64": (ctypes.c_int, _FILTER_HEAD + [_ptr, _ptr, _ptr, _c_i64, _ptr, _c_i32,
                                                                 _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "physs_kf_filter_colloc_f64": (ctypes.c_int, _FILTER_HEAD + [_c_i32, _ptr, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                                                _ptr, _c_i32, _ptr, _ptr, _ptr, _ptr]),
     "physs_kf_vjp_supported": (ctypes.c_int, [_c_i32, _c_i32, _c_i32, _c_i32]),
     "physs_kf_filter_vjp_f64": (ctypes.c_int, _FILTER_HEAD + [_ptr] * 12),
     "physs_pscan_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i32, _c_i64]),

@@ -74,7 +74,7 @@ static inline bool step_strides_ok(int64_t B, int64_t T, int64_t bs, int64_t ts)
 
 extern "C" {
 
-int physs_abi_version(void) { return 7; }
+int physs_abi_version(void) { return 8; }
 
 const char* physs_last_error(void) { return g_err; }
 
@@ -201,6 +201,21 @@ int physs_kf_filter_smooth_f64(FILTER_PARAMS, const double* A_smooth, const doub
                               disc_mode == PHYSS_DISC_GIVEN ? A_smooth : A, A_bstride,
                               disc_mode == PHYSS_DISC_GIVEN ? Q_smooth : Q, Q_bstride, lam, lam_bstride, dt_smooth,
                               dt_smooth_bstride, Pinf, Pinf_bstride, mf, Pf, Hout, mo, jitter, ms, Ps);
+}
+
+int physs_kf_filter_colloc_f64(FILTER_PARAMS, int32_t pc, const double* res_w, int32_t n_terms,
+                               const int32_t* term_out, const int32_t* term_kind, const int32_t* term_idx,
+                               const double* term_coef, const double* forcing, const double* y_pseudo,
+                               const double* boundary, int32_t observe_data, double* mf, double* Pf, double* lml,
+                               double* lml_k) {
+  SeqFilterArgs a;
+  int rc = pack_filter(FILTER_ARGS, mf, Pf, lml, lml_k, a);
+  if (rc || B == 0) return rc;
+  if (n_terms > 0 && (!term_out || !term_kind || !term_idx || !term_coef))
+    return set_error(PHYSS_ERR_BAD_ARG, "collocation filter: null residual term table");
+  if (misaligned(boundary)) return set_error(PHYSS_ERR_BAD_ARG, "collocation filter: boundary must be 16-byte aligned");
+  return colloc_filter((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, a, pc, res_w, n_terms, term_out,
+                       term_kind, term_idx, term_coef, forcing, y_pseudo, boundary, observe_data);
 }
 
 int physs_kf_vjp_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {

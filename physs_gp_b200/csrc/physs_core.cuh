@@ -283,10 +283,12 @@ PHYSS_HD void chol_solve_vec(const double (&L)[N][N], const double (&rdiag)[N], 
 //   HID: H is the identity (full-state pseudo-observations, M == D) -- skips the H products.
 // y may contain NaN (= missing).  Returns this step's log marginal likelihood term.
 // ---------------------------------------------------------------------------------------------
+//   mu_ext != nullptr: the predicted observation is supplied by the caller instead of H m -- the collocation
+//   update of the PDE filter passes the non-linear residual g(m_) with H = dg/dx (kalman_filter.py:395-414).
 template <int D, int M, bool HID>
 PHYSS_HD void kf_update(double (&m)[D], double (&P)[D][D], const double (&H)[M][D],
                         const double (&R)[M][M], const double (&y)[M], double jitter,
-                        double& det_out, double& mahal_out, int& nobs_out) {
+                        double& det_out, double& mahal_out, int& nobs_out, const double* mu_ext = nullptr) {
   // mask
   bool obs[M];
   int n_missing = 0;
@@ -313,7 +315,9 @@ PHYSS_HD void kf_update(double (&m)[D], double (&P)[D][D], const double (&H)[M][
       }
       HP[a][j] = obs[a] ? acc : 0.0;
     }
-    if (HID) {
+    if (mu_ext) {
+      mu = mu_ext[a];
+    } else if (HID) {
       mu = m[a];
     } else {
       PHYSS_UNROLL

@@ -133,6 +133,12 @@ int rt_filter_summary(cudaStream_t st, int d, int m, int disc_mode, int nblk, bo
                       int64_t cfirst, int64_t ccount, double* elems);
 int rt_smooth_summary(cudaStream_t st, int d, int disc_mode, int nblk, const SeqSmoothArgs& a, double* elems);
 
+// physs_colloc.cu: collocation (EKF) filter step, d <= 4 (descriptor arrays are HOST pointers)
+int colloc_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, const SeqFilterArgs& a,
+                  int pc, const double* res_w, int n_terms, const int32_t* t_out, const int32_t* t_kind,
+                  const int32_t* t_idx, const double* t_coef, const double* forcing, const double* y_pseudo,
+                  const double* boundary, int observe_data);
+
 // physs_pscan.cu: parallel-in-time chunked associative scan
 int64_t pscan_workspace_doubles(int64_t B, int64_t T, int d, int64_t chunk_len);
 int pscan_filter_local(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, SeqFilterArgs a,

@@ -18,7 +18,7 @@ import torch
 from . import ops
 from . import settings
 from .dispatch import dispatch, evoke
-from .sdes import BatchedMaternSDE
+from .sdes import PDE, BatchedMaternSDE
 
 
 def _device():
@@ -146,7 +146,25 @@ def _filter_impl(parallel, data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, 
     (disc,), m0, P0, H = lower_prior(prior, X_s, [dtd], dev)
     R = _to_dev(lik_mat, dev)
     Hd = None if _is_identity(H) else _to_dev(H, dev)
-    if parallel:
+    if isinstance(prior, PDE):
+        # collocation (EKF) step: kf_predict_step(PDE, 'sequential'), kalman_filter.py:340-427.  Sequential only
+        # (the reference has no parallel-in-time form of it either).
+        res = prior.residuals
+        T = Yd.shape[1]
+        forcing = None
+        if any(r.forcing is not None for r in res):
+            forcing = _to_dev(np.stack([np.zeros(T) if r.forcing is None else r.forcing for r in res]), dev)
+        terms = [(p_, k, i, c) for p_, r in enumerate(res) for k, i, c in r.terms]
+        bnd = None
+        if prior.boundary_conditions is not None:
+            bc = np.asarray(prior.boundary_conditions, np.float64)
+            if train_index is not None:
+                bc = bc[np.asarray(train_index)]                 # kalman_filter.py:464-467
+            bnd = _to_dev(bc.reshape(1, T, -1), dev).expand(Yd.shape[0], -1, -1).contiguous()
+        lml, mf, Pf = ops.kf_filter_colloc(dtd, Yd, R, Hd, m0, P0, disc, np.stack([r.w for r in res]), terms,
+                                           forcing=forcing, y_pseudo=prior.psuedo_observations()[:, 0], boundary=bnd,
+                                           observe_data=prior.observe_data, jitter=settings.jitter)
+    elif parallel:
         lml, mf, Pf, status = ops.pscan_filter(dtd, Yd, R, Hd, m0, P0, disc, chunk_len=settings.pscan_chunk_len,
                                                jitter=settings.jitter, polish=settings.pscan_polish,
                                                return_status=True)

@@ -5,6 +5,7 @@ every FLOP of the path runs in libphyss_b200.so.  No CPU fallback: non-CUDA tens
 Broadcasting: every argument is viewed with `expand` to its full [B, ...] shape and the resulting
 batch (and, for R, time) stride is handed to the kernel; a stride of 0 means "shared".
 """
+import numpy as np
 import torch
 
 from . import _lib
@@ -189,6 +190,62 @@ def kf_filter(dt, Y, R, H, m0, P0, disc, jitter=None, want_lml_k=False, out=None
         st = lib.physs_kf_filter_f64(*p.head, mf.data_ptr(), Pf.data_ptr(), lml.data_ptr(),
                                      lml_k.data_ptr() if lml_k is not None else None)
     _lib.check(st, "physs_kf_filter_f64")
+    if want_lml_k:
+        return lml, mf, Pf, lml_k
+    return lml, mf, Pf
+
+
+RES_KINDS = {"sin": 0, "cos": 1, "square": 2, "cube": 3}
+
+
+def kf_filter_colloc(dt, Y, R, H, m0, P0, disc, res_w, terms=(), forcing=None, y_pseudo=None, boundary=None,
+                     observe_data=True, jitter=None, want_lml_k=False, out=None, stream=None):
+    """Batched collocation (EKF) filter: kf_predict_step(PDE, 'sequential'), kalman_filter.py:340-427, per series
+    (`physs_kf_filter_colloc_f64`).  Arguments as `kf_filter` plus the residual table
+        g_p(x, k) = res_w[p] . x + sum_q coef_q phi_q(x[idx_q]) + forcing[p, k]
+    res_w [pc, d] (array-like, host); terms: iterable of (output p, kind in RES_KINDS, state index, coefficient);
+    forcing [pc, T] device tensor or None; y_pseudo [pc] (0 / NaN, default zeros); boundary [B, T, m] device tensor
+    (NaN = none) or None.  Returns (lml, mf, Pf[, lml_k])."""
+    import ctypes
+    lib = _lib.load()
+    p = _pack_filter(dt, Y, R, H, m0, P0, disc, jitter, stream)
+    mf, Pf, lml, lml_k = _filter_outputs(p, out, want_lml_k)
+    w = np.ascontiguousarray(np.atleast_2d(np.asarray(res_w, np.float64)))
+    pc = w.shape[0]
+    if w.shape[1] != p.d:
+        raise ValueError("res_w must be [pc, d]")
+    terms = list(terms)
+    t_out = np.array([t[0] for t in terms], np.int32)
+    t_kind = np.array([RES_KINDS[t[1]] if isinstance(t[1], str) else int(t[1]) for t in terms], np.int32)
+    t_idx = np.array([t[2] for t in terms], np.int32)
+    t_coef = np.array([t[3] for t in terms], np.float64)
+    yps = np.zeros(pc) if y_pseudo is None else np.ascontiguousarray(np.asarray(y_pseudo, np.float64).reshape(pc))
+    keep = []
+    fptr = None
+    if forcing is not None:
+        f = _dev(forcing, "forcing").contiguous()
+        if tuple(f.shape) != (pc, p.T):
+            raise ValueError("forcing must be [pc, T]")
+        keep.append(f)
+        fptr = f.data_ptr()
+    bptr = None
+    if boundary is not None:
+        bd, btm = step_layout(boundary, "boundary")
+        if tuple(bd.shape) != (p.B, p.T, p.m) or btm != p.tmaj:
+            if tuple(bd.shape) != (p.B, p.T, p.m):
+                raise ValueError("boundary must be [B, T, m]")
+            bd = bd.transpose(0, 1).contiguous().transpose(0, 1) if p.tmaj else bd.contiguous()
+        keep.append(bd)
+        bptr = bd.data_ptr()
+
+    def hp(a):
+        return a.ctypes.data_as(ctypes.c_void_p) if a.size else None
+    with torch.cuda.device(p.dev):
+        st = lib.physs_kf_filter_colloc_f64(*p.head, pc, hp(w), len(terms), hp(t_out), hp(t_kind), hp(t_idx),
+                                            hp(t_coef), fptr, hp(yps), bptr, 1 if observe_data else 0,
+                                            mf.data_ptr(), Pf.data_ptr(), lml.data_ptr(),
+                                            lml_k.data_ptr() if lml_k is not None else None)
+    _lib.check(st, "physs_kf_filter_colloc_f64")
     if want_lml_k:
         return lml, mf, Pf, lml_k
     return lml, mf, Pf

@@ -119,6 +119,62 @@ LTI_SDE_Full_State_Obs_With_Mask = LTI_SDE_Full_State_Obs   # sdes.py:174-190 (k
 _KINDS = {1: Matern12, 2: Matern32, 3: Matern52, 4: Matern72}
 
 
+class PointResidual:
+    """One point-wise collocation residual on the derivative-augmented state x:
+        g(x, t_k) = w . x + sum_q coef_q * phi_q(x[idx_q]) + forcing[k],   phi in {'sin', 'cos', 'square', 'cube'}
+    -- the form of the residuals the reference ships as `PDE.forward_g` (transforms/pdes.py: Pendulum1D :482-528,
+    DampedPendulum1D :530-597, SimpleODE :424-480, the u^3 - u reaction of Allen-Cahn :700-811).  Its Jacobian,
+    which the reference takes with jax.jacfwd (`PDE.jac`, :236-242), is evaluated on chip."""
+
+    def __init__(self, w, terms=(), forcing=None):
+        self.w = np.asarray(w, np.float64)
+        self.terms = [(str(k), int(i), float(c)) for k, i, c in terms]
+        self.forcing = None if forcing is None else np.asarray(forcing, np.float64)
+
+
+class PDE:
+    """Collocation prior: PDE[LTI_SDE[GP]] of the reference (transforms/pdes.py:227-245) -- an LTI_SDE `parent`
+    constrained at every time step by pseudo-observations of point-wise residuals (EKF-style collocation,
+    kalman_filter.py:340-427).  `filter_type='b200'` runs it with `physs_kf_filter_colloc_f64`; the smoother is the
+    parent's (rts_smoother.py:108-150).
+
+    residuals: 1 or 2 PointResidual; psuedo_observations: one value per residual, 0 (collocate) or NaN (off);
+    boundary_conditions: [Nt, m] array with NaN where there is no boundary observation, or None; observe_data as in
+    the reference (PDE.observe_data, default False there; True here only when asked)."""
+
+    def __init__(self, parent, residuals, psuedo_observations=None, boundary_conditions=None, observe_data=False):
+        self.parent = parent
+        self.residuals = list(residuals)
+        if not 1 <= len(self.residuals) <= 2:
+            raise ValueError("1 or 2 collocation residuals per time step")
+        self._pseudo = (np.zeros(len(self.residuals)) if psuedo_observations is None
+                        else np.asarray(psuedo_observations, np.float64).reshape(len(self.residuals)))
+        self.boundary_conditions = boundary_conditions
+        self.observe_data = observe_data
+
+    def psuedo_observations(self, X_s=None):
+        return self._pseudo[:, None]
+
+    # the LTI part is the parent's (pdes.py:233-234 and the filter's `sde_prior = model.parent`)
+    def m_inf(self, x=None, X_s=None, t=None):
+        return self.parent.m_inf(x, X_s, t)
+
+    def P_inf(self, x=None, X_s=None, t=None):
+        return self.parent.P_inf(x, X_s, t)
+
+    def H(self, x=None, X_s=None, t=None):
+        return self.parent.H(x, X_s, t)
+
+    def expm(self, X_s, t):
+        return self.parent.expm(X_s, t)
+
+    def Q(self, dt_k, A_k, P_inf, X_spatial=None):
+        return self.parent.Q(dt_k, A_k, P_inf, X_spatial)
+
+    def ss_blocks(self):
+        return self.parent.ss_blocks() if hasattr(self.parent, "ss_blocks") else None
+
+
 class BatchedMaternSDE:
     """B independent series, each a stack of `nblk` Matern-(s-1/2) blocks of equal size s with its own
     lengthscales/variances [B, nblk]; `sum_blocks=True` observes the SUM of the blocks (SumKernel,
