@@ -466,7 +466,7 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
 }
 
 // ---------------------------------------------------------------------------------------- smoother
-template <int G, int DM, bool GIVEN, int DC = 0, int SC = 0>
+template <int G, int DM, bool GIVEN, int DC = 0, int SC = 0, bool DMMA = false>
 __global__ void rt_smooth_kernel(const SeqSmoothArgs p, const RtLayout L) {
   extern __shared__ __align__(16) double smem[];
   constexpr int LD = Dim<DM>::LD;
@@ -605,9 +605,19 @@ __global__ void rt_smooth_kernel(const SeqSmoothArgs p, const RtLayout L) {
     chol_solve_t<G, DM>(W2, d, rd, W1, d);              // rows: W1[j][:] = (Pp + jit)^-1 (A Pf)[:, j]  = G[j][:]
     __syncwarp();
     mv<G, DM, false>(ms, W1, dm, d, d, mf, 1.0);        // ms = mf + G dm
-    mm_nn<G, DM, false>(W2, W1, Ps, d, d, nullptr, 1.0);   // G dP
-    __syncwarp();
-    mm_nt<G, DM>(Ps, W2, W1, d, d, Pf, 1.0);            // Ps = Pf + (G dP) G^T
+    if constexpr (DMMA && DM == 32 && G == 32 && DC == 32) {
+      // the two dense products of the step on the FP64 tensor cores: 2 x 128 DMMA.8x8x4 instead of 2 x 1024
+      // DFMA per lane; the fragments of G serve both as the left operand of G dP and as G^T on the right
+      double ag[4][8];
+      dmma_load_a32(W1, LD, ag);
+      dmma_mm_nn32(W2, ag, Ps, LD);                      // W2 = G dP
+      __syncwarp();
+      dmma_mm_nt32(Ps, W2, ag, Pf, LD);                  // Ps = Pf + (G dP) G^T
+    } else {
+      mm_nn<G, DM, false>(W2, W1, Ps, d, d, nullptr, 1.0);   // G dP
+      __syncwarp();
+      mm_nt<G, DM>(Ps, W2, W1, d, d, Pf, 1.0);            // Ps = Pf + (G dP) G^T
+    }
     __syncwarp();
     if (chunked && p.fixup && mo == 0) {
       const bool ag = rt_agrees<G, DM>(ms, Ps, d, msp + k * sts * d, Psp + k * sts * d * d, p.delta);
@@ -672,7 +682,14 @@ int rt_run_smooth(cudaStream_t st, const SeqSmoothArgs& a, int d, int mo, int nb
     kern<<<(unsigned)grid, threads, smem, st>>>(a, L);
     return cuda_status(cudaGetLastError(), "rt_smooth_kernel launch");
   };
-  if (!GIVEN && d == DM && L.s == 4) return launch(rt_smooth_kernel<G, DM, GIVEN, GIVEN ? 0 : DM, GIVEN ? 0 : 4>);
+  if (!GIVEN && d == DM && L.s == 4) {
+    if constexpr (DM == 32 && !GIVEN) {
+      // PHYSS_RT_DMMA=0 keeps the DFMA products (A-B timing of the tensor-core experiment)
+      static const bool dmma = [] { const char* e = getenv("PHYSS_RT_DMMA"); return !(e && e[0] == '0'); }();
+      if (dmma) return launch(rt_smooth_kernel<G, DM, GIVEN, DM, 4, true>);
+    }
+    return launch(rt_smooth_kernel<G, DM, GIVEN, GIVEN ? 0 : DM, GIVEN ? 0 : 4>);
+  }
   return launch(rt_smooth_kernel<G, DM, GIVEN>);
 }
 

@@ -398,6 +398,27 @@ def main():
     fn = os.path.join(HERE, "mc_ell.npz")
     onp.savez_compressed(fn, **mcout)
     written.append(fn)
+    # ================================================== data sort / pad: the reference's own numpy
+    # helpers pad_with_nan_to_make_grid and order_sequentially_np (data/sequential.py:9-144), as SequentialData.sort /
+    # unsort compose them (data/data.py:353-415)
+    ns_d = {"onp": onp, "np": jnp, "chex": chex}
+    seq = mg.extract("data/sequential.py", ["pad_with_nan_to_make_grid", "order_sequentially_np"], ns_d)
+    rng = onp.random.default_rng(77)
+    tt_, ss_ = onp.round(onp.sort(rng.uniform(0, 3, 7)), 3), onp.round(rng.uniform(0, 1, (4, 2)), 3)
+    full = onp.array([[a, *b] for a in tt_ for b in ss_])
+    keep = rng.permutation(full.shape[0])[:19]                      # scattered subset, shuffled
+    X = onp.vstack([full[keep], full[keep[:3]]])                    # with three duplicated locations
+    Y = rng.normal(size=(X.shape[0], 2))
+    added, Xp, Yp = seq["pad_with_nan_to_make_grid"](X, Y)
+    uidx, ridx, sidx, Xs, Ys = seq["order_sequentially_np"](A(Xp), A(Yp))
+    Yst = onp.transpose(onp.asarray(Ys), [0, 2, 1])
+    payload = rng.normal(size=(onp.asarray(Xs).shape[0] * onp.asarray(Xs).shape[1], 3))
+    unsorted = payload[onp.asarray(sidx)][onp.asarray(ridx)][:X.shape[0]]
+    fn = os.path.join(HERE, "sort_pad.npz")
+    onp.savez_compressed(fn, X=X, Y=Y, points_added=added, X_padded=onp.asarray(Xp), Y_padded=onp.asarray(Yp),
+                         unique_idx=onp.asarray(uidx), reverse_idx=onp.asarray(ridx), sort_idx=onp.asarray(sidx),
+                         X_sorted=onp.asarray(Xs), Y_st=Yst, payload=payload, unsorted=unsorted)
+    written.append(fn)
     for f in written:
         print("wrote", os.path.relpath(f, HERE), os.path.getsize(f), "bytes")
 

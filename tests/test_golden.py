@@ -249,3 +249,27 @@ def test_oracle_collocation_filter_matches_reference(path):
     assert rel(mf, g["mf"]) < 1e-11 and rel(Pf, g["Pf"]) < 1e-11
     ms, Ps = ofilters.smoother_sequential(prior, g["t"], mf, Pf, full_state=True, jitter=jit)
     assert rel(ms, g["ms"]) < 1e-10 and rel(Ps, g["Ps"]) < 1e-10
+
+
+def _check_sort_pad(device):
+    import torch
+    from physs_gp_b200.data import SequentialData
+    g = np.load(os.path.join(GOLD, "sort_pad.npz"))
+    X = torch.as_tensor(g["X"], device=device)
+    Y = torch.as_tensor(g["Y"], device=device)
+    sd = SequentialData()
+    Xs, Yst = sd.sort(X, Y)
+    assert sd.num_points_added == int(g["points_added"])
+    assert np.array_equal(Xs.cpu().numpy(), g["X_sorted"])
+    assert np.array_equal(np.nan_to_num(Yst.cpu().numpy(), nan=-777.0), np.nan_to_num(g["Y_st"], nan=-777.0))
+    assert np.array_equal(sd.unique_idx.cpu().numpy(), g["unique_idx"])
+    assert np.array_equal(sd.reverse_unique_idx.cpu().numpy(), g["reverse_idx"])
+    out = sd.unsort(torch.as_tensor(g["payload"], device=device))
+    assert np.array_equal(out.cpu().numpy(), g["unsorted"])
+
+
+def test_device_sort_pad_matches_reference_on_cpu_tensors():
+    """physs_gp_b200.data.SequentialData (torch) == the reference's pad_with_nan_to_make_grid +
+    order_sequentially_np + unsort (data/sequential.py:9-144, data/data.py:353-415; fixture from
+    tests/golden/make_golden_cvi.py): scattered, shuffled, duplicated space-time points."""
+    _check_sort_pad("cpu")

@@ -113,3 +113,10 @@ def test_cuda_gauss_newton_curvature_matches_reference_assembly(cuda_device):
     assert rel(dS, H) < 1e-12
     dS2 = cvi.gauss_newton_curvature(dev(g["J"]), np.array([float(g["var_obs"]), float(g["var_col"])]), y=dev(Y))
     assert rel(dS2, H) < 1e-12
+
+
+def test_device_sort_pad_matches_reference_vectors(cuda_device):
+    """the sort / pad pre-step on the GPU (torch.unique = device sort) against the reference's own
+    numpy helpers."""
+    from tests.test_golden import _check_sort_pad
+    _check_sort_pad(cuda_device)

@@ -309,3 +309,45 @@ def test_scalar_update_non_pd_innovation_gives_nan_lml(cuda_device):
     lml, _, _ = ops.kf_filter(tt(np.full(T, 0.1)), Y, tt(Rn), tt(oprior.H()[None]), tt(np.zeros((1, d))),
                               tt(oprior.P_inf()[None]), disc, jitter=1e-5)
     assert torch.isnan(lml).all()
+
+
+def test_int64_indexing_beyond_2_31_elements(cuda_device):
+    """one array with more than 2^31 elements (Pf: 36,864 x 3,700 x 16 = 2.18e9 doubles, 17.5 GB)
+    so that every per-step offset above 2^31 goes through the int64 index paths, time-major and batch-major.
+    Checked against the same series run as a small batch (bit-for-bit: a series' arithmetic does not depend on
+    the batch it sits in) at the last rows of the big arrays, and against the smoother on top."""
+    from physs_gp_b200 import ops
+    dev = cuda_device
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~45 GB of free device memory")
+    B, T, d = 36864, 3700, 4
+    assert B * T * d * d > 2 ** 31
+    rng = np.random.default_rng(3)
+    tt = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=dev)   # noqa: E731
+    from physs_gp_b200 import sdes
+    ls = np.exp(rng.uniform(np.log(0.5), np.log(2.0), (B, 1)))
+    prior = sdes.BatchedMaternSDE(4, ls)
+    lam, Pinf, H = tt(prior.lam()), tt(prior.P_inf()), tt(prior.H())
+    dt = tt(np.hstack([0.0, rng.uniform(0.05, 0.15, T - 1)]))
+    dts = torch.cat([dt[1:], torch.zeros(1, dtype=torch.float64, device=dev)])
+    g = torch.Generator(device=dev).manual_seed(5)
+    R = tt(np.full((1, 1, 1, 1), 0.1))
+    m0 = tt(np.zeros((1, d)))
+    sel = torch.tensor([0, 1, B // 2, B - 33, B - 2, B - 1], device=dev)
+    for time_major in (True, False):
+        Y = torch.randn((T, B, 1) if time_major else (B, T, 1), generator=g, device=dev, dtype=torch.float64)
+        Y = Y.transpose(0, 1) if time_major else Y
+        disc = ops.Disc.matern(1, lam, Pinf)
+        lml, mf, Pf = ops.kf_filter(dt, Y, R, H, m0, Pinf, disc, jitter=1e-5)
+        ms, Ps = ops.rts_smooth(dts, mf, Pf, disc, Hout=None, jitter=1e-5)
+        small = ops.Disc.matern(1, lam[sel], Pinf[sel])
+        Ys = Y[sel].contiguous()
+        lml_s, mf_s, Pf_s = ops.kf_filter(dt, Ys, R, H, m0, Pinf[sel], small, jitter=1e-5)
+        ms_s, Ps_s = ops.rts_smooth(dts, mf_s, Pf_s, small, Hout=None, jitter=1e-5)
+        assert torch.equal(lml[sel], lml_s)
+        assert torch.equal(mf[sel], mf_s) and torch.equal(Pf[sel], Pf_s)
+        assert torch.equal(ms[sel], ms_s) and torch.equal(Ps[sel], Ps_s)
+        assert bool(torch.isfinite(Ps[-1, 0]).all()) and bool(torch.isfinite(Ps[-1, -1]).all())
+        del Y, mf, Pf, ms, Ps
+        torch.cuda.empty_cache()
