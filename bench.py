@@ -612,18 +612,18 @@ def sweep_point(a, dev, world, rank, d, n_local, n_total, lo, cpu):
     dt_s = torch.as_tensor(np.hstack([steps[1:], 0.0]), device=dev)
     R = torch.full((1, 1, 1, 1), NOISE_VAR, dtype=torch.float64, device=dev)
     Y = device_observations(sub, T, dev, seed=2000 + lo)        # the same observations for every sub-batch
-    mf, Pf = ops.empty_steps(sub, T, (d,), dev, True), ops.empty_steps(sub, T, (d, d), dev, True)
-    ms, Ps = ops.empty_steps(sub, T, (d,), dev, True), ops.empty_steps(sub, T, (d, d), dev, True)
-    tail = n_local - starts[-1]
+    # one flat allocation per output, viewed time-major for whatever batch size a sub-batch has (the ragged last
+    # one re-uses the same memory: no second set of buffers)
+    flat = [torch.empty((T * sub * k,), dtype=torch.float64, device=dev) for k in (d, d * d, d, d * d)]
 
-    def views(n):
-        if n == sub:
-            return Y, mf, Pf, ms, Ps
-        # ragged last sub-batch: fresh time-major buffers of the right batch size (views would not be time-major)
-        return (device_observations(n, T, dev, seed=2001 + lo), ops.empty_steps(n, T, (d,), dev, True),
-                ops.empty_steps(n, T, (d, d), dev, True), ops.empty_steps(n, T, (d,), dev, True),
-                ops.empty_steps(n, T, (d, d), dev, True))
-    tail_bufs = views(tail) if tail != sub else None
+    def out_views(n):
+        shp = ((d,), (d, d), (d,), (d, d))
+        return tuple(f[:T * n * int(np.prod(sh))].view((T, n) + sh).transpose(0, 1) for f, sh in zip(flat, shp))
+    mf, Pf, ms, Ps = out_views(sub)
+    tail = n_local - starts[-1]
+    tail_bufs = None
+    if tail != sub:
+        tail_bufs = (device_observations(tail, T, dev, seed=2001 + lo),) + out_views(tail)
 
     def one_pass(record):
         ev, lmls = [], []
@@ -679,7 +679,7 @@ def sweep_point(a, dev, world, rank, d, n_local, n_total, lo, cpu):
                     "peak_tflops_measured": fp64_peak, "frac": flops * per_gpu / 1e12 / fp64_peak}}
     out["roofline"] = {"bound": "hbm" if out["hbm"]["frac"] >= out["fp64"]["frac"] else "fp64",
                        "frac": max(out["hbm"]["frac"], out["fp64"]["frac"])}
-    del Y, mf, Pf, ms, Ps, tail_bufs
+    del Y, mf, Pf, ms, Ps, tail_bufs, flat
     if cpu:
         cores = os.cpu_count() or 1
         n = max(cores * 2, 16)
@@ -866,6 +866,13 @@ def run_c3(a):
                "h2d_bytes_per_step": B * T * m * 8, "d2h_bytes_per_step": B * T * 2 * d * 8 + B * 8,
                "api": "timeshard.filter_smooth (pscan local/fold/finish over the C ABI), pinned host buffers",
                "result": "smoothed mean + marginal variances of the full state [B,T,d] + lml"}
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        Ts = min(T, 100000)
+        r, elc, reps = cpu_c3_rate(d, m, Ts, budget_s=8.0)
+        cpu = {"value": r, "unit": "state-steps/s", "cores": 1, "kind": "port",
+               "sample": "first %d of %d steps x %d repeats = %.1f s on ONE core (a single series' sequential recursion "
+                         "does not thread) -- %s" % (Ts, T, reps, elc, CPU_KIND_NOTE)}
     if rank == 0:
         line = {"metric": "filter+smoother state-steps/sec (fp64)", "value": value, "unit": "state-steps/s",
                 "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
@@ -884,7 +891,7 @@ def run_c3(a):
                                       "flops_per_state_step": flops, "peak_source": "physs_fp64_probe, this run"},
                              "note": "against the SEQUENTIAL algorithmic bytes / flops per state-step "
                                      "(SURVEY 8d): the scan's extra passes are overhead, not credit"},
-                "cpu_baseline": None, "e2e": e2e, "clocks": clocks, "gpu_launches": None}
+                "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": None}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -1077,6 +1084,12 @@ def run_c2(a):
         e2e_step()
     elw = (time.perf_counter() - tw) / a.steps
     value = world * T / (ms * 1e-3)
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        r, elc = cpu_c2_rate(Ns, 8)
+        cpu = {"value": r, "unit": "state-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "8 of %d time steps = %.1f s (numpy oracle oracle/filters.py, LAPACK threading as numpy "
+                         "configures it) -- restatement, not the JAX reference" % (T, elc)}
     if rank == 0:
         line = {"metric": "filter+smoother state-steps/sec (fp64)", "value": value, "unit": "state-steps/s",
                 "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -1091,7 +1104,7 @@ def run_c2(a):
                              "peak_source": "physs_fp64_probe (FP64 FMA pipe), this run", "traffic": None,
                              "note": "dense sequential flop count per state-step (SURVEY 8d); products and "
                                      "factorisations are cuBLAS / cuSOLVER fp64 calls enqueued per step"},
-                "cpu_baseline": None,
+                "cpu_baseline": cpu,
                 "e2e": {"value": world * T / elw, "unit": "state-steps/s", "h2d_bytes_per_step": T * Ns * 8 * world,
                         "d2h_bytes_per_step": 2 * T * Ns * 8 * world,
                         "api": "SDE_GP.filter_and_smooth(full_state=False, return_lml=True), pinned host buffers"},

@@ -243,8 +243,8 @@ __device__ __forceinline__ void mm_nt_blk(double* __restrict__ C, const double* 
   }
 }
 
-// ---- FP64 tensor-core products (DMMA.8x8x4, PTX mma.sync.aligned.m8n8k4.f64) for the full-size DM = 32 tiles.
-// One warp = one series.  Fragment layout (g = lane >> 2, t = lane & 3):
+// ---- FP64 tensor-core products (DMMA.8x8x4, PTX mma.sync.aligned.m8n8k4.f64) for full-size DM x DM tiles.
+// Fragment layout (g = lane >> 2, t = lane & 3):
 //   A (8 x 4, row)  a      = A[g][t]            B (4 x 8, col)  b = B[t][g]
 //   C (8 x 8)       c0, c1 = C[g][2t], C[g][2t + 1]
 // Measured on this GPU (tools/microbench/fp64_pipes.cu, profiles/fp64_pipes_r02.jsonl): DMMA.8x8x4 issues every
@@ -257,70 +257,79 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// a[mt][kt] = M[8 mt + g][4 kt + t]: the A fragments of a 32 x 32 row-major slab M -- also the B fragments of M^T
-__device__ __forceinline__ void dmma_load_a32(const double* __restrict__ M, int LD, double (&a)[4][8]) {
+// a[mt][kt] = M[8 mt + g][4 kt + t]: the A fragments of a DM x DM row-major slab M -- also the B fragments of M^T.
+// All 32 lanes of the warp work on ONE slab (for DM < 32 the caller loops over the 32 / DM series of the warp).
+template <int DM>
+__device__ __forceinline__ void dmma_load_a(const double* __restrict__ M, double (&a)[DM / 8][DM / 4]) {
+  constexpr int LD = Dim<DM>::LD;
   const int g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) {
+  for (int mt = 0; mt < DM / 8; ++mt) {
 #pragma unroll
-    for (int kt = 0; kt < 8; ++kt) a[mt][kt] = M[(8 * mt + g) * LD + 4 * kt + t];
+    for (int kt = 0; kt < DM / 4; ++kt) a[mt][kt] = M[(8 * mt + g) * LD + 4 * kt + t];
   }
 }
 
-// C = Am . B   (32 x 32 each), Am given as A fragments in registers, B and C row-major slabs (C must not alias B)
-__device__ __forceinline__ void dmma_mm_nn32(double* __restrict__ C, const double (&a)[4][8],
-                                             const double* __restrict__ B, int LD) {
+// C = Am . B   (DM x DM each), Am given as A fragments in registers, B and C row-major slabs (C must not alias B)
+template <int DM>
+__device__ __forceinline__ void dmma_mm_nn(double* __restrict__ C, const double (&a)[DM / 8][DM / 4],
+                                           const double* __restrict__ B) {
+  constexpr int LD = Dim<DM>::LD;
+  constexpr int MT = DM / 8, KT = DM / 4;
   const int g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
-  double acc[4][4][2];
+  double acc[MT][MT][2];
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    for (int nt = 0; nt < MT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 #pragma unroll
-  for (int kt = 0; kt < 8; ++kt) {
-    double b[4];
+  for (int kt = 0; kt < KT; ++kt) {
+    double b[MT];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) b[nt] = B[(4 * kt + t) * LD + 8 * nt + g];
+    for (int nt = 0; nt < MT; ++nt) b[nt] = B[(4 * kt + t) * LD + 8 * nt + g];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt][kt], b[nt]);
+      for (int nt = 0; nt < MT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt][kt], b[nt]);
   }
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < MT; ++nt)
       *reinterpret_cast<double2*>(C + (8 * mt + g) * LD + 8 * nt + 2 * t) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
 }
 
-// C = Add + W . Gm^T   (32 x 32 each): W, Add, C row-major slabs, Gm^T given by the A fragments of Gm
-// (B[k][n] = Gm[n][k] is exactly a[nt][kt]).  C may alias neither W nor Add... C may alias Add (own elements only).
-__device__ __forceinline__ void dmma_mm_nt32(double* C, const double* __restrict__ W, const double (&ag)[4][8],
-                                             const double* Add, int LD) {
+// C = Add + W . Gm^T   (DM x DM each): W, Add, C row-major slabs, Gm^T given by the A fragments of Gm
+// (B[k][n] = Gm[n][k] is exactly a[nt][kt]).  C must not alias W; it may alias Add (own elements only).
+template <int DM>
+__device__ __forceinline__ void dmma_mm_nt(double* C, const double* __restrict__ W, const double (&ag)[DM / 8][DM / 4],
+                                           const double* Add) {
+  constexpr int LD = Dim<DM>::LD;
+  constexpr int MT = DM / 8, KT = DM / 4;
   const int g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
-  double acc[4][4][2];
+  double acc[MT][MT][2];
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+    for (int nt = 0; nt < MT; ++nt) {
       const double2 v = *reinterpret_cast<const double2*>(Add + (8 * mt + g) * LD + 8 * nt + 2 * t);
       acc[mt][nt][0] = v.x;
       acc[mt][nt][1] = v.y;
     }
 #pragma unroll
-  for (int kt = 0; kt < 8; ++kt) {
-    double aw[4];
+  for (int kt = 0; kt < KT; ++kt) {
+    double aw[MT];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) aw[mt] = W[(8 * mt + g) * LD + 4 * kt + t];
+    for (int mt = 0; mt < MT; ++mt) aw[mt] = W[(8 * mt + g) * LD + 4 * kt + t];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], aw[mt], ag[nt][kt]);
+      for (int nt = 0; nt < MT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], aw[mt], ag[nt][kt]);
   }
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < MT; ++nt)
       *reinterpret_cast<double2*>(C + (8 * mt + g) * LD + 8 * nt + 2 * t) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
 }
 

@@ -13,6 +13,10 @@ namespace physs {
 
 using namespace rt;
 
+#ifndef PHYSS_RT_DMMA_DEFAULT
+#define PHYSS_RT_DMMA_DEFAULT 56
+#endif
+
 struct RtLayout {
   int d, m, mo, nblk, s;
   int P, Ac, Pc, Qc, W1, W2, K, S, Sj, H, Ho, Rst[2], AQst[2][2], PfS;
@@ -605,14 +609,26 @@ __global__ void rt_smooth_kernel(const SeqSmoothArgs p, const RtLayout L) {
     chol_solve_t<G, DM>(W2, d, rd, W1, d);              // rows: W1[j][:] = (Pp + jit)^-1 (A Pf)[:, j]  = G[j][:]
     __syncwarp();
     mv<G, DM, false>(ms, W1, dm, d, d, mf, 1.0);        // ms = mf + G dm
-    if constexpr (DMMA && DM == 32 && G == 32 && DC == 32) {
-      // the two dense products of the step on the FP64 tensor cores: 2 x 128 DMMA.8x8x4 instead of 2 x 1024
-      // DFMA per lane; the fragments of G serve both as the left operand of G dP and as G^T on the right
-      double ag[4][8];
-      dmma_load_a32(W1, LD, ag);
-      dmma_mm_nn32(W2, ag, Ps, LD);                      // W2 = G dP
+    if constexpr (DMMA && DC == DM && (DM == 8 || DM == 16 || DM == 32)) {
+      // the two dense products of the step on the FP64 tensor cores (DMMA.8x8x4): per series 2 (DM/8)^2 (DM/4)
+      // instructions instead of 2 DM^2 DFMA per lane; the fragments of G serve both as the left operand of
+      // G dP and as G^T on the right.  All 32 lanes work on one series at a time: the warp walks its 32 / DM
+      // series (their slabs are consecutive in shared memory).
+      constexpr int NG = 32 / G;
+      double* slab0 = smem + (size_t)(g_in_block - (g_in_block % NG)) * L.total;
+      double ag[NG][DM / 8][DM / 4];
+#pragma unroll
+      for (int sgi = 0; sgi < NG; ++sgi) {
+        double* sb = slab0 + (size_t)sgi * L.total;
+        dmma_load_a<DM>(sb + L.W1, ag[sgi]);
+        dmma_mm_nn<DM>(sb + L.W2, ag[sgi], sb + L.P);            // W2 = G dP
+      }
       __syncwarp();
-      dmma_mm_nt32(Ps, W2, ag, Pf, LD);                  // Ps = Pf + (G dP) G^T
+#pragma unroll
+      for (int sgi = 0; sgi < NG; ++sgi) {
+        double* sb = slab0 + (size_t)sgi * L.total;
+        dmma_mm_nt<DM>(sb + L.P, sb + L.W2, ag[sgi], sb + L.PfS);   // Ps = Pf + (G dP) G^T
+      }
     } else {
       mm_nn<G, DM, false>(W2, W1, Ps, d, d, nullptr, 1.0);   // G dP
       __syncwarp();
@@ -683,10 +699,11 @@ int rt_run_smooth(cudaStream_t st, const SeqSmoothArgs& a, int d, int mo, int nb
     return cuda_status(cudaGetLastError(), "rt_smooth_kernel launch");
   };
   if (!GIVEN && d == DM && L.s == 4) {
-    if constexpr (DM == 32 && !GIVEN) {
-      // PHYSS_RT_DMMA=0 keeps the DFMA products (A-B timing of the tensor-core experiment)
-      static const bool dmma = [] { const char* e = getenv("PHYSS_RT_DMMA"); return !(e && e[0] == '0'); }();
-      if (dmma) return launch(rt_smooth_kernel<G, DM, GIVEN, DM, 4, true>);
+    if constexpr (!GIVEN) {
+      // PHYSS_RT_DMMA: bit mask of the padded dims whose dense products run on the FP64 tensor cores
+      // (8 | 16 | 32; default: those the A-B timing of DESIGN.md section 3 found faster)
+      static const int dmma = [] { const char* e = getenv("PHYSS_RT_DMMA"); return e ? atoi(e) : PHYSS_RT_DMMA_DEFAULT; }();
+      if (dmma & DM) return launch(rt_smooth_kernel<G, DM, GIVEN, DM, 4, true>);
     }
     return launch(rt_smooth_kernel<G, DM, GIVEN, GIVEN ? 0 : DM, GIVEN ? 0 : 4>);
   }

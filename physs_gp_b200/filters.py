@@ -53,10 +53,20 @@ def lower_prior(prior, X_s, dts, dev):
     different dt conventions), m0 [*, d], P0 [*, d, d] device tensors and H as a numpy [m, d] array.
     """
     if isinstance(prior, BatchedMaternSDE):
-        lam = _to_dev(prior.lam(), dev)
-        Pinf = _to_dev(prior.P_inf(), dev)
+        # the prior's device tensors are cached on the prior object (keyed by a fingerprint of its
+        # hyper-parameters): a CVI iteration calls the filter + smoother four times with the same prior, and
+        # re-staging lam / P_inf through pinned memory on every call was a measurable part of its step time
+        key = (str(dev), hash(prior.ls.tobytes()), hash(prior.var.tobytes()))
+        cache = getattr(prior, "_b200_cache", None)
+        cur = torch.cuda.current_stream(dev)
+        if cache is None or cache[0] != key:
+            cache = (key, _to_dev(prior.lam(), dev), _to_dev(prior.P_inf(), dev), _to_dev(prior.m_inf(), dev), cur)
+            prior._b200_cache = cache
+        elif cache[4] != cur:
+            cur.wait_stream(cache[4])                  # the staging copies were enqueued on another stream
+        _, lam, Pinf, m0, _ = cache
         disc = ops.Disc.matern(prior.nblk, lam, Pinf)
-        return [disc for _ in dts], _to_dev(prior.m_inf(), dev), Pinf, prior.H()
+        return [disc for _ in dts], m0, Pinf, prior.H()
     P_inf = np.asarray(prior.P_inf(None, X_s, None), np.float64)
     m_inf = np.asarray(prior.m_inf(None, X_s, None), np.float64).reshape(1, -1)
     H = np.asarray(prior.H(None, X_s, None), np.float64)
