@@ -378,6 +378,27 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads to the CPU cores NVML reports as local to its GPU, BEFORE any pinned host
+    buffer is allocated: under torchrun the ranks float over both sockets, and a pinned staging buffer that
+    lands on the far socket sends every host<->device byte of the e2e path across the inter-socket link.
+    Returns a short description for the JSON line (None when NVML / affinity is unavailable)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "rank threads bound to the %d cores local to GPU %d" % (len(allowed), local)
+    except Exception:
+        pass
+    return None
+
+
 def series_split(a, world):
     """(series per GPU, series in total) under --scaling weak (default: --series per GPU) / strong (--series total)."""
     if a.scaling == "strong":
@@ -421,6 +442,7 @@ def run_b200(a):
         raise RuntimeError("bench.py (b200 arm) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -538,7 +560,7 @@ def run_b200(a):
     del out_full, out_tail
     torch.cuda.empty_cache()
     if not a.no_e2e:
-        e2e = run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys)
+        e2e = run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys, numa)
 
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
@@ -690,7 +712,7 @@ def sweep_point(a, dev, world, rank, d, n_local, n_total, lo, cpu):
     return out
 
 
-def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys_dev):
+def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys_dev, numa=None):
     """Same job through the reference-shaped API (SDE_GP.filter_and_smooth) with HOST buffers.
 
     Every sub-batch is one user-level call sequence on its own CUDA stream (eight streams round-robin):
@@ -752,7 +774,7 @@ def run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys_dev):
     k2, el2 = timed(False)
     per_rank_in = n_local * T * 8 + 2 * T * 8
     per_rank_out = n_local * T * 16 + n_local * 8
-    return {"value": n_local * world * T * k / el, "unit": "state-steps/s", "steps": k,
+    return {"value": n_local * world * T * k / el, "unit": "state-steps/s", "steps": k, "host_affinity": numa,
             "h2d_bytes_per_step": per_rank_in * world, "d2h_bytes_per_step": per_rank_out * world,
             "sub_batch": esub, "streams": len(streams),
             "api": "SDE_GP.filter_and_smooth(full_state=False, return_lml=True) per sub-batch, pinned host "

@@ -414,6 +414,13 @@ int physs_cvi_ell_pendulum_f64(void* stream, int64_t N, int32_t D, int32_t i0, i
 int physs_cvi_gauss_newton_f64(void* stream, int64_t N, int32_t D, int32_t P, const double* J, const double* var,
                                int64_t var_stride, const double* y, double* dS_out);
 
+/* Batched inverse of N small SPD matrices, out[n] = (A[n] + jitter I)^-1 by Cholesky (D <= 8; non-PD -> NaN).
+ * Turns precision-parameterised sites R_inv [., T, m, m] into the covariance form the filter entry points take:
+ * the reference's sequential filter has no precision path (kf_update_step_with_lik_precision,
+ * kalman_filter.py:43-126, raises), its parallel filter factors R_inv the same way
+ * (parallel_kalman_filter.py:34-71,117-141). */
+int physs_spd_inverse_f64(void* stream, int64_t N, int32_t D, const double* A, double jitter, double* out);
+
 /* FP64 FMA throughput probe (measurement aid for the FP64-pipe roofline; no reference counterpart).
  * Launches blocks x 256 threads doing iters x 8 independent FMAs each: flops = blocks*256*iters*16. */
 int physs_fp64_probe(void* stream, int32_t blocks, int64_t iters, double* out);

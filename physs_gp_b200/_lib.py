@@ -70,6 +70,7 @@ SIGNATURES = {
                                                   _c_f64, _c_f64, _c_f64, _c_f64, _c_i32, _ptr, _ptr, _ptr]),
     "physs_cvi_gauss_newton_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _c_i32, _ptr, _ptr, _c_i64, _ptr, _ptr]),
     "physs_fp64_probe": (ctypes.c_int, [_ptr, _c_i32, _c_i64, _ptr]),
+    "physs_spd_inverse_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _ptr, _c_f64, _ptr]),
     "physs_cvi_natgrad_step_f64": (ctypes.c_int, [
         _ptr, _c_i64, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64,
         _c_f64, _c_i32, _ptr, _ptr, _ptr, _ptr, _c_f64, _c_f64, _ptr, _ptr, _ptr]),

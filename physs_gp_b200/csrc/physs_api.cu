@@ -218,6 +218,12 @@ int physs_kf_filter_colloc_f64(FILTER_PARAMS, int32_t pc, const double* res_w, i
                        term_kind, term_idx, term_coef, forcing, y_pseudo, boundary, observe_data);
 }
 
+int physs_spd_inverse_f64(void* stream, int64_t N, int32_t D, const double* A, double jitter, double* out) {
+  if (N < 0 || D < 1) return set_error(PHYSS_ERR_BAD_ARG, "spd inverse: bad sizes");
+  if (N > 0 && (!A || !out)) return set_error(PHYSS_ERR_BAD_ARG, "spd inverse: null pointer");
+  return spd_inverse((cudaStream_t)stream, N, D, A, jitter, out);
+}
+
 int physs_kf_vjp_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {
   return vjp_supported(d, m, disc_mode, nblk) ? 1 : 0;
 }

@@ -139,6 +139,9 @@ int colloc_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h
                   const int32_t* t_idx, const double* t_coef, const double* forcing, const double* y_pseudo,
                   const double* boundary, int observe_data);
 
+// physs_spd.cu: batched inverse of small SPD matrices (precision sites -> covariance sites)
+int spd_inverse(cudaStream_t st, int64_t N, int D, const double* A, double jitter, double* out);
+
 // physs_pscan.cu: parallel-in-time chunked associative scan
 int64_t pscan_workspace_doubles(int64_t B, int64_t T, int d, int64_t chunk_len);
 int pscan_filter_local(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, SeqFilterArgs a,

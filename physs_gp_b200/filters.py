@@ -124,10 +124,16 @@ def _filter_impl(parallel, data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, 
     Y [T, m, 1] (or [B, T, m, 1]), lik_mat R [T, m, m] (or [B, T, m, m] / broadcastable),
     dt [T] with dt[0] = 0.  Returns (lml, {'m': [T, d, 1], 'P': [T, d, d]}) with a leading B when
     the inputs were batched."""
-    if not lik_cov_flag:
-        # the reference's sequential path raises for precision sites too (kalman_filter.py:67)
-        raise NotImplementedError("sequential filter with a precision likelihood is not supported")
     dev = _device()
+    if not lik_cov_flag:
+        # precision-parameterised sites (R_inv): the reference's sequential path raises (kalman_filter.py:67) and
+        # only its parallel filter takes them (parallel_kalman_filter.py:34-71,117-141).  Here they are turned into
+        # covariances on the device (Cholesky factor-and-solve, as the reference's precision elements do) and the
+        # ordinary recursion runs.
+        Rinv = _to_dev(lik_mat, dev)
+        if Rinv.shape[-1] > 8:
+            raise NotImplementedError("precision sites: observation blocks up to 8 x 8")
+        lik_mat, lik_cov_flag = ops.spd_inverse(Rinv, 0.0), True
     Yd = _to_dev(Y, dev)
     one = Yd.dim() == 3 or (Yd.dim() == 4 and Yd.shape[0] == 1)
     if one and _use_big(prior, X_s, 1):

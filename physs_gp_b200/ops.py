@@ -118,6 +118,19 @@ def kf_wave_series(d, m=1, nblk=0):
     return w
 
 
+def spd_inverse(A, jitter=0.0, stream=None):
+    """(A + jitter I)^-1 for a batch of small SPD matrices [..., D, D] (D <= 8) -- precision sites R_inv ->
+    covariance sites R (`physs_spd_inverse_f64`)."""
+    A = _dev(A, "A").contiguous()
+    D = A.shape[-1]
+    out = torch.empty_like(A)
+    N = A.numel() // (D * D)
+    with torch.cuda.device(A.device):
+        st = _lib.load().physs_spd_inverse_f64(_stream_ptr(stream), N, D, A.data_ptr(), float(jitter), out.data_ptr())
+    _lib.check(st, "physs_spd_inverse_f64")
+    return out
+
+
 def kf_supported(d, m, disc):
     return bool(_lib.load().physs_kf_supported(d, m, disc.mode, disc.nblk))
 
@@ -517,7 +530,7 @@ def pscan_filter_fold(totals, m0, P0, stream=None):
     return mo, Po
 
 
-def pscan_filter_finish(dt, Y, R, H, m0, P0, disc, chunk_len, ws, start=None, jitter=None, polish=None, delta=1e-13,
+def pscan_filter_finish(dt, Y, R, H, m0, P0, disc, chunk_len, ws, start=None, jitter=None, polish=None, delta=1e-10,
                         patience=4, want_lml_k=False, out=None, stream=None):
     lib = _lib.load()
     p = _pack_filter(dt, Y, R, H, m0, P0, disc, jitter, stream)

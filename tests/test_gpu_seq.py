@@ -351,3 +351,23 @@ def test_int64_indexing_beyond_2_31_elements(cuda_device):
         assert bool(torch.isfinite(Ps[-1, 0]).all()) and bool(torch.isfinite(Ps[-1, -1]).all())
         del Y, mf, Pf, ms, Ps
         torch.cuda.empty_cache()
+
+
+def test_precision_sites_match_covariance_sites(cuda_device):
+    """R_inv (precision-parameterised sites) on the sequential b200 path == the same filter fed
+    R = inv(R_inv); the reference's own sequential path raises for R_inv (kalman_filter.py:67)."""
+    from physs_gp_b200 import data, filters
+    rng = np.random.default_rng(12)
+    pprior, oprior = _priors([[("m32", 1.0, 1.3)], [("m32", 0.4, 0.5)]], False)
+    T, m = 60, 2
+    t = synth.time_grid(T, 0.1, rng)
+    Y = synth.noisy_series(1, T, m, rng, 0.1)[0]
+    R = synth.random_spd(rng, (T,), m)
+    Rinv = np.linalg.inv(R)
+    d = data.TemporalData(t, Y[:, :, None])
+    lml_a, kf_a = filters.filter_loop(d, pprior, R=R)
+    lml_b, kf_b = filters.filter_loop(d, pprior, R_inv=Rinv)
+    assert abs(float(lml_a) - float(lml_b)) <= 1e-10 * abs(float(lml_a))
+    assert rel(kf_b['m'], kf_a['m'].cpu().numpy()) < 1e-10 and rel(kf_b['P'], kf_a['P'].cpu().numpy()) < 1e-10
+    lml_o, mf_o, Pf_o, _ = ofilters.filter_sequential(oprior, t, Y, R, 1e-5)
+    assert rel(kf_b['m'], mf_o) < TOL and rel(kf_b['P'], Pf_o) < TOL
