@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libphyss_b200.so")
 PHYSS_OK = 0
 DISC_GIVEN = 0
 DISC_MATERN = 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _c_i32 = ctypes.c_int32
 _c_i64 = ctypes.c_int64
@@ -44,6 +44,8 @@ SIGNATURES = {
         _ptr, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32,
         _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
         _ptr, _ptr, _ptr, _c_i32, _c_f64, _ptr, _ptr]),
+    "physs_rts_smooth_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32]),
+    "physs_rts_smooth_ws_f64": (ctypes.c_int, _SMOOTH_HEAD + [_ptr, _c_i64, _ptr, _ptr]),
     "physs_kf_filter_smooth_f64": (ctypes.c_int, _FILTER_HEAD + [_ptr, _ptr, _ptr, _c_i64, _ptr, _c_i32,
                                                                 _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "physs_kf_filter_colloc_f64": (ctypes.c_int, _FILTER_HEAD + [_c_i32, _ptr, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
