@@ -122,29 +122,6 @@ int physs_rts_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_bstrid
                          double jitter,
                          double* ms, double* Ps);
 
-/* The same smoother with a caller-provided scratch workspace (XLA: a scratch buffer of the custom call).  For
- * full-size stacks of Matern-7/2 blocks (DISC_MATERN, d = 4 nblk in {8, 16, 32}) with full-state output it runs as
- * TWO kernels per time chunk: the gains G_k, P_pred,k, m_pred,k of all steps of the chunk in a parallel pre-pass
- * (no dependence between steps), then the recursion ms_k = mf_k + G_k (ms_{k+1} - m_pred), Ps_k = Pf_k +
- * G_k (Ps_{k+1} - P_pred) G_k^T as two FP64 tensor-core products per step.  Same results (rts_smoother.py:48-106)
- * up to the accumulation order of those products.  Any other shape, or ws == NULL, runs physs_rts_smooth_f64.
- * physs_rts_smooth_workspace_bytes: recommended size (0 = this shape does not use a workspace); any size that holds
- * the carried state plus >= 8 time steps of scratch, B (d^2 + d) + 8 B (2 d^2 + d) doubles, is accepted. */
-int64_t physs_rts_smooth_workspace_bytes(int64_t B, int64_t T, int32_t d, int32_t disc_mode, int32_t nblk, int32_t mo);
-int physs_rts_smooth_ws_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
-                            int32_t d,
-                            int32_t disc_mode, int32_t nblk,
-                            const double* A, int64_t A_bstride,
-                            const double* Q, int64_t Q_bstride,
-                            const double* lam, int64_t lam_bstride,
-                            const double* dt, int64_t dt_bstride,
-                            const double* Pinf, int64_t Pinf_bstride,
-                            const double* mf, const double* Pf,
-                            const double* Hout, int32_t mo,
-                            double jitter,
-                            void* ws, int64_t ws_bytes,
-                            double* ms, double* Ps);
-
 /* Filter + smoother in one call (`physs_kf_filter_smooth_f64`): physs_kf_filter_f64
  * followed by physs_rts_smooth_f64 on the same stream with the filter's outputs -- what
  * `BASE_SDE_GP.filter_and_smooth` (models/sde_gp.py:212-302) does with two dispatched calls; one FFI custom call

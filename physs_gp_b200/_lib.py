@@ -44,8 +44,6 @@ SIGNATURES = {
         _ptr, _c_i64, _c_i64, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32,
         _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64, _ptr, _c_i64,
         _ptr, _ptr, _ptr, _c_i32, _c_f64, _ptr, _ptr]),
-    "physs_rts_smooth_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i32, _c_i32, _c_i32, _c_i32]),
-    "physs_rts_smooth_ws_f64": (ctypes.c_int, _SMOOTH_HEAD + [_ptr, _c_i64, _ptr, _ptr]),
     "physs_kf_filter_smooth_f64": (ctypes.c_int, _FILTER_HEAD + [_ptr, _ptr, _ptr, _c_i64, _ptr, _c_i32,
                                                                 _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "physs_kf_filter_colloc_f64": (ctypes.c_int, _FILTER_HEAD + [_c_i32, _ptr, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,

@@ -252,25 +252,6 @@ int physs_rts_smooth_f64(SMOOTH_PARAMS, double* ms, double* Ps) {
   return run_smooth_any((cudaStream_t)stream, d, Hout ? mo : 0, disc_mode, nblk, a);
 }
 
-int64_t physs_rts_smooth_workspace_bytes(int64_t B, int64_t T, int32_t d, int32_t disc_mode, int32_t nblk, int32_t mo) {
-  if (B < 1 || T < 2 || !rt2_supported(d, mo, disc_mode, nblk)) return 0;
-  const int64_t steps = (T - 1 < 256) ? T - 1 : 256;          // scratch ring: one chunk of up to 256 time steps
-  return 8 * rt2_ws_doubles(d, B, steps);
-}
-
-int physs_rts_smooth_ws_f64(SMOOTH_PARAMS, void* ws, int64_t ws_bytes, double* ms, double* Ps) {
-  SeqSmoothArgs a;
-  int rc = pack_smooth(SMOOTH_ARGS, ms, Ps, a);
-  if (rc || B == 0) return rc;
-  if (!ms || !Ps) return set_error(PHYSS_ERR_BAD_ARG, "smoother: null output pointer");
-  const int mo_eff = Hout ? mo : 0;
-  if (ws && ws_bytes > 0 && T > 1 && rt2_supported(d, mo_eff, disc_mode, nblk)) {
-    if (misaligned(ws)) return set_error(PHYSS_ERR_BAD_ARG, "smoother: workspace must be 16-byte aligned");
-    return rt2_smooth((cudaStream_t)stream, d, a, (double*)ws, ws_bytes / 8);
-  }
-  return run_smooth_any((cudaStream_t)stream, d, mo_eff, disc_mode, nblk, a);
-}
-
 int64_t physs_pscan_workspace_bytes(int64_t B, int64_t T, int32_t d, int64_t chunk_len) {
   if (B < 1 || T < 1 || d < 1 || chunk_len < 1) return 0;
   return 8 * pscan_workspace_doubles(B, T, d, chunk_len);

@@ -129,10 +129,6 @@ bool vjp_supported(int d, int m, int disc_mode, int nblk);
 int kf_vjp(cudaStream_t st, int d, int m, int disc_mode, int nblk, const SeqFilterArgs& a, const VjpOut& o);
 int rt_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity, const SeqFilterArgs& a);
 int rt_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
-// two-kernel smoother (physs_rt2_impl.cuh): gains of a time chunk in a parallel pre-pass + DMMA recursion
-bool rt2_supported(int d, int mo, int disc_mode, int nblk);
-int64_t rt2_ws_doubles(int d, int64_t B, int64_t steps);
-int rt2_smooth(cudaStream_t st, int d, const SeqSmoothArgs& a, double* ws, int64_t ws_doubles);
 int rt_filter_summary(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, const SeqFilterArgs& a,
                       int64_t cfirst, int64_t ccount, double* elems);
 int rt_smooth_summary(cudaStream_t st, int d, int disc_mode, int nblk, const SeqSmoothArgs& a, double* elems);

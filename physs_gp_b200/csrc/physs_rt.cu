@@ -28,33 +28,6 @@ int rt_smooth_summary_dm(cudaStream_t st, bool given, const SeqSmoothArgs& a, in
 DECL(8) DECL(16) DECL(32)
 #undef DECL
 
-// two-kernel smoother (physs_rt2_impl.cuh; instantiated in physs_rt2_d*.cu)
-template <int DM>
-int rt2_smooth_dm(cudaStream_t st, const SeqSmoothArgs& p, double* ws, int64_t ws_doubles);
-template <int DM>
-int64_t rt2_workspace_doubles(int64_t B, int64_t steps);
-extern template int rt2_smooth_dm<8>(cudaStream_t, const SeqSmoothArgs&, double*, int64_t);
-extern template int rt2_smooth_dm<16>(cudaStream_t, const SeqSmoothArgs&, double*, int64_t);
-extern template int rt2_smooth_dm<32>(cudaStream_t, const SeqSmoothArgs&, double*, int64_t);
-extern template int64_t rt2_workspace_doubles<8>(int64_t, int64_t);
-extern template int64_t rt2_workspace_doubles<16>(int64_t, int64_t);
-extern template int64_t rt2_workspace_doubles<32>(int64_t, int64_t);
-
-// full-size stacks of Matern-7/2 blocks, full-state output, plain (not chunked) mode
-bool rt2_supported(int d, int mo, int disc_mode, int nblk) {
-  return disc_mode == PHYSS_DISC_MATERN && (d == 8 || d == 16 || d == 32) && nblk * 4 == d && mo == 0;
-}
-int64_t rt2_ws_doubles(int d, int64_t B, int64_t steps) {
-  if (d == 8) return rt2_workspace_doubles<8>(B, steps);
-  if (d == 16) return rt2_workspace_doubles<16>(B, steps);
-  return rt2_workspace_doubles<32>(B, steps);
-}
-int rt2_smooth(cudaStream_t st, int d, const SeqSmoothArgs& a, double* ws, int64_t ws_doubles) {
-  if (d == 8) return rt2_smooth_dm<8>(st, a, ws, ws_doubles);
-  if (d == 16) return rt2_smooth_dm<16>(st, a, ws, ws_doubles);
-  return rt2_smooth_dm<32>(st, a, ws, ws_doubles);
-}
-
 // ---------------------------------------------------------------------------------------- dispatch
 bool rt_supported(int d, int m) { return d >= 1 && d <= 32 && m >= 1 && m <= d; }
 

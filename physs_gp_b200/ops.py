@@ -376,45 +376,20 @@ def _smooth_outputs(p, out):
     return ms, Ps
 
 
-def rts_smooth(dt, mf, Pf, disc, Hout=None, jitter=None, out=None, stream=None, ws=None):
+def rts_smooth(dt, mf, Pf, disc, Hout=None, jitter=None, out=None, stream=None):
     """Batched sequential RTS smoother (rts_smoother.py:162-192 semantics per series).
 
     dt -> [B, T] (dt[k] = t_{k+1} - t_k, dt[T-1] = 0);  mf [B, T, d], Pf [B, T, d, d];
     Hout [mo, d] projects the output (None = full_state=True).
     Returns (ms [B, T, mo'], Ps [B, T, mo', mo']).
-    `ws`: optional scratch tensor (float64, 1-D) for the two-kernel path (`physs_rts_smooth_ws_f64`); by default one
-    is allocated and cached when `settings.two_kernel_smoother` is on and the shape uses it.
     """
     lib = _lib.load()
     p = _pack_smooth(dt, mf, Pf, disc, Hout, jitter, stream)
     ms, Ps = _smooth_outputs(p, out)
-    if ws is None and settings.two_kernel_smoother:
-        ws = _smooth_workspace(lib, p, disc)
     with torch.cuda.device(p.dev):
-        if ws is not None:
-            st = lib.physs_rts_smooth_ws_f64(*p.head, ws.data_ptr(), ws.numel() * 8, ms.data_ptr(), Ps.data_ptr())
-        else:
-            st = lib.physs_rts_smooth_f64(*p.head, ms.data_ptr(), Ps.data_ptr())
+        st = lib.physs_rts_smooth_f64(*p.head, ms.data_ptr(), Ps.data_ptr())
     _lib.check(st, "physs_rts_smooth_f64")
     return ms, Ps
-
-
-_SMOOTH_WS = {}
-
-
-def _smooth_workspace(lib, p, disc):
-    """Scratch for the two-kernel smoother (`physs_rts_smooth_ws_f64`), cached per (device, stream) and grown on
-    demand -- the analogue of the scratch buffer XLA hands a custom call.  None when the shape does not use one."""
-    mo = 0 if p.head[-3] is None else p.head[-2]
-    n = int(lib.physs_rts_smooth_workspace_bytes(p.B, p.T, p.d, disc.mode, disc.nblk, mo))
-    if n <= 0 or p.B < settings.two_kernel_smoother_min_batch:
-        return None
-    key = (str(p.dev), p.head[0])
-    ws = _SMOOTH_WS.get(key)
-    if ws is None or ws.numel() * 8 < n:
-        ws = torch.empty((n // 8,), dtype=torch.float64, device=p.dev)
-        _SMOOTH_WS[key] = ws
-    return ws
 
 
 # ------------------------------------------------------------------------------- parallel-in-time

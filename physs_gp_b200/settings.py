@@ -31,8 +31,3 @@ big_block_min_dim = 32
 # when a chunk did not converge; set False to keep the call fully asynchronous
 pscan_check_status = True
 
-# Two-kernel RTS smoother for full-size Matern-7/2 stacks (d = 8 / 16 / 32, full-state output): gains of a time chunk
-# in a parallel pre-pass, then a DMMA recursion (csrc/physs_rt2_impl.cuh).  Off = the one-kernel lane-group smoother.
-import os as _os
-two_kernel_smoother = _os.environ.get("PHYSS_TWO_KERNEL", "1") != "0"
-two_kernel_smoother_min_batch = 64

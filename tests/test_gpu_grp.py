@@ -129,55 +129,3 @@ def test_group_all_missing_and_single_step(cuda_device):
             assert rel(lml, ref["lml"]) < TOL
         assert rel(kf["P"], ref["Pf"]) < TOL and rel(var, ref["Ps"]) < TOL and rel(mu[..., 0], ref["ms"]) < TOL
 
-
-@pytest.mark.parametrize("nblk", [2, 4, 8])
-@pytest.mark.parametrize("time_major", [True, False])
-def test_two_kernel_smoother_matches_one_kernel_and_oracle(cuda_device, nblk, time_major):
-    """physs_rts_smooth_ws_f64 (gain pre-pass + DMMA recursion, csrc/physs_rt2_impl.cuh) against the one-kernel
-    lane-group smoother (1e-11: same arithmetic up to the accumulation order of the tensor-core products) and the
-    C oracle (1e-9), on a ragged batch whose time axis spans several scratch chunks (workspace sized for 40 steps),
-    both memory layouts."""
-    from physs_gp_b200 import ops, sdes
-    dev = cuda_device
-    d = 4 * nblk
-    B, T = 37, 173
-    rng = np.random.default_rng(40 + nblk)
-    ls = synth.log_uniform(rng, 0.5, 2.0, (B, nblk))
-    prior = sdes.BatchedMaternSDE(4, ls)
-    t = synth.time_grid(T, 0.1, rng)
-    Y = synth.noisy_series(B, T, 1, rng, 0.1)
-    tt = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=dev)   # noqa: E731
-    lam, Pinf, H = tt(prior.lam()), tt(prior.P_inf()), tt(prior.H())
-    disc = ops.Disc.matern(nblk, lam, Pinf)
-    dt_f = tt(np.hstack([0.0, np.diff(t)]))
-    dt_s = tt(np.hstack([np.diff(t), 0.0]))
-    Yd = tt(Y)
-    if time_major:
-        Yd = Yd.transpose(0, 1).contiguous().transpose(0, 1)
-    R = tt(np.full((1, 1, 1, 1), 0.1))
-    lml, mf, Pf = ops.kf_filter(dt_f, Yd, R, H, tt(np.zeros((1, d))), Pinf, disc, jitter=1e-5)
-    n = B * (d * d + d) + 40 * B * (2 * d * d + d)
-    ws = torch.empty((n,), dtype=torch.float64, device=dev)
-    ms2, Ps2 = ops.rts_smooth(dt_s, mf, Pf, disc, Hout=None, jitter=1e-5, ws=ws)
-    from physs_gp_b200 import settings
-    old = settings.two_kernel_smoother
-    settings.two_kernel_smoother = False
-    try:
-        ms1, Ps1 = ops.rts_smooth(dt_s, mf, Pf, disc, Hout=None, jitter=1e-5)
-    finally:
-        settings.two_kernel_smoother = old
-    assert rel(ms2, ms1.cpu().numpy()) < 1e-11 and rel(Ps2, Ps1.cpu().numpy()) < 1e-11
-    ref = c_oracle.filter_smooth(4, prior.lam(), prior.P_inf(), prior.H(), t, Y, np.array([[0.1]]), jitter=1e-5,
-                                 full_state=True)
-    assert rel(ms2, ref["ms"]) < TOL and rel(Ps2, ref["Ps"]) < TOL
-    # T = 1 and T = 2 edge cases through the same entry point
-    for Tt in (1, 2):
-        m_, P_ = mf[:, :Tt].contiguous(), Pf[:, :Tt].contiguous()
-        dts = tt(np.hstack([np.diff(t[:Tt]), 0.0]))
-        a, b = ops.rts_smooth(dts, m_, P_, disc, Hout=None, jitter=1e-5, ws=ws)
-        settings.two_kernel_smoother = False
-        try:
-            a1, b1 = ops.rts_smooth(dts, m_, P_, disc, Hout=None, jitter=1e-5)
-        finally:
-            settings.two_kernel_smoother = old
-        assert rel(a, a1.cpu().numpy()) < 1e-11 and rel(b, b1.cpu().numpy()) < 1e-11
