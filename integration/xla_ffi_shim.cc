@@ -6,7 +6,7 @@
 // the one-line build a maintainer of the reference runs where jaxlib exists:
 //
 //   g++ -O2 -fPIC -shared -std=c++17 -I$(python -c "import jax.ffi; print(jax.ffi.include_dir())") \
-//       -I include -I /usr/local/cuda/include physs_gp_b200/csrc/xla_ffi_shim.cc \
+//       -I include -I /usr/local/cuda/include integration/xla_ffi_shim.cc \
 //       -L physs_gp_b200 -lphyss_b200 -o physs_gp_b200/libphyss_b200_ffi.so
 //
 // It contains no arithmetic: it unpacks XLA buffers (device pointers + dimensions) and the CUDA stream XLA
