@@ -531,7 +531,8 @@ def run_b200(a):
     kern = {}
     # which kernel family the C ABI dispatches this shape to (physs_api.cu: prefer_seq / rt_supported)
     if d <= 4:
-        kn = ("seq_filter_kernel<%d>" % d, "seq_smooth_kernel<%d>" % d)
+        # time-major plain mode: the software-pipelined smoother for even d (physs_seq_impl.cuh: launch_smooth)
+        kn = ("seq_filter_kernel<%d>" % d, ("seq_smooth_pipe_kernel<%d>" if d % 2 == 0 else "seq_smooth_kernel<%d>") % d)
     elif d <= 32:
         kn = ("rt_filter_kernel<%d>" % d, "rt_smooth_kernel<%d>" % d)
     else:
