@@ -52,6 +52,11 @@ extern "C" {
                             /* closed-form expm (kernels/ss_utils.py:6-10, kernels/matern.py:152-177,    */
                             /* 306-329) from lam[., nblk] = sqrt(2 nu)/lengthscale, Q_k = Pinf - A Pinf A^T */
                             /* (kernels/kernel.py:207-209) with block-diagonal Pinf[., d, d].             */
+#define PHYSS_DISC_IWP 2    /* one integrated-Wiener block IWP(q), q = d - 1 in 1..3 (WienerVelocity,     */
+                            /* kernels/wiener.py:60-149): A_k[i][j] = dt^(j-i)/(j-i)!, Q_k[i][j] =        */
+                            /* lam dt^(2q+1-i-j) / ((2q+1-i-j)(q-i)!(q-j)!) on chip; lam[., 1] = spectral  */
+                            /* density (the kernel's variance); Pinf unused (may be NULL).  Sequential     */
+                            /* filter / smoother only; larger or stacked IWP priors go through DISC_GIVEN. */
 
 /* ABI version (bumped on any signature change). */
 int physs_abi_version(void);

@@ -133,6 +133,35 @@ class Matern72:
         return self.var * (1. + s7 * r + 14. / 5. * r ** 2 + 7. * s7 / 15. * r ** 3) * np.exp(-s7 * r)
 
 
+class IWP:
+    """kernels/wiener.py:60-149 (WienerVelocity / IntegratedWiener): state (f, f', ..., f^(q)), F = shift matrix;
+    expm :105-123, Q :125-149 (its own closed form: the process is not stationary), to_ss :90-103 with
+    Pinf = stable_state_covariance * I used as the initial covariance."""
+
+    def __init__(self, q=1, variance=1.0, stable_state_covariance=0.0):
+        self.q, self.var, self.ssc = int(q), float(variance), float(stable_state_covariance)
+        self.state_dim = self.q + 1
+
+    def to_ss(self):
+        dim, q = self.q + 1, self.q
+        F = np.eye(dim, k=1)
+        L = np.hstack([np.zeros(dim - 1), [1.0]])[:, None]
+        H = np.hstack([[1.0], np.zeros(q)])[None, :]
+        return F, L, np.array([[self.var]]), H, np.zeros([dim, 1]), np.eye(dim) * self.ssc
+
+    def expm(self, dt):
+        from math import factorial
+        dim = self.q + 1
+        return np.array([[dt ** (j - i) / factorial(j - i) if j >= i else 0.0 for j in range(dim)]
+                         for i in range(dim)])
+
+    def Q(self, dt, A=None, Pinf=None):
+        from math import factorial
+        dim, q = self.q + 1, self.q
+        return self.var * np.array([[dt ** (2 * q + 1 - i - j) / ((2 * q + 1 - i - j) * factorial(q - i) * factorial(q - j))
+                                     for j in range(dim)] for i in range(dim)])
+
+
 class GenericLTI:
     """A stationary LTI SDE given by (F, H, Pinf) with A = scipy expm(F dt) -- the role played in
     the reference by kernels that call jax.scipy.linalg.expm (kernels/periodic.py:250-253)."""
@@ -235,7 +264,17 @@ class LTI_SDE:
 
     def Q(self, dt, A, Pinf):
         # kernel.py:207-209 applied per latent block then re-stacked (transform.py:499-545);
-        # with block-diagonal A and Pinf that equals the dense expression below.
+        # with block-diagonal A and Pinf that equals the dense expression below.  Kernels with their own Q
+        # (the integrated Wiener process, wiener.py:125-149) supply their block.
+        if any(hasattr(k, "Q") for k in self.latents):
+            out, off = [], 0
+            for k in self.latents:
+                n = k.state_dim
+                sl = slice(off, off + n)
+                out.append(k.Q(dt, A[sl, sl], Pinf[sl, sl]) if hasattr(k, "Q")
+                           else Pinf[sl, sl] - A[sl, sl] @ Pinf[sl, sl] @ A[sl, sl].T)
+                off += n
+            return block_diag(out)
         return Pinf - A @ Pinf @ A.T
 
 

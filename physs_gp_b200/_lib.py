@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(_HERE, "libphyss_b200.so")
 PHYSS_OK = 0
 DISC_GIVEN = 0
 DISC_MATERN = 1
-ABI_VERSION = 9
+DISC_IWP = 2
+ABI_VERSION = 10
 
 _c_i32 = ctypes.c_int32
 _c_i64 = ctypes.c_int64

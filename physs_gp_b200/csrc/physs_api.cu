@@ -42,6 +42,8 @@ static bool prefer_seq(int d, int m, int64_t B, int64_t nchunk, bool smoother) {
 }
 
 int run_filter_any(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity, const SeqFilterArgs& a) {
+  if (disc_mode == PHYSS_DISC_IWP && !seq_supported(d, m, disc_mode, nblk))
+    return set_error(PHYSS_ERR_UNSUPPORTED, "DISC_IWP: one block of state dim 2..4 (use DISC_GIVEN otherwise)");
   if (!force_grp(d) && prefer_seq(d, m, a.B, a.nchunk, false) && seq_supported(d, m, disc_mode, nblk))
     return seq_filter(st, d, m, disc_mode, nblk, h_identity, a);
   if (m > d) return set_error(PHYSS_ERR_UNSUPPORTED, "filter: m > d is not supported");
@@ -50,6 +52,8 @@ int run_filter_any(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool 
 }
 
 int run_smooth_any(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a) {
+  if (disc_mode == PHYSS_DISC_IWP && !seq_supported(d, mo == 0 ? d : mo, disc_mode, nblk))
+    return set_error(PHYSS_ERR_UNSUPPORTED, "DISC_IWP: one block of state dim 2..4 (use DISC_GIVEN otherwise)");
   if (!force_grp(d) && prefer_seq(d, 1, a.B, a.nchunk, true) && seq_supported(d, mo == 0 ? d : mo, disc_mode, nblk))
     return seq_smooth(st, d, mo, disc_mode, nblk, a);
   if (!force_grp(d) && rt_supported(d, mo == 0 ? d : mo)) return rt_smooth(st, d, mo, disc_mode, nblk, a);
@@ -74,12 +78,13 @@ static inline bool step_strides_ok(int64_t B, int64_t T, int64_t bs, int64_t ts)
 
 extern "C" {
 
-int physs_abi_version(void) { return 9; }
+int physs_abi_version(void) { return 10; }
 
 const char* physs_last_error(void) { return g_err; }
 
 int physs_kf_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {
   if (seq_supported(d, m, disc_mode, nblk)) return 1;
+  if (disc_mode == PHYSS_DISC_IWP) return 0;
   if (disc_mode == PHYSS_DISC_MATERN) {
     if (nblk < 1 || d % nblk != 0 || d / nblk > 4) return 0;
   }
@@ -133,6 +138,9 @@ static int pack_filter(FILTER_PARAMS, double* mf, double* Pf, double* lml, doubl
   } else if (disc_mode == PHYSS_DISC_MATERN) {
     if (!lam || !Pinf || nblk < 1 || d % nblk != 0)
       return set_error(PHYSS_ERR_BAD_ARG, "filter: DISC_MATERN needs lam, Pinf and nblk | d");
+  } else if (disc_mode == PHYSS_DISC_IWP) {
+    if (!lam || nblk < 1 || d % nblk != 0)
+      return set_error(PHYSS_ERR_BAD_ARG, "filter: DISC_IWP needs lam (spectral densities) and nblk | d");
   } else {
     return set_error(PHYSS_ERR_BAD_ARG, "filter: unknown disc_mode");
   }
@@ -163,6 +171,9 @@ static int pack_smooth(SMOOTH_PARAMS, double* ms, double* Ps, SeqSmoothArgs& a) 
   } else if (disc_mode == PHYSS_DISC_MATERN) {
     if (!lam || !Pinf || nblk < 1 || d % nblk != 0)
       return set_error(PHYSS_ERR_BAD_ARG, "smoother: DISC_MATERN needs lam, Pinf and nblk | d");
+  } else if (disc_mode == PHYSS_DISC_IWP) {
+    if (!lam || nblk < 1 || d % nblk != 0)
+      return set_error(PHYSS_ERR_BAD_ARG, "smoother: DISC_IWP needs lam (spectral densities) and nblk | d");
   } else {
     return set_error(PHYSS_ERR_BAD_ARG, "smoother: unknown disc_mode");
   }

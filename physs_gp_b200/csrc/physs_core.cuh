@@ -178,6 +178,33 @@ struct MaternExpm<4> {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Integrated Wiener process of order q = S - 1 (WienerVelocity, kernels/wiener.py:60-149): F = shift matrix,
+//   A[i][j] = dt^(j-i) / (j-i)!  (j >= i, else 0)                                         (:105-123)
+//   Q[i][j] = var * dt^(2q+1-i-j) / ((2q+1-i-j) (q-i)! (q-j)!)                           (:125-149)
+// Not stationary: there is no P_inf with Q = P_inf - A P_inf A^T, so the predict step takes (A, Q) explicitly.
+// ---------------------------------------------------------------------------------------------
+template <int S>
+struct IwpDisc {
+  static PHYSS_HD void eval(double var, double dt, double (&A)[S][S], double (&Q)[S][S]) {
+    constexpr int q = S - 1;
+    constexpr double fact[8] = {1.0, 1.0, 2.0, 6.0, 24.0, 120.0, 720.0, 5040.0};
+    double pw[2 * q + 2];                       // dt^0 .. dt^(2q+1)
+    pw[0] = 1.0;
+    PHYSS_UNROLL
+    for (int k = 1; k < 2 * q + 2; ++k) pw[k] = pw[k - 1] * dt;
+    PHYSS_UNROLL
+    for (int i = 0; i < S; ++i) {
+      PHYSS_UNROLL
+      for (int j = 0; j < S; ++j) {
+        A[i][j] = (j >= i) ? pw[(j >= i) ? j - i : 0] / fact[(j >= i) ? j - i : 0] : 0.0;
+        const int e = 2 * q + 1 - i - j;
+        Q[i][j] = var * pw[e] / ((double)e * fact[q - i] * fact[q - j]);
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Block-diagonal transition: D = NB * S, block b is an S x S dense matrix.  S == D is a plain dense
 // transition (also used when A_k is supplied by the caller).
 // ---------------------------------------------------------------------------------------------

@@ -1438,6 +1438,8 @@ static double* ps_scan_result(const PsWorkspace& w, int64_t n) {
 
 static int check_matern(int d, int disc_mode, int nblk) {
   if (disc_mode == PHYSS_DISC_GIVEN) return PHYSS_OK;
+  if (disc_mode != PHYSS_DISC_MATERN)
+    return set_error(PHYSS_ERR_UNSUPPORTED, "parallel-in-time forms: DISC_GIVEN or DISC_MATERN only");
   const int s = (nblk > 0) ? d / nblk : 0;
   if (s < 1 || s > 4 || s * nblk != d)
     return set_error(PHYSS_ERR_UNSUPPORTED, "DISC_MATERN needs equal blocks of size 1..4");

@@ -72,6 +72,26 @@ __device__ __forceinline__ void matern_trans(const double (&lam)[D / S], double 
   for (int b = 0; b < D / S; ++b) MaternExpm<S>::eval(lam[b], dt, A.a[b]);
 }
 
+// integrated Wiener blocks: A_k and Q_k of every block in closed form (kernels/wiener.py:105-149), Q block-diagonal
+template <int D, int S>
+__device__ __forceinline__ void iwp_trans(const double (&var)[D / S], double dt, Trans<D, S>& A, double (&Q)[D][D]) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) Q[i][j] = 0.0;
+  }
+#pragma unroll
+  for (int b = 0; b < D / S; ++b) {
+    double q[S][S];
+    IwpDisc<S>::eval(var[b], dt, A.a[b], q);
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+#pragma unroll
+      for (int j = 0; j < S; ++j) Q[b * S + i][b * S + j] = q[i][j];
+    }
+  }
+}
+
 // ------------------------------------------------------------------- warp-cooperative row transfer
 // Rows of N doubles owned one per lane, 32 consecutive series contiguous in global memory (sbs == 1).
 // LD = padded row length of the shared-memory tile.
@@ -236,7 +256,7 @@ __device__ __forceinline__ bool agrees(const double (&m)[D], const double (&P)[D
   return (dP <= delta * sP) && (dm <= delta * sm || dm * dm <= delta * delta * sP);
 }
 
-template <int D, int S, int M, bool HID, bool GIVEN, bool CHUNK>
+template <int D, int S, int M, bool HID, int GIVEN, bool CHUNK>
 __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const SeqFilterArgs p) {
   __shared__ __align__(16) double tiles[SeqBlock<D>::WARPS][RowTile<D * D>::SIZE];
   SeqWork wk;
@@ -249,6 +269,8 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
   const bool coal = (p.sbs == 1);
   const int64_t sts = p.sts;
 
+  // GIVEN: 0 = closed-form Matern blocks (lam, Pinf), 1 = A_k, Q_k supplied, 2 = integrated Wiener blocks
+  // (lam = spectral density, no stationary covariance)
   double m[D], P[D][D], Pinf[D][D], H[M][D], lam[NB];
   if (CHUNK && p.from_bnd) {
     load_vec<D>(p.bnd_m + v * D, m);
@@ -257,8 +279,8 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
     load_vec<D>(p.m0 + b * p.m0_bs, m);
     load_mat<D>(p.P0 + b * p.P0_bs, P);
   }
-  if (!GIVEN) {
-    load_mat<D>(p.Pinf + b * p.Pinf_bs, Pinf);
+  if (GIVEN == 0) load_mat<D>(p.Pinf + b * p.Pinf_bs, Pinf);
+  if (GIVEN != 1) {
 #pragma unroll
     for (int i = 0; i < NB; ++i) lam[i] = p.lam[b * p.lam_bs + i];
   }
@@ -274,8 +296,8 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
   const double* __restrict__ dtp = p.dt + b * p.dt_bs + t0;
   const double* __restrict__ Yp = p.Y + row0 * M;
   const double* __restrict__ Rp = p.R + b * p.R_bs + t0 * p.R_ts;
-  const double* __restrict__ Ap = GIVEN ? p.A + b * p.A_bs + t0 * D * D : nullptr;
-  const double* __restrict__ Qp = GIVEN ? p.Q + b * p.Q_bs + t0 * D * D : nullptr;
+  const double* __restrict__ Ap = (GIVEN == 1) ? p.A + b * p.A_bs + t0 * D * D : nullptr;
+  const double* __restrict__ Qp = (GIVEN == 1) ? p.Q + b * p.Q_bs + t0 * D * D : nullptr;
   double* __restrict__ mfp = p.mf + row0 * D;
   double* __restrict__ Pfp = p.Pf + row0 * D * D;
   double* __restrict__ mfw = p.mf + wrow0 * D;
@@ -296,7 +318,8 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
   load_mat<M>(Rp - w0 * p.R_ts, R_n);
   dt_n = (1 - w0 < T) ? dtp[1 - w0] : 0.0;                   // dt of the step AFTER the first one
   Trans<D, S> A_n;
-  if constexpr (!GIVEN) matern_trans<D, S>(lam, dtp[-w0], A_n);
+  if constexpr (GIVEN == 0) matern_trans<D, S>(lam, dtp[-w0], A_n);
+  double dt_cur = dtp[-w0];                                  // integrated Wiener: dt of the current step
 
   for (int64_t k = -w0; k < T; ++k) {
     double y[M], R[M][M];
@@ -313,10 +336,15 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
     }
     if (k + 2 < T) dt_n = dtp[k + 2];
     Trans<D, S> A;
-    if constexpr (GIVEN) {
+    if constexpr (GIVEN == 1) {
       double Q[D][D];
       load_trans_dense<D, S>(Ap + k * D * D, A);
       load_mat<D>(Qp + k * D * D, Q);
+      kf_predict_givenQ<D, S>(A, Q, m, P);
+    } else if constexpr (GIVEN == 2) {
+      double Q[D][D];
+      iwp_trans<D, S>(lam, dt_cur, A, Q);
+      dt_cur = dt_next;
       kf_predict_givenQ<D, S>(A, Q, m, P);
     } else {
       A = A_n;
@@ -354,7 +382,7 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
 
 // ---------------------------------------------------------------------------------------- smoother
 // MO == 0: full_state (H = I).  MO > 0: project with Hout [MO, D].
-template <int D, int S, int MO, bool GIVEN, bool CHUNK, bool COAL>
+template <int D, int S, int MO, int GIVEN, bool CHUNK, bool COAL>
 __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_smooth_kernel(const SeqSmoothArgs p) {
   __shared__ __align__(16) double tiles[SeqBlock<D>::WARPS][RowTile<D * D>::SIZE];
   SeqWork wk;
@@ -369,8 +397,8 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_smooth_kernel(const 
   const int64_t sts = p.sts;
 
   double Pinf[D][D], lam[NB], Ho[MP][D];
-  if (!GIVEN) {
-    load_mat<D>(p.Pinf + b * p.Pinf_bs, Pinf);
+  if (GIVEN == 0) load_mat<D>(p.Pinf + b * p.Pinf_bs, Pinf);
+  if (GIVEN != 1) {
 #pragma unroll
     for (int i = 0; i < NB; ++i) lam[i] = p.lam[b * p.lam_bs + i];
   }
@@ -384,8 +412,8 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_smooth_kernel(const 
   const int64_t row0 = b * p.sbs + t0 * sts;
   const int64_t wrow0 = wk.b0 * p.sbs + t0 * sts;
   const double* __restrict__ dtp = p.dt + b * p.dt_bs + t0;
-  const double* __restrict__ Ap = GIVEN ? p.A + b * p.A_bs + t0 * D * D : nullptr;
-  const double* __restrict__ Qp = GIVEN ? p.Q + b * p.Q_bs + t0 * D * D : nullptr;
+  const double* __restrict__ Ap = (GIVEN == 1) ? p.A + b * p.A_bs + t0 * D * D : nullptr;
+  const double* __restrict__ Qp = (GIVEN == 1) ? p.Q + b * p.Q_bs + t0 * D * D : nullptr;
   const double* __restrict__ mfp = p.mf + row0 * D;
   const double* __restrict__ Pfp = p.Pf + row0 * D * D;
   const double* __restrict__ mfw = p.mf + wrow0 * D;
@@ -506,10 +534,14 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_smooth_kernel(const 
       dt_n = dtp[k - 1];
     }
     Trans<D, S> A;
-    if constexpr (GIVEN) {
+    if constexpr (GIVEN == 1) {
       double Q[D][D];
       load_trans_dense<D, S>(Ap + k * D * D, A);
       load_mat<D>(Qp + k * D * D, Q);
+      rts_step<D, S>(A, Q, false, mf, Pf, p.jitter, ms, Ps);
+    } else if constexpr (GIVEN == 2) {
+      double Q[D][D];
+      iwp_trans<D, S>(lam, dt, A, Q);
       rts_step<D, S>(A, Q, false, mf, Pf, p.jitter, ms, Ps);
     } else {
       matern_trans<D, S>(lam, dt, A);
@@ -579,7 +611,7 @@ struct SeqPipe {
   static constexpr size_t smem_bytes(int warps) { return (size_t)warps * PER_WARP * sizeof(double); }
 };
 
-template <int D, int S, int MO, bool GIVEN>
+template <int D, int S, int MO, int GIVEN>
 __global__ void __launch_bounds__(128) seq_smooth_pipe_kernel(const SeqSmoothArgs p) {
   extern __shared__ __align__(16) double pipe_smem[];
   SeqWork wk;
@@ -595,8 +627,8 @@ __global__ void __launch_bounds__(128) seq_smooth_pipe_kernel(const SeqSmoothArg
   const int64_t sts = p.sts;
 
   double Pinf[D][D], lam[NB], Ho[MP][D];
-  if (!GIVEN) {
-    load_mat<D>(p.Pinf + b * p.Pinf_bs, Pinf);
+  if (GIVEN == 0) load_mat<D>(p.Pinf + b * p.Pinf_bs, Pinf);
+  if (GIVEN != 1) {
 #pragma unroll
     for (int i = 0; i < NB; ++i) lam[i] = p.lam[b * p.lam_bs + i];
   }
@@ -610,8 +642,8 @@ __global__ void __launch_bounds__(128) seq_smooth_pipe_kernel(const SeqSmoothArg
   const int64_t row0 = b * p.sbs;
   const int64_t wrow0 = wk.b0 * p.sbs;
   const double* __restrict__ dtp = p.dt + b * p.dt_bs;
-  const double* __restrict__ Ap = GIVEN ? p.A + b * p.A_bs : nullptr;
-  const double* __restrict__ Qp = GIVEN ? p.Q + b * p.Q_bs : nullptr;
+  const double* __restrict__ Ap = (GIVEN == 1) ? p.A + b * p.A_bs : nullptr;
+  const double* __restrict__ Qp = (GIVEN == 1) ? p.Q + b * p.Q_bs : nullptr;
   const double* __restrict__ mfp = p.mf + row0 * D;
   const double* __restrict__ Pfp = p.Pf + row0 * D * D;
   const double* __restrict__ mfw = p.mf + wrow0 * D;
@@ -670,10 +702,14 @@ __global__ void __launch_bounds__(128) seq_smooth_pipe_kernel(const SeqSmoothArg
     tile_own_row<D>(st, lane, mf);
     tile_own_row<D * D>(st + RowTile<D>::SIZE, lane, flat<D>(Pf));
     Trans<D, S> A;
-    if constexpr (GIVEN) {
+    if constexpr (GIVEN == 1) {
       double Q[D][D];
       load_trans_dense<D, S>(Ap + k * D * D, A);
       load_mat<D>(Qp + k * D * D, Q);
+      rts_front<D, S>(A, Q, false, mf, Pf, p.jitter, mp, Pp, G);
+    } else if constexpr (GIVEN == 2) {
+      double Q[D][D];
+      iwp_trans<D, S>(lam, dt, A, Q);
       rts_front<D, S>(A, Q, false, mf, Pf, p.jitter, mp, Pp, G);
     } else {
       matern_trans<D, S>(lam, dt, A);
@@ -753,7 +789,7 @@ static inline int pick_block(int64_t B) {
 // One thread per (series, chunk): folds the chunk's steps into ONE scan element, in registers (the d <= 4
 // counterpart of ps_filter_summary_kernel / ps_smooth_summary_kernel in physs_pscan.cu; same element
 // layout in global memory: filter [A | C | J | b | eta], smoother [E | L | g], index b * nchunk + c).
-template <int D, int S, int M, bool HID, bool GIVEN>
+template <int D, int S, int M, bool HID, int GIVEN>
 __global__ void __launch_bounds__(128) seq_filter_summary_kernel(const SeqFilterArgs p, double* __restrict__ elems) {
   SeqWork wk;
   if (!seq_work<true>(p, wk)) return;
@@ -844,7 +880,7 @@ __global__ void __launch_bounds__(128) seq_filter_summary_kernel(const SeqFilter
   }
 }
 
-template <int D, int S, bool GIVEN>
+template <int D, int S, int GIVEN>
 __global__ void __launch_bounds__(128) seq_smooth_summary_kernel(const SeqSmoothArgs p, double* __restrict__ elems) {
   SeqWork wk;
   if (!seq_work<true>(p, wk)) return;
@@ -916,7 +952,7 @@ __global__ void __launch_bounds__(128) seq_smooth_summary_kernel(const SeqSmooth
   }
 }
 
-template <int D, int S, int M, bool HID, bool GIVEN>
+template <int D, int S, int M, bool HID, int GIVEN>
 static int launch_filter_summary(cudaStream_t st, const SeqFilterArgs& a, double* elems) {
   const int64_t n = ((a.B + 31) / 32 * 32) * a.chunk_count;
   const int block = pick_block(n);
@@ -924,7 +960,7 @@ static int launch_filter_summary(cudaStream_t st, const SeqFilterArgs& a, double
   return cuda_status(cudaGetLastError(), "seq_filter_summary_kernel launch");
 }
 
-template <int D, int S, bool GIVEN>
+template <int D, int S, int GIVEN>
 static int filter_summary_by_m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid, double* elems) {
   if (hid && m == D) return launch_filter_summary<D, S, D, true, GIVEN>(st, a, elems);
   if (m == 1) return launch_filter_summary<D, S, 1, false, GIVEN>(st, a, elems);
@@ -934,7 +970,7 @@ static int filter_summary_by_m(cudaStream_t st, const SeqFilterArgs& a, int m, b
   return set_error(PHYSS_ERR_UNSUPPORTED, "seq filter summary: unsupported observation dim");
 }
 
-template <int D, int S, bool GIVEN>
+template <int D, int S, int GIVEN>
 static int launch_smooth_summary(cudaStream_t st, const SeqSmoothArgs& a, double* elems) {
   const int64_t n = ((a.B + 31) / 32 * 32) * a.chunk_count;
   const int block = pick_block(n);
@@ -943,7 +979,7 @@ static int launch_smooth_summary(cudaStream_t st, const SeqSmoothArgs& a, double
 }
 
 
-template <int D, int S, int M, bool HID, bool GIVEN>
+template <int D, int S, int M, bool HID, int GIVEN>
 static int launch_filter(cudaStream_t st, const SeqFilterArgs& a) {
   const int64_t n = ((a.B + 31) / 32 * 32) * (a.nchunk > 0 ? a.chunk_count : 1);
   const int block = pick_block(n) < SeqBlock<D>::THREADS ? pick_block(n) : SeqBlock<D>::THREADS;
@@ -967,7 +1003,7 @@ static int seq_wave(K kern, int threads, int64_t* out) {
   return PHYSS_OK;
 }
 
-template <int D, int S, int MO, bool GIVEN>
+template <int D, int S, int MO, int GIVEN>
 static int launch_smooth(cudaStream_t st, const SeqSmoothArgs& a) {
   if (a.wave_out) {
     if constexpr (D % 2 == 0) {
@@ -1019,7 +1055,7 @@ static int launch_smooth(cudaStream_t st, const SeqSmoothArgs& a) {
 }
 
 // m in 1..D (dense H) or identity H with m == D
-template <int D, int S, bool GIVEN>
+template <int D, int S, int GIVEN>
 static int filter_by_m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid) {
   if (hid && m == D) return launch_filter<D, S, D, true, GIVEN>(st, a);
   if (m == 1) return launch_filter<D, S, 1, false, GIVEN>(st, a);
@@ -1029,7 +1065,7 @@ static int filter_by_m(cudaStream_t st, const SeqFilterArgs& a, int m, bool hid)
   return set_error(PHYSS_ERR_UNSUPPORTED, "seq filter: unsupported observation dim");
 }
 
-template <int D, int S, bool GIVEN>
+template <int D, int S, int GIVEN>
 static int smooth_by_mo(cudaStream_t st, const SeqSmoothArgs& a, int mo) {
   if (mo == 0) return launch_smooth<D, S, 0, GIVEN>(st, a);
   if (mo == 1) return launch_smooth<D, S, 1, GIVEN>(st, a);

@@ -46,7 +46,7 @@ def _np(x):
     return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x, dtype=np.float64)
 
 
-def lower_prior(prior, X_s, dts, dev):
+def lower_prior(prior, X_s, dts, dev, sequential=True):
     """Turn a prior object into what the kernels consume.
 
     Returns (discs, m0, P0, H): one `ops.Disc` per dt array in `dts` (filter and smoother use
@@ -82,6 +82,11 @@ def lower_prior(prior, X_s, dts, dev):
             disc = ops.Disc.matern(len(blocks), lam, P0)
             if ops.kf_supported(d, 1, disc):
                 return [disc for _ in dts], m0, P0, H
+    iwp = prior.iwp_blocks() if (sequential and hasattr(prior, "iwp_blocks")) else None
+    if iwp is not None and len(iwp) == 1 and 2 <= iwp[0][0] <= 4 and iwp[0][0] == d:
+        # one integrated-Wiener block: closed-form A_k, Q_k on chip (PHYSS_DISC_IWP), sequential kernels only
+        disc = ops.Disc.iwp(_to_dev(np.array([[iwp[0][1]]]), dev))
+        return [disc for _ in dts], m0, P0, H
     # generic route: evaluate the reference prior API once per distinct dt (host), ship A_k, Q_k
     discs = []
     for dt in dts:
@@ -159,7 +164,7 @@ def _filter_impl(parallel, data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, 
         # the 32 series of a warp read / write contiguous spans; every output follows Y's memory order
         Yd = Yd.transpose(0, 1).contiguous().transpose(0, 1)
     dtd = _to_dev(dt, dev)
-    (disc,), m0, P0, H = lower_prior(prior, X_s, [dtd], dev)
+    (disc,), m0, P0, H = lower_prior(prior, X_s, [dtd], dev, sequential=not parallel)
     R = _to_dev(lik_mat, dev)
     Hd = None if _is_identity(H) else _to_dev(H, dev)
     if isinstance(prior, PDE):
@@ -245,7 +250,7 @@ def _smoother_impl(parallel, data, model, filter_res, dt, X_t, X_s, full_state):
     if not batched:
         mf, Pf = mf[None], Pf[None]
     dtd = _to_dev(dt, dev)
-    (disc,), _, _, H = lower_prior(model, X_s, [dtd], dev)
+    (disc,), _, _, H = lower_prior(model, X_s, [dtd], dev, sequential=not parallel)
     Hout = None if (full_state or _is_identity(H)) else _to_dev(H, dev)
     if parallel:
         ms, Ps = ops.pscan_smooth(dtd, mf, Pf, disc, Hout=Hout, chunk_len=settings.pscan_chunk_len,

@@ -167,6 +167,51 @@ ScaledMatern52 = Matern52
 ScaledMatern72 = Matern72
 
 
+class WienerVelocity(MarkovKernel):
+    """Integrated Wiener process of order q (stgp/kernels/wiener.py:60-149): state (f, f', ..., f^(q)), F the
+    shift matrix, spectral density `variance`.  Not stationary: `Q` is its own closed form (:125-149), `P_inf`
+    is `stable_state_covariance * I` and only serves as the initial covariance (:97-103)."""
+
+    def __init__(self, q=1, variance=1.0, stable_state_covariance=0.0, m_init=None):
+        self.q = int(q)
+        self.variance = float(variance)
+        self.stable_state_covariance = float(stable_state_covariance)
+        self._state_space_dim = self.q + 1
+        self.m_init = (np.zeros([self.q + 1, 1]) if m_init is None
+                       else np.reshape(np.asarray(m_init, np.float64), [self.q + 1, 1]))
+        self.input_dim = 1
+
+    def to_ss(self, X_spatial=None):
+        dim, q = self.q + 1, self.q
+        F = np.eye(dim, k=1)
+        L = np.hstack([np.zeros(dim - 1), [1.0]])[:, None]
+        H = np.hstack([[1.0], np.zeros(q)])[None, :]
+        return F, L, np.array([[self.variance]]), H, self.m_init, np.eye(dim) * self.stable_state_covariance
+
+    def expm(self, dt, X_spatial=None):
+        import math
+        dim = self.q + 1
+        return np.array([[dt ** (j - i) / math.factorial(j - i) if j >= i else 0.0 for j in range(dim)]
+                         for i in range(dim)])
+
+    def Q(self, dt, A_k=None, P_inf=None, X_spatial=None):
+        import math
+        dim, q = self.q + 1, self.q
+        return self.variance * np.array(
+            [[dt ** (2 * q + 1 - i - j) / ((2 * q + 1 - i - j) * math.factorial(q - i) * math.factorial(q - j))
+              for j in range(dim)] for i in range(dim)])
+
+    def ss_blocks(self):
+        return None                                   # not a Matern block
+
+    def iwp_blocks(self):
+        """[(block size, spectral density)] for the on-chip integrated-Wiener discretisation (PHYSS_DISC_IWP)."""
+        return [(self.q + 1, self.variance)]
+
+
+IntegratedWiener = WienerVelocity
+
+
 class SumKernel(MarkovKernel):
     """stgp/kernels/kernel.py:134-160: block-diagonal F/Pinf/expm, H = hstack."""
 

@@ -31,6 +31,11 @@ class Disc:
     def matern(nblk, lam, Pinf):
         return Disc(_lib.DISC_MATERN, int(nblk), lam=lam, Pinf=Pinf)
 
+    @staticmethod
+    def iwp(var):
+        """One integrated-Wiener block (PHYSS_DISC_IWP): var [B, 1] = spectral density per series."""
+        return Disc(_lib.DISC_IWP, 1, lam=var)
+
 
 def _dev(x, name):
     if not isinstance(x, torch.Tensor):
@@ -102,6 +107,9 @@ def _disc_args(disc, B, T, d):
         keep += [A, Q]
         return keep, (A.data_ptr(), sA[0]), (Q.data_ptr(), sQ[0]), null, null
     lam, sl = _bview(disc.lam, "lam", (B, disc.nblk), 1)
+    if disc.mode == _lib.DISC_IWP:
+        keep += [lam]
+        return keep, null, null, (lam.data_ptr(), sl[0]), null
     Pinf, sP = _bview(disc.Pinf, "Pinf", (B, d, d), 2)
     keep += [lam, Pinf]
     return keep, null, null, (lam.data_ptr(), sl[0]), (Pinf.data_ptr(), sP[0])

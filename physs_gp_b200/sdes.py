@@ -58,6 +58,15 @@ class Independent:
             blocks += b
         return blocks
 
+    def iwp_blocks(self):
+        blocks = []
+        for l in self.parent:
+            b = l.kernel.iwp_blocks() if hasattr(l.kernel, "iwp_blocks") else None
+            if b is None:
+                return None
+            blocks += b
+        return blocks
+
 
 class LTI_SDE:
     """stgp/transforms/sdes.py:18-97."""
@@ -91,6 +100,9 @@ class LTI_SDE:
 
     def ss_blocks(self):
         return self.gp.ss_blocks()
+
+    def iwp_blocks(self):
+        return self.gp.iwp_blocks()
 
 
 class LTI_SDE_Full_State_Obs(LTI_SDE):
@@ -173,6 +185,9 @@ class PDE:
 
     def ss_blocks(self):
         return self.parent.ss_blocks() if hasattr(self.parent, "ss_blocks") else None
+
+    def iwp_blocks(self):
+        return self.parent.iwp_blocks() if hasattr(self.parent, "iwp_blocks") else None
 
 
 class BatchedMaternSDE:

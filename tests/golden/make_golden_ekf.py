@@ -155,6 +155,59 @@ def main():
             fn = os.path.join(HERE, "ekf_%s_jit%s.npz" % (name, "1e-5" if jitter else "0"))
             onp.savez_compressed(fn, **out)
             written.append(fn)
+    # =============================================== integrated Wiener prior (a6): the reference's own
+    # WienerVelocity.{to_ss, expm, Q} (kernels/wiener.py:90-149) under the reference's sequential filter / smoother
+    import scipy.special as ssp
+    ns_w = {"np": jnp, "jax": jax, "chex": chex, "factorial": lambda n: Arr.__array_wrap__(onp.asarray(0.0), ssp.gamma(onp.asarray(n, float) + 1.0))
+            if False else A(ssp.gamma(onp.asarray(n, dtype=float) + 1.0))}
+    wv = mg.extract("kernels/wiener.py", ["WienerVelocity.to_ss", "WienerVelocity.expm", "WienerVelocity.Q",
+                                           "WienerVelocity.state_size"], ns_w)
+
+    class IWPPrior(sdes_mod.LTI_SDE):
+        def __init__(self, q, var, ssc):
+            self.k = types.SimpleNamespace(q=q, variance_param=types.SimpleNamespace(value=var), _state_space_dim=q + 1,
+                                           stable_state_covariance=ssc, m_init=onp.zeros([q + 1, 1]).view(Arr))
+            self.k.state_size = lambda: q + 1
+
+        def _ss(self):
+            return wv["WienerVelocity.to_ss"](self.k)
+
+        def m_inf(self, x, X_s, t):
+            return A(self._ss()[4])
+
+        def P_inf(self, x, X_s, t):
+            return A(self._ss()[5])
+
+        def H(self, x, X_s, t):
+            return A(self._ss()[3])
+
+        def expm(self, X_s, dt):
+            return A(wv["WienerVelocity.expm"](self.k, dt))
+
+        def Q(self, dt, A_k, P_inf, X_spatial=None):
+            return A(wv["WienerVelocity.Q"](self.k, dt, A_k, P_inf))
+    for jitter in (1e-5,):
+        settings.jitter = jitter
+        for q_, var_, ssc_ in ((1, 0.7, 0.5), (2, 1.3, 0.2), (3, 0.4, 1.0)):
+            rng = onp.random.default_rng(90 + q_)
+            T = 50
+            t = onp.cumsum(rng.uniform(0.5, 1.5, T) * 0.1)
+            Y = onp.cumsum(rng.normal(size=(T, 1)) * 0.3, axis=0) + 0.1 * rng.normal(size=(T, 1))
+            Y[rng.uniform(size=Y.shape) < 0.15] = onp.nan
+            R = onp.tile(0.05 * onp.eye(1), [T, 1, 1])
+            prior = IWPPrior(q_, var_, ssc_)
+            data = types.SimpleNamespace(X_time=A(t), X_space=None, Nt=T, Ns=1, P=1, Y_st=A(Y[:, :, None]))
+            lml, res = kf.filter_loop(data, prior, R=A(R), filter_type="sequential")
+            out = {"t": t, "Y": Y, "R": R, "jitter": jitter, "q": q_, "variance": var_, "stable_state_covariance": ssc_,
+                   "A_dt": onp.stack([onp.asarray(prior.expm(None, x)) for x in (0.0, 0.05, 0.9)]),
+                   "Q_dt": onp.stack([onp.asarray(prior.Q(x, None, None)) for x in (0.0, 0.05, 0.9)]),
+                   "lml": float(lml), "mf": onp.asarray(res["m"]), "Pf": onp.asarray(res["P"])}
+            for fs in (False, True):
+                mu, var = rts.smoother_loop(data, prior, res, full_state=fs, filter_type="sequential")
+                out["ms_full%d" % fs], out["Ps_full%d" % fs] = onp.asarray(mu), onp.asarray(var)
+            fn = os.path.join(HERE, "iwp_q%d.npz" % q_)
+            onp.savez_compressed(fn, **out)
+            written.append(fn)
     for f in written:
         print("wrote", os.path.relpath(f, HERE), os.path.getsize(f), "bytes")
 

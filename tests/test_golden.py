@@ -273,3 +273,28 @@ def test_device_sort_pad_matches_reference_on_cpu_tensors():
     order_sequentially_np + unsort (data/sequential.py:9-144, data/data.py:353-415; fixture from
     tests/golden/make_golden_cvi.py): scattered, shuffled, duplicated space-time points."""
     _check_sort_pad("cpu")
+
+
+# --------------------------------------------------------------------------- integrated Wiener prior (row a6)
+@pytest.mark.parametrize("q", [1, 2, 3])
+def test_oracle_and_product_iwp_match_reference(q):
+    """oracle.sde.IWP and the product's kernels.WienerVelocity == the reference's WienerVelocity.{expm, Q, to_ss}
+    (kernels/wiener.py:90-149), and the oracle filter / smoother on that prior == the reference's
+    (tests/golden/make_golden_ekf.py -> iwp_q*.npz)."""
+    from physs_gp_b200 import kernels as K
+    g = np.load(os.path.join(GOLD, "iwp_q%d.npz" % q))
+    var, ssc, jit = float(g["variance"]), float(g["stable_state_covariance"]), float(g["jitter"])
+    ok = osde.IWP(q, var, ssc)
+    pk = K.WienerVelocity(q, var, ssc)
+    for i, dt in enumerate((0.0, 0.05, 0.9)):
+        for k in (ok, pk):
+            assert rel(k.expm(dt), g["A_dt"][i]) < 1e-14
+            Q = k.Q(dt)
+            assert np.abs(Q - g["Q_dt"][i]).max() <= 1e-14 * max(np.abs(g["Q_dt"][i]).max(), 1e-300)
+    prior = osde.LTI_SDE([ok])
+    lml, mf, Pf, _ = ofilters.filter_sequential(prior, g["t"], g["Y"], g["R"], jit)
+    assert abs(lml - float(g["lml"])) < 1e-11 * abs(float(g["lml"]))
+    assert rel(mf, g["mf"]) < 1e-11 and rel(Pf, g["Pf"]) < 1e-11
+    for fs in (False, True):
+        ms, Ps = ofilters.smoother_sequential(prior, g["t"], mf, Pf, full_state=fs, jitter=jit)
+        assert rel(ms, g["ms_full%d" % fs]) < 1e-10 and rel(Ps, g["Ps_full%d" % fs]) < 1e-10

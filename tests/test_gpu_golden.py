@@ -120,3 +120,28 @@ def test_device_sort_pad_matches_reference_vectors(cuda_device):
     numpy helpers."""
     from tests.test_golden import _check_sort_pad
     _check_sort_pad(cuda_device)
+
+
+@pytest.mark.parametrize("q", [1, 2, 3])
+def test_cuda_integrated_wiener_matches_reference_vectors(cuda_device, q, monkeypatch):
+    """the integrated Wiener prior with A_k, Q_k evaluated ON CHIP (PHYSS_DISC_IWP) against the
+    reference's own WienerVelocity under its sequential filter / smoother; the DISC_GIVEN route (A_k, Q_k from the
+    host mirror) must agree with it."""
+    from physs_gp_b200 import data, filters, kernels as K, ops, sdes, settings, _lib
+    g = np.load(os.path.join(GOLD, "iwp_q%d.npz" % q))
+    monkeypatch.setattr(settings, "jitter", float(g["jitter"]))
+    prior = sdes.LTI_SDE(sdes.Independent([K.WienerVelocity(q, float(g["variance"]), float(g["stable_state_covariance"]))]))
+    d = data.TemporalData(g["t"], g["Y"][:, :, None])
+    dev = cuda_device
+    (disc,), _, _, _ = filters.lower_prior(prior, None, [torch.zeros(3, dtype=torch.float64, device=dev)], dev)
+    assert disc.mode == _lib.DISC_IWP                      # the on-chip route is the one under test
+    lml, kf = filters.filter_loop(d, prior, R=g["R"])
+    assert abs(float(lml) - float(g["lml"])) <= TOL * abs(float(g["lml"]))
+    assert rel(kf['m'], g["mf"]) < TOL and rel(kf['P'], g["Pf"]) < TOL
+    for fs in (False, True):
+        mu, var = filters.smoother_loop(d, prior, kf, full_state=fs)
+        assert rel(mu, g["ms_full%d" % fs]) < TOL and rel(var, g["Ps_full%d" % fs]) < TOL
+    # parallel-in-time route lowers the same prior to DISC_GIVEN
+    lml_p, kf_p = filters.filter_loop(d, prior, R=g["R"], filter_type="b200_parallel")
+    assert abs(float(lml_p) - float(g["lml"])) <= TOL * abs(float(g["lml"]))
+    assert rel(kf_p['m'], g["mf"]) < TOL and rel(kf_p['P'], g["Pf"]) < TOL
