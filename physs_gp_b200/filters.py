@@ -190,11 +190,19 @@ def _filter_impl(parallel, data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, 
                                                jitter=settings.jitter, polish=settings.pscan_polish,
                                                return_status=True)
         if settings.pscan_check_status and int(status.item()) != 0:
-            # some chunk did not reconcile with the jittered sequential recursion within the fix-up passes
-            # (slowly mixing filter / chunks too short): return the sequential kernels' result instead
-            warnings.warn("physs_gp_b200: parallel-in-time filter did not converge to the sequential recursion "
-                          "(raise settings.pscan_polish or settings.pscan_chunk_len); using the sequential kernels")
-            lml, mf, Pf = ops.kf_filter(dtd, Yd, R, Hd, m0, P0, disc, jitter=settings.jitter)
+            # Some chunk did not reconcile with the jittered sequential recursion within the fix-up passes (slowly
+            # mixing filter / chunks shorter than its memory).  Every further pass contracts the boundary error by
+            # the forgetting over one chunk and costs a few steps per converged chunk, so first retry with four
+            # times the passes (tens of ms) before giving the result up for the sequential kernels (seconds for a
+            # single long series): no cliff for a merely slow-mixing model.
+            base = settings.pscan_polish if settings.pscan_polish is not None else 4
+            lml, mf, Pf, status = ops.pscan_filter(dtd, Yd, R, Hd, m0, P0, disc, chunk_len=settings.pscan_chunk_len,
+                                                   jitter=settings.jitter, polish=4 * max(base, 1),
+                                                   return_status=True)
+            if int(status.item()) != 0:
+                warnings.warn("physs_gp_b200: parallel-in-time filter did not converge to the sequential recursion "
+                              "(raise settings.pscan_polish or settings.pscan_chunk_len); using the sequential kernels")
+                lml, mf, Pf = ops.kf_filter(dtd, Yd, R, Hd, m0, P0, disc, jitter=settings.jitter)
     else:
         lml, mf, Pf = ops.kf_filter(dtd, Yd, R, Hd, m0, P0, disc, jitter=settings.jitter)
     if batched:

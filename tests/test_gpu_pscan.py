@@ -211,3 +211,29 @@ def test_speculative_mode_flags_insufficient_warmup(cuda_device):
     dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s = _batch_problem(cuda_device, 1, 600, 4, 1, False, 5, False)
     out = ops.pscan_filter_spec(dt_f, Y, R, H, m0, P0, disc_f, chunk_len=8, warm=1, jitter=1e-5, polish=1, patience=50)
     assert int(out[-1].item()) == 1
+
+
+def test_host_api_recovers_from_unconverged_scan(cuda_device, monkeypatch):
+    """filter_type='b200_parallel' with chunks far shorter than the filter's memory and a single fix-up pass: the
+    host API must still return the SEQUENTIAL result at 1e-9 -- by retrying with more passes, or, if that is not
+    enough either, through the sequential kernels (physs_gp_b200/filters.py:_filter_impl)."""
+    import warnings
+    from physs_gp_b200 import data, filters, kernels as K, sdes, settings
+    from oracle import filters as ofilters
+    from oracle import sde as osde
+    rng = np.random.default_rng(8)
+    T = 1500
+    t = np.cumsum(rng.uniform(0.5, 1.5, T) * 0.02)
+    Y = np.sin(0.01 * np.arange(T))[:, None] + 0.3 * rng.normal(size=(T, 1))
+    R = np.tile(0.5 * np.eye(1), [T, 1, 1])
+    prior = sdes.LTI_SDE(sdes.Independent([K.Matern72(3.0, 1.0)]))       # lengthscale = 150 steps
+    oprior = osde.LTI_SDE([osde.Matern72(3.0, 1.0)])
+    monkeypatch.setattr(settings, "pscan_chunk_len", 16)
+    monkeypatch.setattr(settings, "pscan_polish", 1)
+    d = data.TemporalData(t, Y[:, :, None])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        lml, kf = filters.filter_loop(d, prior, R=R, filter_type="b200_parallel")
+    lml_o, mf_o, Pf_o, _ = ofilters.filter_sequential(oprior, t, Y, R, 1e-5)
+    assert abs(float(lml) - lml_o) <= TOL * abs(lml_o)
+    assert rel(kf['m'], mf_o) < TOL and rel(kf['P'], Pf_o) < TOL
