@@ -94,6 +94,9 @@ int physs_kf_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {
 int64_t physs_kf_wave_series(int32_t d, int32_t disc_mode, int32_t nblk) {
   if (d < 1) return 0;
   if (disc_mode == PHYSS_DISC_MATERN && (nblk < 1 || d % nblk != 0)) return 0;
+  // only the register (d <= 4) and register-tile (d <= 32) families answer the query without launching; the
+  // runtime-sized fallback has no fixed wave
+  if (d > 32 || force_grp(d)) return 0;
   int64_t wave = 0;
   SeqSmoothArgs a{};
   a.B = 1; a.T = 1; a.sbs = 1; a.sts = 1;
