@@ -426,6 +426,30 @@ int physs_cvi_gauss_newton_f64(void* stream, int64_t N, int32_t D, int32_t P, co
  * (parallel_kalman_filter.py:34-71,117-141). */
 int physs_spd_inverse_f64(void* stream, int64_t N, int32_t D, const double* A, double jitter, double* out);
 
+/* ---- Separable spatio-temporal prior, ONE series, large state (BASELINE config 2: d = Ns * ds = 400, m = Ns = 200).
+ * Replaces kf_predict_step / kf_update_step / rts_smoother_step (kalman_filter.py:144-241,439-485;
+ * rts_smoother.py:48-106,162-192) for the prior of kernels/kernel.py:213-265 + ss_utils.py:41-53:
+ *   A_k = I_Ns (x) At_k,  Q_k = Ks (x) Qt_k  (Qt_k = Pinf_t - At_k Pinf_t At_k^T, kernel.py:207-209),
+ *   H = I_Ns (x) [1 0 .. 0]  (state index = s * ds + j: the observation picks the first temporal state of every
+ *   spatial point).  The Kronecker structure is used (predict O(d^2) instead of 2 d^3); Cholesky, triangular
+ *   solves and the rank-2m covariance update are hand-written tile kernels on DMMA.8x8x4 inside persistent
+ *   cooperative kernels -- no cuBLAS / cuSOLVER.
+ *   At, Qt [nA, ds, ds]  temporal transition / process noise per DISTINCT step size, 1 <= ds <= 4
+ *   idx    [T] DEVICE int32: entry k selects the (At, Qt) pair of step k.  Filter: dt[0] = 0 (At = I, Qt = 0),
+ *          dt[k] = t_k - t_{k-1}; smoother: dt[k] = t_{k+1} - t_k (entry T-1 unused).
+ *   Ks [Ns, Ns], m0 [d], P0 [d, d], Y [T, Ns] (NaN = missing), R [., Ns, Ns] with R_tstride elements between
+ *   steps (0 = shared); ws: 16-byte aligned device workspace of physs_kron_workspace_bytes(T, Ns, ds, smoother).
+ * Outputs: mf [T, d], Pf [T, d, d], lml [1];  smoother: project = 0 -> ms [T, d], Ps [T, d, d];
+ * project = 1 -> H ms [T, Ns], H Ps H^T [T, Ns, Ns].  Stream-ordered, NaN on numerical failure. */
+int64_t physs_kron_workspace_bytes(int64_t T, int32_t Ns, int32_t ds, int32_t smoother);
+int physs_kf_filter_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, const double* At, const double* Qt,
+                             const int32_t* idx, const double* Ks, const double* m0, const double* P0,
+                             const double* Y, const double* R, int64_t R_tstride, double jitter, void* ws,
+                             int64_t ws_bytes, double* mf, double* Pf, double* lml);
+int physs_rts_smooth_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, const double* At, const double* Qt,
+                              const int32_t* idx, const double* Ks, const double* mf, const double* Pf,
+                              int32_t project, double jitter, void* ws, int64_t ws_bytes, double* ms, double* Ps);
+
 /* FP64 FMA throughput probe (measurement aid for the FP64-pipe roofline; no reference counterpart).
  * Launches blocks x 256 threads doing iters x 8 independent FMAs each: flops = blocks*256*iters*16. */
 int physs_fp64_probe(void* stream, int32_t blocks, int64_t iters, double* out);

@@ -1,0 +1,878 @@
+// physs_kron.cu -- hand-written large-block Kalman filter / RTS smoother for ONE series of a separable
+// spatio-temporal prior (BASELINE config 2: Matern-3/2 (time) x RBF (space), Ns = 200 -> d = 400, m = 200).
+//
+// Reference: kernels/kernel.py:213-265 and kernels/ss_utils.py:41-53 -- A_k = I (x) A_t, P_inf = K_s (x) P_inf_t,
+// H = I (x) [1 0 ..] (state index = s * ds + j) -- driven through kalman_filter.py:144-241,439-485 and
+// rts_smoother.py:48-106,162-192.  The reference builds the dense d x d Kronecker matrices every step and
+// multiplies them out (2 d^3 per predict); here the structure is used:
+//
+//   predict           P_ = A P A^T + Q          ds x ds block transforms, O(d^2)          (elementwise phase)
+//   innovation        S = M P_[::ds, ::ds] M + R a strided gather                          (same phase)
+//   gain              X = W L^-T, K = X L^-1    blocked Cholesky + blocked substitutions (L L^T = S + jitter I)
+//   covariance        P = P_ - K S K^T = P_ - X X^T + jitter K K^T       one rank-2m update on the tensor cores
+//   lml               second Cholesky of the un-jittered, mask-to-identity S (gaussian.py:72-108)
+//
+// One PERSISTENT cooperative kernel runs all T filter steps: 1 CTA per SM, grid-wide barriers between the four
+// phases of a step; every dense product is a tile GEMM on DMMA.8x8x4 (mma.sync.m8n8k4.f64) with cp.async
+// double-buffered operand tiles.  The smoother splits into a part that is PARALLEL over time -- the gains
+// G_k = Pf_k A^T (A Pf_k A^T + Q + jitter I)^-1 depend on the filter output only: one CTA per time step,
+// Cholesky + two triangular solves -- and the sequential recursion P_s,k = Pf_k + G_k (P_s,k+1 - P_pred,k) G_k^T,
+// two distributed GEMMs per step in a second persistent cooperative kernel.
+//
+// All matrices row-major fp64; NaN on numerical failure (sqrt of a non-positive pivot), status 0.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "physs_core.cuh"
+#include "physs_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace physs {
+namespace kron {
+
+constexpr int NTH = 256;      // threads per CTA: 8 warps = 4 column strips x 2 k-halves
+constexpr int TN = 32;        // tile width
+constexpr int KC = 80;        // k-chunk staged per pipeline stage
+constexpr int LDA = KC + 4;   // 84: (LDA mod 16) == 4 -> the 8 x 4 fragment loads of a half-warp hit 16 distinct bank pairs
+constexpr int LDB = TN + 4;   // 36: same property for the 4 x 8 fragment loads of a [K x N] tile
+constexpr int TMMAX = 40;
+constexpr int SM_A = 2 * TMMAX * LDA;
+constexpr int SM_B = 2 * KC * LDB;             // KC * LDB = 2880 >= TN * LDA = 2688 (an [N x K] tile fits as well)
+constexpr int SM_RED = 4 * 5 * 2 * 32;
+constexpr int SM_DG = 32 * 33 + 32;
+constexpr int SM_DOUBLES = SM_A + SM_B + SM_RED + SM_DG;
+constexpr size_t SM_BYTES = SM_DOUBLES * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(double* dst, const double* src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// D(8x8) += A(8x4, row) * B(4x8, col); lane = 4 g + t holds a = A[g][t], b = B[t][g], c = C[g][2t], C[g][2t+1]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------ tile GEMM
+// C[M x N] = Add + sum_p sg[p] * A_p[M x K_p] * op(B_p),  op(B) = B ([K x N] row-major, nt = 0) or B^T (B is
+// [N x K] row-major, nt = 1).  Output tiles TM x 32 (TM = 8 MT) are dealt round-robin to `ncta` CTAs
+// (cta = 0, ncta = 1: the whole product on this CTA).  lower = 1 (needs M == N, MT == 4): only tiles on or
+// below the diagonal are computed and mirrored into the upper triangle.  Optional second outputs:
+// C2 = C - Sub2 (same shape) and the projection Cp[i / ds][j / ds] = C[i][j] for i % ds == j % ds == 0.
+struct Gemm {
+  const double* A[2]; int lda[2];
+  const double* B[2]; int ldb[2];
+  int K[2]; double sg[2]; int npair;
+  int nt;
+  int M, N;
+  const double* Add; int ldadd;
+  double* C; int ldc;
+  int lower;
+  double* C2; const double* Sub2; int ld2;
+  double* Cp; int ldp; int ds;
+};
+
+// [rows x cols] block (cols even) of a row-major global matrix -> shared memory, zero outside the valid
+// extent vr x vc.  16-byte cp.async when the source allows it, else L2 loads + a shared store.
+__device__ __forceinline__ void load_block(double* dst, int lds, const double* src, int64_t ld, int rows, int cols,
+                                           int vr, int vc, bool vec) {
+  const int upr = cols >> 1;
+  for (int idx = threadIdx.x; idx < rows * upr; idx += NTH) {
+    const int r = idx / upr, c = (idx - r * upr) << 1;
+    double* d = dst + r * lds + c;
+    const double* s = src + (int64_t)r * ld + c;
+    if (vec && r < vr && c + 1 < vc) {
+      cp_async16(d, s);
+    } else {
+      const double x0 = (r < vr && c < vc) ? __ldcg(s) : 0.0;
+      const double x1 = (r < vr && c + 1 < vc) ? __ldcg(s + 1) : 0.0;
+      *reinterpret_cast<double2*>(d) = make_double2(x0, x1);
+    }
+  }
+}
+__device__ __forceinline__ bool vec_ok(const double* p, int64_t ld) {
+  return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld & 1) == 0);
+}
+
+template <int MT>
+__device__ void gemm_tiles(const Gemm& g, int cta, int ncta, double* sm) {
+  constexpr int TM = 8 * MT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int wcol = warp & 3, half = warp >> 2;
+  const int tm = (g.M + TM - 1) / TM, tn = (g.N + TN - 1) / TN;
+  const int ntiles = g.lower ? tm * (tm + 1) / 2 : tm * tn;
+  const int nch0 = (g.K[0] + KC - 1) / KC;
+  const int nch = nch0 + (g.npair > 1 ? (g.K[1] + KC - 1) / KC : 0);
+  const int my_tiles = ntiles > cta ? (ntiles - cta + ncta - 1) / ncta : 0;
+  const int nitems = my_tiles * nch;
+  if (nitems == 0) return;
+  double* As = sm;
+  double* Bs = sm + SM_A;
+  double* Red = sm + SM_A + SM_B;
+  const bool va0 = vec_ok(g.A[0], g.lda[0]), vb0 = vec_ok(g.B[0], g.ldb[0]);
+  const bool va1 = g.npair > 1 && vec_ok(g.A[1], g.lda[1]), vb1 = g.npair > 1 && vec_ok(g.B[1], g.ldb[1]);
+
+  auto tile_origin = [&](int it, int& r0, int& c0) {
+    const int t = cta + (it / nch) * ncta;
+    if (g.lower) {
+      int r = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+      while ((r + 1) * (r + 2) / 2 <= t) ++r;
+      while (r * (r + 1) / 2 > t) --r;
+      r0 = r * TM;
+      c0 = (t - r * (r + 1) / 2) * TN;
+    } else {
+      r0 = (t / tn) * TM;
+      c0 = (t % tn) * TN;
+    }
+  };
+  auto chunk_of = [&](int it, int& pr, int& k0, int& kpad) {
+    int ch = it % nch;
+    pr = ch >= nch0 ? 1 : 0;
+    if (pr) ch -= nch0;
+    k0 = ch * KC;
+    const int kc = min(KC, g.K[pr] - k0);
+    kpad = (kc + 3) & ~3;
+  };
+  auto issue = [&](int it) {
+    int r0, c0, pr, k0, kpad;
+    tile_origin(it, r0, c0);
+    chunk_of(it, pr, k0, kpad);
+    const int buf = it & 1;
+    const int K = g.K[pr];
+    load_block(As + buf * TMMAX * LDA, LDA, g.A[pr] + (int64_t)r0 * g.lda[pr] + k0, g.lda[pr], TM, kpad, g.M - r0,
+               K - k0, pr ? va1 : va0);
+    if (g.nt)
+      load_block(Bs + buf * KC * LDB, LDA, g.B[pr] + (int64_t)c0 * g.ldb[pr] + k0, g.ldb[pr], TN, kpad, g.N - c0,
+                 K - k0, pr ? vb1 : vb0);
+    else
+      load_block(Bs + buf * KC * LDB, LDB, g.B[pr] + (int64_t)k0 * g.ldb[pr] + c0, g.ldb[pr], kpad, TN, K - k0,
+                 g.N - c0, pr ? vb1 : vb0);
+    cp_async_commit();
+  };
+
+  double acc[MT][2];
+  issue(0);
+  for (int it = 0; it < nitems; ++it) {
+    int pr, k0, kpad;
+    chunk_of(it, pr, k0, kpad);
+    const int ch = it % nch;
+    if (ch == 0) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+    }
+    if (it + 1 < nitems) {
+      issue(it + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    {
+      const double* as = As + (it & 1) * TMMAX * LDA;
+      const double* bs = Bs + (it & 1) * KC * LDB;
+      const double sgn = g.sg[pr];
+      const int ksteps = kpad >> 2;
+      for (int kt = half; kt < ksteps; kt += 2) {
+        const double b = g.nt ? bs[(8 * wcol + gq) * LDA + 4 * kt + tq] : bs[(4 * kt + tq) * LDB + 8 * wcol + gq];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const double a = sgn * as[(8 * mt + gq) * LDA + 4 * kt + tq];
+          dmma884(acc[mt][0], acc[mt][1], a, b);
+        }
+      }
+    }
+    __syncthreads();
+    if (ch == nch - 1) {
+      if (half == 1) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          Red[((wcol * MT + mt) * 2 + 0) * 32 + lane] = acc[mt][0];
+          Red[((wcol * MT + mt) * 2 + 1) * 32 + lane] = acc[mt][1];
+        }
+      }
+      __syncthreads();
+      if (half == 0) {
+        int r0, c0;
+        tile_origin(it, r0, c0);
+        const bool mirror = g.lower && r0 > c0;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int row = r0 + 8 * mt + gq;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = c0 + 8 * wcol + 2 * tq + e;
+            if (row < g.M && col < g.N) {
+              double v = acc[mt][e] + Red[((wcol * MT + mt) * 2 + e) * 32 + lane];
+              if (g.Add) v += __ldcg(g.Add + (int64_t)row * g.ldadd + col);
+              g.C[(int64_t)row * g.ldc + col] = v;
+              if (mirror) g.C[(int64_t)col * g.ldc + row] = v;
+              if (g.C2) {
+                g.C2[(int64_t)row * g.ld2 + col] = v - __ldcg(g.Sub2 + (int64_t)row * g.ld2 + col);
+                if (mirror) g.C2[(int64_t)col * g.ld2 + row] = v - __ldcg(g.Sub2 + (int64_t)col * g.ld2 + row);
+              }
+              if (g.Cp && row % g.ds == 0 && col % g.ds == 0) {
+                g.Cp[(int64_t)(row / g.ds) * g.ldp + col / g.ds] = v;
+                if (mirror) g.Cp[(int64_t)(col / g.ds) * g.ldp + row / g.ds] = v;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- 32 x 32 diagonal blocks
+// Factor the w x w block at Lm in place (lower Cholesky factor; strictly upper part of the block zeroed).
+// Leaves the factor padded with the identity in Dg (ld 33) and the reciprocal diagonal in rd[32].
+__device__ void diag_factor(double* Lm, int64_t ld, int w, double* Dg, double* rd) {
+  for (int idx = threadIdx.x; idx < 1024; idx += NTH) {
+    const int r = idx >> 5, c = idx & 31;
+    Dg[r * 33 + c] = (r < w && c <= r) ? __ldcg(Lm + r * ld + c) : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int i = threadIdx.x;
+    for (int j = 0; j < w; ++j) {
+      const double dj = Dg[j * 33 + j];
+      const double rs = fast_rsqrt(dj);          // dj <= 0 -> NaN (the reference's Cholesky of a non-PD matrix)
+      __syncwarp();
+      double lij = 0.0;
+      if (i == j) {
+        Dg[j * 33 + j] = dj * rs;
+        rd[j] = rs;
+      } else if (i > j && i < w) {
+        lij = Dg[i * 33 + j] * rs;
+        Dg[i * 33 + j] = lij;
+      }
+      __syncwarp();
+      if (i > j && i < w) {
+        for (int c = j + 1; c <= i; ++c) Dg[i * 33 + c] = fma(-lij, Dg[c * 33 + j], Dg[i * 33 + c]);
+      }
+      __syncwarp();
+    }
+    if (i >= w) rd[i] = 1.0;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 1024; idx += NTH) {
+    const int r = idx >> 5, c = idx & 31;
+    if (r < w && c < w) Lm[r * ld + c] = (c <= r) ? Dg[r * 33 + c] : 0.0;
+  }
+}
+// Load an already factored diagonal block (identity padding) and its reciprocal diagonal.
+__device__ void diag_load(const double* Lm, int64_t ld, int w, double* Dg, double* rd) {
+  for (int idx = threadIdx.x; idx < 1024; idx += NTH) {
+    const int r = idx >> 5, c = idx & 31;
+    Dg[r * 33 + c] = (r < w && c <= r) ? __ldcg(Lm + r * ld + c) : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) rd[threadIdx.x] = 1.0 / Dg[threadIdx.x * 33 + threadIdx.x];
+  __syncthreads();
+}
+// One thread per row: x L^T = t (forward) or x L = t (backward) against the padded 32 x 32 factor in Dg, in
+// place on nr rows of X (columns [0, w)); optionally duplicated into X2.
+template <bool FWD>
+__device__ void subst_rows(double* X, int64_t ldx, int nr, int w, const double* Dg, const double* rd, double* X2,
+                           int64_t ldx2) {
+  for (int r = threadIdx.x; r < nr; r += NTH) {
+    double t[32];
+    double* xr = X + (int64_t)r * ldx;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) t[c] = (c < w) ? __ldcg(xr + c) : 0.0;
+    if (FWD) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const double xk = t[k] * rd[k];
+        t[k] = xk;
+#pragma unroll
+        for (int c = k + 1; c < 32; ++c) t[c] = fma(-xk, Dg[c * 33 + k], t[c]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 31; k >= 0; --k) {
+        const double xk = t[k] * rd[k];
+        t[k] = xk;
+#pragma unroll
+        for (int c = 0; c < k; ++c) t[c] = fma(-xk, Dg[k * 33 + c], t[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (c < w) {
+        xr[c] = t[c];
+        if (X2) X2[(int64_t)r * ldx2 + c] = t[c];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------ CTA-local blocked factorisation / solves
+// Left-looking blocked Cholesky of the n x n matrix at Lm (lower triangle referenced and overwritten), carried
+// through `nrows` >= n rows: extra rows r >= n come out as r L^-T (an appended right-hand side v^T gives
+// (L^-1 v)^T).  One CTA; everything stays in L2 / global memory, tiles pass through shared memory.
+__device__ void chol_blocked(double* Lm, int64_t ld, int n, int nrows, double* sm) {
+  double* Dg = sm + SM_A + SM_B + SM_RED;
+  double* rd = Dg + 32 * 33;
+  for (int r0 = 0; r0 < n; r0 += 32) {
+    const int w = min(32, n - r0);
+    if (r0 > 0) {
+      Gemm g = {};
+      g.npair = 1; g.nt = 1;
+      g.A[0] = Lm + (int64_t)r0 * ld; g.lda[0] = (int)ld;
+      g.B[0] = Lm + (int64_t)r0 * ld; g.ldb[0] = (int)ld;
+      g.K[0] = r0; g.sg[0] = -1.0;
+      g.M = nrows - r0; g.N = w;
+      g.Add = Lm + (int64_t)r0 * ld + r0; g.ldadd = (int)ld;
+      g.C = Lm + (int64_t)r0 * ld + r0; g.ldc = (int)ld;
+      gemm_tiles<5>(g, 0, 1, sm);
+      __syncthreads();
+    }
+    diag_factor(Lm + (int64_t)r0 * ld + r0, ld, w, Dg, rd);
+    __syncthreads();
+    const int nr = nrows - (r0 + w);
+    if (nr > 0) subst_rows<true>(Lm + (int64_t)(r0 + w) * ld + r0, ld, nr, w, Dg, rd, nullptr, 0);
+    __syncthreads();
+  }
+}
+// X L^T = W in place on R rows of X (n columns), L the factor left by chol_blocked.
+template <int MT>
+__device__ void trsm_fwd(double* X, int64_t ldx, int R, const double* Lm, int64_t ldl, int n, double* sm) {
+  double* Dg = sm + SM_A + SM_B + SM_RED;
+  double* rd = Dg + 32 * 33;
+  for (int r0 = 0; r0 < n; r0 += 32) {
+    const int w = min(32, n - r0);
+    if (r0 > 0) {
+      Gemm g = {};
+      g.npair = 1; g.nt = 1;
+      g.A[0] = X; g.lda[0] = (int)ldx;
+      g.B[0] = Lm + (int64_t)r0 * ldl; g.ldb[0] = (int)ldl;
+      g.K[0] = r0; g.sg[0] = -1.0;
+      g.M = R; g.N = w;
+      g.Add = X + r0; g.ldadd = (int)ldx;
+      g.C = X + r0; g.ldc = (int)ldx;
+      gemm_tiles<MT>(g, 0, 1, sm);
+      __syncthreads();
+    }
+    diag_load(Lm + (int64_t)r0 * ldl + r0, ldl, w, Dg, rd);
+    subst_rows<true>(X + r0, ldx, R, w, Dg, rd, nullptr, 0);
+    __syncthreads();
+  }
+}
+// G L = Y in place on R rows of X; the result is also written to X2 when given.
+template <int MT>
+__device__ void trsm_bwd(double* X, int64_t ldx, int R, const double* Lm, int64_t ldl, int n, double* X2, int64_t ldx2,
+                         double* sm) {
+  double* Dg = sm + SM_A + SM_B + SM_RED;
+  double* rd = Dg + 32 * 33;
+  const int nb = (n + 31) / 32;
+  for (int j = nb - 1; j >= 0; --j) {
+    const int r0 = 32 * j, w = min(32, n - r0), r1 = r0 + w;
+    if (r1 < n) {
+      Gemm g = {};
+      g.npair = 1; g.nt = 0;
+      g.A[0] = X + r1; g.lda[0] = (int)ldx;
+      g.B[0] = Lm + (int64_t)r1 * ldl + r0; g.ldb[0] = (int)ldl;
+      g.K[0] = n - r1; g.sg[0] = -1.0;
+      g.M = R; g.N = w;
+      g.Add = X + r0; g.ldadd = (int)ldx;
+      g.C = X + r0; g.ldc = (int)ldx;
+      gemm_tiles<MT>(g, 0, 1, sm);
+      __syncthreads();
+    }
+    diag_load(Lm + (int64_t)r0 * ldl + r0, ldl, w, Dg, rd);
+    subst_rows<false>(X + r0, ldx, R, w, Dg, rd, X2 ? X2 + r0 : nullptr, ldx2);
+    __syncthreads();
+  }
+}
+
+// block reduction of one value over the CTA (result valid in thread 0)
+__device__ double block_sum(double v, double* scratch) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < NTH / 32; ++i) s += scratch[i];
+  return s;
+}
+
+constexpr int DSMAX = 4;
+
+// ------------------------------------------------------------------------------------------- filter
+struct FilterArgs {
+  int64_t T;
+  int Ns, ds, d;
+  const double* At; const double* Qt; const int32_t* idx;
+  const double* Ks; const double* m0; const double* P0;
+  const double* Y; const double* R; int64_t R_ts;
+  double jitter;
+  double* mf; double* Pf; double* lml;
+  double* Pp; double* W; double* Kb; double* SjA; double* SmA; double* mp; double* acc;
+};
+
+__global__ void __launch_bounds__(NTH, 1) kron_filter_kernel(const FilterArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  cg::grid_group grid = cg::this_grid();
+  const int cta = blockIdx.x, ncta = gridDim.x, tid = threadIdx.x;
+  const int Ns = p.Ns, ds = p.ds, d = p.d, m = p.Ns;
+  const int64_t gt = (int64_t)cta * NTH + tid, gstride = (int64_t)ncta * NTH;
+  const int cta_lml = ncta > 1 ? 1 : 0;
+  if (cta == cta_lml && tid == 0) p.acc[0] = 0.0;
+  for (int64_t k = 0; k < p.T; ++k) {
+    const double* At = p.At + (int64_t)p.idx[k] * ds * ds;
+    const double* Qt = p.Qt + (int64_t)p.idx[k] * ds * ds;
+    const double* Pprev = k ? p.Pf + (k - 1) * (int64_t)d * d : p.P0;
+    const double* mprev = k ? p.mf + (k - 1) * (int64_t)d : p.m0;
+    const double* y = p.Y + k * m;
+    const double* Rk = p.R + k * p.R_ts;
+    // ---- phase 1: predict, innovation covariance (jittered and mask-to-identity copies), masked P_ H^T
+    double at[DSMAX][DSMAX], qt[DSMAX][DSMAX];
+#pragma unroll
+    for (int a = 0; a < DSMAX; ++a)
+#pragma unroll
+      for (int b = 0; b < DSMAX; ++b) {
+        at[a][b] = (a < ds && b < ds) ? At[a * ds + b] : 0.0;
+        qt[a][b] = (a < ds && b < ds) ? Qt[a * ds + b] : 0.0;
+      }
+    for (int64_t idx = gt; idx < (int64_t)Ns * Ns; idx += gstride) {
+      const int I = (int)(idx / Ns), J = (int)(idx - (int64_t)I * Ns);
+      double blk[DSMAX][DSMAX], tmp[DSMAX][DSMAX];
+#pragma unroll
+      for (int a = 0; a < DSMAX; ++a)
+#pragma unroll
+        for (int b = 0; b < DSMAX; ++b)
+          blk[a][b] = (a < ds && b < ds) ? __ldcg(Pprev + (int64_t)(I * ds + a) * d + J * ds + b) : 0.0;
+#pragma unroll
+      for (int a = 0; a < DSMAX; ++a)
+#pragma unroll
+        for (int b = 0; b < DSMAX; ++b) {
+          double s = 0.0;
+#pragma unroll
+          for (int c = 0; c < DSMAX; ++c) s = fma(at[a][c], blk[c][b], s);
+          tmp[a][b] = s;
+        }
+      const double ks = p.Ks[(int64_t)I * Ns + J];
+      const double yi = y[I], yj = y[J];
+      const bool oi = !(yi != yi), oj = !(yj != yj);
+#pragma unroll
+      for (int a = 0; a < DSMAX; ++a)
+#pragma unroll
+        for (int b = 0; b < DSMAX; ++b) {
+          double s = 0.0;
+#pragma unroll
+          for (int c = 0; c < DSMAX; ++c) s = fma(tmp[a][c], at[b][c], s);
+          blk[a][b] = s + ks * qt[a][b];
+          if (a < ds && b < ds) p.Pp[(int64_t)(I * ds + a) * d + J * ds + b] = blk[a][b];
+        }
+      const double s = ((oi && oj) ? blk[0][0] : 0.0) + Rk[(int64_t)I * Ns + J];
+      p.SjA[(int64_t)I * m + J] = s + (I == J ? p.jitter : 0.0);
+      p.SmA[(int64_t)I * m + J] = (oi && oj) ? s : (I == J ? 1.0 : 0.0);
+#pragma unroll
+      for (int a = 0; a < DSMAX; ++a)
+        if (a < ds) p.W[(int64_t)(I * ds + a) * m + J] = oj ? blk[a][0] : 0.0;
+    }
+    for (int64_t I = gt; I < Ns; I += gstride) {
+      double mu0 = 0.0;
+      for (int a = 0; a < ds; ++a) {
+        double s = 0.0;
+        for (int b = 0; b < ds; ++b) s = fma(at[a][b], __ldcg(mprev + I * ds + b), s);
+        p.mp[I * ds + a] = s;
+        if (a == 0) mu0 = s;
+      }
+      const double yi = y[I];
+      const double v = (yi != yi) ? 0.0 : yi - mu0;
+      p.SjA[(int64_t)m * m + I] = v;
+      p.SmA[(int64_t)m * m + I] = v;
+    }
+    grid.sync();
+    // ---- phase 2: the two Cholesky factorisations, each with the innovation appended as an extra row
+    if (cta == 0) chol_blocked(p.SjA, m, m, m + 1, sm);
+    if (cta == cta_lml) {
+      if (cta_lml != 0) chol_blocked(p.SmA, m, m, m + 1, sm);
+      else { __syncthreads(); chol_blocked(p.SmA, m, m, m + 1, sm); }
+      double ld = 0.0, mh = 0.0, no = 0.0;
+      for (int a = tid; a < m; a += NTH) {
+        ld += log(__ldcg(p.SmA + (int64_t)a * m + a));
+        const double u = __ldcg(p.SmA + (int64_t)m * m + a);
+        mh = fma(u, u, mh);
+        const double ya = y[a];
+        no += (ya != ya) ? 0.0 : 1.0;
+      }
+      double* scr = sm + SM_A + SM_B;
+      ld = block_sum(ld, scr);
+      mh = block_sum(mh, scr);
+      no = block_sum(no, scr);
+      if (tid == 0) p.acc[0] += -0.5 * (no * 1.8378770664093454835606594728112 + 2.0 * ld + mh);
+    }
+    grid.sync();
+    // ---- phase 3: rows of X = W L^-T (in place in W), the mean update, rows of K = X L^-1
+    for (int rb = cta; rb * 8 < d; rb += ncta) {
+      const int i0 = rb * 8, R = min(8, d - i0);
+      double* Xr = p.W + (int64_t)i0 * m;
+      trsm_fwd<1>(Xr, m, R, p.SjA, m, m, sm);
+      {
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp < R) {
+          double s = 0.0;
+          for (int a = lane; a < m; a += 32) s = fma(__ldcg(Xr + (int64_t)warp * m + a), __ldcg(p.SjA + (int64_t)m * m + a), s);
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0) p.mf[k * (int64_t)d + i0 + warp] = p.mp[i0 + warp] + s;
+        }
+      }
+      if (p.jitter != 0.0) {
+        double* Kr = p.Kb + (int64_t)i0 * m;
+        for (int idx = tid; idx < R * m; idx += NTH) Kr[idx] = __ldcg(Xr + idx);
+        __syncthreads();
+        trsm_bwd<1>(Kr, m, R, p.SjA, m, m, nullptr, 0, sm);
+      }
+    }
+    grid.sync();
+    // ---- phase 4: P = P_ - X X^T + jitter K K^T  (== P_ - K S K^T with the un-jittered S)
+    {
+      Gemm g = {};
+      g.nt = 1;
+      g.A[0] = p.W; g.lda[0] = m; g.B[0] = p.W; g.ldb[0] = m; g.K[0] = m; g.sg[0] = -1.0;
+      g.npair = 1;
+      if (p.jitter != 0.0) {
+        g.A[1] = p.Kb; g.lda[1] = m; g.B[1] = p.Kb; g.ldb[1] = m; g.K[1] = m; g.sg[1] = p.jitter;
+        g.npair = 2;
+      }
+      g.M = d; g.N = d;
+      g.Add = p.Pp; g.ldadd = d;
+      g.C = p.Pf + k * (int64_t)d * d; g.ldc = d;
+      g.lower = 1;
+      gemm_tiles<4>(g, cta, ncta, sm);
+    }
+    grid.sync();
+  }
+  if (cta == cta_lml && tid == 0) p.lml[0] = p.acc[0];
+}
+
+// ------------------------------------------------------------------------------------------ smoother
+struct GainArgs {
+  int64_t k_lo, k_hi;       // steps of this time chunk (inclusive)
+  int Ns, ds, d;
+  const double* At; const double* Qt; const int32_t* idx;
+  const double* Ks; const double* Pf;
+  double jitter;
+  double* Gc; double* Ppc;  // [k_hi - k_lo + 1, d, d] gains and (un-jittered) predicted covariances
+  double* scratch;          // 2 d^2 doubles per CTA
+};
+
+// parallel over time: G_k = Pf_k A^T (A Pf_k A^T + Q + jitter I)^-1, one CTA per step
+__global__ void __launch_bounds__(NTH, 1) kron_gain_kernel(const GainArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, Ns = p.Ns, ds = p.ds, d = p.d;
+  double* Wk = p.scratch + (int64_t)blockIdx.x * 2 * d * d;
+  double* Lk = Wk + (int64_t)d * d;
+  for (int64_t k = p.k_lo + blockIdx.x; k <= p.k_hi; k += gridDim.x) {
+    const double* At = p.At + (int64_t)p.idx[k] * ds * ds;
+    const double* Qt = p.Qt + (int64_t)p.idx[k] * ds * ds;
+    const double* Pfk = p.Pf + k * (int64_t)d * d;
+    double* Ppk = p.Ppc + (k - p.k_lo) * (int64_t)d * d;
+    double at[DSMAX][DSMAX], qt[DSMAX][DSMAX];
+#pragma unroll
+    for (int a = 0; a < DSMAX; ++a)
+#pragma unroll
+      for (int b = 0; b < DSMAX; ++b) {
+        at[a][b] = (a < ds && b < ds) ? At[a * ds + b] : 0.0;
+        qt[a][b] = (a < ds && b < ds) ? Qt[a * ds + b] : 0.0;
+      }
+    for (int idx = tid; idx < Ns * Ns; idx += NTH) {
+      const int I = idx / Ns, J = idx - I * Ns;
+      double blk[DSMAX][DSMAX], wb[DSMAX][DSMAX];
+#pragma unroll
+      for (int a = 0; a < DSMAX; ++a)
+#pragma unroll
+        for (int b = 0; b < DSMAX; ++b)
+          blk[a][b] = (a < ds && b < ds) ? __ldcg(Pfk + (int64_t)(I * ds + a) * d + J * ds + b) : 0.0;
+#pragma unroll
+      for (int a = 0; a < DSMAX; ++a)
+#pragma unroll
+        for (int b = 0; b < DSMAX; ++b) {
+          double s = 0.0;
+#pragma unroll
+          for (int c = 0; c < DSMAX; ++c) s = fma(blk[a][c], at[b][c], s);     // (Pf A^T) block
+          wb[a][b] = s;
+        }
+      const double ks = p.Ks[(int64_t)I * Ns + J];
+#pragma unroll
+      for (int a = 0; a < DSMAX; ++a)
+#pragma unroll
+        for (int b = 0; b < DSMAX; ++b) {
+          double s = 0.0;
+#pragma unroll
+          for (int c = 0; c < DSMAX; ++c) s = fma(at[a][c], wb[c][b], s);
+          s += ks * qt[a][b];
+          if (a < ds && b < ds) {
+            const int64_t o = (int64_t)(I * ds + a) * d + J * ds + b;
+            Wk[o] = wb[a][b];
+            Ppk[o] = s;
+            Lk[o] = s + ((I == J && a == b) ? p.jitter : 0.0);
+          }
+        }
+    }
+    __syncthreads();
+    chol_blocked(Lk, d, d, d, sm);
+    trsm_fwd<5>(Wk, d, d, Lk, d, d, sm);
+    trsm_bwd<5>(Wk, d, d, Lk, d, d, p.Gc + (k - p.k_lo) * (int64_t)d * d, d, sm);
+    __syncthreads();
+  }
+}
+
+struct RecArgs {
+  int64_t k_lo, k_hi;
+  int Ns, ds, d;
+  const double* At; const int32_t* idx;
+  const double* mf; const double* Pf;
+  const double* Gc; const double* Ppc;
+  int project;                 // 1: outputs are H ms [T, Ns], H Ps H^T [T, Ns, Ns]; 0: full state
+  double* ms_out; double* Ps_out;
+  double* ringP; double* ringm; double* dP; double* T1;
+};
+__device__ __forceinline__ double* ps_state(const RecArgs& p, int64_t k) {
+  return p.project ? p.ringP + (k & 1) * (int64_t)p.d * p.d : p.Ps_out + k * (int64_t)p.d * p.d;
+}
+
+// the recursion through time: P_s,k = Pf_k + G_k (P_s,k+1 - P_pred,k) G_k^T, m_s,k = mf_k + G_k (m_s,k+1 - A mf_k)
+__global__ void __launch_bounds__(NTH, 1) kron_smooth_rec_kernel(const RecArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  cg::grid_group grid = cg::this_grid();
+  const int cta = blockIdx.x, ncta = gridDim.x, tid = threadIdx.x;
+  const int Ns = p.Ns, ds = p.ds, d = p.d;
+  const int64_t dd = (int64_t)d * d;
+  const int64_t gt = (int64_t)cta * NTH + tid, gstride = (int64_t)ncta * NTH;
+  {
+    const double* Psn = ps_state(p, p.k_hi + 1);
+    const double* Pp = p.Ppc + (p.k_hi - p.k_lo) * dd;
+    for (int64_t i = gt; i < dd; i += gstride) p.dP[i] = __ldcg(Psn + i) - __ldcg(Pp + i);
+  }
+  grid.sync();
+  for (int64_t k = p.k_hi; k >= p.k_lo; --k) {
+    const double* G = p.Gc + (k - p.k_lo) * dd;
+    {
+      Gemm g = {};
+      g.npair = 1; g.nt = 0;
+      g.A[0] = G; g.lda[0] = d; g.B[0] = p.dP; g.ldb[0] = d; g.K[0] = d; g.sg[0] = 1.0;
+      g.M = d; g.N = d;
+      g.C = p.T1; g.ldc = d;
+      gemm_tiles<5>(g, cta, ncta, sm);
+    }
+    {
+      // mean: one warp per row, rows dealt round-robin over all warps of the grid (from the back, so the CTAs
+      // that hold no second GEMM tile take them)
+      const double* At = p.At + (int64_t)p.idx[k] * ds * ds;
+      const double* mfk = p.mf + k * (int64_t)d;
+      const double* msn = p.ringm + ((k + 1) & 1) * (int64_t)d;
+      double* msk = p.ringm + (k & 1) * (int64_t)d;
+      const int lane = tid & 31;
+      const int gw = (ncta - 1 - cta) * (NTH / 32) + (tid >> 5), nw = ncta * (NTH / 32);
+      for (int row = gw; row < d; row += nw) {
+        double s = 0.0;
+        for (int c = lane; c < d; c += 32) {
+          const int J = c / ds, b = c - J * ds;
+          double am = 0.0;
+          for (int b2 = 0; b2 < ds; ++b2) am = fma(At[b * ds + b2], mfk[J * ds + b2], am);
+          s = fma(__ldcg(G + (int64_t)row * d + c), __ldcg(msn + c) - am, s);
+        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+          const double v = mfk[row] + s;
+          msk[row] = v;
+          if (!p.project) p.ms_out[k * (int64_t)d + row] = v;
+          else if (row % ds == 0) p.ms_out[k * (int64_t)Ns + row / ds] = v;
+        }
+      }
+    }
+    grid.sync();
+    {
+      Gemm g = {};
+      g.npair = 1; g.nt = 1;
+      g.A[0] = p.T1; g.lda[0] = d; g.B[0] = G; g.ldb[0] = d; g.K[0] = d; g.sg[0] = 1.0;
+      g.M = d; g.N = d;
+      g.Add = p.Pf + k * dd; g.ldadd = d;
+      g.C = ps_state(p, k); g.ldc = d;
+      g.lower = 1;
+      if (k > p.k_lo) { g.C2 = p.dP; g.Sub2 = p.Ppc + (k - 1 - p.k_lo) * dd; g.ld2 = d; }
+      if (p.project) { g.Cp = p.Ps_out + k * (int64_t)Ns * Ns; g.ldp = Ns; g.ds = ds; }
+      gemm_tiles<4>(g, cta, ncta, sm);
+    }
+    grid.sync();
+  }
+}
+
+// last step: smoothed == filtered
+__global__ void kron_emit_last_kernel(const RecArgs p, int64_t T) {
+  const int d = p.d, ds = p.ds, Ns = p.Ns;
+  const int64_t dd = (int64_t)d * d, k = T - 1;
+  const double* Pfk = p.Pf + k * dd;
+  const double* mfk = p.mf + k * (int64_t)d;
+  double* Pst = ps_state(p, k);
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = gt; i < dd; i += gs) {
+    const double v = Pfk[i];
+    Pst[i] = v;
+    if (p.project) {
+      const int r = (int)(i / d), c = (int)(i - (int64_t)r * d);
+      if (r % ds == 0 && c % ds == 0) p.Ps_out[k * (int64_t)Ns * Ns + (int64_t)(r / ds) * Ns + c / ds] = v;
+    }
+  }
+  for (int64_t i = gt; i < d; i += gs) {
+    const double v = mfk[i];
+    p.ringm[(k & 1) * (int64_t)d + i] = v;
+    if (!p.project) p.ms_out[k * (int64_t)d + i] = v;
+    else if (i % ds == 0) p.ms_out[k * (int64_t)Ns + i / ds] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------------------- host side
+struct Dev {
+  int sms = 0, coop = 0;
+  int filter_blocks = 0, rec_blocks = 0, gain_blocks = 0;
+};
+int device_setup(Dev& dv) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_status(e, "kron: cudaGetDevice");
+  cudaDeviceGetAttribute(&dv.sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&dv.coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!dv.coop) return set_error(PHYSS_ERR_UNSUPPORTED, "kron: device does not support cooperative launches");
+  e = cudaFuncSetAttribute(kron_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kron_gain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kron_smooth_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BYTES);
+  if (e != cudaSuccess) return cuda_status(e, "kron: cudaFuncSetAttribute(shared memory)");
+  int b = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kron_filter_kernel, NTH, SM_BYTES);
+  if (e != cudaSuccess || b < 1) return cuda_status(e == cudaSuccess ? cudaErrorLaunchOutOfResources : e, "kron: occupancy (filter)");
+  dv.filter_blocks = dv.sms;            // one CTA per SM: the tile counts are sized for it
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kron_smooth_rec_kernel, NTH, SM_BYTES);
+  if (e != cudaSuccess || b < 1) return cuda_status(e == cudaSuccess ? cudaErrorLaunchOutOfResources : e, "kron: occupancy (smoother)");
+  dv.rec_blocks = dv.sms;
+  dv.gain_blocks = dv.sms;
+  return PHYSS_OK;
+}
+
+constexpr int64_t GAIN_CHUNK_WAVES = 4;   // time steps per smoother chunk = 4 x (CTAs of the gain kernel)
+
+inline int64_t align2(int64_t n) { return (n + 1) & ~(int64_t)1; }
+
+struct FilterWs { int64_t Pp, W, Kb, SjA, SmA, mp, acc, total; };
+FilterWs filter_ws(int Ns, int ds) {
+  const int64_t d = (int64_t)Ns * ds, m = Ns;
+  FilterWs w{};
+  int64_t o = 0;
+  w.Pp = o; o += align2(d * d);
+  w.W = o; o += align2(d * m);
+  w.Kb = o; o += align2(d * m);
+  w.SjA = o; o += align2((m + 1) * m);
+  w.SmA = o; o += align2((m + 1) * m);
+  w.mp = o; o += align2(d);
+  w.acc = o; o += 2;
+  w.total = o;
+  return w;
+}
+struct SmoothWs { int64_t Gc, Ppc, scratch, ringP, ringm, dP, T1, total, chunk; };
+SmoothWs smooth_ws(int Ns, int ds, int64_t T, int gain_blocks) {
+  const int64_t d = (int64_t)Ns * ds, dd = d * d;
+  SmoothWs w{};
+  w.chunk = GAIN_CHUNK_WAVES * gain_blocks;
+  if (w.chunk > T - 1) w.chunk = T - 1 > 0 ? T - 1 : 1;
+  int64_t o = 0;
+  w.Gc = o; o += w.chunk * dd;
+  w.Ppc = o; o += w.chunk * dd;
+  w.scratch = o; o += (int64_t)gain_blocks * 2 * dd;
+  w.ringP = o; o += 2 * dd;
+  w.ringm = o; o += align2(2 * d);
+  w.dP = o; o += dd;
+  w.T1 = o; o += dd;
+  w.total = o;
+  return w;
+}
+
+}  // namespace kron
+}  // namespace physs
+
+using namespace physs;
+using namespace physs::kron;
+
+extern "C" {
+
+int64_t physs_kron_workspace_bytes(int64_t T, int32_t Ns, int32_t ds, int32_t smoother) {
+  if (T < 1 || Ns < 1 || ds < 1 || ds > DSMAX) return 0;
+  if (!smoother) return 8 * filter_ws(Ns, ds).total + 16;
+  Dev dv;
+  if (device_setup(dv) != PHYSS_OK) return 0;
+  return 8 * smooth_ws(Ns, ds, T, dv.gain_blocks).total + 16;
+}
+
+int physs_kf_filter_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, const double* At, const double* Qt,
+                             const int32_t* idx, const double* Ks, const double* m0, const double* P0,
+                             const double* Y, const double* R, int64_t R_tstride, double jitter, void* ws,
+                             int64_t ws_bytes, double* mf, double* Pf, double* lml) {
+  if (T < 1 || Ns < 1 || ds < 1 || ds > DSMAX) return set_error(PHYSS_ERR_BAD_ARG, "kron filter: bad sizes (1 <= ds <= 4)");
+  if (!At || !Qt || !idx || !Ks || !m0 || !P0 || !Y || !R || !ws || !mf || !Pf || !lml)
+    return set_error(PHYSS_ERR_BAD_ARG, "kron filter: null required pointer");
+  if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return set_error(PHYSS_ERR_BAD_ARG, "kron filter: workspace must be 16-byte aligned");
+  const FilterWs L = filter_ws(Ns, ds);
+  if (ws_bytes < 8 * L.total) return set_error(PHYSS_ERR_BAD_ARG, "kron filter: workspace too small");
+  Dev dv;
+  if (int rc = device_setup(dv)) return rc;
+  double* w = static_cast<double*>(ws);
+  FilterArgs a{};
+  a.T = T; a.Ns = Ns; a.ds = ds; a.d = Ns * ds;
+  a.At = At; a.Qt = Qt; a.idx = idx; a.Ks = Ks; a.m0 = m0; a.P0 = P0; a.Y = Y; a.R = R; a.R_ts = R_tstride;
+  a.jitter = jitter; a.mf = mf; a.Pf = Pf; a.lml = lml;
+  a.Pp = w + L.Pp; a.W = w + L.W; a.Kb = w + L.Kb; a.SjA = w + L.SjA; a.SmA = w + L.SmA; a.mp = w + L.mp; a.acc = w + L.acc;
+  void* args[] = {&a};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)kron_filter_kernel, dim3(dv.filter_blocks), dim3(NTH), args,
+                                              SM_BYTES, (cudaStream_t)stream);
+  return cuda_status(e, "kron_filter_kernel launch");
+}
+
+int physs_rts_smooth_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, const double* At, const double* Qt,
+                              const int32_t* idx, const double* Ks, const double* mf, const double* Pf,
+                              int32_t project, double jitter, void* ws, int64_t ws_bytes, double* ms, double* Ps) {
+  if (T < 1 || Ns < 1 || ds < 1 || ds > DSMAX) return set_error(PHYSS_ERR_BAD_ARG, "kron smoother: bad sizes (1 <= ds <= 4)");
+  if (!At || !Qt || !idx || !Ks || !mf || !Pf || !ws || !ms || !Ps)
+    return set_error(PHYSS_ERR_BAD_ARG, "kron smoother: null required pointer");
+  if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return set_error(PHYSS_ERR_BAD_ARG, "kron smoother: workspace must be 16-byte aligned");
+  Dev dv;
+  if (int rc = device_setup(dv)) return rc;
+  const SmoothWs L = smooth_ws(Ns, ds, T, dv.gain_blocks);
+  if (ws_bytes < 8 * L.total) return set_error(PHYSS_ERR_BAD_ARG, "kron smoother: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* w = static_cast<double*>(ws);
+  const int d = Ns * ds;
+  RecArgs r{};
+  r.Ns = Ns; r.ds = ds; r.d = d; r.At = At; r.idx = idx; r.mf = mf; r.Pf = Pf;
+  r.Gc = w + L.Gc; r.Ppc = w + L.Ppc; r.project = project ? 1 : 0; r.ms_out = ms; r.Ps_out = Ps;
+  r.ringP = w + L.ringP; r.ringm = w + L.ringm; r.dP = w + L.dP; r.T1 = w + L.T1;
+  kron_emit_last_kernel<<<dv.sms, 256, 0, st>>>(r, T);
+  GainArgs g{};
+  g.Ns = Ns; g.ds = ds; g.d = d; g.At = At; g.Qt = Qt; g.idx = idx; g.Ks = Ks; g.Pf = Pf; g.jitter = jitter;
+  g.Gc = w + L.Gc; g.Ppc = w + L.Ppc; g.scratch = w + L.scratch;
+  for (int64_t k_hi = T - 2; k_hi >= 0;) {
+    const int64_t k_lo = k_hi - L.chunk + 1 > 0 ? k_hi - L.chunk + 1 : 0;
+    g.k_lo = k_lo; g.k_hi = k_hi;
+    const int64_t n = k_hi - k_lo + 1;
+    const int gb = (int)(n < dv.gain_blocks ? n : dv.gain_blocks);
+    kron_gain_kernel<<<gb, NTH, SM_BYTES, st>>>(g);
+    r.k_lo = k_lo; r.k_hi = k_hi;
+    void* args[] = {&r};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)kron_smooth_rec_kernel, dim3(dv.rec_blocks), dim3(NTH), args,
+                                                SM_BYTES, st);
+    if (e != cudaSuccess) return cuda_status(e, "kron_smooth_rec_kernel launch");
+    k_hi = k_lo - 1;
+  }
+  return cuda_status(cudaGetLastError(), "kron smoother launches");
+}
+
+}  // extern "C"

@@ -112,6 +112,38 @@ def lower_prior_big(prior, X_s, dt, dev):
     return ops.BigDisc(_to_dev(A_u, dev), _to_dev(Q_u, dev), inv), _to_dev(m_inf, dev), _to_dev(P_inf, dev), H
 
 
+def _kron_parts(prior, X_s):
+    """(temporal kernel, Ks, ds) when `prior` is a plain LTI_SDE over ONE separable spatio-temporal kernel
+    (kernels/kernel.py:213-265) observed through H = I (x) [1 0 ..] -- the shape the hand-written large-block
+    kernels (physs_kf_filter_kron_f64) cover -- else None."""
+    from .kernels import SpatioTemporalSeperableKernel
+    from .sdes import LTI_SDE
+    if not settings.kron_kernels or type(prior) is not LTI_SDE or len(prior.gp.parent) != 1:
+        return None
+    k = prior.gp.parent[0].kernel
+    if not isinstance(k, SpatioTemporalSeperableKernel):
+        return None
+    h = np.asarray(k.k1.to_ss()[3], np.float64).reshape(-1)
+    ds = h.shape[0]
+    if ds > 4 or h[0] != 1.0 or np.any(h[1:] != 0.0):
+        return None
+    return k.k1, k.Ks, ds
+
+
+def lower_prior_kron(parts, prior, X_s, dt, dev):
+    """Separable route: the TEMPORAL kernel's expm / Q (ds x ds) once per distinct step size; the d x d Kronecker
+    products the reference builds every step (kernel.py:247-254) are never formed."""
+    k1, Ks, ds = parts
+    Pinf_t = np.asarray(k1.to_ss()[5], np.float64)
+    dt_np = _np(dt).reshape(-1)
+    uniq, inv = np.unique(dt_np, return_inverse=True)
+    At = np.stack([np.asarray(k1.expm(float(u)), np.float64) for u in uniq])
+    Qt = np.stack([np.asarray(k1.Q(float(u), At[i], Pinf_t), np.float64) for i, u in enumerate(uniq)])
+    m_inf = np.asarray(prior.m_inf(None, X_s, None), np.float64).reshape(-1)
+    disc = ops.KronDisc(_to_dev(At, dev), _to_dev(Qt, dev), torch.as_tensor(inv.astype(np.int32)), _to_dev(Ks, dev))
+    return disc, _to_dev(m_inf, dev), _to_dev(np.kron(Ks, Pinf_t), dev)
+
+
 def _use_big(prior, X_s, batched_B):
     if isinstance(prior, BatchedMaternSDE) or batched_B != 1:
         return False
@@ -142,14 +174,21 @@ def _filter_impl(parallel, data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, 
     Yd = _to_dev(Y, dev)
     one = Yd.dim() == 3 or (Yd.dim() == 4 and Yd.shape[0] == 1)
     if one and _use_big(prior, X_s, 1):
-        # one series with a large state (BASELINE config 2): cuBLAS / cuSOLVER-backed path
-        disc, m0, P0, H = lower_prior_big(prior, X_s, _to_dev(dt, dev), dev)
+        # one series with a large state (BASELINE config 2)
         R = _to_dev(lik_mat, dev)
         lead = Yd.dim() == 4
         if lead:
             Yd = Yd[0]
             R = R[0] if R.dim() == 4 else R
-        lml, mf, Pf = ops.kf_filter_big(Yd[..., 0], R, _to_dev(H, dev), m0, P0, disc, jitter=settings.jitter)
+        parts = _kron_parts(prior, X_s)
+        if parts is not None:
+            # separable prior: hand-written persistent kernels that use the Kronecker structure
+            disc, m0, P0 = lower_prior_kron(parts, prior, X_s, _to_dev(dt, dev), dev)
+            lml, mf, Pf = ops.kf_filter_kron(Yd[..., 0], R, m0, P0, disc, jitter=settings.jitter)
+        else:
+            # any other large prior: dense A, Q through the cuBLAS / cuSOLVER-backed library path
+            disc, m0, P0, H = lower_prior_big(prior, X_s, _to_dev(dt, dev), dev)
+            lml, mf, Pf = ops.kf_filter_big(Yd[..., 0], R, _to_dev(H, dev), m0, P0, disc, jitter=settings.jitter)
         if lead:
             return lml[None], {'m': mf[None, ..., None], 'P': Pf[None]}
         return lml, {'m': mf[..., None], 'P': Pf}
@@ -246,11 +285,17 @@ def _smoother_impl(parallel, data, model, filter_res, dt, X_t, X_s, full_state):
     Pf = _to_dev(filter_res['P'], dev)
     one = mf.dim() == 2 or (mf.dim() == 3 and mf.shape[0] == 1)
     if one and _use_big(model, X_s, 1):
-        disc, _, _, H = lower_prior_big(model, X_s, _to_dev(dt, dev), dev)
-        Hout = None if (full_state or _is_identity(H)) else _to_dev(H, dev)
         lead = mf.dim() == 3
-        ms, Ps = ops.rts_smooth_big(mf[0] if lead else mf, Pf[0] if lead else Pf, disc, Hout=Hout,
-                                    jitter=settings.jitter)
+        parts = _kron_parts(model, X_s)
+        if parts is not None:
+            disc, _, _ = lower_prior_kron(parts, model, X_s, _to_dev(dt, dev), dev)
+            ms, Ps = ops.rts_smooth_kron(mf[0] if lead else mf, Pf[0] if lead else Pf, disc,
+                                         project=not full_state, jitter=settings.jitter)
+        else:
+            disc, _, _, H = lower_prior_big(model, X_s, _to_dev(dt, dev), dev)
+            Hout = None if (full_state or _is_identity(H)) else _to_dev(H, dev)
+            ms, Ps = ops.rts_smooth_big(mf[0] if lead else mf, Pf[0] if lead else Pf, disc, Hout=Hout,
+                                        jitter=settings.jitter)
         if lead:
             return ms[None, ..., None], Ps[None]
         return ms[..., None], Ps

@@ -683,3 +683,73 @@ def rts_smooth_big(mf, Pf, disc, Hout=None, jitter=None, stream=None):
                                           ws.numel() * 8, ms.data_ptr(), Ps.data_ptr())
     _lib.check_big(st, "physs_rts_smooth_big_f64")
     return ms, Ps
+
+
+# ------------------------------------------------------- separable spatio-temporal prior, hand-written kernels
+class KronDisc:
+    """Discretisation of the separable spatio-temporal route (include/physs_b200.h, physs_kf_filter_kron_f64):
+    temporal At, Qt [nA, ds, ds] per DISTINCT step size, a DEVICE int32 index [T] selecting the pair of every
+    step, and the spatial Gram matrix Ks [Ns, Ns]."""
+
+    def __init__(self, At, Qt, index, Ks):
+        self.At, self.Qt = _dev(At, "At").contiguous(), _dev(Qt, "Qt").contiguous()
+        self.Ks = _dev(Ks, "Ks").contiguous()
+        self.index = index.to(device=self.At.device, dtype=torch.int32).contiguous()
+        self.ds = int(self.At.shape[-1])
+        self.Ns = int(self.Ks.shape[-1])
+
+
+def _kron_ws(T, Ns, ds, smoother, dev):
+    with torch.cuda.device(dev):
+        n = _lib.load().physs_kron_workspace_bytes(T, Ns, ds, 1 if smoother else 0)
+    if n <= 0:
+        raise _lib.PhyssError("physs_kron_workspace_bytes failed: " + (_lib.load().physs_last_error() or b"").decode())
+    return torch.empty((n // 8 + 2,), dtype=torch.float64, device=dev)
+
+
+def kf_filter_kron(Y, R, m0, P0, disc, jitter=None, stream=None):
+    """One series, separable prior: Y [T, Ns], R [T|1, Ns, Ns], m0 [d], P0 [d, d] -> (lml [], mf [T, d], Pf [T, d, d])."""
+    lib = _lib.load()
+    Y, m0, P0 = (_dev(x, n).contiguous() for x, n in ((Y, "Y"), (m0, "m0"), (P0, "P0")))
+    R = _dev(R, "R").contiguous()
+    T, Ns = Y.shape
+    ds, d = disc.ds, disc.ds * disc.Ns
+    if Ns != disc.Ns or P0.shape[-1] != d or R.shape[-1] != Ns:
+        raise ValueError("kf_filter_kron: inconsistent shapes")
+    R_ts = Ns * Ns if (R.dim() == 3 and R.shape[0] > 1) else 0
+    dev = Y.device
+    mf = torch.empty((T, d), dtype=torch.float64, device=dev)
+    Pf = torch.empty((T, d, d), dtype=torch.float64, device=dev)
+    lml = torch.empty((1,), dtype=torch.float64, device=dev)
+    ws = _kron_ws(T, Ns, ds, False, dev)
+    jit = settings.jitter if jitter is None else jitter
+    with torch.cuda.device(dev):
+        st = lib.physs_kf_filter_kron_f64(_stream_ptr(stream), T, Ns, ds, disc.At.data_ptr(), disc.Qt.data_ptr(),
+                                          disc.index.data_ptr(), disc.Ks.data_ptr(), m0.data_ptr(), P0.data_ptr(),
+                                          Y.data_ptr(), R.data_ptr(), R_ts, float(jit), ws.data_ptr(),
+                                          ws.numel() * 8, mf.data_ptr(), Pf.data_ptr(), lml.data_ptr())
+    _lib.check(st, "physs_kf_filter_kron_f64")
+    return lml[0], mf, Pf
+
+
+def rts_smooth_kron(mf, Pf, disc, project=False, jitter=None, stream=None):
+    """project=False -> (ms [T, d], Ps [T, d, d]); True -> (H ms [T, Ns], H Ps H^T [T, Ns, Ns])."""
+    lib = _lib.load()
+    mf, Pf = _dev(mf, "mf").contiguous(), _dev(Pf, "Pf").contiguous()
+    T, d = mf.shape
+    ds, Ns = disc.ds, disc.Ns
+    if d != ds * Ns:
+        raise ValueError("rts_smooth_kron: inconsistent shapes")
+    dev = mf.device
+    mo = Ns if project else d
+    ms = torch.empty((T, mo), dtype=torch.float64, device=dev)
+    Ps = torch.empty((T, mo, mo), dtype=torch.float64, device=dev)
+    ws = _kron_ws(T, Ns, ds, True, dev)
+    jit = settings.jitter if jitter is None else jitter
+    with torch.cuda.device(dev):
+        st = lib.physs_rts_smooth_kron_f64(_stream_ptr(stream), T, Ns, ds, disc.At.data_ptr(), disc.Qt.data_ptr(),
+                                           disc.index.data_ptr(), disc.Ks.data_ptr(), mf.data_ptr(), Pf.data_ptr(),
+                                           1 if project else 0, float(jit), ws.data_ptr(), ws.numel() * 8,
+                                           ms.data_ptr(), Ps.data_ptr())
+    _lib.check(st, "physs_rts_smooth_kron_f64")
+    return ms, Ps

@@ -27,6 +27,9 @@ auto_parallel_min_steps = 1024
 # single series with state dim above this go to the large-block path (libphyss_b200_big.so: cuBLAS / cuSOLVER
 # per step); at or below it the shared-memory lane-group kernels are used
 big_block_min_dim = 32
+# separable spatio-temporal priors (A = I (x) A_t) on that route use the hand-written persistent kernels
+# (physs_kf_filter_kron_f64 / physs_rts_smooth_kron_f64); False sends them through the library path as well
+kron_kernels = True
 # read the device flag of the parallel-in-time filter (one host sync) and fall back to the sequential kernels
 # when a chunk did not converge; set False to keep the call fully asynchronous
 pscan_check_status = True

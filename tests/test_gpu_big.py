@@ -14,6 +14,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
 
+@pytest.fixture(autouse=True)
+def _library_route(monkeypatch):
+    """These tests pin the cuBLAS / cuSOLVER-backed library path; separable priors would otherwise take the
+    hand-written kernels (tests/test_gpu_kron.py)."""
+    from physs_gp_b200 import settings
+    monkeypatch.setattr(settings, "kron_kernels", False)
+
+
 def _st_problem(Ns, T, seed, nan_frac=0.05, irregular=True):
     from physs_gp_b200 import kernels as K
     from physs_gp_b200 import sdes

@@ -1,0 +1,117 @@
+"""-m gpu parity tests of the hand-written large-block kernels for separable spatio-temporal priors
+(physs_kf_filter_kron_f64 / physs_rts_smooth_kron_f64, csrc/physs_kron.cu; BASELINE config 2 shape): persistent
+cooperative filter, time-parallel gain kernel + cooperative smoother recursion, against the numpy oracle (dense
+Kronecker matrices, as the reference builds them) and against the cuBLAS / cuSOLVER library path.  1e-9 relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import filters as ofilters
+from oracle import sde as osde
+from tests import synth
+from tests.test_gpu_seq import rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _problem(Ns, T, seed, kind="m32", nan_frac=0.05, irregular=True, dense_R=False):
+    from physs_gp_b200 import kernels as K
+    from physs_gp_b200 import sdes
+    rng = np.random.default_rng(seed)
+    Xs = rng.uniform(size=(Ns, 2))
+    D2 = ((Xs[:, None, :] - Xs[None, :, :]) ** 2).sum(-1)
+    Ks = np.exp(-0.5 * D2 / 0.2 ** 2) + 1e-6 * np.eye(Ns)
+    pk = {"m32": K.Matern32, "m52": K.Matern52, "m72": K.Matern72}[kind](1.0, 1.0)
+    ok = {"m32": osde.Matern32, "m52": osde.Matern52, "m72": osde.Matern72}[kind](1.0, 1.0)
+    pprior = sdes.LTI_SDE(sdes.Independent([K.SpatioTemporalSeperableKernel(pk, Ks)]))
+    oprior = osde.LTI_SDE([osde.SpaceTimeSeparable(ok, Ks)])
+    t = synth.time_grid(T, 0.1, rng, irregular=irregular)
+    Y = synth.noisy_series(1, T, Ns, rng, nan_frac)[0]
+    R = synth.random_spd(rng, (T,), Ns) if dense_R else np.tile(0.1 * np.eye(Ns), [T, 1, 1])
+    return pprior, oprior, t, Y, R
+
+
+def _run_and_compare(pprior, oprior, t, Y, R, jitter):
+    from physs_gp_b200 import data, filters
+    lml_o, mf_o, Pf_o, _ = ofilters.filter_sequential(oprior, t, Y, R, jitter)
+    d = data.TemporalData(t, Y[:, :, None])
+    lml, kf = filters.filter_loop(d, pprior, R=R)
+    assert rel(kf['P'][0], Pf_o[0]) < TOL, "first filter step"
+    assert rel(kf['m'], mf_o) < TOL and rel(kf['P'], Pf_o) < TOL
+    assert abs(float(lml) - lml_o) <= TOL * abs(lml_o)
+    for fs in (True, False):
+        ms_o, Ps_o = ofilters.smoother_sequential(oprior, t, mf_o, Pf_o, full_state=fs, jitter=jitter)
+        mu, var = filters.smoother_loop(d, pprior, kf, full_state=fs)
+        assert rel(var[-2:], Ps_o[-2:]) < TOL, "last smoother steps (full_state=%s)" % fs
+        assert rel(mu, ms_o) < TOL and rel(var, Ps_o) < TOL
+
+
+@pytest.fixture(autouse=True)
+def _kron_on(monkeypatch):
+    from physs_gp_b200 import ops, settings
+    monkeypatch.setattr(settings, "kron_kernels", True)
+    calls = {"f": 0, "s": 0}
+    f0, s0 = ops.kf_filter_kron, ops.rts_smooth_kron
+    monkeypatch.setattr(ops, "kf_filter_kron", lambda *a, **k: (calls.__setitem__("f", calls["f"] + 1), f0(*a, **k))[1])
+    monkeypatch.setattr(ops, "rts_smooth_kron", lambda *a, **k: (calls.__setitem__("s", calls["s"] + 1), s0(*a, **k))[1])
+    yield calls
+
+
+@pytest.mark.parametrize("Ns,T,irregular", [(20, 40, True), (40, 25, False), (37, 12, True), (70, 10, True)])
+@pytest.mark.parametrize("jitter", [1e-5, 0.0])
+def test_kron_filter_smoother_match_oracle(cuda_device, _kron_on, Ns, T, irregular, jitter, monkeypatch):
+    from physs_gp_b200 import settings
+    monkeypatch.setattr(settings, "jitter", jitter)
+    _run_and_compare(*_problem(Ns, T, 3 + Ns, irregular=irregular), jitter)
+    assert _kron_on["f"] == 1 and _kron_on["s"] == 2            # the hand-written route really ran
+
+
+@pytest.mark.parametrize("kind,Ns", [("m52", 15), ("m72", 12), ("m52", 24)])
+def test_kron_other_temporal_kernels(cuda_device, _kron_on, kind, Ns, monkeypatch):
+    """ds = 3 / 4 temporal blocks (d = 45 is odd: unaligned rows exercise the non-vector tile loads)."""
+    from physs_gp_b200 import settings
+    monkeypatch.setattr(settings, "jitter", 1e-5)
+    _run_and_compare(*_problem(Ns, 15, 11, kind=kind), 1e-5)
+    assert _kron_on["f"] == 1
+
+
+def test_kron_dense_site_covariance(cuda_device, monkeypatch):
+    """Full time-varying R_k (the CVI site covariance of config 2) and no missing data."""
+    from physs_gp_b200 import settings
+    monkeypatch.setattr(settings, "jitter", 1e-5)
+    _run_and_compare(*_problem(48, 8, 5, nan_frac=0.0, dense_R=True), 1e-5)
+
+
+def test_kron_smoother_crosses_time_chunks(cuda_device, monkeypatch):
+    """T larger than one smoother chunk (4 x the CTA count of the gain kernel): the recursion state is handed
+    from one cooperative launch to the next."""
+    from physs_gp_b200 import settings
+    monkeypatch.setattr(settings, "jitter", 1e-5)
+    _run_and_compare(*_problem(17, 1300, 21), 1e-5)
+
+
+def test_kron_equals_library_path(cuda_device, monkeypatch):
+    from physs_gp_b200 import data, filters, settings
+    pprior, oprior, t, Y, R = _problem(40, 30, 9, dense_R=True)
+    d = data.TemporalData(t, Y[:, :, None])
+    lml_a, kf_a = filters.filter_loop(d, pprior, R=R)
+    mu_a, var_a = filters.smoother_loop(d, pprior, kf_a, full_state=False)
+    monkeypatch.setattr(settings, "kron_kernels", False)
+    lml_b, kf_b = filters.filter_loop(d, pprior, R=R)
+    mu_b, var_b = filters.smoother_loop(d, pprior, kf_b, full_state=False)
+    assert rel(lml_a, lml_b.cpu().numpy()) < TOL
+    assert rel(kf_a['P'], kf_b['P'].cpu().numpy()) < TOL and rel(kf_a['m'], kf_b['m'].cpu().numpy()) < TOL
+    assert rel(var_a, var_b.cpu().numpy()) < TOL and rel(mu_a, mu_b.cpu().numpy()) < TOL
+
+
+def test_kron_non_pd_gives_nan(cuda_device, monkeypatch):
+    from physs_gp_b200 import data, filters
+    pprior, oprior, t, Y, R = _problem(20, 12, 5, nan_frac=0.0)
+    R = R.copy()
+    R[4] = -50.0 * np.eye(20)
+    d = data.TemporalData(t, Y[:, :, None])
+    lml, kf = filters.filter_loop(d, pprior, R=R)
+    assert not np.isfinite(float(lml))
+    assert not torch.isfinite(kf['P'][4:]).any() and not torch.isfinite(kf['m'][4:]).any()
+    assert torch.isfinite(kf['P'][:4]).all()
