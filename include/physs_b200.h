@@ -442,6 +442,9 @@ int physs_spd_inverse_f64(void* stream, int64_t N, int32_t D, const double* A, d
  * Outputs: mf [T, d], Pf [T, d, d], lml [1];  smoother: project = 0 -> ms [T, d], Ps [T, d, d];
  * project = 1 -> H ms [T, Ns], H Ps H^T [T, Ns, Ns].  Stream-ordered, NaN on numerical failure. */
 int64_t physs_kron_workspace_bytes(int64_t T, int32_t Ns, int32_t ds, int32_t smoother);
+/* measurement aid: with PHYSS_KRON_PROF=1 in the environment CTA 0 accumulates nanoseconds per phase into 32
+ * doubles at this offset (in doubles) of the workspace */
+int64_t physs_kron_prof_offset(int64_t T, int32_t Ns, int32_t ds, int32_t smoother);
 int physs_kf_filter_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, const double* At, const double* Qt,
                              const int32_t* idx, const double* Ks, const double* m0, const double* P0,
                              const double* Y, const double* R, int64_t R_tstride, double jitter, void* ws,

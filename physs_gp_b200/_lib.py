@@ -72,6 +72,7 @@ SIGNATURES = {
     "physs_cvi_gauss_newton_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _c_i32, _ptr, _ptr, _c_i64, _ptr, _ptr]),
     "physs_fp64_probe": (ctypes.c_int, [_ptr, _c_i32, _c_i64, _ptr]),
     "physs_kron_workspace_bytes": (_c_i64, [_c_i64, _c_i32, _c_i32, _c_i32]),
+    "physs_kron_prof_offset": (_c_i64, [_c_i64, _c_i32, _c_i32, _c_i32]),
     "physs_kf_filter_kron_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
                                                 _ptr, _ptr, _c_i64, _c_f64, _ptr, _c_i64, _ptr, _ptr, _ptr]),
     "physs_rts_smooth_kron_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,

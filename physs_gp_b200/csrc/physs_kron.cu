@@ -20,27 +20,27 @@
 // two distributed GEMMs per step in a second persistent cooperative kernel.
 //
 // All matrices row-major fp64; NaN on numerical failure (sqrt of a non-positive pivot), status 0.
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "physs_core.cuh"
 #include "physs_internal.h"
-
-namespace cg = cooperative_groups;
 
 namespace physs {
 namespace kron {
 
 constexpr int NTH = 256;      // threads per CTA: 8 warps = 4 column strips x 2 k-halves
 constexpr int TN = 32;        // tile width
-constexpr int KC = 80;        // k-chunk staged per pipeline stage
-constexpr int LDA = KC + 4;   // 84: (LDA mod 16) == 4 -> the 8 x 4 fragment loads of a half-warp hit 16 distinct bank pairs
+constexpr int KC = 128;       // largest k-chunk staged per pipeline stage
+constexpr int NST = 2;        // pipeline stages (measured: 2 x 128 beats 4 x 64 -- the per-chunk cost is instruction issue
+                              // on 8 warps, not operand latency)
+constexpr int LDA = KC + 4;   // 132: (LDA mod 16) == 4 -> the 8 x 4 fragment loads of a half-warp hit 16 distinct bank pairs
 constexpr int LDB = TN + 4;   // 36: same property for the 4 x 8 fragment loads of a [K x N] tile
 constexpr int TMMAX = 40;
-constexpr int SM_A = 2 * TMMAX * LDA;
-constexpr int SM_B = 2 * KC * LDB;             // KC * LDB = 2880 >= TN * LDA = 2688 (an [N x K] tile fits as well)
-constexpr int SM_RED = 4 * 5 * 2 * 32;
+constexpr int SM_A = NST * TMMAX * LDA;
+constexpr int SM_B = NST * KC * LDB;           // KC * LDB = 2304 >= TN * LDA = 2176 (an [N x K] tile fits as well)
+constexpr int SM_RED = 4 * 5 * 2 * 32;         // split-k partial sums; reused as the 32 x 33 transposition tile
 constexpr int SM_DG = 32 * 33 + 32;
 constexpr int SM_DOUBLES = SM_A + SM_B + SM_RED + SM_DG;
 constexpr size_t SM_BYTES = SM_DOUBLES * sizeof(double);
@@ -60,12 +60,59 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// accumulate the nanoseconds since *tick into prof[slot] (thread 0 of CTA 0 only; measurement aid)
+__device__ __forceinline__ void ptick(double* prof, int slot, unsigned long long& tick) {
+  if (prof && blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long now = gtimer();
+    prof[slot] += (double)(now - tick);
+    tick = now;
+  }
+}
+
+// ---------------------------------------------------------------------------------- grid-wide barrier
+// Two-level arrive counter (groups of 16 CTAs, then one top counter) with monotonic 64-bit counts: atomics on one
+// address serialise at ~27 cycles each, so 148 arrivals on a single counter cost ~2 us; 16 + 10 cost a quarter.
+// The kernels are launched cooperatively (all CTAs resident).  bar: [0] top counter, [16 (g + 1)] group counters
+// (one 128-byte line each), zeroed before the launch.  __threadfence() on both sides of the arrive / wait is the
+// release / acquire (it also invalidates this SM's L1, so plain loads after the barrier see the other CTAs' data).
+constexpr int BAR_GROUP = 16;
+struct GridBarrier {
+  unsigned long long* bar;
+  unsigned long long round;
+  __device__ __forceinline__ void init(unsigned long long* b) { bar = b; round = 0; }
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ++round;
+      const unsigned ncta = gridDim.x, grp = blockIdx.x / BAR_GROUP;
+      const unsigned ngrp = (ncta + BAR_GROUP - 1) / BAR_GROUP;
+      const unsigned gsize = min((unsigned)BAR_GROUP, ncta - grp * BAR_GROUP);
+      __threadfence();
+      const unsigned long long old = atomicAdd(bar + 16 * (grp + 1), 1ULL);
+      if (old + 1 == round * gsize) atomicAdd(bar, 1ULL);
+      const unsigned long long target = round * ngrp;
+      unsigned long long seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(bar) : "memory");
+      } while (seen < target);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+};
+
 // ------------------------------------------------------------------------------------------ tile GEMM
 // C[M x N] = Add + sum_p sg[p] * A_p[M x K_p] * op(B_p),  op(B) = B ([K x N] row-major, nt = 0) or B^T (B is
 // [N x K] row-major, nt = 1).  Output tiles TM x 32 (TM = 8 MT) are dealt round-robin to `ncta` CTAs
 // (cta = 0, ncta = 1: the whole product on this CTA).  lower = 1 (needs M == N, MT == 4): only tiles on or
-// below the diagonal are computed and mirrored into the upper triangle.  Optional second outputs:
-// C2 = C - Sub2 (same shape) and the projection Cp[i / ds][j / ds] = C[i][j] for i % ds == j % ds == 0.
+// below the diagonal are computed and mirrored into the upper triangle (through a shared-memory transpose, so
+// both copies are written with full rows).  Optional second outputs: C2 = C - Sub2 (same shape) and the
+// projection Cp[i / ds][j / ds] = C[i][j] for i % ds == j % ds == 0.  With two operand pairs sg[1] must be != 0.
 struct Gemm {
   const double* A[2]; int lda[2];
   const double* B[2]; int ldb[2];
@@ -79,15 +126,25 @@ struct Gemm {
   double* Cp; int ldp; int ds;
 };
 
-// [rows x cols] block (cols even) of a row-major global matrix -> shared memory, zero outside the valid
-// extent vr x vc.  16-byte cp.async when the source allows it, else L2 loads + a shared store.
-__device__ __forceinline__ void load_block(double* dst, int lds, const double* src, int64_t ld, int rows, int cols,
-                                           int vr, int vc, bool vec) {
-  const int upr = cols >> 1;
-  for (int idx = threadIdx.x; idx < rows * upr; idx += NTH) {
-    const int r = idx / upr, c = (idx - r * upr) << 1;
-    double* d = dst + r * lds + c;
-    const double* s = src + (int64_t)r * ld + c;
+__device__ __forceinline__ bool vec_ok(const double* p, int64_t ld) {
+  return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld & 1) == 0);
+}
+// [ROWS x kpad] block of a row-major matrix -> shared memory (leading dim LDA), zero outside the valid extent
+// vr x vc.  Thread map: 64 threads x 16 bytes cover one row of up to 128 doubles, 4 rows per pass -- shifts only.
+template <int ROWS>
+__device__ __forceinline__ void load_rows(double* dst, const double* src, int64_t ld, int kpad, int vr, int vc, bool vec) {
+  const int c = (threadIdx.x & 63) << 1;
+  if (c >= kpad) return;
+  int r = threadIdx.x >> 6;
+  const double* s = src + (int64_t)r * ld + c;
+  double* d = dst + r * LDA + c;
+  if (vec && vr >= ROWS && vc >= kpad) {           // interior tile: no predicates
+#pragma unroll
+    for (int i = 0; i < ROWS / 4; ++i) cp_async16(d + i * 4 * LDA, s + (int64_t)i * 4 * ld);
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < ROWS / 4; ++i, r += 4, s += 4 * ld, d += 4 * LDA) {
     if (vec && r < vr && c + 1 < vc) {
       cp_async16(d, s);
     } else {
@@ -97,19 +154,41 @@ __device__ __forceinline__ void load_block(double* dst, int lds, const double* s
     }
   }
 }
-__device__ __forceinline__ bool vec_ok(const double* p, int64_t ld) {
-  return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld & 1) == 0);
+// [kpad x 32] block ([K x N] operand) -> shared memory (leading dim LDB): 16 threads per row, 16 rows per pass
+__device__ __forceinline__ void load_kn(double* dst, const double* src, int64_t ld, int kpad, int vr, int vc, bool vec) {
+  const int c = (threadIdx.x & 15) << 1;
+  if (vec && vr >= kpad && vc >= TN) {             // interior tile: no predicates
+    const double* s = src + (int64_t)(threadIdx.x >> 4) * ld + c;
+    double* d = dst + (threadIdx.x >> 4) * LDB + c;
+    for (int r = threadIdx.x >> 4; r < kpad; r += 16, s += 16 * ld, d += 16 * LDB) cp_async16(d, s);
+    return;
+  }
+  for (int r = threadIdx.x >> 4; r < kpad; r += 16) {
+    const double* s = src + (int64_t)r * ld + c;
+    double* d = dst + r * LDB + c;
+    if (vec && r < vr && c + 1 < vc) {
+      cp_async16(d, s);
+    } else {
+      const double x0 = (r < vr && c < vc) ? __ldcg(s) : 0.0;
+      const double x1 = (r < vr && c + 1 < vc) ? __ldcg(s + 1) : 0.0;
+      *reinterpret_cast<double2*>(d) = make_double2(x0, x1);
+    }
+  }
 }
 
 template <int MT>
-__device__ void gemm_tiles(const Gemm& g, int cta, int ncta, double* sm) {
+__device__ __noinline__ void gemm_tiles(const Gemm& g, int cta, int ncta, double* sm) {
   constexpr int TM = 8 * MT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   const int wcol = warp & 3, half = warp >> 2;
   const int tm = (g.M + TM - 1) / TM, tn = (g.N + TN - 1) / TN;
   const int ntiles = g.lower ? tm * (tm + 1) / 2 : tm * tn;
+  // k-chunks: as few as fit KC, all of (nearly) the same length, a multiple of 4
   const int nch0 = (g.K[0] + KC - 1) / KC;
-  const int nch = nch0 + (g.npair > 1 ? (g.K[1] + KC - 1) / KC : 0);
+  const int kch0 = ((g.K[0] + nch0 - 1) / nch0 + 3) & ~3;
+  const int nch1 = g.npair > 1 ? (g.K[1] + KC - 1) / KC : 0;
+  const int kch1 = nch1 ? ((g.K[1] + nch1 - 1) / nch1 + 3) & ~3 : 0;
+  const int nch = nch0 + nch1;
   const int my_tiles = ntiles > cta ? (ntiles - cta + ncta - 1) / ncta : 0;
   const int nitems = my_tiles * nch;
   if (nitems == 0) return;
@@ -119,8 +198,8 @@ __device__ void gemm_tiles(const Gemm& g, int cta, int ncta, double* sm) {
   const bool va0 = vec_ok(g.A[0], g.lda[0]), vb0 = vec_ok(g.B[0], g.ldb[0]);
   const bool va1 = g.npair > 1 && vec_ok(g.A[1], g.lda[1]), vb1 = g.npair > 1 && vec_ok(g.B[1], g.ldb[1]);
 
-  auto tile_origin = [&](int it, int& r0, int& c0) {
-    const int t = cta + (it / nch) * ncta;
+  auto tile_origin = [&](int tile_no, int& r0, int& c0) {
+    const int t = cta + tile_no * ncta;
     if (g.lower) {
       int r = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
       while ((r + 1) * (r + 2) / 2 <= t) ++r;
@@ -132,64 +211,86 @@ __device__ void gemm_tiles(const Gemm& g, int cta, int ncta, double* sm) {
       c0 = (t % tn) * TN;
     }
   };
-  auto chunk_of = [&](int it, int& pr, int& k0, int& kpad) {
-    int ch = it % nch;
+  auto chunk_of = [&](int ch, int& pr, int& k0, int& kpad) {
     pr = ch >= nch0 ? 1 : 0;
     if (pr) ch -= nch0;
-    k0 = ch * KC;
-    const int kc = min(KC, g.K[pr] - k0);
+    const int kch = pr ? kch1 : kch0;
+    k0 = ch * kch;
+    const int kc = max(0, min(kch, g.K[pr] - k0));
     kpad = (kc + 3) & ~3;
   };
-  auto issue = [&](int it) {
-    int r0, c0, pr, k0, kpad;
-    tile_origin(it, r0, c0);
-    chunk_of(it, pr, k0, kpad);
-    const int buf = it & 1;
+  int ld_tile = 0, ld_ch = 0, ld_r0, ld_c0;      // the (tile, chunk) the next issue() stages
+  tile_origin(0, ld_r0, ld_c0);
+  auto issue = [&](int buf) {
+    int pr, k0, kpad;
+    chunk_of(ld_ch, pr, k0, kpad);
     const int K = g.K[pr];
-    load_block(As + buf * TMMAX * LDA, LDA, g.A[pr] + (int64_t)r0 * g.lda[pr] + k0, g.lda[pr], TM, kpad, g.M - r0,
-               K - k0, pr ? va1 : va0);
+    load_rows<TM>(As + buf * TMMAX * LDA, g.A[pr] + (int64_t)ld_r0 * g.lda[pr] + k0, g.lda[pr], kpad, g.M - ld_r0,
+                  K - k0, pr ? va1 : va0);
     if (g.nt)
-      load_block(Bs + buf * KC * LDB, LDA, g.B[pr] + (int64_t)c0 * g.ldb[pr] + k0, g.ldb[pr], TN, kpad, g.N - c0,
-                 K - k0, pr ? vb1 : vb0);
+      load_rows<TN>(Bs + buf * KC * LDB, g.B[pr] + (int64_t)ld_c0 * g.ldb[pr] + k0, g.ldb[pr], kpad, g.N - ld_c0,
+                    K - k0, pr ? vb1 : vb0);
     else
-      load_block(Bs + buf * KC * LDB, LDB, g.B[pr] + (int64_t)k0 * g.ldb[pr] + c0, g.ldb[pr], kpad, TN, K - k0,
-                 g.N - c0, pr ? vb1 : vb0);
+      load_kn(Bs + buf * KC * LDB, g.B[pr] + (int64_t)k0 * g.ldb[pr] + ld_c0, g.ldb[pr], kpad, K - k0, g.N - ld_c0,
+              pr ? vb1 : vb0);
     cp_async_commit();
+    if (++ld_ch == nch) {
+      ld_ch = 0;
+      ++ld_tile;
+      if (ld_tile < my_tiles) tile_origin(ld_tile, ld_r0, ld_c0);
+    }
   };
 
   double acc[MT][2];
-  issue(0);
+  int r0, c0;
+  tile_origin(0, r0, c0);
+#pragma unroll
+  for (int i = 0; i < NST - 1; ++i) {
+    if (i < nitems) issue(i);
+    else cp_async_commit();
+  }
+  int ch = 0, tile_no = 0;
   for (int it = 0; it < nitems; ++it) {
     int pr, k0, kpad;
-    chunk_of(it, pr, k0, kpad);
-    const int ch = it % nch;
+    chunk_of(ch, pr, k0, kpad);
     if (ch == 0) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+    } else if (ch == nch0) {
+      const double f = g.sg[0] / g.sg[1];        // second operand pair: final scale is sg[1]
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) { acc[mt][0] *= f; acc[mt][1] *= f; }
     }
-    if (it + 1 < nitems) {
-      issue(it + 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    if (it + NST - 1 < nitems) issue((it + NST - 1) % NST);      // refills the buffer consumed one iteration ago
+    else cp_async_commit();                                      // (empty group: keeps the group count uniform)
+    cp_async_wait<NST - 1>();
     __syncthreads();
     {
-      const double* as = As + (it & 1) * TMMAX * LDA;
-      const double* bs = Bs + (it & 1) * KC * LDB;
-      const double sgn = g.sg[pr];
+      const double* as = As + (it % NST) * TMMAX * LDA + gq * LDA + tq;
+      const double* bs = Bs + (it % NST) * KC * LDB + (g.nt ? (8 * wcol + gq) * LDA + tq : tq * LDB + 8 * wcol + gq);
+      const int bstep = g.nt ? 4 : 4 * LDB;
       const int ksteps = kpad >> 2;
-      for (int kt = half; kt < ksteps; kt += 2) {
-        const double b = g.nt ? bs[(8 * wcol + gq) * LDA + 4 * kt + tq] : bs[(4 * kt + tq) * LDB + 8 * wcol + gq];
+      int kt = half;
+      for (; kt + 2 < ksteps; kt += 4) {               // two k-steps per trip: all fragment loads ahead of the DMMAs
+        double a0[MT], a1[MT];
+        const double b0 = bs[kt * bstep], b1 = bs[(kt + 2) * bstep];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const double a = sgn * as[(8 * mt + gq) * LDA + 4 * kt + tq];
-          dmma884(acc[mt][0], acc[mt][1], a, b);
-        }
+        for (int mt = 0; mt < MT; ++mt) { a0[mt] = as[8 * mt * LDA + 4 * kt]; a1[mt] = as[8 * mt * LDA + 4 * kt + 8]; }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][0], acc[mt][1], a0[mt], b0);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][0], acc[mt][1], a1[mt], b1);
+      }
+      for (; kt < ksteps; kt += 2) {
+        const double b = bs[kt * bstep];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][0], acc[mt][1], as[8 * mt * LDA + 4 * kt], b);
       }
     }
     __syncthreads();
     if (ch == nch - 1) {
+      const double sgl = g.sg[g.npair - 1];
+      const bool mirror = g.lower && r0 > c0;
       if (half == 1) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
@@ -199,32 +300,48 @@ __device__ void gemm_tiles(const Gemm& g, int cta, int ncta, double* sm) {
       }
       __syncthreads();
       if (half == 0) {
-        int r0, c0;
-        tile_origin(it, r0, c0);
-        const bool mirror = g.lower && r0 > c0;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const int row = r0 + 8 * mt + gq;
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int col = c0 + 8 * wcol + 2 * tq + e;
+            double v = sgl * (acc[mt][e] + Red[((wcol * MT + mt) * 2 + e) * 32 + lane]);
             if (row < g.M && col < g.N) {
-              double v = acc[mt][e] + Red[((wcol * MT + mt) * 2 + e) * 32 + lane];
               if (g.Add) v += __ldcg(g.Add + (int64_t)row * g.ldadd + col);
               g.C[(int64_t)row * g.ldc + col] = v;
-              if (mirror) g.C[(int64_t)col * g.ldc + row] = v;
-              if (g.C2) {
-                g.C2[(int64_t)row * g.ld2 + col] = v - __ldcg(g.Sub2 + (int64_t)row * g.ld2 + col);
-                if (mirror) g.C2[(int64_t)col * g.ld2 + row] = v - __ldcg(g.Sub2 + (int64_t)col * g.ld2 + row);
-              }
-              if (g.Cp && row % g.ds == 0 && col % g.ds == 0) {
-                g.Cp[(int64_t)(row / g.ds) * g.ldp + col / g.ds] = v;
-                if (mirror) g.Cp[(int64_t)(col / g.ds) * g.ldp + row / g.ds] = v;
-              }
+              if (g.C2) g.C2[(int64_t)row * g.ld2 + col] = v - __ldcg(g.Sub2 + (int64_t)row * g.ld2 + col);
+              if (g.Cp && row % g.ds == 0 && col % g.ds == 0) g.Cp[(int64_t)(row / g.ds) * g.ldp + col / g.ds] = v;
             }
+            acc[mt][e] = v;
           }
         }
       }
+      if (mirror) {                                   // MT == 4 here: a 32 x 32 tile strictly below the diagonal
+        __syncthreads();
+        if (half == 0) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            Red[(8 * mt + gq) * 33 + 8 * wcol + 2 * tq] = acc[mt][0];
+            Red[(8 * mt + gq) * 33 + 8 * wcol + 2 * tq + 1] = acc[mt][1];
+          }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < 1024; idx += NTH) {
+          const int cc = idx >> 5, rr = idx & 31;      // consecutive lanes: consecutive columns of the mirrored row
+          const int row = c0 + cc, col = r0 + rr;
+          if (row < g.N && col < g.M) {
+            const double v = Red[rr * 33 + cc];
+            g.C[(int64_t)row * g.ldc + col] = v;
+            if (g.C2) g.C2[(int64_t)row * g.ld2 + col] = v - __ldcg(g.Sub2 + (int64_t)row * g.ld2 + col);
+            if (g.Cp && row % g.ds == 0 && col % g.ds == 0) g.Cp[(int64_t)(row / g.ds) * g.ldp + col / g.ds] = v;
+          }
+        }
+      }
+      ch = 0;
+      if (++tile_no < my_tiles) tile_origin(tile_no, r0, c0);
+    } else {
+      ++ch;
     }
   }
 }
@@ -232,42 +349,39 @@ __device__ void gemm_tiles(const Gemm& g, int cta, int ncta, double* sm) {
 // ------------------------------------------------------------------------- 32 x 32 diagonal blocks
 // Factor the w x w block at Lm in place (lower Cholesky factor; strictly upper part of the block zeroed).
 // Leaves the factor padded with the identity in Dg (ld 33) and the reciprocal diagonal in rd[32].
-__device__ void diag_factor(double* Lm, int64_t ld, int w, double* Dg, double* rd) {
-  for (int idx = threadIdx.x; idx < 1024; idx += NTH) {
-    const int r = idx >> 5, c = idx & 31;
-    Dg[r * 33 + c] = (r < w && c <= r) ? __ldcg(Lm + r * ld + c) : (r == c ? 1.0 : 0.0);
-  }
-  __syncthreads();
+// Warp 0, lane i = row i held in registers; column j is scaled by rsqrt(pivot) and broadcast with shuffles, so
+// the chain through the 32 pivots is shuffle + rsqrt + multiply-add with no shared-memory round trip.
+__device__ __noinline__ void diag_factor(double* Lm, int64_t ld, int w, double* Dg, double* rd) {
   if (threadIdx.x < 32) {
     const int i = threadIdx.x;
-    for (int j = 0; j < w; ++j) {
-      const double dj = Dg[j * 33 + j];
-      const double rs = fast_rsqrt(dj);          // dj <= 0 -> NaN (the reference's Cholesky of a non-PD matrix)
-      __syncwarp();
-      double lij = 0.0;
-      if (i == j) {
-        Dg[j * 33 + j] = dj * rs;
-        rd[j] = rs;
-      } else if (i > j && i < w) {
-        lij = Dg[i * 33 + j] * rs;
-        Dg[i * 33 + j] = lij;
+    double r[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) r[c] = (i < w && c <= i) ? __ldcg(Lm + i * ld + c) : (c == i ? 1.0 : 0.0);
+    double rdi = 1.0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const double dj = __shfl_sync(0xffffffffu, r[j], j);
+      const double rs = fast_rsqrt(dj);            // dj <= 0 -> NaN (the reference's Cholesky of a non-PD matrix)
+      const double lij = r[j] * rs;                // lane j: sqrt(dj); lanes > j: L[i][j]; lanes < j: 0
+      r[j] = lij;
+      if (i == j) rdi = rs;
+#pragma unroll
+      for (int c = j + 1; c < 32; ++c) {
+        const double lcj = __shfl_sync(0xffffffffu, lij, c);
+        if (c <= i) r[c] = fma(-lij, lcj, r[c]);
       }
-      __syncwarp();
-      if (i > j && i < w) {
-        for (int c = j + 1; c <= i; ++c) Dg[i * 33 + c] = fma(-lij, Dg[c * 33 + j], Dg[i * 33 + c]);
-      }
-      __syncwarp();
     }
-    if (i >= w) rd[i] = 1.0;
+    rd[i] = rdi;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      Dg[i * 33 + c] = r[c];
+      if (i < w && c < w) Lm[i * ld + c] = (c <= i) ? r[c] : 0.0;
+    }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 1024; idx += NTH) {
-    const int r = idx >> 5, c = idx & 31;
-    if (r < w && c < w) Lm[r * ld + c] = (c <= r) ? Dg[r * 33 + c] : 0.0;
-  }
 }
 // Load an already factored diagonal block (identity padding) and its reciprocal diagonal.
-__device__ void diag_load(const double* Lm, int64_t ld, int w, double* Dg, double* rd) {
+__device__ __noinline__ void diag_load(const double* Lm, int64_t ld, int w, double* Dg, double* rd) {
   for (int idx = threadIdx.x; idx < 1024; idx += NTH) {
     const int r = idx >> 5, c = idx & 31;
     Dg[r * 33 + c] = (r < w && c <= r) ? __ldcg(Lm + r * ld + c) : (r == c ? 1.0 : 0.0);
@@ -279,7 +393,7 @@ __device__ void diag_load(const double* Lm, int64_t ld, int w, double* Dg, doubl
 // One thread per row: x L^T = t (forward) or x L = t (backward) against the padded 32 x 32 factor in Dg, in
 // place on nr rows of X (columns [0, w)); optionally duplicated into X2.
 template <bool FWD>
-__device__ void subst_rows(double* X, int64_t ldx, int nr, int w, const double* Dg, const double* rd, double* X2,
+__device__ __noinline__ void subst_rows(double* X, int64_t ldx, int nr, int w, const double* Dg, const double* rd, double* X2,
                            int64_t ldx2) {
   for (int r = threadIdx.x; r < nr; r += NTH) {
     double t[32];
@@ -317,9 +431,10 @@ __device__ void subst_rows(double* X, int64_t ldx, int nr, int w, const double* 
 // Left-looking blocked Cholesky of the n x n matrix at Lm (lower triangle referenced and overwritten), carried
 // through `nrows` >= n rows: extra rows r >= n come out as r L^-T (an appended right-hand side v^T gives
 // (L^-1 v)^T).  One CTA; everything stays in L2 / global memory, tiles pass through shared memory.
-__device__ void chol_blocked(double* Lm, int64_t ld, int n, int nrows, double* sm) {
+__device__ __noinline__ void chol_blocked(double* Lm, int64_t ld, int n, int nrows, double* sm, double* prof = nullptr) {
   double* Dg = sm + SM_A + SM_B + SM_RED;
   double* rd = Dg + 32 * 33;
+  unsigned long long tk = gtimer();
   for (int r0 = 0; r0 < n; r0 += 32) {
     const int w = min(32, n - r0);
     if (r0 > 0) {
@@ -334,18 +449,23 @@ __device__ void chol_blocked(double* Lm, int64_t ld, int n, int nrows, double* s
       gemm_tiles<5>(g, 0, 1, sm);
       __syncthreads();
     }
+    ptick(prof, 16, tk);
     diag_factor(Lm + (int64_t)r0 * ld + r0, ld, w, Dg, rd);
     __syncthreads();
+    ptick(prof, 17, tk);
     const int nr = nrows - (r0 + w);
     if (nr > 0) subst_rows<true>(Lm + (int64_t)(r0 + w) * ld + r0, ld, nr, w, Dg, rd, nullptr, 0);
     __syncthreads();
+    ptick(prof, 18, tk);
   }
 }
 // X L^T = W in place on R rows of X (n columns), L the factor left by chol_blocked.
 template <int MT>
-__device__ void trsm_fwd(double* X, int64_t ldx, int R, const double* Lm, int64_t ldl, int n, double* sm) {
+__device__ __noinline__ void trsm_fwd(double* X, int64_t ldx, int R, const double* Lm, int64_t ldl, int n, double* sm,
+                         double* prof = nullptr) {
   double* Dg = sm + SM_A + SM_B + SM_RED;
   double* rd = Dg + 32 * 33;
+  unsigned long long tk = gtimer();
   for (int r0 = 0; r0 < n; r0 += 32) {
     const int w = min(32, n - r0);
     if (r0 > 0) {
@@ -360,14 +480,17 @@ __device__ void trsm_fwd(double* X, int64_t ldx, int R, const double* Lm, int64_
       gemm_tiles<MT>(g, 0, 1, sm);
       __syncthreads();
     }
+    ptick(prof, 20, tk);
     diag_load(Lm + (int64_t)r0 * ldl + r0, ldl, w, Dg, rd);
+    ptick(prof, 21, tk);
     subst_rows<true>(X + r0, ldx, R, w, Dg, rd, nullptr, 0);
     __syncthreads();
+    ptick(prof, 22, tk);
   }
 }
 // G L = Y in place on R rows of X; the result is also written to X2 when given.
 template <int MT>
-__device__ void trsm_bwd(double* X, int64_t ldx, int R, const double* Lm, int64_t ldl, int n, double* X2, int64_t ldx2,
+__device__ __noinline__ void trsm_bwd(double* X, int64_t ldx, int R, const double* Lm, int64_t ldl, int n, double* X2, int64_t ldx2,
                          double* sm) {
   double* Dg = sm + SM_A + SM_B + SM_RED;
   double* rd = Dg + 32 * 33;
@@ -392,6 +515,334 @@ __device__ void trsm_bwd(double* X, int64_t ldx, int R, const double* Lm, int64_
   }
 }
 
+// ---------------------------------------------------------------- shared-memory resident variants (n <= 208)
+// The per-step m x m innovation Cholesky and the gain solves sit on the critical path of the filter; run out of
+// L2 they are a chain of ~100 dependent round trips.  For m <= 208 the whole lower triangle fits in shared memory
+// (8-row block rows, block row I holds 8 (I + 1) columns with leading dimension 8 (I + 1) + 4: the 8 x 4 fragment
+// loads of a half-warp then hit 16 distinct bank pairs in every block row):
+constexpr int TRI_MAXBR = 26;
+__device__ __forceinline__ int tri_off(int I) { return 32 * I * (I + 2); }
+__device__ __forceinline__ int tri_ld(int I) { return 8 * (I + 1) + 4; }
+__device__ __forceinline__ int tri_idx(int r, int c) { const int I = r >> 3; return tri_off(I) + (r & 7) * tri_ld(I) + c; }
+constexpr int TRI_DOUBLES = 32 * TRI_MAXBR * (TRI_MAXBR + 2);      // 23296
+constexpr int TRI_N = 8 * TRI_MAXBR;                               // 208
+// layout of the shared-memory arena in these phases (doubles)
+constexpr int TS_L = 0;                          // triangle
+constexpr int TS_DG = TS_L + TRI_DOUBLES;        // 32 x 33 padded diagonal block + 32 reciprocal pivots
+constexpr int TS_V = TS_DG + SM_DG;              // appended right-hand side (TRI_N)
+constexpr int TS_X = TS_V + TRI_N + 32;               // 8 rows of X (ld TRI_N + 4), filter phase 3
+constexpr int TS_T = TS_X + 8 * (TRI_N + 4);     // 8 x 36 tile + 2 x 4 x 64 split-k partials
+constexpr int TS_DOUBLES = TS_T + 8 * 36 + 512;
+static_assert(TS_DOUBLES * 8 <= 227 * 1024, "shared-memory arena of the resident factorisation too large");
+constexpr size_t SM_BYTES_FILTER = (TS_DOUBLES > SM_DOUBLES ? TS_DOUBLES : SM_DOUBLES) * sizeof(double);
+
+// global (row-major, ld) lower triangle -> shared triangle; rows >= n are identity padding
+__device__ void tri_load_issue(double* Ls, const double* Sg, int64_t ld, int n, int nbr) {
+  const bool vec = vec_ok(Sg, ld);
+  for (int r = threadIdx.x >> 5; r < 8 * nbr; r += NTH / 32) {
+    const int I = r >> 3, wid = 8 * (I + 1);
+    double* d = Ls + tri_off(I) + (r & 7) * tri_ld(I);
+    const double* s = Sg + (int64_t)r * ld;
+    for (int c = (threadIdx.x & 31) << 1; c < wid; c += 64) {
+      if (r < n && vec && c + 1 < n) {
+        cp_async16(d + c, s + c);
+      } else {
+        const double x0 = (r < n && c < n) ? __ldcg(s + c) : (r == c ? 1.0 : 0.0);
+        const double x1 = (r < n && c + 1 < n) ? __ldcg(s + c + 1) : (r == c + 1 ? 1.0 : 0.0);
+        *reinterpret_cast<double2*>(d + c) = make_double2(x0, x1);
+      }
+    }
+  }
+  cp_async_commit();
+}
+__device__ void tri_load(double* Ls, const double* Sg, int64_t ld, int n, int nbr) {
+  tri_load_issue(Ls, Sg, ld, n, nbr);
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+// warp 0: factor the 32 x 32 (w32 valid) diagonal block at column c0 of the shared triangle in place; padded
+// copy in Dg, reciprocal pivots in rd.  Lane i holds row i in registers; column j goes through a 32-entry
+// shared buffer (one store, then broadcast 16-byte loads) -- per pivot 1 STS + <= 16 LDS instead of 62 shuffles,
+// which a single warp issues at ~5 cycles each.  col: 2 x 32 doubles (double-buffered, 16-byte aligned).
+__device__ __noinline__ void tri_diag_factor(double* Ls, int c0, int w32, double* Dg, double* rd, double* col) {
+  const int i = threadIdx.x;
+  double r[32];
+  const int base = (i < w32) ? tri_idx(c0 + i, c0) : 0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) r[c] = (i < w32 && c <= i) ? Ls[base + c] : (c == i ? 1.0 : 0.0);
+  double rdi = 1.0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    double* cb = col + (j & 1) * 32;
+    const double aij = r[j];
+    cb[i] = aij;                                   // column j below the diagonal (0 for i < j)
+    __syncwarp();
+    const double dj = cb[j];
+    const double rs = fast_rsqrt(dj);              // dj <= 0 -> NaN (the reference's Cholesky of a non-PD matrix)
+    const double t = aij * (rs * rs);              // a_ij / d_j
+    r[j] = aij * rs;                               // l_ij (lane j: sqrt(d_j))
+    if (i == j) rdi = rs;
+#pragma unroll
+    for (int c2 = (j + 1) >> 1; c2 < 16; ++c2) {
+      const double2 q = reinterpret_cast<const double2*>(cb)[c2];
+      if (2 * c2 > j && 2 * c2 <= i) r[2 * c2] = fma(-t, q.x, r[2 * c2]);
+      if (2 * c2 + 1 <= i) r[2 * c2 + 1] = fma(-t, q.y, r[2 * c2 + 1]);
+    }
+  }
+  rd[i] = rdi;
+  const int wid = 8 * (((c0 + i) >> 3) + 1) - c0;      // stored columns of this row inside the block
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    Dg[i * 33 + c] = r[c];
+    if (i < w32 && c < wid) Ls[base + c] = (c <= i) ? r[c] : 0.0;
+  }
+}
+// one thread per row: x L_JJ^T = t on the 32 columns at c0 of rows [row0, row0 + nr) of the shared triangle, and
+// (thread nr) of the appended vector v
+__device__ __noinline__ void tri_panel_solve(double* Ls, double* v, int c0, int row0, int nr, const double* Dg,
+                                             const double* rd) {
+  const int t_ = threadIdx.x;
+  if (t_ > nr) return;
+  double* x = (t_ < nr) ? Ls + tri_idx(row0 + t_, c0) : v + c0;
+  double t[32];
+#pragma unroll
+  for (int c = 0; c < 32; c += 2) {
+    const double2 q = *reinterpret_cast<const double2*>(x + c);
+    t[c] = q.x; t[c + 1] = q.y;
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const double xk = t[k] * rd[k];
+    t[k] = xk;
+#pragma unroll
+    for (int c = k + 1; c < 32; ++c) t[c] = fma(-xk, Dg[c * 33 + k], t[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 32; c += 2) *reinterpret_cast<double2*>(x + c) = make_double2(t[c], t[c + 1]);
+}
+
+// Cholesky of the n x n matrix Sg (+ appended row n = right-hand side v) entirely in shared memory, n <= 208.
+// On return (after a __syncthreads) the shared triangle holds L, v holds L^-1 v.  Lg != nullptr: L (lower
+// triangle) and the solved row are written back to global memory in the layout of Sg.
+__device__ __noinline__ void chol_smem(const double* Sg, int64_t ld, int n, double* Lg, double* sm, double* prof) {
+  double* Ls = sm + TS_L;
+  double* Dg = sm + TS_DG;
+  double* rd = Dg + 32 * 33;
+  double* v = sm + TS_V;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int nbr = (n + 7) >> 3, npad = 8 * nbr;
+  unsigned long long tk = gtimer();
+  tri_load_issue(Ls, Sg, ld, n, nbr);
+  for (int c = tid; c < npad + 32; c += NTH) v[c] = c < n ? __ldcg(Sg + (int64_t)n * ld + c) : 0.0;
+  cp_async_wait<0>();
+  __syncthreads();
+  ptick(prof, 16, tk);
+  for (int c0 = 0; c0 < npad; c0 += 32) {
+    const int w32 = min(32, npad - c0);
+    if (warp == 0) tri_diag_factor(Ls, c0, w32, Dg, rd, sm + TS_T);
+    __syncthreads();
+    ptick(prof, 17, tk);
+    const int row0 = c0 + w32, nr = npad - row0;
+    tri_panel_solve(Ls, v, c0, row0, nr, Dg, rd);
+    __syncthreads();
+    ptick(prof, 18, tk);
+    if (nr > 0) {
+      // trailing update C[I][K] -= L[I][c0..] L[K][c0..]^T on 8 x 8 tiles, block rows dealt round-robin to warps
+      const int I0 = row0 >> 3, ks = w32 >> 2;
+      for (int I = I0 + warp; I < nbr; I += NTH / 32) {
+        double a[8];
+        const double* ai = Ls + tri_idx(8 * I + gq, c0 + tq);
+#pragma unroll
+        for (int kt = 0; kt < 8; ++kt) a[kt] = kt < ks ? -ai[4 * kt] : 0.0;
+        for (int K = I0; K <= I; K += 4) {           // four tiles per trip: independent accumulator chains
+          const double* bk[4];
+          double* cp[4];
+          double2 cc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int Kq = min(K + q, I);
+            bk[q] = Ls + tri_idx(8 * Kq + gq, c0 + tq);
+            cp[q] = Ls + tri_idx(8 * I + gq, 8 * Kq + 2 * tq);
+            cc[q] = *reinterpret_cast<double2*>(cp[q]);
+          }
+#pragma unroll
+          for (int kt = 0; kt < 8; ++kt) {
+            if (kt < ks) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dmma884(cc[q].x, cc[q].y, a[kt], bk[q][4 * kt]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (K + q <= I) *reinterpret_cast<double2*>(cp[q]) = cc[q];
+        }
+      }
+      // appended vector: v[c] -= sum_k x[k] L[c][c0 + k]
+      for (int c = row0 + tid; c < npad; c += NTH) {
+        const double* lc = Ls + tri_idx(c, c0);
+        double s = v[c];
+        for (int k = 0; k < w32; ++k) s = fma(-v[c0 + k], lc[k], s);
+        v[c] = s;
+      }
+    }
+    __syncthreads();
+    ptick(prof, 19, tk);
+  }
+  if (Lg) {
+    for (int r = warp; r < n; r += NTH / 32) {
+      const double* s = Ls + tri_idx(r, 0);
+      for (int c = lane; c <= r; c += 32) Lg[(int64_t)r * ld + c] = s[c];
+    }
+    for (int c = tid; c < n; c += NTH) Lg[(int64_t)n * ld + c] = v[c];
+  }
+}
+
+// Filter phase 3 on one CTA: R <= 8 rows of X = W L^-T (in place in global Wr, ld = n) and, when Kr != nullptr,
+// of K = X L^-1, with the whole factor L resident in shared memory.  The 32 x 32 diagonal blocks of L are
+// inverted once (one warp per block, in place), so every block step is DMMA work: an update with the columns
+// already solved and a multiply by the inverse block.  Also returns the mean update  out_m[i] = mp[i] + X[i,:] . u.
+__device__ __noinline__ void trsm_smem(const double* Lg, int64_t ld, int n, double* Wr, int R, double* Kr, const double* u,
+                          const double* mp, double* out_m, double* sm) {
+  double* Ls = sm + TS_L;
+  double* Xs = sm + TS_X;
+  double* Ts = sm + TS_T;
+  double* Part = Ts + 8 * 36;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int nt = warp & 3, half = warp >> 2;
+  const int nbr = (n + 7) >> 3, npad = 8 * nbr, nb32 = (npad + 31) >> 5;
+  constexpr int LDX = TRI_N + 4;
+  tri_load_issue(Ls, Lg, ld, n, nbr);
+  for (int idx = tid; idx < 8 * npad; idx += NTH) {
+    const int r = idx / npad, c = idx - r * npad;
+    Xs[r * LDX + c] = (r < R && c < n) ? __ldcg(Wr + (int64_t)r * ld + c) : 0.0;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // invert the diagonal blocks in place: warp J takes block J; lane c owns column c of the inverse
+  for (int J = warp; J < nb32; J += NTH / 32) {
+    const int c0 = 32 * J, w32 = min(32, npad - c0);
+    const int c = lane;
+    double x[32];
+    const double dinv = (c < w32) ? 1.0 / Ls[tri_idx(c0 + c, c0 + c)] : 1.0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const double rdi = __shfl_sync(0xffffffffu, dinv, i);
+      double s = (i == c) ? 1.0 : 0.0;
+      if (i < w32) {
+        const double* li = Ls + tri_idx(c0 + i, c0);
+#pragma unroll
+        for (int k = 0; k < i; ++k) s = fma(-li[k], x[k], s);      // x[k] == 0 for k < c
+      }
+      x[i] = (i >= c) ? s * rdi : 0.0;
+    }
+    __syncwarp();
+    if (c < w32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < w32) {
+          const int wid = 8 * (((c0 + i) >> 3) + 1) - c0;
+          if (c < wid) Ls[tri_idx(c0 + i, c0 + c)] = x[i];       // zero above the diagonal inside the stored width
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // forward: X L^T = W, block columns left to right
+  for (int J = 0; J < nb32; ++J) {
+    const int c0 = 32 * J, w32 = min(32, npad - c0);
+    const bool act = 8 * nt < w32;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (act) {
+      const double* xa = Xs + gq * LDX + tq;
+      const double* lb = Ls + tri_idx(c0 + 8 * nt + gq, tq);
+      double e0 = 0.0, e1 = 0.0;                       // second accumulator chain (DMMA latency 26 > issue 16)
+      int kt = half;
+      for (; kt + 2 < 8 * J; kt += 4) {
+        dmma884(acc0, acc1, xa[4 * kt], lb[4 * kt]);
+        dmma884(e0, e1, xa[4 * kt + 8], lb[4 * kt + 8]);
+      }
+      if (kt < 8 * J) dmma884(acc0, acc1, xa[4 * kt], lb[4 * kt]);
+      acc0 += e0; acc1 += e1;
+    }
+    if (half == 1) { Part[(nt * 2 + 0) * 32 + lane] = acc0; Part[(nt * 2 + 1) * 32 + lane] = acc1; }
+    __syncthreads();
+    if (half == 0 && act) {
+      const double2 w = *reinterpret_cast<const double2*>(Xs + gq * LDX + c0 + 8 * nt + 2 * tq);
+      Ts[gq * 36 + 8 * nt + 2 * tq] = w.x - (acc0 + Part[(nt * 2 + 0) * 32 + lane]);
+      Ts[gq * 36 + 8 * nt + 2 * tq + 1] = w.y - (acc1 + Part[(nt * 2 + 1) * 32 + lane]);
+    }
+    __syncthreads();
+    if (half == 0 && act) {
+      // X_J[:, n-tile nt] = sum_k T[:, k] inv[n][k], inv lower triangular: k < 8 (nt + 1)
+      double o0 = 0.0, o1 = 0.0, p0 = 0.0, p1 = 0.0;
+      const double* ta = Ts + gq * 36 + tq;
+      const double* ib = Ls + tri_idx(c0 + 8 * nt + gq, c0 + tq);
+      for (int kt = 0; kt < 2 * (nt + 1); kt += 2) {       // the trip count is even
+        dmma884(o0, o1, ta[4 * kt], ib[4 * kt]);
+        dmma884(p0, p1, ta[4 * kt + 4], ib[4 * kt + 4]);
+      }
+      *reinterpret_cast<double2*>(Xs + gq * LDX + c0 + 8 * nt + 2 * tq) = make_double2(o0 + p0, o1 + p1);
+    }
+    __syncthreads();
+  }
+  // X rows back to global, mean update
+  for (int idx = tid; idx < R * n; idx += NTH) {
+    const int r = idx / n, c = idx - r * n;
+    Wr[(int64_t)r * ld + c] = Xs[r * LDX + c];
+  }
+  if (warp < R) {
+    double s = 0.0;
+    for (int a = lane; a < n; a += 32) s = fma(Xs[warp * LDX + a], __ldcg(u + a), s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out_m[warp] = mp[warp] + s;
+  }
+  if (!Kr) return;
+  __syncthreads();
+  // backward: K L = X, block columns right to left (in place in Xs)
+  for (int J = nb32 - 1; J >= 0; --J) {
+    const int c0 = 32 * J, w32 = min(32, npad - c0), c1 = c0 + w32;
+    const bool act = 8 * nt < w32;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (act) {
+      // sum over solved columns k >= c1: K[:, k] L[k][c0 + n]
+      const double* xa = Xs + gq * LDX + c1 + tq;
+      const int ksteps = (npad - c1) >> 2;
+      double e0 = 0.0, e1 = 0.0;
+      int kt = half;
+      for (; kt + 2 < ksteps; kt += 4) {
+        dmma884(acc0, acc1, xa[4 * kt], Ls[tri_idx(c1 + 4 * kt + tq, c0 + 8 * nt + gq)]);
+        dmma884(e0, e1, xa[4 * kt + 8], Ls[tri_idx(c1 + 4 * kt + 8 + tq, c0 + 8 * nt + gq)]);
+      }
+      if (kt < ksteps) dmma884(acc0, acc1, xa[4 * kt], Ls[tri_idx(c1 + 4 * kt + tq, c0 + 8 * nt + gq)]);
+      acc0 += e0; acc1 += e1;
+    }
+    if (half == 1) { Part[(nt * 2 + 0) * 32 + lane] = acc0; Part[(nt * 2 + 1) * 32 + lane] = acc1; }
+    __syncthreads();
+    if (half == 0 && act) {
+      const double2 w = *reinterpret_cast<const double2*>(Xs + gq * LDX + c0 + 8 * nt + 2 * tq);
+      Ts[gq * 36 + 8 * nt + 2 * tq] = w.x - (acc0 + Part[(nt * 2 + 0) * 32 + lane]);
+      Ts[gq * 36 + 8 * nt + 2 * tq + 1] = w.y - (acc1 + Part[(nt * 2 + 1) * 32 + lane]);
+    }
+    __syncthreads();
+    if (half == 0 && act) {
+      // K_J[:, n-tile nt] = sum_k T[:, k] inv[k][n], inv lower triangular: k >= 8 nt
+      double o0 = 0.0, o1 = 0.0, p0 = 0.0, p1 = 0.0;
+      const double* ta = Ts + gq * 36 + tq;
+      for (int kt = 2 * nt; kt < (w32 >> 2); kt += 2) {    // w32 is a multiple of 8: the trip count is even
+        dmma884(o0, o1, ta[4 * kt], Ls[tri_idx(c0 + 4 * kt + tq, c0 + 8 * nt + gq)]);
+        dmma884(p0, p1, ta[4 * kt + 4], Ls[tri_idx(c0 + 4 * kt + 4 + tq, c0 + 8 * nt + gq)]);
+      }
+      *reinterpret_cast<double2*>(Xs + gq * LDX + c0 + 8 * nt + 2 * tq) = make_double2(o0 + p0, o1 + p1);
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < R * n; idx += NTH) {
+    const int r = idx / n, c = idx - r * n;
+    Kr[(int64_t)r * ld + c] = Xs[r * LDX + c];
+  }
+}
+
 // block reduction of one value over the CTA (result valid in thread 0)
 __device__ double block_sum(double v, double* scratch) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -406,6 +857,14 @@ __device__ double block_sum(double v, double* scratch) {
 
 constexpr int DSMAX = 4;
 
+// phase timers (ns, CTA 0): accumulated into the workspace tail when PHYSS_KRON_PROF is set -- measurement aid
+#define KRON_TICK(slot)                                              \
+  if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) {               \
+    const unsigned long long now_ = gtimer();                        \
+    p.prof[slot] += (double)(now_ - tick_);                          \
+    tick_ = now_;                                                    \
+  }
+
 // ------------------------------------------------------------------------------------------- filter
 struct FilterArgs {
   int64_t T;
@@ -416,16 +875,20 @@ struct FilterArgs {
   double jitter;
   double* mf; double* Pf; double* lml;
   double* Pp; double* W; double* Kb; double* SjA; double* SmA; double* mp; double* acc;
+  double* prof;
+  unsigned long long* bar;
 };
 
 __global__ void __launch_bounds__(NTH, 1) kron_filter_kernel(const FilterArgs p) {
   extern __shared__ __align__(16) double sm[];
-  cg::grid_group grid = cg::this_grid();
+  GridBarrier grid;
+  grid.init(p.bar);
   const int cta = blockIdx.x, ncta = gridDim.x, tid = threadIdx.x;
   const int Ns = p.Ns, ds = p.ds, d = p.d, m = p.Ns;
   const int64_t gt = (int64_t)cta * NTH + tid, gstride = (int64_t)ncta * NTH;
   const int cta_lml = ncta > 1 ? 1 : 0;
   if (cta == cta_lml && tid == 0) p.acc[0] = 0.0;
+  unsigned long long tick_ = gtimer();
   for (int64_t k = 0; k < p.T; ++k) {
     const double* At = p.At + (int64_t)p.idx[k] * ds * ds;
     const double* Qt = p.Qt + (int64_t)p.idx[k] * ds * ds;
@@ -492,32 +955,59 @@ __global__ void __launch_bounds__(NTH, 1) kron_filter_kernel(const FilterArgs p)
       p.SjA[(int64_t)m * m + I] = v;
       p.SmA[(int64_t)m * m + I] = v;
     }
+    KRON_TICK(0)
     grid.sync();
+    KRON_TICK(1)
     // ---- phase 2: the two Cholesky factorisations, each with the innovation appended as an extra row
-    if (cta == 0) chol_blocked(p.SjA, m, m, m + 1, sm);
+    const bool resident = m <= TRI_N;
+    if (cta == 0) {
+      if (resident) chol_smem(p.SjA, m, m, p.SjA, sm, p.prof);
+      else chol_blocked(p.SjA, m, m, m + 1, sm, p.prof);
+    }
     if (cta == cta_lml) {
-      if (cta_lml != 0) chol_blocked(p.SmA, m, m, m + 1, sm);
-      else { __syncthreads(); chol_blocked(p.SmA, m, m, m + 1, sm); }
+      if (cta_lml == 0) __syncthreads();
       double ld = 0.0, mh = 0.0, no = 0.0;
+      if (resident) {
+        chol_smem(p.SmA, m, m, nullptr, sm, nullptr);
+        for (int a = tid; a < m; a += NTH) {
+          ld += log(sm[TS_L + tri_idx(a, a)]);
+          const double u = sm[TS_V + a];
+          mh = fma(u, u, mh);
+        }
+      } else {
+        chol_blocked(p.SmA, m, m, m + 1, sm);
+        for (int a = tid; a < m; a += NTH) {
+          ld += log(__ldcg(p.SmA + (int64_t)a * m + a));
+          const double u = __ldcg(p.SmA + (int64_t)m * m + a);
+          mh = fma(u, u, mh);
+        }
+      }
       for (int a = tid; a < m; a += NTH) {
-        ld += log(__ldcg(p.SmA + (int64_t)a * m + a));
-        const double u = __ldcg(p.SmA + (int64_t)m * m + a);
-        mh = fma(u, u, mh);
         const double ya = y[a];
         no += (ya != ya) ? 0.0 : 1.0;
       }
-      double* scr = sm + SM_A + SM_B;
+      __syncthreads();
+      double* scr = sm + TS_T;
       ld = block_sum(ld, scr);
       mh = block_sum(mh, scr);
       no = block_sum(no, scr);
       if (tid == 0) p.acc[0] += -0.5 * (no * 1.8378770664093454835606594728112 + 2.0 * ld + mh);
     }
+    KRON_TICK(2)
     grid.sync();
+    KRON_TICK(3)
     // ---- phase 3: rows of X = W L^-T (in place in W), the mean update, rows of K = X L^-1
     for (int rb = cta; rb * 8 < d; rb += ncta) {
       const int i0 = rb * 8, R = min(8, d - i0);
       double* Xr = p.W + (int64_t)i0 * m;
-      trsm_fwd<1>(Xr, m, R, p.SjA, m, m, sm);
+      double* Kr = p.Kb + (int64_t)i0 * m;
+      if (resident) {
+        trsm_smem(p.SjA, m, m, Xr, R, p.jitter != 0.0 ? Kr : nullptr, p.SjA + (int64_t)m * m, p.mp + i0,
+                  p.mf + k * (int64_t)d + i0, sm);
+        __syncthreads();
+        continue;
+      }
+      trsm_fwd<1>(Xr, m, R, p.SjA, m, m, sm, p.prof);
       {
         const int warp = tid >> 5, lane = tid & 31;
         if (warp < R) {
@@ -528,13 +1018,14 @@ __global__ void __launch_bounds__(NTH, 1) kron_filter_kernel(const FilterArgs p)
         }
       }
       if (p.jitter != 0.0) {
-        double* Kr = p.Kb + (int64_t)i0 * m;
         for (int idx = tid; idx < R * m; idx += NTH) Kr[idx] = __ldcg(Xr + idx);
         __syncthreads();
         trsm_bwd<1>(Kr, m, R, p.SjA, m, m, nullptr, 0, sm);
       }
     }
+    KRON_TICK(4)
     grid.sync();
+    KRON_TICK(5)
     // ---- phase 4: P = P_ - X X^T + jitter K K^T  (== P_ - K S K^T with the un-jittered S)
     {
       Gemm g = {};
@@ -551,7 +1042,9 @@ __global__ void __launch_bounds__(NTH, 1) kron_filter_kernel(const FilterArgs p)
       g.lower = 1;
       gemm_tiles<4>(g, cta, ncta, sm);
     }
+    KRON_TICK(6)
     grid.sync();
+    KRON_TICK(7)
   }
   if (cta == cta_lml && tid == 0) p.lml[0] = p.acc[0];
 }
@@ -637,6 +1130,8 @@ struct RecArgs {
   int project;                 // 1: outputs are H ms [T, Ns], H Ps H^T [T, Ns, Ns]; 0: full state
   double* ms_out; double* Ps_out;
   double* ringP; double* ringm; double* dP; double* T1;
+  double* prof;
+  unsigned long long* bar;
 };
 __device__ __forceinline__ double* ps_state(const RecArgs& p, int64_t k) {
   return p.project ? p.ringP + (k & 1) * (int64_t)p.d * p.d : p.Ps_out + k * (int64_t)p.d * p.d;
@@ -645,7 +1140,8 @@ __device__ __forceinline__ double* ps_state(const RecArgs& p, int64_t k) {
 // the recursion through time: P_s,k = Pf_k + G_k (P_s,k+1 - P_pred,k) G_k^T, m_s,k = mf_k + G_k (m_s,k+1 - A mf_k)
 __global__ void __launch_bounds__(NTH, 1) kron_smooth_rec_kernel(const RecArgs p) {
   extern __shared__ __align__(16) double sm[];
-  cg::grid_group grid = cg::this_grid();
+  GridBarrier grid;
+  grid.init(p.bar);
   const int cta = blockIdx.x, ncta = gridDim.x, tid = threadIdx.x;
   const int Ns = p.Ns, ds = p.ds, d = p.d;
   const int64_t dd = (int64_t)d * d;
@@ -656,6 +1152,7 @@ __global__ void __launch_bounds__(NTH, 1) kron_smooth_rec_kernel(const RecArgs p
     for (int64_t i = gt; i < dd; i += gstride) p.dP[i] = __ldcg(Psn + i) - __ldcg(Pp + i);
   }
   grid.sync();
+  unsigned long long tick_ = gtimer();
   for (int64_t k = p.k_hi; k >= p.k_lo; --k) {
     const double* G = p.Gc + (k - p.k_lo) * dd;
     {
@@ -666,6 +1163,7 @@ __global__ void __launch_bounds__(NTH, 1) kron_smooth_rec_kernel(const RecArgs p
       g.C = p.T1; g.ldc = d;
       gemm_tiles<5>(g, cta, ncta, sm);
     }
+    KRON_TICK(8)
     {
       // mean: one warp per row, rows dealt round-robin over all warps of the grid (from the back, so the CTAs
       // that hold no second GEMM tile take them)
@@ -692,7 +1190,9 @@ __global__ void __launch_bounds__(NTH, 1) kron_smooth_rec_kernel(const RecArgs p
         }
       }
     }
+    KRON_TICK(9)
     grid.sync();
+    KRON_TICK(10)
     {
       Gemm g = {};
       g.npair = 1; g.nt = 1;
@@ -705,7 +1205,9 @@ __global__ void __launch_bounds__(NTH, 1) kron_smooth_rec_kernel(const RecArgs p
       if (p.project) { g.Cp = p.Ps_out + k * (int64_t)Ns * Ns; g.ldp = Ns; g.ds = ds; }
       gemm_tiles<4>(g, cta, ncta, sm);
     }
+    KRON_TICK(11)
     grid.sync();
+    KRON_TICK(12)
   }
 }
 
@@ -745,12 +1247,12 @@ int device_setup(Dev& dv) {
   cudaDeviceGetAttribute(&dv.sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&dv.coop, cudaDevAttrCooperativeLaunch, dev);
   if (!dv.coop) return set_error(PHYSS_ERR_UNSUPPORTED, "kron: device does not support cooperative launches");
-  e = cudaFuncSetAttribute(kron_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BYTES);
+  e = cudaFuncSetAttribute(kron_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BYTES_FILTER);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kron_gain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kron_smooth_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BYTES);
   if (e != cudaSuccess) return cuda_status(e, "kron: cudaFuncSetAttribute(shared memory)");
   int b = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kron_filter_kernel, NTH, SM_BYTES);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kron_filter_kernel, NTH, SM_BYTES_FILTER);
   if (e != cudaSuccess || b < 1) return cuda_status(e == cudaSuccess ? cudaErrorLaunchOutOfResources : e, "kron: occupancy (filter)");
   dv.filter_blocks = dv.sms;            // one CTA per SM: the tile counts are sized for it
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kron_smooth_rec_kernel, NTH, SM_BYTES);
@@ -764,7 +1266,8 @@ constexpr int64_t GAIN_CHUNK_WAVES = 4;   // time steps per smoother chunk = 4 x
 
 inline int64_t align2(int64_t n) { return (n + 1) & ~(int64_t)1; }
 
-struct FilterWs { int64_t Pp, W, Kb, SjA, SmA, mp, acc, total; };
+constexpr int64_t BAR_WORDS = 16 * 66;     // top counter + up to 65 groups of 16 CTAs, one 128-byte line each
+struct FilterWs { int64_t Pp, W, Kb, SjA, SmA, mp, acc, prof, bar, total; };
 FilterWs filter_ws(int Ns, int ds) {
   const int64_t d = (int64_t)Ns * ds, m = Ns;
   FilterWs w{};
@@ -776,10 +1279,12 @@ FilterWs filter_ws(int Ns, int ds) {
   w.SmA = o; o += align2((m + 1) * m);
   w.mp = o; o += align2(d);
   w.acc = o; o += 2;
+  w.prof = o; o += 32;
+  w.bar = o; o += BAR_WORDS;
   w.total = o;
   return w;
 }
-struct SmoothWs { int64_t Gc, Ppc, scratch, ringP, ringm, dP, T1, total, chunk; };
+struct SmoothWs { int64_t Gc, Ppc, scratch, ringP, ringm, dP, T1, prof, bar, total, chunk; };
 SmoothWs smooth_ws(int Ns, int ds, int64_t T, int gain_blocks) {
   const int64_t d = (int64_t)Ns * ds, dd = d * d;
   SmoothWs w{};
@@ -793,6 +1298,8 @@ SmoothWs smooth_ws(int Ns, int ds, int64_t T, int gain_blocks) {
   w.ringm = o; o += align2(2 * d);
   w.dP = o; o += dd;
   w.T1 = o; o += dd;
+  w.prof = o; o += 32;
+  w.bar = o; o += BAR_WORDS;
   w.total = o;
   return w;
 }
@@ -813,6 +1320,14 @@ int64_t physs_kron_workspace_bytes(int64_t T, int32_t Ns, int32_t ds, int32_t sm
   return 8 * smooth_ws(Ns, ds, T, dv.gain_blocks).total + 16;
 }
 
+/* measurement aid: offset (in doubles) of the 32 phase timers inside the workspace (PHYSS_KRON_PROF=1) */
+int64_t physs_kron_prof_offset(int64_t T, int32_t Ns, int32_t ds, int32_t smoother) {
+  if (!smoother) return filter_ws(Ns, ds).prof;
+  Dev dv;
+  if (device_setup(dv) != PHYSS_OK) return -1;
+  return smooth_ws(Ns, ds, T, dv.gain_blocks).prof;
+}
+
 int physs_kf_filter_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, const double* At, const double* Qt,
                              const int32_t* idx, const double* Ks, const double* m0, const double* P0,
                              const double* Y, const double* R, int64_t R_tstride, double jitter, void* ws,
@@ -830,10 +1345,15 @@ int physs_kf_filter_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, co
   a.T = T; a.Ns = Ns; a.ds = ds; a.d = Ns * ds;
   a.At = At; a.Qt = Qt; a.idx = idx; a.Ks = Ks; a.m0 = m0; a.P0 = P0; a.Y = Y; a.R = R; a.R_ts = R_tstride;
   a.jitter = jitter; a.mf = mf; a.Pf = Pf; a.lml = lml;
+  a.prof = getenv("PHYSS_KRON_PROF") ? w + L.prof : nullptr;
+  if (a.prof) cudaMemsetAsync(a.prof, 0, 32 * sizeof(double), (cudaStream_t)stream);
   a.Pp = w + L.Pp; a.W = w + L.W; a.Kb = w + L.Kb; a.SjA = w + L.SjA; a.SmA = w + L.SmA; a.mp = w + L.mp; a.acc = w + L.acc;
+  a.bar = reinterpret_cast<unsigned long long*>(w + L.bar);
+  cudaError_t e = cudaMemsetAsync(a.bar, 0, BAR_WORDS * sizeof(double), (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_status(e, "kron filter: barrier reset");
   void* args[] = {&a};
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)kron_filter_kernel, dim3(dv.filter_blocks), dim3(NTH), args,
-                                              SM_BYTES, (cudaStream_t)stream);
+  e = cudaLaunchCooperativeKernel((void*)kron_filter_kernel, dim3(dv.filter_blocks), dim3(NTH), args, SM_BYTES_FILTER,
+                                  (cudaStream_t)stream);
   return cuda_status(e, "kron_filter_kernel launch");
 }
 
@@ -855,6 +1375,8 @@ int physs_rts_smooth_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, c
   r.Ns = Ns; r.ds = ds; r.d = d; r.At = At; r.idx = idx; r.mf = mf; r.Pf = Pf;
   r.Gc = w + L.Gc; r.Ppc = w + L.Ppc; r.project = project ? 1 : 0; r.ms_out = ms; r.Ps_out = Ps;
   r.ringP = w + L.ringP; r.ringm = w + L.ringm; r.dP = w + L.dP; r.T1 = w + L.T1;
+  r.prof = getenv("PHYSS_KRON_PROF") ? w + L.prof : nullptr;
+  if (r.prof) cudaMemsetAsync(r.prof, 0, 32 * sizeof(double), st);
   kron_emit_last_kernel<<<dv.sms, 256, 0, st>>>(r, T);
   GainArgs g{};
   g.Ns = Ns; g.ds = ds; g.d = d; g.At = At; g.Qt = Qt; g.idx = idx; g.Ks = Ks; g.Pf = Pf; g.jitter = jitter;
@@ -866,8 +1388,11 @@ int physs_rts_smooth_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, c
     const int gb = (int)(n < dv.gain_blocks ? n : dv.gain_blocks);
     kron_gain_kernel<<<gb, NTH, SM_BYTES, st>>>(g);
     r.k_lo = k_lo; r.k_hi = k_hi;
+    r.bar = reinterpret_cast<unsigned long long*>(w + L.bar);
+    cudaError_t e = cudaMemsetAsync(r.bar, 0, BAR_WORDS * sizeof(double), st);
+    if (e != cudaSuccess) return cuda_status(e, "kron smoother: barrier reset");
     void* args[] = {&r};
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)kron_smooth_rec_kernel, dim3(dv.rec_blocks), dim3(NTH), args,
+    e = cudaLaunchCooperativeKernel((void*)kron_smooth_rec_kernel, dim3(dv.rec_blocks), dim3(NTH), args,
                                                 SM_BYTES, st);
     if (e != cudaSuccess) return cuda_status(e, "kron_smooth_rec_kernel launch");
     k_hi = k_lo - 1;

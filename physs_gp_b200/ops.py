@@ -5,6 +5,8 @@ every FLOP of the path runs in libphyss_b200.so.  No CPU fallback: non-CUDA tens
 Broadcasting: every argument is viewed with `expand` to its full [B, ...] shape and the resulting
 batch (and, for R, time) stride is handed to the kernel; a stride of 0 means "shared".
 """
+import os
+
 import numpy as np
 import torch
 
@@ -686,6 +688,9 @@ def rts_smooth_big(mf, Pf, disc, Hout=None, jitter=None, stream=None):
 
 
 # ------------------------------------------------------- separable spatio-temporal prior, hand-written kernels
+kron_prof = {}       # PHYSS_KRON_PROF=1: device views of the phase timers of the last call (measurement aid)
+
+
 class KronDisc:
     """Discretisation of the separable spatio-temporal route (include/physs_b200.h, physs_kf_filter_kron_f64):
     temporal At, Qt [nA, ds, ds] per DISTINCT step size, a DEVICE int32 index [T] selecting the pair of every
@@ -729,6 +734,9 @@ def kf_filter_kron(Y, R, m0, P0, disc, jitter=None, stream=None):
                                           Y.data_ptr(), R.data_ptr(), R_ts, float(jit), ws.data_ptr(),
                                           ws.numel() * 8, mf.data_ptr(), Pf.data_ptr(), lml.data_ptr())
     _lib.check(st, "physs_kf_filter_kron_f64")
+    if os.environ.get("PHYSS_KRON_PROF"):
+        o = lib.physs_kron_prof_offset(T, Ns, ds, 0)
+        kron_prof["filter"] = ws[o:o + 32]
     return lml[0], mf, Pf
 
 
@@ -752,4 +760,7 @@ def rts_smooth_kron(mf, Pf, disc, project=False, jitter=None, stream=None):
                                            1 if project else 0, float(jit), ws.data_ptr(), ws.numel() * 8,
                                            ms.data_ptr(), Ps.data_ptr())
     _lib.check(st, "physs_rts_smooth_kron_f64")
+    if os.environ.get("PHYSS_KRON_PROF"):
+        o = lib.physs_kron_prof_offset(T, Ns, ds, 1)
+        kron_prof["smoother"] = ws[o:o + 32]
     return ms, Ps
