@@ -1062,6 +1062,11 @@ def run_c2(a):
     G = 0.05 * torch.randn((T, Ns, Ns), dtype=torch.float64, device=dev, generator=torch.Generator(dev).manual_seed(1))
     R = G @ G.transpose(-1, -2) + NOISE_VAR * torch.eye(Ns, dtype=torch.float64, device=dev)   # site covariances
 
+    from physs_gp_b200 import settings as _settings
+    if os.environ.get("PHYSS_C2_LIBRARY"):
+        _settings.kron_kernels = False                       # A-B run: the cuBLAS / cuSOLVER-backed library path
+    kron = bool(_settings.kron_kernels)
+
     def step(Yd):
         model = models.SDE_GP(data.TemporalData(t, Yd[:, :, None]), prior, likelihood.BlockDiagonalGaussian(R))
         return model.filter_and_smooth(full_state=False, return_lml=True)
@@ -1125,13 +1130,21 @@ def run_c2(a):
                 "roofline": {"bound": "tensor", "achieved": flops * (value / world) / 1e12, "peak": fp64,
                              "unit": "TFLOP/s", "frac": flops * (value / world) / 1e12 / fp64,
                              "peak_source": "physs_fp64_probe (FP64 FMA pipe), this run", "traffic": None,
-                             "note": "dense sequential flop count per state-step (SURVEY 8d); products and "
-                                     "factorisations are cuBLAS / cuSOLVER fp64 calls enqueued per step"},
+                             "note": "dense sequential flop count per state-step (SURVEY 8d: the reference multiplies "
+                                     "the d x d Kronecker matrices out); " + (
+                                         "hand-written persistent cooperative kernels (csrc/physs_kron.cu: Kronecker-"
+                                         "structured predict, shared-memory Cholesky, DMMA tile GEMMs), no library calls"
+                                         if kron else "products and factorisations are cuBLAS / cuSOLVER fp64 calls "
+                                         "enqueued per step (PHYSS_C2_LIBRARY=1)")},
                 "cpu_baseline": cpu,
                 "e2e": {"value": world * T / elw, "unit": "state-steps/s", "h2d_bytes_per_step": T * Ns * 8 * world,
                         "d2h_bytes_per_step": 2 * T * Ns * 8 * world,
                         "api": "SDE_GP.filter_and_smooth(full_state=False, return_lml=True), pinned host buffers"},
-                "clocks": clocks, "gpu_launches": None}
+                "clocks": clocks,
+                # kernels of libphyss_b200.so per step: the persistent filter + last-step emit + one (gain, recursion)
+                # pair per smoother time chunk of 4 x SM-count steps
+                "gpu_launches": (a.steps * (2 + 2 * -(-(T - 1) // (4 * torch.cuda.get_device_properties(dev).multi_processor_count)))
+                                 if kron else None)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -124,27 +124,34 @@ struct Gemm {
   int lower;
   double* C2; const double* Sub2; int ld2;
   double* Cp; int ldp; int ds;
+  double* prof;                 // measurement aid: slots 24.. (thread 0 of CTA 0)
 };
 
 __device__ __forceinline__ bool vec_ok(const double* p, int64_t ld) {
   return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld & 1) == 0);
 }
+// Warp roles inside gemm_tiles: warps 0-3 (one per scheduler) issue the DMMAs, each on one 8-column strip of the
+// tile with MT independent accumulator pairs; warps 4-7 only stage the NEXT k-chunk with cp.async while the
+// current one is consumed.  (All eight warps doing both put ~900 address / predicate instructions per chunk in
+// front of 80 DMMAs on every warp: measured 3.3 us per 40 x 32 x 128 chunk against 1.35 us of DMMA issue time.)
+constexpr int NLOAD = 128;     // loader threads (tid >= NTH - NLOAD)
 // [ROWS x kpad] block of a row-major matrix -> shared memory (leading dim LDA), zero outside the valid extent
-// vr x vc.  Thread map: 64 threads x 16 bytes cover one row of up to 128 doubles, 4 rows per pass -- shifts only.
+// vr x vc.  lt = loader thread index: 64 threads x 16 bytes cover one row of up to 128 doubles, 2 rows per pass.
 template <int ROWS>
-__device__ __forceinline__ void load_rows(double* dst, const double* src, int64_t ld, int kpad, int vr, int vc, bool vec) {
-  const int c = (threadIdx.x & 63) << 1;
+__device__ __forceinline__ void load_rows(int lt, double* dst, const double* src, int64_t ld, int kpad, int vr, int vc,
+                                          bool vec) {
+  const int c = (lt & 63) << 1;
   if (c >= kpad) return;
-  int r = threadIdx.x >> 6;
+  int r = lt >> 6;
   const double* s = src + (int64_t)r * ld + c;
   double* d = dst + r * LDA + c;
   if (vec && vr >= ROWS && vc >= kpad) {           // interior tile: no predicates
 #pragma unroll
-    for (int i = 0; i < ROWS / 4; ++i) cp_async16(d + i * 4 * LDA, s + (int64_t)i * 4 * ld);
+    for (int i = 0; i < ROWS / 2; ++i) cp_async16(d + i * 2 * LDA, s + (int64_t)i * 2 * ld);
     return;
   }
 #pragma unroll
-  for (int i = 0; i < ROWS / 4; ++i, r += 4, s += 4 * ld, d += 4 * LDA) {
+  for (int i = 0; i < ROWS / 2; ++i, r += 2, s += 2 * ld, d += 2 * LDA) {
     if (vec && r < vr && c + 1 < vc) {
       cp_async16(d, s);
     } else {
@@ -154,16 +161,17 @@ __device__ __forceinline__ void load_rows(double* dst, const double* src, int64_
     }
   }
 }
-// [kpad x 32] block ([K x N] operand) -> shared memory (leading dim LDB): 16 threads per row, 16 rows per pass
-__device__ __forceinline__ void load_kn(double* dst, const double* src, int64_t ld, int kpad, int vr, int vc, bool vec) {
-  const int c = (threadIdx.x & 15) << 1;
+// [kpad x 32] block ([K x N] operand) -> shared memory (leading dim LDB): 16 threads per row, 8 rows per pass
+__device__ __forceinline__ void load_kn(int lt, double* dst, const double* src, int64_t ld, int kpad, int vr, int vc,
+                                        bool vec) {
+  const int c = (lt & 15) << 1;
   if (vec && vr >= kpad && vc >= TN) {             // interior tile: no predicates
-    const double* s = src + (int64_t)(threadIdx.x >> 4) * ld + c;
-    double* d = dst + (threadIdx.x >> 4) * LDB + c;
-    for (int r = threadIdx.x >> 4; r < kpad; r += 16, s += 16 * ld, d += 16 * LDB) cp_async16(d, s);
+    const double* s = src + (int64_t)(lt >> 4) * ld + c;
+    double* d = dst + (lt >> 4) * LDB + c;
+    for (int r = lt >> 4; r < kpad; r += 8, s += 8 * ld, d += 8 * LDB) cp_async16(d, s);
     return;
   }
-  for (int r = threadIdx.x >> 4; r < kpad; r += 16) {
+  for (int r = lt >> 4; r < kpad; r += 8) {
     const double* s = src + (int64_t)r * ld + c;
     double* d = dst + r * LDB + c;
     if (vec && r < vr && c + 1 < vc) {
@@ -180,7 +188,8 @@ template <int MT>
 __device__ __noinline__ void gemm_tiles(const Gemm& g, int cta, int ncta, double* sm) {
   constexpr int TM = 8 * MT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-  const int wcol = warp & 3, half = warp >> 2;
+  const bool loader = tid >= NTH - NLOAD;
+  const int lt = tid - (NTH - NLOAD);
   const int tm = (g.M + TM - 1) / TM, tn = (g.N + TN - 1) / TN;
   const int ntiles = g.lower ? tm * (tm + 1) / 2 : tm * tn;
   // k-chunks: as few as fit KC, all of (nearly) the same length, a multiple of 4
@@ -194,7 +203,7 @@ __device__ __noinline__ void gemm_tiles(const Gemm& g, int cta, int ncta, double
   if (nitems == 0) return;
   double* As = sm;
   double* Bs = sm + SM_A;
-  double* Red = sm + SM_A + SM_B;
+  double* Tt = sm + SM_A + SM_B;
   const bool va0 = vec_ok(g.A[0], g.lda[0]), vb0 = vec_ok(g.B[0], g.ldb[0]);
   const bool va1 = g.npair > 1 && vec_ok(g.A[1], g.lda[1]), vb1 = g.npair > 1 && vec_ok(g.B[1], g.ldb[1]);
 
@@ -219,19 +228,19 @@ __device__ __noinline__ void gemm_tiles(const Gemm& g, int cta, int ncta, double
     const int kc = max(0, min(kch, g.K[pr] - k0));
     kpad = (kc + 3) & ~3;
   };
-  int ld_tile = 0, ld_ch = 0, ld_r0, ld_c0;      // the (tile, chunk) the next issue() stages
+  int ld_tile = 0, ld_ch = 0, ld_r0, ld_c0;      // loaders: the (tile, chunk) the next issue() stages
   tile_origin(0, ld_r0, ld_c0);
   auto issue = [&](int buf) {
     int pr, k0, kpad;
     chunk_of(ld_ch, pr, k0, kpad);
     const int K = g.K[pr];
-    load_rows<TM>(As + buf * TMMAX * LDA, g.A[pr] + (int64_t)ld_r0 * g.lda[pr] + k0, g.lda[pr], kpad, g.M - ld_r0,
+    load_rows<TM>(lt, As + buf * TMMAX * LDA, g.A[pr] + (int64_t)ld_r0 * g.lda[pr] + k0, g.lda[pr], kpad, g.M - ld_r0,
                   K - k0, pr ? va1 : va0);
     if (g.nt)
-      load_rows<TN>(Bs + buf * KC * LDB, g.B[pr] + (int64_t)ld_c0 * g.ldb[pr] + k0, g.ldb[pr], kpad, g.N - ld_c0,
+      load_rows<TN>(lt, Bs + buf * KC * LDB, g.B[pr] + (int64_t)ld_c0 * g.ldb[pr] + k0, g.ldb[pr], kpad, g.N - ld_c0,
                     K - k0, pr ? vb1 : vb0);
     else
-      load_kn(Bs + buf * KC * LDB, g.B[pr] + (int64_t)k0 * g.ldb[pr] + ld_c0, g.ldb[pr], kpad, K - k0, g.N - ld_c0,
+      load_kn(lt, Bs + buf * KC * LDB, g.B[pr] + (int64_t)k0 * g.ldb[pr] + ld_c0, g.ldb[pr], kpad, K - k0, g.N - ld_c0,
               pr ? vb1 : vb0);
     cp_async_commit();
     if (++ld_ch == nch) {
@@ -244,71 +253,88 @@ __device__ __noinline__ void gemm_tiles(const Gemm& g, int cta, int ncta, double
   double acc[MT][2];
   int r0, c0;
   tile_origin(0, r0, c0);
-#pragma unroll
-  for (int i = 0; i < NST - 1; ++i) {
-    if (i < nitems) issue(i);
+  if (loader) {                 // two chunks in flight from the start
+    issue(0);
+    if (nitems > 1) issue(1);
     else cp_async_commit();
+    cp_async_wait<1>();
   }
+  double addv[MT][2];
   int ch = 0, tile_no = 0;
+  unsigned long long tk = gtimer();
   for (int it = 0; it < nitems; ++it) {
     int pr, k0, kpad;
     chunk_of(ch, pr, k0, kpad);
-    if (ch == 0) {
+    ptick(g.prof, 24, tk);
+    __syncthreads();            // chunk `it` has landed (the loaders waited for it); chunk it - 1 has been consumed
+    ptick(g.prof, it == 0 ? 25 : 26, tk);
+    if (loader) {
+      if (it >= 1 && it + 1 < nitems) issue((it + 1) & 1);
+      cp_async_wait<0>();
+    } else {
+      if (ch == nch - 1 && g.Add) {                  // the addend of the epilogue: loads in flight during the k-loop
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
-    } else if (ch == nch0) {
-      const double f = g.sg[0] / g.sg[1];        // second operand pair: final scale is sg[1]
+        for (int mt = 0; mt < MT; ++mt) {
+          const int row = r0 + 8 * mt + gq, col = c0 + 8 * warp + 2 * tq;
+          addv[mt][0] = (row < g.M && col < g.N) ? __ldcg(g.Add + (int64_t)row * g.ldadd + col) : 0.0;
+          addv[mt][1] = (row < g.M && col + 1 < g.N) ? __ldcg(g.Add + (int64_t)row * g.ldadd + col + 1) : 0.0;
+        }
+      }
+      if (ch == 0) {
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) { acc[mt][0] *= f; acc[mt][1] *= f; }
-    }
-    if (it + NST - 1 < nitems) issue((it + NST - 1) % NST);      // refills the buffer consumed one iteration ago
-    else cp_async_commit();                                      // (empty group: keeps the group count uniform)
-    cp_async_wait<NST - 1>();
-    __syncthreads();
-    {
-      const double* as = As + (it % NST) * TMMAX * LDA + gq * LDA + tq;
-      const double* bs = Bs + (it % NST) * KC * LDB + (g.nt ? (8 * wcol + gq) * LDA + tq : tq * LDB + 8 * wcol + gq);
+        for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+      } else if (ch == nch0) {
+        const double f = g.sg[0] / g.sg[1];        // second operand pair: the final scale is sg[1]
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) { acc[mt][0] *= f; acc[mt][1] *= f; }
+      }
+      const double* as = As + (it & 1) * TMMAX * LDA + gq * LDA + tq;
+      const double* bs = Bs + (it & 1) * KC * LDB + (g.nt ? (8 * warp + gq) * LDA + tq : tq * LDB + 8 * warp + gq);
       const int bstep = g.nt ? 4 : 4 * LDB;
       const int ksteps = kpad >> 2;
-      int kt = half;
-      for (; kt + 2 < ksteps; kt += 4) {               // two k-steps per trip: all fragment loads ahead of the DMMAs
-        double a0[MT], a1[MT];
-        const double b0 = bs[kt * bstep], b1 = bs[(kt + 2) * bstep];
+      // software-pipelined: the fragments of k-step kt + 1 are loaded before the DMMAs of k-step kt are issued
+      // (a warp issues in order; with the loads behind the DMMAs the FP64 pipe idles for a shared-memory
+      // round trip every step -- measured 29 instead of 16 cycles per DMMA)
+      double a0[MT], a1[MT], b0, b1;
+      if (ksteps > 0) {
+        b0 = bs[0];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) { a0[mt] = as[8 * mt * LDA + 4 * kt]; a1[mt] = as[8 * mt * LDA + 4 * kt + 8]; }
+        for (int mt = 0; mt < MT; ++mt) a0[mt] = as[8 * mt * LDA];
+      }
+      int kt = 0;
+      for (; kt + 2 <= ksteps; kt += 2) {
+        b1 = bs[(kt + 1) * bstep];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) a1[mt] = as[8 * mt * LDA + 4 * kt + 4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][0], acc[mt][1], a0[mt], b0);
+        if (kt + 2 < ksteps) {
+          b0 = bs[(kt + 2) * bstep];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) a0[mt] = as[8 * mt * LDA + 4 * kt + 8];
+        }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][0], acc[mt][1], a1[mt], b1);
       }
-      for (; kt < ksteps; kt += 2) {
-        const double b = bs[kt * bstep];
+      if (kt < ksteps) {
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][0], acc[mt][1], as[8 * mt * LDA + 4 * kt], b);
+        for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][0], acc[mt][1], a0[mt], b0);
       }
     }
-    __syncthreads();
+    ptick(g.prof, 27, tk);
     if (ch == nch - 1) {
       const double sgl = g.sg[g.npair - 1];
       const bool mirror = g.lower && r0 > c0;
-      if (half == 1) {
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          Red[((wcol * MT + mt) * 2 + 0) * 32 + lane] = acc[mt][0];
-          Red[((wcol * MT + mt) * 2 + 1) * 32 + lane] = acc[mt][1];
-        }
-      }
-      __syncthreads();
-      if (half == 0) {
+      if (!loader) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const int row = r0 + 8 * mt + gq;
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int col = c0 + 8 * wcol + 2 * tq + e;
-            double v = sgl * (acc[mt][e] + Red[((wcol * MT + mt) * 2 + e) * 32 + lane]);
+            const int col = c0 + 8 * warp + 2 * tq + e;
+            double v = sgl * acc[mt][e];
             if (row < g.M && col < g.N) {
-              if (g.Add) v += __ldcg(g.Add + (int64_t)row * g.ldadd + col);
+              if (g.Add) v += addv[mt][e];
               g.C[(int64_t)row * g.ldc + col] = v;
               if (g.C2) g.C2[(int64_t)row * g.ld2 + col] = v - __ldcg(g.Sub2 + (int64_t)row * g.ld2 + col);
               if (g.Cp && row % g.ds == 0 && col % g.ds == 0) g.Cp[(int64_t)(row / g.ds) * g.ldp + col / g.ds] = v;
@@ -318,12 +344,12 @@ __device__ __noinline__ void gemm_tiles(const Gemm& g, int cta, int ncta, double
         }
       }
       if (mirror) {                                   // MT == 4 here: a 32 x 32 tile strictly below the diagonal
-        __syncthreads();
-        if (half == 0) {
+        __syncthreads();                              // (Tt may still be read by the previous tile's mirror stores)
+        if (!loader) {
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
-            Red[(8 * mt + gq) * 33 + 8 * wcol + 2 * tq] = acc[mt][0];
-            Red[(8 * mt + gq) * 33 + 8 * wcol + 2 * tq + 1] = acc[mt][1];
+            Tt[(8 * mt + gq) * 33 + 8 * warp + 2 * tq] = acc[mt][0];
+            Tt[(8 * mt + gq) * 33 + 8 * warp + 2 * tq + 1] = acc[mt][1];
           }
         }
         __syncthreads();
@@ -331,7 +357,7 @@ __device__ __noinline__ void gemm_tiles(const Gemm& g, int cta, int ncta, double
           const int cc = idx >> 5, rr = idx & 31;      // consecutive lanes: consecutive columns of the mirrored row
           const int row = c0 + cc, col = r0 + rr;
           if (row < g.N && col < g.M) {
-            const double v = Red[rr * 33 + cc];
+            const double v = Tt[rr * 33 + cc];
             g.C[(int64_t)row * g.ldc + col] = v;
             if (g.C2) g.C2[(int64_t)row * g.ld2 + col] = v - __ldcg(g.Sub2 + (int64_t)row * g.ld2 + col);
             if (g.Cp && row % g.ds == 0 && col % g.ds == 0) g.Cp[(int64_t)(row / g.ds) * g.ldp + col / g.ds] = v;
@@ -344,6 +370,8 @@ __device__ __noinline__ void gemm_tiles(const Gemm& g, int cta, int ncta, double
       ++ch;
     }
   }
+  ptick(g.prof, 28, tk);
+  __syncthreads();              // the staging buffers are free again
 }
 
 // ------------------------------------------------------------------------- 32 x 32 diagonal blocks
@@ -538,12 +566,15 @@ constexpr size_t SM_BYTES_FILTER = (TS_DOUBLES > SM_DOUBLES ? TS_DOUBLES : SM_DO
 
 // global (row-major, ld) lower triangle -> shared triangle; rows >= n are identity padding
 __device__ void tri_load_issue(double* Ls, const double* Sg, int64_t ld, int n, int nbr) {
+  // one warp per block row, lane = (row in the block row, one of four interleaved 16-byte column units): no
+  // divisions, every lane busy whatever the row length
   const bool vec = vec_ok(Sg, ld);
-  for (int r = threadIdx.x >> 5; r < 8 * nbr; r += NTH / 32) {
-    const int I = r >> 3, wid = 8 * (I + 1);
-    double* d = Ls + tri_off(I) + (r & 7) * tri_ld(I);
+  const int lane = threadIdx.x & 31, rl = lane >> 2, sub = lane & 3;
+  for (int I = threadIdx.x >> 5; I < nbr; I += NTH / 32) {
+    const int r = 8 * I + rl;
+    double* d = Ls + tri_off(I) + rl * tri_ld(I);
     const double* s = Sg + (int64_t)r * ld;
-    for (int c = (threadIdx.x & 31) << 1; c < wid; c += 64) {
+    for (int c = 2 * sub; c < 8 * (I + 1); c += 8) {
       if (r < n && vec && c + 1 < n) {
         cp_async16(d + c, s + c);
       } else {
@@ -585,16 +616,18 @@ __device__ __noinline__ void tri_diag_factor(double* Ls, int c0, int w32, double
     if (i == j) rdi = rs;
 #pragma unroll
     for (int c2 = (j + 1) >> 1; c2 < 16; ++c2) {
+      // unconditional: entries above the diagonal (c > i) turn into garbage that nothing reads -- the column
+      // buffer is only read at rows >= j -- and that is zeroed on write-back; a predicate costs two selects each
       const double2 q = reinterpret_cast<const double2*>(cb)[c2];
-      if (2 * c2 > j && 2 * c2 <= i) r[2 * c2] = fma(-t, q.x, r[2 * c2]);
-      if (2 * c2 + 1 <= i) r[2 * c2 + 1] = fma(-t, q.y, r[2 * c2 + 1]);
+      if (2 * c2 > j) r[2 * c2] = fma(-t, q.x, r[2 * c2]);
+      r[2 * c2 + 1] = fma(-t, q.y, r[2 * c2 + 1]);
     }
   }
   rd[i] = rdi;
   const int wid = 8 * (((c0 + i) >> 3) + 1) - c0;      // stored columns of this row inside the block
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
-    Dg[i * 33 + c] = r[c];
+    Dg[i * 33 + c] = (c <= i) ? r[c] : 0.0;
     if (i < w32 && c < wid) Ls[base + c] = (c <= i) ? r[c] : 0.0;
   }
 }
@@ -638,56 +671,67 @@ __device__ __noinline__ void chol_smem(const double* Sg, int64_t ld, int n, doub
   cp_async_wait<0>();
   __syncthreads();
   ptick(prof, 16, tk);
+  // four 8 x 8 tiles (I, K0 .. K0 + 3) of the trailing update C[I][K] -= L[I][c0..] L[K][c0..]^T: independent
+  // accumulator chains (DMMA latency 26 cycles > issue interval 16)
+  auto quad = [&](int I, int K0, int c0, int ks) {
+    double a[8];
+    const double* ai = Ls + tri_idx(8 * I + gq, c0 + tq);
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt) a[kt] = kt < ks ? -ai[4 * kt] : 0.0;
+    const double* bk[4];
+    double* cp[4];
+    double2 cc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int Kq = min(K0 + q, I);
+      bk[q] = Ls + tri_idx(8 * Kq + gq, c0 + tq);
+      cp[q] = Ls + tri_idx(8 * I + gq, 8 * Kq + 2 * tq);
+      cc[q] = *reinterpret_cast<double2*>(cp[q]);
+    }
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt) {
+      if (kt < ks) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dmma884(cc[q].x, cc[q].y, a[kt], bk[q][4 * kt]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (K0 + q <= I) *reinterpret_cast<double2*>(cp[q]) = cc[q];
+  };
+  // Right-looking, 32 columns per step, with look-ahead: once the NEXT block column is up to date, warp 0 factors
+  // its diagonal block (a chain of 32 dependent pivots, ~6 us) while warps 1-7 finish the trailing update.
+  if (warp == 0) tri_diag_factor(Ls, 0, min(32, npad), Dg, rd, sm + TS_T);
+  __syncthreads();
+  ptick(prof, 17, tk);
   for (int c0 = 0; c0 < npad; c0 += 32) {
     const int w32 = min(32, npad - c0);
-    if (warp == 0) tri_diag_factor(Ls, c0, w32, Dg, rd, sm + TS_T);
-    __syncthreads();
-    ptick(prof, 17, tk);
     const int row0 = c0 + w32, nr = npad - row0;
     tri_panel_solve(Ls, v, c0, row0, nr, Dg, rd);
     __syncthreads();
     ptick(prof, 18, tk);
     if (nr > 0) {
-      // trailing update C[I][K] -= L[I][c0..] L[K][c0..]^T on 8 x 8 tiles, block rows dealt round-robin to warps
       const int I0 = row0 >> 3, ks = w32 >> 2;
-      for (int I = I0 + warp; I < nbr; I += NTH / 32) {
-        double a[8];
-        const double* ai = Ls + tri_idx(8 * I + gq, c0 + tq);
-#pragma unroll
-        for (int kt = 0; kt < 8; ++kt) a[kt] = kt < ks ? -ai[4 * kt] : 0.0;
-        for (int K = I0; K <= I; K += 4) {           // four tiles per trip: independent accumulator chains
-          const double* bk[4];
-          double* cp[4];
-          double2 cc[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int Kq = min(K + q, I);
-            bk[q] = Ls + tri_idx(8 * Kq + gq, c0 + tq);
-            cp[q] = Ls + tri_idx(8 * I + gq, 8 * Kq + 2 * tq);
-            cc[q] = *reinterpret_cast<double2*>(cp[q]);
-          }
-#pragma unroll
-          for (int kt = 0; kt < 8; ++kt) {
-            if (kt < ks) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) dmma884(cc[q].x, cc[q].y, a[kt], bk[q][4 * kt]);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (K + q <= I) *reinterpret_cast<double2*>(cp[q]) = cc[q];
-        }
-      }
-      // appended vector: v[c] -= sum_k x[k] L[c][c0 + k]
-      for (int c = row0 + tid; c < npad; c += NTH) {
+      for (int I = I0 + warp; I < nbr; I += NTH / 32) quad(I, I0, c0, ks);      // next block column first
+      for (int c = row0 + tid; c < npad; c += NTH) {                            // appended vector
         const double* lc = Ls + tri_idx(c, c0);
         double s = v[c];
         for (int k = 0; k < w32; ++k) s = fma(-v[c0 + k], lc[k], s);
         v[c] = s;
       }
+      __syncthreads();
+      ptick(prof, 19, tk);
+      if (warp == 0) {
+        tri_diag_factor(Ls, row0, min(32, npad - row0), Dg, rd, sm + TS_T);
+      } else {
+        int cnt = 0;
+        for (int I = I0 + 4; I < nbr; ++I)
+          for (int K0 = I0 + 4; K0 <= I; K0 += 4)
+            if (cnt++ % (NTH / 32 - 1) == warp - 1) quad(I, K0, c0, ks);
+      }
+      __syncthreads();
+      ptick(prof, 17, tk);
     }
-    __syncthreads();
-    ptick(prof, 19, tk);
   }
   if (Lg) {
     for (int r = warp; r < n; r += NTH / 32) {
@@ -703,7 +747,8 @@ __device__ __noinline__ void chol_smem(const double* Sg, int64_t ld, int n, doub
 // inverted once (one warp per block, in place), so every block step is DMMA work: an update with the columns
 // already solved and a multiply by the inverse block.  Also returns the mean update  out_m[i] = mp[i] + X[i,:] . u.
 __device__ __noinline__ void trsm_smem(const double* Lg, int64_t ld, int n, double* Wr, int R, double* Kr, const double* u,
-                          const double* mp, double* out_m, double* sm) {
+                          const double* mp, double* out_m, double* sm, double* prof) {
+  unsigned long long tk = gtimer();
   double* Ls = sm + TS_L;
   double* Xs = sm + TS_X;
   double* Ts = sm + TS_T;
@@ -719,6 +764,7 @@ __device__ __noinline__ void trsm_smem(const double* Lg, int64_t ld, int n, doub
   }
   cp_async_wait<0>();
   __syncthreads();
+  ptick(prof, 20, tk);
   // invert the diagonal blocks in place: warp J takes block J; lane c owns column c of the inverse
   for (int J = warp; J < nb32; J += NTH / 32) {
     const int c0 = 32 * J, w32 = min(32, npad - c0);
@@ -731,8 +777,15 @@ __device__ __noinline__ void trsm_smem(const double* Lg, int64_t ld, int n, doub
       double s = (i == c) ? 1.0 : 0.0;
       if (i < w32) {
         const double* li = Ls + tri_idx(c0 + i, c0);
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;                     // four partial sums: the dot product is a chain
 #pragma unroll
-        for (int k = 0; k < i; ++k) s = fma(-li[k], x[k], s);      // x[k] == 0 for k < c
+        for (int k = 0; k < i; ++k) {                             // x[k] == 0 for k < c
+          if ((k & 3) == 0) s = fma(-li[k], x[k], s);
+          else if ((k & 3) == 1) s1 = fma(-li[k], x[k], s1);
+          else if ((k & 3) == 2) s2 = fma(-li[k], x[k], s2);
+          else s3 = fma(-li[k], x[k], s3);
+        }
+        s = (s + s1) + (s2 + s3);
       }
       x[i] = (i >= c) ? s * rdi : 0.0;
     }
@@ -748,6 +801,7 @@ __device__ __noinline__ void trsm_smem(const double* Lg, int64_t ld, int n, doub
     }
   }
   __syncthreads();
+  ptick(prof, 21, tk);
   // forward: X L^T = W, block columns left to right
   for (int J = 0; J < nb32; ++J) {
     const int c0 = 32 * J, w32 = min(32, npad - c0);
@@ -797,6 +851,7 @@ __device__ __noinline__ void trsm_smem(const double* Lg, int64_t ld, int n, doub
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) out_m[warp] = mp[warp] + s;
   }
+  ptick(prof, 22, tk);
   if (!Kr) return;
   __syncthreads();
   // backward: K L = X, block columns right to left (in place in Xs)
@@ -841,6 +896,7 @@ __device__ __noinline__ void trsm_smem(const double* Lg, int64_t ld, int n, doub
     const int r = idx / n, c = idx - r * n;
     Kr[(int64_t)r * ld + c] = Xs[r * LDX + c];
   }
+  ptick(prof, 23, tk);
 }
 
 // block reduction of one value over the CTA (result valid in thread 0)
@@ -1003,7 +1059,7 @@ __global__ void __launch_bounds__(NTH, 1) kron_filter_kernel(const FilterArgs p)
       double* Kr = p.Kb + (int64_t)i0 * m;
       if (resident) {
         trsm_smem(p.SjA, m, m, Xr, R, p.jitter != 0.0 ? Kr : nullptr, p.SjA + (int64_t)m * m, p.mp + i0,
-                  p.mf + k * (int64_t)d + i0, sm);
+                  p.mf + k * (int64_t)d + i0, sm, p.prof);
         __syncthreads();
         continue;
       }
@@ -1152,18 +1208,21 @@ __global__ void __launch_bounds__(NTH, 1) kron_smooth_rec_kernel(const RecArgs p
     for (int64_t i = gt; i < dd; i += gstride) p.dP[i] = __ldcg(Psn + i) - __ldcg(Pp + i);
   }
   grid.sync();
-  unsigned long long tick_ = gtimer();
+  unsigned long long tick_ = gtimer(), tcta_ = tick_;
   for (int64_t k = p.k_hi; k >= p.k_lo; --k) {
     const double* G = p.Gc + (k - p.k_lo) * dd;
+    tcta_ = gtimer();
     {
       Gemm g = {};
       g.npair = 1; g.nt = 0;
       g.A[0] = G; g.lda[0] = d; g.B[0] = p.dP; g.ldb[0] = d; g.K[0] = d; g.sg[0] = 1.0;
       g.M = d; g.N = d;
       g.C = p.T1; g.ldc = d;
+      g.prof = p.prof;
       gemm_tiles<5>(g, cta, ncta, sm);
     }
     KRON_TICK(8)
+    if (p.prof && tid == 0) { const unsigned long long now_ = gtimer(); p.prof[32 + 2 * cta] += (double)(now_ - tcta_); tcta_ = now_; }
     {
       // mean: one warp per row, rows dealt round-robin over all warps of the grid (from the back, so the CTAs
       // that hold no second GEMM tile take them)
@@ -1172,27 +1231,44 @@ __global__ void __launch_bounds__(NTH, 1) kron_smooth_rec_kernel(const RecArgs p
       const double* msn = p.ringm + ((k + 1) & 1) * (int64_t)d;
       double* msk = p.ringm + (k & 1) * (int64_t)d;
       const int lane = tid & 31;
-      const int gw = (ncta - 1 - cta) * (NTH / 32) + (tid >> 5), nw = ncta * (NTH / 32);
-      for (int row = gw; row < d; row += nw) {
-        double s = 0.0;
-        for (int c = lane; c < d; c += 32) {
+      // rows go to the CTAs that hold no tile of the product above when there are any (their work is then hidden
+      // behind the GEMM), else to every CTA
+      const int nt1 = ((d + 39) / 40) * ((d + 31) / 32);
+      const int first = ncta > nt1 ? nt1 : 0;
+      const int gw = cta >= first ? (cta - first) * (NTH / 32) + (tid >> 5) : d, nw = (ncta - first) * (NTH / 32);
+      if (cta >= first) {
+        double* dm = sm;                              // m_s,k+1 - A mf_k, once per CTA
+        for (int c = tid; c < d; c += NTH) {
           const int J = c / ds, b = c - J * ds;
           double am = 0.0;
           for (int b2 = 0; b2 < ds; ++b2) am = fma(At[b * ds + b2], mfk[J * ds + b2], am);
-          s = fma(__ldcg(G + (int64_t)row * d + c), __ldcg(msn + c) - am, s);
+          dm[c] = __ldcg(msn + c) - am;
         }
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) {
-          const double v = mfk[row] + s;
-          msk[row] = v;
-          if (!p.project) p.ms_out[k * (int64_t)d + row] = v;
-          else if (row % ds == 0) p.ms_out[k * (int64_t)Ns + row / ds] = v;
+        __syncthreads();
+        for (int row = gw; row < d; row += nw) {
+          const double* gr = G + (int64_t)row * d;
+          double s0 = 0.0, s1 = 0.0;
+          int c = lane;
+          for (; c + 32 < d; c += 64) {
+            s0 = fma(__ldcg(gr + c), dm[c], s0);
+            s1 = fma(__ldcg(gr + c + 32), dm[c + 32], s1);
+          }
+          if (c < d) s0 = fma(__ldcg(gr + c), dm[c], s0);
+          double s = s0 + s1;
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0) {
+            const double v = mfk[row] + s;
+            msk[row] = v;
+            if (!p.project) p.ms_out[k * (int64_t)d + row] = v;
+            else if (row % ds == 0) p.ms_out[k * (int64_t)Ns + row / ds] = v;
+          }
         }
       }
     }
     KRON_TICK(9)
     grid.sync();
     KRON_TICK(10)
+    tcta_ = gtimer();
     {
       Gemm g = {};
       g.npair = 1; g.nt = 1;
@@ -1206,6 +1282,7 @@ __global__ void __launch_bounds__(NTH, 1) kron_smooth_rec_kernel(const RecArgs p
       gemm_tiles<4>(g, cta, ncta, sm);
     }
     KRON_TICK(11)
+    if (p.prof && tid == 0) { const unsigned long long now_ = gtimer(); p.prof[32 + 2 * cta + 1] += (double)(now_ - tcta_); }
     grid.sync();
     KRON_TICK(12)
   }
@@ -1298,7 +1375,7 @@ SmoothWs smooth_ws(int Ns, int ds, int64_t T, int gain_blocks) {
   w.ringm = o; o += align2(2 * d);
   w.dP = o; o += dd;
   w.T1 = o; o += dd;
-  w.prof = o; o += 32;
+  w.prof = o; o += 32 + 2 * 1024;
   w.bar = o; o += BAR_WORDS;
   w.total = o;
   return w;
@@ -1376,7 +1453,7 @@ int physs_rts_smooth_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, c
   r.Gc = w + L.Gc; r.Ppc = w + L.Ppc; r.project = project ? 1 : 0; r.ms_out = ms; r.Ps_out = Ps;
   r.ringP = w + L.ringP; r.ringm = w + L.ringm; r.dP = w + L.dP; r.T1 = w + L.T1;
   r.prof = getenv("PHYSS_KRON_PROF") ? w + L.prof : nullptr;
-  if (r.prof) cudaMemsetAsync(r.prof, 0, 32 * sizeof(double), st);
+  if (r.prof) cudaMemsetAsync(r.prof, 0, (32 + 2 * 1024) * sizeof(double), st);
   kron_emit_last_kernel<<<dv.sms, 256, 0, st>>>(r, T);
   GainArgs g{};
   g.Ns = Ns; g.ds = ds; g.d = d; g.At = At; g.Qt = Qt; g.idx = idx; g.Ks = Ks; g.Pf = Pf; g.jitter = jitter;

@@ -762,5 +762,5 @@ def rts_smooth_kron(mf, Pf, disc, project=False, jitter=None, stream=None):
     _lib.check(st, "physs_rts_smooth_kron_f64")
     if os.environ.get("PHYSS_KRON_PROF"):
         o = lib.physs_kron_prof_offset(T, Ns, ds, 1)
-        kron_prof["smoother"] = ws[o:o + 32]
+        kron_prof["smoother"] = ws[o:o + 32 + 2048]
     return ms, Ps

@@ -33,7 +33,12 @@ for rep in range(reps):
         f = ops.kron_prof["filter"].cpu().numpy() / T / 1e3
         s_ = ops.kron_prof["smoother"].cpu().numpy() / T / 1e3
         print("  filter us/step: F1 %.1f sync %.1f | F2 chol %.1f (gemm %.1f diag %.1f subst %.1f) sync %.1f | F3 trsm %.1f "
-              "(fwd: gemm %.1f diag_load %.1f subst %.1f) sync %.1f | F4 %.1f sync %.1f"
-              % (f[0], f[1], f[2], f[16], f[17], f[18], f[3], f[4], f[20], f[21], f[22], f[5], f[6], f[7]))
+              "(load %.1f inv %.1f fwd %.1f bwd %.1f) sync %.1f | F4 %.1f sync %.1f"
+              % (f[0], f[1], f[2], f[16], f[17], f[18], f[3], f[4], f[20], f[21], f[22], f[23], f[5], f[6], f[7]))
         print("  smoother rec us/step: B1 gemm %.1f mean %.1f sync %.1f | B2 gemm %.1f sync %.1f"
               % (s_[8], s_[9], s_[10], s_[11], s_[12]))
+        pc = s_[32:32 + 2 * 148].reshape(148, 2)
+        print("  per-CTA B1 gemm us/step:", np.round(pc[::10, 0], 1), "max %.1f" % pc[:, 0].max())
+        print("  per-CTA B2 gemm us/step:", np.round(pc[::10, 1], 1), "max %.1f" % pc[:, 1].max())
+        print("  B1 gemm detail (CTA 0) us/step: setup %.2f first-wait %.2f later-waits %.2f compute %.2f epilogue %.2f"
+              % (s_[24], s_[25], s_[26], s_[27], s_[28]))
