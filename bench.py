@@ -940,7 +940,13 @@ def cvi_measure(a, dev, world, rank, local, B, T, steps, warmup, with_clocks, cp
     q = cvi.FullConjugateGaussian(t, prior, 1, B=B, device=dev, filter_type=a.filter_type)
     model = cvi.VGP(Yh, cvi.PoissonLik(1.0), q, ell_quad_points=20)
 
+    graphed = not os.environ.get("PHYSS_CVI_EAGER")
+    if graphed:
+        model.compile_step(0.1)                  # natgrad + ELBO as ONE CUDA graph (VGP.compile_step)
+
     def step():
+        if graphed:
+            return model.step()
         model.natural_gradient_update(0.1)
         return model.elbo()
 
@@ -999,7 +1005,9 @@ def cvi_measure(a, dev, world, rank, local, B, T, steps, warmup, with_clocks, cp
            "cpu_baseline": None,
            "e2e": {"value": 1e3 * float(elw.item()) / steps, "unit": "ms", "h2d_bytes_per_step": B * T * 8 * world,
                    "d2h_bytes_per_step": B * 8 * world,
-                   "api": "VGP.natural_gradient_update(0.1) + VGP.elbo(), data from pinned host memory"},
+                   "api": ("VGP.compile_step(0.1) once, then VGP.set_data + VGP.step() (one CUDA graph per iteration)"
+                           if graphed else "VGP.natural_gradient_update(0.1) + VGP.elbo()") +
+                          ", data from pinned host memory"},
            "clocks": clocks}
     if cpu:
         n = a.cpu_sample_series or max(os.cpu_count() or 1, 8)

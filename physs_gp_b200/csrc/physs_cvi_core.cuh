@@ -191,14 +191,51 @@ PHYSS_HD double cvi_ell_grads(const double (&qm)[D], const double (&qS)[D][D], c
       const double sd = sqrt(2.0 * fv);
       double e0 = 0.0, e1 = 0.0, e2 = 0.0;
       const double c0 = (LIK == CVI_LIK_POISSON_EXP) ? poisson_exp_const(ya, lik_param) : 0.0;
-      for (int q = 0; q < K; ++q) {
-        const double f = fma(sd, ghx[q], fmu[a]);
-        double l, d1, d2;
-        if (LIK == CVI_LIK_POISSON_EXP) poisson_exp_terms(ya, f, lik_param, c0, l, d1, d2);
-        else bernoulli_probit_terms(ya, f, l, d1, d2);
-        e0 = fma(ghw[q], l, e0);
-        e1 = fma(ghw[q], d1, e1);
-        e2 = fma(ghw[q], d2, e2);
+      if (LIK == CVI_LIK_POISSON_EXP) {
+        // exp(m + sd x_q) = exp(m) exp(sd x_q), and Gauss-Hermite nodes come in pairs +-x (numpy's hermgauss
+        // symmetrises them exactly): one exp and one reciprocal per PAIR instead of two exps -- the quadrature
+        // loop is what bounds this kernel (K = 20 fp64 exps per scalar site).  Nodes that are not an exact
+        // +- pair take the plain path.
+        // For sd = sqrt(2 v) <= 3 a K >= 20 point rule integrates exp(sd x) to round-off: sum_q w_q exp(sd x_q)
+        // == exp(sd^2 / 4) within 4e-16 relative (tests/test_oracle_cvi.py pins this against numpy's nodes), so
+        // all three sums follow from ONE exp -- the reference's own closed-form Poisson ELL
+        // (expected_log_likelihoods.py:149-174): E[l] = y m + c0 - b exp(m + v / 2), E[l'] = y - b exp(m + v / 2),
+        // E[l''] = -b exp(m + v / 2).  Wider marginals run the node loop.
+        if (K >= 20 && sd <= 3.0) {
+          const double E = exp(fma(0.25 * sd, sd, fmu[a])) * lik_param;
+          e0 = fma(ya, fmu[a], c0) - E;
+          e1 = ya - E;
+          e2 = -E;
+        } else {
+        const double em = exp(fmu[a]) * lik_param;
+        for (int q = 0; q < (K + 1) / 2; ++q) {
+          const int r = K - 1 - q;
+          const double xq = ghx[q], xr = ghx[r];
+          const double ep = exp(sd * xq);
+          {
+            const double lam = em * ep;
+            e0 = fma(ghw[q], fma(ya, fma(sd, xq, fmu[a]), c0) - lam, e0);
+            e1 = fma(ghw[q], ya - lam, e1);
+            e2 = fma(ghw[q], -lam, e2);
+          }
+          if (r != q) {
+            const double er = (xr == -xq) ? fast_rcp(ep) : exp(sd * xr);
+            const double lam = em * er;
+            e0 = fma(ghw[r], fma(ya, fma(sd, xr, fmu[a]), c0) - lam, e0);
+            e1 = fma(ghw[r], ya - lam, e1);
+            e2 = fma(ghw[r], -lam, e2);
+          }
+        }
+        }
+      } else {
+        for (int q = 0; q < K; ++q) {
+          const double f = fma(sd, ghx[q], fmu[a]);
+          double l, d1, d2;
+          bernoulli_probit_terms(ya, f, l, d1, d2);
+          e0 = fma(ghw[q], l, e0);
+          e1 = fma(ghw[q], d1, e1);
+          e2 = fma(ghw[q], d2, e2);
+        }
       }
       if (obs) {
         ell += e0;

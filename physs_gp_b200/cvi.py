@@ -281,12 +281,52 @@ class VGP:
         self.K = ell_quad_points
 
     def set_data(self, Y):
-        """Data [B, T, P] (host or device); stored in the memory order of the sites."""
+        """Data [B, T, P] (host or device); stored in the memory order of the sites.  A second call with the same
+        shape overwrites the existing device buffer in place (a compiled step keeps reading it)."""
         dev = self.q.Y_tilde.device
         Y = torch.as_tensor(Y, dtype=torch.float64).to(dev, non_blocking=True)
         if Y.dim() == 2:
             Y = Y[None]
+        cur = getattr(self, "Y", None)
+        if cur is not None and cur.shape == Y.shape:
+            cur.copy_(Y)                       # strided destination when the sites are time-major
+            return
         self.Y = time_major_blocks(Y) if _is_tm(self.q.Y_tilde) else Y
+
+    def compile_step(self, lr, enforce_psd_type=None):
+        """Capture natural_gradient_update(lr) + elbo() -- one CVI iteration, vgp.py:274-282,148-157 -- into ONE CUDA
+        graph.  The iteration is ~85 short launches (chunk summaries, scans, replays, site kernels, reductions); as
+        a graph the host enqueues a single node list and the launch gaps disappear.  The sites, the data buffer
+        (set_data) and the returned ELBO tensor keep their addresses; step() replays the graph.  Parallel-in-time
+        filters cannot fall back inside a graph: their device flags are OR-ed into self.step_status (0 = converged),
+        which the caller may read whenever a host sync is acceptable."""
+        from . import filters as _filters
+        q = self.q
+        Yt0, Vt0 = q.Y_tilde.clone(), q.V_tilde.clone()
+        side = torch.cuda.Stream(device=q.Y_tilde.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up off the capture: caches, workspaces, kernel attributes
+            for _ in range(2):
+                self.natural_gradient_update(lr, enforce_psd_type=enforce_psd_type)
+                self.elbo()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        q.Y_tilde.copy_(Yt0); q.V_tilde.copy_(Vt0)
+        graph = torch.cuda.CUDAGraph()
+        del _filters.captured_status[:]
+        with torch.cuda.graph(graph):
+            self.natural_gradient_update(lr, enforce_psd_type=enforce_psd_type)
+            elbo = self.elbo()
+            flags = list(_filters.captured_status)
+            status = torch.stack([f.reshape(-1)[0] for f in flags]).max() if flags else None
+        del _filters.captured_status[:]
+        self._graph, self._graph_elbo, self.step_status = graph, elbo, status
+        return self
+
+    def step(self):
+        """Replay the compiled iteration (compile_step); returns the ELBO tensor [B] (same storage every call)."""
+        self._graph.replay()
+        return self._graph_elbo
 
     def natural_gradient_update(self, lr, enforce_psd_type=None, prediction_samples=None):
         """vgp.py:274-282 -> cvi_nat_grad.py:508-515,346-410 -> cvi_parameterisations.py:63-93."""

@@ -30,13 +30,38 @@ def _device():
 _PIN_LIMIT = 256 << 20      # larger pageable arrays are copied as they are (their copy time dwarfs the stall)
 
 
+_SMALL_LIMIT = 1 << 20      # host arrays up to this size are cached on the device by content
+_small_cache = {}           # (digest, shape, device) -> (device tensor, copy-done event)
+captured_status = []        # device flags of parallel-in-time filters enqueued while a CUDA graph is captured
+
+
 def _to_dev(x, dev):
     """Host -> device without stalling the host: a copy from PAGEABLE memory synchronises the stream before it
     starts (the host then waits for every kernel already queued on it -- measured 10 ms per call in a
     pipelined batch), so host arrays go through a pinned staging tensor (torch's caching host allocator keeps
-    it alive until the copy has run) and the copy is stream-ordered like everything else."""
+    it alive until the copy has run) and the copy is stream-ordered like everything else.
+
+    Small numpy arrays (time axes, H, hyper-parameters: the same few arrays on every call of a training loop) are
+    cached on the device keyed by a digest of their CONTENT, so a steady-state CVI step issues no host -> device
+    copy at all -- which is also what makes the step capturable in a CUDA graph (VGP.compile_step).  The cached
+    tensors are inputs; nothing on the path writes to them."""
     if not isinstance(x, torch.Tensor):
-        x = torch.as_tensor(np.asarray(x, dtype=np.float64))
+        a = np.ascontiguousarray(x, dtype=np.float64)
+        if a.nbytes <= _SMALL_LIMIT:
+            import hashlib
+            key = (hashlib.blake2b(a.tobytes(), digest_size=16).digest(), a.shape, dev.index)
+            hit = _small_cache.get(key)
+            if hit is None:
+                if len(_small_cache) >= 512:
+                    _small_cache.clear()
+                t = torch.as_tensor(a).pin_memory().to(device=dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                _small_cache[key] = hit = (t, ev)
+            elif not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream(dev).wait_event(hit[1])     # another stream may have staged it
+            return hit[0]
+        x = torch.as_tensor(a)
     if x.device.type == 'cpu' and not x.is_pinned() and x.numel() * 8 <= _PIN_LIMIT:
         x = x.to(torch.float64).pin_memory()
     return x.to(device=dev, dtype=torch.float64, non_blocking=True)
@@ -62,8 +87,10 @@ def lower_prior(prior, X_s, dts, dev, sequential=True):
         if cache is None or cache[0] != key:
             cache = (key, _to_dev(prior.lam(), dev), _to_dev(prior.P_inf(), dev), _to_dev(prior.m_inf(), dev), cur)
             prior._b200_cache = cache
-        elif cache[4] != cur:
+        elif cache[4] != cur and not torch.cuda.is_current_stream_capturing():
             cur.wait_stream(cache[4])                  # the staging copies were enqueued on another stream
+            # (a graph capture is preceded by a device-wide sync in VGP.compile_step: nothing to wait for, and a
+            #  dependency on uncaptured work would invalidate the capture)
         _, lam, Pinf, m0, _ = cache
         disc = ops.Disc.matern(prior.nblk, lam, Pinf)
         return [disc for _ in dts], m0, Pinf, prior.H()
@@ -228,7 +255,9 @@ def _filter_impl(parallel, data, prior, lik_mat, Y, X_t, X_s, dt, lik_cov_flag, 
         lml, mf, Pf, status = ops.pscan_filter(dtd, Yd, R, Hd, m0, P0, disc, chunk_len=settings.pscan_chunk_len,
                                                jitter=settings.jitter, polish=settings.pscan_polish,
                                                return_status=True)
-        if settings.pscan_check_status and int(status.item()) != 0:
+        if torch.cuda.is_current_stream_capturing():
+            captured_status.append(status)          # no host sync inside a graph: the owner of the graph reads it
+        elif settings.pscan_check_status and int(status.item()) != 0:
             # Some chunk did not reconcile with the jittered sequential recursion within the fix-up passes (slowly
             # mixing filter / chunks shorter than its memory).  Every further pass contracts the boundary error by
             # the forgetting over one chunk and costs a few steps per converged chunk, so first retry with four

@@ -169,3 +169,21 @@ def test_gauss_hermite_ell_within_4_sigma_of_reference_monte_carlo():
             ell = cvi.gh_ell_and_grads(float(y), float(m), float(v), kind, K=20, binsize=float(g[kind + "_binsize"]))[0]
             assert abs(ell - mean) < 4.0 * se, (kind, y, m, v, ell, mean, se)
             assert se < 0.02 * max(1.0, abs(mean))             # the pin is tight enough to mean something
+
+
+def test_gauss_hermite_20_equals_poisson_closed_form_for_moderate_variance():
+    """Pin behind the one-exp fast path of the Poisson site kernel (csrc/physs_cvi_core.cuh): for sd = sqrt(2 v) <= 3
+    the K = 20 Gauss-Hermite sums of l, l', l'' equal the reference's closed-form Poisson ELL
+    (expected_log_likelihoods.py:149-174) to round-off, so switching between the two is invisible at 1e-9."""
+    x, w = np.polynomial.hermite.hermgauss(20)
+    w = w / np.sqrt(np.pi)
+    assert np.array_equal(x, -x[::-1])                     # exact +- pairs (the kernel's reciprocal shortcut)
+    rng = np.random.default_rng(0)
+    for sd in np.concatenate([np.linspace(0.0, 3.0, 31), rng.uniform(0, 3, 50)]):
+        m, y, b = rng.normal(), float(rng.integers(0, 6)), 0.7
+        f = m + sd * x
+        lam = b * np.exp(f)
+        E = b * np.exp(m + 0.25 * sd * sd)
+        for quad, closed in (((w * (y * f - lam)).sum(), y * m - E), ((w * (y - lam)).sum(), y - E),
+                             ((w * -lam).sum(), -E)):
+            assert abs(quad - closed) <= 2e-15 * max(1.0, abs(closed), E)
