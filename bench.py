@@ -573,7 +573,7 @@ def run_b200(a):
                          % (n, n_local, T, reps, el, CPU_KIND_NOTE)}
 
     # ------------------------------------------- the rest of BASELINE config 5 (d = 8, 16, 32) and metric (2)
-    sweep, cvi_sec = None, None
+    sweep, cvi_sec, c2_sec = None, None, None
     if not a.no_sweep and d == 4:
         Ys = None
         torch.cuda.empty_cache()
@@ -585,6 +585,11 @@ def run_b200(a):
         cvi_sec = cvi_measure(a, dev, world, rank, local, 1000, T_STEPS, steps=max(3, min(a.steps, 10)),
                               warmup=max(3, a.warmup), with_clocks=False,
                               cpu=(rank == 0 and not a.no_cpu_baseline))
+        torch.cuda.empty_cache()
+        # BASELINE config 2 (one series, d = 400, m = 200, T = 5000) on the hand-written separable-prior kernels:
+        # every rank runs its own replica ("replicas only"), two timed passes
+        c2_sec = c2_measure(a, 200, 5000, steps=2, warmup=1, with_clocks=False,
+                            cpu_base=(rank == 0 and not a.no_cpu_baseline), init_dist=False)
 
     if rank == 0:
         launches = 2 * len(starts) * a.steps
@@ -599,6 +604,7 @@ def run_b200(a):
         if sweep is not None:
             line["sweep"] = sweep
             line["cvi"] = cvi_sec
+            line["c2"] = c2_sec
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -1040,7 +1046,7 @@ def run_cvi(a):
 
 
 # ------------------------------------------------------------- c2: separable spatio-temporal CVI (d = 2 Ns)
-def run_c2(a):
+def c2_measure(a, Ns, T, steps, warmup, with_clocks, cpu_base, init_dist):
     """BASELINE config 2 shape: Matern-3/2 (time) x RBF (space), Ns = --series spatial points (default 200) x T
     time points (default 5000): state d = 2 Ns, observations / CVI sites over f at the Ns points (m = Ns) with a
     full time-varying site covariance R_k [m, m].  One step = the posterior pass every CVI iteration runs
@@ -1055,9 +1061,8 @@ def run_c2(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and init_dist:
         dist.init_process_group("nccl", device_id=dev)
-    Ns, T = a.series, a.T
     rng = np.random.default_rng(0)
     Xs = rng.uniform(size=(Ns, 2))
     D2 = ((Xs[:, None, :] - Xs[None, :, :]) ** 2).sum(-1)
@@ -1083,24 +1088,24 @@ def run_c2(a):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         out = step(Y)
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and with_clocks:
         sampler.start()
     barrier()                                 # rank 0 waits for nvidia-smi to come up: keep the ranks together
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.steps):
+    for _ in range(steps):
         out = step(Y)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and with_clocks) else None
     el = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    ms = float(el.item()) / a.steps
+    ms = float(el.item()) / steps
     assert torch.isfinite(out[0]).all()
     d, m = 2 * Ns, Ns
     flops = 14.3 * d ** 3 + 4 * m * d * d + 6 * m * m * d + 0.67 * m ** 3
@@ -1116,19 +1121,19 @@ def run_c2(a):
         torch.cuda.synchronize()
     e2e_step(); barrier()
     tw = time.perf_counter()
-    for _ in range(a.steps):
+    for _ in range(steps):
         e2e_step()
-    elw = (time.perf_counter() - tw) / a.steps
+    elw = (time.perf_counter() - tw) / steps
     value = world * T / (ms * 1e-3)
     cpu = None
-    if rank == 0 and not a.no_cpu_baseline:
+    if rank == 0 and cpu_base:
         r, elc = cpu_c2_rate(Ns, 8)
         cpu = {"value": r, "unit": "state-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "8 of %d time steps = %.1f s (numpy oracle oracle/filters.py, LAPACK threading as numpy "
                          "configures it) -- restatement, not the JAX reference" % (T, elc)}
     if rank == 0:
         line = {"metric": "filter+smoother state-steps/sec (fp64)", "value": value, "unit": "state-steps/s",
-                "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "c2: separable Matern-3/2 x RBF, %d spatial x %d time points, state dim %d, "
                                        "obs dim %d, full time-varying site covariance, 5%% missing" % (Ns, T, d, m),
@@ -1151,11 +1156,19 @@ def run_c2(a):
                 "clocks": clocks,
                 # kernels of libphyss_b200.so per step: the persistent filter + last-step emit + one (gain, recursion)
                 # pair per smoother time chunk of 4 x SM-count steps
-                "gpu_launches": (a.steps * (2 + 2 * -(-(T - 1) // (4 * torch.cuda.get_device_properties(dev).multi_processor_count)))
+                "gpu_launches": (steps * (2 + 2 * -(-(T - 1) // (4 * torch.cuda.get_device_properties(dev).multi_processor_count)))
                                  if kron else None)}
-        print(json.dumps(line), flush=True)
+        return line
+    return None
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_c2(a):
+    line = c2_measure(a, a.series, a.T, a.steps, a.warmup, with_clocks=True, cpu_base=not a.no_cpu_baseline,
+                      init_dist=True)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------ c3cvi: physics-informed CVI step on one long series
