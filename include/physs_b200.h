@@ -196,7 +196,10 @@ int physs_kf_filter_colloc_f64(void* stream, int64_t B, int64_t T, int64_t step_
  * (trainers/trainer.py:43,128-136; trainers/standard.py:58-91): the backward half of a `jax.custom_vjp` around
  * the filter call.  Same inputs as physs_kf_filter_f64 plus its outputs (mf, Pf); every matrix
  * entry counts as an independent variable (what autodiff of the reference's formulation gives, K from
- * solve(S, M H P_)).  Supported: d <= 4, m == 1 (physs_kf_vjp_supported).
+ * solve(S, M H P_)).  Supported (physs_kf_vjp_supported): d <= 4, m == 1 with either discretisation (register
+ * kernel, csrc/physs_vjp.cu), and d <= 32, any m <= d with PHYSS_DISC_GIVEN (lane-group kernel,
+ * csrc/physs_vjp_grp.cu: full-state sites m = d at d = 6 .. 12 are the shapes a VB_NG_ADAM epoch of the
+ * reference differentiates through; the chain from gA, gQ to kernel hyper-parameters is T-independent).
  *   g_lml  [B] or NULL (= 1)
  *   DISC_GIVEN : gA, gQ [B, T, d, d] in the step layout (required)
  *   DISC_MATERN: glam [B, nblk], gPinf [B, d, d] (required): the chain through A_k = expm(F(lam) dt_k) (closed

@@ -239,7 +239,7 @@ int physs_spd_inverse_f64(void* stream, int64_t N, int32_t D, const double* A, d
 }
 
 int physs_kf_vjp_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {
-  return vjp_supported(d, m, disc_mode, nblk) ? 1 : 0;
+  return (vjp_supported(d, m, disc_mode, nblk) || grp_vjp_supported(d, m, disc_mode)) ? 1 : 0;
 }
 
 int physs_kf_filter_vjp_f64(FILTER_PARAMS, const double* mf, const double* Pf, const double* g_lml, double* gA,
@@ -255,6 +255,8 @@ int physs_kf_filter_vjp_f64(FILTER_PARAMS, const double* mf, const double* Pf, c
   VjpOut o{};
   o.g_lml = g_lml; o.gA = gA; o.gQ = gQ; o.glam = glam; o.gPinf = gPinf; o.gH = gH;
   o.gR_step = gR_step; o.gR_sum = gR_sum; o.gm0 = gm0; o.gP0 = gP0;
+  if (!vjp_supported(d, m, disc_mode, nblk) && grp_vjp_supported(d, m, disc_mode))
+    return grp_kf_vjp((cudaStream_t)stream, d, m, H == nullptr, a, o);       // general (d, m): lane groups
   return kf_vjp((cudaStream_t)stream, d, m, disc_mode, nblk, a, o);
 }
 

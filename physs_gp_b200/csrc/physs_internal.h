@@ -127,6 +127,9 @@ int grp_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const Se
 bool rt_supported(int d, int m);
 bool vjp_supported(int d, int m, int disc_mode, int nblk);
 int kf_vjp(cudaStream_t st, int d, int m, int disc_mode, int nblk, const SeqFilterArgs& a, const VjpOut& o);
+// physs_vjp_grp.cu: the same reverse pass for general (d <= 32, m <= d), DISC_GIVEN, one lane group per series
+bool grp_vjp_supported(int d, int m, int disc_mode);
+int grp_kf_vjp(cudaStream_t st, int d, int m, bool h_identity, const SeqFilterArgs& a, const VjpOut& o);
 int rt_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity, const SeqFilterArgs& a);
 int rt_smooth(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);
 int rt_filter_summary(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, const SeqFilterArgs& a,

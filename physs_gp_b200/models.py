@@ -8,6 +8,20 @@ from .data import TemporalData
 from .likelihood import get_R_R_inv
 
 
+def _block_diag_batched(blocks):
+    """[..., s, s] blocks -> [..., d, d] block-diagonal (differentiable)."""
+    lead = blocks[0].shape[:-2]
+    sizes = [b.shape[-1] for b in blocks]
+    d = sum(sizes)
+    rows, o = [], 0
+    for b, sz in zip(blocks, sizes):
+        left = torch.zeros(lead + (sz, o), dtype=b.dtype, device=b.device)
+        right = torch.zeros(lead + (sz, d - o - sz), dtype=b.dtype, device=b.device)
+        rows.append(torch.cat([left, b, right], dim=-1))
+        o += sz
+    return torch.cat(rows, dim=-2)
+
+
 class SDE_GP:
     def __init__(self, data, prior, likelihood, full_state_observed=False, filter_type='b200'):
         self.data = data
@@ -70,10 +84,10 @@ class SDE_GP:
         from .likelihood import Gaussian
         from .sdes import BatchedMaternSDE
         prior, data = self.prior, self.data
-        if not isinstance(prior, BatchedMaternSDE) or not isinstance(self.likelihood, Gaussian):
-            raise NotImplementedError("lml gradient: BatchedMaternSDE prior with a Gaussian likelihood")
-        if data.P * data.Ns != 1 or prior.full_state_obs:
-            raise NotImplementedError("lml gradient: scalar observations (m == 1)")
+        if not isinstance(prior, BatchedMaternSDE):
+            raise NotImplementedError("lml gradient: BatchedMaternSDE prior")
+        if data.P * data.Ns != 1 or prior.full_state_obs or prior.d > 4 or not isinstance(self.likelihood, Gaussian):
+            return self._lml_and_grad_general()
         dev = filters._device()
         X_t = filters._time_axis(data, dev)
         dt = torch.cat([torch.zeros(1, dtype=torch.float64, device=dev), X_t[1:] - X_t[:-1]])
@@ -93,6 +107,78 @@ class SDE_GP:
         g_ls, g_var = prior.hyper_grads(g['glam'].cpu().numpy(), (g['gPinf'] + g['gP0']).cpu().numpy())
         return lml, {'lengthscale': torch.as_tensor(g_ls, device=dev), 'variance': torch.as_tensor(g_var, device=dev),
                      'noise': g['gR'][:, 0, 0]}
+
+    def _lml_and_grad_general(self):
+        """The same pair for any state / observation dimension (d <= 32, m <= d; e.g. full-state sites m = d at
+        d = 6 .. 12, the shapes a VB_NG_ADAM epoch differentiates through): the transitions A_k = expm(F dt_k),
+        Q_k = Pinf - A_k Pinf A_k^T (kernels/kernel.py:207-209) are built ONCE with torch from the kernel
+        hyper-parameters, the filter and its reverse pass run on them (`physs_kf_filter_vjp_f64`, lane-group
+        kernel: gA_k, gQ_k, gP0, gR), and torch differentiates the T-independent closed forms.  Materialises
+        [B, T, d, d] transitions: meant for few series.  Likelihood: `Gaussian` (adds 'noise') or
+        `BlockDiagonalGaussian` site covariances (kernel gradients only)."""
+        from . import ops, settings
+        from .likelihood import Gaussian
+        prior, data = self.prior, self.data
+        dev = filters._device()
+        X_t = filters._time_axis(data, dev)
+        dt = torch.cat([torch.zeros(1, dtype=torch.float64, device=dev), X_t[1:] - X_t[:-1]])
+        Y = filters._to_dev(data.Y_st, dev)
+        Y = Y.reshape(*Y.shape[:-2], -1)                          # [.., Nt, m]
+        if Y.dim() == 2:
+            Y = Y[None]
+        B, T, m = prior.B, Y.shape[1], Y.shape[2]
+        if Y.shape[0] == 1 and B > 1:
+            Y = Y.expand(B, -1, -1).contiguous()
+        s, nblk, d = prior.s, prior.nblk, prior.d
+        ls = torch.tensor(prior.ls, dtype=torch.float64, device=dev, requires_grad=True)
+        var = torch.tensor(prior.var, dtype=torch.float64, device=dev, requires_grad=True)
+        lam = (2.0 * s - 1.0) ** 0.5 / ls                          # [B, nblk]
+        # companion drift of a Matern-(s - 1/2) block: last row -C(s, i) lam^(s - i)
+        import math
+        F = torch.zeros((B, nblk, s, s), dtype=torch.float64, device=dev)
+        for i in range(s - 1):
+            F[..., i, i + 1] = 1.0
+        rows = [-(math.comb(s, i)) * lam ** (s - i) for i in range(s)]
+        F = F + torch.stack([torch.zeros_like(lam)] * (s * (s - 1)) + rows, dim=-1).reshape(B, nblk, s, s)
+        udt, inv = torch.unique(dt, return_inverse=True)
+        E = torch.linalg.matrix_exp(F[:, :, None] * udt[None, None, :, None, None])          # [B, nblk, U, s, s]
+        Ab = E[:, :, inv]                                                                    # [B, nblk, T, s, s]
+        # stationary covariance blocks (closed forms of kernels.py / BatchedMaternSDE.P_inf)
+        z = torch.zeros_like(lam)
+        if s == 1:
+            Pb = var[..., None, None]
+        elif s == 2:
+            Pb = torch.stack([var, z, z, lam ** 2 * var], -1).reshape(B, nblk, 2, 2)
+        elif s == 3:
+            k = lam ** 2 * var / 3.0
+            Pb = torch.stack([var, z, -k, z, k, z, -k, z, lam ** 4 * var], -1).reshape(B, nblk, 3, 3)
+        else:
+            k1, k2 = lam ** 2 * var / 5.0, lam ** 4 * var / 5.0
+            Pb = torch.stack([var, z, -k1, z, z, k1, z, -k2, -k1, z, k2, z, z, -k2, z, lam ** 6 * var],
+                             -1).reshape(B, nblk, 4, 4)
+        A = _block_diag_batched([Ab[:, q] for q in range(nblk)])                              # [B, T, d, d]
+        Pinf = _block_diag_batched([Pb[:, q] for q in range(nblk)])                           # [B, d, d]
+        Q = Pinf[:, None] - A @ Pinf[:, None] @ A.transpose(-1, -2)
+        H = prior.H()
+        Hd = None if (H.shape[0] == H.shape[1] and np.array_equal(H, np.eye(H.shape[0]))) else filters._to_dev(H, dev)
+        if isinstance(self.likelihood, Gaussian):
+            R = (self.likelihood.variance_scalar * torch.eye(m, dtype=torch.float64, device=dev)).reshape(1, 1, m, m)
+        else:
+            R = filters._to_dev(self.likelihood.variance, dev)
+            R = R if R.dim() == 4 else R[None]
+        R = R.expand(B, T, m, m).contiguous()
+        dtb = dt[None].expand(B, T).contiguous()
+        m0 = torch.zeros((B, d), dtype=torch.float64, device=dev)
+        Ad, Qd, P0 = A.detach().contiguous(), Q.detach().contiguous(), Pinf.detach().contiguous()
+        disc = ops.Disc.given(Ad, Qd)
+        lml, mf, Pf = ops.kf_filter(dtb, Y, R, Hd, m0, P0, disc, jitter=settings.jitter)
+        g = ops.kf_filter_vjp(dtb, Y, R, Hd, m0, P0, disc, mf, Pf, jitter=settings.jitter)
+        surrogate = (g['gA'] * A).sum() + (g['gQ'] * Q).sum() + (g['gP0'] * Pinf).sum()
+        g_ls, g_var = torch.autograd.grad(surrogate, [ls, var])
+        out = {'lengthscale': g_ls, 'variance': g_var}
+        if isinstance(self.likelihood, Gaussian):
+            out['noise'] = torch.diagonal(g['gR'], dim1=-2, dim2=-1).sum(-1)
+        return lml, out
 
     # ---------------------------------------------------------------- prediction at new times
     def predict_f(self, XS, diagonal=True, squeeze=False, filter_only=False, force_full_state=False):

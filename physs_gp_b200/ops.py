@@ -312,12 +312,15 @@ def kf_filter_vjp(dt, Y, R, H, m0, P0, disc, mf, Pf, g_lml=None, jitter=None, wa
 
     Returns a dict: DISC_GIVEN -> 'gA', 'gQ' [B, T, d, d]; DISC_MATERN -> 'glam' [B, nblk], 'gPinf' [B, d, d];
     always 'gH' [B, m, d], 'gR' [B, m, m] (summed over the steps), 'gm0' [B, d], 'gP0' [B, d, d];
-    'gR_step' [B, T, m, m] with want_R_step.  Supported for d <= 4, m == 1."""
+    'gR_step' [B, T, m, m] with want_R_step.  d <= 4, m == 1: register kernel, any discretisation; otherwise
+    d <= 32, m <= d with Disc.given (lane-group kernel; chain (gA, gQ) to hyper-parameters with torch, see
+    models.SDE_GP.log_marginal_likelihood_and_grad)."""
     lib = _lib.load()
     p = _pack_filter(dt, Y, R, H, m0, P0, disc, jitter, stream)
     B, T, d, m, dev = p.B, p.T, p.d, p.m, p.dev
     if not lib.physs_kf_vjp_supported(d, m, disc.mode, disc.nblk):
-        raise NotImplementedError("kf_filter_vjp: d <= 4 and m == 1 only (d=%d, m=%d)" % (d, m))
+        raise NotImplementedError("kf_filter_vjp: d <= 4 with m == 1 (any discretisation) or d <= 32, m <= d with "
+                                  "Disc.given (d=%d, m=%d)" % (d, m))
     mfv, tm1 = step_layout(_dev(mf, "mf"), "mf")
     Pfv, tm2 = step_layout(_dev(Pf, "Pf"), "Pf")
     if tm1 != p.tmaj or tm2 != p.tmaj:
