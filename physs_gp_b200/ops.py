@@ -515,11 +515,16 @@ def pscan_smooth(dt, mf, Pf, disc, Hout=None, chunk_len=None, jitter=None, out=N
 
 
 # ---- time-sharded building blocks (used by physs_gp_b200/timeshard.py)
-def pscan_filter_local(dt, Y, R, H, m0, P0, disc, chunk_len, ws, jitter=None, stream=None):
-    """Scan element of this whole time range, [B, 3 d^2 + 2 d]; prefixes stay in `ws` for *_finish."""
+def pscan_filter_local(dt, Y, R, H, m0, P0, disc, chunk_len, ws, jitter=None, stream=None, out=None):
+    """Scan element of this whole time range, [B, 3 d^2 + 2 d]; prefixes stay in `ws` for *_finish.
+    `out`: a contiguous [B, 3 d^2 + 2 d] view to write it into -- the time-sharded driver passes this rank's slot
+    of the all-gather buffer, so the summary kernel's store IS the collective's send buffer."""
     lib = _lib.load()
     p = _pack_filter(dt, Y, R, H, m0, P0, disc, jitter, stream)
-    total = torch.empty((p.B, 3 * p.d * p.d + 2 * p.d), dtype=torch.float64, device=p.dev)
+    ne = 3 * p.d * p.d + 2 * p.d
+    if out is not None and (tuple(out.shape) != (p.B, ne) or not out.is_contiguous() or out.dtype != torch.float64):
+        raise ValueError("pscan_filter_local: out must be a contiguous float64 [B, 3 d^2 + 2 d] tensor")
+    total = out if out is not None else torch.empty((p.B, ne), dtype=torch.float64, device=p.dev)
     with torch.cuda.device(p.dev):
         st = lib.physs_pscan_filter_local_f64(*p.head, int(chunk_len), ws.data_ptr(), total.data_ptr())
     _lib.check(st, "physs_pscan_filter_local_f64")

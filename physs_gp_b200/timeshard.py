@@ -41,6 +41,15 @@ class SingleProcess:
     def all_gather(self, x):
         return x[None]
 
+    def gather_buffer(self, shape, device):
+        """([world, *shape] buffer, this rank's slot): a kernel that writes its result into the slot needs no copy
+        before all_gather_inplace."""
+        buf = torch.empty((1,) + tuple(shape), dtype=torch.float64, device=device)
+        return buf, buf[0]
+
+    def all_gather_inplace(self, buf):
+        return buf
+
     def shift_from_prev(self, x):
         return None
 
@@ -58,6 +67,16 @@ class TorchDist:
         out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         self.dist.all_gather_into_tensor(out, x, group=self.group)     # concatenated along dim 0
         return out.view((self.world,) + tuple(x.shape))
+
+    def gather_buffer(self, shape, device):
+        buf = torch.empty((self.world,) + tuple(shape), dtype=torch.float64, device=device)
+        return buf, buf[self.rank]
+
+    def all_gather_inplace(self, buf):
+        """In-place all-gather: every rank's slot buf[rank] is already filled (NCCL: sendbuff == recvbuff + rank *
+        count, no staging copy on either side)."""
+        self.dist.all_gather_into_tensor(buf.view(-1), buf[self.rank].reshape(-1), group=self.group)
+        return buf
 
     def shift_from_prev(self, x):
         """Every rank sends x to rank + 1; returns what rank - 1 sent (None on rank 0)."""
@@ -89,8 +108,10 @@ def filter_smooth(comm, ops, dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s, chunk_
         ws = ops.pscan_workspace(B, T, d, chunk_len, Y.device)
     r, G = comm.rank, comm.world
     # ---------------------------------------------------------------- filter
-    total = ops.pscan_filter_local(dt_f, Y, R, H, m0, P0, disc_f, chunk_len, ws, jitter=jitter)
-    totals = comm.all_gather(total)                                   # [G, B, ne]
+    # the range summary is written by its kernel straight into this rank's slot of the all-gather buffer
+    totals, slot = comm.gather_buffer((B, 3 * d * d + 2 * d), Y.device)
+    ops.pscan_filter_local(dt_f, Y, R, H, m0, P0, disc_f, chunk_len, ws, jitter=jitter, out=slot)
+    totals = comm.all_gather_inplace(totals)                          # [G, B, ne]
     start = None
     if r > 0:
         m0b = m0.expand(B, d) if m0.dim() == 2 else m0

@@ -37,7 +37,7 @@ def _elements(Y, R, H, disc, jitter):
     return els
 
 
-def pscan_filter_local(dt, Y, R, H, m0, P0, disc, chunk_len, ws, jitter=0.0, stream=None):
+def pscan_filter_local(dt, Y, R, H, m0, P0, disc, chunk_len, ws, jitter=0.0, stream=None, out=None):
     Yn, Rn, Hn = _np(Y), _np(R), _np(H)
     B, d = Yn.shape[0], disc.A.shape[-1]
     totals = []
@@ -49,7 +49,11 @@ def pscan_filter_local(dt, Y, R, H, m0, P0, disc, chunk_len, ws, jitter=0.0, str
         A, bb, C, J, eta = acc
         totals.append(np.concatenate([A.ravel(), C.ravel(), J.ravel(), bb.ravel(), eta.ravel()]))
     ws['filter'] = True
-    return _t(np.stack(totals))
+    res = _t(np.stack(totals))
+    if out is not None:
+        out.copy_(res)                  # the product's kernel writes the gather slot in place; mirror that
+        return out
+    return res
 
 
 def _unpack_filter(e, d):
