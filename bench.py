@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "cvi", "c2", "c3cvi", "grad"],
+    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "cvi", "c2", "c2cvi", "c3cvi", "grad"],
                     help="c5 (default, the headline metric): batched sweep; c3: one long series, parallel-in-time "
                          "scan, time-sharded over the ranks; cvi: CVI ELBO + natural-gradient step (config 4)")
     ap.add_argument("--chunk-len", type=int, default=256, help="c3: steps per scan chunk")
@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--cpu-sample-series", type=int, default=0, help="series in the CPU sample (0 = auto)")
     a = ap.parse_args()
     dflt = {"c5": (SERIES_TOTAL, T_STEPS, 4), "c3": (1, 1000000, 8), "cvi": (1000, T_STEPS, 2),
-            "c2": (200, 5000, 400), "c3cvi": (1, 1000000, 4), "grad": (32768, T_STEPS, 4)}[a.workload]
+            "c2": (200, 5000, 400), "c2cvi": (200, 5000, 400), "c3cvi": (1, 1000000, 4), "grad": (32768, T_STEPS, 4)}[a.workload]
     a.series = dflt[0] if a.series is None else a.series
     a.T = dflt[1] if a.T is None else a.T
     a.state_dim = dflt[2] if a.state_dim is None else a.state_dim
@@ -354,6 +354,21 @@ def run_reference(a):
                                         "[CPU arm: %s]" % (Ns, T, 2 * Ns, sample), "spatial_points": Ns, "T": T},
                     cpu_baseline={"value": value, "unit": "state-steps/s", "cores": cores, "kind": "port", "sample": sample},
                     e2e={"value": value, "unit": "state-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return
+    if a.workload == "c2cvi":
+        Ns = a.series
+        vals = [cpu_c2cvi_ms(Ns, 4) * T / 4 for i in range(a.warmup + a.steps)][a.warmup:]
+        value = float(np.mean(vals))
+        sample = ("4 of %d time steps, scaled linearly (numpy oracle: oracle/filters.py + oracle/cvi.py, LAPACK threading as "
+                  "numpy configures it) -- restatement, not the JAX reference" % T)
+        line = dict(base, metric="CVI ELBO+natgrad step time", value=value, unit="ms", ms_per_step=value,
+                    higher_is_better=False, scaling="weak",
+                    config={"workload": "c2cvi: CVI iteration of a separable Matern-3/2 x RBF model, %d spatial x %d time "
+                                        "points, one D = %d site block per step [CPU arm: %s]" % (Ns, T, Ns, sample),
+                            "spatial_points": Ns, "T": T},
+                    cpu_baseline={"value": value, "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
+                    e2e={"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         print(json.dumps(line), flush=True)
         return
     n = a.cpu_sample_series or max(cores * 8, 64)
@@ -1164,6 +1179,130 @@ def c2_measure(a, Ns, T, steps, warmup, with_clocks, cpu_base, init_dist):
         dist.destroy_process_group()
 
 
+def cpu_c2cvi_ms(Ns, T_sample):
+    """ms per CVI iteration of the numpy oracle on T_sample steps of the config-2 shape (natgrad + ELBO)."""
+    from oracle import cvi as ocvi
+    from oracle import filters as of
+    from oracle import sde as osde
+    rng = np.random.default_rng(0)
+    Xs = rng.uniform(size=(Ns, 2))
+    D2 = ((Xs[:, None, :] - Xs[None, :, :]) ** 2).sum(-1)
+    Ks = np.exp(-0.5 * D2 / 0.2 ** 2) + 1e-6 * np.eye(Ns)
+    prior = osde.LTI_SDE([osde.SpaceTimeSeparable(osde.Matern32(10 * DT0, 1.0), Ks)])
+    t = DT0 * np.arange(1, T_sample + 1)
+    Y = rng.normal(size=(T_sample, Ns))
+    Yt = 1e-5 * np.ones((T_sample, Ns)); Vt = np.tile(np.eye(Ns), [T_sample, 1, 1])
+    R = NOISE_VAR * np.eye(Ns)
+    t0 = time.perf_counter()
+    _, qm, qv = of.filter_and_smooth(prior, t, Yt, Vt)
+    g = [ocvi.gaussian_ell_and_grads(Y[i], R, None, qm[i][:, 0], qv[i]) for i in range(T_sample)]
+    Yt, Vt = ocvi.cvi_step(Yt, Vt, qm[:, :, 0], qv, np.stack([x[1] for x in g]), np.stack([x[2] for x in g]), 0.5)
+    lml, qm, qv = of.filter_and_smooth(prior, t, Yt, Vt)
+    ell = sum(ocvi.gaussian_ell_and_grads(Y[i], R, None, qm[i][:, 0], qv[i])[0] for i in range(T_sample))
+    ocvi.elbo(ell, ocvi.surrogate_ell(Yt, Vt, qm[:, :, 0], qv), lml)
+    return 1e3 * (time.perf_counter() - t0)
+
+
+def run_c2cvi(a):
+    """BASELINE config 2 as the reference runs it: the CVI iteration of a spatio-temporal separable Matern-3/2 x RBF
+    model, 200 spatial x 5000 time points, ONE D = 200 site block per time step, Gaussian likelihood, 5 % missing.
+    One step = natural-gradient site update (posterior pass on the separable-prior kernels, theta <-> lambda and block
+    update on the large-block site kernels) + ELBO (posterior pass on the new sites, data ELL, surrogate ELL).
+    Every rank runs its own replica ("replicas only")."""
+    import torch
+    import torch.distributed as dist
+    from physs_gp_b200 import cvi, kernels as K, ops, sdes
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    Ns, T = a.series, a.T
+    rng = np.random.default_rng(0)
+    Xs = rng.uniform(size=(Ns, 2))
+    D2 = ((Xs[:, None, :] - Xs[None, :, :]) ** 2).sum(-1)
+    Ks = np.exp(-0.5 * D2 / 0.2 ** 2) + 1e-6 * np.eye(Ns)
+    prior = sdes.LTI_SDE(sdes.Independent([K.SpatioTemporalSeperableKernel(K.Matern32(10 * DT0, 1.0), Ks)]))
+    t = DT0 * np.arange(1, T + 1)
+    Yh = np.sin(0.02 * np.arange(T))[:, None] * np.cos(3 * Xs[:, 0])[None, :] + 0.3 * rng.normal(size=(T, Ns))
+    Yh[rng.uniform(size=Yh.shape) < NAN_FRAC] = np.nan
+    q = cvi.FullConjugateGaussian(t, prior, Ns, B=1, device=dev)
+    model = cvi.VGP(Yh[None], cvi.GaussianLik(NOISE_VAR * np.eye(Ns)), q)
+
+    def step():
+        model.natural_gradient_update(0.5)
+        return model.elbo()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(a.warmup):
+        elbo = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        elbo = step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    el = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    ms = float(el.item()) / a.steps
+    assert torch.isfinite(elbo).all()
+    Y_host = torch.empty((1, T, Ns), dtype=torch.float64, pin_memory=True); Y_host.copy_(torch.as_tensor(Yh)[None])
+    o_elbo = torch.empty((1,), dtype=torch.float64, pin_memory=True)
+
+    def e2e_step():
+        model.set_data(Y_host)
+        o_elbo.copy_(step(), non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_step(); barrier()
+    tw = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    elw = 1e3 * (time.perf_counter() - tw) / a.steps
+    d, m = 2 * Ns, Ns
+    # two posterior passes + (2 + 1) SPD inverses of D x D per step (chol D^3/3 + inverse 2 D^3/3 ... = D^3 each, FMA = 2)
+    flops = 2 * (14.3 * d ** 3 + 4 * m * d * d + 6 * m * m * d + 0.67 * m ** 3) + 3 * 2.0 * m ** 3
+    fp64 = ops.fp64_peak_tflops(dev)
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        ms_s = cpu_c2cvi_ms(Ns, 4)
+        cpu = {"value": ms_s * T / 4, "unit": "ms", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "4 of %d time steps = %.1f s (numpy oracle: oracle/filters.py + oracle/cvi.py, LAPACK threading "
+                         "as numpy configures it), scaled linearly -- restatement, not the JAX reference" % (T, ms_s / 1e3)}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "CVI ELBO+natgrad step time", "value": ms, "unit": "ms", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "c2cvi: CVI iteration (natgrad + ELBO) of a separable Matern-3/2 x RBF model, %d spatial x "
+                                   "%d time points, one D = %d site block per time step, Gaussian likelihood, 5%% missing"
+                                   % (Ns, T, Ns), "spatial_points": Ns, "T": T, "state_dim": d, "site_block": m,
+                       "l2": "filtered covariances %.1f GB >> 126 MB L2" % (T * d * d * 8 / 1e9),
+                       "parallelism": "replicas only (one series; no collective)"},
+            "state_steps_per_s": world * T / (ms * 1e-3),
+            "roofline": {"bound": "tensor", "achieved": flops * T / (ms * 1e-3) / 1e12, "peak": fp64, "unit": "TFLOP/s",
+                         "frac": flops * T / (ms * 1e-3) / 1e12 / fp64, "traffic": None,
+                         "peak_source": "physs_fp64_probe (FP64 FMA pipe), this run",
+                         "note": "dense flop count of two posterior passes (SURVEY 8d) + three D x D SPD inverses per block"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": elw, "unit": "ms", "h2d_bytes_per_step": T * Ns * 8 * world, "d2h_bytes_per_step": 8 * world,
+                    "api": "VGP.set_data + VGP.natural_gradient_update(0.5) + VGP.elbo(), pinned host buffers"},
+            "clocks": clocks, "gpu_launches": None}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_c2(a):
     line = c2_measure(a, a.series, a.T, a.steps, a.warmup, with_clocks=True, cpu_base=not a.no_cpu_baseline,
                       init_dist=True)
@@ -1346,6 +1485,8 @@ def main():
         run_c3cvi(a)
     elif a.workload == "c2":
         run_c2(a)
+    elif a.workload == "c2cvi":
+        run_c2cvi(a)
     elif a.workload == "c3":
         run_c3(a)
     elif a.workload == "cvi":

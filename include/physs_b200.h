@@ -456,6 +456,21 @@ int physs_rts_smooth_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, c
                               const int32_t* idx, const double* Ks, const double* mf, const double* Pf,
                               int32_t project, double jitter, void* ws, int64_t ws_bytes, double* ms, double* Ps);
 
+/* ---- CVI site update and surrogate ELL for LARGE site blocks (D <= 208: the D = Ns = 200 blocks of config 2, one block
+ * per time step), one CTA per block on the shared-memory Cholesky of the separable-prior kernels above.  Same algebra as
+ * physs_cvi_natgrad_step_f64 (cvi_nat_grad.py:47-87, exponential_family_transforms.py:25-95) with the ELL gradients
+ * supplied (LIK_GIVEN): dm [T, D]; dS [T, D, D], or its diagonal [T, D] with dS_diag = 1 (Gaussian likelihood with
+ * diagonal noise: dm = (y - m) / s2, dS = -1 / (2 s2), zero at missing entries).  Yt [T, D], Vt [T, D, D] sites in,
+ * Yn / Vn out (may not alias the inputs); qm [T, D], qS [T, D, D] posterior marginals of the blocks.
+ * physs_cvi_ell_sur_big_f64: ell[t] = log N(Yt_t | qm_t, Vt_t) - 1/2 tr(Vt_t^-1 qS_t) (expected_log_likelihoods.py:90-117;
+ * sites carry no missing entries).  ws: 16-byte aligned, physs_cvi_big_workspace_bytes(D) bytes. */
+int64_t physs_cvi_big_workspace_bytes(int32_t D);
+int physs_cvi_natgrad_big_f64(void* stream, int64_t T, int32_t D, const double* Yt, const double* Vt, const double* qm,
+                              const double* dm, const double* dS, int32_t dS_diag, double beta, double ngj, void* ws,
+                              int64_t ws_bytes, double* Yn, double* Vn);
+int physs_cvi_ell_sur_big_f64(void* stream, int64_t T, int32_t D, const double* Yt, const double* Vt, const double* qm,
+                              const double* qS, void* ws, int64_t ws_bytes, double* ell);
+
 /* FP64 FMA throughput probe (measurement aid for the FP64-pipe roofline; no reference counterpart).
  * Launches blocks x 256 threads doing iters x 8 independent FMAs each: flops = blocks*256*iters*16. */
 int physs_fp64_probe(void* stream, int32_t blocks, int64_t iters, double* out);

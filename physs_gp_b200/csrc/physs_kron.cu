@@ -746,8 +746,11 @@ __device__ __noinline__ void chol_smem(const double* Sg, int64_t ld, int n, doub
 // of K = X L^-1, with the whole factor L resident in shared memory.  The 32 x 32 diagonal blocks of L are
 // inverted once (one warp per block, in place), so every block step is DMMA work: an update with the columns
 // already solved and a multiply by the inverse block.  Also returns the mean update  out_m[i] = mp[i] + X[i,:] . u.
+// prepared: the factor (with inverted diagonal blocks) is still resident from a previous call on this CTA;
+// ident_row0 >= 0: the right-hand side is rows ident_row0 .. + R of the identity (rows of (L L^T)^-1 come out in Kr).
 __device__ __noinline__ void trsm_smem(const double* Lg, int64_t ld, int n, double* Wr, int R, double* Kr, const double* u,
-                          const double* mp, double* out_m, double* sm, double* prof) {
+                          const double* mp, double* out_m, double* sm, double* prof, bool prepared = false,
+                          int ident_row0 = -1) {
   unsigned long long tk = gtimer();
   double* Ls = sm + TS_L;
   double* Xs = sm + TS_X;
@@ -757,16 +760,17 @@ __device__ __noinline__ void trsm_smem(const double* Lg, int64_t ld, int n, doub
   const int nt = warp & 3, half = warp >> 2;
   const int nbr = (n + 7) >> 3, npad = 8 * nbr, nb32 = (npad + 31) >> 5;
   constexpr int LDX = TRI_N + 4;
-  tri_load_issue(Ls, Lg, ld, n, nbr);
+  if (!prepared) tri_load_issue(Ls, Lg, ld, n, nbr);
   for (int idx = tid; idx < 8 * npad; idx += NTH) {
     const int r = idx / npad, c = idx - r * npad;
-    Xs[r * LDX + c] = (r < R && c < n) ? __ldcg(Wr + (int64_t)r * ld + c) : 0.0;
+    if (ident_row0 >= 0) Xs[r * LDX + c] = (r < R && c == ident_row0 + r) ? 1.0 : 0.0;
+    else Xs[r * LDX + c] = (r < R && c < n) ? __ldcg(Wr + (int64_t)r * ld + c) : 0.0;
   }
   cp_async_wait<0>();
   __syncthreads();
   ptick(prof, 20, tk);
   // invert the diagonal blocks in place: warp J takes block J; lane c owns column c of the inverse
-  for (int J = warp; J < nb32; J += NTH / 32) {
+  for (int J = warp; !prepared && J < nb32; J += NTH / 32) {
     const int c0 = 32 * J, w32 = min(32, npad - c0);
     const int c = lane;
     double x[32];
@@ -841,11 +845,11 @@ __device__ __noinline__ void trsm_smem(const double* Lg, int64_t ld, int n, doub
     __syncthreads();
   }
   // X rows back to global, mean update
-  for (int idx = tid; idx < R * n; idx += NTH) {
+  for (int idx = tid; Wr && ident_row0 < 0 && idx < R * n; idx += NTH) {
     const int r = idx / n, c = idx - r * n;
     Wr[(int64_t)r * ld + c] = Xs[r * LDX + c];
   }
-  if (warp < R) {
+  if (u && warp < R) {
     double s = 0.0;
     for (int a = lane; a < n; a += 32) s = fma(Xs[warp * LDX + a], __ldcg(u + a), s);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -909,6 +913,140 @@ __device__ double block_sum(double v, double* scratch) {
   if (threadIdx.x == 0)
     for (int i = 0; i < NTH / 32; ++i) s += scratch[i];
   return s;
+}
+
+
+// ----------------------------------------------------------------- CVI site update / surrogate ELL, large blocks
+// The D = m = Ns site blocks of the config-2 CVI posterior (FullConjugateGaussian over the spatial points of one time
+// step; cvi_nat_grad.py:47-87, exponential_family_transforms.py:25-95, expected_log_likelihoods.py:90-117): one CTA per
+// time step, D <= 208.  Every SPD inverse is the shared-memory Cholesky above followed by the resident gain solves on
+// identity rows (rows of (L L^T)^-1, eight at a time).
+struct CviBigArgs {
+  int64_t T; int D;
+  const double* Yt; const double* Vt;          // sites [T, D], [T, D, D]
+  const double* qm; const double* qS;          // posterior marginals of the site blocks (qS: surrogate ELL only)
+  const double* dm; const double* dS;          // dELL/dm [T, D], dELL/dS [T, D, D] or its diagonal [T, D]
+  int dS_diag;
+  double beta, ngj;
+  double* Yn; double* Vn;                      // updated sites
+  double* ell;                                 // surrogate ELL per step [T]
+  double* scratch;                             // per CTA: 2 (D + 1) D + D D + 2 D doubles
+};
+__host__ __device__ __forceinline__ int64_t cvi_big_scratch(int D) { return 2 * (int64_t)(D + 1) * D + (int64_t)D * D + 2 * D + 8; }
+
+// (M + 0)^-1 for the SPD matrix in Mg ((D + 1) x D, appended row = right-hand side v): factor into Lg, rows of the
+// inverse into Inv (ld D).  On return v holds L^-1 v in shared memory (TS_V) and the diagonal of L is in the triangle.
+__device__ void spd_inverse_big(const double* Mg, double* Lg, double* Inv, int D, double* sm) {
+  chol_smem(Mg, D, D, Lg, sm, nullptr);
+  __syncthreads();
+  for (int rb = 0; rb * 8 < D; ++rb) {
+    const int R = min(8, D - 8 * rb);
+    trsm_smem(Lg, D, D, nullptr, R, Inv + (int64_t)rb * 8 * D, nullptr, nullptr, nullptr, sm, nullptr, rb > 0, 8 * rb);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(NTH, 1) kron_cvi_site_kernel(const CviBigArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, D = p.D;
+  const int64_t DD = (int64_t)D * D;
+  double* Mg = p.scratch + (int64_t)blockIdx.x * cvi_big_scratch(D);
+  double* Lg = Mg + (int64_t)(D + 1) * D;
+  double* Inv = Lg + (int64_t)(D + 1) * D;
+  double* l1 = Inv + DD;
+  for (int64_t t = blockIdx.x; t < p.T; t += gridDim.x) {
+    const double* Yt = p.Yt + t * D;
+    const double* Vt = p.Vt + t * DD;
+    const double* qm = p.qm + t * D;
+    const double* dm = p.dm + t * D;
+    const double* dS = p.dS + t * (p.dS_diag ? (int64_t)D : DD);
+    // theta -> lambda: Vinv = (V~ + ng_jitter I)^-1
+    for (int idx = tid; idx < (D + 1) * D; idx += NTH) {
+      const int i = idx / D, j = idx - i * D;
+      Mg[idx] = i < D ? Vt[idx] + (i == j ? p.ngj : 0.0) : 0.0;
+    }
+    __syncthreads();
+    spd_inverse_big(Mg, Lg, Inv, D, sm);
+    // block update: lambda_1' = (1 - beta) Vinv Y~ + beta (dm - 2 dS m),  -2 lambda_2' = (1 - beta) Vinv - 2 beta dS
+    for (int i = warp; i < D; i += NTH / 32) {
+      double a = 0.0, g = 0.0;
+      for (int k = lane; k < D; k += 32) {
+        a = fma(__ldcg(Inv + (int64_t)i * D + k), Yt[k], a);
+        if (!p.dS_diag) g = fma(dS[(int64_t)i * D + k], qm[k], g);
+      }
+      for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); g += __shfl_xor_sync(0xffffffffu, g, o); }
+      if (lane == 0) {
+        if (p.dS_diag) g = dS[i] * qm[i];
+        l1[i] = (1.0 - p.beta) * a + p.beta * (dm[i] - 2.0 * g);
+      }
+    }
+    for (int idx = tid; idx < (D + 1) * D; idx += NTH) {
+      const int i = idx / D, j = idx - i * D;
+      if (i < D) {
+        const double ds = p.dS_diag ? (i == j ? dS[i] : 0.0) : dS[idx];
+        Mg[idx] = (1.0 - p.beta) * __ldcg(Inv + idx) - 2.0 * p.beta * ds + (i == j ? p.ngj : 0.0);
+      } else {
+        Mg[idx] = 0.0;
+      }
+    }
+    __syncthreads();
+    // lambda -> theta: V~' = (-2 lambda_2' + ng_jitter I)^-1,  Y~' = V~' lambda_1'
+    double* Vn = p.Vn + t * DD;
+    spd_inverse_big(Mg, Lg, Vn, D, sm);
+    for (int i = warp; i < D; i += NTH / 32) {
+      double a = 0.0;
+      for (int k = lane; k < D; k += 32) a = fma(__ldcg(Vn + (int64_t)i * D + k), __ldcg(l1 + k), a);
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) p.Yn[t * D + i] = a;
+    }
+    __syncthreads();
+  }
+}
+
+// surrogate ELL of one step: log N(Y~ | m, V~) - 1/2 tr(V~^-1 S)   (sites carry no missing entries)
+__global__ void __launch_bounds__(NTH, 1) kron_cvi_ell_sur_kernel(const CviBigArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, D = p.D;
+  const int64_t DD = (int64_t)D * D;
+  double* Mg = p.scratch + (int64_t)blockIdx.x * cvi_big_scratch(D);
+  double* Lg = Mg + (int64_t)(D + 1) * D;
+  double* Inv = Lg + (int64_t)(D + 1) * D;
+  for (int64_t t = blockIdx.x; t < p.T; t += gridDim.x) {
+    const double* Yt = p.Yt + t * D;
+    const double* Vt = p.Vt + t * DD;
+    const double* qm = p.qm + t * D;
+    const double* qS = p.qS + t * DD;
+    for (int idx = tid; idx < (D + 1) * D; idx += NTH) {
+      const int i = idx / D, j = idx - i * D;
+      Mg[idx] = i < D ? Vt[idx] : Yt[j] - qm[j];
+    }
+    __syncthreads();
+    chol_smem(Mg, D, D, Lg, sm, nullptr);
+    __syncthreads();
+    double ld = 0.0, mh = 0.0, tr = 0.0;
+    for (int a = tid; a < D; a += NTH) {
+      ld += log(sm[TS_L + tri_idx(a, a)]);
+      const double u = sm[TS_V + a];
+      mh = fma(u, u, mh);
+    }
+    __syncthreads();
+    for (int rb = 0; rb * 8 < D; ++rb) {
+      const int R = min(8, D - 8 * rb);
+      trsm_smem(Lg, D, D, nullptr, R, Inv + (int64_t)rb * 8 * D, nullptr, nullptr, nullptr, sm, nullptr, rb > 0, 8 * rb);
+      __syncthreads();
+    }
+    for (int idx = tid; idx < D * D; idx += NTH) {
+      const int i = idx / D, j = idx - i * D;
+      tr = fma(__ldcg(Inv + idx), qS[(int64_t)j * D + i], tr);
+    }
+    double* scr = sm + TS_T;
+    ld = block_sum(ld, scr);
+    mh = block_sum(mh, scr);
+    tr = block_sum(tr, scr);
+    if (tid == 0) p.ell[t] = -0.5 * (D * 1.8378770664093454835606594728112 + 2.0 * ld + mh + tr);
+    __syncthreads();
+  }
+  (void)warp; (void)lane;
 }
 
 constexpr int DSMAX = 4;
@@ -1432,6 +1570,50 @@ int physs_kf_filter_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, co
   e = cudaLaunchCooperativeKernel((void*)kron_filter_kernel, dim3(dv.filter_blocks), dim3(NTH), args, SM_BYTES_FILTER,
                                   (cudaStream_t)stream);
   return cuda_status(e, "kron_filter_kernel launch");
+}
+
+int64_t physs_cvi_big_workspace_bytes(int32_t D) {
+  if (D < 1 || D > TRI_N) return 0;
+  Dev dv;
+  if (device_setup(dv) != PHYSS_OK) return 0;
+  return 8 * cvi_big_scratch(D) * dv.sms + 16;
+}
+
+static int cvi_big_launch(void* stream, bool update, CviBigArgs& a, void* ws, int64_t ws_bytes) {
+  if (a.T < 0 || a.D < 1 || a.D > TRI_N) return set_error(PHYSS_ERR_UNSUPPORTED, "cvi (large blocks): 1 <= D <= 208");
+  if (a.T == 0) return PHYSS_OK;
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15) != 0) return set_error(PHYSS_ERR_BAD_ARG, "cvi (large blocks): workspace missing or not 16-byte aligned");
+  Dev dv;
+  if (int rc = device_setup(dv)) return rc;
+  if (ws_bytes < 8 * cvi_big_scratch(a.D) * dv.sms) return set_error(PHYSS_ERR_BAD_ARG, "cvi (large blocks): workspace too small");
+  a.scratch = static_cast<double*>(ws);
+  const int grid = (int)(a.T < dv.sms ? a.T : dv.sms);
+  cudaError_t e = cudaFuncSetAttribute(update ? (const void*)kron_cvi_site_kernel : (const void*)kron_cvi_ell_sur_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BYTES_FILTER);
+  if (e != cudaSuccess) return cuda_status(e, "cvi (large blocks): cudaFuncSetAttribute");
+  if (update) kron_cvi_site_kernel<<<grid, NTH, SM_BYTES_FILTER, (cudaStream_t)stream>>>(a);
+  else kron_cvi_ell_sur_kernel<<<grid, NTH, SM_BYTES_FILTER, (cudaStream_t)stream>>>(a);
+  return cuda_status(cudaGetLastError(), "cvi (large blocks) launch");
+}
+
+int physs_cvi_natgrad_big_f64(void* stream, int64_t T, int32_t D, const double* Yt, const double* Vt, const double* qm,
+                              const double* dm, const double* dS, int32_t dS_diag, double beta, double ngj, void* ws,
+                              int64_t ws_bytes, double* Yn, double* Vn) {
+  if (T > 0 && (!Yt || !Vt || !qm || !dm || !dS || !Yn || !Vn))
+    return set_error(PHYSS_ERR_BAD_ARG, "cvi natgrad (large blocks): null required pointer");
+  CviBigArgs a{};
+  a.T = T; a.D = D; a.Yt = Yt; a.Vt = Vt; a.qm = qm; a.dm = dm; a.dS = dS; a.dS_diag = dS_diag ? 1 : 0;
+  a.beta = beta; a.ngj = ngj; a.Yn = Yn; a.Vn = Vn;
+  return cvi_big_launch(stream, true, a, ws, ws_bytes);
+}
+
+int physs_cvi_ell_sur_big_f64(void* stream, int64_t T, int32_t D, const double* Yt, const double* Vt, const double* qm,
+                              const double* qS, void* ws, int64_t ws_bytes, double* ell) {
+  if (T > 0 && (!Yt || !Vt || !qm || !qS || !ell))
+    return set_error(PHYSS_ERR_BAD_ARG, "cvi surrogate ELL (large blocks): null required pointer");
+  CviBigArgs a{};
+  a.T = T; a.D = D; a.Yt = Yt; a.Vt = Vt; a.qm = qm; a.qS = qS; a.ell = ell;
+  return cvi_big_launch(stream, false, a, ws, ws_bytes);
 }
 
 int physs_rts_smooth_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, const double* At, const double* Qt,

@@ -106,6 +106,8 @@ def natgrad_step(Ytil, Vtil, q_mu, q_var, y, W, lik, beta, ng_jitter=None, K=20,
     Ytil [..., D], Vtil [..., D, D], q_mu, q_var alike; y [..., P]; W [P, D] or None.
     Returns (Ytil_new, Vtil_new[, ell [...]])."""
     lib = _lib.load()
+    if Ytil.shape[-1] > BIG_BLOCK_MIN:
+        return _natgrad_step_big(Ytil, Vtil, q_mu, q_var, y, W, lik, beta, ng_jitter, dm, dS, want_ell, out, stream)
     given = dm is not None
     (Ytil, Vtil, q_mu, q_var, yv, dm, dS), tm = _block_order(
         [Ytil, Vtil, q_mu, q_var, None if given else y, dm, dS])
@@ -149,6 +151,8 @@ def expected_log_likelihood(q_mu, q_var, y, W, lik, K=20, noise=None, want_grads
     """Raw op: per-block ELL [...], optionally with dELL/dm [..., D] and dELL/dS [..., D, D].
     `noise` overrides lik.noise with a per-block tensor [..., P, P] (used for the surrogate ELL)."""
     lib = _lib.load()
+    if q_mu.shape[-1] > BIG_BLOCK_MIN:
+        return _expected_log_likelihood_big(q_mu, q_var, y, W, lik, noise, want_grads, stream)
     per_block_noise = noise if (noise is not None and noise.dim() > 2) else None
     (q_mu, q_var, y, per_block_noise), tm = _block_order([q_mu, q_var, y, per_block_noise])
     D, P = q_mu.shape[-1], y.shape[-1]
@@ -177,6 +181,108 @@ def expected_log_likelihood(q_mu, q_var, y, W, lik, K=20, noise=None, want_grads
     _lib.check(st, "physs_cvi_ell_f64")
     ell, dm, dS = _back(ell, tm), _back(dm, tm), _back(dS, tm)
     return (ell, dm, dS) if want_grads else ell
+
+
+# ------------------------------------------------------------------ large site blocks (config 2: D = Ns = 200)
+BIG_BLOCK_MIN = 32            # site blocks above this size go to the one-CTA-per-block kernels (D <= 208)
+
+
+def _big_ws(D, dev):
+    with torch.cuda.device(dev):
+        n = _lib.load().physs_cvi_big_workspace_bytes(D)
+    if n <= 0:
+        raise NotImplementedError("CVI site blocks: D <= 208 (D = %d)" % D)
+    return torch.empty((n // 8 + 2,), dtype=torch.float64, device=dev)
+
+
+def gaussian_diag_ell(q_mu, q_var, y, noise_var, want_grads=False):
+    """Closed-form block ELL of a Gaussian likelihood with DIAGONAL noise on the block entries themselves (W = I):
+    sum over the observed entries of log N(y_a | m_a, s2_a) - S_aa / (2 s2_a) (expected_log_likelihoods.py:90-117 with a
+    diagonal R), its gradient dm = (y - m) / s2 and the DIAGONAL of dS = -1 / (2 s2), zero at missing entries.
+    Elementwise torch ops on the device the marginals live on."""
+    obs = ~torch.isnan(y)
+    y0 = torch.where(obs, y, torch.zeros_like(y))
+    s2 = noise_var.expand_as(q_mu)
+    diag = torch.diagonal(q_var, dim1=-2, dim2=-1)
+    r = y0 - q_mu
+    ell = torch.where(obs, -0.5 * (np.log(2 * np.pi) + torch.log(s2) + (r * r + diag) / s2), torch.zeros_like(r)).sum(-1)
+    if not want_grads:
+        return ell
+    dm = torch.where(obs, r / s2, torch.zeros_like(r))
+    dS = torch.where(obs, -0.5 / s2, torch.zeros_like(r))
+    return ell, dm, dS
+
+
+def _diag_noise(lik, noise, D, dev):
+    nz = noise if noise is not None else lik.noise
+    nz = nz if isinstance(nz, torch.Tensor) else torch.as_tensor(np.asarray(nz, np.float64), device=dev)
+    if nz.dim() >= 2 and nz.shape[-1] == nz.shape[-2]:
+        off = nz - torch.diag_embed(torch.diagonal(nz, dim1=-2, dim2=-1))
+        if bool((off != 0).any()):
+            return None
+        nz = torch.diagonal(nz, dim1=-2, dim2=-1)
+    return nz.to(dev)
+
+
+def _natgrad_step_big(Ytil, Vtil, q_mu, q_var, y, W, lik, beta, ng_jitter, dm, dS, want_ell, out, stream):
+    lib = _lib.load()
+    D = Ytil.shape[-1]
+    lead = Ytil.shape[:-1]
+    dev = Ytil.device
+    ell = None
+    if dm is None:
+        if W is not None or getattr(lik, "kind", None) != _lib.LIK_GAUSS:
+            raise NotImplementedError("site blocks with D > %d: Gaussian likelihood on the block entries, or supplied "
+                                      "ELL gradients (dm, dS)" % BIG_BLOCK_MIN)
+        nz = _diag_noise(lik, None, D, dev)
+        if nz is None:
+            raise NotImplementedError("site blocks with D > %d: diagonal likelihood noise" % BIG_BLOCK_MIN)
+        ell, dm, dS = gaussian_diag_ell(q_mu, q_var, y, nz, want_grads=True)
+    Ytil, Vtil, q_mu, dm, dS = (_c(x) for x in (Ytil, Vtil, q_mu, dm, dS))
+    N = int(np.prod(lead))
+    diag = dS.dim() == dm.dim()
+    if out is None:
+        Yn, Vn = torch.empty_like(Ytil), torch.empty_like(Vtil)
+    else:
+        Yn, Vn = torch.empty_like(Ytil), torch.empty_like(Vtil)       # the kernel reads the old sites while writing
+    ws = _big_ws(D, dev)
+    ngj = settings.ng_jitter if ng_jitter is None else ng_jitter
+    s = stream if stream is not None else torch.cuda.current_stream()
+    with torch.cuda.device(dev):
+        st = lib.physs_cvi_natgrad_big_f64(s.cuda_stream, N, D, Ytil.data_ptr(), Vtil.data_ptr(), q_mu.data_ptr(),
+                                           dm.data_ptr(), dS.data_ptr(), 1 if diag else 0, float(beta), float(ngj),
+                                           ws.data_ptr(), ws.numel() * 8, Yn.data_ptr(), Vn.data_ptr())
+    _lib.check(st, "physs_cvi_natgrad_big_f64")
+    if out is not None:
+        out[0].copy_(Yn); out[1].copy_(Vn)
+        Yn, Vn = out
+    return (Yn, Vn, ell) if want_ell else (Yn, Vn)
+
+
+def _expected_log_likelihood_big(q_mu, q_var, y, W, lik, noise, want_grads, stream):
+    """D > BIG_BLOCK_MIN: diagonal Gaussian likelihood in closed form (torch), or -- `noise` a per-block full
+    covariance [..., D, D], the surrogate ELL -- physs_cvi_ell_sur_big_f64."""
+    lib = _lib.load()
+    D = q_mu.shape[-1]
+    dev = q_mu.device
+    if getattr(lik, "kind", None) != _lib.LIK_GAUSS or W is not None:
+        raise NotImplementedError("site blocks with D > %d: Gaussian likelihoods on the block entries" % BIG_BLOCK_MIN)
+    nz = _diag_noise(lik, noise, D, dev)
+    if nz is not None:
+        return gaussian_diag_ell(q_mu, q_var, y, nz, want_grads=want_grads)
+    if want_grads:
+        raise NotImplementedError("gradients of a full-covariance block ELL with D > %d" % BIG_BLOCK_MIN)
+    lead = q_mu.shape[:-1]
+    N = int(np.prod(lead))
+    Yt, Vt, qm, qS = (_c(x) for x in (y, noise, q_mu, q_var))
+    ell = torch.empty(lead, dtype=torch.float64, device=dev)
+    ws = _big_ws(D, dev)
+    s = stream if stream is not None else torch.cuda.current_stream()
+    with torch.cuda.device(dev):
+        st = lib.physs_cvi_ell_sur_big_f64(s.cuda_stream, N, D, Yt.data_ptr(), Vt.data_ptr(), qm.data_ptr(), qS.data_ptr(),
+                                           ws.data_ptr(), ws.numel() * 8, ell.data_ptr())
+    _lib.check(st, "physs_cvi_ell_sur_big_f64")
+    return ell
 
 
 class DampedPendulumLik:

@@ -115,3 +115,73 @@ def test_kron_non_pd_gives_nan(cuda_device, monkeypatch):
     assert not np.isfinite(float(lml))
     assert not torch.isfinite(kf['P'][4:]).any() and not torch.isfinite(kf['m'][4:]).any()
     assert torch.isfinite(kf['P'][:4]).all()
+
+
+# ----------------------------------------------------------------- CVI on large site blocks (config-2 CVI step)
+@pytest.mark.parametrize("D,diag", [(40, False), (40, True), (75, False), (200, True)])
+def test_big_block_site_update_matches_oracle(cuda_device, D, diag):
+    """physs_cvi_natgrad_big_f64 (theta -> lambda, cvi_block_update, lambda -> theta on D x D blocks, one CTA per block)
+    against oracle/cvi.py:cvi_step -- itself pinned to the reference's cvi_block_update / theta <-> lambda."""
+    from oracle import cvi as ocvi
+    from physs_gp_b200 import cvi
+    rng = np.random.default_rng(D + diag)
+    T = 5 if D < 100 else 3
+    Yt = rng.normal(size=(T, D))
+    Vt = synth.random_spd(rng, (T,), D, base=0.5, spread=0.1)
+    qm = rng.normal(size=(T, D))
+    qS = synth.random_spd(rng, (T,), D, base=0.2, spread=0.05)
+    dm = rng.normal(size=(T, D))
+    if diag:
+        dSd = -rng.uniform(0.5, 3.0, size=(T, D))
+        dS = np.stack([np.diag(x) for x in dSd])
+    else:
+        dS = -synth.random_spd(rng, (T,), D, base=0.5, spread=0.1)
+    Yo, Vo = ocvi.cvi_step(Yt, Vt, qm, qS, dm, dS, 0.3, ng_jitter=1e-7)
+    tt = lambda x: torch.as_tensor(x, dtype=torch.float64, device=cuda_device)      # noqa: E731
+    Yn, Vn = cvi.natgrad_step(tt(Yt), tt(Vt), tt(qm), tt(qS), None, None, None, 0.3, ng_jitter=1e-7,
+                              dm=tt(dm), dS=tt(dSd if diag else dS))
+    assert rel(Yn, Yo) < TOL and rel(Vn, Vo) < TOL
+
+
+def test_big_block_surrogate_ell_matches_oracle(cuda_device):
+    from oracle import cvi as ocvi
+    from physs_gp_b200 import cvi
+    rng = np.random.default_rng(3)
+    T, D = 4, 56
+    Yt = rng.normal(size=(T, D)); qm = rng.normal(size=(T, D))
+    Vt = synth.random_spd(rng, (T,), D, base=0.5, spread=0.1)
+    qS = synth.random_spd(rng, (T,), D, base=0.2, spread=0.05)
+    tt = lambda x: torch.as_tensor(x, dtype=torch.float64, device=cuda_device)      # noqa: E731
+    ell = cvi.expected_log_likelihood(tt(qm), tt(qS), tt(Yt), None, cvi.GaussianLik(np.eye(D)), noise=tt(Vt))
+    ref = np.array([ocvi.full_gaussian_ell(Yt[t][:, None], Vt[t], qm[t][:, None], qS[t]) for t in range(T)])
+    assert rel(ell, ref) < TOL
+
+
+def test_config2_cvi_iterations_match_oracle(cuda_device, monkeypatch):
+    """The config-2 CVI step end to end at a small size: separable Matern-3/2 x RBF prior over Ns = 36 points, ONE
+    D = 36 site block per time step, Gaussian likelihood with missing data -- two natural-gradient iterations
+    (kron filter + smoother, site update on the large-block kernels) and the ELBO against the numpy oracle."""
+    from oracle import cvi as ocvi
+    from physs_gp_b200 import cvi, settings
+    monkeypatch.setattr(settings, "jitter", 1e-5)
+    Ns, T, beta, s2 = 36, 14, 0.5, 0.3
+    pprior, oprior, t, Y, _ = _problem(Ns, T, 31)
+    q = cvi.FullConjugateGaussian(t, pprior, Ns, B=1)
+    model = cvi.VGP(Y[None], cvi.GaussianLik(s2 * np.eye(Ns)), q)
+    for _ in range(2):
+        model.natural_gradient_update(beta)
+    elbo = model.elbo()
+    torch.cuda.synchronize()
+    Yt = 1e-5 * np.ones((T, Ns)); Vt = np.tile(np.eye(Ns), [T, 1, 1])
+    R = s2 * np.eye(Ns)
+    for _ in range(2):
+        _, qm, qv = ofilters.filter_and_smooth(oprior, t, Yt, Vt)
+        dm = np.zeros((T, Ns)); dS = np.zeros((T, Ns, Ns))
+        for i in range(T):
+            _, dm[i], dS[i] = ocvi.gaussian_ell_and_grads(Y[i], R, np.eye(Ns), qm[i][:, 0], qv[i])
+        Yt, Vt = ocvi.cvi_step(Yt, Vt, qm[:, :, 0], qv, dm, dS, beta)
+    lml, qm, qv = ofilters.filter_and_smooth(oprior, t, Yt, Vt)
+    ell = sum(ocvi.gaussian_ell_and_grads(Y[i], R, np.eye(Ns), qm[i][:, 0], qv[i])[0] for i in range(T))
+    ref = ocvi.elbo(ell, ocvi.surrogate_ell(Yt, Vt, qm[:, :, 0], qv), lml)
+    assert rel(model.q.Y_tilde[0], Yt) < 1e-8 and rel(model.q.V_tilde[0], Vt) < 1e-8
+    assert abs(float(elbo[0]) - ref) <= 1e-8 * abs(ref)
