@@ -298,3 +298,31 @@ def test_oracle_and_product_iwp_match_reference(q):
     for fs in (False, True):
         ms, Ps = ofilters.smoother_sequential(prior, g["t"], mf, Pf, full_state=fs, jitter=jit)
         assert rel(ms, g["ms_full%d" % fs]) < 1e-10 and rel(Ps, g["Ps_full%d" % fs]) < 1e-10
+
+
+# ---- separable spatio-temporal prior (config 2): tests/golden/make_golden_st.py
+def _st_files():
+    return sorted(glob.glob(os.path.join(GOLD, "st_*.npz")))
+
+
+def test_st_golden_files_present():
+    assert len(_st_files()) == 4
+
+
+@pytest.mark.parametrize("path", _st_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_oracle_separable_prior_matches_reference(path):
+    """oracle/sde.py:SpaceTimeSeparable (Kronecker stacking of kernel.py:213-265 / ss_utils.py:41-53) and the oracle's
+    filter / smoother on it against what the reference's own classes produce."""
+    g = np.load(path)
+    kind = osde.Matern32 if "m32" in path else osde.Matern52
+    prior = osde.LTI_SDE([osde.SpaceTimeSeparable(kind(*g["temporal"]), g["Ks"])])
+    assert rel(prior.P_inf(), g["P_inf"]) < 1e-14 and rel(prior.H(), g["H"]) == 0.0
+    for i, dt in enumerate((0.0, 0.05, 0.9)):
+        assert rel(prior.expm(dt), g["A_dt"][i]) < 1e-13
+    jit = float(g["jitter"])
+    lml, mf, Pf, _ = ofilters.filter_sequential(prior, g["t"], g["Y"], g["R"], jit)
+    assert abs(lml - float(g["seq_lml"])) <= 1e-11 * abs(float(g["seq_lml"]))
+    assert rel(mf, g["seq_mf"]) < 1e-10 and rel(Pf, g["seq_Pf"]) < 1e-10
+    for fs in (False, True):
+        ms, Ps = ofilters.smoother_sequential(prior, g["t"], mf, Pf, full_state=fs, jitter=jit)
+        assert rel(ms, g["seq_ms_full%d" % fs]) < 1e-9 and rel(Ps, g["seq_Ps_full%d" % fs]) < 1e-9

@@ -185,3 +185,32 @@ def test_config2_cvi_iterations_match_oracle(cuda_device, monkeypatch):
     ref = ocvi.elbo(ell, ocvi.surrogate_ell(Yt, Vt, qm[:, :, 0], qv), lml)
     assert rel(model.q.Y_tilde[0], Yt) < 1e-8 and rel(model.q.V_tilde[0], Vt) < 1e-8
     assert abs(float(elbo[0]) - ref) <= 1e-8 * abs(ref)
+
+
+# ----------------------------------------------------------- against REFERENCE output (tests/golden/make_golden_st.py)
+import glob  # noqa: E402
+import os  # noqa: E402
+
+_ST = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "st_*.npz")))
+
+
+@pytest.mark.parametrize("path", _ST, ids=lambda p: os.path.basename(p)[:-4])
+def test_kron_kernels_match_reference_vectors(cuda_device, _kron_on, path, monkeypatch):
+    """The separable-prior kernels against vectors the reference's own SpatioTemporalSeperableKernel + filter_loop +
+    smoother_loop produced (no oracle in between): d = 36 (ds = 2, Ns = 18 and ds = 3, Ns = 12), irregular grid,
+    dense R_k, partially missing steps, both jitters."""
+    from physs_gp_b200 import data, filters, kernels as K, sdes, settings
+    g = np.load(path)
+    jit = float(g["jitter"])
+    monkeypatch.setattr(settings, "jitter", jit)
+    kind = K.Matern32 if "m32" in path else K.Matern52
+    prior = sdes.LTI_SDE(sdes.Independent([K.SpatioTemporalSeperableKernel(kind(*g["temporal"]), g["Ks"])]))
+    assert rel(prior.P_inf(), g["P_inf"]) < 1e-14 and np.array_equal(prior.H(), g["H"])
+    d = data.TemporalData(g["t"], g["Y"][:, :, None])
+    lml, kf = filters.filter_loop(d, prior, R=g["R"])
+    assert _kron_on["f"] == 1
+    assert abs(float(lml) - float(g["seq_lml"])) <= TOL * abs(float(g["seq_lml"]))
+    assert rel(kf['m'], g["seq_mf"]) < TOL and rel(kf['P'], g["seq_Pf"]) < TOL
+    for fs in (False, True):
+        mu, var = filters.smoother_loop(d, prior, kf, full_state=fs)
+        assert rel(mu, g["seq_ms_full%d" % fs]) < TOL and rel(var, g["seq_Ps_full%d" % fs]) < TOL
