@@ -125,6 +125,18 @@ struct Gemm {
   double* C2; const double* Sub2; int ld2;
   double* Cp; int ldp; int ds;
   double* prof;                 // measurement aid: slots 24.. (thread 0 of CTA 0)
+  const struct PredictFuse* fuse;   // filter only: predict of the NEXT step applied to every finished tile
+};
+
+// The predict phase of step k + 1 fused into the update epilogue of step k (lower mode, 32 % ds == 0): a finished
+// 32 x 32 tile of P_k holds whole ds x ds blocks, so  P_ = A P A^T + Q,  the innovation covariances and the masked
+// P_ H^T of the next step follow tile by tile -- one phase and one grid barrier less per step.  The outputs go to the
+// OTHER half of the double-buffered (Pp, W): this step's tiles are still being read by other CTAs.
+struct PredictFuse {
+  int Ns, ds, d;
+  const double* At; const double* Qt;      // ds x ds of step k + 1
+  const double* Ks; const double* y; const double* R; double jitter;
+  double* Pp; double* W; double* SjA; double* SmA;
 };
 
 __device__ __forceinline__ bool vec_ok(const double* p, int64_t ld) {
@@ -181,6 +193,73 @@ __device__ __forceinline__ void load_kn(int lt, double* dst, const double* src, 
       const double x1 = (r < vr && c + 1 < vc) ? __ldcg(s + 1) : 0.0;
       *reinterpret_cast<double2*>(d) = make_double2(x0, x1);
     }
+  }
+}
+
+constexpr int DSMAX = 4;
+
+__device__ __noinline__ void fused_predict(const PredictFuse& f, const double* Tt, int r0, int c0, bool mirror) {
+  const int ds = f.ds, Ns = f.Ns, d = f.d, m = f.Ns;
+  const int nbt = 32 / ds;
+  double at[DSMAX][DSMAX], qt[DSMAX][DSMAX];
+#pragma unroll
+  for (int a = 0; a < DSMAX; ++a)
+#pragma unroll
+    for (int b = 0; b < DSMAX; ++b) {
+      at[a][b] = (a < ds && b < ds) ? f.At[a * ds + b] : 0.0;
+      qt[a][b] = (a < ds && b < ds) ? f.Qt[a * ds + b] : 0.0;
+    }
+  for (int bp = threadIdx.x; bp < nbt * nbt; bp += NTH) {
+    const int bi = bp / nbt, bj = bp - bi * nbt;
+    const int I = r0 / ds + bi, J = c0 / ds + bj;
+    if (I >= Ns || J >= Ns) continue;
+    double blk[DSMAX][DSMAX], tmp[DSMAX][DSMAX];
+#pragma unroll
+    for (int a = 0; a < DSMAX; ++a)
+#pragma unroll
+      for (int b = 0; b < DSMAX; ++b) blk[a][b] = (a < ds && b < ds) ? Tt[(bi * ds + a) * 33 + bj * ds + b] : 0.0;
+#pragma unroll
+    for (int a = 0; a < DSMAX; ++a)
+#pragma unroll
+      for (int b = 0; b < DSMAX; ++b) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < DSMAX; ++c) s = fma(at[a][c], blk[c][b], s);
+        tmp[a][b] = s;
+      }
+    const double ks = f.Ks[(int64_t)I * Ns + J];
+    const double yi = f.y[I], yj = f.y[J];
+    const bool oi = !(yi != yi), oj = !(yj != yj);
+#pragma unroll
+    for (int a = 0; a < DSMAX; ++a)
+#pragma unroll
+      for (int b = 0; b < DSMAX; ++b) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < DSMAX; ++c) s = fma(tmp[a][c], at[b][c], s);
+        blk[a][b] = s + ks * qt[a][b];
+        if (a < ds && b < ds) {
+          f.Pp[(int64_t)(I * ds + a) * d + J * ds + b] = blk[a][b];
+          if (mirror) f.Pp[(int64_t)(J * ds + b) * d + I * ds + a] = blk[a][b];
+        }
+      }
+    const double p00 = (oi && oj) ? blk[0][0] : 0.0;
+    {
+      const double sv = p00 + f.R[(int64_t)I * Ns + J];
+      f.SjA[(int64_t)I * m + J] = sv + (I == J ? f.jitter : 0.0);
+      f.SmA[(int64_t)I * m + J] = (oi && oj) ? sv : (I == J ? 1.0 : 0.0);
+    }
+    if (mirror) {                                     // I != J in a tile strictly below the diagonal
+      const double sv = p00 + f.R[(int64_t)J * Ns + I];
+      f.SjA[(int64_t)J * m + I] = sv;
+      f.SmA[(int64_t)J * m + I] = (oi && oj) ? sv : 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < DSMAX; ++a)
+      if (a < ds) {
+        f.W[(int64_t)(I * ds + a) * m + J] = oj ? blk[a][0] : 0.0;
+        if (mirror) f.W[(int64_t)(J * ds + a) * m + I] = oi ? blk[0][a] : 0.0;      // P_ symmetric
+      }
   }
 }
 
@@ -343,8 +422,8 @@ __device__ __noinline__ void gemm_tiles(const Gemm& g, int cta, int ncta, double
           }
         }
       }
-      if (mirror) {                                   // MT == 4 here: a 32 x 32 tile strictly below the diagonal
-        __syncthreads();                              // (Tt may still be read by the previous tile's mirror stores)
+      if (mirror || g.fuse) {                         // MT == 4 here: stage the finished 32 x 32 tile in shared memory
+        __syncthreads();                              // (Tt may still be read by the previous tile's readers)
         if (!loader) {
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
@@ -353,7 +432,8 @@ __device__ __noinline__ void gemm_tiles(const Gemm& g, int cta, int ncta, double
           }
         }
         __syncthreads();
-        for (int idx = tid; idx < 1024; idx += NTH) {
+        if (g.fuse) fused_predict(*g.fuse, Tt, r0, c0, mirror);
+        for (int idx = tid; mirror && idx < 1024; idx += NTH) {
           const int cc = idx >> 5, rr = idx & 31;      // consecutive lanes: consecutive columns of the mirrored row
           const int row = c0 + cc, col = r0 + rr;
           if (row < g.N && col < g.M) {
@@ -1049,8 +1129,6 @@ __global__ void __launch_bounds__(NTH, 1) kron_cvi_ell_sur_kernel(const CviBigAr
   (void)warp; (void)lane;
 }
 
-constexpr int DSMAX = 4;
-
 // phase timers (ns, CTA 0): accumulated into the workspace tail when PHYSS_KRON_PROF is set -- measurement aid
 #define KRON_TICK(slot)                                              \
   if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) {               \
@@ -1071,6 +1149,7 @@ struct FilterArgs {
   double* Pp; double* W; double* Kb; double* SjA; double* SmA; double* mp; double* acc;
   double* prof;
   unsigned long long* bar;
+  int fuse_predict;
 };
 
 __global__ void __launch_bounds__(NTH, 1) kron_filter_kernel(const FilterArgs p) {
@@ -1082,15 +1161,14 @@ __global__ void __launch_bounds__(NTH, 1) kron_filter_kernel(const FilterArgs p)
   const int64_t gt = (int64_t)cta * NTH + tid, gstride = (int64_t)ncta * NTH;
   const int cta_lml = ncta > 1 ? 1 : 0;
   if (cta == cta_lml && tid == 0) p.acc[0] = 0.0;
-  unsigned long long tick_ = gtimer();
-  for (int64_t k = 0; k < p.T; ++k) {
+  const int64_t dd = (int64_t)d * d, dm_ = (int64_t)d * m;
+  // predict of step k: P_ = A P A^T + Q into Pp_o, innovation covariances, masked P_ H^T into W_o (all CTAs)
+  auto predict_cov = [&](int64_t k, double* Pp_o, double* W_o) {
     const double* At = p.At + (int64_t)p.idx[k] * ds * ds;
     const double* Qt = p.Qt + (int64_t)p.idx[k] * ds * ds;
-    const double* Pprev = k ? p.Pf + (k - 1) * (int64_t)d * d : p.P0;
-    const double* mprev = k ? p.mf + (k - 1) * (int64_t)d : p.m0;
+    const double* Pprev = k ? p.Pf + (k - 1) * dd : p.P0;
     const double* y = p.Y + k * m;
     const double* Rk = p.R + k * p.R_ts;
-    // ---- phase 1: predict, innovation covariance (jittered and mask-to-identity copies), masked P_ H^T
     double at[DSMAX][DSMAX], qt[DSMAX][DSMAX];
 #pragma unroll
     for (int a = 0; a < DSMAX; ++a)
@@ -1127,20 +1205,26 @@ __global__ void __launch_bounds__(NTH, 1) kron_filter_kernel(const FilterArgs p)
 #pragma unroll
           for (int c = 0; c < DSMAX; ++c) s = fma(tmp[a][c], at[b][c], s);
           blk[a][b] = s + ks * qt[a][b];
-          if (a < ds && b < ds) p.Pp[(int64_t)(I * ds + a) * d + J * ds + b] = blk[a][b];
+          if (a < ds && b < ds) Pp_o[(int64_t)(I * ds + a) * d + J * ds + b] = blk[a][b];
         }
       const double s = ((oi && oj) ? blk[0][0] : 0.0) + Rk[(int64_t)I * Ns + J];
       p.SjA[(int64_t)I * m + J] = s + (I == J ? p.jitter : 0.0);
       p.SmA[(int64_t)I * m + J] = (oi && oj) ? s : (I == J ? 1.0 : 0.0);
 #pragma unroll
       for (int a = 0; a < DSMAX; ++a)
-        if (a < ds) p.W[(int64_t)(I * ds + a) * m + J] = oj ? blk[a][0] : 0.0;
+        if (a < ds) W_o[(int64_t)(I * ds + a) * m + J] = oj ? blk[a][0] : 0.0;
     }
-    for (int64_t I = gt; I < Ns; I += gstride) {
+  };
+  // predicted mean and innovation of step k (threads first, first + stride, ...)
+  auto predict_mean = [&](int64_t k, int64_t first, int64_t stride) {
+    const double* At = p.At + (int64_t)p.idx[k] * ds * ds;
+    const double* mprev = k ? p.mf + (k - 1) * (int64_t)d : p.m0;
+    const double* y = p.Y + k * m;
+    for (int64_t I = first; I < Ns; I += stride) {
       double mu0 = 0.0;
       for (int a = 0; a < ds; ++a) {
         double s = 0.0;
-        for (int b = 0; b < ds; ++b) s = fma(at[a][b], __ldcg(mprev + I * ds + b), s);
+        for (int b = 0; b < ds; ++b) s = fma(At[a * ds + b], __ldcg(mprev + I * ds + b), s);
         p.mp[I * ds + a] = s;
         if (a == 0) mu0 = s;
       }
@@ -1149,9 +1233,21 @@ __global__ void __launch_bounds__(NTH, 1) kron_filter_kernel(const FilterArgs p)
       p.SjA[(int64_t)m * m + I] = v;
       p.SmA[(int64_t)m * m + I] = v;
     }
-    KRON_TICK(0)
-    grid.sync();
-    KRON_TICK(1)
+  };
+  // the predict of step k + 1 rides in the update epilogue of step k when tiles hold whole ds x ds blocks
+  const bool fusable = (32 % ds) == 0 && p.fuse_predict;
+  unsigned long long tick_ = gtimer();
+  predict_cov(0, p.Pp, p.W);
+  predict_mean(0, gt, gstride);
+  KRON_TICK(0)
+  grid.sync();
+  KRON_TICK(1)
+  for (int64_t k = 0; k < p.T; ++k) {
+    double* Ppc = p.Pp + (k & 1) * dd;              // this step's predicted covariance and P_ H^T / X
+    double* Wc = p.W + (k & 1) * dm_;
+    double* Ppn = p.Pp + ((k + 1) & 1) * dd;        // the next step's
+    double* Wn = p.W + ((k + 1) & 1) * dm_;
+    const double* y = p.Y + k * m;
     // ---- phase 2: the two Cholesky factorisations, each with the innovation appended as an extra row
     const bool resident = m <= TRI_N;
     if (cta == 0) {
@@ -1193,7 +1289,7 @@ __global__ void __launch_bounds__(NTH, 1) kron_filter_kernel(const FilterArgs p)
     // ---- phase 3: rows of X = W L^-T (in place in W), the mean update, rows of K = X L^-1
     for (int rb = cta; rb * 8 < d; rb += ncta) {
       const int i0 = rb * 8, R = min(8, d - i0);
-      double* Xr = p.W + (int64_t)i0 * m;
+      double* Xr = Wc + (int64_t)i0 * m;
       double* Kr = p.Kb + (int64_t)i0 * m;
       if (resident) {
         trsm_smem(p.SjA, m, m, Xr, R, p.jitter != 0.0 ? Kr : nullptr, p.SjA + (int64_t)m * m, p.mp + i0,
@@ -1220,25 +1316,43 @@ __global__ void __launch_bounds__(NTH, 1) kron_filter_kernel(const FilterArgs p)
     KRON_TICK(4)
     grid.sync();
     KRON_TICK(5)
-    // ---- phase 4: P = P_ - X X^T + jitter K K^T  (== P_ - K S K^T with the un-jittered S)
+    // ---- phase 4: P = P_ - X X^T + jitter K K^T  (== P_ - K S K^T with the un-jittered S), and -- fused into its
+    // epilogue -- the predict of step k + 1
+    const bool fuse = fusable && k + 1 < p.T;
     {
+      PredictFuse fz;
+      if (fuse) {
+        fz.Ns = Ns; fz.ds = ds; fz.d = d;
+        fz.At = p.At + (int64_t)p.idx[k + 1] * ds * ds; fz.Qt = p.Qt + (int64_t)p.idx[k + 1] * ds * ds;
+        fz.Ks = p.Ks; fz.y = p.Y + (k + 1) * m; fz.R = p.R + (k + 1) * p.R_ts; fz.jitter = p.jitter;
+        fz.Pp = Ppn; fz.W = Wn; fz.SjA = p.SjA; fz.SmA = p.SmA;
+      }
       Gemm g = {};
       g.nt = 1;
-      g.A[0] = p.W; g.lda[0] = m; g.B[0] = p.W; g.ldb[0] = m; g.K[0] = m; g.sg[0] = -1.0;
+      g.A[0] = Wc; g.lda[0] = m; g.B[0] = Wc; g.ldb[0] = m; g.K[0] = m; g.sg[0] = -1.0;
       g.npair = 1;
       if (p.jitter != 0.0) {
         g.A[1] = p.Kb; g.lda[1] = m; g.B[1] = p.Kb; g.ldb[1] = m; g.K[1] = m; g.sg[1] = p.jitter;
         g.npair = 2;
       }
       g.M = d; g.N = d;
-      g.Add = p.Pp; g.ldadd = d;
-      g.C = p.Pf + k * (int64_t)d * d; g.ldc = d;
+      g.Add = Ppc; g.ldadd = d;
+      g.C = p.Pf + k * dd; g.ldc = d;
       g.lower = 1;
+      g.fuse = fuse ? &fz : nullptr;
       gemm_tiles<4>(g, cta, ncta, sm);
+      if (fuse && cta == ncta - 1) predict_mean(k + 1, tid, NTH);      // mf[k] is complete since the last barrier
     }
     KRON_TICK(6)
     grid.sync();
     KRON_TICK(7)
+    if (!fuse && k + 1 < p.T) {
+      predict_cov(k + 1, Ppn, Wn);
+      predict_mean(k + 1, gt, gstride);
+      KRON_TICK(0)
+      grid.sync();
+      KRON_TICK(1)
+    }
   }
   if (cta == cta_lml && tid == 0) p.lml[0] = p.acc[0];
 }
@@ -1487,8 +1601,8 @@ FilterWs filter_ws(int Ns, int ds) {
   const int64_t d = (int64_t)Ns * ds, m = Ns;
   FilterWs w{};
   int64_t o = 0;
-  w.Pp = o; o += align2(d * d);
-  w.W = o; o += align2(d * m);
+  w.Pp = o; o += 2 * align2(d * d);            // double-buffered: the predict of step k + 1 is written while the
+  w.W = o; o += 2 * align2(d * m);             // tiles of step k are still being read
   w.Kb = o; o += align2(d * m);
   w.SjA = o; o += align2((m + 1) * m);
   w.SmA = o; o += align2((m + 1) * m);
@@ -1560,6 +1674,7 @@ int physs_kf_filter_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, co
   a.T = T; a.Ns = Ns; a.ds = ds; a.d = Ns * ds;
   a.At = At; a.Qt = Qt; a.idx = idx; a.Ks = Ks; a.m0 = m0; a.P0 = P0; a.Y = Y; a.R = R; a.R_ts = R_tstride;
   a.jitter = jitter; a.mf = mf; a.Pf = Pf; a.lml = lml;
+  a.fuse_predict = getenv("PHYSS_KRON_NOFUSE") ? 0 : 1;
   a.prof = getenv("PHYSS_KRON_PROF") ? w + L.prof : nullptr;
   if (a.prof) cudaMemsetAsync(a.prof, 0, 32 * sizeof(double), (cudaStream_t)stream);
   a.Pp = w + L.Pp; a.W = w + L.W; a.Kb = w + L.Kb; a.SjA = w + L.SjA; a.SmA = w + L.SmA; a.mp = w + L.mp; a.acc = w + L.acc;
