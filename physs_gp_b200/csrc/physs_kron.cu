@@ -12,12 +12,16 @@
 //   covariance        P = P_ - K S K^T = P_ - X X^T + jitter K K^T       one rank-2m update on the tensor cores
 //   lml               second Cholesky of the un-jittered, mask-to-identity S (gaussian.py:72-108)
 //
-// One PERSISTENT cooperative kernel runs all T filter steps: 1 CTA per SM, grid-wide barriers between the four
-// phases of a step; every dense product is a tile GEMM on DMMA.8x8x4 (mma.sync.m8n8k4.f64) with cp.async
-// double-buffered operand tiles.  The smoother splits into a part that is PARALLEL over time -- the gains
-// G_k = Pf_k A^T (A Pf_k A^T + Q + jitter I)^-1 depend on the filter output only: one CTA per time step,
-// Cholesky + two triangular solves -- and the sequential recursion P_s,k = Pf_k + G_k (P_s,k+1 - P_pred,k) G_k^T,
-// two distributed GEMMs per step in a second persistent cooperative kernel.
+// One PERSISTENT cooperative kernel runs all T filter steps: 1 CTA per SM, a two-level atomic grid barrier between
+// the phases of a step -- innovation Cholesky (shared-memory resident, with look-ahead), gain solves (factor resident
+// in shared memory, 8 rows per CTA), rank-2m covariance update with the predict of the NEXT step fused into its
+// epilogue.  Every dense product is a tile GEMM on DMMA.8x8x4 (mma.sync.m8n8k4.f64): warps 0-3 issue the DMMAs,
+// warps 4-7 stage the next 128-deep operand chunk with 16-byte cp.async.  The smoother splits into a part that is
+// PARALLEL over time -- the gains G_k = Pf_k A^T (A Pf_k A^T + Q + jitter I)^-1 depend on the filter output only: one
+// CTA per time step, blocked Cholesky + two blocked triangular solves out of L2 -- and the sequential recursion
+// P_s,k = Pf_k + G_k (P_s,k+1 - P_pred,k) G_k^T, two distributed GEMMs per step in a second persistent cooperative
+// kernel.  The same shared-memory Cholesky serves the CVI site update / surrogate ELL of D <= 208 site blocks
+// (kron_cvi_site_kernel, kron_cvi_ell_sur_kernel).  Measured phase budgets: DESIGN.md section 3, "Config 2".
 //
 // All matrices row-major fp64; NaN on numerical failure (sqrt of a non-positive pivot), status 0.
 #include <cuda_runtime.h>
