@@ -214,3 +214,13 @@ def test_kron_kernels_match_reference_vectors(cuda_device, _kron_on, path, monke
     for fs in (False, True):
         mu, var = filters.smoother_loop(d, prior, kf, full_state=fs)
         assert rel(mu, g["seq_ms_full%d" % fs]) < TOL and rel(var, g["seq_Ps_full%d" % fs]) < TOL
+
+
+def test_kron_beyond_resident_size_and_single_step(cuda_device, _kron_on, monkeypatch):
+    """m = 212 > 208: the innovation Cholesky and the gain solves no longer fit in shared memory and run the blocked
+    out-of-L2 forms (chol_blocked / trsm_fwd / trsm_bwd); and T = 1 (no smoother recursion, no fused predict)."""
+    from physs_gp_b200 import settings
+    monkeypatch.setattr(settings, "jitter", 1e-5)
+    _run_and_compare(*_problem(212, 3, 77), 1e-5)
+    _run_and_compare(*_problem(20, 1, 78), 1e-5)
+    assert _kron_on["f"] == 2
