@@ -181,6 +181,22 @@ class GenericLTI:
         return sla.expm(self.F * dt)
 
 
+class ApproxPeriodicBN(GenericLTI):
+    """kernels/periodic.py:171-253 (`ApproxSDEPeriodic_BN`): the periodic covariance as a sum of n_terms + 1 harmonic
+    oscillators (Solin & Sarkka 2014).  F = kron(diag(0..J), [[0, -w], [w, 0]]) (:231), Pinf = kron(diag(q2), I_2) (:234)
+    with q2_j = (1 if j == 0 else 2) * variance * ive(j, lengthscale^-2) (:226; tfp's `bessel_ive` is scipy's `ive`),
+    H = kron(ones, [1, 0]) (:236), A = expm(F dt) through the generic Pade `expm` (:250-253) as in the reference."""
+
+    def __init__(self, frequency, lengthscale, variance, n_terms=10):
+        from scipy.special import ive
+        J = int(n_terms)
+        q2 = np.array([1.0] + [2.0] * J) * variance * ive(np.arange(J + 1, dtype=float), float(lengthscale) ** (-2))
+        F = np.kron(np.diag(np.arange(J + 1, dtype=float)), np.array([[0.0, -frequency], [frequency, 0.0]]))
+        Pinf = np.kron(np.diag(q2), np.eye(2))
+        H = np.kron(np.ones([1, J + 1]), np.array([[1.0, 0.0]]))
+        super().__init__(F, H, Pinf)
+
+
 class SumKernel:
     """kernels/kernel.py:134-160: block-diagonal F/Pinf/expm, hstacked H."""
 

@@ -124,6 +124,22 @@ struct MaternExpm<2> {
   }
 };
 
+// Size-2 block of a DISC_MATERN stack on the lane-group paths: lam >= 0 is a Matern-3/2 block; a lam with the SIGN BIT
+// set (including -0.0) selects a harmonic-oscillator block with angular frequency -lam, F = [[0, -w], [w, 0]],
+// expm(F dt) = rotation by w dt -- the j-th component of the reference's periodic kernels (kernels/periodic.py:
+// 213-253, F = kron(diag(0..J), [[0, -w0], [w0, 0]]), which the reference pushes through the generic
+// jax.scipy.linalg.expm).  Pinf of such a block is q_j^2 I, so Q_k = Pinf - A Pinf A^T vanishes to round-off.
+PHYSS_HD void block2_expm(double lam, double dt, double (&A)[2][2]) {
+  if (signbit(lam)) {
+    double sn, cs;
+    sincos(-lam * dt, &sn, &cs);
+    A[0][0] = cs; A[0][1] = -sn;
+    A[1][0] = sn; A[1][1] = cs;
+  } else {
+    MaternExpm<2>::eval(lam, dt, A);
+  }
+}
+
 template <>
 struct MaternExpm<3> {
   static PHYSS_HD void eval(double lam, double dt, double (&A)[3][3]) { evalT<double>(lam, dt, A); }

@@ -170,7 +170,7 @@ __device__ __forceinline__ void rt_matern_A(double* __restrict__ A, int s, int n
       blk[0] = a[0][0];
     } else if (s == 2) {
       double a[2][2];
-      MaternExpm<2>::eval(lam[b], dt, a);
+      block2_expm(lam[b], dt, a);
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -205,7 +205,7 @@ __device__ __forceinline__ void rt_matern_Ac(double* __restrict__ Ac, int s, int
       blk[0] = a[0][0];
     } else if (s == 2) {
       double a[2][2];
-      MaternExpm<2>::eval(lam[b], dt, a);
+      block2_expm(lam[b], dt, a);
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll

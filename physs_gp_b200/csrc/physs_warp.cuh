@@ -220,7 +220,7 @@ __device__ __forceinline__ void matern_A(double* __restrict__ A, int ld, int d, 
       blk[0] = a[0][0];
     } else if (s == 2) {
       double a[2][2];
-      MaternExpm<2>::eval(lam[b], dt, a);
+      block2_expm(lam[b], dt, a);
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll

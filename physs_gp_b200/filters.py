@@ -101,6 +101,8 @@ def lower_prior(prior, X_s, dts, dev, sequential=True):
     blocks = prior.ss_blocks() if hasattr(prior, "ss_blocks") else None
     P0 = _to_dev(P_inf[None], dev)
     m0 = _to_dev(m_inf, dev)
+    if blocks is not None and d <= 4 and any(np.signbit(l) for _, l in blocks):
+        blocks = None   # oscillator blocks (periodic kernels) are evaluated on chip by the lane-group kernels only
     if blocks is not None and len({s for s, _ in blocks}) == 1:
         s = blocks[0][0]
         mask = np.kron(np.eye(len(blocks)), np.ones([s, s]))

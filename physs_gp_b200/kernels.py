@@ -212,6 +212,56 @@ class WienerVelocity(MarkovKernel):
 IntegratedWiener = WienerVelocity
 
 
+class ApproxSDEPeriodic_BN(MarkovKernel):
+    """stgp/kernels/periodic.py:171-253: periodic covariance as a stack of n_terms + 1 harmonic oscillators,
+    d = 2 (n_terms + 1).  Same constructor arguments and `to_ss` / `expm` / `K` as the reference.  The reference
+    evaluates `expm(F dt)` with the generic Pade routine per step; F is block-diagonal with blocks j w [[0, -1], [1, 0]],
+    so A_k is a stack of plane rotations by j w dt -- which is what `expm` returns here and what the kernels evaluate on
+    chip (`ss_blocks`: a size-2 block whose lam carries the SIGN BIT is an oscillator of angular frequency -lam;
+    j = 0 is the identity block, lam = -0.0).  `include_dt` / `include_dt2` add the derivative rows of H (:238-245)."""
+
+    def __init__(self, frequency, lengthscale, variance, n_terms=10, include_dt=False, include_dt2=False):
+        self.frequency = float(frequency)
+        self.lengthscale = float(lengthscale)
+        self.variance = float(variance)
+        self.n_terms = self.order = int(n_terms)
+        self.include_dt, self.include_dt2 = bool(include_dt), bool(include_dt2)
+        self._state_space_dim = 2 * (self.n_terms + 1)
+        self.input_dim = 1
+
+    def _q2(self):
+        from scipy.special import ive          # tfp.math.bessel_ive of the reference (:226)
+        J = self.order
+        return np.array([1.0] + [2.0] * J) * self.variance * ive(np.arange(J + 1, dtype=np.float64),
+                                                                  self.lengthscale ** (-2))
+
+    def to_ss(self, X_spatial=None):
+        """(F, L, Qc, H, m_inf, Pinf).  The reference's periodic kernel returns five values (no m_inf, :247), which its
+        own `Independent.state_space_representation` (transform.py:400-408, out_dim = 6) cannot stack; the zero
+        stationary mean is supplied here so that the kernel composes like every other Markov kernel."""
+        J, w = self.order, self.frequency
+        j = np.arange(J + 1, dtype=np.float64)
+        F = np.kron(np.diag(j), np.array([[0.0, -w], [w, 0.0]]))
+        Pinf = np.kron(np.diag(self._q2()), np.eye(2))
+        H = np.kron(np.ones([1, J + 1]), np.array([[1.0, 0.0]]))
+        if self.include_dt2:
+            H = np.vstack([H, np.kron(-j * w, np.array([0.0, 1.0])), np.kron(-j * w, np.array([1.0, 0.0]))])
+        elif self.include_dt:
+            H = np.vstack([H, np.kron(-j * w, np.array([0.0, 1.0]))])
+        return F, np.eye(2 * (J + 1)), np.zeros([2 * (J + 1), 2 * (J + 1)]), H, np.zeros([2 * (J + 1), 1]), Pinf
+
+    def expm(self, dt, X_spatial=None):
+        ang = np.arange(self.order + 1, dtype=np.float64) * self.frequency * dt
+        return _block_diag([np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]) for a in ang])
+
+    def K(self, X1, X2):
+        tau = np.abs(X1.reshape(-1, 1) - X2.reshape(1, -1))
+        return self.variance * np.exp(-2.0 * np.square(np.sin(self.frequency * tau / 2.0) / self.lengthscale))
+
+    def ss_blocks(self):
+        return [(2, -(j * self.frequency)) for j in range(self.order + 1)]     # -(0 * w) = -0.0: identity block
+
+
 class SumKernel(MarkovKernel):
     """stgp/kernels/kernel.py:134-160: block-diagonal F/Pinf/expm, H = hstack."""
 

@@ -300,6 +300,57 @@ def test_oracle_and_product_iwp_match_reference(q):
         assert rel(ms, g["ms_full%d" % fs]) < 1e-10 and rel(Ps, g["Ps_full%d" % fs]) < 1e-10
 
 
+# --------------------------------------------------------------------------- periodic prior (row a6)
+def _periodic_files():
+    return sorted(glob.glob(os.path.join(GOLD, "periodic_*.npz")))
+
+
+def periodic_priors(g, osde_mod=None, K=None):
+    """(oracle kernel list, product kernel) of one periodic golden case."""
+    args = (float(g["frequency"]), float(g["lengthscale"]), float(g["variance"]), int(g["n_terms"]))
+    extra = g["extra_m32"]
+    ok = pk = None
+    if osde_mod is not None:
+        ok = [osde_mod.ApproxPeriodicBN(*args)] + ([osde_mod.Matern32(*extra)] if extra.size else [])
+        ok = [osde_mod.SumKernel(ok)] if len(ok) > 1 else ok
+    if K is not None:
+        pk = K.ApproxSDEPeriodic_BN(*args)
+        if extra.size:
+            pk = K.SumKernel(pk, K.Matern32(extra[0], extra[1]))
+    return ok, pk
+
+
+def test_periodic_golden_files_present():
+    assert len(_periodic_files()) == 5
+
+
+@pytest.mark.parametrize("path", _periodic_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_oracle_and_product_periodic_match_reference(path):
+    """oracle.sde.ApproxPeriodicBN (generic Pade expm, as the reference) and the product's closed-form rotation stack
+    kernels.ApproxSDEPeriodic_BN == the reference's ApproxSDEPeriodic_BN.{to_ss, expm} (kernels/periodic.py:213-253),
+    and the oracle filter / smoother on that prior == the reference's (tests/golden/make_golden_periodic.py)."""
+    from physs_gp_b200 import kernels as K, sdes
+    g = np.load(path)
+    ok, pk = periodic_priors(g, osde, K)
+    prior = osde.LTI_SDE(ok)
+    pprior = sdes.LTI_SDE(sdes.Independent([pk]))
+    assert rel(prior.P_inf(), g["P_inf"]) < 1e-14 and rel(prior.H(), g["H"]) == 0.0
+    assert rel(pprior.P_inf(), g["P_inf"]) < 1e-14 and rel(pprior.H(), g["H"]) == 0.0
+    for i, dt in enumerate((0.0, 0.05, 0.9)):
+        assert rel(prior.expm(dt), g["A_dt"][i]) < 1e-13
+        # closed-form rotations vs the reference's Pade expm (whose own error reaches 2e-13 at j w dt = 56 rad)
+        assert rel(pprior.expm(None, dt), g["A_dt"][i]) < 1e-12
+    blocks = pprior.ss_blocks()
+    assert all(s == 2 for s, _ in blocks) and np.signbit(blocks[0][1]) and blocks[0][1] == 0.0
+    jit = float(g["jitter"])
+    lml, mf, Pf, _ = ofilters.filter_sequential(prior, g["t"], g["Y"], g["R"], jit)
+    assert abs(lml - float(g["lml"])) <= 1e-10 * abs(float(g["lml"]))
+    assert rel(mf, g["mf"]) < 1e-9 and rel(Pf, g["Pf"]) < 1e-9
+    for fs in (False, True):
+        ms, Ps = ofilters.smoother_sequential(prior, g["t"], mf, Pf, full_state=fs, jitter=jit)
+        assert rel(ms, g["ms_full%d" % fs]) < 1e-8 and rel(Ps, g["Ps_full%d" % fs]) < 1e-8
+
+
 # ---- separable spatio-temporal prior (config 2): tests/golden/make_golden_st.py
 def _st_files():
     return sorted(glob.glob(os.path.join(GOLD, "st_*.npz")))

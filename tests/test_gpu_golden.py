@@ -145,3 +145,40 @@ def test_cuda_integrated_wiener_matches_reference_vectors(cuda_device, q, monkey
     lml_p, kf_p = filters.filter_loop(d, prior, R=g["R"], filter_type="b200_parallel")
     assert abs(float(lml_p) - float(g["lml"])) <= TOL * abs(float(g["lml"]))
     assert rel(kf_p['m'], g["mf"]) < TOL and rel(kf_p['P'], g["Pf"]) < TOL
+
+
+# --------------------------------------------------------------------------- periodic prior (row a6)
+import glob  # noqa: E402
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "periodic_*.npz"))),
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_cuda_periodic_prior_matches_reference_vectors(cuda_device, path, monkeypatch):
+    """the periodic prior (stack of harmonic oscillators, optionally summed with a Matern-3/2) with
+    A_k = rotation stack evaluated ON CHIP (sign-bit lam blocks of PHYSS_DISC_MATERN) against the reference's own
+    ApproxSDEPeriodic_BN -- which goes through the generic Pade expm -- under its sequential filter / smoother;
+    the DISC_GIVEN route (A_k, Q_k from the host mirror) and the parallel-in-time kernels must agree with it."""
+    from physs_gp_b200 import data, filters, kernels as K, sdes, settings, _lib
+    from tests.test_golden import periodic_priors
+    g = np.load(path)
+    monkeypatch.setattr(settings, "jitter", float(g["jitter"]))
+    _, pk = periodic_priors(g, None, K)
+    prior = sdes.LTI_SDE(sdes.Independent([pk]))
+    d = data.TemporalData(g["t"], g["Y"][:, :, None])
+    dev = cuda_device
+    (disc,), _, _, _ = filters.lower_prior(prior, None, [torch.zeros(3, dtype=torch.float64, device=dev)], dev)
+    assert disc.mode == _lib.DISC_MATERN                   # the on-chip route is the one under test
+    lml, kf = filters.filter_loop(d, prior, R=g["R"])
+    assert abs(float(lml) - float(g["lml"])) <= TOL * abs(float(g["lml"]))
+    assert rel(kf['m'], g["mf"]) < TOL and rel(kf['P'], g["Pf"]) < TOL
+    for fs in (False, True):
+        mu, var = filters.smoother_loop(d, prior, kf, full_state=fs)
+        assert rel(mu, g["ms_full%d" % fs]) < 1e-8 and rel(var, g["Ps_full%d" % fs]) < 1e-8
+    lml_p, kf_p = filters.filter_loop(d, prior, R=g["R"], filter_type="b200_parallel")
+    assert abs(float(lml_p) - float(g["lml"])) <= TOL * abs(float(g["lml"]))
+    assert rel(kf_p['m'], g["mf"]) < TOL and rel(kf_p['P'], g["Pf"]) < TOL
+    # host-evaluated transitions (what any prior without on-chip blocks uses) give the same answer
+    monkeypatch.setattr(type(pk), "ss_blocks", lambda self: None)
+    lml_g, kf_g = filters.filter_loop(d, prior, R=g["R"])
+    assert abs(float(lml_g) - float(g["lml"])) <= TOL * abs(float(g["lml"]))
+    assert rel(kf_g['P'], g["Pf"]) < TOL
