@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "cvi", "c2", "c2cvi", "c3cvi", "grad"],
+    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "cvi", "c2", "c2cvi", "c3cvi", "grad", "spatial"],
                     help="c5 (default, the headline metric): batched sweep; c3: one long series, parallel-in-time "
                          "scan, time-sharded over the ranks; cvi: CVI ELBO + natural-gradient step (config 4)")
     ap.add_argument("--chunk-len", type=int, default=256, help="c3: steps per scan chunk")
@@ -64,7 +64,8 @@ def parse():
     ap.add_argument("--cpu-sample-series", type=int, default=0, help="series in the CPU sample (0 = auto)")
     a = ap.parse_args()
     dflt = {"c5": (SERIES_TOTAL, T_STEPS, 4), "c3": (1, 1000000, 8), "cvi": (1000, T_STEPS, 2),
-            "c2": (200, 5000, 400), "c2cvi": (200, 5000, 400), "c3cvi": (1, 1000000, 4), "grad": (32768, T_STEPS, 4)}[a.workload]
+            "c2": (200, 5000, 400), "c2cvi": (200, 5000, 400), "c3cvi": (1, 1000000, 4), "grad": (32768, T_STEPS, 4),
+            "spatial": (200, 5000, 200)}[a.workload]
     a.series = dflt[0] if a.series is None else a.series
     a.T = dflt[1] if a.T is None else a.T
     a.state_dim = dflt[2] if a.state_dim is None else a.state_dim
@@ -1471,6 +1472,86 @@ def run_grad(a):
     print(json.dumps(line), flush=True)
 
 
+def run_spatial(a):
+    """SURVEY section 8 row f3 (second half): the spatial conditional behind the smoother at the config-2 shape -- the
+    posterior at M = 200 spatial points of each of T = 5000 steps carried to N new points
+    (physs_spatial_conditional_f64; --series = N, --state-dim = M).  Metric: conditioned time steps per second, full
+    N x N covariance blocks; the diagonal-only variant beside it.  Roofline: FP64 (DMMA) -- 2 M M N + N (N + 32) M flops
+    per step (lower triangle of the second product in 32-wide tiles) against the measured FP64 peak."""
+    import torch
+    from physs_gp_b200 import spatial
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        raise SystemExit("--workload spatial is a single-GPU workload (time steps are independent: shard T)")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    M, N, T = a.state_dim, a.series, a.T
+    rng = np.random.default_rng(5)
+    X, XS = rng.uniform(size=[M, 2]), rng.uniform(size=[N, 2])
+
+    def gram(A, B):
+        r = np.sqrt(((A[:, None, :] - B[None, :, :]) ** 2).sum(-1)) * np.sqrt(3.0) / 0.3
+        return (1.0 + r) * np.exp(-r)
+    Kzz, Ksz, Kss = gram(X, X), gram(XS, X), gram(XS, XS)
+    g = torch.Generator(device=dev).manual_seed(3)
+    Bm = torch.randn((T, M, 16), dtype=torch.float64, device=dev, generator=g) * 0.1
+    P = 0.2 * torch.as_tensor(Kzz, device=dev)[None] + Bm @ Bm.transpose(1, 2) + 0.01 * torch.eye(M, dtype=torch.float64, device=dev)
+    m = torch.randn((T, M, 1), dtype=torch.float64, device=dev, generator=g)
+    del Bm
+
+    def timed(diagonal):
+        for _ in range(a.warmup):
+            spatial.spatial_conditional_block(Kzz, Ksz, Kss, 0.9, m, P, diagonal=diagonal, jitter=1e-6)
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(a.steps):
+            mu, var = spatial.spatial_conditional_block(Kzz, Ksz, Kss, 0.9, m, P, diagonal=diagonal, jitter=1e-6)
+        t1.record()
+        torch.cuda.synchronize()
+        assert torch.isfinite(var).all()
+        return t0.elapsed_time(t1) / a.steps
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms_full = timed(False)
+    clocks = sampler.stop()
+    ms_diag = timed(True)
+    nt = (N + 31) // 32
+    flops_full = T * (2.0 * M * M * N + 2.0 * M * 32 * 32 * nt * (nt + 1) / 2)
+    flops_diag = T * (2.0 * M * M * N + 2.0 * M * N)
+    fp64_peak = 34.8
+    try:
+        fp64_peak = float(json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["tflops"])
+    except Exception:
+        pass
+    cpu = None
+    if not a.no_cpu_baseline:
+        from oracle import dense_gp
+        Ts = 40
+        t0 = time.perf_counter()
+        dense_gp.spatial_conditional(Kzz, Ksz, Kss, np.full(Ts, 0.9), m[:Ts].cpu().numpy(), P[:Ts].cpu().numpy(), 1e-6)
+        dt = time.perf_counter() - t0
+        cpu = {"value": Ts / dt, "unit": "time-steps/s", "cores": _host_threads(), "kind": "port",
+               "sample": "%d of %d steps (%.1f s): oracle/dense_gp.py:spatial_conditional, numpy / LAPACK -- "
+                         "restatement, not the JAX reference" % (Ts, T, dt)}
+    line = {"metric": "spatial conditional time-steps/sec (fp64)", "value": T / (ms_full * 1e-3), "unit": "time-steps/s",
+            "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_full, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "spatial: posterior at M = %d spatial points x %d time steps carried to N = %d new "
+                                   "points, full N x N covariance blocks (config-2 shape)" % (M, T, N),
+                       "M": M, "N": N, "T": T, "l2": "P [T, M, M] = %.1f GB >> 126 MB L2" % (T * M * M * 8 / 1e9)},
+            "roofline": {"bound": "tensor", "kernel": "kron_spatial_cond_kernel", "achieved": flops_full / (ms_full * 1e-3) / 1e12,
+                         "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops_full / (ms_full * 1e-3) / 1e12 / fp64_peak,
+                         "peak_source": "FP64 DFMA probe of round 1 (tools / physs_fp64_probe), not the bf16 figure of "
+                                        "MEASURED_PEAKS.json: the path computes in f64", "traffic": None,
+                         "hbm_gbs": T * 8.0 * (M * M + M + N * N + N) / (ms_full * 1e-3) / 1e9},
+            "diagonal_only": {"ms": ms_diag, "value": T / (ms_diag * 1e-3), "tflops": flops_diag / (ms_diag * 1e-3) / 1e12,
+                              "hbm_gbs": T * 8.0 * (M * M + M + 2 * N) / (ms_diag * 1e-3) / 1e9},
+            "cpu_baseline": cpu, "e2e": None, "clocks": clocks, "gpu_launches": 2 * a.steps}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     a = parse()
     # stdout carries the ONE JSON line and nothing else: native libraries that write to file descriptor 1 (NCCL's
@@ -1493,6 +1574,8 @@ def main():
         run_cvi(a)
     elif a.workload == "grad":
         run_grad(a)
+    elif a.workload == "spatial":
+        run_spatial(a)
     else:
         run_b200(a)
 

@@ -471,6 +471,22 @@ int physs_cvi_natgrad_big_f64(void* stream, int64_t T, int32_t D, const double* 
 int physs_cvi_ell_sur_big_f64(void* stream, int64_t T, int32_t D, const double* Yt, const double* Vt, const double* qm,
                               const double* qS, void* ws, int64_t ws_bytes, double* ell);
 
+/* ---- Spatial conditional after the smoother (second half): posterior at N new spatial points from the
+ * smoothed posterior (m_t, P_t) at the M inducing points, every time step independently.  Replaces the vmapped
+ * `gaussian_spatial_conditional_cholesky` (computation/marginals.py:82-113) that `spatial_conditional_block`
+ * (computation/spatial_conditionals.py:30-207, the f_only branch :150-207) runs per time step:
+ *     mu_t  = W m_t                                   W  = Ksz Kzz^-1                  [N, M]
+ *     var_t = ktt_t C0 + W (P_t + jitter I) W^T       C0 = Kss - Ksz Kzz^-1 Kzs        [N, N]
+ * (the reference factors P_t + jitter I, :137-141, and multiplies the factor back, marginals.py:104-107).  W and C0 are
+ * time-invariant and prepared by the caller; ktt [T] = the temporal kernel's variance at each step (`Ktt`, :84) or NULL
+ * for 1.  m [T, M], P [T, M, M] (symmetric), mu [T, N]; var [T, N, N] (exactly symmetric) or, with diagonal = 1, only
+ * its diagonal [T, N].  One persistent CTA per SM, tile GEMMs on DMMA.  ws: 16-byte aligned,
+ * physs_spatial_conditional_ws_bytes(M, N) bytes. */
+int64_t physs_spatial_conditional_ws_bytes(int32_t M, int32_t N);
+int physs_spatial_conditional_f64(void* stream, int64_t T, int32_t M, int32_t N, const double* W, const double* C0,
+                                  const double* ktt, const double* m, const double* P, double jitter,
+                                  int32_t diagonal, void* ws, int64_t ws_bytes, double* mu, double* var);
+
 /* FP64 FMA throughput probe (measurement aid for the FP64-pipe roofline; no reference counterpart).
  * Launches blocks x 256 threads doing iters x 8 independent FMAs each: flops = blocks*256*iters*16. */
 int physs_fp64_probe(void* stream, int32_t blocks, int64_t iters, double* out);

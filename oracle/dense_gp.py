@@ -26,3 +26,29 @@ def posterior(K, y, noise_var):
     V = sla.solve_triangular(L, K, lower=True)
     var = np.diag(K) - np.sum(V * V, axis=0)
     return mean, var
+
+
+def spatial_conditional(Kzz, Ksz, Kss, Ktt, pred_mean, pred_var, jitter):
+    """Posterior at new spatial points from the per-step posterior at the inducing points -- the `f_only` branch of
+    `spatial_conditional_block` (computation/spatial_conditionals.py:137-207: per-step Cholesky of
+    pred_var + jitter I, Cholesky of Kzz + jitter I, then the vmapped `gaussian_spatial_conditional_cholesky`,
+    computation/marginals.py:82-113), restated step by step:
+        A = L_zz^-1 Kzs, A1 = L_zz^-T A, A2 = (S_chol^T A1)^T,  mu = A1^T m,  sig = Ktt (Kss - A^T A) + A2 A2^T.
+    Kzz [M, M], Ksz [N, M], Kss [N, N], Ktt [T] (variance of the temporal kernel per step), pred_mean [T, M, 1],
+    pred_var [T, M, M].  Returns mu [T, N, 1], var [T, 1, N, N] (:198-201)."""
+    Kzz, Ksz, Kss = (np.asarray(x, float) for x in (Kzz, Ksz, Kss))
+    M = Kzz.shape[0]
+    Lzz = np.linalg.cholesky(Kzz + jitter * np.eye(M))
+    A = sla.solve_triangular(Lzz, Ksz.T, lower=True)
+    A1 = sla.solve_triangular(Lzz.T, A, lower=False)
+    C0 = Kss - A.T @ A
+    T = pred_mean.shape[0]
+    N = Kss.shape[0]
+    mu = np.zeros([T, N, 1])
+    var = np.zeros([T, 1, N, N])
+    for t in range(T):
+        S_chol = np.linalg.cholesky(pred_var[t] + jitter * np.eye(M))
+        A2 = (S_chol.T @ A1).T
+        mu[t] = A1.T @ pred_mean[t].reshape(M, 1)
+        var[t, 0] = Ktt[t] * C0 + A2 @ A2.T
+    return mu, var

@@ -13,7 +13,7 @@ PHYSS_OK = 0
 DISC_GIVEN = 0
 DISC_MATERN = 1
 DISC_IWP = 2
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _c_i32 = ctypes.c_int32
 _c_i64 = ctypes.c_int64
@@ -75,6 +75,9 @@ SIGNATURES = {
     "physs_cvi_natgrad_big_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i32, _c_f64, _c_f64,
                                                  _ptr, _c_i64, _ptr, _ptr]),
     "physs_cvi_ell_sur_big_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _ptr]),
+    "physs_spatial_conditional_ws_bytes": (_c_i64, [_c_i32, _c_i32]),
+    "physs_spatial_conditional_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _c_f64,
+                                                     _c_i32, _ptr, _c_i64, _ptr, _ptr]),
     "physs_kron_workspace_bytes": (_c_i64, [_c_i64, _c_i32, _c_i32, _c_i32]),
     "physs_kron_prof_offset": (_c_i64, [_c_i64, _c_i32, _c_i32, _c_i32]),
     "physs_kf_filter_kron_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,

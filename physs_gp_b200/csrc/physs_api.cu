@@ -78,7 +78,7 @@ static inline bool step_strides_ok(int64_t B, int64_t T, int64_t bs, int64_t ts)
 
 extern "C" {
 
-int physs_abi_version(void) { return 12; }
+int physs_abi_version(void) { return 13; }
 
 const char* physs_last_error(void) { return g_err; }
 

@@ -130,6 +130,7 @@ struct Gemm {
   double* Cp; int ldp; int ds;
   double* prof;                 // measurement aid: slots 24.. (thread 0 of CTA 0)
   const struct PredictFuse* fuse;   // filter only: predict of the NEXT step applied to every finished tile
+  const double* add_scale;      // optional device scalar multiplying Add (null: 1)
 };
 
 // The predict phase of step k + 1 fused into the update epilogue of step k (lower mode, 32 % ds == 0): a finished
@@ -417,7 +418,7 @@ __device__ __noinline__ void gemm_tiles(const Gemm& g, int cta, int ncta, double
             const int col = c0 + 8 * warp + 2 * tq + e;
             double v = sgl * acc[mt][e];
             if (row < g.M && col < g.N) {
-              if (g.Add) v += addv[mt][e];
+              if (g.Add) v = g.add_scale ? fma(__ldg(g.add_scale), addv[mt][e], v) : v + addv[mt][e];
               g.C[(int64_t)row * g.ldc + col] = v;
               if (g.C2) g.C2[(int64_t)row * g.ld2 + col] = v - __ldcg(g.Sub2 + (int64_t)row * g.ld2 + col);
               if (g.Cp && row % g.ds == 0 && col % g.ds == 0) g.Cp[(int64_t)(row / g.ds) * g.ldp + col / g.ds] = v;
@@ -1141,6 +1142,89 @@ __global__ void __launch_bounds__(NTH, 1) kron_cvi_ell_sur_kernel(const CviBigAr
     tick_ = now_;                                                    \
   }
 
+// ---------------------------------------------------------------- spatial conditional after the smoother (row f3)
+// Posterior at new spatial points from the smoothed posterior (m_t, P_t) at the M inducing points, every time step
+// independently (computation/spatial_conditionals.py:30-207 -> marginals.py:82-113, the `f_only` branch):
+//   mu_t  = W m_t,                     W = Ksz Kzz^-1  [N x M]   (time-invariant, prepared by the caller)
+//   var_t = ktt_t C0 + W (P_t + jitter I) W^T,   C0 = Kss - Ksz Kzz^-1 Kzs  [N x N]
+// (the reference factors P_t + jitter I and multiplies the factor back: the sum above is what that evaluates to).
+// One CTA per time step, persistent over t: U = jitter W^T + P_t W^T (M x N, per-CTA scratch that stays in L2), then
+// either the full N x N block by a second tile GEMM on the lower triangle (mirrored) or only its diagonal.
+struct SpatialCondArgs {
+  int64_t T; int M, N;
+  const double* W;        // [N, M]
+  const double* Wt;       // [M, N]  W^T            (workspace, written by spatial_cond_prep_kernel)
+  const double* jWt;      // [M, N]  jitter W^T     (workspace)
+  const double* C0;       // [N, N]
+  const double* ktt;      // [T] or null
+  const double* m;        // [T, M]
+  const double* P;        // [T, M, M]
+  int diagonal;
+  double* mu;             // [T, N]
+  double* var;            // [T, N, N] or [T, N]
+  double* scratch;        // per CTA: M N doubles
+};
+
+__global__ void spatial_cond_prep_kernel(const double* W, double* Wt, double* jWt, int M, int N, double jitter) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < (int64_t)M * N;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx / N), i = (int)(idx - (int64_t)j * N);
+    const double w = W[(int64_t)i * M + j];
+    Wt[idx] = w;
+    jWt[idx] = jitter * w;
+  }
+}
+
+__global__ void __launch_bounds__(NTH, 1) kron_spatial_cond_kernel(const SpatialCondArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, M = p.M, N = p.N;
+  double* U = p.scratch + (int64_t)blockIdx.x * M * N;
+  for (int64_t t = blockIdx.x; t < p.T; t += gridDim.x) {
+    const double* Pt = p.P + t * (int64_t)M * M;
+    const double* mt = p.m + t * (int64_t)M;
+    {
+      Gemm g = {};
+      g.npair = 1; g.nt = 1;
+      g.A[0] = Pt; g.lda[0] = M; g.B[0] = p.W; g.ldb[0] = M; g.K[0] = M; g.sg[0] = 1.0;
+      g.M = M; g.N = N;
+      g.Add = p.jWt; g.ldadd = N;
+      g.C = U; g.ldc = N;
+      gemm_tiles<5>(g, 0, 1, sm);
+    }
+    // mean: one warp per new point
+    for (int i = warp; i < N; i += NTH / 32) {
+      double a = 0.0;
+      for (int k = lane; k < M; k += 32) a = fma(__ldg(p.W + (int64_t)i * M + k), mt[k], a);
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) p.mu[t * N + i] = a;
+    }
+    __syncthreads();            // U complete (written by this CTA's own threads)
+    if (p.diagonal) {
+      const double kt = p.ktt ? p.ktt[t] : 1.0;
+      for (int i = tid; i < N; i += NTH) {
+        double a0 = 0.0, a1 = 0.0;
+        int j = 0;
+        for (; j + 2 <= M; j += 2) {
+          a0 = fma(__ldg(p.Wt + (int64_t)j * N + i), __ldcg(U + (int64_t)j * N + i), a0);
+          a1 = fma(__ldg(p.Wt + (int64_t)(j + 1) * N + i), __ldcg(U + (int64_t)(j + 1) * N + i), a1);
+        }
+        if (j < M) a0 = fma(__ldg(p.Wt + (int64_t)j * N + i), __ldcg(U + (int64_t)j * N + i), a0);
+        p.var[t * N + i] = fma(kt, __ldg(p.C0 + (int64_t)i * N + i), a0 + a1);
+      }
+    } else {
+      Gemm g = {};
+      g.npair = 1; g.nt = 0;
+      g.A[0] = p.W; g.lda[0] = M; g.B[0] = U; g.ldb[0] = N; g.K[0] = M; g.sg[0] = 1.0;
+      g.M = N; g.N = N;
+      g.Add = p.C0; g.ldadd = N; g.add_scale = p.ktt ? p.ktt + t : nullptr;
+      g.C = p.var + t * (int64_t)N * N; g.ldc = N;
+      g.lower = 1;
+      gemm_tiles<4>(g, 0, 1, sm);
+    }
+    __syncthreads();            // U is overwritten by the next step
+  }
+}
+
 // ------------------------------------------------------------------------------------------- filter
 struct FilterArgs {
   int64_t T;
@@ -1733,6 +1817,38 @@ int physs_cvi_ell_sur_big_f64(void* stream, int64_t T, int32_t D, const double* 
   CviBigArgs a{};
   a.T = T; a.D = D; a.Yt = Yt; a.Vt = Vt; a.qm = qm; a.qS = qS; a.ell = ell;
   return cvi_big_launch(stream, false, a, ws, ws_bytes);
+}
+
+int64_t physs_spatial_conditional_ws_bytes(int32_t M, int32_t N) {
+  if (M < 1 || N < 1) return 0;
+  Dev dv;
+  if (device_setup(dv) != PHYSS_OK) return 0;
+  return 8 * ((int64_t)M * N * (dv.sms + 2)) + 16;
+}
+
+int physs_spatial_conditional_f64(void* stream, int64_t T, int32_t M, int32_t N, const double* W, const double* C0,
+                                  const double* ktt, const double* m, const double* P, double jitter,
+                                  int32_t diagonal, void* ws, int64_t ws_bytes, double* mu, double* var) {
+  if (T < 0 || M < 1 || N < 1) return set_error(PHYSS_ERR_BAD_ARG, "spatial conditional: bad sizes");
+  if (T == 0) return PHYSS_OK;
+  if (!W || !C0 || !m || !P || !mu || !var) return set_error(PHYSS_ERR_BAD_ARG, "spatial conditional: null required pointer");
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15) != 0)
+    return set_error(PHYSS_ERR_BAD_ARG, "spatial conditional: workspace missing or not 16-byte aligned");
+  Dev dv;
+  if (int rc = device_setup(dv)) return rc;
+  const int64_t MN = (int64_t)M * N;
+  if (ws_bytes < 8 * MN * (dv.sms + 2)) return set_error(PHYSS_ERR_BAD_ARG, "spatial conditional: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* w = static_cast<double*>(ws);
+  SpatialCondArgs a{};
+  a.T = T; a.M = M; a.N = N; a.W = W; a.Wt = w; a.jWt = w + MN; a.scratch = w + 2 * MN;
+  a.C0 = C0; a.ktt = ktt; a.m = m; a.P = P; a.diagonal = diagonal ? 1 : 0; a.mu = mu; a.var = var;
+  spatial_cond_prep_kernel<<<(int)((MN + 255) / 256 < 1024 ? (MN + 255) / 256 : 1024), 256, 0, st>>>(W, w, w + MN, M, N, jitter);
+  cudaError_t e = cudaFuncSetAttribute(kron_spatial_cond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BYTES);
+  if (e != cudaSuccess) return cuda_status(e, "spatial conditional: cudaFuncSetAttribute");
+  const int grid = (int)(T < dv.sms ? T : dv.sms);
+  kron_spatial_cond_kernel<<<grid, NTH, SM_BYTES, st>>>(a);
+  return cuda_status(cudaGetLastError(), "spatial conditional launch");
 }
 
 int physs_rts_smooth_kron_f64(void* stream, int64_t T, int32_t Ns, int32_t ds, const double* At, const double* Qt,

@@ -377,3 +377,31 @@ def test_oracle_separable_prior_matches_reference(path):
     for fs in (False, True):
         ms, Ps = ofilters.smoother_sequential(prior, g["t"], mf, Pf, full_state=fs, jitter=jit)
         assert rel(ms, g["seq_ms_full%d" % fs]) < 1e-9 and rel(Ps, g["seq_Ps_full%d" % fs]) < 1e-9
+
+
+# ---- spatial conditional after the smoother (row f3): tests/golden/make_golden_spatial.py
+def _spatial_files():
+    return sorted(glob.glob(os.path.join(GOLD, "spatial_cond_*.npz")))
+
+
+def test_spatial_golden_files_present():
+    assert len(_spatial_files()) == 3
+
+
+@pytest.mark.parametrize("path", _spatial_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_oracle_spatial_conditional_matches_reference(path):
+    """oracle/dense_gp.py:spatial_conditional and the product's host-side weights (W, C0) against the reference's own
+    gaussian_spatial_conditional_cholesky vmapped over time (marginals.py:82-113)."""
+    from oracle import dense_gp
+    from physs_gp_b200 import spatial
+    g = np.load(path)
+    jit = float(g["jitter"])
+    mu, var = dense_gp.spatial_conditional(g["Kzz"], g["Ksz"], g["Kss"], g["Ktt"], g["pred_mean"], g["pred_var"], jit)
+    assert rel(mu, g["mu"]) < 1e-12 and rel(var, g["var"]) < 1e-12
+    # the closed form the kernel evaluates: var_t = ktt_t C0 + W (P_t + jitter I) W^T
+    W, C0 = spatial.conditional_weights(g["Kzz"], g["Ksz"], g["Kss"], jit)
+    M = W.shape[1]
+    for t in range(g["pred_mean"].shape[0]):
+        v = g["Ktt"][t] * C0 + W @ (g["pred_var"][t] + jit * np.eye(M)) @ W.T
+        assert rel(v, g["var"][t, 0]) < 1e-11
+        assert rel(W @ g["pred_mean"][t], g["mu"][t]) < 1e-12

@@ -1,0 +1,91 @@
+"""-m gpu: the spatial conditional after the smoother (`physs_spatial_conditional_f64`) through the host
+mirror `physs_gp_b200.spatial` against vectors produced by the reference's own `gaussian_spatial_conditional_cholesky`
+(tests/golden/make_golden_spatial.py), against the numpy oracle at config-2 size, and end to end behind the smoother."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-9
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "spatial_cond_*.npz"))),
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_cuda_spatial_conditional_matches_reference_vectors(cuda_device, path):
+    from physs_gp_b200 import spatial
+    g = np.load(path)
+    jit = float(g["jitter"])
+    Ktt = g["Ktt"] if np.ptp(g["Ktt"]) > 0 else float(g["Ktt"][0])
+    mu, var = spatial.spatial_conditional_block(g["Kzz"], g["Ksz"], g["Kss"], Ktt, g["pred_mean"], g["pred_var"],
+                                                jitter=jit)
+    assert tuple(mu.shape) == g["mu"].shape and tuple(var.shape) == g["var"].shape
+    assert rel(mu, g["mu"]) < TOL and rel(var, g["var"]) < TOL
+    v = var.cpu().numpy()
+    assert np.abs(v - np.swapaxes(v, -1, -2)).max() < 1e-13 * np.abs(v).max()    # mirrored lower-triangle product
+    mu_d, var_d = spatial.spatial_conditional_block(g["Kzz"], g["Ksz"], g["Kss"], Ktt, g["pred_mean"], g["pred_var"],
+                                                    diagonal=True, jitter=jit)
+    assert rel(mu_d, g["mu"]) < TOL
+    assert rel(var_d[..., 0], np.diagonal(g["var"][:, 0], axis1=-2, axis2=-1)) < TOL
+
+
+def _gram(X1, X2, ls, var):
+    r = np.sqrt(((X1[:, None, :] - X2[None, :, :]) ** 2).sum(-1))
+    a = np.sqrt(3.0) * r / ls
+    return var * (1.0 + a) * np.exp(-a)
+
+
+@pytest.mark.parametrize("M,N,T", [(200, 200, 300), (200, 333, 5), (37, 1, 3), (1, 5, 2), (208, 64, 150)])
+def test_cuda_spatial_conditional_matches_oracle(cuda_device, M, N, T):
+    """config-2 size (M = 200 inducing points), more steps than SMs (persistent loop), ragged tile edges."""
+    from oracle import dense_gp
+    from physs_gp_b200 import spatial
+    rng = np.random.default_rng(M * 1000 + N)
+    X, XS = rng.uniform(size=[M, 2]), rng.uniform(size=[N, 2])
+    Kzz, Ksz, Kss = _gram(X, X, 0.3, 1.1), _gram(XS, X, 0.3, 1.1), _gram(XS, XS, 0.3, 1.1)
+    pm = rng.normal(size=[T, M, 1])
+    B = rng.normal(size=[T, M, M]) * 0.1
+    pv = 0.2 * Kzz[None] + B @ np.swapaxes(B, 1, 2) / M + 0.01 * np.eye(M)
+    Ktt = 0.8 + 0.2 * rng.uniform(size=T)
+    jit = 1e-6
+    mu_o, var_o = dense_gp.spatial_conditional(Kzz, Ksz, Kss, Ktt, pm, pv, jit)
+    mu, var = spatial.spatial_conditional_block(Kzz, Ksz, Kss, Ktt, pm, pv, jitter=jit)
+    assert rel(mu, mu_o) < TOL and rel(var, var_o) < TOL
+    _, var_d = spatial.spatial_conditional_block(Kzz, Ksz, Kss, Ktt, pm, pv, diagonal=True, jitter=jit)
+    assert rel(var_d[..., 0], np.diagonal(var_o[:, 0], axis1=-2, axis2=-1)) < TOL
+
+
+def test_spatial_prediction_behind_the_smoother(cuda_device, monkeypatch):
+    """End to end: separable prior -> filter + smoother (f only) -> spatial conditional at new points, against the
+    numpy oracle's filter / smoother + dense conditional; at the training points themselves the conditional returns
+    the smoothed marginals."""
+    from oracle import dense_gp, filters as ofilters, sde as osde
+    from physs_gp_b200 import data, kernels as K, likelihood, models, sdes, settings, spatial
+    monkeypatch.setattr(settings, "jitter", 1e-6)
+    rng = np.random.default_rng(7)
+    Ns, T = 24, 40
+    X = rng.uniform(size=[Ns, 2])
+    XS = np.vstack([X[:5], rng.uniform(size=[9, 2])])
+    kern = lambda A, B: _gram(A, B, 0.4, 1.0)
+    Ks = kern(X, X)
+    t = np.cumsum(rng.uniform(0.05, 0.15, T))
+    Y = rng.normal(size=[T, 1, Ns])
+    Y[rng.uniform(size=Y.shape) < 0.1] = np.nan
+    prior = sdes.LTI_SDE(sdes.Independent([K.SpatioTemporalSeperableKernel(K.Matern32(0.6, 0.9), Ks)]))
+    model = models.SDE_GP(data.TemporalData(t, Y, X), prior, likelihood.Gaussian(0.05))
+    mu, var = spatial.spatial_conditional(model, XS, kern, diagonal=False)
+    oprior = osde.LTI_SDE([osde.SpaceTimeSeparable(osde.Matern32(0.6, 0.9), Ks)])
+    R = np.tile(0.05 * np.eye(Ns), [T, 1, 1])
+    _, mf, Pf, _ = ofilters.filter_sequential(oprior, t, Y[:, 0, :], R, 1e-6)
+    ms, Ps = ofilters.smoother_sequential(oprior, t, mf, Pf, full_state=False, jitter=1e-6)
+    mu_o, var_o = dense_gp.spatial_conditional(Ks, kern(XS, X), kern(XS, XS), np.full(T, 0.9), ms, Ps, 1e-6)
+    assert rel(mu, mu_o) < 1e-8 and rel(var, var_o) < 1e-8
+    assert np.abs(mu.cpu().numpy()[:, :5, 0] - ms[:, :5, 0]).max() < 1e-4     # jittered Kzz: not exact
