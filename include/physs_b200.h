@@ -159,18 +159,23 @@ int physs_kf_filter_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_
  * when observe_data != 0 (:417-421).  lml_k is the term of the LAST update of the step, as in the reference.
  * The smoother of this model is physs_rts_smooth_f64 on (mf, Pf) (rts_smoother.py:108-150).
  *
- * Residual table (HOST pointers, read during the call; pc = 1 or 2 outputs, n_terms <= 8):
+ * Residual table (HOST pointers, read during the call; pc = 1 or 2 outputs -- up to 3 with three latents --, n_terms <= 12):
  *     g_p(x, k) = sum_j res_w[p, j] x[j] + sum_{q : term_out[q] = p} term_coef[q] * phi_{term_kind[q]}(x[term_idx[q]])
  *                 + forcing[p, k]
- *   phi: PHYSS_RES_SIN / _COS / _SQUARE / _CUBE.  forcing [pc, T] (DEVICE, shared by the batch) or NULL.
+ *   phi: PHYSS_RES_SIN / _COS / _SQUARE / _CUBE, or the bilinear PHYSS_RES_PROD: term_coef[q] x[i] x[j] with
+ *   term_idx[q] = i | (j << 8) (the x y couplings of LotkaVolterra / LorenzSystem, transforms/pdes.py:818-1090).
+ *   forcing [pc, T] (DEVICE, shared by the batch) or NULL.
  *   y_pseudo [pc] (HOST): the pseudo observation, NaN = output not collocated (PDE.psuedo_observations).
  *   boundary [B, T, m] in the step layout (DEVICE, NaN = no boundary observation at that step) or NULL.
- * Shapes supported: 2 <= d <= 4 with one Matern block (DISC_MATERN, nblk = 1) or DISC_GIVEN; m = 1, or identity H
- * with m = d.  Everything else as physs_kf_filter_f64. */
+ * Shapes supported: one latent, 2 <= d <= 4 with one Matern block (DISC_MATERN, nblk = 1) or DISC_GIVEN, m = 1 or
+ * identity H with m = d; systems of ODEs over 2 / 3 independent latents of state dim 2 (d = 4 / 6: DISC_MATERN with
+ * nblk = d / 2 Matern-3/2 blocks, or DISC_GIVEN with dense transitions), one observation per latent (m = d / 2, any H) or
+ * identity H with m = d.  Everything else as physs_kf_filter_f64. */
 #define PHYSS_RES_SIN 0
 #define PHYSS_RES_COS 1
 #define PHYSS_RES_SQUARE 2
 #define PHYSS_RES_CUBE 3
+#define PHYSS_RES_PROD 4   /* bilinear: coef * x[i] * x[j], term_idx = i | (j << 8) */
 int physs_kf_filter_colloc_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
                                int32_t d, int32_t m,
                                int32_t disc_mode, int32_t nblk,

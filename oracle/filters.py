@@ -76,9 +76,11 @@ class PointResidual:
     with its Jacobian dg/dx = w + sum_q coef_q phi_q'(x[idx_q]) e_idx_q -- what `PDE.forward_g` / `PDE.H_jac`
     (transforms/pdes.py:236-245) evaluate with jax.jacfwd for the point-wise residuals the reference ships
     (Pendulum1D :482-528, DampedPendulum1D :530-597, SimpleODE :424-480, Allen-Cahn's u^3 - u :700-811)."""
-    KINDS = {"sin": 0, "cos": 1, "square": 2, "cube": 3}
+    KINDS = {"sin": 0, "cos": 1, "square": 2, "cube": 3, "prod": 4}
 
     def __init__(self, w, terms=(), forcing=None):
+        """terms: (kind, state index, coefficient); kind "prod" is the bilinear coef * x[i] * x[j] of the reference's
+        ODE systems (LotkaVolterra, LorenzSystem: transforms/pdes.py:818-1008) with the index i | (j << 8)."""
         self.w = np.asarray(w, float)
         self.terms = [(k, int(i), float(c)) for k, i, c in terms]
         self.forcing = None if forcing is None else np.asarray(forcing, float)
@@ -87,6 +89,9 @@ class PointResidual:
         x = np.ravel(x)
         v = float(self.w @ x)
         for kind, i, c in self.terms:
+            if kind == "prod":
+                v += c * x[i & 255] * x[i >> 8]
+                continue
             v += c * {"sin": np.sin, "cos": np.cos, "square": lambda z: z * z, "cube": lambda z: z ** 3}[kind](x[i])
         return v + (0.0 if self.forcing is None else self.forcing[k])
 
@@ -94,6 +99,10 @@ class PointResidual:
         x = np.ravel(x)
         J = self.w.copy()
         for kind, i, c in self.terms:
+            if kind == "prod":
+                J[i & 255] += c * x[i >> 8]
+                J[i >> 8] += c * x[i & 255]
+                continue
             J[i] += c * {"sin": np.cos, "cos": lambda z: -np.sin(z), "square": lambda z: 2 * z,
                          "cube": lambda z: 3 * z * z}[kind](x[i])
         return J[None, :]

@@ -1,4 +1,5 @@
-// physs_colloc.cu -- collocation (EKF) Kalman filter step, one thread per series, state dim d <= 4.
+// physs_colloc.cu -- collocation (EKF) Kalman filter step, one thread per series: one latent with d <= 4, or systems of
+// ODEs over 2 / 3 independent Matern-3/2 latents (d = 4 / 6: LotkaVolterra, LorenzSystem, transforms/pdes.py:818-1090).
 //
 // Reference: kf_predict_step(PDE, 'sequential'), computation/filters/kalman_filter.py:340-427, inside
 // filter('sequential') (:439-485).  Per step:
@@ -17,25 +18,26 @@
 
 namespace physs {
 
-constexpr int kMaxTerms = 8;
+constexpr int kMaxTerms = 12;
+constexpr int kMaxPc = 3, kMaxD = 8;
 
 struct CollocArgs {
   int pc;                         // collocation outputs (PC template value)
-  double w[2][4];                 // linear part  [pc][d]
+  double w[kMaxPc][kMaxD];        // linear part  [pc][d]
   int n_terms;
   int t_out[kMaxTerms], t_kind[kMaxTerms], t_idx[kMaxTerms];
   double t_coef[kMaxTerms];
   const double* forcing;          // [pc, T] device, or NULL
-  double y_pseudo[2];             // 0, or NaN = this output is not collocated
+  double y_pseudo[kMaxPc];        // 0, or NaN = this output is not collocated
   const double* boundary;         // step layout [.., M] device, or NULL
   int observe_data;
 };
 
-template <int D>
+template <int D, int PC>
 __device__ __forceinline__ void eval_residual(const CollocArgs& c, const double (&m)[D], int64_t k, int64_t T,
-                                              double (&f)[2], double (&Hj)[2][D]) {
+                                              double (&f)[PC], double (&Hj)[PC][D]) {
 #pragma unroll
-  for (int p = 0; p < 2; ++p) {
+  for (int p = 0; p < PC; ++p) {
     double acc = (c.forcing && p < c.pc) ? c.forcing[p * T + k] : 0.0;
 #pragma unroll
     for (int j = 0; j < D; ++j) {
@@ -45,27 +47,33 @@ __device__ __forceinline__ void eval_residual(const CollocArgs& c, const double 
     f[p] = acc;
   }
   for (int q = 0; q < c.n_terms; ++q) {                      // uniform over the grid
-    const int idx = c.t_idx[q], kind = c.t_kind[q], out = c.t_out[q];
-    double x = 0.0;
+    const int idx = c.t_idx[q] & 255, idx2 = c.t_idx[q] >> 8, kind = c.t_kind[q], out = c.t_out[q];
+    double x = 0.0, x2 = 0.0;
 #pragma unroll
-    for (int j = 0; j < D; ++j) x = (idx == j) ? m[j] : x;   // no dynamic register indexing
-    double val, der;
+    for (int j = 0; j < D; ++j) {                            // no dynamic register indexing
+      x = (idx == j) ? m[j] : x;
+      x2 = (idx2 == j) ? m[j] : x2;
+    }
+    double val, der, der2 = 0.0;
     if (kind == PHYSS_RES_SIN) { val = sin(x); der = cos(x); }
     else if (kind == PHYSS_RES_COS) { val = cos(x); der = -sin(x); }
     else if (kind == PHYSS_RES_SQUARE) { val = x * x; der = 2.0 * x; }
+    else if (kind == PHYSS_RES_PROD) { val = x * x2; der = x2; der2 = x; }
     else { val = x * x * x; der = 3.0 * x * x; }
     const double cf = c.t_coef[q];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < PC; ++p) {
       if (out == p) f[p] = fma(cf, val, f[p]);
 #pragma unroll
-      for (int j = 0; j < D; ++j)
+      for (int j = 0; j < D; ++j) {
         if (out == p && idx == j) Hj[p][j] = fma(cf, der, Hj[p][j]);
+        if (kind == PHYSS_RES_PROD && out == p && idx2 == j) Hj[p][j] = fma(cf, der2, Hj[p][j]);
+      }
     }
   }
 }
 
-template <int D, int S, int M, bool HID, bool GIVEN>
+template <int D, int S, int M, int PC, bool HID, bool GIVEN>
 __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_colloc_kernel(const SeqFilterArgs p,
                                                                                  const CollocArgs c) {
   __shared__ __align__(16) double tiles[SeqBlock<D>::WARPS][RowTile<D * D>::SIZE];
@@ -125,8 +133,8 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_colloc_kernel
       kf_predict_stationary<D, S>(A, Pinf, m, P);
     }
     // residual and its Jacobian at the predicted mean, BEFORE the boundary update (kalman_filter.py:378-379)
-    double f[2], Hj[2][D];
-    eval_residual<D>(c, m, k, T, f, Hj);
+    double f[PC], Hj[PC][D];
+    eval_residual<D, PC>(c, m, k, T, f, Hj);
     double det = 1.0, mahal = 0.0;
     int nobs = 0;
     if (Bp) {                                                  // uniform
@@ -140,9 +148,14 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_colloc_kernel
       kf_update<D, M, HID>(m, P, H, R0, yb, p.jitter, det, mahal, nobs);
     }
     {
-      double yp[2] = {c.y_pseudo[0], c.y_pseudo[1]};
-      double R0[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-      kf_update<D, 2, false>(m, P, Hj, R0, yp, p.jitter, det, mahal, nobs, f);
+      double yp[PC], R0[PC][PC];
+#pragma unroll
+      for (int a = 0; a < PC; ++a) {
+        yp[a] = c.y_pseudo[a];
+#pragma unroll
+        for (int cc = 0; cc < PC; ++cc) R0[a][cc] = 0.0;
+      }
+      kf_update<D, PC, false>(m, P, Hj, R0, yp, p.jitter, det, mahal, nobs, f);
     }
     if (c.observe_data) kf_update<D, M, HID>(m, P, H, R, y, p.jitter, det, mahal, nobs);
     acc.add(det, mahal, nobs);
@@ -158,14 +171,16 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_colloc_kernel
   if (active) p.lml[b] = acc.value();
 }
 
-template <int D, int S, bool GIVEN>
+// NB = number of latents: systems observe one output per latent and carry 3 residuals for 3 latents
+template <int D, int S, int NB, bool GIVEN>
 static int colloc_launch(cudaStream_t st, const SeqFilterArgs& a, const CollocArgs& c, int m, bool hid) {
   const int64_t n = (a.B + 31) / 32 * 32;
   const int block = pick_block(n) < SeqBlock<D>::THREADS ? pick_block(n) : SeqBlock<D>::THREADS;
   const unsigned grid = (unsigned)((n + block - 1) / block);
-  if (hid && m == D) seq_filter_colloc_kernel<D, S, D, true, GIVEN><<<grid, block, 0, st>>>(a, c);
-  else if (m == 1) seq_filter_colloc_kernel<D, S, 1, false, GIVEN><<<grid, block, 0, st>>>(a, c);
-  else return set_error(PHYSS_ERR_UNSUPPORTED, "collocation filter: observation dim 1 (or identity H with m == d)");
+  constexpr int PC = NB == 3 ? 3 : 2;
+  if (hid && m == D) seq_filter_colloc_kernel<D, S, D, PC, true, GIVEN><<<grid, block, 0, st>>>(a, c);
+  else if (m == NB) seq_filter_colloc_kernel<D, S, NB, PC, false, GIVEN><<<grid, block, 0, st>>>(a, c);
+  else return set_error(PHYSS_ERR_UNSUPPORTED, "collocation filter: one observation per latent (or identity H with m == d)");
   return cuda_status(cudaGetLastError(), "seq_filter_colloc_kernel launch");
 }
 
@@ -173,33 +188,46 @@ int colloc_filter(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h
                   int pc, const double* res_w, int n_terms, const int32_t* t_out, const int32_t* t_kind,
                   const int32_t* t_idx, const double* t_coef, const double* forcing, const double* y_pseudo,
                   const double* boundary, int observe_data) {
-  if (d < 2 || d > 4) return set_error(PHYSS_ERR_UNSUPPORTED, "collocation filter: state dim 2..4");
-  if (pc < 1 || pc > 2 || n_terms < 0 || n_terms > kMaxTerms || !res_w || !y_pseudo)
-    return set_error(PHYSS_ERR_BAD_ARG, "collocation filter: 1..2 outputs, at most 8 non-linear terms");
   const bool given = disc_mode == PHYSS_DISC_GIVEN;
-  if (!given && nblk != 1) return set_error(PHYSS_ERR_UNSUPPORTED, "collocation filter: one Matern block (or DISC_GIVEN)");
+  // shapes: one latent (d = 2..4, given: one dense block), or -- Matern-3/2 latents only -- 2 / 3 latents of state dim 2
+  int s = 0;
+  if (given) s = (d >= 2 && d <= 4) || d == 6 ? d : 0;
+  else if (d >= 2 && d <= 4 && nblk == 1) s = d;
+  else if ((d == 4 || d == 6) && nblk == d / 2) s = 2;
+  if (!s)
+    return set_error(PHYSS_ERR_UNSUPPORTED, "collocation filter: one block with d = 2..4, or nblk = d / 2 blocks of size 2 with d = 4, 6");
+  const int pcmax = d == 6 ? 3 : 2;
+  if (pc < 1 || pc > pcmax || n_terms < 0 || n_terms > kMaxTerms || !res_w || !y_pseudo)
+    return set_error(PHYSS_ERR_BAD_ARG, "collocation filter: 1..2 outputs (3 for three latents), at most 12 non-linear terms");
   CollocArgs c{};
   c.pc = pc;
-  for (int p = 0; p < 2; ++p) {
-    for (int j = 0; j < 4; ++j) c.w[p][j] = (p < pc && j < d) ? res_w[p * d + j] : 0.0;
-    // an absent second output is a masked pseudo-observation: H row 0, y = NaN  ->  identity update
+  for (int p = 0; p < kMaxPc; ++p) {
+    for (int j = 0; j < kMaxD; ++j) c.w[p][j] = (p < pc && j < d) ? res_w[p * d + j] : 0.0;
+    // an absent output is a masked pseudo-observation: H row 0, y = NaN  ->  identity update
     c.y_pseudo[p] = (p < pc) ? y_pseudo[p] : nan("");
   }
   c.n_terms = n_terms;
   for (int q = 0; q < n_terms; ++q) {
-    if (t_out[q] < 0 || t_out[q] >= pc || t_idx[q] < 0 || t_idx[q] >= d || t_kind[q] < 0 || t_kind[q] > PHYSS_RES_CUBE)
+    const int i1 = t_idx[q] & 255, i2 = t_idx[q] >> 8;
+    const bool prod = t_kind[q] == PHYSS_RES_PROD;
+    if (t_out[q] < 0 || t_out[q] >= pc || t_idx[q] < 0 || i1 >= d || (prod ? i2 >= d : i2 != 0) || t_kind[q] < 0 ||
+        t_kind[q] > PHYSS_RES_PROD)
       return set_error(PHYSS_ERR_BAD_ARG, "collocation filter: bad residual term");
     c.t_out[q] = t_out[q]; c.t_kind[q] = t_kind[q]; c.t_idx[q] = t_idx[q]; c.t_coef[q] = t_coef[q];
   }
   c.forcing = forcing; c.boundary = boundary; c.observe_data = observe_data;
-  if (given) {
-    if (d == 2) return colloc_launch<2, 2, true>(st, a, c, m, hid);
-    if (d == 3) return colloc_launch<3, 3, true>(st, a, c, m, hid);
-    return colloc_launch<4, 4, true>(st, a, c, m, hid);
+  if (given) {                // supplied transitions are dense: one d x d block whatever the number of latents
+    if (d == 6) return colloc_launch<6, 6, 3, true>(st, a, c, m, hid);
+    if (d == 4 && m == 2) return colloc_launch<4, 4, 2, true>(st, a, c, m, hid);
+    if (d == 2) return colloc_launch<2, 2, 1, true>(st, a, c, m, hid);
+    if (d == 3) return colloc_launch<3, 3, 1, true>(st, a, c, m, hid);
+    return colloc_launch<4, 4, 1, true>(st, a, c, m, hid);
   }
-  if (d == 2) return colloc_launch<2, 2, false>(st, a, c, m, hid);
-  if (d == 3) return colloc_launch<3, 3, false>(st, a, c, m, hid);
-  return colloc_launch<4, 4, false>(st, a, c, m, hid);
+  if (s == 2 && d == 4) return colloc_launch<4, 2, 2, false>(st, a, c, m, hid);
+  if (s == 2 && d == 6) return colloc_launch<6, 2, 3, false>(st, a, c, m, hid);
+  if (d == 2) return colloc_launch<2, 2, 1, false>(st, a, c, m, hid);
+  if (d == 3) return colloc_launch<3, 3, 1, false>(st, a, c, m, hid);
+  return colloc_launch<4, 4, 1, false>(st, a, c, m, hid);
 }
 
 }  // namespace physs

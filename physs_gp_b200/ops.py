@@ -218,7 +218,7 @@ def kf_filter(dt, Y, R, H, m0, P0, disc, jitter=None, want_lml_k=False, out=None
     return lml, mf, Pf
 
 
-RES_KINDS = {"sin": 0, "cos": 1, "square": 2, "cube": 3}
+RES_KINDS = {"sin": 0, "cos": 1, "square": 2, "cube": 3, "prod": 4}
 
 
 def kf_filter_colloc(dt, Y, R, H, m0, P0, disc, res_w, terms=(), forcing=None, y_pseudo=None, boundary=None,
@@ -226,7 +226,8 @@ def kf_filter_colloc(dt, Y, R, H, m0, P0, disc, res_w, terms=(), forcing=None, y
     """Batched collocation (EKF) filter: kf_predict_step(PDE, 'sequential'), kalman_filter.py:340-427, per series
     (`physs_kf_filter_colloc_f64`).  Arguments as `kf_filter` plus the residual table
         g_p(x, k) = res_w[p] . x + sum_q coef_q phi_q(x[idx_q]) + forcing[p, k]
-    res_w [pc, d] (array-like, host); terms: iterable of (output p, kind in RES_KINDS, state index, coefficient);
+    res_w [pc, d] (array-like, host); terms: iterable of (output p, kind in RES_KINDS, state index, coefficient) --
+    kind "prod" is the bilinear coef * x[i] * x[j] with the index i | (j << 8), or the pair (i, j);
     forcing [pc, T] device tensor or None; y_pseudo [pc] (0 / NaN, default zeros); boundary [B, T, m] device tensor
     (NaN = none) or None.  Returns (lml, mf, Pf[, lml_k])."""
     import ctypes
@@ -240,7 +241,7 @@ def kf_filter_colloc(dt, Y, R, H, m0, P0, disc, res_w, terms=(), forcing=None, y
     terms = list(terms)
     t_out = np.array([t[0] for t in terms], np.int32)
     t_kind = np.array([RES_KINDS[t[1]] if isinstance(t[1], str) else int(t[1]) for t in terms], np.int32)
-    t_idx = np.array([t[2] for t in terms], np.int32)
+    t_idx = np.array([t[2][0] | (t[2][1] << 8) if isinstance(t[2], (tuple, list)) else t[2] for t in terms], np.int32)
     t_coef = np.array([t[3] for t in terms], np.float64)
     yps = np.zeros(pc) if y_pseudo is None else np.ascontiguousarray(np.asarray(y_pseudo, np.float64).reshape(pc))
     keep = []

@@ -134,13 +134,16 @@ _KINDS = {1: Matern12, 2: Matern32, 3: Matern52, 4: Matern72}
 class PointResidual:
     """One point-wise collocation residual on the derivative-augmented state x:
         g(x, t_k) = w . x + sum_q coef_q * phi_q(x[idx_q]) + forcing[k],   phi in {'sin', 'cos', 'square', 'cube'}
+    plus bilinear terms ('prod', (i, j), coef) = coef * x[i] * x[j]
     -- the form of the residuals the reference ships as `PDE.forward_g` (transforms/pdes.py: Pendulum1D :482-528,
-    DampedPendulum1D :530-597, SimpleODE :424-480, the u^3 - u reaction of Allen-Cahn :700-811).  Its Jacobian,
+    DampedPendulum1D :530-597, SimpleODE :424-480, the u^3 - u reaction of Allen-Cahn :700-811, and with the
+    bilinear terms the components of LotkaVolterra :912-1090 and LorenzSystem :818-910).  Its Jacobian,
     which the reference takes with jax.jacfwd (`PDE.jac`, :236-242), is evaluated on chip."""
 
     def __init__(self, w, terms=(), forcing=None):
         self.w = np.asarray(w, np.float64)
-        self.terms = [(str(k), int(i), float(c)) for k, i, c in terms]
+        self.terms = [(str(k), (int(i[0]) | (int(i[1]) << 8)) if isinstance(i, (tuple, list)) else int(i), float(c))
+                      for k, i, c in terms]
         self.forcing = None if forcing is None else np.asarray(forcing, np.float64)
 
 
@@ -150,15 +153,16 @@ class PDE:
     kalman_filter.py:340-427).  `filter_type='b200'` runs it with `physs_kf_filter_colloc_f64`; the smoother is the
     parent's (rts_smoother.py:108-150).
 
-    residuals: 1 or 2 PointResidual; psuedo_observations: one value per residual, 0 (collocate) or NaN (off);
+    residuals: 1 or 2 PointResidual (up to 3 over three latents: systems of ODEs such as `LorenzSystem`, two latents for
+    `LotkaVolterra` -- independent Matern-3/2 latents, one observed output each); psuedo_observations: one value per residual, 0 (collocate) or NaN (off);
     boundary_conditions: [Nt, m] array with NaN where there is no boundary observation, or None; observe_data as in
     the reference (PDE.observe_data, default False there; True here only when asked)."""
 
     def __init__(self, parent, residuals, psuedo_observations=None, boundary_conditions=None, observe_data=False):
         self.parent = parent
         self.residuals = list(residuals)
-        if not 1 <= len(self.residuals) <= 2:
-            raise ValueError("1 or 2 collocation residuals per time step")
+        if not 1 <= len(self.residuals) <= 3:
+            raise ValueError("1 to 3 collocation residuals per time step")
         self._pseudo = (np.zeros(len(self.residuals)) if psuedo_observations is None
                         else np.asarray(psuedo_observations, np.float64).reshape(len(self.residuals)))
         self.boundary_conditions = boundary_conditions

@@ -155,6 +155,74 @@ def main():
             fn = os.path.join(HERE, "ekf_%s_jit%s.npz" % (name, "1e-5" if jitter else "0"))
             onp.savez_compressed(fn, **out)
             written.append(fn)
+    # =============================================== systems of ODEs over several latents: the reference's own
+    # LotkaVolterra components (transforms/pdes.py:912-1008, stacked as LotkaVolterra.forward does, :1059-1072) and the
+    # three Lorenz components (:818-910) over 2 / 3 independent Matern-3/2 latents (state x, xt, y, yt[, z, zt]), one
+    # observed output per latent.  Bilinear terms are stored as term_idx = i | (j << 8), kind "prod".
+    lv_names = ["_LotkaVolterraSystemX.forward", "_LotkaVolterraSystemX._dfdt", "_LotkaVolterraSystemY.forward",
+                "_LotkaVolterraSystemY._dfdt"]
+    lv = mg.extract("transforms/pdes.py", lv_names, ns)
+    lz = mg.extract("transforms/pdes.py", ["_LorenzSystemX.forward", "_LorenzSystemY.forward", "_LorenzSystemZ.forward"], ns)
+    al, be, de, ga = 1.1, 0.4, 0.1, 0.4
+    sg, rho, bt = 10.0, 28.0, 8.0 / 3.0
+    par = lambda v: types.SimpleNamespace(value=v)
+    lvx = types.SimpleNamespace(alpha_param=par(al), beta_param=par(be))
+    lvx._dfdt = lambda f: lv["_LotkaVolterraSystemX._dfdt"](lvx, f)
+    lvy = types.SimpleNamespace(delta_param=par(de), gamma_param=par(ga))
+    lvy._dfdt = lambda f: lv["_LotkaVolterraSystemY._dfdt"](lvy, f)
+    lzs = types.SimpleNamespace(sigma_param=par(sg), rho_param=par(rho), beta_param=par(bt))
+    enc = lambda i, j: i | (j << 8)
+    sys_cases = {
+        "lotka_volterra": ([("m32", 1.5, 4.0), ("m32", 1.2, 3.0)],
+                           lambda x, t: jnp.hstack([onp.squeeze(lv["_LotkaVolterraSystemX.forward"](lvx, x)),
+                                                    onp.squeeze(lv["_LotkaVolterraSystemY.forward"](lvy, x))]),
+                           [dict(w=[-al, 1.0, 0.0, 0.0], terms=[("prod", enc(0, 2), be)]),
+                            dict(w=[0.0, 0.0, ga, 1.0], terms=[("prod", enc(0, 2), -de)])],
+                           True, True, [0.0, 0.0]),
+        "lorenz": ([("m32", 0.3, 60.0), ("m32", 0.3, 80.0), ("m32", 0.3, 90.0)],
+                   lambda x, t: jnp.hstack([onp.squeeze(lz["_LorenzSystemX.forward"](lzs, x)),
+                                            onp.squeeze(lz["_LorenzSystemY.forward"](lzs, x)),
+                                            onp.squeeze(lz["_LorenzSystemZ.forward"](lzs, x))]),
+                   [dict(w=[sg, 1.0, -sg, 0.0, 0.0, 0.0], terms=[]),
+                    dict(w=[-rho, 0.0, 1.0, 1.0, 0.0, 0.0], terms=[("prod", enc(0, 4), 1.0)]),
+                    dict(w=[0.0, 0.0, 0.0, 0.0, bt, 1.0], terms=[("prod", enc(0, 2), -1.0)])],
+                   False, True, [0.0, 0.0, 0.0]),
+    }
+    settings.jitter = 1e-5
+    for name, (kerns, g_fn, desc, has_bnd, observe, yp) in sys_cases.items():
+        rng = onp.random.default_rng(sum(map(ord, name)))
+        nl = len(kerns)
+        parent = LTIParent([[Kern(*k)] for k in kerns], False)
+        T = 40
+        t = onp.cumsum(rng.uniform(0.5, 1.5, T) * (0.05 if nl == 2 else 0.004))
+        base = onp.stack([2.0 + onp.sin(1.3 * t + q) for q in range(nl)], 1) if nl == 2 else \
+            onp.stack([1.0 + 3.0 * t, 1.5 + 5.0 * t, 20.0 + 2.0 * t], 1)
+        Y = base + 0.05 * rng.normal(size=(T, nl))
+        Y[rng.uniform(size=Y.shape) < 0.3] = onp.nan
+        R = onp.tile(0.05 ** 2 * onp.eye(nl), [T, 1, 1])
+        bnd = None
+        if has_bnd:
+            bnd = onp.full((T, nl, 1), onp.nan)
+            bnd[0, :, 0] = base[0]
+        model = Model(parent, g_fn, None if bnd is None else A(bnd), observe, yp)
+        data = types.SimpleNamespace(X_time=A(t), X_space=None, Nt=T, Ns=1, P=nl, Y_st=A(Y[:, :, None]))
+        lml, res = kf.filter_loop(data, model, R=A(R), filter_type="sequential")
+        mu, var = rts.smoother_loop(data, model, res, full_state=True, filter_type="sequential")
+        out = {"t": t, "Y": Y, "R": R, "jitter": 1e-5, "observe_data": observe, "y_pseudo": yp,
+               "kernel": onp.array([k[0] for k in kerns]), "hyper": onp.array([k[1:] for k in kerns]), "n_res": len(desc),
+               "lml": float(lml), "mf": onp.asarray(res["m"]), "Pf": onp.asarray(res["P"]),
+               "ms": onp.asarray(mu), "Ps": onp.asarray(var)}
+        for p, dsc in enumerate(desc):
+            out["w%d" % p] = onp.array(dsc["w"])
+            out["term_kind%d" % p] = onp.array([k for k, _, _ in dsc["terms"]], dtype="U8")
+            out["term_idx%d" % p] = onp.array([i for _, i, _ in dsc["terms"]], dtype=int)
+            out["term_coef%d" % p] = onp.array([c for _, _, c in dsc["terms"]], dtype=float)
+            out["forcing%d" % p] = onp.zeros(0)
+        if bnd is not None:
+            out["boundary"] = bnd[:, :, 0]
+        fn = os.path.join(HERE, "ekfsys_%s_jit1e-5.npz" % name)
+        onp.savez_compressed(fn, **out)
+        written.append(fn)
     # =============================================== integrated Wiener prior (a6): the reference's own
     # WienerVelocity.{to_ss, expm, Q} (kernels/wiener.py:90-149) under the reference's sequential filter / smoother
     import scipy.special as ssp

@@ -215,7 +215,7 @@ def test_product_prior_stacking_matches_reference():
 
 # ------------------------------------------------------------------------------- collocation (EKF) filter step
 def _ekf_files():
-    return sorted(glob.glob(os.path.join(GOLD, "ekf_*.npz")))
+    return sorted(glob.glob(os.path.join(GOLD, "ekf_*.npz")) + glob.glob(os.path.join(GOLD, "ekfsys_*.npz")))
 
 
 def ekf_residuals(g):
@@ -229,17 +229,17 @@ def ekf_residuals(g):
 
 
 def test_ekf_golden_files_present():
-    assert len(_ekf_files()) == 5
+    assert len(_ekf_files()) == 7
 
 
-@pytest.mark.parametrize("path", _ekf_files(), ids=[os.path.basename(p)[4:-4] for p in _ekf_files()])
+@pytest.mark.parametrize("path", _ekf_files(), ids=[os.path.basename(p)[:-4] for p in _ekf_files()])
 def test_oracle_collocation_filter_matches_reference(path):
     """oracle.filters.filter_pde_sequential == the reference's kf_predict_step(PDE, 'sequential')
     (kalman_filter.py:340-427) run by tests/golden/make_golden_ekf.py, and the smoother on its output ==
     rts_step_wrapper(PDE) (rts_smoother.py:108-150)."""
     g = np.load(path)
-    ls, var = g["hyper"]
-    prior = osde.LTI_SDE([KIND[str(g["kernel"][0])](float(ls), float(var))])
+    hyper = np.atleast_2d(g["hyper"])               # one row per latent (ekfsys_*: systems of ODEs over 2 / 3 latents)
+    prior = osde.LTI_SDE([KIND[str(k)](float(ls), float(var)) for k, (ls, var) in zip(g["kernel"], hyper)])
     jit = float(g["jitter"])
     bnd = g["boundary"] if "boundary" in g.files else None
     lml, mf, Pf, _ = ofilters.filter_pde_sequential(prior, ekf_residuals(g), g["t"], g["Y"], g["R"], boundary=bnd,

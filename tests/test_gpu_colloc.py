@@ -18,7 +18,7 @@ from tests.test_golden import ekf_residuals
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = 1e-9
-FILES = sorted(glob.glob(os.path.join(GOLD, "ekf_*.npz")))
+FILES = sorted(glob.glob(os.path.join(GOLD, "ekf_*.npz")) + glob.glob(os.path.join(GOLD, "ekfsys_*.npz")))
 
 
 def rel(a, b):
@@ -29,16 +29,16 @@ def rel(a, b):
 def _product_pde(g, oracle_res):
     from physs_gp_b200 import kernels as K
     from physs_gp_b200 import sdes
-    kind = {"m32": K.Matern32, "m52": K.Matern52, "m72": K.Matern72}[str(g["kernel"][0])]
-    ls, var = g["hyper"]
-    parent = sdes.LTI_SDE(sdes.Independent([kind(float(ls), float(var))]))
+    kind = {"m32": K.Matern32, "m52": K.Matern52, "m72": K.Matern72}
+    hyper = np.atleast_2d(g["hyper"])     # one row per latent (ekfsys_*: LotkaVolterra / Lorenz over 2 / 3 latents)
+    parent = sdes.LTI_SDE(sdes.Independent([kind[str(k)](float(ls), float(var)) for k, (ls, var) in zip(g["kernel"], hyper)]))
     res = [sdes.PointResidual(r.w, r.terms, r.forcing) for r in oracle_res]
     bnd = g["boundary"] if "boundary" in g.files else None
     return sdes.PDE(parent, res, psuedo_observations=g["y_pseudo"], boundary_conditions=bnd,
                     observe_data=bool(g["observe_data"]))
 
 
-@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p)[4:-4] for p in FILES])
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p)[:-4] for p in FILES])
 def test_cuda_collocation_filter_matches_reference_vectors(cuda_device, path, monkeypatch):
     from physs_gp_b200 import data, filters, settings
     g = np.load(path)
@@ -46,6 +46,12 @@ def test_cuda_collocation_filter_matches_reference_vectors(cuda_device, path, mo
     prior = _product_pde(g, ekf_residuals(g))
     d = data.TemporalData(g["t"], g["Y"][:, :, None])
     lml, kf = filters.filter_loop(d, prior, R=g["R"])
+    if g["kernel"].size > 1:
+        # systems: the supplied-transition route (dense A_k, Q_k from the host mirror) runs other instantiations
+        monkeypatch.setattr(type(prior), "ss_blocks", lambda self: None)
+        lml_g, kf_g = filters.filter_loop(d, prior, R=g["R"])
+        assert abs(float(lml_g) - float(g["lml"])) <= TOL * abs(float(g["lml"]))
+        assert rel(kf_g['m'], g["mf"]) < TOL and rel(kf_g['P'], g["Pf"]) < TOL
     assert abs(float(lml) - float(g["lml"])) <= TOL * abs(float(g["lml"]))
     assert rel(kf['m'], g["mf"]) < TOL and rel(kf['P'], g["Pf"]) < TOL
     mu, var = filters.smoother_loop(d, prior.parent, kf, full_state=True)
