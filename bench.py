@@ -372,6 +372,38 @@ def run_reference(a):
                     e2e={"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
         print(json.dumps(line), flush=True)
         return
+    if a.workload == "spatial":
+        from oracle import dense_gp
+        M, N = a.state_dim, a.series
+        rng = np.random.default_rng(5)
+        X, XS = rng.uniform(size=[M, 2]), rng.uniform(size=[N, 2])
+
+        def gram(A_, B_):
+            r = np.sqrt(((A_[:, None, :] - B_[None, :, :]) ** 2).sum(-1)) * np.sqrt(3.0) / 0.3
+            return (1.0 + r) * np.exp(-r)
+        Kzz, Ksz, Kss = gram(X, X), gram(XS, X), gram(XS, XS)
+        Ts = 40
+        Bm = rng.normal(size=[Ts, M, 16]) * 0.1
+        P = 0.2 * Kzz[None] + Bm @ np.swapaxes(Bm, 1, 2) + 0.01 * np.eye(M)
+        mm = rng.normal(size=[Ts, M, 1])
+        vals = []
+        for i in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
+            dense_gp.spatial_conditional(Kzz, Ksz, Kss, np.full(Ts, 0.9), mm, P, 1e-6)
+            if i >= a.warmup:
+                vals.append(Ts / (time.perf_counter() - t0))
+        value = float(np.mean(vals))
+        sample = ("%d of %d time steps (oracle/dense_gp.py:spatial_conditional, numpy / LAPACK threading as numpy configures "
+                  "it) -- restatement, not the JAX reference" % (Ts, T))
+        line = dict(base, metric="spatial conditional time-steps/sec (fp64)", value=value, unit="time-steps/s",
+                    ms_per_step=1e3 * T / value, higher_is_better=True, scaling="weak",
+                    config={"workload": "spatial: posterior at M = %d spatial points x %d time steps carried to N = %d new "
+                                        "points, full N x N covariance blocks [CPU arm: %s]" % (M, T, N, sample),
+                            "M": M, "N": N, "T": T},
+                    cpu_baseline={"value": value, "unit": "time-steps/s", "cores": cores, "kind": "port", "sample": sample},
+                    e2e={"value": value, "unit": "time-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return
     n = a.cpu_sample_series or max(cores * 8, 64)
     if d > 4:
         n = max(cores * 2, 16)
