@@ -87,6 +87,24 @@ def gaussian_ell_and_grads(Y, noise, W, q_mu, q_var):
     return ell, dm, dS
 
 
+def spatial_sparsity_gaussian_ell_and_grads(Y, s2, W, c0_diag, jitter, q_mu, q_var):
+    """ELL of a Gaussian likelihood with noise variance s2 at N data locations whose marginals come from the block
+    posterior q(u) = N(q_mu, q_var) at M inducing locations through the spatial conditional
+    (computation/spatial_conditionals.py:30-207 -> marginals.py:82-113):
+        m_x = W q_mu,   v_x = c0_diag + diag(W (q_var + jitter I) W^T),   ELL = sum_obs log N(y | m_x, s2) - v_x / (2 s2)
+    with the gradients w.r.t. (q_mu, q_var) that `jax.grad(partial_ell, (1, 2))` (cvi_nat_grad.py:381-383) produces for
+    the SpatialSparsity posterior.  Y [N] (NaN = missing), W [N, M], c0_diag [N]."""
+    M = q_mu.shape[0]
+    m_x = W @ q_mu
+    v_x = c0_diag + np.einsum("ij,jk,ik->i", W, q_var + jitter * np.eye(M), W)
+    obs = ~np.isnan(Y)
+    r = np.where(obs, np.nan_to_num(Y) - m_x, 0.0)
+    ell = float(np.sum(np.where(obs, -0.5 * (np.log(2 * np.pi * s2) + (r * r + v_x) / s2), 0.0)))
+    dm = W.T @ (r / s2)
+    dS = -0.5 * (W.T * np.where(obs, 1.0 / s2, 0.0)) @ W
+    return ell, dm, dS
+
+
 def log_poisson(y, f, binsize=1.0):
     """general.py:9-11 with likelihood/poisson.py:20-22 (exp link)."""
     lam = np.exp(f) * binsize

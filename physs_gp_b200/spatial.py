@@ -29,28 +29,12 @@ def conditional_weights(Kzz, Ksz, Kss, jitter=None):
     return np.ascontiguousarray(A1.T), Kss - A.T @ A
 
 
-def spatial_conditional_block(Kzz, Ksz, Kss, Ktt, pred_mean, pred_var, diagonal=False, jitter=None, stream=None):
-    """pred_mean [T, M, 1] (or [T, M]), pred_var [T, M, M] (or [T, 1, M, M]) device or host arrays in
-    time-(latent-)space format; Ktt [T], a scalar (stationary temporal kernel: its variance), or None for 1.
-    Returns (mu [T, N, 1], var [T, 1, N, N]) as the reference does (:198-201), or var [T, N, 1] with `diagonal`."""
-    dev = _device()
+def _apply(Wd, C0d, ktt, m, P, jit, diagonal, stream=None):
+    """physs_spatial_conditional_f64 on device tensors: Wd [N, M], C0d [N, N], ktt [T] or None, m [T, M], P [T, M, M]."""
     lib = _lib.load()
-    jit = settings.jitter if jitter is None else jitter
-    W, C0 = conditional_weights(Kzz, Ksz, Kss, jit)
-    N, M = W.shape
-    m = _to_dev(pred_mean, dev).reshape(-1, M).contiguous()
+    dev = Wd.device
+    N, M = Wd.shape
     T = m.shape[0]
-    P = _to_dev(pred_var, dev).reshape(T, M, M).contiguous()
-    ktt = None
-    if Ktt is not None:
-        k = np.asarray(Ktt.detach().cpu().numpy() if isinstance(Ktt, torch.Tensor) else Ktt, np.float64).reshape(-1)
-        if k.size == 1:
-            C0 = C0 * k[0]
-        else:
-            if k.size != T:
-                raise ValueError("Ktt must have one entry per time step")
-            ktt = _to_dev(k, dev)
-    Wd, C0d = _to_dev(W, dev), _to_dev(C0, dev)
     mu = torch.empty((T, N, 1), dtype=torch.float64, device=dev)
     var = torch.empty((T, N, 1) if diagonal else (T, 1, N, N), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
@@ -66,6 +50,29 @@ def spatial_conditional_block(Kzz, Ksz, Kss, Ktt, pred_mean, pred_var, diagonal=
                                                mu.data_ptr(), var.data_ptr())
     _lib.check(st, "physs_spatial_conditional_f64")
     return mu, var
+
+
+def spatial_conditional_block(Kzz, Ksz, Kss, Ktt, pred_mean, pred_var, diagonal=False, jitter=None, stream=None):
+    """pred_mean [T, M, 1] (or [T, M]), pred_var [T, M, M] (or [T, 1, M, M]) device or host arrays in
+    time-(latent-)space format; Ktt [T], a scalar (stationary temporal kernel: its variance), or None for 1.
+    Returns (mu [T, N, 1], var [T, 1, N, N]) as the reference does (:198-201), or var [T, N, 1] with `diagonal`."""
+    dev = _device()
+    jit = settings.jitter if jitter is None else jitter
+    W, C0 = conditional_weights(Kzz, Ksz, Kss, jit)
+    N, M = W.shape
+    m = _to_dev(pred_mean, dev).reshape(-1, M).contiguous()
+    T = m.shape[0]
+    P = _to_dev(pred_var, dev).reshape(T, M, M).contiguous()
+    ktt = None
+    if Ktt is not None:
+        k = np.asarray(Ktt.detach().cpu().numpy() if isinstance(Ktt, torch.Tensor) else Ktt, np.float64).reshape(-1)
+        if k.size == 1:
+            C0 = C0 * k[0]
+        else:
+            if k.size != T:
+                raise ValueError("Ktt must have one entry per time step")
+            ktt = _to_dev(k, dev)
+    return _apply(_to_dev(W, dev), _to_dev(C0, dev), ktt, m, P, jit, diagonal, stream)
 
 
 def spatial_conditional(model, XS_space, spatial_kernel, diagonal=True):
@@ -91,3 +98,78 @@ def _temporal_variance(prior):
     k = getattr(k, "kernel", k)
     k = getattr(k, "k1", k)
     return float(k.variance)
+
+
+# ------------------------------------------------------------------------- SpatialSparsity CVI (Gaussian likelihood)
+class SpatialSparsityVGP:
+    """CVI with `SpatialSparsity` (sparsity/sparsity.py; `natural_gradients(VGP, FullConjugateGaussian, SpatialSparsity)`,
+    natural_gradients/cvi_nat_grad.py:346-410): the sites -- one block per time step -- live at M inducing spatial points
+    Z while the data sit at N spatial points X.  The reference evaluates the ELL on the marginals of f at X, obtained
+    from q at Z with the spatial conditional (elbos/marginals/dispatched_marginal_predictors.py -> spatial_conditional),
+    and takes `jax.grad` of it with respect to the block moments (:381-383).  Here, for a Gaussian likelihood with
+    diagonal noise:
+        m_x = W m_z,   v_x = diag(Ktt C0 + W (S_z + jitter I) W^T)                 (physs_spatial_conditional_f64)
+        ELL_t = sum_i log N(y_i | m_x,i, s2) - v_x,i / (2 s2)                        (observed entries)
+        dELL/dm_z = W^T (y - m_x) / s2,   dELL/dS_z = W^T diag(-1 / (2 s2)) W      (the same kernel with the roles of
+                                                                                    Z and X exchanged)
+    followed by the ordinary block update (physs_cvi_natgrad_big_f64 or physs_cvi_natgrad_step_f64, gradients supplied).
+    Y [T, N] (NaN = missing); approximate_posterior: cvi.FullConjugateGaussian with block_size M and B = 1."""
+
+    def __init__(self, Y, noise_var, approximate_posterior, Kzz, Kxz, Kxx, Ktt=1.0, jitter=None):
+        q = approximate_posterior
+        dev = q.Y_tilde.device
+        self.q = q
+        self.jitter = settings.jitter if jitter is None else jitter
+        W, C0 = conditional_weights(Kzz, Kxz, Kxx, self.jitter)
+        self.N, self.M = W.shape
+        if q.block_size != self.M or q.Y_tilde.shape[0] != 1:
+            raise ValueError("SpatialSparsityVGP: one site block of size M = %d per time step, B = 1" % self.M)
+        self.W = torch.as_tensor(W, device=dev)
+        self.Wt = torch.as_tensor(np.ascontiguousarray(W.T), device=dev)
+        self.C0 = torch.as_tensor(C0 * float(Ktt), device=dev)
+        self.zero_MM = torch.zeros((self.M, self.M), dtype=torch.float64, device=dev)
+        self.Y = torch.as_tensor(np.asarray(Y, np.float64), device=dev).reshape(-1, self.N)
+        self.noise_var = float(noise_var)
+
+    def _ell(self, q_mu, q_var, want_grads):
+        """q_mu [T, M], q_var [T, M, M] -> ELL per step [T] (and the gradients w.r.t. the block moments)."""
+        m_x, v_x = _apply(self.W, self.C0, None, q_mu, q_var, self.jitter, True)
+        m_x, v_x = m_x[..., 0], v_x[..., 0]
+        s2 = self.noise_var
+        obs = ~torch.isnan(self.Y)
+        r = torch.where(obs, self.Y, torch.zeros_like(self.Y)) - m_x
+        ell = torch.where(obs, -0.5 * (np.log(2 * np.pi * s2) + (r * r + v_x) / s2), torch.zeros_like(r)).sum(-1)
+        if not want_grads:
+            return ell
+        dm_x = torch.where(obs, r / s2, torch.zeros_like(r)).contiguous()
+        dS_x = torch.diag_embed(torch.where(obs, torch.full_like(r, -0.5 / s2), torch.zeros_like(r))).contiguous()
+        dm_z, dS_z = _apply(self.Wt, self.zero_MM, None, dm_x, dS_x, 0.0, False)
+        return ell, dm_z[..., 0], dS_z[:, 0]
+
+    def _posterior(self, want_lml=False):
+        out = self.q.surrogate.posterior_blocks(return_lml=want_lml)
+        lml = out[0] if want_lml else None
+        q_mu, q_var = out[-2][0, :, :, 0].contiguous(), out[-1][0, :, 0].contiguous()
+        return lml, q_mu, q_var
+
+    def natural_gradient_update(self, lr, enforce_psd_type=None, prediction_samples=None):
+        if enforce_psd_type is not None:
+            raise NotImplementedError("enforce_psd_type: the Gaussian ELL curvature is already negative semi-definite")
+        from . import cvi
+        q = self.q
+        _, q_mu, q_var = self._posterior()
+        _, dm, dS = self._ell(q_mu, q_var, True)
+        cvi.natgrad_step(q.Y_tilde, q.V_tilde, q_mu[None], q_var[None], None, None, None, lr,
+                         dm=dm[None].contiguous(), dS=dS[None].contiguous(), out=(q.Y_tilde, q.V_tilde))
+
+    def elbo(self):
+        from . import cvi
+        q = self.q
+        lml, q_mu, q_var = self._posterior(want_lml=True)
+        ell = self._ell(q_mu, q_var, False)
+        sur = cvi.GaussianLik(np.eye(q.block_size))
+        ell_s = cvi.expected_log_likelihood(q_mu[None], q_var[None], q.Y_tilde, None, sur, noise=q.V_tilde)
+        return ell.sum(dim=-1) - ell_s.sum(dim=-1) + lml
+
+    def get_objective(self):
+        return -self.elbo()

@@ -89,3 +89,45 @@ def test_spatial_prediction_behind_the_smoother(cuda_device, monkeypatch):
     mu_o, var_o = dense_gp.spatial_conditional(Ks, kern(XS, X), kern(XS, XS), np.full(T, 0.9), ms, Ps, 1e-6)
     assert rel(mu, mu_o) < 1e-8 and rel(var, var_o) < 1e-8
     assert np.abs(mu.cpu().numpy()[:, :5, 0] - ms[:, :5, 0]).max() < 1e-4     # jittered Kzz: not exact
+
+
+@pytest.mark.parametrize("Nz,Nx", [(12, 20), (40, 33)])
+def test_spatial_sparsity_cvi_iterations_match_oracle(cuda_device, monkeypatch, Nz, Nx):
+    """SpatialSparsity CVI (sites at Nz inducing points, data at Nx other points, Gaussian likelihood with missing
+    entries): two natural-gradient iterations and the ELBO against the numpy oracle -- filter / smoother on the
+    separable prior, ELL gradients pulled back through the spatial conditional, block update.  Nz = 12 runs the
+    small-block site kernel, Nz = 40 the large-block one."""
+    from oracle import cvi as ocvi, filters as ofilters, sde as osde
+    from physs_gp_b200 import cvi, kernels as K, sdes, settings, spatial
+    monkeypatch.setattr(settings, "jitter", 1e-5)
+    rng = np.random.default_rng(100 + Nz)
+    T, beta, s2 = 11, 0.6, 0.2
+    Z, X = rng.uniform(size=[Nz, 2]), rng.uniform(size=[Nx, 2])
+    Kzz, Kxz, Kxx = _gram(Z, Z, 0.4, 1.0), _gram(X, Z, 0.4, 1.0), _gram(X, X, 0.4, 1.0)
+    t = np.cumsum(rng.uniform(0.05, 0.15, T))
+    Y = rng.normal(size=[T, Nx])
+    Y[rng.uniform(size=Y.shape) < 0.15] = np.nan
+    kvar = 0.9
+    pprior = sdes.LTI_SDE(sdes.Independent([K.SpatioTemporalSeperableKernel(K.Matern32(0.7, kvar), Kzz)]))
+    oprior = osde.LTI_SDE([osde.SpaceTimeSeparable(osde.Matern32(0.7, kvar), Kzz)])
+    q = cvi.FullConjugateGaussian(t, pprior, Nz, B=1)
+    model = spatial.SpatialSparsityVGP(Y, s2, q, Kzz, Kxz, Kxx, Ktt=kvar)
+    for _ in range(2):
+        model.natural_gradient_update(beta)
+    elbo = model.elbo()
+    torch.cuda.synchronize()
+    W, C0 = spatial.conditional_weights(Kzz, Kxz, Kxx, 1e-5)
+    c0 = kvar * np.diag(C0)
+    Yt = 1e-5 * np.ones((T, Nz)); Vt = np.tile(np.eye(Nz), [T, 1, 1])
+
+    def grads(qm, qv):
+        out = [ocvi.spatial_sparsity_gaussian_ell_and_grads(Y[i], s2, W, c0, 1e-5, qm[i][:, 0], qv[i]) for i in range(T)]
+        return sum(o[0] for o in out), np.stack([o[1] for o in out]), np.stack([o[2] for o in out])
+    for _ in range(2):
+        _, qm, qv = ofilters.filter_and_smooth(oprior, t, Yt, Vt)
+        _, dm, dS = grads(qm, qv)
+        Yt, Vt = ocvi.cvi_step(Yt, Vt, qm[:, :, 0], qv, dm, dS, beta)
+    lml, qm, qv = ofilters.filter_and_smooth(oprior, t, Yt, Vt)
+    ref = ocvi.elbo(grads(qm, qv)[0], ocvi.surrogate_ell(Yt, Vt, qm[:, :, 0], qv), lml)
+    assert rel(model.q.Y_tilde[0], Yt) < 1e-8 and rel(model.q.V_tilde[0], Vt) < 1e-8
+    assert abs(float(elbo[0]) - ref) <= 1e-8 * abs(ref)

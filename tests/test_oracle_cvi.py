@@ -187,3 +187,36 @@ def test_gauss_hermite_20_equals_poisson_closed_form_for_moderate_variance():
         for quad, closed in (((w * (y * f - lam)).sum(), y * m - E), ((w * (y - lam)).sum(), y - E),
                              ((w * -lam).sum(), -E)):
             assert abs(quad - closed) <= 2e-15 * max(1.0, abs(closed), E)
+
+
+def test_spatial_sparsity_ell_gradients_by_finite_differences():
+    """oracle.cvi.spatial_sparsity_gaussian_ell_and_grads: the closed-form pull-back of the data-location gradients
+    through the spatial conditional equals central differences of the ELL w.r.t. every entry of (q_mu, q_var) --
+    the quantity `jax.grad(partial_ell, (1, 2))` returns (cvi_nat_grad.py:381-383)."""
+    import numpy as np
+    from oracle import cvi as ocvi
+    rng = np.random.default_rng(3)
+    M, N = 5, 8
+    W = rng.normal(size=(N, M))
+    c0 = rng.uniform(0.1, 0.5, N)
+    y = rng.normal(size=N)
+    y[[1, 6]] = np.nan
+    qm = rng.normal(size=M)
+    B = rng.normal(size=(M, M))
+    qS = B @ B.T + np.eye(M)
+    ell, dm, dS = ocvi.spatial_sparsity_gaussian_ell_and_grads(y, 0.3, W, c0, 1e-5, qm, qS)
+    h = 1e-6
+    for i in range(M):
+        e = np.zeros(M); e[i] = h
+        fd = (ocvi.spatial_sparsity_gaussian_ell_and_grads(y, 0.3, W, c0, 1e-5, qm + e, qS)[0]
+              - ocvi.spatial_sparsity_gaussian_ell_and_grads(y, 0.3, W, c0, 1e-5, qm - e, qS)[0]) / (2 * h)
+        assert abs(fd - dm[i]) < 1e-6 * max(1.0, abs(dm[i]))
+        for j in range(M):
+            E = np.zeros((M, M)); E[i, j] = h
+            fd = (ocvi.spatial_sparsity_gaussian_ell_and_grads(y, 0.3, W, c0, 1e-5, qm, qS + E)[0]
+                  - ocvi.spatial_sparsity_gaussian_ell_and_grads(y, 0.3, W, c0, 1e-5, qm, qS - E)[0]) / (2 * h)
+            assert abs(fd - dS[i, j]) < 1e-6 * max(1.0, abs(dS[i, j]))
+    # with the data AT the inducing points (W = I, c0 = 0, no jitter) it reduces to the NoSparsity gradients
+    ell1, dm1, dS1 = ocvi.spatial_sparsity_gaussian_ell_and_grads(y[:M], 0.3, np.eye(M), np.zeros(M), 0.0, qm, qS)
+    ell0, dm0, dS0 = ocvi.gaussian_ell_and_grads(y[:M], 0.3 * np.eye(M), None, qm, qS)
+    assert abs(ell1 - ell0) < 1e-12 * abs(ell0) and np.allclose(dm1, dm0, atol=1e-13) and np.allclose(dS1, dS0, atol=1e-13)
