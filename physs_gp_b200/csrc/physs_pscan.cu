@@ -1023,21 +1023,11 @@ __device__ __forceinline__ void small_solve(double (&M)[D][D], double (&X)[D][D]
   }
 }
 
+// o = l (x) r for two filtering elements (A, C, J, b, eta) stored as NE = 3 D^2 + 2 D consecutive doubles; l, r, o
+// may live in global or shared memory, o may not alias l or r.
 template <int D>
-__global__ void __launch_bounds__(128) ps_filter_scan_reg_kernel(const double* __restrict__ in, double* __restrict__ out,
-                                                                 int64_t B, int64_t nchunk, int64_t nsum, int64_t stride) {
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= B * nsum) return;
-  const int64_t b = gid / nsum, c = gid % nsum;
-  constexpr int NE = 3 * D * D + 2 * D;
-  const double* r = in + (b * nchunk + c) * NE;
-  double* o = out + (b * nchunk + c) * NE;
-  if (c < stride) {                                       // identity on the left
-#pragma unroll
-    for (int i = 0; i < NE; ++i) o[i] = r[i];
-    return;
-  }
-  const double* l = in + (b * nchunk + c - stride) * NE;
+__device__ __forceinline__ void ps_filter_combine(const double* __restrict__ l, const double* __restrict__ r,
+                                                  double* __restrict__ o) {
   double Ai[D][D], Ci[D][D], Ji[D][D], Aj[D][D], Cj[D][D], Jj[D][D], bi[D], ei[D], bj[D], ej[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) {
@@ -1117,22 +1107,29 @@ __global__ void __launch_bounds__(128) ps_filter_scan_reg_kernel(const double* _
     }
 }
 
-// suffix scan step of the smoother: out[c] = in[c] o in[c + stride]  (identity on the right past the end)
 template <int D>
-__global__ void __launch_bounds__(128) ps_smooth_scan_reg_kernel(const double* __restrict__ in, double* __restrict__ out,
-                                                                 int64_t B, int64_t nchunk, int64_t stride) {
+__global__ void __launch_bounds__(128) ps_filter_scan_reg_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                                 int64_t B, int64_t nchunk, int64_t nsum, int64_t stride) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= B * nchunk) return;
-  const int64_t b = gid / nchunk, c = gid % nchunk;
-  constexpr int NS = 2 * D * D + D;
-  const double* l = in + (b * nchunk + c) * NS;
-  double* o = out + (b * nchunk + c) * NS;
-  if (c + stride >= nchunk) {
+  if (gid >= B * nsum) return;
+  const int64_t b = gid / nsum, c = gid % nsum;
+  constexpr int NE = 3 * D * D + 2 * D;
+  const double* r = in + (b * nchunk + c) * NE;
+  double* o = out + (b * nchunk + c) * NE;
+  if (c < stride) {                                       // identity on the left
 #pragma unroll
-    for (int i = 0; i < NS; ++i) o[i] = l[i];
+    for (int i = 0; i < NE; ++i) o[i] = r[i];
     return;
   }
-  const double* r = in + (b * nchunk + c + stride) * NS;
+  const double* l = in + (b * nchunk + c - stride) * NE;
+  ps_filter_combine<D>(l, r, o);
+}
+
+// suffix scan step of the smoother: out[c] = in[c] o in[c + stride]  (identity on the right past the end)
+// o = l (x) r for two smoothing elements (E, L, g), NS = 2 D^2 + D consecutive doubles each
+template <int D>
+__device__ __forceinline__ void ps_smooth_combine(const double* __restrict__ l, const double* __restrict__ r,
+                                                  double* __restrict__ o) {
   double Ei[D][D], Li[D][D], Ej[D][D], Lj[D][D], gi[D], gj[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) {
@@ -1175,6 +1172,59 @@ __global__ void __launch_bounds__(128) ps_smooth_scan_reg_kernel(const double* _
   for (int i = 0; i < D; ++i)
 #pragma unroll
     for (int j = 0; j < D; ++j) o[D * D + i * D + j] = 0.5 * (Lo[i][j] + Lo[j][i]);
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) ps_smooth_scan_reg_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                                 int64_t B, int64_t nchunk, int64_t stride) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * nchunk) return;
+  const int64_t b = gid / nchunk, c = gid % nchunk;
+  constexpr int NS = 2 * D * D + D;
+  const double* l = in + (b * nchunk + c) * NS;
+  double* o = out + (b * nchunk + c) * NS;
+  if (c + stride >= nchunk) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) o[i] = l[i];
+    return;
+  }
+  const double* r = in + (b * nchunk + c + stride) * NS;
+  ps_smooth_combine<D>(l, r, o);
+}
+
+// All Hillis-Steele passes of one series in ONE launch: a block per series, its <= 128 chunk elements ping-pong between
+// two shared-memory buffers (element stride padded to an odd number of doubles: conflict-free), one __syncthreads per
+// pass.  Replaces log2(nchunk) launches that each round-trip every element through L2 (7 x 20 us -> one ~25 us kernel at
+// 1000 series x 79 chunks, d = 2).  dst may alias in (every element is read before any is written).
+template <int D, bool SUFFIX>
+__global__ void __launch_bounds__(128) ps_scan_fused_kernel(const double* in, double* dst, int64_t nchunk, int n) {
+  constexpr int NE = SUFFIX ? 2 * D * D + D : 3 * D * D + 2 * D;
+  constexpr int LDE = NE | 1;
+  extern __shared__ __align__(16) double ps_fused_sm[];
+  double* cur = ps_fused_sm;
+  double* nxt = ps_fused_sm + 128 * LDE;
+  const int c = threadIdx.x;
+  const double* src = in + (int64_t)blockIdx.x * nchunk * NE;
+  for (int idx = threadIdx.x; idx < n * NE; idx += 128) cur[(idx / NE) * LDE + idx % NE] = src[idx];
+  __syncthreads();
+  for (int stride = 1; stride < n; stride *= 2) {
+    if (c < n) {
+      double* o = nxt + c * LDE;
+      const bool edge = SUFFIX ? (c + stride >= n) : (c < stride);
+      if (edge) {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) o[i] = cur[c * LDE + i];
+      } else if (SUFFIX) {
+        ps_smooth_combine<D>(cur + c * LDE, cur + (c + stride) * LDE, o);
+      } else {
+        ps_filter_combine<D>(cur + (c - stride) * LDE, cur + c * LDE, o);
+      }
+    }
+    __syncthreads();
+    double* t = cur; cur = nxt; nxt = t;
+  }
+  double* out = dst + (int64_t)blockIdx.x * nchunk * NE;
+  for (int idx = threadIdx.x; idx < n * NE; idx += 128) out[idx] = cur[(idx / NE) * LDE + idx % NE];
 }
 
 // apply steps in registers (same role as ps_filter_apply_kernel / ps_smooth_apply_kernel above)
@@ -1360,6 +1410,32 @@ static int run_smooth_scan_reg(cudaStream_t st, int d, const double* in, double*
   return cuda_status(cudaGetLastError(), "ps_smooth_scan_reg_kernel launch");
 }
 
+// fused scan (ps_scan_fused_kernel): all passes in one launch when a series has at most 128 elements to scan
+static bool ps_fused_scan(int d, int64_t n) {
+  static const bool off = getenv("PHYSS_PSCAN_NOFUSE") != nullptr;
+  return ps_reg_scan(d) && n >= 2 && n <= 128 && !off;
+}
+template <int D, bool SUFFIX>
+static int launch_scan_fused(cudaStream_t st, const double* in, double* dst, int64_t B, int64_t nchunk, int64_t n) {
+  constexpr int NE = SUFFIX ? 2 * D * D + D : 3 * D * D + 2 * D;
+  const size_t smem = 2 * 128 * (size_t)(NE | 1) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ps_scan_fused_kernel<D, SUFFIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "ps_scan_fused_kernel: shared memory attribute");
+    configured = true;
+  }
+  ps_scan_fused_kernel<D, SUFFIX><<<(unsigned)B, 128, smem, st>>>(in, dst, nchunk, (int)n);
+  return cuda_status(cudaGetLastError(), "ps_scan_fused_kernel launch");
+}
+template <bool SUFFIX>
+static int run_scan_fused(cudaStream_t st, int d, const double* in, double* dst, int64_t B, int64_t nchunk, int64_t n) {
+  if (d == 1) return launch_scan_fused<1, SUFFIX>(st, in, dst, B, nchunk, n);
+  if (d == 2) return launch_scan_fused<2, SUFFIX>(st, in, dst, B, nchunk, n);
+  if (d == 3) return launch_scan_fused<3, SUFFIX>(st, in, dst, B, nchunk, n);
+  return launch_scan_fused<4, SUFFIX>(st, in, dst, B, nchunk, n);
+}
+
 template <int G>
 static int run_filter_apply(cudaStream_t st, const double* prefix, int64_t B, int64_t nchunk, int64_t nsum,
                             const double* m0, int64_t m0_bs, const double* P0, int64_t P0_bs, double* bnd_m,
@@ -1481,7 +1557,13 @@ int pscan_filter_local(cudaStream_t st, int d, int m, int disc_mode, int nblk, b
   rc = summarise(nfull_sum, nsum - nfull_sum);
   if (rc) return rc;
   double* in = w.e0; double* out = w.e1;
-  for (int64_t stride = 1; stride < nsum; stride *= 2) {
+  const bool fused = ps_fused_scan(d, nsum) && a.B <= 0x7fffffff;
+  if (fused) {                  // the result lands where the pass-by-pass ping-pong would have left it
+    for (int64_t stride = 1; stride < nsum; stride *= 2) { double* t = in; in = out; out = t; }
+    rc = run_scan_fused<false>(st, d, w.e0, in, a.B, nchunk, nsum);
+    if (rc) return rc;
+  }
+  for (int64_t stride = 1; !fused && stride < nsum; stride *= 2) {
     rc = ps_reg_scan(d) ? run_filter_scan_reg(st, d, in, out, a.B, nchunk, nsum, stride)
                         : PS_BY_G(run_filter_scan, st, in, out, a.B, nchunk, nsum, stride, Lc);
     if (rc) return rc;
@@ -1733,7 +1815,13 @@ int pscan_smooth_local(cudaStream_t st, int d, int disc_mode, int nblk, SeqSmoot
     if (rc) return rc;
   }
   double* in = w.e0; double* out = w.e1;
-  for (int64_t stride = 1; stride < nchunk; stride *= 2) {
+  const bool fused = ps_fused_scan(d, nchunk) && a.B <= 0x7fffffff;
+  if (fused) {
+    for (int64_t stride = 1; stride < nchunk; stride *= 2) { double* t = in; in = out; out = t; }
+    rc = run_scan_fused<true>(st, d, w.e0, in, a.B, nchunk, nchunk);
+    if (rc) return rc;
+  }
+  for (int64_t stride = 1; !fused && stride < nchunk; stride *= 2) {
     rc = ps_reg_scan(d) ? run_smooth_scan_reg(st, d, in, out, a.B, nchunk, stride)
                         : PS_BY_G(run_smooth_scan, st, in, out, a.B, nchunk, stride, Ls);
     if (rc) return rc;
