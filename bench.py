@@ -1031,14 +1031,28 @@ def cvi_measure(a, dev, world, rank, local, B, T, steps, warmup, with_clocks, cp
     Y_host = torch.empty(Yh.shape, dtype=torch.float64, pin_memory=True); Y_host.copy_(torch.as_tensor(Yh))
     o_elbo = torch.empty((B,), dtype=torch.float64, pin_memory=True)
 
+    pipelined = graphed and not os.environ.get("PHYSS_CVI_E2E_SERIAL")
+
     def e2e_step():
         model.set_data(Y_host)
         o_elbo.copy_(step(), non_blocking=True)
         torch.cuda.synchronize()
     e2e_step(); barrier()
     tw = time.perf_counter()
-    for _ in range(steps):
-        e2e_step()
+    if pipelined:
+        # every step's data still comes from pinned host memory; the upload of step i + 1 runs on a copy stream while
+        # step i computes (VGP.stage_data / commit_data), the ELBO of every step is read back before the next commit
+        model.stage_data(Y_host)
+        for i in range(steps):
+            model.commit_data()
+            if i + 1 < steps:
+                model.stage_data(Y_host)
+            o_elbo.copy_(step(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        torch.cuda.synchronize()
+    else:
+        for _ in range(steps):
+            e2e_step()
     elw = torch.tensor([time.perf_counter() - tw], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(elw, op=dist.ReduceOp.MAX)
@@ -1061,7 +1075,8 @@ def cvi_measure(a, dev, world, rank, local, B, T, steps, warmup, with_clocks, cp
                    "d2h_bytes_per_step": B * 8 * world,
                    "api": ("VGP.compile_step(0.1) once, then VGP.set_data + VGP.step() (one CUDA graph per iteration)"
                            if graphed else "VGP.natural_gradient_update(0.1) + VGP.elbo()") +
-                          ", data from pinned host memory"},
+                          (", data from pinned host memory; the upload of step i + 1 (VGP.stage_data, copy stream) overlaps "
+                           "step i, VGP.commit_data swaps it in" if pipelined else ", data from pinned host memory")},
            "clocks": clocks}
     if cpu:
         n = a.cpu_sample_series or max(os.cpu_count() or 1, 8)

@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(128) cvi_site_kernel(const CviArgs p) {
     }
     if (LIK == CVI_LIK_GAUSS)
       ldv<P * P>(p.noise + n * p.noise_stride, *reinterpret_cast<double (*)[P * P]>(&noise[0][0]));
-    ell = cvi_ell_grads<D, P, LIK>(qm, qS, y, W, noise, p.lik_param, p.K, p.ghx, p.ghw, dm, dS);
+    ell = cvi_ell_grads<D, P, LIK>(qm, qS, y, W, noise, p.lik_param, p.K, p.ghx, p.ghw, dm, dS, p.ell != nullptr,
+                                   p.log_param, p.logfact, true);
     if (p.ell) p.ell[n] = ell;
     if (p.dm_out) stv<D>(p.dm_out + n * D, dm);
     if (p.dS_out) stv<D * D>(p.dS_out + n * D * D, *reinterpret_cast<double (*)[D * D]>(&dS[0][0]));
@@ -58,8 +59,37 @@ __global__ void __launch_bounds__(128) cvi_site_kernel(const CviArgs p) {
   }
 }
 
+// log(y!) for the counts 0..255, evaluated once per process on the host (lgammal, rounded to double) and kept in device
+// memory.  The first request that arrives while its stream is being captured into a CUDA graph gets no table (the
+// kernels then call lgamma themselves): the upload is a synchronous copy, which a capture does not allow.
+__device__ double g_logfact[kLogFactN];
+static const double* logfact_table(cudaStream_t st) {
+  static const double* table = nullptr;
+  static int device = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (table && dev == device) return table;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
+  double h[kLogFactN];
+  for (int i = 0; i < kLogFactN; ++i) h[i] = (double)lgammal((long double)i + 1.0L);
+  void* ptr = nullptr;
+  if (cudaMemcpyToSymbol(g_logfact, h, sizeof(h)) != cudaSuccess || cudaGetSymbolAddress(&ptr, g_logfact) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  table = static_cast<const double*>(ptr);
+  device = dev;
+  return table;
+}
+
 template <int D, int P, int LIK, bool UPDATE>
-static int launch(cudaStream_t st, const CviArgs& a) {
+static int launch(cudaStream_t st, const CviArgs& a0) {
+  CviArgs a = a0;
+  if (LIK == CVI_LIK_POISSON_EXP) {
+    a.log_param = log(a.lik_param);
+    a.logfact = logfact_table(st);
+  }
   const int block = 128;
   const int64_t grid = (a.N + block - 1) / block;
   cvi_site_kernel<D, P, LIK, UPDATE><<<(unsigned)grid, block, 0, st>>>(a);

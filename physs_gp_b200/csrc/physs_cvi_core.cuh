@@ -24,6 +24,14 @@ constexpr double kInvSqrt2 = 0.70710678118654752440084436210485;
 // `c0` = y log(binsize) - lgamma(y + 1): the part of l(f) that does not depend on f, evaluated ONCE per site by
 // the caller (lgamma inside the quadrature loop cost more than the exp it sits next to).
 PHYSS_HD double poisson_exp_const(double y, double binsize) { return y * log(binsize) - lgamma(y + 1.0); }
+// The same constant with log(binsize) hoisted out of the kernel and lgamma(y + 1) read from a table of log-factorials
+// for the integer counts 0..255 (lgamma is ~250 fp64 instructions with branches: more than the rest of the closed-form
+// Poisson site together).  logfact == nullptr, or a count outside the table: the plain evaluation.
+constexpr int kLogFactN = 256;
+PHYSS_HD double poisson_exp_const_tab(double y, double log_binsize, const double* logfact) {
+  const bool tab = logfact != nullptr && y >= 0.0 && y < (double)kLogFactN && y == floor(y);
+  return y * log_binsize - (tab ? logfact[(int)y] : lgamma(y + 1.0));
+}
 PHYSS_HD void poisson_exp_terms(double y, double f, double binsize, double c0, double& l, double& d1, double& d2) {
   const double lam = exp(f) * binsize;
   l = fma(y, f, c0) - lam;
@@ -115,7 +123,8 @@ template <int D, int P, int LIK>
 PHYSS_HD double cvi_ell_grads(const double (&qm)[D], const double (&qS)[D][D], const double (&y)[P],
                               const double (&W)[P][D], const double (&noise)[P][P], double lik_param,
                               int K, const double* ghx, const double* ghw, double (&dm)[D],
-                              double (&dS)[D][D]) {
+                              double (&dS)[D][D], bool want_ell = true, double log_param = 0.0,
+                              const double* logfact = nullptr, bool have_log = false) {
   double fmu[P], WS[P][D];
   PHYSS_UNROLL
   for (int a = 0; a < P; ++a) {
@@ -190,7 +199,10 @@ PHYSS_HD double cvi_ell_grads(const double (&qm)[D], const double (&qS)[D][D], c
       const double ya = obs ? y[a] : 0.0;
       const double sd = sqrt(2.0 * fv);
       double e0 = 0.0, e1 = 0.0, e2 = 0.0;
-      const double c0 = (LIK == CVI_LIK_POISSON_EXP) ? poisson_exp_const(ya, lik_param) : 0.0;
+      // the f-independent part of l(f) only shifts the ELL: skipped when the caller wants the gradients alone
+      double c0 = 0.0;
+      if (LIK == CVI_LIK_POISSON_EXP && want_ell)
+        c0 = have_log ? poisson_exp_const_tab(ya, log_param, logfact) : poisson_exp_const(ya, lik_param);
       if (LIK == CVI_LIK_POISSON_EXP) {
         // exp(m + sd x_q) = exp(m) exp(sd x_q), and Gauss-Hermite nodes come in pairs +-x (numpy's hermgauss
         // symmetrises them exactly): one exp and one reciprocal per PAIR instead of two exps -- the quadrature

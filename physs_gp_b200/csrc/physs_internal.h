@@ -105,6 +105,7 @@ struct CviArgs {
   const double* W;                          // [P,D] shared, NULL = identity
   const double* noise; int64_t noise_stride;  // Gaussian noise [.,P,P]
   double lik_param; int K; const double* ghx; const double* ghw;
+  double log_param; const double* logfact;  // Poisson: log(binsize) and the device table of log-factorials (or NULL)
   const double* dm_in; const double* dS_in;
   double beta, ngj;
   double* Yn; double* Vn;

@@ -399,6 +399,32 @@ class VGP:
             return
         self.Y = time_major_blocks(Y) if _is_tm(self.q.Y_tilde) else Y
 
+    def stage_data(self, Y):
+        """Start uploading the NEXT data set [B, T, P] (pinned host memory) on a side stream into a staging buffer while
+        the current iteration computes; `commit_data()` then swaps it in.  The pair does what `set_data` does, with the
+        host -> device copy overlapped with the previous step (the upload of 80 MB takes as long as the step itself)."""
+        dev = self.q.Y_tilde.device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staging = torch.empty(self.Y.shape, dtype=torch.float64, device=dev)   # dense [B, T, P]
+            self._staged, self._consumed = torch.cuda.Event(), None
+        Y = torch.as_tensor(Y, dtype=torch.float64)
+        if Y.dim() == 2:
+            Y = Y[None]
+        with torch.cuda.stream(self._copy_stream):
+            if self._consumed is not None:
+                self._copy_stream.wait_event(self._consumed)      # the previous commit has read the staging buffer
+            self._staging.copy_(Y, non_blocking=True)
+            self._staged.record(self._copy_stream)
+
+    def commit_data(self):
+        """Make the staged data set current (device -> device, into the buffer a compiled step reads)."""
+        cur = torch.cuda.current_stream(self.q.Y_tilde.device)
+        cur.wait_event(self._staged)
+        self.Y.copy_(self._staging)                # strided destination when the sites are time-major
+        self._consumed = torch.cuda.Event()
+        self._consumed.record(cur)
+
     def compile_step(self, lr, enforce_psd_type=None):
         """Capture natural_gradient_update(lr) + elbo() -- one CVI iteration, vgp.py:274-282,148-157 -- into ONE CUDA
         graph.  The iteration is ~85 short launches (chunk summaries, scans, replays, site kernels, reductions); as

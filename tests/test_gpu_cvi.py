@@ -328,7 +328,9 @@ def test_compiled_cvi_step_equals_eager(cuda_device, B, T, ftype):
     e_ref, e_got = [], []
     for it in range(4):
         if it == 2:
-            eager.set_data(Y2); comp.set_data(Y2)
+            eager.set_data(Y2)
+            # the staged route: upload on the copy stream, swap in on the compute stream (what bench.py's e2e uses)
+            comp.stage_data(torch.as_tensor(Y2).pin_memory()); comp.commit_data()
         eager.natural_gradient_update(0.2)
         e_ref.append(eager.elbo().clone())
         e_got.append(comp.step().clone())
