@@ -1078,6 +1078,28 @@ def cvi_measure(a, dev, world, rank, local, B, T, steps, warmup, with_clocks, cp
                           (", data from pinned host memory; the upload of step i + 1 (VGP.stage_data, copy stream) overlaps "
                            "step i, VGP.commit_data swaps it in" if pipelined else ", data from pinned host memory")},
            "clocks": clocks}
+    if graphed and world == 1 and not os.environ.get("PHYSS_CVI_NO_REUSE"):
+        # beside the standard step (NOT the headline value): the training-loop form that serves the posterior of iteration
+        # i's ELBO to iteration i + 1's natural-gradient step -- same sites, same numbers, one posterior pass per iteration
+        q2 = cvi.FullConjugateGaussian(t, prior, 1, B=B, device=dev, filter_type=a.filter_type)
+        m2 = cvi.VGP(Yh, cvi.PoissonLik(1.0), q2, ell_quad_points=20)
+        m2.compile_step(0.1, reuse_posterior=True)
+        for _ in range(warmup):
+            m2.step()
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(steps):
+            eb = m2.step()
+        r1.record()
+        torch.cuda.synchronize()
+        assert torch.isfinite(eb).all()
+        rec["reuse_posterior"] = {"ms_per_step": r0.elapsed_time(r1) / steps, "unit": "ms",
+                                  "api": "VGP.compile_step(0.1, reuse_posterior=True): the filter + smoother pass of the "
+                                         "ELBO of iteration i feeds the natural-gradient step of iteration i + 1 (the "
+                                         "reference runs it twice per iteration, vgp.py:274-282,148-157); bitwise the "
+                                         "same sites and ELBOs (tests/test_gpu_cvi.py)"}
+        del m2, q2
     if cpu:
         n = a.cpu_sample_series or max(os.cpu_count() or 1, 8)
         ms_full, threads, elc, reps, ms_s = cpu_cvi_step_ms(B, T, n, budget_s=6.0)

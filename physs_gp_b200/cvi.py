@@ -425,7 +425,7 @@ class VGP:
         self._consumed = torch.cuda.Event()
         self._consumed.record(cur)
 
-    def compile_step(self, lr, enforce_psd_type=None):
+    def compile_step(self, lr, enforce_psd_type=None, reuse_posterior=False):
         """Capture natural_gradient_update(lr) + elbo() -- one CVI iteration, vgp.py:274-282,148-157 -- into ONE CUDA
         graph.  The iteration is ~85 short launches (chunk summaries, scans, replays, site kernels, reductions); as
         a graph the host enqueues a single node list and the launch gaps disappear.  The sites, the data buffer
@@ -444,11 +444,24 @@ class VGP:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         q.Y_tilde.copy_(Yt0); q.V_tilde.copy_(Vt0)
+        self._post = None
+        if reuse_posterior:
+            # the posterior under the CURRENT sites, in buffers that keep their addresses: every replay reads them in
+            # its natural-gradient half and refreshes them from the posterior its ELBO half computes
+            self.reuse_posterior = True
+            self._posterior(want_lml=True)
+            self._post_static = tuple(x.clone() for x in self._post)
+            self._post = self._post_static
+            torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         del _filters.captured_status[:]
         with torch.cuda.graph(graph):
             self.natural_gradient_update(lr, enforce_psd_type=enforce_psd_type)
             elbo = self.elbo()
+            if reuse_posterior:
+                for dst, src in zip(self._post_static, self._post):
+                    dst.copy_(src)
+                self._post = self._post_static
             flags = list(_filters.captured_status)
             status = torch.stack([f.reshape(-1)[0] for f in flags]).max() if flags else None
         del _filters.captured_status[:]
@@ -460,6 +473,26 @@ class VGP:
         self._graph.replay()
         return self._graph_elbo
 
+    reuse_posterior = False     # opt-in: see _posterior
+
+    def _posterior(self, want_lml=False):
+        """(lml, q_mu [B,T,D], q_var [B,T,D,D]) of the surrogate under the current sites.  The reference runs the
+        filter + smoother once in `natural_gradients` and once more in `elbo` (vgp.py:274-282, 148-157); in a training
+        loop the pass of iteration i's ELBO and the one of iteration i + 1's natural-gradient step see the SAME sites.
+        With `reuse_posterior = True` the result is kept until the sites change (natural_gradient_update) and served
+        from there: one posterior pass per iteration instead of two, same numbers.  The surrogate's prior must not
+        change in between (call `invalidate()` after a hyper-parameter step)."""
+        if self.reuse_posterior and getattr(self, "_post", None) is not None:
+            return self._post
+        lml, q_mu, q_var = self.q.surrogate.posterior_blocks(return_lml=True)
+        out = (lml, q_mu[..., 0], q_var[..., 0, :, :])
+        if self.reuse_posterior:
+            self._post = out
+        return out
+
+    def invalidate(self):
+        self._post = None
+
     def natural_gradient_update(self, lr, enforce_psd_type=None, prediction_samples=None):
         """vgp.py:274-282 -> cvi_nat_grad.py:508-515,346-410 -> cvi_parameterisations.py:63-93."""
         pde = getattr(self.lik, "kind", None) == "pendulum"
@@ -467,8 +500,8 @@ class VGP:
             raise NotImplementedError("enforce_psd_type: None, or 'laplace_gauss_newton_delta_u' with a PDE "
                                       "collocation likelihood, are implemented on the b200 path")
         q = self.q
-        q_mu, q_var = q.surrogate.posterior_blocks()               # [B,T,D,1], [B,T,1,D,D]
-        q_mu, q_var = q_mu[..., 0], q_var[..., 0, :, :]
+        _, q_mu, q_var = self._posterior()                         # [B,T,D], [B,T,D,D]
+        self._post = None                                          # the sites change below
         if pde:
             # cvi_nat_grad.py:381-387: dELL/dm from the ELL, dELL/dS replaced by the Gauss-Newton curvature
             _, dm, dS = pendulum_expected_log_likelihood(q_mu, q_var, self.Y, self.lik,
@@ -482,8 +515,7 @@ class VGP:
     def elbo(self):
         """elbos.py:163-194; returns one ELBO per batch member [B]."""
         q = self.q
-        lml, q_mu, q_var = q.surrogate.posterior_blocks(return_lml=True)
-        q_mu, q_var = q_mu[..., 0], q_var[..., 0, :, :]
+        lml, q_mu, q_var = self._posterior(want_lml=True)
         if getattr(self.lik, "kind", None) == "pendulum":
             ell = pendulum_expected_log_likelihood(q_mu, q_var, self.Y, self.lik)
         else:

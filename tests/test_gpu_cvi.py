@@ -340,3 +340,53 @@ def test_compiled_cvi_step_equals_eager(cuda_device, B, T, ftype):
     assert torch.equal(eager.q.Y_tilde, comp.q.Y_tilde) and torch.equal(eager.q.V_tilde, comp.q.V_tilde)
     if comp.step_status is not None:
         assert int(comp.step_status.item()) == 0
+
+
+@pytest.mark.parametrize("compiled", [False, True])
+def test_posterior_reuse_gives_the_same_iterations(cuda_device, compiled):
+    """VGP.reuse_posterior: the filter + smoother pass of iteration i's ELBO is served to iteration i + 1's
+    natural-gradient step (same sites) -- one posterior pass per iteration instead of the reference's two.  Sites and
+    ELBOs must equal the standard iteration bitwise, eager and as a compiled graph, also across set_data."""
+    from physs_gp_b200 import cvi, sdes
+    rng = np.random.default_rng(23)
+    B, T = 6, 700
+    t = synth.time_grid(T, 0.1, rng)
+    ls = synth.log_uniform(rng, 0.5, 2.0, (B, 1))
+    Y = rng.poisson(1.5, size=(B, T, 1)).astype(float)
+    Y[rng.uniform(size=Y.shape) < 0.05] = np.nan
+    Y2 = rng.poisson(0.7, size=(B, T, 1)).astype(float)
+
+    def make():
+        q = cvi.FullConjugateGaussian(t, sdes.BatchedMaternSDE(2, ls), 1, B=B, filter_type="b200_parallel")
+        return cvi.VGP(Y, cvi.PoissonLik(1.0), q, ell_quad_points=20)
+    std, fast = make(), make()
+    calls = {"n": 0}
+    if compiled:
+        fast.compile_step(0.2, reuse_posterior=True)
+    else:
+        fast.reuse_posterior = True
+        sur = type(fast.q).surrogate.fget
+
+        class Counting:                      # counts the posterior passes of the eager route
+            def __init__(self, inner): self.inner = inner
+            def posterior_blocks(self, **k):
+                calls["n"] += 1
+                return self.inner.posterior_blocks(**k)
+        fast.q.__class__ = type("CountingQ", (type(fast.q),), {"surrogate": property(lambda self: Counting(sur(self)))})
+    e_ref, e_got = [], []
+    for it in range(4):
+        if it == 2:
+            std.set_data(Y2); fast.set_data(Y2)
+        std.natural_gradient_update(0.2)
+        e_ref.append(std.elbo().clone())
+        if compiled:
+            e_got.append(fast.step().clone())
+        else:
+            fast.natural_gradient_update(0.2)
+            e_got.append(fast.elbo().clone())
+    torch.cuda.synchronize()
+    for a, b in zip(e_ref, e_got):
+        assert torch.equal(a, b)
+    assert torch.equal(std.q.Y_tilde, fast.q.Y_tilde) and torch.equal(std.q.V_tilde, fast.q.V_tilde)
+    if not compiled:
+        assert calls["n"] == 5               # one pass for the first natural-gradient step, then one per iteration
