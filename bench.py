@@ -1340,6 +1340,23 @@ def run_c2cvi(a):
     for _ in range(a.steps):
         e2e_step()
     elw = 1e3 * (time.perf_counter() - tw) / a.steps
+    reuse = None
+    if world == 1 and not os.environ.get("PHYSS_CVI_NO_REUSE"):
+        # beside the standard iteration (not in `value`): posterior of iteration i's ELBO served to iteration i + 1
+        model.reuse_posterior = True
+        step(); torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(a.steps):
+            eb = step()
+        r1.record()
+        torch.cuda.synchronize()
+        assert torch.isfinite(eb).all()
+        reuse = {"ms_per_step": r0.elapsed_time(r1) / a.steps, "unit": "ms",
+                 "api": "VGP.reuse_posterior = True: one filter + smoother pass per iteration instead of the reference's two "
+                        "(vgp.py:274-282,148-157), same sites and ELBOs"}
+        model.reuse_posterior = False
+        model.invalidate()
     d, m = 2 * Ns, Ns
     # two posterior passes + (2 + 1) SPD inverses of D x D per step (chol D^3/3 + inverse 2 D^3/3 ... = D^3 each, FMA = 2)
     flops = 2 * (14.3 * d ** 3 + 4 * m * d * d + 6 * m * m * d + 0.67 * m ** 3) + 3 * 2.0 * m ** 3
@@ -1365,7 +1382,7 @@ def run_c2cvi(a):
                          "frac": flops * T / (ms * 1e-3) / 1e12 / fp64, "traffic": None,
                          "peak_source": "physs_fp64_probe (FP64 FMA pipe), this run",
                          "note": "dense flop count of two posterior passes (SURVEY 8d) + three D x D SPD inverses per block"},
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "reuse_posterior": reuse,
             "e2e": {"value": elw, "unit": "ms", "h2d_bytes_per_step": T * Ns * 8 * world, "d2h_bytes_per_step": 8 * world,
                     "api": "VGP.set_data + VGP.natural_gradient_update(0.5) + VGP.elbo(), pinned host buffers"},
             "clocks": clocks, "gpu_launches": None}), flush=True)
