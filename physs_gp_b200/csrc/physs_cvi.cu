@@ -29,6 +29,13 @@ __global__ void __launch_bounds__(128) cvi_site_kernel(const CviArgs p) {
   double qm[D], qS[D][D], dm[D], dS[D][D];
   ldv<D>(p.qm + n * D, qm);
   ldv<D * D>(p.qS + n * D * D, *reinterpret_cast<double (*)[D * D]>(&qS[0][0]));
+  // the sites are loaded up front: behind the ELL (and its optional stores, which the compiler must assume alias) their
+  // latency was a second, fully exposed round trip to HBM (ncu: 9.8 long-scoreboard stalls per issue)
+  double Yt[D], Vt[D][D];
+  if (UPDATE) {
+    ldv<D>(p.Yt + n * D, Yt);
+    ldv<D * D>(p.Vt + n * D * D, *reinterpret_cast<double (*)[D * D]>(&Vt[0][0]));
+  }
   double ell = 0.0;
   if (LIK == CVI_LIK_GIVEN) {
     ldv<D>(p.dm_in + n * D, dm);
@@ -50,9 +57,7 @@ __global__ void __launch_bounds__(128) cvi_site_kernel(const CviArgs p) {
     if (p.dS_out) stv<D * D>(p.dS_out + n * D * D, *reinterpret_cast<double (*)[D * D]>(&dS[0][0]));
   }
   if (UPDATE) {
-    double Yt[D], Vt[D][D], Yn[D], Vn[D][D];
-    ldv<D>(p.Yt + n * D, Yt);
-    ldv<D * D>(p.Vt + n * D * D, *reinterpret_cast<double (*)[D * D]>(&Vt[0][0]));
+    double Yn[D], Vn[D][D];
     cvi_site_update<D>(Yt, Vt, qm, qS, dm, dS, p.beta, p.ngj, Yn, Vn);
     stv<D>(p.Yn + n * D, Yn);
     stv<D * D>(p.Vn + n * D * D, *reinterpret_cast<double (*)[D * D]>(&Vn[0][0]));
