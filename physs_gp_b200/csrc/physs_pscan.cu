@@ -904,6 +904,31 @@ __global__ void __launch_bounds__(256) ps_lml_partial_kernel(const double* __res
     partial[b * nseg + sg] = t;
   }
 }
+// the same partial sums for the time-major step layout (sbs == 1: the series index is the fastest one): a block takes
+// 32 CONSECUTIVE series x one segment, every warp reads 32 series of one step -- 256 contiguous bytes -- where the kernel
+// above reads one 8-byte word per 32-byte sector (ncu: 107 long-scoreboard stalls per issue, 1.9 TB/s of useful bytes).
+__global__ void __launch_bounds__(256) ps_lml_partial_tm_kernel(const double* __restrict__ lml_k, int64_t B, int64_t T,
+                                                                int64_t sts, int64_t seg, int64_t nseg,
+                                                                double* __restrict__ partial) {
+  __shared__ double red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t nb32 = (B + 31) / 32;
+  const int64_t b = ((int64_t)blockIdx.x % nb32) * 32 + lane, sg = (int64_t)blockIdx.x / nb32;
+  const int64_t k0 = sg * seg, k1 = (k0 + seg < T) ? k0 + seg : T;
+  double s0 = 0.0, s1 = 0.0;
+  if (b < B) {
+    int64_t k = k0 + w;
+    for (; k + 8 < k1; k += 16) { s0 += lml_k[b + k * sts]; s1 += lml_k[b + (k + 8) * sts]; }
+    if (k < k1) s0 += lml_k[b + k * sts];
+  }
+  red[w][lane] = s0 + s1;
+  __syncthreads();
+  if (w == 0 && b < B) {
+    double t = 0.0;
+    for (int q = 0; q < 8; ++q) t += red[q][lane];
+    partial[b * nseg + sg] = t;
+  }
+}
 __global__ void ps_lml_final_kernel(const double* __restrict__ partial, int64_t B, int64_t nseg,
                                     double* __restrict__ lml) {
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -916,6 +941,29 @@ __global__ void ps_lml_final_kernel(const double* __restrict__ partial, int64_t 
 }
 static inline int64_t ps_lml_seg(int64_t T) { return T < 4096 ? T : 4096; }
 static inline int64_t ps_lml_nseg(int64_t T) { const int64_t sg = ps_lml_seg(T); return (T + sg - 1) / sg; }
+// lml[b] = sum_k lml_k[b, k].  Time-major layout with a free scratch of `big_n` doubles: 512-step segments summed by
+// the coalesced kernel (enough blocks to fill the GPU), else 4096-step segments by the strided one into `small`.
+static int ps_lml_sum(cudaStream_t st, const double* lml_k, int64_t B, int64_t T, int64_t sbs, int64_t sts,
+                      double* small, double* big, int64_t big_n, double* lml) {
+  const int64_t seg_tm = 512, nseg_tm = (T + seg_tm - 1) / seg_tm;
+  const double* partial;
+  int64_t nseg;
+  if (sbs == 1 && B >= 32 && big && B * nseg_tm <= big_n) {
+    nseg = nseg_tm;
+    partial = big;
+    ps_lml_partial_tm_kernel<<<(unsigned)(nseg * ((B + 31) / 32)), 256, 0, st>>>(lml_k, B, T, sts, seg_tm, nseg, big);
+  } else {
+    const int64_t seg = ps_lml_seg(T);
+    nseg = ps_lml_nseg(T);
+    partial = small;
+    ps_lml_partial_kernel<<<(unsigned)(nseg * B), 256, 0, st>>>(lml_k, T, sbs, sts, seg, nseg, small);
+  }
+  int rc = cuda_status(cudaGetLastError(), "ps_lml_partial_kernel launch");
+  if (rc) return rc;
+  const int64_t threads = B * 32;
+  ps_lml_final_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(partial, B, nseg, lml);
+  return cuda_status(cudaGetLastError(), "ps_lml_final_kernel launch");
+}
 
 // dst[r * dst_stride + i] = src[r * src_stride + i], i < n, r < rows   (src_stride may be 0 = broadcast)
 __global__ void ps_copy_rows_kernel(double* __restrict__ dst, int64_t dst_stride, const double* __restrict__ src,
@@ -1638,14 +1686,10 @@ int pscan_filter_finish(cudaStream_t st, int d, int m, int disc_mode, int nblk, 
     a.fixup = 0;
   }
   {
-    const int64_t seg = ps_lml_seg(a.T), nseg = ps_lml_nseg(a.T);
-    double* partial = w.lml_partial;
-    ps_lml_partial_kernel<<<(unsigned)(nseg * a.B), 256, 0, st>>>(a.lml_k, a.T, a.sbs, a.sts, seg, nseg, partial);
-    rc = cuda_status(cudaGetLastError(), "ps_lml_partial_kernel launch");
-    if (rc) return rc;
-    const int64_t threads = a.B * 32;
-    ps_lml_final_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(partial, a.B, nseg, a.lml);
-    rc = cuda_status(cudaGetLastError(), "ps_lml_final_kernel launch");
+    // scratch for the partial sums: the scan buffer that does NOT hold the prefixes (both are free once the boundaries
+    // exist, but the caller of a time-sharded pass may still read the prefixes)
+    double* other = (nchunk > 1 && ps_scan_result(w, had_total ? nchunk : nchunk - 1) == w.e1) ? w.e0 : w.e1;
+    rc = ps_lml_sum(st, a.lml_k, a.B, a.T, a.sbs, a.sts, w.lml_partial, other, a.B * nchunk * ps_filter_elem(d), a.lml);
     if (rc) return rc;
   }
   if (status_out) {
@@ -1710,13 +1754,7 @@ int pscan_filter_spec(cudaStream_t st, int d, int m, int disc_mode, int nblk, bo
     a.fixup = 0;
   }
   {
-    const int64_t seg = ps_lml_seg(a.T), nseg = ps_lml_nseg(a.T);
-    ps_lml_partial_kernel<<<(unsigned)(nseg * a.B), 256, 0, st>>>(a.lml_k, a.T, a.sbs, a.sts, seg, nseg, w.lml_partial);
-    rc = cuda_status(cudaGetLastError(), "ps_lml_partial_kernel launch");
-    if (rc) return rc;
-    const int64_t threads = a.B * 32;
-    ps_lml_final_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(w.lml_partial, a.B, nseg, a.lml);
-    rc = cuda_status(cudaGetLastError(), "ps_lml_final_kernel launch");
+    rc = ps_lml_sum(st, a.lml_k, a.B, a.T, a.sbs, a.sts, w.lml_partial, w.e0, a.B * nchunk * ps_filter_elem(d), a.lml);
     if (rc) return rc;
   }
   if (status_out) {
