@@ -492,6 +492,13 @@ int physs_spatial_conditional_f64(void* stream, int64_t T, int32_t M, int32_t N,
                                   const double* ktt, const double* m, const double* P, double jitter,
                                   int32_t diagonal, void* ws, int64_t ws_bytes, double* mu, double* var);
 
+/* Per-series sums over the time axis: out[b] = sum_k (x[b, k] - sub[b, k]) for a [B, T] array with element strides
+ * (bstride, tstride) -- either step layout; sub may be NULL.  The ELL sums of `elbo` (elbos.py:163-194: `np.sum` of the
+ * per-block expected log-likelihoods, data minus surrogate) in two deterministic stages, coalesced in the time-major
+ * layout.  scratch: B * ceil(T / 512) doubles. */
+int physs_sum_steps_f64(void* stream, int64_t B, int64_t T, int64_t bstride, int64_t tstride, const double* x,
+                        const double* sub, double* scratch, double* out);
+
 /* FP64 FMA throughput probe (measurement aid for the FP64-pipe roofline; no reference counterpart).
  * Launches blocks x 256 threads doing iters x 8 independent FMAs each: flops = blocks*256*iters*16. */
 int physs_fp64_probe(void* stream, int32_t blocks, int64_t iters, double* out);

@@ -75,6 +75,7 @@ SIGNATURES = {
     "physs_cvi_natgrad_big_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i32, _c_f64, _c_f64,
                                                  _ptr, _c_i64, _ptr, _ptr]),
     "physs_cvi_ell_sur_big_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64, _ptr]),
+    "physs_sum_steps_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i64, _c_i64, _c_i64, _ptr, _ptr, _ptr, _ptr]),
     "physs_spatial_conditional_ws_bytes": (_c_i64, [_c_i32, _c_i32]),
     "physs_spatial_conditional_f64": (ctypes.c_int, [_ptr, _c_i64, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _c_f64,
                                                      _c_i32, _ptr, _c_i64, _ptr, _ptr]),

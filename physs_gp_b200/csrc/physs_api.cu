@@ -268,6 +268,13 @@ int physs_rts_smooth_f64(SMOOTH_PARAMS, double* ms, double* Ps) {
   return run_smooth_any((cudaStream_t)stream, d, Hout ? mo : 0, disc_mode, nblk, a);
 }
 
+int physs_sum_steps_f64(void* stream, int64_t B, int64_t T, int64_t bstride, int64_t tstride, const double* x,
+                        const double* sub, double* scratch, double* out) {
+  if (B < 0 || T < 0) return set_error(PHYSS_ERR_BAD_ARG, "sum over steps: bad sizes");
+  if (B > 0 && T > 0 && (!x || !scratch || !out)) return set_error(PHYSS_ERR_BAD_ARG, "sum over steps: null pointer");
+  return sum_steps((cudaStream_t)stream, B, T, bstride, tstride, x, sub, scratch, out);
+}
+
 int64_t physs_pscan_workspace_bytes(int64_t B, int64_t T, int32_t d, int64_t chunk_len) {
   if (B < 1 || T < 1 || d < 1 || chunk_len < 1) return 0;
   return 8 * pscan_workspace_doubles(B, T, d, chunk_len);

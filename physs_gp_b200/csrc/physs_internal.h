@@ -150,6 +150,9 @@ int spd_inverse(cudaStream_t st, int64_t N, int D, const double* A, double jitte
 int64_t pscan_workspace_doubles(int64_t B, int64_t T, int d, int64_t chunk_len);
 int pscan_filter_local(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, SeqFilterArgs a,
                        int64_t chunk_len, double* ws, double* total_out);
+// physs_pscan.cu: out[b] = sum_k (x[b, k] - sub[b, k]) over a [B, T] array with strides (sbs, sts); sub may be NULL
+int sum_steps(cudaStream_t st, int64_t B, int64_t T, int64_t sbs, int64_t sts, const double* x, const double* sub,
+              double* scratch, double* out);
 int pscan_filter_finish(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool hid, SeqFilterArgs a,
                         int64_t chunk_len, double* ws, bool had_total, const double* start_m,
                         const double* start_P, int polish, double delta, int patience, int* status_out);

@@ -888,13 +888,14 @@ __global__ void ps_gather_bnd_next_kernel(const double* __restrict__ ms, const d
 // `seg` steps) -> partial[b, s]; then one warp per series over the partials.
 __global__ void __launch_bounds__(256) ps_lml_partial_kernel(const double* __restrict__ lml_k, int64_t T, int64_t sbs,
                                                              int64_t sts, int64_t seg, int64_t nseg,
-                                                             double* __restrict__ partial) {
+                                                             double* __restrict__ partial,
+                                                             const double* __restrict__ sub = nullptr) {
   __shared__ double red[8];
   // flat grid of B * nseg blocks (gridDim.y is capped at 65,535: B >= 65,536 series must not fail)
   const int64_t b = (int64_t)blockIdx.x / nseg, sg = (int64_t)blockIdx.x % nseg;
   const int64_t k0 = sg * seg, k1 = (k0 + seg < T) ? k0 + seg : T;
   double s = 0.0;
-  for (int64_t k = k0 + threadIdx.x; k < k1; k += 256) s += lml_k[b * sbs + k * sts];
+  for (int64_t k = k0 + threadIdx.x; k < k1; k += 256) s += lml_k[b * sbs + k * sts] - (sub ? sub[b * sbs + k * sts] : 0.0);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -909,7 +910,8 @@ __global__ void __launch_bounds__(256) ps_lml_partial_kernel(const double* __res
 // above reads one 8-byte word per 32-byte sector (ncu: 107 long-scoreboard stalls per issue, 1.9 TB/s of useful bytes).
 __global__ void __launch_bounds__(256) ps_lml_partial_tm_kernel(const double* __restrict__ lml_k, int64_t B, int64_t T,
                                                                 int64_t sts, int64_t seg, int64_t nseg,
-                                                                double* __restrict__ partial) {
+                                                                double* __restrict__ partial,
+                                                                const double* __restrict__ sub = nullptr) {
   __shared__ double red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t nb32 = (B + 31) / 32;
@@ -918,8 +920,16 @@ __global__ void __launch_bounds__(256) ps_lml_partial_tm_kernel(const double* __
   double s0 = 0.0, s1 = 0.0;
   if (b < B) {
     int64_t k = k0 + w;
-    for (; k + 8 < k1; k += 16) { s0 += lml_k[b + k * sts]; s1 += lml_k[b + (k + 8) * sts]; }
-    if (k < k1) s0 += lml_k[b + k * sts];
+    if (sub) {                   // sum of (x - sub): the ELBO's data ELL minus surrogate ELL
+      for (; k + 8 < k1; k += 16) {
+        s0 += lml_k[b + k * sts] - sub[b + k * sts];
+        s1 += lml_k[b + (k + 8) * sts] - sub[b + (k + 8) * sts];
+      }
+      if (k < k1) s0 += lml_k[b + k * sts] - sub[b + k * sts];
+    } else {
+      for (; k + 8 < k1; k += 16) { s0 += lml_k[b + k * sts]; s1 += lml_k[b + (k + 8) * sts]; }
+      if (k < k1) s0 += lml_k[b + k * sts];
+    }
   }
   red[w][lane] = s0 + s1;
   __syncthreads();
@@ -944,19 +954,19 @@ static inline int64_t ps_lml_nseg(int64_t T) { const int64_t sg = ps_lml_seg(T);
 // lml[b] = sum_k lml_k[b, k].  Time-major layout with a free scratch of `big_n` doubles: 512-step segments summed by
 // the coalesced kernel (enough blocks to fill the GPU), else 4096-step segments by the strided one into `small`.
 static int ps_lml_sum(cudaStream_t st, const double* lml_k, int64_t B, int64_t T, int64_t sbs, int64_t sts,
-                      double* small, double* big, int64_t big_n, double* lml) {
+                      double* small, double* big, int64_t big_n, double* lml, const double* sub = nullptr) {
   const int64_t seg_tm = 512, nseg_tm = (T + seg_tm - 1) / seg_tm;
   const double* partial;
   int64_t nseg;
   if (sbs == 1 && B >= 32 && big && B * nseg_tm <= big_n) {
     nseg = nseg_tm;
     partial = big;
-    ps_lml_partial_tm_kernel<<<(unsigned)(nseg * ((B + 31) / 32)), 256, 0, st>>>(lml_k, B, T, sts, seg_tm, nseg, big);
+    ps_lml_partial_tm_kernel<<<(unsigned)(nseg * ((B + 31) / 32)), 256, 0, st>>>(lml_k, B, T, sts, seg_tm, nseg, big, sub);
   } else {
     const int64_t seg = ps_lml_seg(T);
     nseg = ps_lml_nseg(T);
     partial = small;
-    ps_lml_partial_kernel<<<(unsigned)(nseg * B), 256, 0, st>>>(lml_k, T, sbs, sts, seg, nseg, small);
+    ps_lml_partial_kernel<<<(unsigned)(nseg * B), 256, 0, st>>>(lml_k, T, sbs, sts, seg, nseg, small, sub);
   }
   int rc = cuda_status(cudaGetLastError(), "ps_lml_partial_kernel launch");
   if (rc) return rc;
@@ -1697,6 +1707,14 @@ int pscan_filter_finish(cudaStream_t st, int d, int m, int disc_mode, int nblk, 
     if (e != cudaSuccess) return cuda_status(e, "pscan filter: status copy");
   }
   return PHYSS_OK;
+}
+
+// per-series sums over the time axis of a [B, T] array in either step layout (the ELBO's ELL sums); scratch:
+// B * ceil(T / 512) doubles
+int sum_steps(cudaStream_t st, int64_t B, int64_t T, int64_t sbs, int64_t sts, const double* x, const double* sub,
+              double* scratch, double* out) {
+  if (B <= 0 || T <= 0) return PHYSS_OK;
+  return ps_lml_sum(st, x, B, T, sbs, sts, scratch, scratch, B * ((T + 511) / 512), out, sub);
 }
 
 // ---------------------------------------------------------------------------------- speculative mode

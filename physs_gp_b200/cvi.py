@@ -522,10 +522,29 @@ class VGP:
             ell = expected_log_likelihood(q_mu, q_var, self.Y, self.W, self.lik, K=self.K)
         sur = GaussianLik(np.eye(q.block_size))
         ell_s = expected_log_likelihood(q_mu, q_var, q.Y_tilde, None, sur, noise=q.V_tilde)
-        return ell.sum(dim=-1) - ell_s.sum(dim=-1) + lml
+        return sum_steps(ell, ell_s) + lml
 
     def get_objective(self):
         return -self.elbo()
+
+
+def sum_steps(x, sub=None, stream=None):
+    """out[b] = sum_k (x[b, k] - sub[b, k]) for [B, T] device tensors in either step layout (`physs_sum_steps_f64`): the
+    ELL sums of the ELBO in one deterministic two-stage pass."""
+    if x.dim() != 2 or (sub is not None and (sub.shape != x.shape or sub.stride() != x.stride())):
+        return x.sum(dim=-1) - (0 if sub is None else sub.sum(dim=-1))
+    B, T = x.shape
+    sb, st_ = x.stride()
+    if not ((sb == T and st_ == 1) or (sb == 1 and st_ == B)):
+        return x.sum(dim=-1) - (0 if sub is None else sub.sum(dim=-1))
+    out = torch.empty((B,), dtype=torch.float64, device=x.device)
+    scratch = torch.empty((B * ((T + 511) // 512),), dtype=torch.float64, device=x.device)
+    s = stream if stream is not None else torch.cuda.current_stream()
+    with torch.cuda.device(x.device):
+        rc = _lib.load().physs_sum_steps_f64(s.cuda_stream, B, T, sb, st_, x.data_ptr(), _ptr(sub), scratch.data_ptr(),
+                                             out.data_ptr())
+    _lib.check(rc, "physs_sum_steps_f64")
+    return out
 
 
 class MeanFieldConjugateGaussian:
