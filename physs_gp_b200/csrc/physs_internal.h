@@ -41,6 +41,9 @@ struct SeqFilterArgs {
   double delta;
   const double* bnd_m; const double* bnd_P;
   int* unconverged;
+  // fix-up passes that change nothing are fixed points: a chunk whose recomputed step disagrees with the stored one sets
+  // *pass_changed; a pass whose predecessor left *prev_changed == 0 returns at once (register kernels, d <= 4)
+  int* pass_changed; const int* prev_changed;
 };
 
 // Outputs of the filter's reverse pass (physs_vjp.cu); any pointer may be NULL except the ones the mode needs.
@@ -93,6 +96,7 @@ int seq_filter_summary(cudaStream_t st, int d, int m, int disc_mode, int nblk, b
                        const SeqFilterArgs& a, double* elems);
 int seq_smooth_summary(cudaStream_t st, int d, int disc_mode, int nblk, const SeqSmoothArgs& a, double* elems);
 // size dispatch shared by the plain and the chunked entry points (physs_api.cu)
+bool run_filter_is_seq(int d, int m, int disc_mode, int nblk, int64_t B, int64_t nchunk);
 int run_filter_any(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool h_identity,
                    const SeqFilterArgs& a);
 int run_smooth_any(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a);

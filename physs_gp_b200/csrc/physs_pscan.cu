@@ -853,7 +853,9 @@ __global__ void ps_smooth_fold_kernel(const double* __restrict__ totals, int64_t
 // polish: boundary of chunk c (c >= 1) <- replayed filtered state at the last step of chunk c - 1
 __global__ void ps_gather_bnd_kernel(const double* __restrict__ mf, const double* __restrict__ Pf, int64_t B,
                                      int64_t nchunk, int64_t chunk_len, int64_t sbs, int64_t sts, int d,
-                                     double* __restrict__ bnd_m, double* __restrict__ bnd_P) {
+                                     double* __restrict__ bnd_m, double* __restrict__ bnd_P,
+                                     const int* __restrict__ prev_changed = nullptr) {
+  if (prev_changed && *prev_changed == 0) return;          // the previous fix-up pass changed nothing
   const int64_t n = B * nchunk * (int64_t)(d * d + d);
   const int per = d * d + d;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1680,20 +1682,26 @@ int pscan_filter_finish(cudaStream_t st, int d, int m, int disc_mode, int nblk, 
   if (rc) return rc;
   rc = replay(nfull, nchunk - nfull);
   if (rc) return rc;
+  // fix-up passes after a pass that changed nothing are no-ops: the register kernels flag a pass in which any recomputed
+  // step disagreed (w.flag[1 + parity]); the next pass and its boundary gather return at once when that flag is clear
+  const bool early_out = run_filter_is_seq(d, m, disc_mode, nblk, a.B, nchunk) && !getenv("PHYSS_PSCAN_NO_EARLY_OUT");
   for (int it = 0; it < polish && nchunk > 1; ++it) {
     const int64_t total = a.B * nchunk * (int64_t)(d * d + d);
     const int64_t want = (total + 255) / 256;
     const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
-    ps_gather_bnd_kernel<<<blocks, 256, 0, st>>>(a.mf, a.Pf, a.B, nchunk, chunk_len, a.sbs, a.sts, d, w.bnd_m, w.bnd_P);
+    int* cur = early_out ? w.flag + 1 + (it & 1) : nullptr;
+    const int* prev = (early_out && it > 0) ? w.flag + 1 + ((it + 1) & 1) : nullptr;
+    ps_gather_bnd_kernel<<<blocks, 256, 0, st>>>(a.mf, a.Pf, a.B, nchunk, chunk_len, a.sbs, a.sts, d, w.bnd_m, w.bnd_P, prev);
     rc = cuda_status(cudaGetLastError(), "ps_gather_bnd_kernel launch");
     if (rc) return rc;
     e = cudaMemsetAsync(w.flag, 0, sizeof(int), st);
+    if (e == cudaSuccess && cur) e = cudaMemsetAsync(cur, 0, sizeof(int), st);
     if (e != cudaSuccess) return cuda_status(e, "pscan filter: flag reset");
-    a.fixup = 1;
+    a.fixup = 1; a.pass_changed = cur; a.prev_changed = prev;
     rc = replay(1, nfull - 1);
     if (rc) return rc;
     if (nfull >= 1) { rc = replay(nfull, nchunk - nfull); if (rc) return rc; }
-    a.fixup = 0;
+    a.fixup = 0; a.pass_changed = nullptr; a.prev_changed = nullptr;
   }
   {
     // scratch for the partial sums: the scan buffer that does NOT hold the prefixes (both are free once the boundaries

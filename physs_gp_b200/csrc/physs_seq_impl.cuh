@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
   __shared__ __align__(16) double tiles[SeqBlock<D>::WARPS][RowTile<D * D>::SIZE];
   SeqWork wk;
   if (!seq_work<CHUNK>(p, wk)) return;
+  if (CHUNK && p.fixup && p.prev_changed && *p.prev_changed == 0) return;   // the previous pass was a fixed point
   constexpr int NB = D / S;
   const int64_t b = wk.b, v = wk.v, t0 = wk.t0, T = wk.T;
   const bool active = wk.active;
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
     acc.add(det, mahal, nobs);
     if (CHUNK && p.fixup && !done) {
       streak = agrees<D>(m, P, mfp + k * sts * D, Pfp + k * sts * D * D, p.delta) ? streak + 1 : 0;
+      if (streak == 0 && active && p.pass_changed) atomicOr(p.pass_changed, 1);
     }
     if (k < 0) continue;                                   // warm-up step: nothing is stored
     if (coal) {
