@@ -51,10 +51,11 @@ int run_filter_any(cudaStream_t st, int d, int m, int disc_mode, int nblk, bool 
   return grp_filter(st, d, m, disc_mode, nblk, h_identity, a);
 }
 
-// true when run_filter_any sends this shape to the register kernels (physs_seq*): the only family that implements the
-// pass_changed / prev_changed early-out of the fix-up passes
+// true when run_filter_any sends this shape to the register (physs_seq*) or register-tile (physs_rt*) kernels: the
+// families that implement the pass_changed / prev_changed early-out of the fix-up passes
 bool run_filter_is_seq(int d, int m, int disc_mode, int nblk, int64_t B, int64_t nchunk) {
-  return !force_grp(d) && prefer_seq(d, m, B, nchunk, false) && seq_supported(d, m, disc_mode, nblk);
+  if (!force_grp(d) && prefer_seq(d, m, B, nchunk, false) && seq_supported(d, m, disc_mode, nblk)) return true;
+  return m <= d && !force_grp(d) && rt_supported(d, m);          // the register-tile kernels implement it as well
 }
 
 int run_smooth_any(cudaStream_t st, int d, int mo, int disc_mode, int nblk, const SeqSmoothArgs& a) {

@@ -249,6 +249,7 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
   const int g_in_block = threadIdx.x / G;
   const RtWork wk = rt_work(p, (int64_t)blockIdx.x * gpb + g_in_block);
   const bool active = wk.active, chunked = wk.chunked;
+  if (p.fixup && p.prev_changed && *p.prev_changed == 0) return;   // the previous fix-up pass was a fixed point
   const int64_t bb = wk.b, vs = wk.v, t0 = wk.t0, T = wk.T;
   const int gl = lane<G>();
   double* sm = smem + (size_t)g_in_block * L.total;
@@ -449,6 +450,7 @@ __global__ void rt_filter_kernel(const SeqFilterArgs p, const RtLayout L, const 
     if (chunked && p.fixup) {          // warp-uniform: the comparison shuffles across the whole warp
       const bool ag = rt_agrees<G, DM>(mv_, P, d, mfp + k * sts * d, Pfp + k * sts * d * d, p.delta);
       if (!done) streak = ag ? streak + 1 : 0;
+      if (!done && !ag && active && gl == 0 && p.pass_changed) atomicOr(p.pass_changed, 1);
     }
     __syncwarp();
     if (active && !done) {
