@@ -331,10 +331,14 @@ static PcLayout pc_layout(int d) {
 // (A, b, C, J, eta)_out = left (x) right, filtering_operator of parallel_kalman_filter.py:178-220 with the
 // general solves of its default branch (:201-211) and force_symmetric on C, J (:216-219).
 // Operands in shared memory; the result overwrites the `j` slots (Aj, Cj, Jj, bj, ej).
-template <int G>
+// DC != 0: the state dimension as a compile-time constant (d = 6, 8, 12: the physics-informed shapes of config 3) --
+// the index divisions, loop bounds and row strides of the generic products and LU solves below then fold to constants
+// (the runtime-sized form spent 100 us on ONE 8 x 8 combine, 1.2 of the 10 ms of a 1M-step scan).  Same arithmetic in
+// the same order: bitwise equal to DC = 0.
+template <int G, int DC = 0>
 __device__ __forceinline__ void filter_combine(double* sm, const PcLayout& L) {
   const int gl = Lanes<G>::gl();
-  const int d = L.d, ld = L.ld;
+  const int d = DC ? DC : L.d, ld = DC ? ((DC % 2 == 0) ? DC + 2 : (DC | 1)) : L.ld;
   double* Ai = sm + L.Ai; double* Ci = sm + L.Ci; double* Ji = sm + L.Ji;
   double* Aj = sm + L.Aj; double* Cj = sm + L.Cj; double* Jj = sm + L.Jj;
   double* M1 = sm + L.M1; double* M1T = sm + L.M1T; double* X1 = sm + L.X1; double* X2 = sm + L.X2;
@@ -459,7 +463,7 @@ __device__ __forceinline__ void store_filter_elem(const double* sm, const PcLayo
 }
 
 // Hillis-Steele step: out[c] = in[c - stride] (x) in[c]  (identity on the left for c < stride)
-template <int G>
+template <int G, int DC = 0>
 __global__ void ps_filter_scan_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t B,
                                       int64_t nchunk, int64_t nsum, int64_t stride, const PcLayout L) {
   extern __shared__ __align__(16) double smem[];
@@ -478,7 +482,7 @@ __global__ void ps_filter_scan_kernel(const double* __restrict__ in, double* __r
   if (c >= stride) bytes += load_filter_elem<G>(sm, L, false, in + (b * nchunk + c - stride) * ne);
   else left_special<G>(sm, L, nullptr, nullptr);
   tma_finish<G>(sm, L.bar, bytes, parity);
-  filter_combine<G>(sm, L);
+  filter_combine<G, DC>(sm, L);
   if (active) store_filter_elem<G>(sm, L, out + (b * nchunk + c) * ne);
 }
 
@@ -1028,6 +1032,9 @@ static int run_filter_summary(cudaStream_t st, const SeqFilterArgs& a, const PsL
 template <int G>
 static int run_filter_scan(cudaStream_t st, const double* in, double* out, int64_t B, int64_t nchunk, int64_t nsum,
                            int64_t stride, const PcLayout& L) {
+  if (L.d == 8) PS_LAUNCH((ps_filter_scan_kernel<G, 8>), L, B * nsum, in, out, B, nchunk, nsum, stride, L);
+  if (L.d == 6) PS_LAUNCH((ps_filter_scan_kernel<G, 6>), L, B * nsum, in, out, B, nchunk, nsum, stride, L);
+  if (L.d == 12) PS_LAUNCH((ps_filter_scan_kernel<G, 12>), L, B * nsum, in, out, B, nchunk, nsum, stride, L);
   PS_LAUNCH((ps_filter_scan_kernel<G>), L, B * nsum, in, out, B, nchunk, nsum, stride, L);
 }
 // ---------------------------------------------------------------------------------------------------------
