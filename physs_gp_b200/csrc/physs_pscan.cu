@@ -1630,9 +1630,16 @@ int pscan_filter_local(cudaStream_t st, int d, int m, int disc_mode, int nblk, b
     rc = run_scan_fused<false>(st, d, w.e0, in, a.B, nchunk, nsum);
     if (rc) return rc;
   }
+  // few elements (one long series): a pass is as long as ONE combine, so every combine gets a whole warp
+  static const int scan_g = [] { const char* e = getenv("PHYSS_PSCAN_SCAN_G"); return e ? atoi(e) : 0; }();
+  const int Gscan = (scan_g == 8 || scan_g == 16 || scan_g == 32) ? scan_g : (a.B * nsum <= 148 * 64 ? 32 : G);
   for (int64_t stride = 1; !fused && stride < nsum; stride *= 2) {
-    rc = ps_reg_scan(d) ? run_filter_scan_reg(st, d, in, out, a.B, nchunk, nsum, stride)
-                        : PS_BY_G(run_filter_scan, st, in, out, a.B, nchunk, nsum, stride, Lc);
+    if (ps_reg_scan(d)) {
+      rc = run_filter_scan_reg(st, d, in, out, a.B, nchunk, nsum, stride);
+    } else {
+      const int G = Gscan;      // (shadows the group size of the summary kernels inside PS_BY_G)
+      rc = PS_BY_G(run_filter_scan, st, in, out, a.B, nchunk, nsum, stride, Lc);
+    }
     if (rc) return rc;
     double* t = in; in = out; out = t;
   }
