@@ -237,3 +237,44 @@ def test_host_api_recovers_from_unconverged_scan(cuda_device, monkeypatch):
     lml_o, mf_o, Pf_o, _ = ofilters.filter_sequential(oprior, t, Y, R, 1e-5)
     assert abs(float(lml) - lml_o) <= TOL * abs(lml_o)
     assert rel(kf['m'], mf_o) < TOL and rel(kf['P'], Pf_o) < TOL
+
+
+@pytest.mark.parametrize("B,T,d,m,time_major", [(40, 3000, 2, 1, True), (3, 4000, 4, 1, False), (2, 2500, 8, 8, False)])
+def test_fixup_early_out_is_bitwise_neutral(cuda_device, monkeypatch, B, T, d, m, time_major):
+    """Fix-up passes after a pass in which no recomputed step disagreed are skipped on the device (pass_changed /
+    prev_changed flags); the result must be bitwise the one of running all passes (PHYSS_PSCAN_NO_EARLY_OUT=1), for the
+    register kernels (d <= 4) and the register-tile kernels (d = 8), with jitter (the case that needs the passes)."""
+    from physs_gp_b200 import ops
+    dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s = _batch_problem(cuda_device, B, T, d, m, False, 40 + d, time_major)
+    outs = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("PHYSS_PSCAN_NO_EARLY_OUT", "1")
+        else:
+            monkeypatch.delenv("PHYSS_PSCAN_NO_EARLY_OUT", raising=False)
+        lml, mf, Pf, st = ops.pscan_filter(dt_f, Y, R, H, m0, P0, disc_f, chunk_len=100, jitter=1e-5, polish=6,
+                                           return_status=True)
+        torch.cuda.synchronize()
+        assert int(st.item()) == 0
+        outs.append((lml.clone(), mf.clone(), Pf.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_sum_steps_matches_torch(cuda_device):
+    """physs_sum_steps_f64 (the ELBO's per-series ELL sums) in both step layouts, with and without the subtracted
+    array, ragged sizes."""
+    from physs_gp_b200 import cvi
+    g = torch.Generator(device=cuda_device).manual_seed(5)
+    for B, T in ((1000, 3001), (37, 513), (1, 20000), (70, 1)):
+        x = torch.randn((B, T), dtype=torch.float64, device=cuda_device, generator=g)
+        y = torch.randn((B, T), dtype=torch.float64, device=cuda_device, generator=g)
+        for tm in (False, True):
+            xx = x.t().contiguous().t() if tm else x
+            yy = y.t().contiguous().t() if tm else y
+            ref = x.sum(-1)
+            got = cvi.sum_steps(xx)
+            assert float((got - ref).abs().max()) <= 1e-12 * max(1.0, float(ref.abs().max()))
+            got2 = cvi.sum_steps(xx, yy)
+            ref2 = (x - y).sum(-1)
+            assert float((got2 - ref2).abs().max()) <= 1e-12 * max(1.0, float(ref2.abs().max()))
