@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="c5: weak = --series per GPU (default); strong = --series in TOTAL, split over the ranks")
+    ap.add_argument("--no-post", action="store_true",
+                    help="skip the posterior-only (packed hand-over) timing beside the c5 d = 4 line")
     ap.add_argument("--no-sweep", action="store_true",
                     help="c5 default line: skip the d = 8 / 16 / 32 sweep and the CVI-step section")
     ap.add_argument("--cpu-sample-series", type=int, default=0, help="series in the CPU sample (0 = auto)")
@@ -608,6 +610,48 @@ def run_b200(a):
     e2e = None
     del out_full, out_tail
     torch.cuda.empty_cache()
+    # ---- the posterior-only call (filter_and_smooth(full_state=False): smoothed mean / variance of f + lml, no
+    # filtered output): packed hand-over in a workspace (physs_kf_filter_smooth_packed_f64) beside the two-output
+    # call, same inputs, device-timed.  Not part of `value` (which materialises all four full-state outputs).
+    post = None
+    if d == 4 and not a.no_post:
+        post = {}
+        k_post = max(2, min(a.steps, 5))
+        ws = None
+        for name in ("packed", "two_output"):
+            def call(i, s, n):
+                disc = ops.Disc.matern(nblk, lam[s:s + n], Pinf[s:s + n])
+                if name == "packed":
+                    return ops.kf_filter_smooth_packed(dt_f, dt_s, Ys[i], R, H, m0, Pinf[s:s + n], disc, Hout=H,
+                                                       jitter=1e-5, ws=ws)[0]
+                return ops.kf_filter_smooth(dt_f, dt_s, Ys[i], R, H, m0, Pinf[s:s + n], disc, Hout=H, jitter=1e-5)[0]
+            if name == "packed":
+                need = ops._lib.load().physs_kf_filter_smooth_packed_ws_bytes(sub, T, sub, d)
+                ws = torch.empty((int(need),), dtype=torch.uint8, device=dev)
+            for i, s in enumerate(starts):                                  # warm-up
+                call(i, s, min(sub, n_local - s))
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(k_post):
+                for i, s in enumerate(starts):
+                    lml_p = call(i, s, min(sub, n_local - s))
+            p1.record()
+            barrier()
+            ms_p = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ms_p, op=dist.ReduceOp.MAX)
+            assert torch.isfinite(lml_p).all()
+            rate = n_total * T * k_post / (float(ms_p.item()) * 1e-3)
+            # y, R, dt in + hand-over out and back + (mean, variance) out
+            bpss = 8 * (3 + 2 * (14 if name == "packed" else d * d + d) + 2)
+            post[name] = {"value": rate, "unit": "state-steps/s", "steps": k_post,
+                          "ms_per_step": float(ms_p.item()) / k_post, "bytes_per_state_step": bpss,
+                          "achieved_gbs": bpss * (rate / world) / 1e9, "frac": bpss * (rate / world) / 1e9 / peak}
+            ws = None
+            torch.cuda.empty_cache()
+        post["api"] = ("ops.kf_filter_smooth_packed vs ops.kf_filter_smooth(Hout=H): inputs resident in HBM, sub-batches "
+                       "of %d series, outputs = smoothed mean / variance of f [B, T] + lml [B]" % sub)
     if not a.no_e2e:
         e2e = run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys, numa)
 
@@ -649,6 +693,8 @@ def run_b200(a):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": launches,
         }
+        if post is not None:
+            line["posterior_only"] = post
         if sweep is not None:
             line["sweep"] = sweep
             line["cvi"] = cvi_sec

@@ -150,6 +150,40 @@ int physs_kf_filter_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_
                                const double* Hout, int32_t mo,
                                double* mf, double* Pf, double* lml, double* lml_k, double* ms, double* Ps);
 
+/* Filter + smoother in one call WITHOUT the filtered moments as an output: what `BASE_SDE_GP.filter_and_smooth`
+ * (models/sde_gp.py:212-302) needs when the caller only wants the smoothed (projected) posterior and the lml -- the
+ * reference's filter_loop (kalman_filter.py:487-547) still materialises every filtered (m, P) for smoother_loop
+ * (rts_smoother.py:194-219) to read back.  Here the hand-over stays in a caller-supplied workspace as packed rows
+ * [m (d) | upper triangle of P (d (d + 1) / 2)] (the update leaves P bitwise symmetric, so the smoother sees exactly
+ * the (m, P) the two-call path stores): 14 instead of 20 doubles per step each way at d = 4, i.e. 264 instead of
+ * 360 B per state-step with a projected scalar output.  Same arithmetic, operation for operation: lml and the
+ * full-state (ms, Ps) are BITWISE those of physs_kf_filter_smooth_f64; projected outputs agree to 1e-14 (two
+ * instantiations of one source, nvcc picks one contraction differently).
+ * Register kernels only: d = 2 or 4 (physs_kf_filter_smooth_packed_supported), time-major steps
+ * (step_bstride == 1, step_tstride >= B); anything else returns PHYSS_ERR_UNSUPPORTED and the caller takes the
+ * two-output call.  ws: device memory, 16-byte aligned, >= physs_kf_filter_smooth_packed_ws_bytes(...) bytes. */
+int physs_kf_filter_smooth_packed_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk);
+int64_t physs_kf_filter_smooth_packed_ws_bytes(int64_t B, int64_t T, int64_t step_tstride, int32_t d);
+int physs_kf_filter_smooth_packed_f64(void* stream, int64_t B, int64_t T, int64_t step_bstride, int64_t step_tstride,
+                                      int32_t d, int32_t m,
+                                      int32_t disc_mode, int32_t nblk,
+                                      const double* A, int64_t A_bstride,
+                                      const double* Q, int64_t Q_bstride,
+                                      const double* lam, int64_t lam_bstride,
+                                      const double* dt, int64_t dt_bstride,
+                                      const double* Pinf, int64_t Pinf_bstride,
+                                      const double* m0, int64_t m0_bstride,
+                                      const double* P0, int64_t P0_bstride,
+                                      const double* H, int64_t H_bstride,
+                                      const double* Y,
+                                      const double* R, int64_t R_bstride, int64_t R_tstride,
+                                      double jitter,
+                                      const double* A_smooth, const double* Q_smooth,
+                                      const double* dt_smooth, int64_t dt_smooth_bstride,
+                                      const double* Hout, int32_t mo,
+                                      void* ws, int64_t ws_bytes,
+                                      double* lml, double* lml_k, double* ms, double* Ps);
+
 /* Collocation (EKF) Kalman filter over B independent series: the state-space prior constrained by a point-wise
  * ODE / PDE residual at every step.  Replaces kf_predict_step(PDE, 'sequential') inside filter('sequential')
  * (computation/filters/kalman_filter.py:340-427, 439-485).  Per step: LTI predict; residual f = g(m_) and Jacobian

@@ -13,7 +13,7 @@ PHYSS_OK = 0
 DISC_GIVEN = 0
 DISC_MATERN = 1
 DISC_IWP = 2
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 _c_i32 = ctypes.c_int32
 _c_i64 = ctypes.c_int64
@@ -47,6 +47,10 @@ SIGNATURES = {
         _ptr, _ptr, _ptr, _c_i32, _c_f64, _ptr, _ptr]),
     "physs_kf_filter_smooth_f64": (ctypes.c_int, _FILTER_HEAD + [_ptr, _ptr, _ptr, _c_i64, _ptr, _c_i32,
                                                                 _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "physs_kf_filter_smooth_packed_supported": (ctypes.c_int, [_c_i32, _c_i32, _c_i32, _c_i32]),
+    "physs_kf_filter_smooth_packed_ws_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64, _c_i32]),
+    "physs_kf_filter_smooth_packed_f64": (ctypes.c_int, _FILTER_HEAD + [_ptr, _ptr, _ptr, _c_i64, _ptr, _c_i32,
+                                                                       _ptr, _c_i64, _ptr, _ptr, _ptr, _ptr]),
     "physs_kf_filter_colloc_f64": (ctypes.c_int, _FILTER_HEAD + [_c_i32, _ptr, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
                                                                 _ptr, _c_i32, _ptr, _ptr, _ptr, _ptr]),
     "physs_kf_vjp_supported": (ctypes.c_int, [_c_i32, _c_i32, _c_i32, _c_i32]),

@@ -85,7 +85,7 @@ static inline bool step_strides_ok(int64_t B, int64_t T, int64_t bs, int64_t ts)
 
 extern "C" {
 
-int physs_abi_version(void) { return 13; }
+int physs_abi_version(void) { return 14; }
 
 const char* physs_last_error(void) { return g_err; }
 
@@ -222,6 +222,48 @@ int physs_kf_filter_smooth_f64(FILTER_PARAMS, const double* A_smooth, const doub
                               disc_mode == PHYSS_DISC_GIVEN ? A_smooth : A, A_bstride,
                               disc_mode == PHYSS_DISC_GIVEN ? Q_smooth : Q, Q_bstride, lam, lam_bstride, dt_smooth,
                               dt_smooth_bstride, Pinf, Pinf_bstride, mf, Pf, Hout, mo, jitter, ms, Ps);
+}
+
+// rows of the packed hand-over buffer: [m | upper triangle of P], padded to an even count (PackedRow<D>::N)
+static inline int64_t packed_row_doubles(int32_t d) { return (d + d * (d + 1) / 2 + 1) & ~1; }
+
+int physs_kf_filter_smooth_packed_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {
+  return ((d == 2 || d == 4) && seq_supported(d, m, disc_mode, nblk)) ? 1 : 0;
+}
+
+int64_t physs_kf_filter_smooth_packed_ws_bytes(int64_t B, int64_t T, int64_t step_tstride, int32_t d) {
+  if (B < 0 || T < 1 || d < 1) return 0;
+  const int64_t ts = step_tstride > B ? step_tstride : B;
+  return ts * T * packed_row_doubles(d) * (int64_t)sizeof(double);
+}
+
+int physs_kf_filter_smooth_packed_f64(FILTER_PARAMS, const double* A_smooth, const double* Q_smooth,
+                                      const double* dt_smooth, int64_t dt_smooth_bstride, const double* Hout,
+                                      int32_t mo, void* ws, int64_t ws_bytes, double* lml, double* lml_k, double* ms,
+                                      double* Ps) {
+  if (!physs_kf_filter_smooth_packed_supported(d, m, disc_mode, nblk))
+    return set_error(PHYSS_ERR_UNSUPPORTED, "packed filter + smoother: register kernels with even d <= 4");
+  if (step_bstride != 1 || step_tstride < B)
+    return set_error(PHYSS_ERR_UNSUPPORTED, "packed filter + smoother: time-major steps (strides (1, >= B))");
+  if (!ws || misaligned(ws) || ws_bytes < physs_kf_filter_smooth_packed_ws_bytes(B, T, step_tstride, d))
+    return set_error(PHYSS_ERR_BAD_ARG, "packed filter + smoother: workspace missing, misaligned or too small");
+  if (!dt_smooth || !ms || !Ps) return set_error(PHYSS_ERR_BAD_ARG, "packed filter + smoother: null required pointer");
+  double* pk = static_cast<double*>(ws);
+  SeqFilterArgs f;
+  // pack_filter insists on (mf, Pf): the packed rows stand in for both (never written through these pointers)
+  int rc = pack_filter(FILTER_ARGS, pk, pk, lml, lml_k, f);
+  if (rc || B == 0) return rc;
+  f.mf = nullptr; f.Pf = nullptr; f.pk = pk;
+  rc = seq_filter((cudaStream_t)stream, d, m, disc_mode, nblk, H == nullptr, f);
+  if (rc) return rc;
+  SeqSmoothArgs s;
+  rc = pack_smooth(stream, B, T, step_bstride, step_tstride, d, disc_mode, nblk,
+                   disc_mode == PHYSS_DISC_GIVEN ? A_smooth : A, A_bstride,
+                   disc_mode == PHYSS_DISC_GIVEN ? Q_smooth : Q, Q_bstride, lam, lam_bstride, dt_smooth,
+                   dt_smooth_bstride, Pinf, Pinf_bstride, pk, pk, Hout, mo, jitter, ms, Ps, s);
+  if (rc) return rc;
+  s.mf = nullptr; s.Pf = nullptr; s.pk = pk;
+  return seq_smooth((cudaStream_t)stream, d, Hout ? mo : 0, disc_mode, nblk, s);
 }
 
 int physs_kf_filter_colloc_f64(FILTER_PARAMS, int32_t pc, const double* res_w, int32_t n_terms,

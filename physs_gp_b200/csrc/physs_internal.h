@@ -44,6 +44,10 @@ struct SeqFilterArgs {
   // fix-up passes that change nothing are fixed points: a chunk whose recomputed step disagrees with the stored one sets
   // *pass_changed; a pass whose predecessor left *prev_changed == 0 returns at once (register kernels, d <= 4)
   int* pass_changed; const int* prev_changed;
+  // packed hand-over (physs_kf_filter_smooth_packed_f64; register kernels, even d <= 4, time-major steps, plain
+  // mode): when set, the filtered moments go to pk as rows of PackedRow<D>::N doubles [m | upper triangle of P]
+  // instead of (mf, Pf) -- the update leaves P bitwise symmetric, so nothing is lost
+  double* pk;
 };
 
 // Outputs of the filter's reverse pass (physs_vjp.cu); any pointer may be NULL except the ones the mode needs.
@@ -85,6 +89,7 @@ struct SeqSmoothArgs {
   // host-side query (physs_kf_wave_series): when set, the launcher writes the number of series one full wave
   // of its kernel keeps resident on the device and returns WITHOUT launching
   int64_t* wave_out;
+  const double* pk;      // packed filtered moments (see SeqFilterArgs::pk) read INSTEAD of (mf, Pf)
 };
 
 // physs_seq.cu: one thread per series, registers (d in {1,2,3,4,6,8})

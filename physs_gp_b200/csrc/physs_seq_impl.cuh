@@ -95,9 +95,11 @@ __device__ __forceinline__ void iwp_trans(const double (&var)[D / S], double dt,
 // ------------------------------------------------------------------- warp-cooperative row transfer
 // Rows of N doubles owned one per lane, 32 consecutive series contiguous in global memory (sbs == 1).
 // LD = padded row length of the shared-memory tile.
+// Even N moves 16-byte pieces: a quarter warp (8 lanes) is conflict-free when the row stride is an ODD number of
+// 16-byte units, i.e. LD / 2 odd -- N itself when N / 2 is odd (N = 2, 6, 10, 14: the packed rows), else N + 2.
 template <int N>
 struct RowTile {
-  static constexpr int LD = (N % 2 == 0) ? N + 2 : N;
+  static constexpr int LD = (N % 2 == 0) ? (((N / 2) % 2 == 1) ? N : N + 2) : N;
   static constexpr int SIZE = 32 * LD;
 };
 
@@ -199,6 +201,46 @@ __device__ __forceinline__ const double (&flat(const double (&P)[D][D]))[D * D] 
   return *reinterpret_cast<const double (*)[D * D]>(&P[0][0]);
 }
 
+// Packed hand-over row of the fused filter + smoother call: [m (D) | upper triangle of P, row-major (D (D + 1) / 2)]
+// padded to an even number of doubles (16-byte pieces).  The filter's update mirrors P, so the row carries all of it.
+template <int D>
+struct PackedRow {
+  static constexpr int N = (D + D * (D + 1) / 2 + 1) & ~1;
+};
+template <int D>
+__device__ __forceinline__ void pack_row(const double (&m)[D], const double (&P)[D][D], double (&row)[PackedRow<D>::N]) {
+  int n = 0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) row[n++] = m[i];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = i; j < D; ++j) row[n++] = P[i][j];
+  }
+#pragma unroll
+  for (int i = D + D * (D + 1) / 2; i < PackedRow<D>::N; ++i) row[i] = 0.0;
+}
+template <int D>
+__device__ __forceinline__ void unpack_row(const double (&row)[PackedRow<D>::N], double (&m)[D], double (&P)[D][D]) {
+  int n = 0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) m[i] = row[n++];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = i; j < D; ++j) {
+      P[i][j] = row[n];
+      P[j][i] = row[n++];
+    }
+  }
+}
+// the filter's transpose tile holds the larger of a P row and a packed row
+template <int D>
+struct SeqTile {
+  static constexpr int SIZE = (RowTile<D * D>::SIZE > RowTile<PackedRow<D>::N>::SIZE) ? RowTile<D * D>::SIZE
+                                                                                       : RowTile<PackedRow<D>::N>::SIZE;
+};
+
 // warps per block: the row tile of the largest per-step block must fit the 48 KB static shared memory
 template <int D>
 struct SeqBlock {
@@ -258,7 +300,7 @@ __device__ __forceinline__ bool agrees(const double (&m)[D], const double (&P)[D
 
 template <int D, int S, int M, bool HID, int GIVEN, bool CHUNK>
 __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const SeqFilterArgs p) {
-  __shared__ __align__(16) double tiles[SeqBlock<D>::WARPS][RowTile<D * D>::SIZE];
+  __shared__ __align__(16) double tiles[SeqBlock<D>::WARPS][SeqTile<D>::SIZE];
   SeqWork wk;
   if (!seq_work<CHUNK>(p, wk)) return;
   if (CHUNK && p.fixup && p.prev_changed && *p.prev_changed == 0) return;   // the previous pass was a fixed point
@@ -361,7 +403,13 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
       if (streak == 0 && active && p.pass_changed) atomicOr(p.pass_changed, 1);
     }
     if (k < 0) continue;                                   // warm-up step: nothing is stored
-    if (coal) {
+    if (!CHUNK && D % 2 == 0 && D <= 4 && coal && p.pk) {
+      // packed hand-over to the smoother of the same call: one row [m | triu(P)] per series-step
+      constexpr int NP = PackedRow<D>::N;
+      double row[NP];
+      pack_row<D>(m, P, row);
+      warp_store_rows<NP>(p.pk + (wrow0 + k * sts) * NP, row, tile, lane, wk.nvalid);
+    } else if (coal) {
       // converged lanes keep rewriting what is already stored to `delta`; the warp leaves together
       warp_store_rows<D>(mfw + k * sts * D, m, tile, lane, wk.nvalid);
       warp_store_rows<D * D>(Pfw + k * sts * D * D, flat<D>(P), tile, lane, wk.nvalid);
@@ -613,7 +661,9 @@ struct SeqPipe {
   static constexpr size_t smem_bytes(int warps) { return (size_t)warps * PER_WARP * sizeof(double); }
 };
 
-template <int D, int S, int MO, int GIVEN>
+// PACK: the filtered moments come as packed rows [m | triu(P)] (SeqSmoothArgs::pk, written by the filter of the same
+// physs_kf_filter_smooth_packed_f64 call) -- one ring tile of PackedRow<D>::N doubles per stage instead of two.
+template <int D, int S, int MO, int GIVEN, bool PACK = false>
 __global__ void __launch_bounds__(128) seq_smooth_pipe_kernel(const SeqSmoothArgs p) {
   extern __shared__ __align__(16) double pipe_smem[];
   SeqWork wk;
@@ -650,6 +700,9 @@ __global__ void __launch_bounds__(128) seq_smooth_pipe_kernel(const SeqSmoothArg
   const double* __restrict__ Pfp = p.Pf + row0 * D * D;
   const double* __restrict__ mfw = p.mf + wrow0 * D;
   const double* __restrict__ Pfw = p.Pf + wrow0 * D * D;
+  constexpr int NP = PackedRow<D>::N;
+  const double* __restrict__ pkp = PACK ? p.pk + row0 * NP : nullptr;
+  const double* __restrict__ pkw = PACK ? p.pk + wrow0 * NP : nullptr;
   double* __restrict__ msp = p.ms + row0 * MP;
   double* __restrict__ Psp = p.Ps + row0 * MP * MP;
   double* __restrict__ msw = p.ms + wrow0 * MP;
@@ -694,15 +747,28 @@ __global__ void __launch_bounds__(128) seq_smooth_pipe_kernel(const SeqSmoothArg
   auto stage_of = [&](int64_t k) { return ring + (int)(k % NST) * SeqPipe<D>::STAGE; };
   auto issue = [&](int64_t k) {
     double* st = stage_of(k);
-    warp_rows_async<D>(mfw + k * sts * D, st, lane, wk.nvalid);
-    warp_rows_async<D * D>(Pfw + k * sts * D * D, st + RowTile<D>::SIZE, lane, wk.nvalid);
+    if constexpr (PACK) {
+      warp_rows_async<NP>(pkw + k * sts * NP, st, lane, wk.nvalid);
+    } else {
+      warp_rows_async<D>(mfw + k * sts * D, st, lane, wk.nvalid);
+      warp_rows_async<D * D>(Pfw + k * sts * D * D, st + RowTile<D>::SIZE, lane, wk.nvalid);
+    }
     seq_cp_async_commit();
   };
+  // this lane's filtered moments of a landed stage
+  auto own = [&](const double* st, double (&mf)[D], double (&Pf)[D][D]) {
+    if constexpr (PACK) {
+      double row[NP];
+      tile_own_row<NP>(st, lane, row);
+      unpack_row<D>(row, mf, Pf);
+    } else {
+      tile_own_row<D>(st, lane, mf);
+      tile_own_row<D * D>(st + RowTile<D>::SIZE, lane, flat<D>(Pf));
+    }
+  };
   auto front = [&](int64_t k, double dt, double (&mp)[D], double (&Pp)[D][D], double (&G)[D][D]) {
-    const double* st = stage_of(k);
     double mf[D], Pf[D][D];
-    tile_own_row<D>(st, lane, mf);
-    tile_own_row<D * D>(st + RowTile<D>::SIZE, lane, flat<D>(Pf));
+    own(stage_of(k), mf, Pf);
     Trans<D, S> A;
     if constexpr (GIVEN == 1) {
       double Q[D][D];
@@ -720,17 +786,21 @@ __global__ void __launch_bounds__(128) seq_smooth_pipe_kernel(const SeqSmoothArg
   };
   auto back = [&](int64_t k, const double (&mp)[D], const double (&Pp)[D][D], const double (&G)[D][D],
                   double (&ms)[D], double (&Ps)[D][D]) {
-    const double* st = stage_of(k);
     double mf[D], Pf[D][D];
-    tile_own_row<D>(st, lane, mf);
-    tile_own_row<D * D>(st + RowTile<D>::SIZE, lane, flat<D>(Pf));
+    own(stage_of(k), mf, Pf);
     rts_back<D>(mf, Pf, mp, Pp, G, ms, Ps);
   };
 
   // terminal step: smoothed = filtered
   double ms[D], Ps[D][D];
-  load_vec<D>(mfp + (T - 1) * sts * D, ms);
-  load_mat<D>(Pfp + (T - 1) * sts * D * D, Ps);
+  if constexpr (PACK) {
+    double row[NP];
+    load_vec<NP>(pkp + (T - 1) * sts * NP, row);
+    unpack_row<D>(row, ms, Ps);
+  } else {
+    load_vec<D>(mfp + (T - 1) * sts * D, ms);
+    load_mat<D>(Pfp + (T - 1) * sts * D * D, Ps);
+  }
   emit(T - 1, ms, Ps);
   if (T < 2) return;
   // prologue: front(T - 2)
@@ -1027,9 +1097,26 @@ static int launch_smooth(cudaStream_t st, const SeqSmoothArgs& a) {
   const int block = pick_block(n) < SeqBlock<D>::THREADS ? pick_block(n) : SeqBlock<D>::THREADS;
   const int64_t grid = (n + block - 1) / block;
   const bool coal = (a.sbs == 1);
+  if constexpr (D % 2 == 0 && D <= 4) {
+    if (a.pk && coal && a.nchunk == 0) {
+      // packed hand-over from the filter of the same call (same launch shape as the unpacked pipe kernel below)
+      auto kern = seq_smooth_pipe_kernel<D, S, MO, GIVEN, true>;
+      const size_t smem = SeqPipe<D>::smem_bytes(1);
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return cuda_status(e, "seq_smooth_pipe_kernel (packed): configuration");
+        configured = true;
+      }
+      kern<<<(unsigned)(n / 32), 32, smem, st>>>(a);
+      return cuda_status(cudaGetLastError(), "seq_smooth_pipe_kernel (packed) launch");
+    }
+  }
   if constexpr (D % 2 == 0) {
     static const bool no_pipe = [] { const char* e = getenv("PHYSS_SEQ_NOPIPE"); return e && e[0] == '1'; }();
-    if (coal && a.nchunk == 0 && !no_pipe) {
+    if (!a.pk && coal && a.nchunk == 0 && !no_pipe) {
       // one warp per block: the block scheduler spreads the (few) warps of a batch evenly over the SMs
       auto kern = seq_smooth_pipe_kernel<D, S, MO, GIVEN>;
       const size_t smem = SeqPipe<D>::smem_bytes(1);
@@ -1045,6 +1132,7 @@ static int launch_smooth(cudaStream_t st, const SeqSmoothArgs& a) {
       return cuda_status(cudaGetLastError(), "seq_smooth_pipe_kernel launch");
     }
   }
+  if (a.pk) return set_error(PHYSS_ERR_UNSUPPORTED, "packed hand-over: even d <= 4, time-major steps, plain mode");
   if (a.nchunk > 0) {
     if (MO != 0 && a.fixup) return set_error(PHYSS_ERR_BAD_ARG, "smoother fix-up needs full_state output");
     if (coal) seq_smooth_kernel<D, S, MO, GIVEN, true, true><<<(unsigned)grid, block, 0, st>>>(a);

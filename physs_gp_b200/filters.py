@@ -389,6 +389,52 @@ def smoother_loop(data, model, filter_res, full_state=False, filter_type='b200')
     return smoother_fn(data, model, filter_res, dt, X_t, X_s, full_state)
 
 
+def filter_smooth_fused(data, prior, R=None, R_inv=None, filter_type='b200'):
+    """`filter_loop` + `smoother_loop(full_state=False)` (sde_gp.py:231-253) as ONE C-ABI call that never
+    materialises the filtered moments (`physs_kf_filter_smooth_packed_f64`): the hand-over between the two passes
+    is a workspace of packed rows [m | triu(P)].  Returns (lml, mu, var) -- what the two loops return (lml bitwise,
+    the projected moments to 1e-14) -- or None when the problem is outside what the packed call covers (sequential register kernels, state dim 2 or 4,
+    a time-major batch, covariance-parameterised noise); the caller then takes the two loops."""
+    if not settings.fused_packed or R_inv is not None or R is None or isinstance(prior, PDE):
+        return None
+    X_s = data.X_space
+    d = prior.d if isinstance(prior, BatchedMaternSDE) else np.asarray(prior.P_inf(None, X_s, None)).shape[0]
+    if d not in (2, 4):
+        return None
+    dev = _device()
+    X_t = _time_axis(data, dev)
+    Y = _to_dev(data.Y_st, dev)
+    Y = Y.reshape(*Y.shape[:-2], -1)                  # [..., Nt, P*Ns]
+    batched = Y.dim() == 3 or isinstance(prior, BatchedMaternSDE)
+    if not batched:
+        return None                                   # one series: nothing to coalesce over
+    if filter_type == 'b200_auto':
+        Bq = Y.shape[0] if Y.dim() == 3 else prior.B
+        if _auto_parallel(Bq, Y.shape[-2]):
+            return None
+    elif filter_type != 'b200':
+        return None
+    if Y.dim() == 2:
+        Y = Y[None]
+    if isinstance(prior, BatchedMaternSDE) and Y.shape[0] == 1 and prior.B > 1:
+        Y = Y.expand(prior.B, -1, -1)
+    if not (settings.time_major and Y.shape[0] >= settings.time_major_min_batch):
+        return None
+    if not ops.step_layout(Y, "Y")[1]:
+        Y = Y.transpose(0, 1).contiguous().transpose(0, 1)
+    zero = torch.zeros(1, dtype=torch.float64, device=dev)
+    diff = X_t[1:] - X_t[:-1]
+    dt_f, dt_s = torch.cat([zero, diff]), torch.cat([diff, zero])
+    (disc_f, disc_s), m0, P0, H = lower_prior(prior, X_s, [dt_f, dt_s], dev, sequential=True)
+    if not ops.kf_filter_smooth_packed_supported(Y, d, Y.shape[-1], disc_f):
+        return None
+    ident = _is_identity(H)
+    Hd = None if ident else _to_dev(H, dev)
+    lml, ms, Ps = ops.kf_filter_smooth_packed(dt_f, dt_s, Y, _to_dev(R, dev), Hd, m0, P0, disc_f, disc_s, Hout=Hd,
+                                              jitter=settings.jitter)
+    return lml, ms[..., None], Ps
+
+
 @dispatch('b200_auto')
 def smoother(data, model, filter_res, dt, X_t, X_s, full_state):  # noqa: F811
     mf = filter_res['m']

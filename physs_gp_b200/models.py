@@ -48,6 +48,11 @@ class SDE_GP:
 
     def filter_and_smooth(self, full_state=False, return_lml=False):
         R, R_inv = self._R()
+        if not full_state:
+            # nobody reads the filtered moments: one call, packed hand-over (None = outside what it covers)
+            fused = filters.filter_smooth_fused(self.data, self.prior, R=R, R_inv=R_inv, filter_type=self.filter_type)
+            if fused is not None:
+                return fused if return_lml else fused[1:]
         lml, kf = filters.filter_loop(self.data, self.prior, R=R, R_inv=R_inv, filter_type=self.filter_type)
         mu, var = filters.smoother_loop(self.data, self.prior, kf, full_state=full_state,
                                         filter_type=self.filter_type)

@@ -307,6 +307,54 @@ def kf_filter_smooth(dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s=None, Hout=None
     return lml, mf, Pf, ms, Ps
 
 
+def kf_filter_smooth_packed_supported(Y, d, m, disc):
+    """True when `kf_filter_smooth_packed` covers this problem: register kernels with d = 2 or 4 and Y [B, T, m]
+    time-major (a transposed view of a contiguous [T, B, m] tensor)."""
+    lib = _lib.load()
+    if Y.dim() != 3 or not lib.physs_kf_filter_smooth_packed_supported(d, m, disc.mode, disc.nblk):
+        return False
+    return bool(step_layout(Y, "Y")[1])
+
+
+def kf_filter_smooth_packed(dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s=None, Hout=None, jitter=None, ws=None,
+                            stream=None):
+    """Filter + smoother in ONE C-ABI call that never writes the filtered moments as an output
+    (physs_kf_filter_smooth_packed_f64): the hand-over between the two passes is a workspace of packed rows
+    [m | triu(P)].  Same arguments as `kf_filter_smooth`; returns (lml, ms, Ps): lml and full-state (ms, Ps) bitwise
+    what `kf_filter_smooth` returns, projected outputs to 1e-14.  `ws`: optional caller-kept uint8 workspace (reused across calls when large enough)."""
+    lib = _lib.load()
+    p = _pack_filter(dt_f, Y, R, H, m0, P0, disc_f, jitter, stream)
+    B, T, d = p.B, p.T, p.d
+    if not p.tmaj:
+        raise NotImplementedError("kf_filter_smooth_packed: time-major steps only (see kf_filter_smooth_packed_supported)")
+    dtv, sdt = _bview(dt_s, "dt_s", (B, T), 1)
+    pA = pQ = None
+    keep = []
+    if disc_f.mode == _lib.DISC_GIVEN:
+        if disc_s is None:
+            raise ValueError("DISC_GIVEN needs disc_s (the smoother's transitions)")
+        keep, (pA, bA), (pQ, bQ), _, _ = _disc_args(disc_s, B, T, d)
+        if (bA, bQ) != (p.head[10], p.head[12]):
+            raise ValueError("disc_f and disc_s must share their batch layout")
+    if Hout is None:
+        mo, Hptr, mp = 0, None, d
+    else:
+        Hout = _dev(Hout, "Hout").contiguous()
+        mo, Hptr, mp = Hout.shape[0], Hout.data_ptr(), Hout.shape[0]
+    need = int(lib.physs_kf_filter_smooth_packed_ws_bytes(B, T, p.head[4], d))
+    if ws is None or ws.numel() < need or ws.device != p.dev:
+        ws = torch.empty((need,), dtype=torch.uint8, device=p.dev)
+    lml = torch.empty((B,), dtype=torch.float64, device=p.dev)
+    ms = empty_steps(B, T, (mp,), p.dev, True)
+    Ps = empty_steps(B, T, (mp, mp), p.dev, True)
+    with torch.cuda.device(p.dev):
+        st = lib.physs_kf_filter_smooth_packed_f64(*p.head, pA, pQ, dtv.data_ptr(), sdt[0], Hptr, mo, ws.data_ptr(),
+                                                   ws.numel(), lml.data_ptr(), None, ms.data_ptr(), Ps.data_ptr())
+    _lib.check(st, "physs_kf_filter_smooth_packed_f64")
+    del keep
+    return lml, ms, Ps
+
+
 def kf_filter_vjp(dt, Y, R, H, m0, P0, disc, mf, Pf, g_lml=None, jitter=None, want_R_step=False, stream=None):
     """Reverse pass of `kf_filter`'s lml (include/physs_b200.h: physs_kf_filter_vjp_f64): gradients of
     sum_b g_lml[b] * lml[b] with respect to the filter's inputs, given its outputs (mf, Pf).
