@@ -159,7 +159,7 @@ int physs_kf_filter_smooth_f64(void* stream, int64_t B, int64_t T, int64_t step_
  * 360 B per state-step with a projected scalar output.  Same arithmetic, operation for operation: lml and the
  * full-state (ms, Ps) are BITWISE those of physs_kf_filter_smooth_f64; projected outputs agree to 1e-14 (two
  * instantiations of one source, nvcc picks one contraction differently).
- * Register kernels only: d = 2 or 4 (physs_kf_filter_smooth_packed_supported), time-major steps
+ * Register kernels only: d <= 4 (physs_kf_filter_smooth_packed_supported), time-major steps
  * (step_bstride == 1, step_tstride >= B); anything else returns PHYSS_ERR_UNSUPPORTED and the caller takes the
  * two-output call.  ws: device memory, 16-byte aligned, >= physs_kf_filter_smooth_packed_ws_bytes(...) bytes. */
 int physs_kf_filter_smooth_packed_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk);

@@ -228,7 +228,7 @@ int physs_kf_filter_smooth_f64(FILTER_PARAMS, const double* A_smooth, const doub
 static inline int64_t packed_row_doubles(int32_t d) { return (d + d * (d + 1) / 2 + 1) & ~1; }
 
 int physs_kf_filter_smooth_packed_supported(int32_t d, int32_t m, int32_t disc_mode, int32_t nblk) {
-  return ((d == 2 || d == 4) && seq_supported(d, m, disc_mode, nblk)) ? 1 : 0;
+  return (d >= 1 && d <= 4 && seq_supported(d, m, disc_mode, nblk)) ? 1 : 0;
 }
 
 int64_t physs_kf_filter_smooth_packed_ws_bytes(int64_t B, int64_t T, int64_t step_tstride, int32_t d) {
@@ -242,7 +242,7 @@ int physs_kf_filter_smooth_packed_f64(FILTER_PARAMS, const double* A_smooth, con
                                       int32_t mo, void* ws, int64_t ws_bytes, double* lml, double* lml_k, double* ms,
                                       double* Ps) {
   if (!physs_kf_filter_smooth_packed_supported(d, m, disc_mode, nblk))
-    return set_error(PHYSS_ERR_UNSUPPORTED, "packed filter + smoother: register kernels with even d <= 4");
+    return set_error(PHYSS_ERR_UNSUPPORTED, "packed filter + smoother: register kernels, d <= 4");
   if (step_bstride != 1 || step_tstride < B)
     return set_error(PHYSS_ERR_UNSUPPORTED, "packed filter + smoother: time-major steps (strides (1, >= B))");
   if (!ws || misaligned(ws) || ws_bytes < physs_kf_filter_smooth_packed_ws_bytes(B, T, step_tstride, d))

@@ -44,7 +44,7 @@ struct SeqFilterArgs {
   // fix-up passes that change nothing are fixed points: a chunk whose recomputed step disagrees with the stored one sets
   // *pass_changed; a pass whose predecessor left *prev_changed == 0 returns at once (register kernels, d <= 4)
   int* pass_changed; const int* prev_changed;
-  // packed hand-over (physs_kf_filter_smooth_packed_f64; register kernels, even d <= 4, time-major steps, plain
+  // packed hand-over (physs_kf_filter_smooth_packed_f64; register kernels, d <= 4, time-major steps, plain
   // mode): when set, the filtered moments go to pk as rows of PackedRow<D>::N doubles [m | upper triangle of P]
   // instead of (mf, Pf) -- the update leaves P bitwise symmetric, so nothing is lost
   double* pk;

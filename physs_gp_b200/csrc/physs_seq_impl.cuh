@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
       if (streak == 0 && active && p.pass_changed) atomicOr(p.pass_changed, 1);
     }
     if (k < 0) continue;                                   // warm-up step: nothing is stored
-    if (!CHUNK && D % 2 == 0 && D <= 4 && coal && p.pk) {
+    if (!CHUNK && D <= 4 && coal && p.pk) {
       // packed hand-over to the smoother of the same call: one row [m | triu(P)] per series-step
       constexpr int NP = PackedRow<D>::N;
       double row[NP];
@@ -1097,7 +1097,9 @@ static int launch_smooth(cudaStream_t st, const SeqSmoothArgs& a) {
   const int block = pick_block(n) < SeqBlock<D>::THREADS ? pick_block(n) : SeqBlock<D>::THREADS;
   const int64_t grid = (n + block - 1) / block;
   const bool coal = (a.sbs == 1);
-  if constexpr (D % 2 == 0 && D <= 4) {
+  if constexpr (D <= 4) {
+    // (odd d as well: the packed row has an even number of doubles, so the 16-byte ring works where the (m, P) rows
+    //  of d = 1, 3 do not)
     if (a.pk && coal && a.nchunk == 0) {
       // packed hand-over from the filter of the same call (same launch shape as the unpacked pipe kernel below)
       auto kern = seq_smooth_pipe_kernel<D, S, MO, GIVEN, true>;
@@ -1132,7 +1134,7 @@ static int launch_smooth(cudaStream_t st, const SeqSmoothArgs& a) {
       return cuda_status(cudaGetLastError(), "seq_smooth_pipe_kernel launch");
     }
   }
-  if (a.pk) return set_error(PHYSS_ERR_UNSUPPORTED, "packed hand-over: even d <= 4, time-major steps, plain mode");
+  if (a.pk) return set_error(PHYSS_ERR_UNSUPPORTED, "packed hand-over: d <= 4, time-major steps, plain mode");
   if (a.nchunk > 0) {
     if (MO != 0 && a.fixup) return set_error(PHYSS_ERR_BAD_ARG, "smoother fix-up needs full_state output");
     if (coal) seq_smooth_kernel<D, S, MO, GIVEN, true, true><<<(unsigned)grid, block, 0, st>>>(a);

@@ -393,13 +393,13 @@ def filter_smooth_fused(data, prior, R=None, R_inv=None, filter_type='b200'):
     """`filter_loop` + `smoother_loop(full_state=False)` (sde_gp.py:231-253) as ONE C-ABI call that never
     materialises the filtered moments (`physs_kf_filter_smooth_packed_f64`): the hand-over between the two passes
     is a workspace of packed rows [m | triu(P)].  Returns (lml, mu, var) -- what the two loops return (lml bitwise,
-    the projected moments to 1e-14) -- or None when the problem is outside what the packed call covers (sequential register kernels, state dim 2 or 4,
+    the projected moments to 1e-14) -- or None when the problem is outside what the packed call covers (sequential register kernels, state dim <= 4,
     a time-major batch, covariance-parameterised noise); the caller then takes the two loops."""
     if not settings.fused_packed or R_inv is not None or R is None or isinstance(prior, PDE):
         return None
     X_s = data.X_space
     d = prior.d if isinstance(prior, BatchedMaternSDE) else np.asarray(prior.P_inf(None, X_s, None)).shape[0]
-    if d not in (2, 4):
+    if d > 4:
         return None
     dev = _device()
     X_t = _time_axis(data, dev)

@@ -308,7 +308,7 @@ def kf_filter_smooth(dt_f, dt_s, Y, R, H, m0, P0, disc_f, disc_s=None, Hout=None
 
 
 def kf_filter_smooth_packed_supported(Y, d, m, disc):
-    """True when `kf_filter_smooth_packed` covers this problem: register kernels with d = 2 or 4 and Y [B, T, m]
+    """True when `kf_filter_smooth_packed` covers this problem: register kernels (d <= 4) and Y [B, T, m]
     time-major (a transposed view of a contiguous [T, B, m] tensor)."""
     lib = _lib.load()
     if Y.dim() != 3 or not lib.physs_kf_filter_smooth_packed_supported(d, m, disc.mode, disc.nblk):

@@ -13,7 +13,7 @@ verbose = False
 # [B, T, ...] views), which lets a warp's 32 series move one contiguous span per step.
 time_major = True
 time_major_min_batch = 32
-# filter_and_smooth(full_state=False) on a time-major batch with state dim 2 or 4: one C-ABI call whose filtered
+# filter_and_smooth(full_state=False) on a time-major batch with state dim <= 4: one C-ABI call whose filtered
 # moments stay in a packed workspace (physs_kf_filter_smooth_packed_f64) instead of two calls around full (m, P)
 # outputs; same arithmetic (lml bitwise, moments to 1e-14).  False = always the two calls (A-B timing)
 fused_packed = True

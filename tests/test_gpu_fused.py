@@ -102,7 +102,7 @@ def _packed_problem(dev, rng, B, T, s, nblk, mode, m_obs=1):
     return dt_f, dt_s, Yt, R, H, m0, Pinf, disc_f, disc_s
 
 
-@pytest.mark.parametrize("shape", [(4, 1), (2, 2), (1, 4), (2, 1), (1, 2)])      # (block size, blocks): d = 4, 4, 4, 2, 2
+@pytest.mark.parametrize("shape", [(4, 1), (2, 2), (1, 4), (2, 1), (1, 2), (3, 1), (1, 3), (1, 1)])  # (block size, blocks)
 @pytest.mark.parametrize("projected", [False, True])
 def test_packed_matches_the_two_output_call_matern(cuda_device, shape, projected):
     """The packed hand-over (14 instead of 20 doubles per step at d = 4) changes no bit of lml and of the full-state
@@ -118,8 +118,9 @@ def test_packed_matches_the_two_output_call_matern(cuda_device, shape, projected
     _same_posterior((lml, ms, Ps), (lml2, ms2, Ps2), bitwise=not projected)
 
 
-@pytest.mark.parametrize("case", [("given", 4, 1, 1), ("given", 2, 1, 1), ("iwp", 4, 1, 1), ("iwp", 2, 1, 1),
-                                  ("matern", 4, 1, 2), ("matern", 2, 1, 2)])
+@pytest.mark.parametrize("case", [("given", 4, 1, 1), ("given", 2, 1, 1), ("given", 3, 1, 1), ("iwp", 4, 1, 1),
+                                  ("iwp", 3, 1, 1), ("iwp", 2, 1, 1), ("matern", 4, 1, 2), ("matern", 3, 1, 2),
+                                  ("matern", 2, 1, 2)])
 def test_packed_other_discretisations_and_m(cuda_device, case):
     """Supplied transitions, integrated-Wiener blocks and two observed outputs per step; T = 2, 3 are the
     prologue / epilogue corner cases of the pipelined smoother."""
@@ -146,8 +147,8 @@ def test_packed_other_discretisations_and_m(cuda_device, case):
 def test_packed_rejects_what_it_does_not_cover(cuda_device):
     from physs_gp_b200 import ops
     rng = np.random.default_rng(2)
-    dt_f, dt_s, Yt, R, H, m0, P0, disc_f, disc_s = _packed_problem(cuda_device, rng, 40, 30, 3, 1, "matern")
-    assert not ops.kf_filter_smooth_packed_supported(Yt, 3, 1, disc_f)           # odd state dim
+    dt_f, dt_s, Yt, R, H, m0, P0, disc_f, disc_s = _packed_problem(cuda_device, rng, 40, 30, 4, 2, "matern")
+    assert not ops.kf_filter_smooth_packed_supported(Yt, 8, 1, disc_f)           # beyond the register kernels
     with pytest.raises(Exception):
         ops.kf_filter_smooth_packed(dt_f, dt_s, Yt, R, H, m0, P0, disc_f, disc_s, Hout=H)
     dt_f, dt_s, Yt, R, H, m0, P0, disc_f, disc_s = _packed_problem(cuda_device, rng, 40, 30, 4, 1, "matern")
@@ -160,7 +161,7 @@ def test_packed_rejects_what_it_does_not_cover(cuda_device):
     assert bool(torch.isfinite(out[1]).all())
 
 
-@pytest.mark.parametrize("order", [4, 2])
+@pytest.mark.parametrize("order", [4, 3, 2])
 def test_model_filter_and_smooth_takes_the_packed_call(cuda_device, order, monkeypatch):
     """SDE_GP.filter_and_smooth(full_state=False) routes a time-major batch through the packed call and returns
     bitwise what the two loops return (settings.fused_packed = False)."""

@@ -44,6 +44,28 @@ def test_cuda_filter_smoother_matches_reference_vectors(cuda_device, name, jit, 
         assert rel(mu, g["seq_ms_full%d" % fs]) < TOL and rel(var, g["seq_Ps_full%d" % fs]) < TOL
 
 
+@pytest.mark.parametrize("jit", [1e-5, 0.0])
+@pytest.mark.parametrize("name", ["m32", "m52", "m72", "indep_m32x2"])
+def test_cuda_packed_posterior_call_matches_reference_vectors(cuda_device, name, jit, monkeypatch):
+    """The posterior-only call (physs_kf_filter_smooth_packed_f64 behind filters.filter_smooth_fused: packed hand-over,
+    no filtered outputs) on a batch of 64 copies of each reference case with state dim <= 4: lml and the projected
+    smoothed moments of EVERY copy against the reference's own filter_loop / smoother_loop outputs."""
+    from physs_gp_b200 import data, filters, settings
+    monkeypatch.setattr(settings, "jitter", jit)
+    g = np.load(os.path.join(GOLD, "filter_%s_jit%s.npz" % (name, "1e-5" if jit else "0")))
+    prior = product_prior(name)
+    B = 64
+    Y = np.broadcast_to(g["Y"][None, :, :, None], (B,) + g["Y"].shape + (1,)).copy()
+    out = filters.filter_smooth_fused(data.TemporalData(g["t"], Y), prior, R=g["R"])
+    assert out is not None, "the packed call must cover these shapes"
+    lml, mu, var = out
+    assert lml.shape == (B,) and mu.shape[0] == B and var.shape[0] == B
+    for b in (0, 31, 32, B - 1):
+        assert abs(float(lml[b]) - float(g["seq_lml"])) <= TOL * abs(float(g["seq_lml"]))
+        assert rel(mu[b], g["seq_ms_full0"]) < TOL and rel(var[b], g["seq_Ps_full0"]) < TOL
+    assert torch.equal(mu[0], mu[B - 1]) and torch.equal(var[0], var[B - 1])
+
+
 def test_cuda_cvi_blocks_match_reference_vectors(cuda_device):
     """theta -> lambda -> cvi_block_update -> theta (one fused kernel) and the closed-form block ELL."""
     from physs_gp_b200 import cvi
