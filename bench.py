@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="c5: weak = --series per GPU (default); strong = --series in TOTAL, split over the ranks")
+    ap.add_argument("--post-sub-batch", type=int, default=None,
+                    help="series per launch of the packed posterior-only timing (default: the whole batch when its "
+                         "workspace fits)")
     ap.add_argument("--no-post", action="store_true",
                     help="skip the posterior-only (packed hand-over) timing beside the c5 d = 4 line")
     ap.add_argument("--no-sweep", action="store_true",
@@ -618,24 +621,37 @@ def run_b200(a):
         post = {}
         k_post = max(2, min(a.steps, 5))
         ws = None
+        # the packed call needs 112 B per series-step of workspace instead of 320 B of filtered outputs: the whole
+        # batch fits one launch (twice the resident warps of a 32,768-series sub-batch) where the two-output call
+        # needs the sub-batches of the main line
+        ws_need = lambda n: int(ops._lib.load().physs_kf_filter_smooth_packed_ws_bytes(n, T, n, d))   # noqa: E731
+        psub = n_local if (a.post_sub_batch is None and ws_need(n_local) <= 90e9) else min(a.post_sub_batch or sub, n_local)
+        Yp = Ys
+        if psub != sub:
+            Y_all = torch.cat([y.transpose(0, 1) for y in Ys], dim=1).transpose(0, 1)    # time-major [T][n_local][1]
+            Yp = [Y_all[s:s + psub] for s in range(0, n_local, psub)]
+            if psub != n_local:
+                Yp = [y.transpose(0, 1).contiguous().transpose(0, 1) for y in Yp]
         for name in ("packed", "two_output"):
+            ysrc, nsub = (Yp, psub) if name == "packed" else (Ys, sub)
+            pstarts = list(range(0, n_local, nsub))
+
             def call(i, s, n):
                 disc = ops.Disc.matern(nblk, lam[s:s + n], Pinf[s:s + n])
                 if name == "packed":
-                    return ops.kf_filter_smooth_packed(dt_f, dt_s, Ys[i], R, H, m0, Pinf[s:s + n], disc, Hout=H,
+                    return ops.kf_filter_smooth_packed(dt_f, dt_s, ysrc[i], R, H, m0, Pinf[s:s + n], disc, Hout=H,
                                                        jitter=1e-5, ws=ws)[0]
-                return ops.kf_filter_smooth(dt_f, dt_s, Ys[i], R, H, m0, Pinf[s:s + n], disc, Hout=H, jitter=1e-5)[0]
+                return ops.kf_filter_smooth(dt_f, dt_s, ysrc[i], R, H, m0, Pinf[s:s + n], disc, Hout=H, jitter=1e-5)[0]
             if name == "packed":
-                need = ops._lib.load().physs_kf_filter_smooth_packed_ws_bytes(sub, T, sub, d)
-                ws = torch.empty((int(need),), dtype=torch.uint8, device=dev)
-            for i, s in enumerate(starts):                                  # warm-up
-                call(i, s, min(sub, n_local - s))
+                ws = torch.empty((ws_need(nsub),), dtype=torch.uint8, device=dev)
+            for i, s in enumerate(pstarts):                                 # warm-up
+                call(i, s, min(nsub, n_local - s))
             barrier()
             p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             p0.record()
             for _ in range(k_post):
-                for i, s in enumerate(starts):
-                    lml_p = call(i, s, min(sub, n_local - s))
+                for i, s in enumerate(pstarts):
+                    lml_p = call(i, s, min(nsub, n_local - s))
             p1.record()
             barrier()
             ms_p = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
@@ -645,13 +661,14 @@ def run_b200(a):
             rate = n_total * T * k_post / (float(ms_p.item()) * 1e-3)
             # y, R, dt in + hand-over out and back + (mean, variance) out
             bpss = 8 * (3 + 2 * (14 if name == "packed" else d * d + d) + 2)
-            post[name] = {"value": rate, "unit": "state-steps/s", "steps": k_post,
+            post[name] = {"value": rate, "unit": "state-steps/s", "steps": k_post, "series_per_launch": nsub,
                           "ms_per_step": float(ms_p.item()) / k_post, "bytes_per_state_step": bpss,
                           "achieved_gbs": bpss * (rate / world) / 1e9, "frac": bpss * (rate / world) / 1e9 / peak}
             ws = None
             torch.cuda.empty_cache()
-        post["api"] = ("ops.kf_filter_smooth_packed vs ops.kf_filter_smooth(Hout=H): inputs resident in HBM, sub-batches "
-                       "of %d series, outputs = smoothed mean / variance of f [B, T] + lml [B]" % sub)
+        Yp = None
+        post["api"] = ("ops.kf_filter_smooth_packed vs ops.kf_filter_smooth(Hout=H): inputs resident in HBM, "
+                       "outputs = smoothed mean / variance of f [B, T] + lml [B]")
     if not a.no_e2e:
         e2e = run_e2e(a, dev, world, rank, prior, steps, starts, sub, n_local, Ys, numa)
 
