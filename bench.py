@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "cvi", "c2", "c2cvi", "c3cvi", "grad", "spatial"],
+    ap.add_argument("--workload", default="c5", choices=["c5", "c1", "c3", "cvi", "c2", "c2cvi", "c3cvi", "grad", "spatial"],
                     help="c5 (default, the headline metric): batched sweep; c3: one long series, parallel-in-time "
                          "scan, time-sharded over the ranks; cvi: CVI ELBO + natural-gradient step (config 4)")
     ap.add_argument("--chunk-len", type=int, default=256, help="c3: steps per scan chunk")
@@ -68,7 +68,7 @@ def parse():
                     help="c5 default line: skip the d = 8 / 16 / 32 sweep and the CVI-step section")
     ap.add_argument("--cpu-sample-series", type=int, default=0, help="series in the CPU sample (0 = auto)")
     a = ap.parse_args()
-    dflt = {"c5": (SERIES_TOTAL, T_STEPS, 4), "c3": (1, 1000000, 8), "cvi": (1000, T_STEPS, 2),
+    dflt = {"c5": (SERIES_TOTAL, T_STEPS, 4), "c1": (1, 10000, 2), "c3": (1, 1000000, 8), "cvi": (1000, T_STEPS, 2),
             "c2": (200, 5000, 400), "c2cvi": (200, 5000, 400), "c3cvi": (1, 1000000, 4), "grad": (32768, T_STEPS, 4),
             "spatial": (200, 5000, 200)}[a.workload]
     a.series = dflt[0] if a.series is None else a.series
@@ -322,6 +322,20 @@ def run_reference(a):
                     higher_is_better=False, scaling="weak", config=cfg,
                     cpu_baseline={"value": value, "unit": "ms", "cores": threads, "kind": "port", "sample": sample},
                     e2e={"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return
+    if a.workload == "c1":
+        vals = [cpu_c1_ms(T, budget_s=1.0)[0] for _ in range(a.warmup + a.steps)][a.warmup:]
+        ms = float(np.mean(vals))
+        sample = "the whole workload (1 series x %d steps), ONE core -- %s" % (T, CPU_KIND_NOTE)
+        line = dict(base, metric="filter+smoother state-steps/sec (fp64)", value=T / (ms * 1e-3), unit="state-steps/s",
+                    ms_per_step=ms, higher_is_better=True, scaling="weak",
+                    config={"workload": "c1: ONE 1-D temporal Matern-3/2 series (state dim 2) x %d steps [CPU arm: %s]"
+                                        % (T, sample)},
+                    cpu_baseline={"value": T / (ms * 1e-3), "unit": "state-steps/s", "cores": 1, "kind": "port",
+                                  "sample": sample},
+                    e2e={"value": T / (ms * 1e-3), "unit": "state-steps/s", "h2d_bytes_per_step": 0,
+                         "d2h_bytes_per_step": 0})
         print(json.dumps(line), flush=True)
         return
     if a.workload in ("c3", "c3cvi"):
@@ -1701,6 +1715,89 @@ def run_spatial(a):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ c1: BASELINE configs[0]
+def _c1_problem(T):
+    rng = np.random.default_rng(0)
+    t = np.cumsum(rng.uniform(0.5, 1.5, T) * DT0)
+    y = np.sin(0.5 * t) + 0.3 * rng.normal(size=T)
+    y[rng.uniform(size=T) < 0.05] = np.nan
+    return t, y, 10 * DT0, 1.0            # lengthscale, variance
+
+
+def cpu_c1_ms(T, budget_s=5.0):
+    """ms per exact lml + smoothed posterior of ONE Matern-3/2 series (C port of the oracle, one core)."""
+    from oracle import c_oracle
+    from physs_gp_b200 import sdes
+    c_oracle.build()
+    t, y, ls, var = _c1_problem(T)
+    prior = sdes.BatchedMaternSDE(2, np.array([[ls]]), np.array([[var]]))
+    args = (2, prior.lam(), prior.P_inf(), prior.H(), t, y[None, :, None], NOISE_VAR * np.eye(1))
+    c_oracle.filter_smooth(*args, jitter=1e-5, full_state=False, nthreads=1)
+    el, reps = 0.0, 0
+    while el < budget_s and reps < 2000:
+        t0 = time.perf_counter()
+        c_oracle.filter_smooth(*args, jitter=1e-5, full_state=False, nthreads=1)
+        el += time.perf_counter() - t0
+        reps += 1
+    return el / reps * 1e3, el, reps
+
+
+def run_c1(a):
+    """BASELINE configs[0] (the reference's own CPU-runnable case): ONE 1-D temporal Matern-3/2 GP, Gaussian
+    likelihood, N = 10k, exact marginal likelihood + smoothed posterior through the host API
+    (`SDE_GP.filter_and_smooth(return_lml=True)`).  One series cannot fill a GPU: the sequential kernel walks it with
+    one thread (filter_type='b200'), the chunked scan spreads it over the chip ('b200_parallel'); both are timed,
+    the faster one is `value`.  A parity-test shape, not a throughput shape -- reported for completeness."""
+    import torch
+    from physs_gp_b200 import data, kernels, likelihood, models, sdes
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("--workload c1 is one series: single GPU")
+    torch.cuda.set_device(0)
+    T = a.T
+    t, y, ls, var = _c1_problem(T)
+    res = {}
+    for ft in ("b200", "b200_parallel"):
+        prior = sdes.LTI_SDE(sdes.Independent([kernels.Matern32(ls, var)]))
+        model = models.SDE_GP(data.TemporalData(t, y[:, None, None]), prior, likelihood.Gaussian(NOISE_VAR),
+                              filter_type=ft)
+        for _ in range(max(3, a.warmup)):
+            lml, mu, v = model.filter_and_smooth(return_lml=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(a.steps):
+            lml, mu, v = model.filter_and_smooth(return_lml=True)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / a.steps * 1e3
+        assert bool(torch.isfinite(lml).all()) and bool(torch.isfinite(mu).all())
+        res[ft] = {"ms_per_call": e0.elapsed_time(e1) / a.steps, "wall_ms_per_call": wall, "lml": float(lml)}
+    best = min(res, key=lambda k: res[k]["ms_per_call"])
+    ms = res[best]["ms_per_call"]
+    cpu = None
+    if not a.no_cpu_baseline:
+        cms, el, reps = cpu_c1_ms(T)
+        cpu = {"value": T / (cms * 1e-3), "unit": "state-steps/s", "ms_per_call": cms, "cores": 1, "kind": "port",
+               "sample": "the whole workload (1 series x %d steps) x %d repeats = %.1f s -- %s" % (T, reps, el, CPU_KIND_NOTE)}
+    line = {"metric": "filter+smoother state-steps/sec (fp64)", "value": T / (ms * 1e-3), "unit": "state-steps/s",
+            "n_gpus": 1, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "c1: ONE 1-D temporal Matern-3/2 series (state dim 2) x %d steps, Gaussian likelihood, 5%% "
+                                   "missing: exact lml + smoothed posterior through SDE_GP.filter_and_smooth; filter_type=%s" % (T, best),
+                       "l2": "working set %.1f MB < L2: a latency-bound single series, no flush" % (T * 8 * 16 / 1e6),
+                       "parallelism": "single GPU"},
+            "by_filter_type": res,
+            "roofline": {"bound": "hbm", "achieved": T * 8 * (3 + 2 * 6 + 2) / (ms * 1e-3) / 1e9, "peak": measured_peak_gbs()[0],
+                         "unit": "GB/s", "frac": T * 8 * (3 + 2 * 6 + 2) / (ms * 1e-3) / 1e9 / measured_peak_gbs()[0],
+                         "traffic": None, "note": "one series x 10k steps is launch / latency bound by construction"},
+            "cpu_baseline": cpu, "e2e": {"value": T / (res[best]["wall_ms_per_call"] * 1e-3), "unit": "state-steps/s",
+                                         "h2d_bytes_per_step": T * 8 * 2, "d2h_bytes_per_step": 0,
+                                         "note": "host wall clock per call, numpy inputs uploaded by the host API every call; results left on the device"},
+            "clocks": None, "gpu_launches": None}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     a = parse()
     # stdout carries the ONE JSON line and nothing else: native libraries that write to file descriptor 1 (NCCL's
@@ -1711,6 +1808,8 @@ def main():
     sys.stdout = os.fdopen(keep, "w")
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "c1":
+        run_c1(a)
     elif a.workload == "c3cvi":
         run_c3cvi(a)
     elif a.workload == "c2":
