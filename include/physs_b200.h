@@ -421,6 +421,23 @@ int physs_cvi_natgrad_step_f64(void* stream, int64_t N, int32_t D, int32_t P, in
                                double beta, double ng_jitter,
                                double* Ytil_out, double* Vtil_out, double* ell_out);
 
+/* The same update for sites stored in the PRECISION parameterisation ('NG_Precision'): Ptil [N, D, D] is the site
+ * precision (the surrogate's PrecisionBlockDiagonalGaussian, likelihood/gaussian.py:96-105) in and out.  Replaces
+ * theta_precision_to_lambda / lambda_to_theta_precision (exponential_family_transforms.py:44-53,85-95) around
+ * cvi_block_update, i.e. natural_gradients(VGP, FullConjugateGaussian, "NG_Precision")
+ * (cvi_parameterisations.py:95-113 with cvi_nat_grad_utils.py:62-63): lambda_2 = -1/2 Ptil,
+ * lambda_1 = (Ptil + ng_jitter I)^-1 Ytil -- the reference's own cholesky_solve with the precision's factor --,
+ * Ptil' = -2 lambda_2', Ytil' = (Ptil' + ng_jitter I)^-1 lambda_1'.  Everything else as above. */
+int physs_cvi_natgrad_step_prec_f64(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik,
+                                    const double* Ytil, const double* Ptil,
+                                    const double* q_mu, const double* q_var,
+                                    const double* y, const double* W,
+                                    const double* noise, int64_t noise_stride,
+                                    double lik_param, int32_t K, const double* ghx, const double* ghw,
+                                    const double* dm_in, const double* dS_in,
+                                    double beta, double ng_jitter,
+                                    double* Ytil_out, double* Ptil_out, double* ell_out);
+
 /* Per-block expected log-likelihood (and optionally its gradients) under q = N(q_mu, q_var).
  * Replaces full_gaussian_expected_log_likelihood (computation/elbos/expected_log_likelihoods.py:90-117)
  * vmapped over blocks (dispatched_ell.py:47-132) and the non-Gaussian approximate_expectation route

@@ -45,6 +45,22 @@ def lambda_to_theta(lambda_1, lambda_2, ng_jitter=la.NG_JITTER):
     return theta_1, theta_2
 
 
+def theta_precision_to_lambda(theta_1, theta_2, ng_jitter=la.NG_JITTER):
+    """exponential_family_transforms.py:44-53 ('NG_Precision': theta_2 is the site PRECISION): lambda_2 = -1/2 theta_2
+    and -- exactly as the reference writes it -- lambda_1 = (theta_2 + ng_jitter I)^-1 theta_1, a cholesky_solve with
+    the precision's factor (not the product precision @ theta_1)."""
+    D = theta_1.shape[0]
+    L = la.cholesky(theta_2 + ng_jitter * np.eye(D))
+    return la.cholesky_solve(L, theta_1), -0.5 * theta_2
+
+
+def lambda_to_theta_precision(lambda_1, lambda_2, ng_jitter=la.NG_JITTER):
+    """exponential_family_transforms.py:85-95: theta_2 = -2 lambda_2 (precision), theta_1 = (-2 lambda_2 + jit I)^-1 lambda_1."""
+    D = lambda_1.shape[0]
+    L = la.cholesky(-2 * lambda_2 + ng_jitter * np.eye(D))
+    return la.cholesky_solve(L, lambda_1), -2 * lambda_2
+
+
 def cvi_block_update(lambda_1, lambda_2, m, s, m_grad, s_grad, beta):
     """cvi_nat_grad.py:47-87 with enforce_psd_type=None."""
     grad_1 = m_grad - 2 * s_grad @ m
@@ -170,6 +186,19 @@ def cvi_step(Ytil, Vtil, q_mu, q_var, dm, dS, beta, ng_jitter=la.NG_JITTER):
         th1, th2 = lambda_to_theta(l1n, l2n, ng_jitter)
         Yn[t], Vn[t] = th1[:, 0], th2
     return Yn, Vn
+
+
+def cvi_step_precision(Ytil, Ptil, q_mu, q_var, dm, dS, beta, ng_jitter=la.NG_JITTER):
+    """natural_gradients(FullConjugateGaussian) + the 'NG_Precision' re-entry (cvi_parameterisations.py:95-113,
+    cvi_nat_grad_utils.py:62-63) for all T blocks: the sites carry (Y~, precision).  Returns new (Ytil, Ptil)."""
+    T, D = Ytil.shape
+    Yn, Pn = np.empty_like(Ytil), np.empty_like(Ptil)
+    for t in range(T):
+        l1, l2 = theta_precision_to_lambda(Ytil[t][:, None], Ptil[t], ng_jitter)
+        l1n, l2n = cvi_block_update(l1, l2, q_mu[t][:, None], q_var[t], dm[t][:, None], dS[t], beta)
+        th1, th2 = lambda_to_theta_precision(l1n, l2n, ng_jitter)
+        Yn[t], Pn[t] = th1[:, 0], th2
+    return Yn, Pn
 
 
 def surrogate_ell(Ytil, Vtil, q_mu, q_var):

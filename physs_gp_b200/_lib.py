@@ -93,6 +93,9 @@ SIGNATURES = {
     "physs_cvi_natgrad_step_f64": (ctypes.c_int, [
         _ptr, _c_i64, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64,
         _c_f64, _c_i32, _ptr, _ptr, _ptr, _ptr, _c_f64, _c_f64, _ptr, _ptr, _ptr]),
+    "physs_cvi_natgrad_step_prec_f64": (ctypes.c_int, [
+        _ptr, _c_i64, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64,
+        _c_f64, _c_i32, _ptr, _ptr, _ptr, _ptr, _c_f64, _c_f64, _ptr, _ptr, _ptr]),
     "physs_cvi_ell_f64": (ctypes.c_int, [
         _ptr, _c_i64, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i64,
         _c_f64, _c_i32, _ptr, _ptr, _ptr, _ptr, _ptr]),

@@ -447,6 +447,12 @@ static int cvi_dispatch(void* stream, int64_t N, int32_t D, int32_t P, int32_t l
   return cvi_grp_run((cudaStream_t)stream, D, P, lik, update, a);
 }
 
+static int cvi_natgrad_step(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik, const double* Ytil,
+                            const double* Vtil, const double* q_mu, const double* q_var, const double* y,
+                            const double* W, const double* noise, int64_t noise_stride, double lik_param, int32_t K,
+                            const double* ghx, const double* ghw, const double* dm_in, const double* dS_in, double beta,
+                            double ng_jitter, double* Ytil_out, double* Vtil_out, double* ell_out, int prec);
+
 int physs_cvi_natgrad_step_f64(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik,
                                const double* Ytil, const double* Vtil,
                                const double* q_mu, const double* q_var,
@@ -456,6 +462,28 @@ int physs_cvi_natgrad_step_f64(void* stream, int64_t N, int32_t D, int32_t P, in
                                const double* dm_in, const double* dS_in,
                                double beta, double ng_jitter,
                                double* Ytil_out, double* Vtil_out, double* ell_out) {
+  return cvi_natgrad_step(stream, N, D, P, lik, Ytil, Vtil, q_mu, q_var, y, W, noise, noise_stride, lik_param, K, ghx,
+                          ghw, dm_in, dS_in, beta, ng_jitter, Ytil_out, Vtil_out, ell_out, 0);
+}
+
+int physs_cvi_natgrad_step_prec_f64(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik,
+                                    const double* Ytil, const double* Ptil,
+                                    const double* q_mu, const double* q_var,
+                                    const double* y, const double* W,
+                                    const double* noise, int64_t noise_stride,
+                                    double lik_param, int32_t K, const double* ghx, const double* ghw,
+                                    const double* dm_in, const double* dS_in,
+                                    double beta, double ng_jitter,
+                                    double* Ytil_out, double* Ptil_out, double* ell_out) {
+  return cvi_natgrad_step(stream, N, D, P, lik, Ytil, Ptil, q_mu, q_var, y, W, noise, noise_stride, lik_param, K, ghx,
+                          ghw, dm_in, dS_in, beta, ng_jitter, Ytil_out, Ptil_out, ell_out, 1);
+}
+
+static int cvi_natgrad_step(void* stream, int64_t N, int32_t D, int32_t P, int32_t lik, const double* Ytil,
+                            const double* Vtil, const double* q_mu, const double* q_var, const double* y,
+                            const double* W, const double* noise, int64_t noise_stride, double lik_param, int32_t K,
+                            const double* ghx, const double* ghw, const double* dm_in, const double* dS_in, double beta,
+                            double ng_jitter, double* Ytil_out, double* Vtil_out, double* ell_out, int prec) {
   if (N > 0 && (!Ytil || !Vtil || !q_mu || !q_var || !Ytil_out || !Vtil_out))
     return set_error(PHYSS_ERR_BAD_ARG, "cvi step: null required pointer");
   if (lik == 3 && N > 0 && (!dm_in || !dS_in)) return set_error(PHYSS_ERR_BAD_ARG, "cvi step: LIK_GIVEN needs dm, dS");
@@ -464,7 +492,7 @@ int physs_cvi_natgrad_step_f64(void* stream, int64_t N, int32_t D, int32_t P, in
   CviArgs a{};
   a.N = N; a.Yt = Ytil; a.Vt = Vtil; a.qm = q_mu; a.qS = q_var; a.y = y; a.W = W;
   a.noise = noise; a.noise_stride = noise_stride; a.lik_param = lik_param; a.K = K; a.ghx = ghx; a.ghw = ghw;
-  a.dm_in = dm_in; a.dS_in = dS_in; a.beta = beta; a.ngj = ng_jitter;
+  a.dm_in = dm_in; a.dS_in = dS_in; a.beta = beta; a.ngj = ng_jitter; a.prec = prec;
   a.Yn = Ytil_out; a.Vn = Vtil_out; a.ell = ell_out; a.dm_out = nullptr; a.dS_out = nullptr;
   return cvi_dispatch(stream, N, D, P, lik, true, a);
 }

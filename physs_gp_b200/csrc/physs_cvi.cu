@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128) cvi_site_kernel(const CviArgs p) {
   }
   if (UPDATE) {
     double Yn[D], Vn[D][D];
-    cvi_site_update<D>(Yt, Vt, qm, qS, dm, dS, p.beta, p.ngj, Yn, Vn);
+    cvi_site_update<D>(Yt, Vt, qm, qS, dm, dS, p.beta, p.ngj, Yn, Vn, p.prec != 0);
     stv<D>(p.Yn + n * D, Yn);
     stv<D * D>(p.Vn + n * D * D, *reinterpret_cast<double (*)[D * D]>(&Vn[0][0]));
   }

@@ -264,11 +264,15 @@ PHYSS_HD double cvi_ell_grads(const double (&qm)[D], const double (&qS)[D][D], c
 }
 
 // One natural-gradient site update (theta -> lambda, cvi_block_update, lambda -> theta).
+//   prec ('NG_Precision', exponential_family_transforms.py:44-53,85-95; cvi_parameterisations.py:95-113): Vt is the site
+//   PRECISION.  lambda_2 = -1/2 Vt; lambda_1 = (Vt + ng_jitter I)^-1 Y~ -- the reference's own cholesky_solve with the
+//   precision's factor --; on the way back theta_2' = -2 lambda_2' (written to Vn) and
+//   theta_1' = (-2 lambda_2' + ng_jitter I)^-1 lambda_1'.
 template <int D>
 PHYSS_HD void cvi_site_update(const double (&Yt)[D], const double (&Vt)[D][D], const double (&qm)[D],
                               const double (&qS)[D][D], const double (&dm)[D],
                               const double (&dS)[D][D], double beta, double ngj, double (&Yn)[D],
-                              double (&Vn)[D][D]) {
+                              double (&Vn)[D][D], bool prec = false) {
   double Vinv[D][D];
   spd_inverse<D>(Vt, ngj, Vinv);                 // (V~ + ng_jitter I)^-1
   double l1[D], l2[D][D];
@@ -283,7 +287,7 @@ PHYSS_HD void cvi_site_update(const double (&Yt)[D], const double (&Vt)[D][D], c
     for (int k = 0; k < D; ++k) g = fma(-2.0 * dS[i][k], qm[k], g);
     l1[i] = (1.0 - beta) * t + beta * g;
     PHYSS_UNROLL
-    for (int j = 0; j < D; ++j) l2[i][j] = (1.0 - beta) * (-0.5 * Vinv[i][j]) + beta * dS[i][j];
+    for (int j = 0; j < D; ++j) l2[i][j] = (1.0 - beta) * (-0.5 * (prec ? Vt[i][j] : Vinv[i][j])) + beta * dS[i][j];
   }
   (void)qS;
   double Pm[D][D];
@@ -299,6 +303,13 @@ PHYSS_HD void cvi_site_update(const double (&Yt)[D], const double (&Vt)[D][D], c
     PHYSS_UNROLL
     for (int k = 0; k < D; ++k) t = fma(Vn[i][k], l1[k], t);
     Yn[i] = t;
+  }
+  if (prec) {
+    PHYSS_UNROLL
+    for (int i = 0; i < D; ++i) {
+      PHYSS_UNROLL
+      for (int j = 0; j < D; ++j) Vn[i][j] = Pm[i][j];
+    }
   }
 }
 

@@ -176,20 +176,25 @@ __global__ void cvi_grp_kernel(const CviArgs p, const CviGrpLayout L) {
       l1[i] = (1.0 - p.beta) * t + p.beta * g;
     }
     __syncwarp();
+    // 'NG_Precision' (p.prec): the site matrix IS the precision -- lambda_2 = -1/2 of it (re-read: M1 now holds the
+    // inverse that lambda_1 uses, as the reference's cholesky_solve does) and theta_2' = -2 lambda_2' goes out as it is
     for (int idx = gl; idx < D * D; idx += G) {
       const int i = idx / D, j = idx - i * D;
-      const double l2 = (1.0 - p.beta) * (-0.5 * M1[i * ld + j]) + p.beta * dS[i * ld + j];
+      const double src = p.prec ? p.Vt[n * D * D + idx] : M1[i * ld + j];
+      const double l2 = (1.0 - p.beta) * (-0.5 * src) + p.beta * dS[i * ld + j];
       M2[i * ld + j] = -2.0 * l2;
     }
     __syncwarp();
-    spd_inverse_smem<G>(M2, M1, ld, D, p.ngj, rd);                   // M2 = V~'
+    if (p.prec && active) s2g<G>(p.Vn + n * D * D, M2, ld, D, D);
+    __syncwarp();
+    spd_inverse_smem<G>(M2, M1, ld, D, p.ngj, rd);                   // M2 = V~'  (prec: the inverse theta_1' needs)
     if (active) {
       for (int i = gl; i < D; i += G) {
         double t = 0.0;
         for (int k = 0; k < D; ++k) t = fma(M2[i * ld + k], l1[k], t);
         p.Yn[n * D + i] = t;
       }
-      s2g<G>(p.Vn + n * D * D, M2, ld, D, D);
+      if (!p.prec) s2g<G>(p.Vn + n * D * D, M2, ld, D, D);
     }
   }
 }

@@ -117,6 +117,7 @@ struct CviArgs {
   double log_param; const double* logfact;  // Poisson: log(binsize) and the device table of log-factorials (or NULL)
   const double* dm_in; const double* dS_in;
   double beta, ngj;
+  int prec;                                 // sites carry (Y~, PRECISION): the 'NG_Precision' re-entry
   double* Yn; double* Vn;
   double* ell; double* dm_out; double* dS_out;
 };

@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from . import settings
 from .data import TemporalData
-from .likelihood import BlockDiagonalGaussian
+from .likelihood import BlockDiagonalGaussian, PrecisionBlockDiagonalGaussian
 from .models import SDE_GP
 
 
@@ -95,18 +95,27 @@ def _back(x, tm):
     return x.transpose(0, 1) if (tm and x is not None) else x
 
 
+def _like_sites(x, sites):
+    """x [B, T, ...] re-stored in the memory order of the site tensors (the site kernels want one order)."""
+    return time_major_blocks(x) if (_is_tm(sites) and not _is_tm(x)) else x
+
+
 def time_major_blocks(x):
     """Re-store a [B, T, ...] tensor time-major (logical shape unchanged)."""
     return x.transpose(0, 1).contiguous().transpose(0, 1)
 
 
 def natgrad_step(Ytil, Vtil, q_mu, q_var, y, W, lik, beta, ng_jitter=None, K=20, dm=None, dS=None,
-                 want_ell=False, out=None, stream=None):
+                 want_ell=False, out=None, stream=None, precision=False):
     """Raw op: all tensors are CUDA float64 with the site blocks flattened to N = prod(leading dims).
     Ytil [..., D], Vtil [..., D, D], q_mu, q_var alike; y [..., P]; W [P, D] or None.
+    `precision=True`: the 'NG_Precision' parameterisation -- Vtil holds the site PRECISION in and out
+    (physs_cvi_natgrad_step_prec_f64; exponential_family_transforms.py:44-53,85-95).
     Returns (Ytil_new, Vtil_new[, ell [...]])."""
     lib = _lib.load()
     if Ytil.shape[-1] > BIG_BLOCK_MIN:
+        if precision:
+            raise NotImplementedError("NG_Precision sites: blocks up to %d x %d" % (BIG_BLOCK_MIN, BIG_BLOCK_MIN))
         return _natgrad_step_big(Ytil, Vtil, q_mu, q_var, y, W, lik, beta, ng_jitter, dm, dS, want_ell, out, stream)
     given = dm is not None
     (Ytil, Vtil, q_mu, q_var, yv, dm, dS), tm = _block_order(
@@ -136,8 +145,9 @@ def natgrad_step(Ytil, Vtil, q_mu, q_var, y, W, lik, beta, ng_jitter=None, K=20,
     ell = torch.empty(lead, dtype=torch.float64, device=dev) if want_ell else None
     ngj = settings.ng_jitter if ng_jitter is None else ng_jitter
     s = stream if stream is not None else torch.cuda.current_stream()
+    step_fn = lib.physs_cvi_natgrad_step_prec_f64 if precision else lib.physs_cvi_natgrad_step_f64
     with torch.cuda.device(dev):
-        st = lib.physs_cvi_natgrad_step_f64(
+        st = step_fn(
             s.cuda_stream, N, D, P, kind, Ytil.data_ptr(), Vtil.data_ptr(), q_mu.data_ptr(), q_var.data_ptr(),
             _ptr(yv), _ptr(Wv), _ptr(noise), nstride, float(0.0 if given else lik.param), int(K),
             _ptr(ghx), _ptr(ghw), _ptr(dm if given else None), _ptr(dS if given else None),
@@ -349,7 +359,12 @@ class FullConjugateGaussian:
     V~ = I (:209-218)."""
 
     def __init__(self, X_time, surrogate_prior, block_size, B=1, Y_tilde=None, V_tilde=None, device=None,
-                 filter_type='b200'):
+                 filter_type='b200', parameterisation='NG_Moment'):
+        if parameterisation not in ('NG_Moment', 'NG_Precision'):
+            raise ValueError("parameterisation: 'NG_Moment' or 'NG_Precision' (natural_gradients/parameterisations.py)")
+        # 'NG_Precision': V_tilde holds the site PRECISION (the surrogate's PrecisionBlockDiagonalGaussian); the
+        # reference's initialisation theta_2 = I is the same matrix either way
+        self.parameterisation = parameterisation
         dev = device or torch.device("cuda", torch.cuda.current_device())
         T = len(X_time)
         D = block_size
@@ -369,7 +384,9 @@ class FullConjugateGaussian:
     @property
     def surrogate(self):
         data = TemporalData(self.X_time, self.Y_tilde[..., None])          # [B, T, P=D, Ns=1]
-        return SDE_GP(data, self.prior, BlockDiagonalGaussian(self.V_tilde), filter_type=self.filter_type)
+        lik = (PrecisionBlockDiagonalGaussian(self.V_tilde) if self.parameterisation == 'NG_Precision'
+               else BlockDiagonalGaussian(self.V_tilde))
+        return SDE_GP(data, self.prior, lik, filter_type=self.filter_type)
 
 
 class VGP:
@@ -500,6 +517,7 @@ class VGP:
             raise NotImplementedError("enforce_psd_type: None, or 'laplace_gauss_newton_delta_u' with a PDE "
                                       "collocation likelihood, are implemented on the b200 path")
         q = self.q
+        prec = getattr(q, "parameterisation", 'NG_Moment') == 'NG_Precision'   # cvi_parameterisations.py:95-113
         _, q_mu, q_var = self._posterior()                         # [B,T,D], [B,T,D,D]
         self._post = None                                          # the sites change below
         if pde:
@@ -507,10 +525,10 @@ class VGP:
             _, dm, dS = pendulum_expected_log_likelihood(q_mu, q_var, self.Y, self.lik,
                                                          gauss_newton=enforce_psd_type is not None, want_grads=True)
             natgrad_step(q.Y_tilde, q.V_tilde, q_mu, q_var, None, None, None, lr, dm=dm, dS=dS,
-                         out=(q.Y_tilde, q.V_tilde))
+                         out=(q.Y_tilde, q.V_tilde), precision=prec)
             return
         natgrad_step(q.Y_tilde, q.V_tilde, q_mu, q_var, self.Y, self.W, self.lik, lr, K=self.K,
-                     out=(q.Y_tilde, q.V_tilde))
+                     out=(q.Y_tilde, q.V_tilde), precision=prec)
 
     def elbo(self):
         """elbos.py:163-194; returns one ELBO per batch member [B]."""
@@ -521,7 +539,10 @@ class VGP:
         else:
             ell = expected_log_likelihood(q_mu, q_var, self.Y, self.W, self.lik, K=self.K)
         sur = GaussianLik(np.eye(q.block_size))
-        ell_s = expected_log_likelihood(q_mu, q_var, q.Y_tilde, None, sur, noise=q.V_tilde)
+        noise = q.V_tilde
+        if getattr(q, "parameterisation", 'NG_Moment') == 'NG_Precision':
+            noise = _like_sites(PrecisionBlockDiagonalGaussian(q.V_tilde).variance, q.V_tilde)   # mat_inv(precision)
+        ell_s = expected_log_likelihood(q_mu, q_var, q.Y_tilde, None, sur, noise=noise)
         return sum_steps(ell, ell_s) + lml
 
     def get_objective(self):

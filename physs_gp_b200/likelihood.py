@@ -44,5 +44,36 @@ class BlockDiagonalGaussian:
         return np.concatenate([V, eye], axis=-3)[..., unique_idx, :, :]
 
 
+class PrecisionBlockDiagonalGaussian(BlockDiagonalGaussian):
+    """BlockDiagonalGaussian storing the PRECISION blocks [.., Nt, m, m] (likelihood/gaussian.py:96-105): what the
+    'NG_Precision' CVI sites live in.  `variance` is the reference's `mat_inv` of the precision
+    (computation/matrix_ops.py:383-385: Cholesky of precision + settings.jitter I, then solve on the identity)."""
+
+    def __init__(self, precision):
+        self._precision = precision
+
+    @property
+    def precision(self):
+        return self._precision
+
+    @property
+    def variance(self):
+        import torch
+        from . import ops, settings
+        P = self._precision
+        if not isinstance(P, torch.Tensor):
+            P = torch.as_tensor(np.asarray(P, np.float64)).cuda()
+        return ops.spd_inverse(P, settings.jitter)
+
+    def R(self, Nt, m):
+        return self.variance
+
+    def R_predict(self, Nt, NS, unique_idx, m):
+        return BlockDiagonalGaussian(self.variance).R_predict(Nt, NS, unique_idx, m)
+
+
 def get_R_R_inv(likelihood, Nt, m):
+    """sde_gp.py:30-43: (variance, None), or (None, precision) for a PrecisionBlockDiagonalGaussian."""
+    if isinstance(likelihood, PrecisionBlockDiagonalGaussian):
+        return None, likelihood.precision
     return likelihood.R(Nt, m), None

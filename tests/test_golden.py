@@ -118,6 +118,25 @@ def test_cvi_blocks_match_reference():
             assert abs(e - float(g[k + "ell"])) <= 1e-12 * abs(float(g[k + "ell"]))
 
 
+def test_cvi_precision_blocks_match_reference():
+    """'NG_Precision' (tests/golden/make_golden_prec.py): the reference's own theta_precision_to_lambda ->
+    cvi_block_update -> lambda_to_theta_precision, and mat_inv of the stored precision."""
+    from oracle import linalg as ola
+    g = np.load(os.path.join(GOLD, "cvi_blocks_prec.npz"))
+    for D in (1, 2, 3, 4, 6, 8):
+        for tag, ngj in (("1e-7", 1e-7), ("1e-5", 1e-5)):
+            k = "D%d_ngj%s_" % (D, tag)
+            l1, l2 = ocvi.theta_precision_to_lambda(g[k + "Yt"], g[k + "Lam"], ngj)
+            assert rel(l1, g[k + "l1"]) < 1e-12 and rel(l2, g[k + "l2"]) < 1e-12
+            t1, t2 = ocvi.lambda_to_theta_precision(g[k + "n1"], g[k + "n2"], ngj)
+            assert rel(t1, g[k + "t1"]) < 1e-12 and rel(t2, g[k + "t2"]) < 1e-12
+            Yn, Pn = ocvi.cvi_step_precision(g[k + "Yt"][None, :, 0], g[k + "Lam"][None], g[k + "mq"][None, :, 0],
+                                             g[k + "S"][None], g[k + "dm"][None, :, 0], g[k + "dS"][None],
+                                             float(g[k + "beta"]), ngj)
+            assert rel(Yn[0], g[k + "t1"][:, 0]) < 1e-12 and rel(Pn[0], g[k + "t2"]) < 1e-12
+            assert rel(ola.mat_inv(g[k + "Lam"], 1e-5), g[k + "var"]) < 1e-12
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # tests/golden/make_golden_cvi.py: the reference's OWN natural_gradients / elbo / Gauss-Newton assembly /
 # Independent stacking, executed in place.  These move rows a10 / a12 / a13 / a6 from "oracle compared with

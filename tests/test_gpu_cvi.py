@@ -141,6 +141,54 @@ def test_vgp_cvi_iterations_match_oracle(cuda_device, kind):
         assert abs(float(elbo[b]) - ref) < tol * abs(ref)
 
 
+@pytest.mark.parametrize("kind", ["m32_f", "m52_fullstate"])
+def test_vgp_precision_parameterisation_matches_oracle(cuda_device, kind):
+    """'NG_Precision' sites (cvi_parameterisations.py:95-113): three CVI iterations and the ELBO with the sites stored as
+    (Y~, precision) against the numpy oracle -- the surrogate filters with R = precision^-1, the site update is the
+    reference's theta_precision_to_lambda -> cvi_block_update -> lambda_to_theta_precision (pinned to reference output
+    in tests/test_golden.py), the surrogate ELL uses mat_inv(precision) as PrecisionBlockDiagonalGaussian.variance."""
+    from oracle import linalg as ola
+    from physs_gp_b200 import cvi, sdes
+    rng = np.random.default_rng(18)
+    B, T = 3, 70
+    t = synth.time_grid(T, 0.1, rng)
+    if kind == "m32_f":
+        s, D, fso, W = 2, 1, False, None
+    else:
+        s, D, fso, W = 3, 3, True, np.array([[1.0, 0.0, 0.0]])
+    ls = synth.log_uniform(rng, 0.5, 2.0, (B, 1)); var = synth.log_uniform(rng, 0.5, 2.0, (B, 1))
+    prior = sdes.BatchedMaternSDE(s, ls, var, full_state_obs=fso)
+    Y = rng.integers(0, 5, size=(B, T, 1)).astype(float)
+    Y[rng.uniform(size=Y.shape) < 0.1] = np.nan
+    q = cvi.FullConjugateGaussian(t, prior, D, B=B, parameterisation='NG_Precision')
+    model = cvi.VGP(Y, cvi.PoissonLik(1.0), q, W=W, ell_quad_points=20)
+    beta = 0.3
+    for _ in range(3):
+        model.natural_gradient_update(beta)
+    elbo = model.elbo()
+    torch.cuda.synchronize()
+    okind = {2: osde.Matern32, 3: osde.Matern52}[s]
+    inv = lambda P: np.stack([np.linalg.inv(p) for p in P])                        # noqa: E731
+    for b in range(B):
+        k = okind(ls[b, 0], var[b, 0])
+        op = osde.LTI_SDE_Full_State_Obs([k]) if fso else osde.LTI_SDE([k])
+        Yt = 1e-5 * np.ones((T, D)); Pt = np.tile(np.eye(D), [T, 1, 1])
+        Wm = np.eye(D) if W is None else W
+        for _ in range(3):
+            _, qm, qv = ofilters.filter_and_smooth(op, t, Yt, inv(Pt))
+            dm = np.zeros((T, D)); dS = np.zeros((T, D, D))
+            for i in range(T):
+                _, dm[i], dS[i] = _oracle_grads("poisson", Y[b, i], Wm, None, qm[i][:, 0], qv[i], 1.0, 20)
+            Yt, Pt = ocvi.cvi_step_precision(Yt, Pt, qm[:, :, 0], qv, dm, dS, beta)
+        lml, qm, qv = ofilters.filter_and_smooth(op, t, Yt, inv(Pt))
+        ell = sum(_oracle_grads("poisson", Y[b, i], Wm, None, qm[i][:, 0], qv[i], 1.0, 20)[0] for i in range(T))
+        ell_s = ocvi.surrogate_ell(Yt, np.stack([ola.mat_inv(p, 1e-5) for p in Pt]), qm[:, :, 0], qv)
+        ref = ocvi.elbo(ell, ell_s, lml)
+        tol = 1e-7 if fso else TOL
+        assert rel(q.Y_tilde[b], Yt) < tol and rel(q.V_tilde[b], Pt) < tol
+        assert abs(float(elbo[b]) - ref) < tol * abs(ref)
+
+
 def test_cvi_gaussian_fixed_point_on_gpu(cuda_device):
     """beta = 1 with a Gaussian likelihood: one step gives (Y~, V~) = (y, R) up to O(ng_jitter), and the
     ELBO equals the exact log marginal likelihood."""

@@ -90,6 +90,27 @@ def test_cuda_cvi_blocks_match_reference_vectors(cuda_device):
             assert abs(float(ell[0]) - float(g[k + "ell"])) <= TOL * abs(float(g[k + "ell"]))
 
 
+def test_cuda_cvi_precision_blocks_match_reference_vectors(cuda_device):
+    """'NG_Precision' site update (physs_cvi_natgrad_step_prec_f64; register kernel D <= 4, lane-group kernel above)
+    against the reference's own theta_precision_to_lambda -> cvi_block_update -> lambda_to_theta_precision
+    (tests/golden/make_golden_prec.py), and the surrogate variance mat_inv(precision)."""
+    from physs_gp_b200 import cvi, likelihood
+
+    def dev(x):
+        return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64).cuda()
+    g = np.load(os.path.join(GOLD, "cvi_blocks_prec.npz"))
+    for D in (1, 2, 3, 4, 6, 8):
+        for tag, ngj in (("1e-7", 1e-7), ("1e-5", 1e-5)):
+            k = "D%d_ngj%s_" % (D, tag)
+            Yn, Pn = cvi.natgrad_step(dev(g[k + "Yt"][None, :, 0]), dev(g[k + "Lam"][None]), dev(g[k + "mq"][None, :, 0]),
+                                      dev(g[k + "S"][None]), None, None, None, float(g[k + "beta"]), ng_jitter=ngj,
+                                      dm=dev(g[k + "dm"][None, :, 0]), dS=dev(g[k + "dS"][None]), precision=True)
+            cond = np.linalg.cond(g[k + "Lam"]) * np.linalg.cond(g[k + "t2"] + ngj * np.eye(D))
+            assert rel(Pn[0], g[k + "t2"]) < TOL and rel(Yn[0], g[k + "t1"][:, 0]) < TOL * max(1.0, cond)
+            var = likelihood.PrecisionBlockDiagonalGaussian(dev(g[k + "Lam"][None])).variance
+            assert rel(var[0], g[k + "var"]) < TOL * max(1.0, np.linalg.cond(g[k + "Lam"]))
+
+
 def test_cuda_cvi_iteration_and_elbo_match_reference_assembly(cuda_device, monkeypatch):
     """One whole CVI iteration and the ELBO through the reference-shaped objects (cvi.VGP.natural_gradient_update
     / .elbo: posterior kernels -> fused site kernel -> ELL kernels) against the reference's OWN
