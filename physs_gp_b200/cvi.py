@@ -627,7 +627,9 @@ class MeanFieldVGP:
             dm_q = dm[..., o:o + k].contiguous()
             dS_q = dS[..., o:o + k, o:o + k].contiguous()
             Yt, Vt = q.Y_tilde.contiguous(), q.V_tilde.contiguous()
-            Yn, Vn = natgrad_step(Yt, Vt, mu_q, cov_q, None, None, None, lr, dm=dm_q, dS=dS_q)
+            # each factor keeps its own parameterisation (cvi_parameterisations.py:14-61)
+            Yn, Vn = natgrad_step(Yt, Vt, mu_q, cov_q, None, None, None, lr, dm=dm_q, dS=dS_q,
+                                  precision=getattr(q, "parameterisation", 'NG_Moment') == 'NG_Precision')
             q.Y_tilde.copy_(Yn)
             q.V_tilde.copy_(Vn)
             o += k
@@ -638,8 +640,10 @@ class MeanFieldVGP:
         out = ell
         for q, mu_q, cov_q, lml in zip(self.q.approx_posteriors, mus, covs, lmls):
             sur = GaussianLik(np.eye(q.block_size))
-            ell_s = expected_log_likelihood(mu_q, cov_q, q.Y_tilde.contiguous(), None, sur,
-                                            noise=q.V_tilde.contiguous())
+            noise = q.V_tilde.contiguous()
+            if getattr(q, "parameterisation", 'NG_Moment') == 'NG_Precision':
+                noise = PrecisionBlockDiagonalGaussian(noise).variance
+            ell_s = expected_log_likelihood(mu_q, cov_q, q.Y_tilde.contiguous(), None, sur, noise=noise)
             out = out - ell_s.sum(dim=-1) + lml           # - KL_q = -(ELL_sur,q - lml_q)   (elbos.py:74-90)
         return out
 

@@ -283,16 +283,23 @@ def test_pendulum_cvi_iterations_match_oracle_and_fit(cuda_device):
     assert float(np.abs(mu[0, :, 0, 0].cpu().numpy() - xs).max()) < 0.3
 
 
-def test_mean_field_cvi_matches_oracle(cuda_device):
+@pytest.mark.parametrize("param", ["NG_Moment", "NG_Precision"])
+def test_mean_field_cvi_matches_oracle(cuda_device, param):
     """MeanFieldConjugateGaussian (cvi_nat_grad.py:89-145, elbos.py:136-160): two latents (Matern-3/2 and
-    Matern-5/2), Poisson counts driven by f_1 + f_2; three iterations and the ELBO against the numpy oracle."""
+    Matern-5/2), Poisson counts driven by f_1 + f_2; three iterations and the ELBO against the numpy oracle, in the
+    moment and in the precision parameterisation of the sites (cvi_parameterisations.py:14-61)."""
+    from oracle import linalg as ola
     from physs_gp_b200 import cvi, sdes
+    prec = param == "NG_Precision"
+    o_step = ocvi.cvi_step_precision if prec else ocvi.cvi_step
+    o_cov = (lambda V: np.stack([np.linalg.inv(v) for v in V])) if prec else (lambda V: V)          # noqa: E731
+    o_var = (lambda V: np.stack([ola.mat_inv(v, 1e-5) for v in V])) if prec else (lambda V: V)      # noqa: E731
     rng = np.random.default_rng(12)
     B, T = 2, 70
     t = synth.time_grid(T, 0.1, rng)
     pri = [sdes.BatchedMaternSDE(2, np.full((B, 1), 0.8), np.full((B, 1), 1.1)),
            sdes.BatchedMaternSDE(3, np.full((B, 1), 0.5), np.full((B, 1), 0.7))]
-    qs = [cvi.FullConjugateGaussian(t, p, 1, B=B) for p in pri]
+    qs = [cvi.FullConjugateGaussian(t, p, 1, B=B, parameterisation=param) for p in pri]
     Y = rng.integers(0, 6, size=(B, T, 1)).astype(float)
     Y[rng.uniform(size=Y.shape) < 0.1] = np.nan
     W = np.array([[1.0, 1.0]])
@@ -308,7 +315,7 @@ def test_mean_field_cvi_matches_oracle(cuda_device):
         Vt = [np.tile(np.eye(1), [T, 1, 1]) for _ in range(2)]
 
         def marg():
-            out = [ofilters.filter_and_smooth(ops_[q], t, Yt[q], Vt[q]) for q in range(2)]
+            out = [ofilters.filter_and_smooth(ops_[q], t, Yt[q], o_cov(Vt[q])) for q in range(2)]
             m = np.concatenate([o[1][:, :, 0] for o in out], -1)           # [T, 2]
             S = np.zeros((T, 2, 2))
             S[:, 0, 0], S[:, 1, 1] = out[0][2][:, 0, 0], out[1][2][:, 0, 0]
@@ -319,11 +326,11 @@ def test_mean_field_cvi_matches_oracle(cuda_device):
             for q in range(2):
                 dm = np.array([x[1][q] for x in g])[:, None]
                 dS = np.array([x[2][q, q] for x in g])[:, None, None]
-                Yt[q], Vt[q] = ocvi.cvi_step(Yt[q], Vt[q], m[:, q:q + 1], S[:, q:q + 1, q:q + 1], dm, dS, beta)
+                Yt[q], Vt[q] = o_step(Yt[q], Vt[q], m[:, q:q + 1], S[:, q:q + 1, q:q + 1], dm, dS, beta)
         out, m, S = marg()
         ref = sum(_oracle_grads("poisson", Y[b, i], W, None, m[i], S[i], 1.0, 20)[0] for i in range(T))
         for q in range(2):
-            ref += -ocvi.surrogate_ell(Yt[q], Vt[q], m[:, q:q + 1], S[:, q:q + 1, q:q + 1]) + out[q][0]
+            ref += -ocvi.surrogate_ell(Yt[q], o_var(Vt[q]), m[:, q:q + 1], S[:, q:q + 1, q:q + 1]) + out[q][0]
             assert rel(qs[q].Y_tilde[b], Yt[q]) < TOL and rel(qs[q].V_tilde[b], Vt[q]) < TOL
         assert abs(float(elbo[b]) - ref) < TOL * abs(ref)
 
