@@ -121,6 +121,19 @@ def spatial_sparsity_gaussian_ell_and_grads(Y, s2, W, c0_diag, jitter, q_mu, q_v
     return ell, dm, dS
 
 
+def spatial_sparsity_gh_ell_and_grads(Y, kind, W, c0_diag, jitter, q_mu, q_var, K=20, binsize=1.0):
+    """The same pull-back for independent non-Gaussian observations at the N data locations (Poisson exp-link /
+    Bernoulli probit): per point the K-point Gauss-Hermite E[l], E[l'], 1/2 E[l''] under N(m_x,i, v_x,i), then
+    dELL/dq_mu = W^T E[l'],  dELL/dq_var = W^T diag(1/2 E[l'']) W   (chain rule through m_x = W q_mu and
+    v_x = c0 + diag(W (q_var + jitter I) W^T); what jax.grad of the reference's ELL gives, cvi_nat_grad.py:381-383)."""
+    M = q_mu.shape[0]
+    m_x = W @ q_mu
+    v_x = c0_diag + np.einsum("ij,jk,ik->i", W, q_var + jitter * np.eye(M), W)
+    g = [gh_ell_and_grads(Y[i], m_x[i], v_x[i], kind, K, binsize) for i in range(Y.shape[0])]
+    e0, e1, e2 = (np.array([x[j] for x in g]) for j in range(3))
+    return float(e0.sum()), W.T @ e1, (W.T * e2) @ W
+
+
 def log_poisson(y, f, binsize=1.0):
     """general.py:9-11 with likelihood/poisson.py:20-22 (exp link)."""
     lam = np.exp(f) * binsize

@@ -113,9 +113,14 @@ class SpatialSparsityVGP:
         dELL/dm_z = W^T (y - m_x) / s2,   dELL/dS_z = W^T diag(-1 / (2 s2)) W      (the same kernel with the roles of
                                                                                     Z and X exchanged)
     followed by the ordinary block update (physs_cvi_natgrad_big_f64 or physs_cvi_natgrad_step_f64, gradients supplied).
+    With `likelihood` = cvi.PoissonLik / cvi.BernoulliLik (independent non-Gaussian observations at X) the per-point
+    terms E[l(f_i)], E[l'(f_i)], 1/2 E[l''(f_i)] under f_i ~ N(m_x,i, v_x,i) come from the Gauss-Hermite site kernel
+    (physs_cvi_ell_f64 on N scalar blocks per step) and are pulled back the same way:
+        dELL/dm_z = W^T E[l'],   dELL/dS_z = W^T diag(1/2 E[l'']) W.
     Y [T, N] (NaN = missing); approximate_posterior: cvi.FullConjugateGaussian with block_size M and B = 1."""
 
-    def __init__(self, Y, noise_var, approximate_posterior, Kzz, Kxz, Kxx, Ktt=1.0, jitter=None):
+    def __init__(self, Y, noise_var, approximate_posterior, Kzz, Kxz, Kxx, Ktt=1.0, jitter=None, likelihood=None,
+                 ell_quad_points=20):
         q = approximate_posterior
         dev = q.Y_tilde.device
         self.q = q
@@ -129,12 +134,27 @@ class SpatialSparsityVGP:
         self.C0 = torch.as_tensor(C0 * float(Ktt), device=dev)
         self.zero_MM = torch.zeros((self.M, self.M), dtype=torch.float64, device=dev)
         self.Y = torch.as_tensor(np.asarray(Y, np.float64), device=dev).reshape(-1, self.N)
-        self.noise_var = float(noise_var)
+        self.noise_var = None if noise_var is None else float(noise_var)
+        self.lik = likelihood                  # None: Gaussian with variance noise_var
+        self.K = ell_quad_points
+        if (self.lik is None) == (self.noise_var is None):
+            raise ValueError("SpatialSparsityVGP: give noise_var (Gaussian) or likelihood (Poisson / Bernoulli), not both")
 
     def _ell(self, q_mu, q_var, want_grads):
         """q_mu [T, M], q_var [T, M, M] -> ELL per step [T] (and the gradients w.r.t. the block moments)."""
         m_x, v_x = _apply(self.W, self.C0, None, q_mu, q_var, self.jitter, True)
         m_x, v_x = m_x[..., 0], v_x[..., 0]
+        if self.lik is not None:
+            from . import cvi
+            out = cvi.expected_log_likelihood(m_x[..., None].contiguous(), v_x[..., None, None].contiguous(),
+                                              self.Y[..., None].contiguous(), None, self.lik, K=self.K,
+                                              want_grads=want_grads)
+            if not want_grads:
+                return out.sum(-1)
+            ell, dm_x, dS_x = out
+            dm_z, dS_z = _apply(self.Wt, self.zero_MM, None, dm_x[..., 0].contiguous(),
+                                torch.diag_embed(dS_x[..., 0, 0]).contiguous(), 0.0, False)
+            return ell.sum(-1), dm_z[..., 0], dS_z[:, 0]
         s2 = self.noise_var
         obs = ~torch.isnan(self.Y)
         r = torch.where(obs, self.Y, torch.zeros_like(self.Y)) - m_x
@@ -154,7 +174,8 @@ class SpatialSparsityVGP:
 
     def natural_gradient_update(self, lr, enforce_psd_type=None, prediction_samples=None):
         if enforce_psd_type is not None:
-            raise NotImplementedError("enforce_psd_type: the Gaussian ELL curvature is already negative semi-definite")
+            raise NotImplementedError("enforce_psd_type: the Gaussian ELL curvature is already negative semi-definite; "
+                                      "log-concave Poisson / Bernoulli sites give a negative semi-definite W^T diag W too")
         from . import cvi
         q = self.q
         _, q_mu, q_var = self._posterior()

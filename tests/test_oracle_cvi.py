@@ -220,3 +220,33 @@ def test_spatial_sparsity_ell_gradients_by_finite_differences():
     ell1, dm1, dS1 = ocvi.spatial_sparsity_gaussian_ell_and_grads(y[:M], 0.3, np.eye(M), np.zeros(M), 0.0, qm, qS)
     ell0, dm0, dS0 = ocvi.gaussian_ell_and_grads(y[:M], 0.3 * np.eye(M), None, qm, qS)
     assert abs(ell1 - ell0) < 1e-12 * abs(ell0) and np.allclose(dm1, dm0, atol=1e-13) and np.allclose(dS1, dS0, atol=1e-13)
+
+
+def test_spatial_sparsity_non_gaussian_ell_gradients_by_finite_differences():
+    """oracle.cvi.spatial_sparsity_gh_ell_and_grads (Poisson / Bernoulli observations away from the inducing points):
+    W^T E[l'] and W^T diag(1/2 E[l'']) W equal central differences of a 60-point quadrature of the ELL w.r.t. every
+    entry of (q_mu, q_var) -- what `jax.grad(partial_ell, (1, 2))` returns (cvi_nat_grad.py:381-383).  (Bonnet / Price:
+    dE[l]/dm = E[l'], dE[l]/dv = 1/2 E[l'']; a high-order rule makes the quadrature error of both sides negligible.)"""
+    import numpy as np
+    from oracle import cvi as ocvi
+    rng = np.random.default_rng(4)
+    M, N, K = 4, 7, 60
+    W = 0.5 * rng.normal(size=(N, M))
+    c0 = rng.uniform(0.05, 0.2, N)
+    qm = 0.3 * rng.normal(size=M)
+    B = 0.3 * rng.normal(size=(M, M))
+    qS = B @ B.T + 0.2 * np.eye(M)
+    for kind in ("poisson", "bernoulli"):
+        y = (rng.integers(0, 4, N) if kind == "poisson" else rng.integers(0, 2, N)).astype(float)
+        y[2] = np.nan
+        f = lambda m, S: ocvi.spatial_sparsity_gh_ell_and_grads(y, kind, W, c0, 1e-5, m, S, K=K)[0]     # noqa: E731
+        ell, dm, dS = ocvi.spatial_sparsity_gh_ell_and_grads(y, kind, W, c0, 1e-5, qm, qS, K=K)
+        h = 1e-5
+        for i in range(M):
+            e = np.zeros(M); e[i] = h
+            fd = (f(qm + e, qS) - f(qm - e, qS)) / (2 * h)
+            assert abs(fd - dm[i]) < 1e-6 * max(1.0, abs(dm[i])), (kind, i)
+            for j in range(M):
+                E = np.zeros((M, M)); E[i, j] = h
+                fd = (f(qm, qS + E) - f(qm, qS - E)) / (2 * h)
+                assert abs(fd - dS[i, j]) < 1e-6 * max(1.0, abs(dS[i, j])), (kind, i, j)
