@@ -71,3 +71,38 @@ def test_R_predict_on_the_merged_grid():
                 np.testing.assert_array_equal(R[k], np.eye(m))
     # the test rows are found again through the inverse index
     assert list(np.concatenate([t, ts])[ui][ri.reshape(-1)[Nt:]]) == list(ts)
+
+
+def test_get_R_R_inv_follows_the_likelihood_class():
+    """sde_gp.py:30-43: a PrecisionBlockDiagonalGaussian hands (None, precision) to filter_loop, every other Gaussian
+    container (variance, None)."""
+    import numpy as np
+    from physs_gp_b200 import likelihood
+    P = np.tile(2.0 * np.eye(3), [5, 1, 1])
+    R, R_inv = likelihood.get_R_R_inv(likelihood.PrecisionBlockDiagonalGaussian(P), 5, 3)
+    assert R is None and R_inv is P
+    R, R_inv = likelihood.get_R_R_inv(likelihood.BlockDiagonalGaussian(P), 5, 3)
+    assert R is P and R_inv is None
+    R, R_inv = likelihood.get_R_R_inv(likelihood.Gaussian(0.3), 5, 2)
+    assert R_inv is None and R.shape == (1, 2, 2) and R[0, 1, 1] == 0.3
+
+
+def test_packed_route_declines_without_touching_the_gpu():
+    """filters.filter_smooth_fused returns None -- the caller then takes filter_loop + smoother_loop -- for everything the
+    packed call does not cover, and decides that before any device work: precision sites, collocation priors, state
+    dims above 4, the switch settings.fused_packed."""
+    import numpy as np
+    from physs_gp_b200 import data, filters, sdes, settings
+    t = np.linspace(0.0, 1.0, 20)
+    Y = np.zeros((40, 20, 1, 1))
+    d = data.TemporalData(t, Y)
+    big = sdes.BatchedMaternSDE(4, np.ones((40, 2)))                     # state dim 8
+    assert filters.filter_smooth_fused(d, big, R=np.eye(1)[None]) is None
+    small = sdes.BatchedMaternSDE(4, np.ones((40, 1)))
+    assert filters.filter_smooth_fused(d, small, R=None, R_inv=np.eye(1)[None]) is None
+    old = settings.fused_packed
+    settings.fused_packed = False
+    try:
+        assert filters.filter_smooth_fused(d, small, R=np.eye(1)[None]) is None
+    finally:
+        settings.fused_packed = old
