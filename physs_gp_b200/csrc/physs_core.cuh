@@ -35,8 +35,9 @@ constexpr double kLn2 = 0.69314718055994530941723212145818;
 PHYSS_HD double fast_rcp(double x) {
 #if defined(__CUDA_ARCH__)
   double r;
+  // hardware seed (MUFU.RCP64H: ~2^-20 relative) + two Newton steps: 2^-40, then rounding-limited (a third step, kept
+  // until the end of round 2, changed nothing but the length of the dependency chain)
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  r = fma(r, fma(-x, r, 1.0), r);
   r = fma(r, fma(-x, r, 1.0), r);
   r = fma(r, fma(-x, r, 1.0), r);
   return r;
@@ -50,7 +51,6 @@ PHYSS_HD double fast_rsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   const double hx = 0.5 * x;
-  y = fma(y, fma(-hx * y, y, 0.5), y);
   y = fma(y, fma(-hx * y, y, 0.5), y);
   y = fma(y, fma(-hx * y, y, 0.5), y);
   return y;

@@ -371,3 +371,15 @@ def test_precision_sites_match_covariance_sites(cuda_device):
     assert rel(kf_b['m'], kf_a['m'].cpu().numpy()) < 1e-10 and rel(kf_b['P'], kf_a['P'].cpu().numpy()) < 1e-10
     lml_o, mf_o, Pf_o, _ = ofilters.filter_sequential(oprior, t, Y, R, 1e-5)
     assert rel(kf_b['m'], mf_o) < TOL and rel(kf_b['P'], Pf_o) < TOL
+
+
+def test_reciprocal_primitives_are_ulp_accurate(cuda_device):
+    """fast_rcp / fast_rsqrt (physs_core.cuh: hardware seed + two Newton steps) through the 1 x 1 case of
+    physs_spd_inverse_f64, (a)^-1 = (1 * rsqrt(a)) * rsqrt(a): a few ulp over twelve decades -- a seed worse than
+    2^-14 (or a missing Newton step) would show up here long before the 1e-9 parity tolerance notices."""
+    from physs_gp_b200 import ops
+    rng = np.random.default_rng(0)
+    a = np.exp(rng.uniform(np.log(1e-6), np.log(1e6), 200000))
+    inv = ops.spd_inverse(torch.as_tensor(a, device=cuda_device).reshape(-1, 1, 1), 0.0).reshape(-1).cpu().numpy()
+    err = np.abs(inv * a - 1.0).max()
+    assert err < 1e-15, err
