@@ -298,9 +298,12 @@ __device__ __forceinline__ bool agrees(const double (&m)[D], const double (&P)[D
   return (dP <= delta * sP) && (dm <= delta * sm || dm * dm <= delta * delta * sP);
 }
 
-template <int D, int S, int M, bool HID, int GIVEN, bool CHUNK>
+// PACK (plain mode, time-major steps, D <= 4): the filtered moments go out as packed rows [m | triu(P)] (SeqFilterArgs::pk)
+// instead of (mf, Pf).  A template argument, not a run-time branch: the branch cost the unpacked kernel 14 % of its
+// cycles (12.5 -> 13.5 ms per 32,768 x 10k; measured at the end of round 2).
+template <int D, int S, int M, bool HID, int GIVEN, bool CHUNK, bool PACK = false>
 __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const SeqFilterArgs p) {
-  __shared__ __align__(16) double tiles[SeqBlock<D>::WARPS][SeqTile<D>::SIZE];
+  __shared__ __align__(16) double tiles[SeqBlock<D>::WARPS][PACK ? SeqTile<D>::SIZE : RowTile<D * D>::SIZE];
   SeqWork wk;
   if (!seq_work<CHUNK>(p, wk)) return;
   if (CHUNK && p.fixup && p.prev_changed && *p.prev_changed == 0) return;   // the previous pass was a fixed point
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(SeqBlock<D>::THREADS) seq_filter_kernel(const 
       if (streak == 0 && active && p.pass_changed) atomicOr(p.pass_changed, 1);
     }
     if (k < 0) continue;                                   // warm-up step: nothing is stored
-    if (!CHUNK && D <= 4 && coal && p.pk) {
+    if constexpr (PACK) {
       // packed hand-over to the smoother of the same call: one row [m | triu(P)] per series-step
       constexpr int NP = PackedRow<D>::N;
       double row[NP];
@@ -1056,6 +1059,16 @@ static int launch_filter(cudaStream_t st, const SeqFilterArgs& a) {
   const int64_t n = ((a.B + 31) / 32 * 32) * (a.nchunk > 0 ? a.chunk_count : 1);
   const int block = pick_block(n) < SeqBlock<D>::THREADS ? pick_block(n) : SeqBlock<D>::THREADS;
   const int64_t grid = (n + block - 1) / block;
+  if (a.pk) {
+    if constexpr (D <= 4) {
+      if (a.nchunk > 0 || a.sbs != 1)
+        return set_error(PHYSS_ERR_UNSUPPORTED, "packed hand-over: time-major steps, plain mode");
+      seq_filter_kernel<D, S, M, HID, GIVEN, false, true><<<(unsigned)grid, block, 0, st>>>(a);
+      return cuda_status(cudaGetLastError(), "seq_filter_kernel (packed) launch");
+    } else {
+      return set_error(PHYSS_ERR_UNSUPPORTED, "packed hand-over: d <= 4");
+    }
+  }
   if (a.nchunk > 0)
     seq_filter_kernel<D, S, M, HID, GIVEN, true><<<(unsigned)grid, block, 0, st>>>(a);
   else
